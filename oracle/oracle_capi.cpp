@@ -1,0 +1,198 @@
+// ORACLE — test infrastructure only (see oracle.hpp).  C entry points for the
+// ctypes harness in tests/ and bench.py's cpu_baseline / --impl reference legs.
+// 4x4 transforms cross this boundary as 16 floats in Eigen's column-major order.
+#include <omp.h>
+
+#include <cstring>
+#include <string>
+
+#include "../delta_graph_slam_b200/synth/synth_scene.h"
+#include "oracle.hpp"
+
+using namespace orc;
+
+namespace {
+struct Handle {
+  int method;  // 0 NDT, 1 FAST_GICP
+  NDT ndt;
+  FastGICP gicp;
+  Cloud aligned;
+  Registration& reg() { return method == 0 ? (Registration&)ndt : (Registration&)gicp; }
+};
+M4f from_colmajor(const float* c) {
+  M4f m;
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 4; ++k) m(r, k) = c[4 * k + r];
+  return m;
+}
+void to_colmajor(const M4f& m, float* c) {
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 4; ++k) c[4 * k + r] = m(r, k);
+}
+}  // namespace
+
+extern "C" {
+
+int orc_max_threads() { return omp_get_max_threads(); }
+
+long long orc_voxelgrid(const float* in, long long n, float lx, float ly, float lz, unsigned min_pts, int is_dense, float* out, unsigned* voxel_id, unsigned* count, unsigned* key, int* grid6, int* overflow) {
+  VoxelGridResult r = voxelgrid_filter((const Pt*)in, (size_t)n, lx, ly, lz, min_pts, is_dense != 0);
+  if (out && !r.out.empty()) std::memcpy(out, r.out.data(), r.out.size() * sizeof(Pt));
+  if (voxel_id && !r.voxel_id.empty()) std::memcpy(voxel_id, r.voxel_id.data(), r.voxel_id.size() * 4);
+  if (count && !r.count.empty()) std::memcpy(count, r.count.data(), r.count.size() * 4);
+  if (key && n) std::memcpy(key, r.key.data(), (size_t)n * 4);
+  if (grid6) {
+    for (int a = 0; a < 3; ++a) { grid6[a] = r.min_b[a]; grid6[3 + a] = r.div_b[a]; }
+  }
+  if (overflow) *overflow = r.overflow ? 1 : 0;
+  return (long long)r.out.size();
+}
+
+void* orc_reg_create(int method) {
+  Handle* h = new Handle();
+  h->method = method;
+  return h;
+}
+void orc_reg_destroy(void* hv) { delete (Handle*)hv; }
+
+int orc_reg_set(void* hv, const char* name, double v) {
+  Handle* h = (Handle*)hv;
+  std::string s(name);
+  if (s == "num_threads") { h->ndt.setNumThreads((int)v); h->gicp.setNumThreads((int)v); }
+  else if (s == "trans_eps") { h->reg().setTransformationEpsilon(v); }
+  else if (s == "max_iter") { h->reg().setMaximumIterations((int)v); }
+  else if (s == "resolution") { h->ndt.setResolution((float)v); }
+  else if (s == "nn_search") { h->ndt.setNeighborhoodSearchMethod((NeighborSearchMethod)(int)v); }
+  else if (s == "step_size") { h->ndt.setStepSize(v); }
+  else if (s == "outlier_ratio") { h->ndt.setOutlierRatio(v); }
+  else if (s == "max_corr_dist") { h->gicp.setMaxCorrespondenceDistance(v); }
+  else if (s == "k_corr") { h->gicp.setCorrespondenceRandomness((int)v); }
+  else if (s == "regularization") { h->gicp.setRegularizationMethod((RegularizationMethod)(int)v); }
+  else if (s == "rot_eps") { h->gicp.setRotationEpsilon(v); }
+  else if (s == "lsq") { h->gicp.setLsqOptimizer((LsqOptimizer)(int)v); }
+  else return -1;
+  return 0;
+}
+
+void orc_reg_set_target(void* hv, const float* xyzw, long long n) { ((Handle*)hv)->reg().setInputTarget((const Pt*)xyzw, (size_t)n); }
+void orc_reg_set_source(void* hv, const float* xyzw, long long n) { ((Handle*)hv)->reg().setInputSource((const Pt*)xyzw, (size_t)n); }
+
+int orc_reg_align(void* hv, const float* guess_colmajor, float* aligned_out) {
+  Handle* h = (Handle*)hv;
+  h->reg().align(h->aligned, from_colmajor(guess_colmajor));
+  if (aligned_out && !h->aligned.empty()) std::memcpy(aligned_out, h->aligned.data(), h->aligned.size() * sizeof(Pt));
+  return h->reg().hasConverged() ? 1 : 0;
+}
+
+// info: [0] transformation probability (NDT), [1] derivative passes, [2] (point,voxel) hits;
+// GICP: [1] linearize calls, [2] compute_error calls
+void orc_reg_get_result(void* hv, float* T_colmajor, int* converged, int* iterations, double* info3) {
+  Handle* h = (Handle*)hv;
+  to_colmajor(h->reg().getFinalTransformation(), T_colmajor);
+  if (converged) *converged = h->reg().hasConverged() ? 1 : 0;
+  if (iterations) *iterations = h->reg().getFinalNumIteration();
+  if (info3) {
+    if (h->method == 0) {
+      info3[0] = h->ndt.getTransformationProbability(); info3[1] = (double)h->ndt.n_eval; info3[2] = (double)h->ndt.n_hits;
+    } else {
+      info3[0] = 0.0; info3[1] = (double)h->gicp.n_linearize; info3[2] = (double)h->gicp.n_error;
+    }
+  }
+}
+
+double orc_reg_fitness(void* hv, double max_range) { return ((Handle*)hv)->reg().getFitnessScore(max_range); }
+double orc_reg_inlier_fraction(void* hv, const float* aligned, long long n, double max_dist) {
+  Cloud c((const Pt*)aligned, (const Pt*)aligned + n);
+  return ((Handle*)hv)->reg().inlierFraction(c, max_dist);
+}
+
+// ---- NDT introspection -----------------------------------------------------
+long long orc_ndt_num_leaves(void* hv) { return (long long)((Handle*)hv)->ndt.cells().leaves().size(); }
+void orc_ndt_grid(void* hv, int* min_b3, int* div_b3) {
+  const VoxelGridCovariance& c = ((Handle*)hv)->ndt.cells();
+  for (int a = 0; a < 3; ++a) { min_b3[a] = c.min_b_[a]; div_b3[a] = c.div_b_[a]; }
+}
+void orc_ndt_get_leaves(void* hv, unsigned long long* idx, int* npts, double* mean3, double* cov9, double* icov9, float* centroid3) {
+  long long k = 0;
+  for (auto& kv : ((Handle*)hv)->ndt.cells().leaves()) {
+    const Leaf& l = kv.second;
+    idx[k] = kv.first;
+    npts[k] = l.nr_points;
+    for (int a = 0; a < 3; ++a) { mean3[3 * k + a] = l.mean[a]; centroid3[3 * k + a] = l.centroid[a]; }
+    for (int a = 0; a < 9; ++a) { cov9[9 * k + a] = l.cov.m[a]; icov9[9 * k + a] = l.icov.m[a]; }
+    ++k;
+  }
+}
+double orc_ndt_derivatives(void* hv, const double* p6, double* g6, double* H36, int compute_hessian) {
+  return ((Handle*)hv)->ndt.derivativesAt(p6, g6, H36, compute_hessian != 0);
+}
+
+// ---- GICP introspection ----------------------------------------------------
+void orc_gicp_covariances(void* hv, int which, double* out9) {
+  Handle* h = (Handle*)hv;
+  const std::vector<M3>& c = which == 0 ? h->gicp.sourceCovariances() : h->gicp.targetCovariances();
+  for (size_t i = 0; i < c.size(); ++i) std::memcpy(out9 + 9 * i, c[i].m, 9 * sizeof(double));
+}
+
+// ---- search ----------------------------------------------------------------
+void orc_knn(const float* pts, long long n, const float* queries, long long m, int k, int* idx, float* d2) {
+  KdTree t;
+  t.build(pts, (size_t)n);
+#pragma omp parallel for schedule(guided, 64)
+  for (long long i = 0; i < m; ++i) {
+    int found = t.knn(queries + 4 * i, k, idx + (size_t)k * i, d2 + (size_t)k * i);
+    for (int j = found; j < k; ++j) { idx[(size_t)k * i + j] = -1; d2[(size_t)k * i + j] = 3.402823466e+38f; }
+  }
+}
+
+// ---- linear algebra known-answer hooks -------------------------------------
+void orc_sym_eigen3(const double* a9, double* evals3, double* evecs9) {
+  M3 a, v;
+  std::memcpy(a.m, a9, sizeof a.m);
+  m3_sym_eigen(a, evals3, v);
+  std::memcpy(evecs9, v.m, sizeof v.m);
+}
+void orc_inverse3(const double* a9, double* out9) {
+  M3 a;
+  std::memcpy(a.m, a9, sizeof a.m);
+  M3 r = m3_inverse(a);
+  std::memcpy(out9, r.m, sizeof r.m);
+}
+void orc_svd_solve6(const double* A36, const double* b6, double* x6) {
+  M6 A; V6 b;
+  std::memcpy(A.m, A36, sizeof A.m);
+  std::memcpy(b.v, b6, sizeof b.v);
+  V6 x = m6_svd_solve(A, b);
+  std::memcpy(x6, x.v, sizeof x.v);
+}
+void orc_ldlt_solve6(const double* A36, const double* b6, double* x6) {
+  M6 A; V6 b;
+  std::memcpy(A.m, A36, sizeof A.m);
+  std::memcpy(b.v, b6, sizeof b.v);
+  V6 x = m6_ldlt_solve(A, b);
+  std::memcpy(x6, x.v, sizeof x.v);
+}
+void orc_euler_xyz(const float* T_colmajor, float* out3) { m4f_euler_xyz(from_colmajor(T_colmajor), out3); }
+void orc_transform_from_p(const double* p6, float* T_colmajor) { to_colmajor(m4f_from_xyz_euler(p6), T_colmajor); }
+
+// ---- synthetic scans (CPU build of delta_graph_slam_b200/synth/synth_scene.h) ---
+long long orc_synth_scan(int sensor, unsigned long long scene_seed, unsigned long long noise_seed, const double* pose_rowmajor, float* out_xyzw) {
+  synth::Sensor s = sensor == 0 ? synth::sensor_hdl64() : synth::sensor_dense128();
+  const long rays = (long)s.beams * s.azimuth_steps;
+  std::vector<unsigned char> ok(rays);
+  std::vector<float> tmp((size_t)rays * 4);
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (long r = 0; r < rays; ++r) ok[r] = synth::scan_ray(s, scene_seed, noise_seed, pose_rowmajor, r, &tmp[4 * (size_t)r]) ? 1 : 0;
+  long long n = 0;
+  for (long r = 0; r < rays; ++r)
+    if (ok[r]) { std::memcpy(out_xyzw + 4 * n, &tmp[4 * (size_t)r], 16); ++n; }
+  return n;
+}
+long long orc_synth_num_rays(int sensor) {
+  synth::Sensor s = sensor == 0 ? synth::sensor_hdl64() : synth::sensor_dense128();
+  return (long long)s.beams * s.azimuth_steps;
+}
+void orc_synth_traj(long long k, unsigned long long seed, double* T_rowmajor) { synth::traj_kitti_like((long)k, seed, T_rowmajor); }
+void orc_synth_pose(const double* xyzrpy, double* T_rowmajor) { synth::pose_from_xyzrpy(xyzrpy, T_rowmajor); }
+
+}  // extern "C"
