@@ -1,0 +1,603 @@
+// b200reg — C ABI implementation (include/b200reg.h).  Host side is plain C++; the device work is
+// the hand-written sm_100a kernels in the .cuh files next to this one.  There is no CPU
+// fallback anywhere: a missing device or a CUDA error surfaces as B200REG_E_CUDA.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200reg.h"
+#include "ndt_align.cuh"
+#include "nn_grid.cuh"
+#include "voxelgrid.cuh"
+
+using namespace b200;
+
+struct b200reg_handle {
+  b200reg_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int num_sm = kNumSM;
+
+  // clouds (device, float4)
+  DevBuf<float4> src, tgt, stage_in, stage_out, aligned;
+  PinnedBuf<float4> pin_in, pin_out;
+  int n_src = 0, n_tgt = 0;
+  bool have_src = false, have_tgt = false;
+
+  // VoxelGrid filter
+  VoxelSort vg_sort;
+  DevBuf<uint32_t> vg_id, vg_count;
+  DevBuf<VgCounts> vg_counts;
+  int vg_last_n = 0, vg_last_out = 0;
+
+  // NDT
+  NdtGrid grid;
+  bool grid_stale = true;  // resolution changed since the grid was built
+  DevBuf<NdtJob> jobs;
+  DevBuf<b200reg_result> d_result;
+  DevBuf<double> partials, deriv;
+  DevBuf<unsigned int> barriers;
+  PinnedBuf<unsigned char> pin_small;  // results / jobs staging
+
+  // exact-NN structure on the target (fitness, inlier fraction, GICP)
+  NnGrid nn;
+  bool nn_stale = true;
+  DevBuf<double> fit_partials;
+
+  b200reg_result last;
+  bool have_result = false;
+
+  void set_error(const std::string& s) { err = s; }
+};
+
+namespace {
+
+const char* kVersion = "b200reg 0.1 (sm_100a)";
+
+int set_device(b200reg_handle* h) {
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) {
+    h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return B200REG_E_CUDA;
+  }
+  return B200REG_OK;
+}
+
+// host cloud (any stride) -> device float4 buffer on the handle's stream
+int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, DevBuf<float4>& dst) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) {
+    h->err = "stride_bytes must be a multiple of 4 and at least 12";
+    return B200REG_E_INVALID;
+  }
+  B200_CUDA_TRY(dst.reserve(n ? n : 1));
+  if (!n) return B200REG_OK;
+  B200_CUDA_TRY(h->pin_in.reserve(n));
+  if (stride_bytes == 16) {
+    memcpy(h->pin_in.p, xyzw, n * 16);
+  } else {
+    const unsigned char* b = (const unsigned char*)xyzw;
+    for (size_t i = 0; i < n; ++i) {
+      const float* p = (const float*)(b + i * stride_bytes);
+      h->pin_in.p[i] = make_float4(p[0], p[1], p[2], 1.0f);
+    }
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(dst.p, h->pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
+  // the pinned staging buffer is reused by the next upload
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return B200REG_OK;
+}
+
+// Eigen 3.3 Matrix3f::eulerAngles(0,1,2) of the rotation block; host libm floats
+void euler_xyz_from_colmajor(const float* T, float out[3]) {
+  auto M = [&](int r, int c) { return T[4 * c + r]; };
+  const float pi = 3.14159265358979323846f;
+  float r0 = atan2f(M(1, 2), M(2, 2));
+  float c2 = sqrtf(M(0, 0) * M(0, 0) + M(0, 1) * M(0, 1));
+  float r1;
+  if (r0 > 0.f) {
+    r0 -= pi;
+    r1 = atan2f(-M(0, 2), -c2);
+  } else {
+    r1 = atan2f(-M(0, 2), c2);
+  }
+  float s1 = sinf(r0), c1 = cosf(r0);
+  float r2 = atan2f(s1 * M(2, 0) - c1 * M(1, 0), c1 * M(1, 1) - s1 * M(2, 1));
+  out[0] = -r0; out[1] = -r1; out[2] = -r2;
+}
+
+__global__ void k_transform_cloud(const float4* __restrict__ in, int n, const b200reg_result* __restrict__ res, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* T = res->transformation;  // column-major
+  const float4 p = in[i];
+  out[i] = make_float4(affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z), affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z),
+                       affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z), 1.0f);
+}
+
+int ensure_ndt_grid(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h->grid_stale && h->grid.built) return B200REG_OK;
+  B200_CUDA_TRY(h->grid.build(h->stream, h->tgt.p, h->n_tgt, (float)h->cfg.resolution));
+  h->grid_stale = false;
+  return B200REG_OK;
+}
+
+int ensure_nn_grid(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h->nn_stale && h->nn.built) return B200REG_OK;
+  B200_CUDA_TRY(h->nn.build(h->stream, h->tgt.p, h->n_tgt));
+  h->nn_stale = false;
+  return B200REG_OK;
+}
+
+template <int MODE>
+cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups) {
+  NdtParams prm;
+  prm.search = h->cfg.nn_search;
+  prm.resolution = h->cfg.resolution;
+  prm.step_size = h->cfg.step_size;
+  prm.outlier_ratio = h->cfg.outlier_ratio;
+  prm.trans_eps = h->cfg.transformation_epsilon;
+  prm.max_iterations = h->cfg.maximum_iterations;
+  const NdtJob* jobs = h->jobs.p;
+  double* partials = h->partials.p;
+  unsigned int* barriers = h->barriers.p;
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers};
+  return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, 0, h->stream);
+}
+
+cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups) {
+  switch (h->cfg.nn_search) {
+    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups);
+    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups);
+    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups);
+    default: return launch_ndt<7>(h, n_jobs, G, n_groups);
+  }
+}
+
+// one NDT job on the whole GPU; result lands in h->d_result[0]
+int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double* p_eval) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  int rc = ensure_ndt_grid(h);
+  if (rc) return rc;
+  const int G = h->num_sm;
+  B200_CUDA_TRY(h->jobs.reserve(1));
+  B200_CUDA_TRY(h->d_result.reserve(1));
+  B200_CUDA_TRY(h->deriv.reserve(64));
+  B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
+  B200_CUDA_TRY(h->barriers.reserve(32));
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
+  NdtJob* job = reinterpret_cast<NdtJob*>(h->pin_small.p);
+  memset(job, 0, sizeof(NdtJob));
+  job->src = h->src.p;
+  job->n_src = h->n_src;
+  job->grid = h->grid.view();
+  job->result = h->d_result.p;
+  job->deriv_out = h->deriv.p;
+  if (p_eval) {
+    job->eval_only = 1;
+    for (int i = 0; i < 6; ++i) job->p0[i] = p_eval[i];
+  } else {
+    float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const float* g = guess_colmajor ? guess_colmajor : I;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) job->guess[4 * r + c] = g[4 * c + r];
+    float eul[3];
+    euler_xyz_from_colmajor(g, eul);
+    job->p0[0] = g[12]; job->p0[1] = g[13]; job->p0[2] = g[14];
+    job->p0[3] = eul[0]; job->p0[4] = eul[1]; job->p0[5] = eul[2];
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, job, sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 32 * sizeof(unsigned int), h->stream));
+  B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1));
+  return B200REG_OK;
+}
+
+int fetch_result(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  b200reg_result* pr = reinterpret_cast<b200reg_result*>(h->pin_small.p + sizeof(NdtJob));
+  B200_CUDA_TRY(cudaMemcpyAsync(pr, h->d_result.p, sizeof(b200reg_result), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->last = *pr;
+  h->have_result = true;
+  return B200REG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200reg_version(void) { return kVersion; }
+
+void b200reg_default_config(int method, b200reg_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->device = 0;
+  c->method = method;
+  // defaults of select_registration_method [REF src/hdl_graph_slam/registrations.cpp:26-119]
+  c->resolution = 0.5;                  // reg_resolution (NDT branch)
+  c->nn_search = B200REG_DIRECT7;       // reg_nn_search_method
+  c->transformation_epsilon = 0.01;     // reg_transformation_epsilon
+  c->maximum_iterations = 64;           // reg_maximum_iterations
+  c->step_size = 0.1;                   // pclomp default, never set by the reference
+  c->outlier_ratio = 0.55;              // pclomp default
+  c->max_correspondence_distance = 2.5; // reg_max_correspondence_distance
+  c->correspondence_randomness = 20;    // reg_correspondence_randomness
+  c->rotation_epsilon = 2e-3;           // fast_gicp default
+  c->regularization = B200REG_REG_PLANE;
+  c->lsq_optimizer = B200REG_LSQ_LM;
+  c->num_threads = 0;
+}
+
+int b200reg_create(const b200reg_config* cfg, b200reg_handle** out) {
+  if (!cfg || !out) return B200REG_E_INVALID;
+  *out = nullptr;
+  if (cfg->method < B200REG_METHOD_NONE || cfg->method > B200REG_METHOD_GICP) return B200REG_E_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || cfg->device < 0 || cfg->device >= count) return B200REG_E_CUDA;
+  b200reg_handle* h = new (std::nothrow) b200reg_handle();
+  if (!h) return B200REG_E_INVALID;
+  h->cfg = *cfg;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return B200REG_E_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return B200REG_E_CUDA; }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+  if (prop.major < 10 || !coop) { delete h; return B200REG_E_CUDA; }  // sm_100a only
+  h->num_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return B200REG_E_CUDA; }
+  *out = h;
+  return B200REG_OK;
+}
+
+int b200reg_destroy(b200reg_handle* h) {
+  if (!h) return B200REG_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
+  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release();
+  h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release();
+  h->nn.release(); h->fit_partials.release();
+  delete h;
+  return B200REG_OK;
+}
+
+const char* b200reg_last_error(const b200reg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200reg_set_resolution(b200reg_handle* h, double r) {
+  if (!h || !(r > 0)) return B200REG_E_INVALID;
+  if ((float)r != (float)h->cfg.resolution) h->grid_stale = true;  // pclomp::setResolution re-inits the grid
+  h->cfg.resolution = r;
+  return B200REG_OK;
+}
+int b200reg_set_nn_search(b200reg_handle* h, int m) {
+  if (!h || m < B200REG_KDTREE || m > B200REG_DIRECT1) return B200REG_E_INVALID;
+  h->cfg.nn_search = m;
+  return B200REG_OK;
+}
+int b200reg_set_transformation_epsilon(b200reg_handle* h, double e) { if (!h) return B200REG_E_INVALID; h->cfg.transformation_epsilon = e; return B200REG_OK; }
+int b200reg_set_maximum_iterations(b200reg_handle* h, int n) { if (!h) return B200REG_E_INVALID; h->cfg.maximum_iterations = n; return B200REG_OK; }
+int b200reg_set_max_correspondence_distance(b200reg_handle* h, double d) { if (!h) return B200REG_E_INVALID; h->cfg.max_correspondence_distance = d; return B200REG_OK; }
+int b200reg_set_correspondence_randomness(b200reg_handle* h, int k) { if (!h || k < 1) return B200REG_E_INVALID; h->cfg.correspondence_randomness = k; return B200REG_OK; }
+
+int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t stride) {
+  if (!h) return B200REG_E_INVALID;
+  if (!n || !xyzw) { h->err = "Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = upload_cloud(h, xyzw, n, stride, h->tgt))) return rc;
+  h->n_tgt = (int)n;
+  h->have_tgt = true;
+  h->grid_stale = true;
+  h->nn_stale = true;
+  if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);  // ndt->setInputTarget builds the grid eagerly
+  return B200REG_OK;
+}
+
+int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t stride) {
+  if (!h || (n && !xyzw)) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = upload_cloud(h, xyzw, n, stride, h->src))) return rc;
+  h->n_src = (int)n;
+  h->have_src = true;
+  return B200REG_OK;
+}
+
+int b200reg_set_target_device(b200reg_handle* h, const float* d_xyzw, size_t n) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  if (!n || !d_xyzw) { h->err = "Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(h->tgt.reserve(n));
+  B200_CUDA_TRY(cudaMemcpyAsync(h->tgt.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
+  h->n_tgt = (int)n;
+  h->have_tgt = true;
+  h->grid_stale = true;
+  h->nn_stale = true;
+  if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);
+  return B200REG_OK;
+}
+
+int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || (n && !d_xyzw)) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(h->src.reserve(n ? n : 1));
+  if (n) B200_CUDA_TRY(cudaMemcpyAsync(h->src.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
+  h->n_src = (int)n;
+  h->have_src = true;
+  return B200REG_OK;
+}
+
+int b200reg_promote_source_to_target(b200reg_handle* h) {
+  if (!h) return B200REG_E_INVALID;
+  if (!h->have_src || h->n_src == 0) { h->err = "no source to promote"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  // swap the buffers: the old target storage becomes the (now unset) source storage
+  std::swap(h->src, h->tgt);
+  h->n_tgt = h->n_src;
+  h->have_tgt = true;
+  h->have_src = false;
+  h->n_src = 0;
+  h->grid_stale = true;
+  h->nn_stale = true;
+  if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);
+  return B200REG_OK;
+}
+
+int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  h->have_result = false;
+  if (!h->have_tgt) { h->err = "No input target dataset was given!"; return B200REG_E_STATE; }
+  if (!h->have_src || h->n_src == 0) { h->err = "No input source dataset was given!"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->cfg.method == B200REG_METHOD_NDT) {
+    if ((rc = run_ndt_single(h, guess, nullptr))) return rc;
+  } else {
+    h->err = "align: registration method not available on this handle";
+    return B200REG_E_STATE;
+  }
+  if (aligned_xyzw) {
+    B200_CUDA_TRY(h->aligned.reserve(h->n_src));
+    B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
+    k_transform_cloud<<<(h->n_src + 255) / 256, 256, 0, h->stream>>>(h->src.p, h->n_src, h->d_result.p, h->aligned.p);
+    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if ((rc = fetch_result(h))) return rc;
+  if (aligned_xyzw) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  return B200REG_OK;
+}
+
+int b200reg_has_converged(b200reg_handle* h, int* out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = h->have_result ? h->last.converged : 0;
+  return B200REG_OK;
+}
+int b200reg_get_final_transformation(b200reg_handle* h, float* out16) {
+  if (!h || !out16) return B200REG_E_INVALID;
+  if (!h->have_result) {
+    for (int i = 0; i < 16; ++i) out16[i] = (i % 5 == 0) ? 1.f : 0.f;
+    return B200REG_OK;
+  }
+  memcpy(out16, h->last.transformation, 64);
+  return B200REG_OK;
+}
+int b200reg_get_num_iterations(b200reg_handle* h, int* out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = h->have_result ? h->last.iterations : 0;
+  return B200REG_OK;
+}
+int b200reg_get_transformation_probability(b200reg_handle* h, double* out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = h->have_result ? h->last.score : 0.0;
+  return B200REG_OK;
+}
+int b200reg_get_result(b200reg_handle* h, b200reg_result* out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  if (!h->have_result) return B200REG_E_STATE;
+  *out = h->last;
+  return B200REG_OK;
+}
+
+int b200reg_get_fitness_score(b200reg_handle* h, double max_range, double* out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = 1.7976931348623157e308;
+  if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;  // DBL_MAX, as upstream with no correspondences
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_nn_grid(h))) return rc;
+  float T[16];
+  b200reg_get_final_transformation(h, T);
+  double sum = 0.0;
+  long long cnt = 0;
+  B200_CUDA_TRY(nn_fitness(h->stream, h->nn, h->src.p, h->n_src, T, max_range, /*strict_less=*/false, h->fit_partials, h->pin_small, &sum, &cnt));
+  h->last.fitness = cnt > 0 ? sum / (double)cnt : 1.7976931348623157e308;
+  *out = h->last.fitness;
+  return B200REG_OK;
+}
+
+int b200reg_calc_fitness_score(b200reg_handle* h, const float* relpose16, double max_range, double* out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out || !relpose16) return B200REG_E_INVALID;
+  *out = 1.7976931348623157e308;
+  if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_nn_grid(h))) return rc;
+  double sum = 0.0;
+  long long cnt = 0;
+  B200_CUDA_TRY(nn_fitness(h->stream, h->nn, h->src.p, h->n_src, relpose16, max_range, /*strict_less=*/false, h->fit_partials, h->pin_small, &sum, &cnt));
+  *out = cnt > 0 ? sum / (double)cnt : 1.7976931348623157e308;
+  return B200REG_OK;
+}
+
+int b200reg_get_inlier_fraction(b200reg_handle* h, double max_dist, double* out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = 0.0;
+  if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_nn_grid(h))) return rc;
+  float T[16];
+  b200reg_get_final_transformation(h, T);
+  double sum = 0.0;
+  long long cnt = 0;
+  // k_sq_dists[0] < max_correspondence_dist^2 [REF apps/scan_matching_odometry_nodelet.cpp:328]
+  B200_CUDA_TRY(nn_fitness(h->stream, h->nn, h->src.p, h->n_src, T, max_dist * max_dist, /*strict_less=*/true, h->fit_partials, h->pin_small, &sum, &cnt));
+  *out = (double)((float)cnt / (float)h->n_src);
+  return B200REG_OK;
+}
+
+// ---- VoxelGrid -------------------------------------------------------------------------------
+static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float leaf[3], unsigned min_pts, int dense, float4* d_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  B200_CUDA_TRY(h->vg_id.reserve(n ? n : 1));
+  B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
+  B200_CUDA_TRY(h->vg_counts.reserve(1));
+  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true));
+  const int blocks = n ? (int)((n + 255) / 256) : 1;
+  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
+                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
+  if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
+  B200_CUDA_TRY(cudaGetLastError());
+  h->vg_last_n = (int)n;
+  return B200REG_OK;
+}
+
+int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out, size_t* n_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !leaf || !n_out || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
+  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = vg_run(h, (const float4*)d_xyzw, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
+  VgCounts* pc = reinterpret_cast<VgCounts*>(h->pin_small.p);
+  B200_CUDA_TRY(cudaMemcpyAsync(pc, h->vg_counts.p, sizeof(VgCounts), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *n_out = pc->n_out;
+  h->vg_last_out = (int)pc->n_out;
+  return B200REG_OK;
+}
+
+int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* out, size_t cap,
+                             size_t* n_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !leaf || !n_out || (n && !xyzw)) return B200REG_E_INVALID;
+  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = upload_cloud(h, xyzw, n, stride, h->stage_in))) return rc;
+  B200_CUDA_TRY(h->stage_out.reserve(n ? n : 1));
+  size_t m = 0;
+  if ((rc = b200reg_voxelgrid_filter_device(h, (const float*)h->stage_in.p, n, leaf, min_pts, dense, (float*)h->stage_out.p, &m))) return rc;
+  *n_out = m;
+  if (m > cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
+  if (m) {
+    if (!out) return B200REG_E_INVALID;
+    B200_CUDA_TRY(h->pin_out.reserve(m));
+    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->pin_out.p, m * 16);
+  }
+  return B200REG_OK;
+}
+
+int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_vox, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  if (!h->vg_sort.meta.p) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  SortMeta meta;
+  B200_CUDA_TRY(cudaMemcpyAsync(&meta, h->vg_sort.meta.p, sizeof(meta), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (overflow) *overflow = meta.grid.overflow;
+  if (grid6) for (int a = 0; a < 3; ++a) { grid6[a] = meta.grid.min_b[a]; grid6[3 + a] = meta.grid.div_b[a]; }
+  if (meta.grid.overflow) return B200REG_OK;
+  size_t nv = n_vox < (size_t)h->vg_last_out ? n_vox : (size_t)h->vg_last_out;
+  if (voxel_id && nv) B200_CUDA_TRY(cudaMemcpyAsync(voxel_id, h->vg_id.p, nv * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (count && nv) B200_CUDA_TRY(cudaMemcpyAsync(count, h->vg_count.p, nv * 4, cudaMemcpyDeviceToHost, h->stream));
+  size_t np = n_points < (size_t)h->vg_last_n ? n_points : (size_t)h->vg_last_n;
+  if (key && np) B200_CUDA_TRY(cudaMemcpyAsync(key, h->vg_sort.point_key.p, np * 4, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return B200REG_OK;
+}
+
+// ---- NDT introspection -----------------------------------------------------------------------
+int b200reg_ndt_num_leaves(b200reg_handle* h, size_t* out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out) return B200REG_E_INVALID;
+  if (!h->have_tgt) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_ndt_grid(h))) return rc;
+  SortMeta meta;
+  B200_CUDA_TRY(cudaMemcpyAsync(&meta, h->grid.sort.meta.p, sizeof(meta), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = meta.n_vox;
+  return B200REG_OK;
+}
+
+int b200reg_ndt_get_leaves(b200reg_handle* h, uint64_t* idx, int32_t* n, double* mean3, double* cov9, double* icov9, float* centroid3, int32_t* grid6) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  size_t nv = 0;
+  int rc = b200reg_ndt_num_leaves(h, &nv);
+  if (rc) return rc;
+  SortMeta meta;
+  B200_CUDA_TRY(cudaMemcpy(&meta, h->grid.sort.meta.p, sizeof(meta), cudaMemcpyDeviceToHost));
+  if (grid6) for (int a = 0; a < 3; ++a) { grid6[a] = meta.grid.min_b[a]; grid6[3 + a] = meta.grid.div_b[a]; }
+  if (!nv) return B200REG_OK;
+  if (idx) {
+    std::vector<uint32_t> k(nv);
+    B200_CUDA_TRY(cudaMemcpy(k.data(), h->grid.sort.vox_key.p, nv * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nv; ++i) idx[i] = k[i];
+  }
+  if (n) B200_CUDA_TRY(cudaMemcpy(n, h->grid.leaf_n.p, nv * 4, cudaMemcpyDeviceToHost));
+  if (mean3) B200_CUDA_TRY(cudaMemcpy(mean3, h->grid.leaf_mean.p, nv * 24, cudaMemcpyDeviceToHost));
+  if (cov9) B200_CUDA_TRY(cudaMemcpy(cov9, h->grid.leaf_cov.p, nv * 72, cudaMemcpyDeviceToHost));
+  if (icov9) B200_CUDA_TRY(cudaMemcpy(icov9, h->grid.leaf_icov.p, nv * 72, cudaMemcpyDeviceToHost));
+  if (centroid3) {
+    std::vector<float4> c(nv);
+    B200_CUDA_TRY(cudaMemcpy(c.data(), h->grid.centroids.p, nv * 16, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nv; ++i) { centroid3[3 * i] = c[i].x; centroid3[3 * i + 1] = c[i].y; centroid3[3 * i + 2] = c[i].z; }
+  }
+  return B200REG_OK;
+}
+
+int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score, double g[6], double H[36]) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !p) return B200REG_E_INVALID;
+  if (h->cfg.method != B200REG_METHOD_NDT || !h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = run_ndt_single(h, nullptr, p))) return rc;
+  double* pd = reinterpret_cast<double*>(h->pin_small.p + sizeof(NdtJob) + sizeof(b200reg_result));
+  B200_CUDA_TRY(cudaMemcpyAsync(pd, h->deriv.p, 43 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (score) *score = pd[0];
+  if (g) memcpy(g, pd + 1, 6 * sizeof(double));
+  if (H) memcpy(H, pd + 7, 36 * sizeof(double));
+  return B200REG_OK;
+}
+
+int b200reg_get_stream(b200reg_handle* h, void** out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = (void*)h->stream;
+  return B200REG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,549 @@
+// b200reg — NDT alignment: the B200 replacement of
+// pclomp::NormalDistributionsTransform::computeTransformation and everything under it
+// (computeDerivatives / updateDerivatives / computePointDerivatives / computeAngleDerivatives /
+// computeStepLengthMT / trialValueSelectionMT / updateIntervalMT / computeHessian),
+// reached through registration->align [REF apps/scan_matching_odometry_nodelet.cpp:218;
+// include/hdl_graph_slam/loop_detector.hpp:145].
+//
+// One persistent cooperative kernel runs a whole registration: every derivative pass, the
+// Newton solve and the More-Thuente line search happen on the device, so an iteration costs no
+// host round trip.  A *group* of G CTAs owns one registration (G = all 148 SMs for a single
+// odometry alignment, a handful for loop-closure batches where many groups run side by side):
+//   pass   : each thread transforms its source points (float, same operation order as
+//            pcl::transformPoint), probes the DIRECT1/7/26 (or KDTREE-radius) voxels through
+//            the target hash, and accumulates score / gradient / Hessian
+//   reduce : warp shuffles -> shared memory -> one 29-double partial per CTA in global memory
+//   sync   : a counter barrier among the group's CTAs (co-residency guaranteed by the
+//            cooperative launch), then EVERY CTA sums the partials in the same fixed order
+//   step   : every CTA runs the Newton / More-Thuente state machine redundantly on the
+//            identical totals — bit-identical decisions, so no broadcast and no second barrier.
+//
+// Per-hit arithmetic is float and the sums are double, as upstream.  The per-hit Hessian is
+// factored through the point: with v = sum_hits e*(C q) and M = sum_hits e*(C - d2 (Cq)(Cq)^T),
+//   g = J^T v,   H = J^T M J + [v . d2x/dpi dpj]
+// which is the same polynomial as updateDerivatives' per-hit 6x6 update evaluated in a
+// different (cheaper) order.
+#pragma once
+#include "../../include/b200reg.h"
+#include "ndt_grid.cuh"
+
+namespace b200 {
+
+constexpr int kAlignThreads = 512;
+constexpr int kNumAcc = 29;  // score, g[6], H upper triangle [21], hits
+constexpr int kAccStride = 32;
+
+enum NdtPhase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_ITER = 2, PH_HESSIAN = 3, PH_DONE = 4, PH_EVAL_ONLY = 5 };
+
+struct NdtParams {
+  int search;  // b200reg_nn_search
+  double resolution, step_size, outlier_ratio, trans_eps;
+  int max_iterations;
+};
+
+struct NdtJob {
+  const float4* src;
+  int n_src;
+  NdtGridView grid;
+  float guess[12];  // row-major 3x4 of the initial guess
+  double p0[6];     // [t, eulerXYZ] of the guess (host: Eigen eulerAngles(0,1,2) restated, A.6)
+  int eval_only;    // 1: a single derivative pass at p0 (introspection), T built from p0
+  b200reg_result* result;  // device
+  double* deriv_out;       // device, 1 + 6 + 36 doubles (eval_only)
+};
+
+struct NdtShared {
+  // inputs of the current pass
+  float T[12];
+  float j_ang[8][3];
+  float h_ang[15][3];
+  int need_hessian;
+  int phase;
+  // optimiser state (identical in every CTA of the group)
+  double p[6], x_t[6], dir[6];
+  double score, g[6], H[36];
+  double phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t, psi_t, d_psi_t;
+  int step_iterations, open_interval, interval_converged;
+  int nr_iterations, converged, n_eval;
+  double hits;
+  double gauss_d1, gauss_d2;
+  double tot[kAccStride];
+  double red[kAlignThreads / 32][kAccStride];
+};
+
+// ---- the pose -> transform / angle-derivative tables ---------------------------------------
+// T = Translation(p0..2) * Rx(p3) * Ry(p4) * Rz(p5) composed in float exactly like the oracle's
+// m4f_from_xyz_euler (sequence of float 4x4 products with exact zeros and ones collapsed).
+__device__ inline void pose_to_T(const double p[6], float T[12]) {
+  const float rx = (float)p[3], ry = (float)p[4], rz = (float)p[5];
+  const float cx = (float)cos((double)rx), sx = (float)sin((double)rx);
+  const float cy = (float)cos((double)ry), sy = (float)sin((double)ry);
+  const float cz = (float)cos((double)rz), sz = (float)sin((double)rz);
+  const float b10 = __fmul_rn(sx, sy), b12 = -__fmul_rn(sx, cy), b20 = -__fmul_rn(cx, sy), b22 = __fmul_rn(cx, cy);
+  T[0] = __fmul_rn(cy, cz); T[1] = -__fmul_rn(cy, sz); T[2] = sy; T[3] = (float)p[0];
+  T[4] = __fadd_rn(__fmul_rn(b10, cz), __fmul_rn(cx, sz));
+  T[5] = __fadd_rn(__fmul_rn(b10, -sz), __fmul_rn(cx, cz));
+  T[6] = b12; T[7] = (float)p[1];
+  T[8] = __fadd_rn(__fmul_rn(b20, cz), __fmul_rn(sx, sz));
+  T[9] = __fadd_rn(__fmul_rn(b20, -sz), __fmul_rn(sx, cz));
+  T[10] = b22; T[11] = (float)p[2];
+}
+
+// computeAngleDerivatives (A.4): rows of j_ang (8) and h_ang (15) as float; evaluated in double
+// without contraction so the float casts match the oracle.
+__device__ inline void angle_tables(const double p[6], float j_ang[8][3], float h_ang[15][3]) {
+  double cx, cy, cz, sx, sy, sz;
+  if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
+  if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
+  if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
+#define M2(a, b) __dmul_rn(a, b)
+#define M3(a, b, c) __dmul_rn(__dmul_rn(a, b), c)
+#define AD(a, b) __dadd_rn(a, b)
+#define SB(a, b) __dsub_rn(a, b)
+  const double j[8][3] = {
+      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M2(-sx, cz), M3(cx, sy, sz)), M2(-cx, cy)},
+      {AD(M2(cx, sz), M3(sx, sy, cz)), SB(M2(cx, cz), M3(sx, sy, sz)), M2(-sx, cy)},
+      {M2(-sy, cz), M2(sy, sz), cy},
+      {M3(sx, cy, cz), M3(-sx, cy, sz), M2(sx, sy)},
+      {M3(-cx, cy, cz), M3(cx, cy, sz), M2(-cx, sy)},
+      {M2(-cy, sz), M2(-cy, cz), 0.0},
+      {SB(M2(cx, cz), M3(sx, sy, sz)), SB(M2(-cx, sz), M3(sx, sy, cz)), 0.0},
+      {AD(M2(sx, cz), M3(cx, sy, sz)), SB(M3(cx, sy, cz), M2(sx, sz)), 0.0}};
+  const double h[15][3] = {
+      {SB(M2(-cx, sz), M3(sx, sy, cz)), AD(M2(-cx, cz), M3(sx, sy, sz)), M2(sx, cy)},
+      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M3(-cx, sy, sz), M2(sx, cz)), M2(-cx, cy)},
+      {M3(cx, cy, cz), M3(-cx, cy, sz), M2(cx, sy)},
+      {M3(sx, cy, cz), M3(-sx, cy, sz), M2(sx, sy)},
+      {SB(M2(-sx, cz), M3(cx, sy, sz)), SB(M2(sx, sz), M3(cx, sy, cz)), 0.0},
+      {SB(M2(cx, cz), M3(sx, sy, sz)), SB(M3(-sx, sy, cz), M2(cx, sz)), 0.0},
+      {M2(-cy, cz), M2(cy, sz), sy},  // d1: upstream's (+sy), kept
+      {M3(-sx, sy, cz), M3(sx, sy, sz), M2(sx, cy)},
+      {M3(cx, sy, cz), M3(-cx, sy, sz), M2(-cx, cy)},
+      {M2(sy, sz), M2(sy, cz), 0.0},
+      {M3(-sx, cy, sz), M3(-sx, cy, cz), 0.0},
+      {M3(cx, cy, sz), M3(cx, cy, cz), 0.0},
+      {M2(-cy, cz), M2(cy, sz), 0.0},
+      {SB(M2(-cx, sz), M3(sx, sy, cz)), AD(M2(-cx, cz), M3(sx, sy, sz)), 0.0},
+      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M3(-cx, sy, sz), M2(sx, cz)), 0.0}};
+#undef M2
+#undef M3
+#undef AD
+#undef SB
+  for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < 3; ++c) j_ang[r][c] = (float)j[r][c];
+  for (int r = 0; r < 15; ++r)
+    for (int c = 0; c < 3; ++c) h_ang[r][c] = (float)h[r][c];
+}
+
+// ---- More-Thuente helpers (A.4) ---------------------------------------------------------------
+__device__ inline double mt_psi(double a, double f_a, double f_0, double g_0, double mu) { return f_a - f_0 - mu * g_0 * a; }
+__device__ inline double mt_dpsi(double g_a, double g_0, double mu) { return g_a - mu * g_0; }
+
+__device__ inline bool mt_update_interval(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t) {
+  if (f_t > f_l) { a_u = a_t; f_u = f_t; g_u = g_t; return false; }
+  if (g_t * (a_l - a_t) > 0) { a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+  if (g_t * (a_l - a_t) < 0) { a_u = a_l; f_u = f_l; g_u = g_l; a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+  return true;
+}
+
+__device__ inline double mt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
+  if (f_t > f_l) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+    return fabs(a_c - a_l) < fabs(a_q - a_l) ? a_c : 0.5 * (a_q + a_c);
+  }
+  if (g_t * g_l < 0) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    return fabs(a_c - a_t) >= fabs(a_s - a_t) ? a_c : a_s;
+  }
+  if (fabs(g_t) <= fabs(g_l)) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    double a_n = fabs(a_c - a_t) < fabs(a_s - a_t) ? a_c : a_s;
+    return a_t > a_l ? fmin(a_t + 0.66 * (a_u - a_t), a_n) : fmax(a_t + 0.66 * (a_u - a_t), a_n);
+  }
+  double z = 3 * (f_t - f_u) / (a_t - a_u) - g_t - g_u;
+  double w = sqrt(z * z - g_t * g_u);
+  return a_u + (a_t - a_u) * (w - g_u - z) / (g_t - g_u + 2 * w);
+}
+
+// H upper-triangle index of (i, j), i <= j, inside the accumulator vector
+__host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (i - 1)) / 2 + (j - i); }
+
+// ---- the optimiser state machine; runs on one thread after every derivative pass -----------
+// Returns the phase of the next pass (PH_DONE when the registration is finished).
+__device__ __noinline__ void ndt_request_eval(NdtShared& s, const double x_t[6], int phase, int need_hessian) {
+  pose_to_T(x_t, s.T);
+  angle_tables(x_t, s.j_ang, s.h_ang);
+  s.phase = phase;
+  s.need_hessian = need_hessian;
+}
+
+__device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, int n_src) {
+  const double mu = 1.e-4, nu = 0.9;
+  const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
+  const double* t = s.tot;
+  s.n_eval++;
+  s.hits += t[28];
+  bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
+  switch (s.phase) {
+    case PH_INIT:
+    case PH_MT_FIRST:
+      s.score = t[0];
+      for (int i = 0; i < 6; ++i) s.g[i] = t[1 + i];
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = t[hidx(i, j)];
+      if (s.phase == PH_INIT) go_newton_begin = true;
+      else go_loop_check = true;
+      break;
+    case PH_MT_ITER:
+      s.score = t[0];
+      for (int i = 0; i < 6; ++i) s.g[i] = t[1 + i];
+      go_loop_check = true;
+      break;
+    case PH_HESSIAN:
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = t[hidx(i, j)];
+      go_newton_end = true;
+      break;
+    default:
+      return;
+  }
+  if (go_loop_check) {
+    // the evaluation at a_t just finished
+    s.phi_t = -s.score;
+    double gd = 0;
+    for (int i = 0; i < 6; ++i) gd += s.g[i] * s.dir[i];
+    s.d_phi_t = -gd;
+    s.psi_t = mt_psi(s.a_t, s.phi_t, s.phi_0, s.d_phi_0, mu);
+    s.d_psi_t = mt_dpsi(s.d_phi_t, s.d_phi_0, mu);
+    if (s.phase == PH_MT_ITER) {
+      if (s.open_interval && (s.psi_t <= 0 && s.d_psi_t >= 0)) {
+        s.open_interval = 0;
+        s.f_l = s.f_l + s.phi_0 - mu * s.d_phi_0 * s.a_l;
+        s.g_l = s.g_l + mu * s.d_phi_0;
+        s.f_u = s.f_u + s.phi_0 - mu * s.d_phi_0 * s.a_u;
+        s.g_u = s.g_u + mu * s.d_phi_0;
+      }
+      if (s.open_interval) s.interval_converged = mt_update_interval(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.psi_t, s.d_psi_t);
+      else s.interval_converged = mt_update_interval(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.phi_t, s.d_phi_t);
+      s.step_iterations++;
+    }
+  }
+  while (true) {
+    if (go_loop_check) {
+      go_loop_check = false;
+      if (!s.interval_converged && s.step_iterations < 10 && !(s.psi_t <= 0 && s.d_phi_t <= -nu * s.d_phi_0)) {
+        if (s.open_interval) s.a_t = mt_trial_value(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.psi_t, s.d_psi_t);
+        else s.a_t = mt_trial_value(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.phi_t, s.d_phi_t);
+        s.a_t = fmin(s.a_t, step_max);
+        s.a_t = fmax(s.a_t, step_min);
+        for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
+        ndt_request_eval(s, s.x_t, PH_MT_ITER, 0);
+        return;
+      }
+      if (s.step_iterations) {  // computeHessian at x_t (same transform and tables as the last pass)
+        s.phase = PH_HESSIAN;
+        s.need_hessian = 1;
+        return;
+      }
+      go_newton_end = true;
+    }
+    if (go_newton_end) {
+      go_newton_end = false;
+      for (int i = 0; i < 6; ++i) s.p[i] += s.dir[i] * s.a_t;
+      if (s.nr_iterations > prm.max_iterations || (s.nr_iterations && (fabs(s.a_t) < prm.trans_eps))) s.converged = 1;
+      s.nr_iterations++;
+      if (s.converged) { s.phase = PH_DONE; return; }
+      go_newton_begin = true;
+    }
+    if (go_newton_begin) {
+      go_newton_begin = false;
+      double neg_g[6], dp[6];
+      for (int i = 0; i < 6; ++i) neg_g[i] = -s.g[i];
+      solve6(s.H, neg_g, dp);
+      double nrm = 0;
+      for (int i = 0; i < 6; ++i) nrm += dp[i] * dp[i];
+      nrm = sqrt(nrm);
+      if (nrm == 0 || nrm != nrm) {
+        s.converged = (nrm == nrm) ? 1 : 0;
+        s.phase = PH_DONE;
+        return;
+      }
+      for (int i = 0; i < 6; ++i) s.dir[i] = dp[i] / nrm;
+      // computeStepLengthMT prologue
+      s.phi_0 = -s.score;
+      double gd = 0;
+      for (int i = 0; i < 6; ++i) gd += s.g[i] * s.dir[i];
+      s.d_phi_0 = -gd;
+      if (s.d_phi_0 >= 0) {
+        if (s.d_phi_0 == 0) {  // returns 0 without evaluating anything
+          s.a_t = 0;
+          go_newton_end = true;
+          continue;
+        }
+        s.d_phi_0 *= -1;
+        for (int i = 0; i < 6; ++i) s.dir[i] *= -1;
+      }
+      s.step_iterations = 0;
+      s.a_l = 0; s.a_u = 0;
+      s.f_l = mt_psi(s.a_l, s.phi_0, s.phi_0, s.d_phi_0, mu);
+      s.g_l = mt_dpsi(s.d_phi_0, s.d_phi_0, mu);
+      s.f_u = mt_psi(s.a_u, s.phi_0, s.phi_0, s.d_phi_0, mu);
+      s.g_u = mt_dpsi(s.d_phi_0, s.d_phi_0, mu);
+      s.interval_converged = (step_max - step_min) < 0;
+      s.open_interval = 1;
+      s.a_t = nrm;
+      s.a_t = fmin(s.a_t, step_max);
+      s.a_t = fmax(s.a_t, step_min);
+      for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
+      ndt_request_eval(s, s.x_t, PH_MT_FIRST, 1);
+      return;
+    }
+  }
+}
+
+// ---- one source point ------------------------------------------------------------------------
+template <int MODE>  // 1, 7, 27 (DIRECT*) or 0 (KDTREE radius search over voxel centroids)
+__device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView& grid, const GridParams& gp, float4 pt, float d1f_unused, double gauss_d1, float gauss_d2,
+                                          float res, int need_hessian, double acc[kNumAcc]) {
+  const float x0 = pt.x, x1 = pt.y, x2 = pt.z;
+  const float xt0 = affine_row(s.T[0], s.T[1], s.T[2], s.T[3], x0, x1, x2);
+  const float xt1 = affine_row(s.T[4], s.T[5], s.T[6], s.T[7], x0, x1, x2);
+  const float xt2 = affine_row(s.T[8], s.T[9], s.T[10], s.T[11], x0, x1, x2);
+  // getNeighborhoodAtPoint*: float DIVISION by the leaf size (A.3)
+  const int c0 = (int)floorf(__fdiv_rn(xt0, gp.leaf[0])), c1 = (int)floorf(__fdiv_rn(xt1, gp.leaf[1])), c2 = (int)floorf(__fdiv_rn(xt2, gp.leaf[2]));
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;                                       // sum e (C q)
+  float m00 = 0.f, m01 = 0.f, m02 = 0.f, m11 = 0.f, m12 = 0.f, m22 = 0.f;  // sum e (C - d2 Cq Cq^T)
+  double score = 0.0;
+  int hits = 0;
+  constexpr int NOFF = MODE == 0 ? 27 : MODE;
+#pragma unroll
+  for (int o = 0; o < NOFF; ++o) {
+    int dx, dy, dz;
+    if (NOFF == 1) { dx = dy = dz = 0; }
+    else if (NOFF == 7) {
+      // (0,0,0), (+1,0,0), (-1,0,0), (0,+1,0), (0,-1,0), (0,0,+1), (0,0,-1)
+      dx = o == 1 ? 1 : o == 2 ? -1 : 0;
+      dy = o == 3 ? 1 : o == 4 ? -1 : 0;
+      dz = o == 5 ? 1 : o == 6 ? -1 : 0;
+    } else { dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1; }
+    const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
+    if (i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]) continue;
+    const uint32_t key = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
+    const int slot = ndt_lookup(grid, key);
+    if (slot < 0) continue;
+    if (MODE == 0) {  // radiusSearch over the voxel centroids, d2 < resolution^2
+      float4 c = __ldg(grid.centroids + slot);
+      if (!(l2_simple(xt0, xt1, xt2, c.x, c.y, c.z) < __fmul_rn(res, res))) continue;
+    }
+    const double2* vp = reinterpret_cast<const double2*>(grid.voxels + slot);
+    const double2 ma = __ldg(vp), mb = __ldg(vp + 1);  // mean0 mean1 | mean2 (icov0 icov1)
+    const float4 cb = __ldg(reinterpret_cast<const float4*>(vp + 2));
+    const float C00 = __int_as_float(__double2loint(mb.y)), C01 = __int_as_float(__double2hiint(mb.y));
+    const float C02 = cb.x, C11 = cb.y, C12 = cb.z, C22 = cb.w;
+    ++hits;
+    const float q0 = (float)((double)xt0 - ma.x), q1 = (float)((double)xt1 - ma.y), q2 = (float)((double)xt2 - mb.x);
+    const float cq0 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C00), __fmul_rn(q1, C01)), __fmul_rn(q2, C02));
+    const float cq1 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C01), __fmul_rn(q1, C11)), __fmul_rn(q2, C12));
+    const float cq2 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C02), __fmul_rn(q1, C12)), __fmul_rn(q2, C22));
+    const float qCq = __fadd_rn(__fadd_rn(__fmul_rn(q0, cq0), __fmul_rn(q1, cq1)), __fmul_rn(q2, cq2));
+    float e = expf(__fmul_rn(__fmul_rn(-gauss_d2, qCq), 0.5f));
+    const float score_inc = (float)(-gauss_d1 * (double)e);
+    e = __fmul_rn(gauss_d2, e);
+    if (e > 1.f || e < 0.f || e != e) continue;  // upstream returns 0 for this hit (score included)
+    score += (double)score_inc;
+    e = (float)((double)e * gauss_d1);
+    v0 = fmaf(e, cq0, v0); v1 = fmaf(e, cq1, v1); v2 = fmaf(e, cq2, v2);
+    if (need_hessian) {
+      const float ed = __fmul_rn(e, gauss_d2);
+      m00 += e * C00 - ed * cq0 * cq0; m01 += e * C01 - ed * cq0 * cq1; m02 += e * C02 - ed * cq0 * cq2;
+      m11 += e * C11 - ed * cq1 * cq1; m12 += e * C12 - ed * cq1 * cq2; m22 += e * C22 - ed * cq2 * cq2;
+    }
+  }
+  if (!hits) return;
+  acc[28] += (double)hits;
+  acc[0] += score;
+  // point_gradient columns 3..5: j3 = (0, a.x, b.x), j4 = (c.x, d.x, e.x), j5 = (f.x, g.x, h.x)
+  auto dotj = [&](int r) { return s.j_ang[r][0] * x0 + s.j_ang[r][1] * x1 + s.j_ang[r][2] * x2; };
+  const float j3y = dotj(0), j3z = dotj(1);
+  const float j4x = dotj(2), j4y = dotj(3), j4z = dotj(4);
+  const float j5x = dotj(5), j5y = dotj(6), j5z = dotj(7);
+  acc[1] += (double)v0; acc[2] += (double)v1; acc[3] += (double)v2;
+  acc[4] += (double)(v1 * j3y + v2 * j3z);
+  acc[5] += (double)(v0 * j4x + v1 * j4y + v2 * j4z);
+  acc[6] += (double)(v0 * j5x + v1 * j5y + v2 * j5z);
+  if (!need_hessian) return;
+  // M J_k for the rotational columns
+  const float a0 = m01 * j3y + m02 * j3z, a1 = m11 * j3y + m12 * j3z, a2 = m12 * j3y + m22 * j3z;                          // M j3
+  const float b0 = m00 * j4x + m01 * j4y + m02 * j4z, b1 = m01 * j4x + m11 * j4y + m12 * j4z, b2 = m02 * j4x + m12 * j4y + m22 * j4z;  // M j4
+  const float e0 = m00 * j5x + m01 * j5y + m02 * j5z, e1 = m01 * j5x + m11 * j5y + m12 * j5z, e2 = m02 * j5x + m12 * j5y + m22 * j5z;  // M j5
+  auto doth = [&](int r) { return s.h_ang[r][0] * x0 + s.h_ang[r][1] * x1 + s.h_ang[r][2] * x2; };
+  // second derivatives: a=(0,h0,h1) b=(0,h2,h3) c=(0,h4,h5) d=(h6,h7,h8) e=(h9,h10,h11) f=(h12,h13,h14)
+  const float vh33 = v1 * doth(0) + v2 * doth(1);
+  const float vh34 = v1 * doth(2) + v2 * doth(3);
+  const float vh35 = v1 * doth(4) + v2 * doth(5);
+  const float vh44 = v0 * doth(6) + v1 * doth(7) + v2 * doth(8);
+  const float vh45 = v0 * doth(9) + v1 * doth(10) + v2 * doth(11);
+  const float vh55 = v0 * doth(12) + v1 * doth(13) + v2 * doth(14);
+  acc[hidx(0, 0)] += (double)m00; acc[hidx(0, 1)] += (double)m01; acc[hidx(0, 2)] += (double)m02;
+  acc[hidx(1, 1)] += (double)m11; acc[hidx(1, 2)] += (double)m12; acc[hidx(2, 2)] += (double)m22;
+  acc[hidx(0, 3)] += (double)a0; acc[hidx(1, 3)] += (double)a1; acc[hidx(2, 3)] += (double)a2;
+  acc[hidx(0, 4)] += (double)b0; acc[hidx(1, 4)] += (double)b1; acc[hidx(2, 4)] += (double)b2;
+  acc[hidx(0, 5)] += (double)e0; acc[hidx(1, 5)] += (double)e1; acc[hidx(2, 5)] += (double)e2;
+  acc[hidx(3, 3)] += (double)(j3y * a1 + j3z * a2 + vh33);
+  acc[hidx(3, 4)] += (double)(j3y * b1 + j3z * b2 + vh34);
+  acc[hidx(3, 5)] += (double)(j3y * e1 + j3z * e2 + vh35);
+  acc[hidx(4, 4)] += (double)(j4x * b0 + j4y * b1 + j4z * b2 + vh44);
+  acc[hidx(4, 5)] += (double)(j4x * e0 + j4y * e1 + j4z * e2 + vh45);
+  acc[hidx(5, 5)] += (double)(j5x * e0 + j5y * e1 + j5z * e2 + vh55);
+}
+
+// group barrier: monotonically increasing counter, one arrival per CTA per use
+__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct NdtWorkspace {       // per group, device
+  double* partials;         // [2][G][kAccStride]
+  unsigned int* barrier;    // counter (zeroed before the launch)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers) {
+  __shared__ NdtShared s;
+  const int G = ctas_per_group;
+  const int group = blockIdx.x / G, rank = blockIdx.x % G, n_groups = gridDim.x / G;
+  double* partials = partials_all + (size_t)group * 2 * G * kAccStride;
+  unsigned int* barrier = barriers + group * 32;  // one 128-byte line per group
+  unsigned int epoch = 0;
+  int parity = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int jb = group; jb < n_jobs; jb += n_groups) {
+    const NdtJob& job = jobs[jb];
+    const GridParams gp = job.grid.meta->grid;
+    const int n_src = job.n_src;
+    if (tid == 0) {
+      // gauss constants (A.4), recomputed per registration like upstream
+      const double c1 = 10.0 * (1 - prm.outlier_ratio);
+      const double c2 = prm.outlier_ratio / pow((double)(float)prm.resolution, 3);
+      const double d3 = -log(c2);
+      s.gauss_d1 = -log(c1 + c2) - d3;
+      s.gauss_d2 = -2 * log((-log(c1 * exp(-0.5) + c2) - d3) / s.gauss_d1);
+      for (int i = 0; i < 6; ++i) s.p[i] = job.p0[i];
+      s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.hits = 0.0;
+      s.score = 0.0;
+      if (job.eval_only) {
+        ndt_request_eval(s, s.p, PH_EVAL_ONLY, 1);
+      } else {
+        for (int i = 0; i < 12; ++i) s.T[i] = job.guess[i];
+        angle_tables(s.p, s.j_ang, s.h_ang);
+        s.phase = PH_INIT;
+        s.need_hessian = 1;
+      }
+    }
+    __syncthreads();
+    while (true) {
+      // ---- pass
+      double acc[kNumAcc];
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
+      const int need_h = s.need_hessian;
+      const double gd1 = s.gauss_d1;
+      const float gd2 = (float)s.gauss_d2;
+      const float res = (float)prm.resolution;
+      if (gp.any && !gp.overflow) {
+        for (int i = rank * kAlignThreads + tid; i < n_src; i += G * kAlignThreads) {
+          const float4 pt = __ldg(job.src + i);
+          ndt_point<MODE>(s, job.grid, gp, pt, 0.f, gd1, gd2, res, need_h, acc);
+        }
+      }
+      // ---- block reduce
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s.red[warp][k] = v;
+      }
+      __syncthreads();
+      if (tid < kNumAcc) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kAlignThreads / 32; ++w) v += s.red[w][tid];
+        partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
+      }
+      // ---- group sync + redundant fixed-order reduction of the G partials
+      epoch += (unsigned)G;
+      group_barrier(barrier, epoch);
+      {
+        const int col = tid >> 4, sub = tid & 15;  // 16 threads per accumulator
+        double v = 0.0;
+        if (col < kNumAcc)
+          for (int r = sub; r < G; r += 16) v += __ldcg(partials + ((size_t)parity * G + r) * kAccStride + col);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (col < kNumAcc && sub == 0) s.tot[col] = v;
+      }
+      parity ^= 1;
+      __syncthreads();
+      // ---- optimiser step (thread 0 of every CTA, identical inputs -> identical state)
+      if (tid == 0) {
+        if (s.phase == PH_EVAL_ONLY) {
+          s.n_eval++;
+          s.hits += s.tot[28];
+          s.phase = PH_DONE;
+        } else {
+          ndt_step(s, prm, n_src);
+        }
+      }
+      __syncthreads();
+      if (s.phase == PH_DONE) break;
+    }
+    // ---- result
+    if (rank == 0 && tid == 0) {
+      if (job.eval_only) {
+        double* o = job.deriv_out;
+        o[0] = s.tot[0];
+        for (int i = 0; i < 6; ++i) o[1 + i] = s.tot[1 + i];
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) o[7 + 6 * i + j] = s.tot[i <= j ? hidx(i, j) : hidx(j, i)];
+      }
+      b200reg_result r;
+      // column-major 4x4 from the row-major 3x4 of the last evaluated transform
+      for (int c = 0; c < 4; ++c) {
+        for (int rr = 0; rr < 3; ++rr) r.transformation[4 * c + rr] = s.T[4 * rr + c];
+        r.transformation[4 * c + 3] = c == 3 ? 1.f : 0.f;
+      }
+      r.fitness = 0.0;
+      r.score = n_src > 0 ? s.score / (double)n_src : 0.0;
+      r.converged = s.converged;
+      r.iterations = s.nr_iterations;
+      r.evaluations = s.n_eval;
+      r.reserved = 0;
+      r.hits = (long long)s.hits;
+      *job.result = r;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,391 @@
+// b200reg — voxel keys + stable LSD radix sort + run segmentation.
+//
+// The machinery shared by VoxelGrid down-sampling, the NDT target grid and the
+// exact-NN cell grid: every point gets the linear index of its voxel (bit-exact with
+// pcl::VoxelGrid), (key, point index) pairs are sorted by key
+// with a hand-written stable radix sort (so points inside a voxel stay in input order),
+// and runs of equal keys are numbered.  Nothing here synchronises with the host: sizes
+// that depend on the data (bits to sort, number of voxels) stay in device memory and the
+// kernels that need them read them there.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kSortThreads = 256;
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
+
+struct SortMeta {     // device-resident, written by k_grid_keys / k_seg_scan
+  GridParams grid;
+  uint32_t nbits;     // key bits that have to be sorted
+  uint32_t skip_key;  // key given to skipped (non-finite) points: sorts after every voxel
+  uint32_t n_vox;     // number of runs (occupied voxels), skipped points excluded
+  uint32_t n_valid;   // points that received a voxel
+};
+
+// ---- min / max -------------------------------------------------------------
+__global__ void k_minmax_init(int* mm) {
+  if (threadIdx.x < 3) mm[threadIdx.x] = 0x7FFFFFFF;
+  else if (threadIdx.x < 6) mm[threadIdx.x] = (int)0x80000000;
+  else if (threadIdx.x == 6) mm[6] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const float4* __restrict__ pts, int n, int is_dense, int* mm) {
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  int any = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(pts + i);
+    if (!is_dense && !finite3(p.x, p.y, p.z)) continue;
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    any = 1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    any |= __shfl_xor_sync(0xffffffffu, any, o);
+  }
+  if ((threadIdx.x & 31) == 0 && any) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(mm + a, float_to_ordered(mn[a]));
+      atomicMax(mm + 3 + a, float_to_ordered(mx[a]));
+    }
+    atomicOr(mm + 6, 1);
+  }
+}
+
+// A.1 steps 2-3 from the reduced min / max
+__device__ __forceinline__ void make_grid(const int* mm, float lx, float ly, float lz, GridParams& g) {
+  const float leaf[3] = {lx, ly, lz};
+  g.any = mm[6];
+  g.overflow = 0;
+  long long cells = 1;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    g.leaf[a] = leaf[a];
+    g.inv_leaf[a] = __fdiv_rn(1.0f, leaf[a]);
+    float mn = ordered_to_float(mm[a]), mx = ordered_to_float(mm[3 + a]);
+    if (!g.any) { mn = 0.f; mx = 0.f; }
+    long long d = (long long)__fmul_rn(__fsub_rn(mx, mn), g.inv_leaf[a]) + 1;
+    cells *= d;
+    g.min_b[a] = (int)floorf(__fmul_rn(mn, g.inv_leaf[a]));
+    g.max_b[a] = (int)floorf(__fmul_rn(mx, g.inv_leaf[a]));
+    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
+  }
+  // the guard multiplies the three truncated extents exactly as PCL does (int64)
+  {
+    long long dx = (long long)__fmul_rn(__fsub_rn(ordered_to_float(mm[3]), ordered_to_float(mm[0])), g.inv_leaf[0]) + 1;
+    long long dy = (long long)__fmul_rn(__fsub_rn(ordered_to_float(mm[4]), ordered_to_float(mm[1])), g.inv_leaf[1]) + 1;
+    long long dz = (long long)__fmul_rn(__fsub_rn(ordered_to_float(mm[5]), ordered_to_float(mm[2])), g.inv_leaf[2]) + 1;
+    if (g.any && dx * dy * dz > 2147483647ll) g.overflow = 1;
+  }
+  g.mul[0] = 1;
+  g.mul[1] = g.div_b[0];
+  g.mul[2] = g.div_b[0] * g.div_b[1];
+}
+
+__device__ __forceinline__ uint32_t voxel_key(const GridParams& g, float x, float y, float z) {
+  int i0 = (int)__fsub_rn(floorf(__fmul_rn(x, g.inv_leaf[0])), (float)g.min_b[0]);
+  int i1 = (int)__fsub_rn(floorf(__fmul_rn(y, g.inv_leaf[1])), (float)g.min_b[1]);
+  int i2 = (int)__fsub_rn(floorf(__fmul_rn(z, g.inv_leaf[2])), (float)g.min_b[2]);
+  return (uint32_t)(i0 * g.mul[0] + i1 * g.mul[1] + i2 * g.mul[2]);
+}
+
+// keys (A.1 step 4) + pass-0 digit histogram per tile
+__global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __restrict__ pts, int n, int is_dense, float lx, float ly, float lz, const int* __restrict__ mm,
+                                                             SortMeta* meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ point_key) {
+  __shared__ GridParams g;
+  __shared__ uint32_t s_skip;
+  if (threadIdx.x == 0) {
+    make_grid(mm, lx, ly, lz, g);
+    // cells < 2^31 when !overflow (div_b product can exceed the truncated-extent product by a
+    // rounding cell per axis; clamp so the skip key still sorts last)
+    unsigned long long cells = (unsigned long long)g.div_b[0] * (unsigned long long)g.div_b[1] * (unsigned long long)g.div_b[2];
+    if (cells > 0xFFFFFFFEull) cells = 0xFFFFFFFEull;
+    s_skip = (uint32_t)cells;
+    if (blockIdx.x == 0) {
+      meta->grid = g;
+      meta->skip_key = s_skip;
+      meta->nbits = g.overflow ? 0u : (uint32_t)(64 - __clzll((unsigned long long)s_skip));
+      meta->n_vox = 0;
+      meta->n_valid = 0;
+    }
+  }
+  __syncthreads();
+  if (g.overflow) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(pts + i);
+    uint32_t k = s_skip;
+    if (is_dense || finite3(p.x, p.y, p.z)) k = voxel_key(g, p.x, p.y, p.z);
+    keys[i] = k;
+    vals[i] = (uint32_t)i;
+    if (point_key) point_key[i] = (k == s_skip) ? kInvalidKey : k;
+  }
+}
+
+// ---- radix sort: one pass = hist -> scan -> scatter --------------------------
+// hist[tile][digit] (tile-major so the scan reads coalesced rows)
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, int n, int pass, const SortMeta* __restrict__ meta, uint32_t* __restrict__ hist) {
+  if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
+  __shared__ uint32_t s[kRadix];
+  s[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * (kSortThreads * ITEMS);
+  const int shift = pass * kRadixBits;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    int i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&s[(keys[i] >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  hist[blockIdx.x * kRadix + threadIdx.x] = s[threadIdx.x];
+}
+
+// exclusive scan over (digit-major, tile-minor) order, in place
+__global__ void __launch_bounds__(kRadix) k_sort_scan(uint32_t* __restrict__ hist, int n_tiles, int pass, const SortMeta* __restrict__ meta) {
+  if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
+  __shared__ uint32_t s_tot[kRadix];
+  const int d = threadIdx.x;
+  uint32_t run = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    uint32_t c = hist[t * kRadix + d];
+    hist[t * kRadix + d] = run;
+    run += c;
+  }
+  s_tot[d] = run;
+  __syncthreads();
+  // exclusive scan of the 256 digit totals (Hillis-Steele in shared memory)
+  uint32_t v = run;
+  for (int o = 1; o < kRadix; o <<= 1) {
+    uint32_t add = d >= o ? s_tot[d - o] : 0;
+    __syncthreads();
+    s_tot[d] += add;
+    __syncthreads();
+  }
+  uint32_t excl = s_tot[d] - v;
+  for (int t = 0; t < n_tiles; ++t) hist[t * kRadix + d] += excl;
+}
+
+// stable scatter: each warp owns a contiguous slice of the tile and walks it in rounds of 32
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out, int n, int pass, const SortMeta* __restrict__ meta, const uint32_t* __restrict__ hist) {
+  if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
+  constexpr int WARPS = kSortThreads / 32;
+  __shared__ uint32_t cnt[WARPS][kRadix];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < WARPS * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int shift = pass * kRadixBits;
+  const int wbase = blockIdx.x * (kSortThreads * ITEMS) + warp * (32 * ITEMS);
+  uint32_t k[ITEMS], v[ITEMS];
+  // phase A: per-warp digit counts
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    int i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    k[r] = ok ? keys_in[i] : 0u;
+    v[r] = ok ? vals_in[i] : 0u;
+    uint32_t dgt = ok ? ((k[r] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // kRadix = "no element"
+    uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // phase B: digit bases for every warp = global base of (digit, tile) + counts of lower warps
+  {
+    const int d = threadIdx.x;  // kSortThreads == kRadix
+    uint32_t run = hist[blockIdx.x * kRadix + d];
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      uint32_t c = cnt[w][d];
+      cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase C: ranks inside the warp round, in lane order
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    int i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    uint32_t dgt = ok ? ((k[r] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;
+    uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t dst = 0;
+    if (ok) dst = cnt[warp][dgt] + rank;
+    __syncwarp();
+    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      keys_out[dst] = k[r];
+      vals_out[dst] = v[r];
+    }
+  }
+}
+
+// ---- run segmentation --------------------------------------------------------
+// sorted buffers live in A when an even number of passes ran, else in B
+__device__ __forceinline__ bool sorted_in_b(const SortMeta* meta) { return (((meta->nbits + kRadixBits - 1) / kRadixBits) & 1u) != 0; }
+
+// heads per tile
+__global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, const SortMeta* __restrict__ meta,
+                                                   uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_valid) {
+  if (meta->grid.overflow) return;
+  const uint32_t* keys = sorted_in_b(meta) ? keys_b : keys_a;
+  const uint32_t skip = meta->skip_key;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int head = 0, valid = 0;
+  if (i < n) {
+    uint32_t k = keys[i];
+    valid = k != skip;
+    head = valid && (i == 0 || keys[i - 1] != k);
+  }
+  int h = __syncthreads_count(head);
+  int v = __syncthreads_count(valid);
+  if (threadIdx.x == 0) {
+    tile_heads[blockIdx.x] = (uint32_t)h;
+    tile_valid[blockIdx.x] = (uint32_t)v;
+  }
+}
+
+// slot of every head (= exclusive count of heads before it); vox_start[slot] = position of the
+// head in the sorted order; vox_start[n_vox] = n_valid closes the last run
+__global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, SortMeta* meta,
+                                                  const uint32_t* __restrict__ tile_heads, const uint32_t* __restrict__ tile_valid, int n_tiles,
+                                                  uint32_t* __restrict__ vox_start, uint32_t* __restrict__ vox_key) {
+  if (meta->grid.overflow) return;
+  const uint32_t* keys = sorted_in_b(meta) ? keys_b : keys_a;
+  const uint32_t skip = meta->skip_key;
+  __shared__ uint32_t s_red[8];
+  __shared__ uint32_t s_base, s_tot, s_valid;
+  // base = heads in all earlier tiles (block-wide strided sum; n_tiles is a few hundred)
+  uint32_t part = 0, tot = 0, val = 0;
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    uint32_t h = tile_heads[t];
+    if (t < (int)blockIdx.x) part += h;
+    tot += h;
+    val += tile_valid[t];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_sum = [&](uint32_t x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_red[w];
+    return r;
+  };
+  uint32_t b = block_sum(part), T = block_sum(tot), V = block_sum(val);
+  if (threadIdx.x == 0) { s_base = b; s_tot = T; s_valid = V; }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int head = 0;
+  uint32_t k = 0;
+  if (i < n) {
+    k = keys[i];
+    head = (k != skip) && (i == 0 || keys[i - 1] != k);
+  }
+  // in-block exclusive scan of the head flags
+  uint32_t bal = __ballot_sync(0xffffffffu, head);
+  uint32_t wpre = __popc(bal & ((1u << lane) - 1u));
+  __syncthreads();
+  if (lane == 0) s_red[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < warp) woff += s_red[w];
+  if (head) {
+    uint32_t slot = s_base + woff + wpre;
+    vox_start[slot] = (uint32_t)i;
+    vox_key[slot] = k;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    meta->n_vox = s_tot;
+    meta->n_valid = s_valid;
+    vox_start[s_tot] = s_valid;
+  }
+}
+
+// ---- host driver -------------------------------------------------------------
+struct VoxelSort {
+  DevBuf<uint32_t> keys_a, keys_b, vals_a, vals_b, hist, tile_heads, tile_valid, vox_start, vox_key, point_key;
+  DevBuf<int> mm;
+  DevBuf<SortMeta> meta;
+  int n = 0;
+
+  void release() {
+    keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); hist.release(); tile_heads.release(); tile_valid.release();
+    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release();
+  }
+
+  // enqueue: keys -> sort -> segmentation.  Afterwards (on the stream):
+  //   meta->grid / n_vox / n_valid, sorted (key, point index) in A or B (sorted_in_b), vox_start[0..n_vox], vox_key[0..n_vox)
+  cudaError_t run(cudaStream_t st, const float4* d_pts, int n_points, int is_dense, float lx, float ly, float lz, bool keep_point_keys) {
+    n = n_points;
+    cudaError_t e;
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    if ((e = keys_a.reserve(nn)) != cudaSuccess) return e;
+    if ((e = keys_b.reserve(nn)) != cudaSuccess) return e;
+    if ((e = vals_a.reserve(nn)) != cudaSuccess) return e;
+    if ((e = vals_b.reserve(nn)) != cudaSuccess) return e;
+    if ((e = vox_start.reserve(nn + 1)) != cudaSuccess) return e;
+    if ((e = vox_key.reserve(nn)) != cudaSuccess) return e;
+    if ((e = mm.reserve(8)) != cudaSuccess) return e;
+    if ((e = meta.reserve(1)) != cudaSuccess) return e;
+    if (keep_point_keys && (e = point_key.reserve(nn)) != cudaSuccess) return e;
+    int items = 4;
+    while (items < 32 && (n + kSortThreads * items - 1) / (kSortThreads * items) > 256) items *= 2;
+    const int tile = kSortThreads * items;
+    const int n_tiles = n > 0 ? (n + tile - 1) / tile : 1;
+    const int n_seg_tiles = n > 0 ? (n + 255) / 256 : 1;
+    if ((e = hist.reserve((size_t)n_tiles * kRadix)) != cudaSuccess) return e;
+    if ((e = tile_heads.reserve(n_seg_tiles)) != cudaSuccess) return e;
+    if ((e = tile_valid.reserve(n_seg_tiles)) != cudaSuccess) return e;
+
+    k_minmax_init<<<1, 32, 0, st>>>(mm.p);
+    int blocks = n > 0 ? (n + 255) / 256 : 1;
+    if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+    if (n > 0) k_minmax<<<blocks, 256, 0, st>>>(d_pts, n, is_dense, mm.p);
+    k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
+    if (n > 0) {
+      for (int pass = 0; pass < 4; ++pass) {
+        const uint32_t* ki = (pass & 1) ? keys_b.p : keys_a.p;
+        const uint32_t* vi = (pass & 1) ? vals_b.p : vals_a.p;
+        uint32_t* ko = (pass & 1) ? keys_a.p : keys_b.p;
+        uint32_t* vo = (pass & 1) ? vals_a.p : vals_b.p;
+        switch (items) {
+#define B200_SORT_PASS(IT)                                                                              \
+  case IT:                                                                                              \
+    k_sort_hist<IT><<<n_tiles, kSortThreads, 0, st>>>(ki, n, pass, meta.p, hist.p);                    \
+    k_sort_scan<<<1, kRadix, 0, st>>>(hist.p, n_tiles, pass, meta.p);                                  \
+    k_sort_scatter<IT><<<n_tiles, kSortThreads, 0, st>>>(ki, vi, ko, vo, n, pass, meta.p, hist.p);     \
+    break;
+          B200_SORT_PASS(4)
+          B200_SORT_PASS(8)
+          B200_SORT_PASS(16)
+          B200_SORT_PASS(32)
+#undef B200_SORT_PASS
+        }
+      }
+    }
+    k_seg_count<<<n_seg_tiles, 256, 0, st>>>(keys_a.p, keys_b.p, n, meta.p, tile_heads.p, tile_valid.p);
+    k_seg_scan<<<n_seg_tiles, 256, 0, st>>>(keys_a.p, keys_b.p, n, meta.p, tile_heads.p, tile_valid.p, n_seg_tiles, vox_start.p, vox_key.p);
+    return cudaGetLastError();
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,73 @@
+// b200reg — pcl::VoxelGrid<PointXYZ>::applyFilter on the device, reached through
+// PrefilteringNodelet::downsample [REF apps/prefiltering_nodelet.cpp:249-260] and
+// ScanMatchingOdometryNodelet::downsample [REF apps/scan_matching_odometry_nodelet.cpp:155-165].
+#pragma once
+#include "voxel_sort.cuh"
+
+namespace b200 {
+
+struct VgCounts {  // device-resident summary of the last filter call
+  uint32_t n_out;
+  uint32_t overflow;
+};
+
+// One thread per occupied voxel: float centroid accumulated in ascending input order (the stable
+// sort's in-voxel order), divided by float(count) — A.1 step 7.
+__global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__ pts, int n, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                                                      const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_start, const uint32_t* __restrict__ vox_key,
+                                                      unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id, uint32_t* __restrict__ out_count,
+                                                      VgCounts* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (meta->grid.overflow) {  // "Leaf size is too small for the input dataset": output = *input_
+    if (i < n) out[i] = pts[i];
+    if (i == 0) { counts->n_out = (uint32_t)n; counts->overflow = 1; }
+    return;
+  }
+  const uint32_t* vals = sorted_in_b(meta) ? vals_b : vals_a;
+  const int n_vox = (int)meta->n_vox;
+  if (i == 0 && min_points <= 1) { counts->n_out = (uint32_t)n_vox; counts->overflow = 0; }
+  if (i >= n_vox) return;
+  const uint32_t s = vox_start[i], e = vox_start[i + 1];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (uint32_t j = s; j < e; ++j) {
+    const float4 p = __ldg(pts + vals[j]);
+    ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
+  }
+  const float cnt = (float)(e - s);
+  out[i] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
+  if (out_id) out_id[i] = vox_key[i];
+  if (out_count) out_count[i] = e - s;
+}
+
+// min_points_per_voxel > 1 (never set by the reference): drop sparse voxels, keeping the order.
+// Single block; voxel counts are at most the point count.
+__global__ void __launch_bounds__(1024) k_vg_compact(const SortMeta* __restrict__ meta, unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id,
+                                                     uint32_t* __restrict__ out_count, VgCounts* __restrict__ counts) {
+  if (meta->grid.overflow) return;
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_base;
+  const int n_vox = (int)meta->n_vox;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n_vox; base += 1024) {
+    const int i = base + threadIdx.x;
+    float4 c = make_float4(0, 0, 0, 0);
+    uint32_t id = 0, cnt = 0;
+    int keep = 0;
+    if (i < n_vox) { c = out[i]; id = out_id[i]; cnt = out_count[i]; keep = cnt >= min_points; }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();  // all reads of out[] in this chunk are done before any write (dst <= i)
+    if (keep) { out[dst] = c; out_id[dst] = id; out_count[dst] = cnt; }
+    if (threadIdx.x == 1023) s_base = off + __popc(bal);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { counts->n_out = s_base; counts->overflow = 0; }
+}
+
+}  // namespace b200

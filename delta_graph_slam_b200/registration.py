@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's registration interface over the b200reg C ABI.
+
+`select_registration_method(params)` follows [REF src/hdl_graph_slam/registrations.cpp:22-124]:
+same parameter names (`registration_method`, `reg_*`), same defaults, same banners, same
+fall-back-to-NDT warning for unknown strings.  The objects it returns expose the
+pcl::Registration calls the reference makes: setInputTarget, setInputSource,
+align, hasConverged, getFinalTransformation, getFitnessScore — backed by the CUDA engine only.
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200RegError, Config, Result
+
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+class Registration:
+    """pcl::Registration<PointXYZ, PointXYZ> call surface on one b200reg handle."""
+
+    method = _lib.METHOD_NONE
+    reg_name = "Registration"
+
+    def __init__(self, device=0, **overrides):
+        L = _lib.load()
+        cfg = Config()
+        L.b200reg_default_config(self.method, C.byref(cfg))
+        cfg.device = device
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        rc = L.b200reg_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            raise B200RegError(rc, "b200reg_create failed (no usable sm_100 CUDA device?)")
+        self._n_src = 0
+        self._src_ref = None
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().b200reg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(self._h, rc)
+
+    # ---- setters used by the factory
+    def setNumThreads(self, n):  # reg_num_threads: the CUDA grid replaces OpenMP
+        self._cfg.num_threads = int(n)
+
+    def setTransformationEpsilon(self, eps):
+        self._ck(_lib.load().b200reg_set_transformation_epsilon(self._h, float(eps)))
+
+    def setMaximumIterations(self, n):
+        self._ck(_lib.load().b200reg_set_maximum_iterations(self._h, int(n)))
+
+    # ---- data
+    def setInputTarget(self, cloud):
+        c = _lib.as_cloud(cloud)
+        if len(c) == 0:  # PCL_ERROR + return: the previous target stays
+            print("[b200reg::setInputTarget] Invalid or empty point cloud dataset given!", file=sys.stderr)
+            return
+        if self._src_ref is not None and cloud is self._src_ref:
+            # keyframe = filtered; setInputTarget(keyframe) [REF apps/scan_matching_odometry_nodelet.cpp:253-254]
+            self._ck(_lib.load().b200reg_promote_source_to_target(self._h))
+            self._src_ref = None
+            self._n_src = 0
+            return
+        self._ck(_lib.load().b200reg_set_target(self._h, c.ctypes.data, len(c), 16))
+
+    def setInputSource(self, cloud):
+        c = _lib.as_cloud(cloud)
+        self._ck(_lib.load().b200reg_set_source(self._h, c.ctypes.data if len(c) else None, len(c), 16))
+        self._n_src = len(c)
+        self._src_ref = cloud
+
+    def setInputTargetDevice(self, ptr, n):
+        self._ck(_lib.load().b200reg_set_target_device(self._h, ptr, n))
+
+    def setInputSourceDevice(self, ptr, n):
+        self._ck(_lib.load().b200reg_set_source_device(self._h, ptr, n))
+        self._n_src = n
+        self._src_ref = None
+
+    def promoteSourceToTarget(self):
+        self._ck(_lib.load().b200reg_promote_source_to_target(self._h))
+        self._n_src = 0
+        self._src_ref = None
+
+    # ---- run
+    def align(self, guess=None, want_aligned=False):
+        """registration->align(*aligned, guess).  Returns the aligned cloud when asked for."""
+        g = _lib.colmajor(np.eye(4) if guess is None else guess)
+        out = np.zeros((self._n_src, 4), np.float32) if want_aligned else None
+        rc = _lib.load().b200reg_align(self._h, g.ctypes.data, out.ctypes.data if want_aligned and self._n_src else None)
+        if rc == _lib.E_STATE:  # PCL logs and returns with converged_ == false
+            print(f"[b200reg::align] {_lib.load().b200reg_last_error(self._h).decode()}", file=sys.stderr)
+            return out
+        self._ck(rc)
+        return out
+
+    # ---- results
+    def hasConverged(self):
+        v = C.c_int()
+        self._ck(_lib.load().b200reg_has_converged(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def getFinalTransformation(self):
+        T = np.zeros(16, np.float32)
+        self._ck(_lib.load().b200reg_get_final_transformation(self._h, T.ctypes.data))
+        return _lib.from_colmajor(T)
+
+    def getFinalNumIteration(self):
+        v = C.c_int()
+        self._ck(_lib.load().b200reg_get_num_iterations(self._h, C.byref(v)))
+        return v.value
+
+    def getFitnessScore(self, max_range=DBL_MAX):
+        v = C.c_double()
+        self._ck(_lib.load().b200reg_get_fitness_score(self._h, float(max_range), C.byref(v)))
+        return v.value
+
+    def calcFitnessScore(self, relpose, max_range=DBL_MAX):
+        """InformationMatrixCalculator::calc_fitness_score(target, source, relpose, max_range)."""
+        T = _lib.colmajor(relpose)
+        v = C.c_double()
+        self._ck(_lib.load().b200reg_calc_fitness_score(self._h, T.ctypes.data, float(max_range), C.byref(v)))
+        return v.value
+
+    def getInlierFraction(self, max_correspondence_dist=0.5):
+        v = C.c_double()
+        self._ck(_lib.load().b200reg_get_inlier_fraction(self._h, float(max_correspondence_dist), C.byref(v)))
+        return v.value
+
+    def getResult(self):
+        r = Result()
+        self._ck(_lib.load().b200reg_get_result(self._h, C.byref(r)))
+        return dict(transformation=_lib.from_colmajor(np.array(r.transformation[:], np.float32)), fitness=r.fitness, score=r.score, converged=bool(r.converged),
+                    iterations=r.iterations, evaluations=r.evaluations, hits=r.hits)
+
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(_lib.load().b200reg_get_stream(self._h, C.byref(p)))
+        return p.value
+
+    # ---- pcl::VoxelGrid on the same device / stream
+    def voxelgrid_filter(self, cloud, leaf, min_points_per_voxel=0, is_dense=False):
+        c = _lib.as_cloud(cloud)
+        leaf3 = (C.c_float * 3)(*((leaf,) * 3 if np.isscalar(leaf) else leaf))
+        out = np.empty((max(len(c), 1), 4), np.float32)
+        n_out = C.c_size_t()
+        self._ck(_lib.load().b200reg_voxelgrid_filter(self._h, c.ctypes.data if len(c) else None, len(c), 16, leaf3, min_points_per_voxel, int(is_dense), out.ctypes.data,
+                                                      len(out), C.byref(n_out)))
+        return out[: n_out.value].copy()
+
+    def voxelgrid_last_layout(self, n_voxels, n_points):
+        vid = np.zeros(max(n_voxels, 1), np.uint32)
+        cnt = np.zeros(max(n_voxels, 1), np.uint32)
+        key = np.zeros(max(n_points, 1), np.uint32)
+        grid = np.zeros(6, np.int32)
+        ovf = C.c_int()
+        self._ck(_lib.load().b200reg_voxelgrid_last_layout(self._h, vid.ctypes.data, cnt.ctypes.data, n_voxels, key.ctypes.data, n_points, grid.ctypes.data, C.byref(ovf)))
+        return dict(voxel_id=vid[:n_voxels], count=cnt[:n_voxels], key=key[:n_points], min_b=grid[:3], div_b=grid[3:], overflow=bool(ovf.value))
+
+
+class NormalDistributionsTransform(Registration):
+    """Replaces pclomp::NormalDistributionsTransform ("NDT_OMP") [REF registrations.cpp:105-119]."""
+
+    method = _lib.METHOD_NDT
+    reg_name = "NormalDistributionsTransform"
+
+    def setResolution(self, r):
+        self._ck(_lib.load().b200reg_set_resolution(self._h, float(r)))
+
+    def setNeighborhoodSearchMethod(self, m):
+        self._ck(_lib.load().b200reg_set_nn_search(self._h, int(m)))
+
+    def getTransformationProbability(self):
+        v = C.c_double()
+        self._ck(_lib.load().b200reg_get_transformation_probability(self._h, C.byref(v)))
+        return v.value
+
+    def ndt_leaves(self):
+        n = C.c_size_t()
+        self._ck(_lib.load().b200reg_ndt_num_leaves(self._h, C.byref(n)))
+        n = n.value
+        m = max(n, 1)
+        idx = np.zeros(m, np.uint64); npts = np.zeros(m, np.int32); mean = np.zeros((m, 3)); cov = np.zeros((m, 9)); icov = np.zeros((m, 9))
+        cen = np.zeros((m, 3), np.float32); grid = np.zeros(6, np.int32)
+        self._ck(_lib.load().b200reg_ndt_get_leaves(self._h, idx.ctypes.data, npts.ctypes.data, mean.ctypes.data, cov.ctypes.data, icov.ctypes.data, cen.ctypes.data, grid.ctypes.data))
+        return dict(idx=idx[:n], n=npts[:n], mean=mean[:n], cov=cov[:n].reshape(-1, 3, 3), icov=icov[:n].reshape(-1, 3, 3), centroid=cen[:n], min_b=grid[:3], div_b=grid[3:])
+
+    def ndt_derivatives(self, p):
+        p = np.ascontiguousarray(p, np.float64)
+        s = C.c_double(); g = np.zeros(6); H = np.zeros(36)
+        self._ck(_lib.load().b200reg_ndt_derivatives(self._h, p.ctypes.data, C.byref(s), g.ctypes.data, H.ctypes.data))
+        return s.value, g, H.reshape(6, 6)
+
+
+class FastGICP(Registration):
+    """Replaces fast_gicp::FastGICP ("FAST_GICP") [REF registrations.cpp:27-36]."""
+
+    method = _lib.METHOD_GICP
+    reg_name = "FastGICP"
+
+    def setMaxCorrespondenceDistance(self, d):
+        self._ck(_lib.load().b200reg_set_max_correspondence_distance(self._h, float(d)))
+
+    def setCorrespondenceRandomness(self, k):
+        self._ck(_lib.load().b200reg_set_correspondence_randomness(self._h, int(k)))
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid<PointXYZ> as the nodelets use it: setLeafSize + setInputCloud + filter
+    [REF apps/prefiltering_nodelet.cpp:59-63,249-260; apps/scan_matching_odometry_nodelet.cpp:85-89,155-165]."""
+
+    def __init__(self, device=0):
+        self._reg = Registration(device=device)
+        self._leaf = (0.0, 0.0, 0.0)
+        self._input = None
+        self.is_dense = False  # distance_filter marks its output is_dense = false [REF apps/prefiltering_nodelet.cpp:286]
+        self.min_points_per_voxel = 0
+
+    def setLeafSize(self, lx, ly, lz):
+        self._leaf = (float(np.float32(lx)), float(np.float32(ly)), float(np.float32(lz)))
+
+    def setInputCloud(self, cloud, is_dense=False):
+        self._input = cloud
+        self.is_dense = is_dense
+
+    def setMinimumPointsNumberPerVoxel(self, n):
+        self.min_points_per_voxel = int(n)
+
+    def filter(self):
+        return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense)
+
+    def last_layout(self, n_voxels, n_points):
+        return self._reg.voxelgrid_last_layout(n_voxels, n_points)
+
+
+def select_registration_method(params=None, device=0, out=sys.stdout):
+    """hdl_graph_slam::select_registration_method(ros::NodeHandle&) over a dict of private params."""
+    p = dict(params or {})
+    registration_method = p.get("registration_method", "NDT_OMP")
+    if registration_method == "FAST_GICP":
+        print("registration: FAST_GICP", file=out)
+        gicp = FastGICP(device=device)
+        gicp.setNumThreads(p.get("reg_num_threads", 0))
+        gicp.setTransformationEpsilon(p.get("reg_transformation_epsilon", 0.01))
+        gicp.setMaximumIterations(p.get("reg_maximum_iterations", 64))
+        gicp.setMaxCorrespondenceDistance(p.get("reg_max_correspondence_distance", 2.5))
+        gicp.setCorrespondenceRandomness(p.get("reg_correspondence_randomness", 20))
+        return gicp
+    if registration_method in ("FAST_VGICP", "FAST_VGICP_CUDA", "ICP") or "GICP" in registration_method:
+        # selectable in the reference, not on the path this engine replaces:
+        # a maintainer keeps the reference's own branch for these.
+        raise NotImplementedError(f"registration_method={registration_method} stays on the reference's CPU implementation; "
+                                  "b200reg replaces NDT_OMP and FAST_GICP")
+    if "NDT" not in registration_method:
+        print(f"warning: unknown registration type({registration_method})", file=sys.stderr)
+        print("       : use NDT", file=sys.stderr)
+    ndt_resolution = p.get("reg_resolution", 0.5)
+    if "OMP" not in registration_method and "NDT" in registration_method:
+        raise NotImplementedError("registration_method=NDT (single-thread pcl::NormalDistributionsTransform) stays on the reference's CPU implementation")
+    num_threads = p.get("reg_num_threads", 0)
+    nn_search_method = p.get("reg_nn_search_method", "DIRECT7")
+    print(f"registration: NDT_OMP {nn_search_method} {ndt_resolution:g} ({num_threads} threads)", file=out)
+    ndt = NormalDistributionsTransform(device=device)
+    if num_threads > 0:
+        ndt.setNumThreads(num_threads)
+    ndt.setTransformationEpsilon(p.get("reg_transformation_epsilon", 0.01))
+    ndt.setMaximumIterations(p.get("reg_maximum_iterations", 64))
+    ndt.setResolution(ndt_resolution)
+    if nn_search_method == "KDTREE":
+        ndt.setNeighborhoodSearchMethod(_lib.KDTREE)
+    elif nn_search_method == "DIRECT1":
+        ndt.setNeighborhoodSearchMethod(_lib.DIRECT1)
+    else:
+        ndt.setNeighborhoodSearchMethod(_lib.DIRECT7)
+    return ndt

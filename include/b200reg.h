@@ -1,0 +1,162 @@
+/* b200reg — C ABI of the B200-native scan-registration engine.
+ *
+ * Drop-in boundary for the data-parallel hot path of delta_graph_slam: the object
+ * returned by select_registration_method() [REF src/hdl_graph_slam/registrations.cpp:22-124,
+ * include/hdl_graph_slam/registrations.hpp:17] and the pcl::Filter used by
+ * PrefilteringNodelet::downsample [REF apps/prefiltering_nodelet.cpp:249-260] and
+ * ScanMatchingOdometryNodelet::downsample [REF apps/scan_matching_odometry_nodelet.cpp:155-165].
+ * That boundary is a C++ virtual interface (pcl::Registration / pcl::Filter); this header
+ * is the plain-C surface underneath it.  include/b200reg_pcl.hpp holds the header-only
+ * pcl::Registration / pcl::Filter adapters a maintainer compiles against their PCL, and
+ * INTEGRATION.md shows the factory patch.
+ *
+ * Conventions
+ *  - every call returns 0 on success or a negative B200REG_E_* code; nothing throws or
+ *    aborts (the reference's callers branch only on hasConverged() and the fitness
+ *    value [REF apps/scan_matching_odometry_nodelet.cpp:222, include/hdl_graph_slam/loop_detector.hpp:149]);
+ *  - clouds are arrays of pcl::PointXYZ: 16-byte records {float x, y, z, pad};
+ *    `stride_bytes` is the record size (16 for PointXYZ), the pad is ignored;
+ *  - 4x4 transforms are 16 floats in Eigen::Matrix4f storage order (column-major);
+ *  - host pointers may be pageable; the library stages through its own pinned buffers
+ *    on the handle's own CUDA stream.  Handles are independent (own stream, own device
+ *    memory): the odometry object and the loop-detector object of one process may run
+ *    concurrently from different threads; one handle is driven by one thread at a time.
+ *  - the library never falls back to the CPU: without a usable CUDA device
+ *    b200reg_create fails with B200REG_E_CUDA.
+ */
+#ifndef B200REG_H_
+#define B200REG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REG_OK 0
+#define B200REG_E_INVALID (-1)   /* bad argument */
+#define B200REG_E_CUDA (-2)      /* CUDA runtime error (text in b200reg_last_error) */
+#define B200REG_E_STATE (-3)     /* call order: no target / no source set */
+#define B200REG_E_CAPACITY (-4)  /* caller's output buffer too small */
+
+/* registration_method [REF src/hdl_graph_slam/registrations.cpp:26] */
+enum b200reg_method {
+  B200REG_METHOD_NONE = 0, /* filter-only handle (prefiltering nodelet) */
+  B200REG_METHOD_NDT = 1,  /* replaces pclomp::NormalDistributionsTransform ("NDT_OMP") */
+  B200REG_METHOD_GICP = 2  /* replaces fast_gicp::FastGICP ("FAST_GICP") */
+};
+/* reg_nn_search_method [REF src/hdl_graph_slam/registrations.cpp:103,112-118]; values follow pclomp::NeighborSearchMethod */
+enum b200reg_nn_search { B200REG_KDTREE = 0, B200REG_DIRECT26 = 1, B200REG_DIRECT7 = 2, B200REG_DIRECT1 = 3 };
+/* fast_gicp::RegularizationMethod */
+enum b200reg_regularization { B200REG_REG_NONE = 0, B200REG_REG_MIN_EIG = 1, B200REG_REG_NORMALIZED_MIN_EIG = 2, B200REG_REG_PLANE = 3, B200REG_REG_FROBENIUS = 4 };
+enum b200reg_lsq { B200REG_LSQ_GN = 0, B200REG_LSQ_LM = 1 };
+
+/* Launch parameters of the path.  b200reg_default_config fills
+ * the reference's code defaults for the chosen method. */
+typedef struct b200reg_config {
+  int device;                       /* CUDA device ordinal */
+  int method;                       /* enum b200reg_method */
+  double resolution;                /* reg_resolution              (NDT voxel size) */
+  int nn_search;                    /* reg_nn_search_method */
+  double transformation_epsilon;    /* reg_transformation_epsilon */
+  int maximum_iterations;           /* reg_maximum_iterations */
+  double step_size;                 /* NDT More-Thuente step_max (upstream 0.1, never set by the reference) */
+  double outlier_ratio;             /* NDT (upstream 0.55) */
+  double max_correspondence_distance; /* reg_max_correspondence_distance (GICP) */
+  int correspondence_randomness;    /* reg_correspondence_randomness   (GICP k-NN size) */
+  double rotation_epsilon;          /* GICP (upstream 2e-3) */
+  int regularization;               /* GICP (upstream PLANE) */
+  int lsq_optimizer;                /* GICP (upstream LM) */
+  int num_threads;                  /* reg_num_threads: accepted and ignored (the CUDA grid replaces OpenMP) */
+} b200reg_config;
+
+typedef struct b200reg_handle b200reg_handle;
+
+/* Result record of one registration (also the unit gathered across GPUs for loop batches). */
+typedef struct b200reg_result {
+  float transformation[16]; /* getFinalTransformation(), column-major */
+  double fitness;           /* getFitnessScore(max_range) if requested, else 0 */
+  double score;             /* NDT: getTransformationProbability(); GICP: last sum of errors */
+  int32_t converged;        /* hasConverged() */
+  int32_t iterations;       /* getFinalNumIteration() */
+  int32_t evaluations;      /* derivative passes (NDT) / linearize + error passes (GICP) */
+  int32_t reserved;
+  int64_t hits;             /* (point, voxel) pairs visited (NDT) / correspondences evaluated (GICP) */
+} b200reg_result;
+
+void b200reg_default_config(int method, b200reg_config* out);
+int b200reg_create(const b200reg_config* cfg, b200reg_handle** out);
+int b200reg_destroy(b200reg_handle* h);
+const char* b200reg_last_error(const b200reg_handle* h);
+const char* b200reg_version(void);
+
+/* setters used by the factory after construction [REF src/hdl_graph_slam/registrations.cpp:30-34,106-118] */
+int b200reg_set_resolution(b200reg_handle* h, double resolution);
+int b200reg_set_nn_search(b200reg_handle* h, int nn_search);
+int b200reg_set_transformation_epsilon(b200reg_handle* h, double eps);
+int b200reg_set_maximum_iterations(b200reg_handle* h, int n);
+int b200reg_set_max_correspondence_distance(b200reg_handle* h, double d);
+int b200reg_set_correspondence_randomness(b200reg_handle* h, int k);
+
+/* pcl::Registration::setInputTarget / setInputSource
+ * [REF apps/scan_matching_odometry_nodelet.cpp:180,185,254; include/hdl_graph_slam/loop_detector.hpp:124,138].
+ * An empty target is an error that leaves the previous target in place (PCL_ERROR + return). */
+int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes);
+int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes);
+/* same, for clouds already resident on the handle's device (bench "value" leg, device pipelines) */
+int b200reg_set_target_device(b200reg_handle* h, const float* d_xyzw, size_t n);
+int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n);
+/* keyframe = filtered; registration->setInputTarget(keyframe)
+ * [REF apps/scan_matching_odometry_nodelet.cpp:253-254]: the current source becomes the target
+ * without leaving the device (same result as b200reg_set_target on the same cloud). */
+int b200reg_promote_source_to_target(b200reg_handle* h);
+
+/* pcl::Registration::align(output, guess) [REF apps/scan_matching_odometry_nodelet.cpp:218;
+ * include/hdl_graph_slam/loop_detector.hpp:145].  guess == NULL means identity.
+ * aligned_xyzw (optional, host, n_source * 16 bytes) receives the transformed source. */
+int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw);
+
+int b200reg_has_converged(b200reg_handle* h, int* out);
+int b200reg_get_final_transformation(b200reg_handle* h, float* out16);
+int b200reg_get_num_iterations(b200reg_handle* h, int* out);
+int b200reg_get_transformation_probability(b200reg_handle* h, double* out);
+int b200reg_get_result(b200reg_handle* h, b200reg_result* out);
+/* pcl::Registration::getFitnessScore(max_range) [REF include/hdl_graph_slam/loop_detector.hpp:148;
+ * apps/scan_matching_odometry_nodelet.cpp:318; src/hdl_graph_slam/information_matrix_calculator.cpp:77-108] */
+int b200reg_get_fitness_score(b200reg_handle* h, double max_range, double* out);
+/* InformationMatrixCalculator::calc_fitness_score(cloud1 = target, cloud2 = source, relpose, max_range)
+ * [REF src/hdl_graph_slam/information_matrix_calculator.cpp:77-108]: same loop as getFitnessScore with an
+ * explicit transform (column-major float 4x4) instead of the last align result. */
+int b200reg_calc_fitness_score(b200reg_handle* h, const float* relpose16, double max_range, double* out);
+/* inlier fraction of publish_scan_matching_status [REF apps/scan_matching_odometry_nodelet.cpp:320-332] */
+int b200reg_get_inlier_fraction(b200reg_handle* h, double max_correspondence_dist, double* out);
+
+/* pcl::VoxelGrid<PointXYZ>::filter [REF apps/prefiltering_nodelet.cpp:59-63,249-260;
+ * apps/scan_matching_odometry_nodelet.cpp:85-89,155-165].  Works on any handle (METHOD_NONE for a
+ * filter-only object).  out has room for out_capacity points; *n_out receives the count.
+ * PCL's "leaf size too small" overflow guard is reproduced: the output is then the input copy. */
+int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, const float leaf[3], unsigned min_points_per_voxel,
+                             int input_is_dense, float* out_xyzw, size_t out_capacity, size_t* n_out);
+/* device-resident variant: d_out must hold n points; *n_out is written on the host after a stream sync */
+int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_points_per_voxel, int input_is_dense,
+                                    float* d_out_xyzw, size_t* n_out);
+/* introspection of the last filter call (parity tests): per output voxel linear index and point
+ * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
+int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);
+
+/* introspection of the NDT target grid (parity tests): number of occupied voxels, then per
+ * voxel (ascending linear index): index, point count (-1 = rejected by the eigenvalue test),
+ * mean[3], cov[9], icov[9] (row-major doubles), centroid[3] floats.  Any pointer may be NULL. */
+int b200reg_ndt_num_leaves(b200reg_handle* h, size_t* out);
+int b200reg_ndt_get_leaves(b200reg_handle* h, uint64_t* idx, int32_t* n, double* mean3, double* cov9, double* icov9, float* centroid3, int32_t* grid6);
+/* score / gradient / Hessian of the current source at pose p = [t, eulerXYZ] (one derivative pass) */
+int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score, double g[6], double H[36]);
+
+/* raw CUDA stream of the handle (cudaStream_t) so a host can time or order work against it */
+int b200reg_get_stream(b200reg_handle* h, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REG_H_ */

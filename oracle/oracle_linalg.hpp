@@ -239,8 +239,12 @@ inline M4f m4f_mul_affine(const M4f& a, const M4f& b) {
 // parameter vector (ndt_omp builds Eigen::Translation<float>/AngleAxis<float>
 // from static_cast<float>(p(i))).
 inline M4f m4f_from_xyz_euler(const double p[6]) {
+  // float trig evaluated as the float rounding of the double function: correctly rounded in
+  // all but ~1e-9 of cases, where glibc's cosf/sinf (what Eigen::AngleAxisf calls) may differ
+  // by one ulp; chosen so the CUDA engine can reproduce the same bits.
   float rx = (float)p[3], ry = (float)p[4], rz = (float)p[5];
-  float cx = std::cos(rx), sx = std::sin(rx), cy = std::cos(ry), sy = std::sin(ry), cz = std::cos(rz), sz = std::sin(rz);
+  float cx = (float)std::cos((double)rx), sx = (float)std::sin((double)rx), cy = (float)std::cos((double)ry), sy = (float)std::sin((double)ry);
+  float cz = (float)std::cos((double)rz), sz = (float)std::sin((double)rz);
   M4f T = m4f_identity(), Rx = m4f_identity(), Ry = m4f_identity(), Rz = m4f_identity();
   T(0, 3) = (float)p[0]; T(1, 3) = (float)p[1]; T(2, 3) = (float)p[2];
   Rx(1, 1) = cx; Rx(1, 2) = -sx; Rx(2, 1) = sx; Rx(2, 2) = cx;

@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same
+seeded synthetic scans.  Bars (BASELINE.json): voxel assignment / counts / order bit-exact;
+final transforms within 1e-4 m / 1e-4 rad; fitness within 1e-5 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-4    # metres
+TOL_R = 1e-4    # radians
+TOL_FIT = 1e-5  # relative
+
+
+def rot_angle(Ra, Rb):
+    R = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import delta_graph_slam_b200 as d
+    return d
+
+
+def test_voxelgrid_bit_exact(eng, oracle, scans):
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    for raw in (scans["raw0"], scans["raw1"]):
+        ref = oracle.voxelgrid(raw, 0.1, is_dense=False)
+        vg.setInputCloud(raw, is_dense=False)
+        out = vg.filter()
+        lay = vg.last_layout(len(out), len(raw))
+        assert len(out) == len(ref["out"])
+        assert np.array_equal(lay["min_b"], ref["min_b"]) and np.array_equal(lay["div_b"], ref["div_b"])
+        assert np.array_equal(lay["key"], ref["key"]), "per-point voxel assignment must be bit-exact"
+        assert np.array_equal(lay["voxel_id"], ref["voxel_id"]), "output order (ascending voxel index) must be bit-exact"
+        assert np.array_equal(lay["count"], ref["count"]), "per-voxel point counts must be bit-exact"
+        # both sides sum in ascending input order without contraction -> identical bits
+        assert np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+
+
+def test_voxelgrid_edge_cases(eng, oracle):
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    # empty
+    vg.setInputCloud(np.zeros((0, 4), np.float32))
+    assert len(vg.filter()) == 0
+    # single point, duplicates, NaN rows skipped when !is_dense
+    rng = np.random.default_rng(3)
+    pts = np.ones((1000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-5, 5, (1000, 3)).astype(np.float32)
+    pts[::7, 1] = np.nan
+    pts[5::31, 0] = np.inf
+    pts[10:20] = pts[9]
+    ref = oracle.voxelgrid(pts, 0.25, is_dense=False)
+    vg.setLeafSize(0.25, 0.25, 0.25)
+    vg.setInputCloud(pts, is_dense=False)
+    out = vg.filter()
+    lay = vg.last_layout(len(out), len(pts))
+    assert np.array_equal(lay["key"], ref["key"])
+    assert np.array_equal(lay["count"], ref["count"])
+    assert np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+    # leaf too small for the extent: PCL returns the input unfiltered
+    far = np.ones((4, 4), np.float32)
+    far[:, :3] = [[0, 0, 0], [4000, 0, 0], [0, 4000, 0], [0, 0, 4000]]
+    vg.setLeafSize(0.001, 0.001, 0.001)
+    vg.setInputCloud(far, is_dense=True)
+    out = vg.filter()
+    ref = oracle.voxelgrid(far, 0.001, is_dense=True)
+    assert ref["overflow"] and len(out) == 4 and np.array_equal(out, far)
+    # anisotropic leaf + min_points_per_voxel
+    ref = oracle.voxelgrid(pts, (0.5, 0.25, 1.0), min_points_per_voxel=2, is_dense=False)
+    vg.setLeafSize(0.5, 0.25, 1.0)
+    vg.setMinimumPointsNumberPerVoxel(2)
+    vg.setInputCloud(pts, is_dense=False)
+    out = vg.filter()
+    assert len(out) == len(ref["out"]) and np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+
+
+def test_ndt_target_grid(eng, oracle, scans):
+    ref = oracle.Registration(oracle.NDT, resolution=1.0)
+    ref.setInputTarget(scans["ds0"])
+    L = ref.ndt_leaves()
+    ndt = eng.NormalDistributionsTransform()
+    ndt.setResolution(1.0)
+    ndt.setInputTarget(scans["ds0"])
+    G = ndt.ndt_leaves()
+    assert np.array_equal(G["min_b"], L["min_b"]) and np.array_equal(G["div_b"], L["div_b"])
+    assert np.array_equal(G["idx"], L["idx"]), "occupied voxel set must be bit-exact"
+    assert np.array_equal(G["n"], L["n"]), "per-voxel counts / validity must be bit-exact"
+    valid = L["n"] >= 6
+    assert valid.sum() > 1000
+    np.testing.assert_allclose(G["mean"], L["mean"], rtol=0, atol=1e-12)
+    scale = np.abs(L["cov"][valid]).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(G["cov"][valid] - L["cov"][valid]) / scale) < 1e-9
+    scale = np.abs(L["icov"][valid]).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(G["icov"][valid] - L["icov"][valid]) / scale) < 1e-7
+
+
+@pytest.mark.parametrize("search", ["DIRECT7", "DIRECT1", "KDTREE", "DIRECT26"])
+def test_ndt_derivatives(eng, oracle, scans, search):
+    code = dict(KDTREE=0, DIRECT26=1, DIRECT7=2, DIRECT1=3)[search]
+    ref = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=code)
+    ref.setInputTarget(scans["ds0"])
+    ref.setInputSource(scans["ds1"])
+    ndt = eng.NormalDistributionsTransform()
+    ndt.setResolution(1.0)
+    ndt.setNeighborhoodSearchMethod(code)
+    ndt.setInputTarget(scans["ds0"])
+    ndt.setInputSource(scans["ds1"])
+    for p in ([0, 0, 0, 0, 0, 0], [1.0, 0.0, 0.0, 0.0, 0.0, 0.0063], [0.4, -0.1, 0.03, 0.01, -0.02, 0.05], [0.9, 0.05, 0.0, 3.13, 3.12, -3.1]):
+        p = np.array(p, np.float64)
+        s0, g0, H0 = ref.ndt_derivatives(p)
+        s1, g1, H1 = ndt.ndt_derivatives(p)
+        assert abs(s1 - s0) <= 2e-6 * abs(s0)
+        assert np.max(np.abs(g1 - g0)) <= 2e-6 * np.max(np.abs(g0)) + 1e-3
+        assert np.max(np.abs(H1 - H0)) <= 2e-6 * np.max(np.abs(H0))
+
+
+@pytest.mark.parametrize("search", ["DIRECT7", "DIRECT1", "KDTREE"])
+def test_ndt_align_parity(eng, oracle, scans, search):
+    code = dict(KDTREE=0, DIRECT7=2, DIRECT1=3)[search]
+    ref = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=code, trans_eps=0.01, max_iter=64)
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method=search))
+    ref.setInputTarget(scans["ds0"])
+    ndt.setInputTarget(scans["ds0"])
+    ref.setInputSource(scans["ds1"])
+    ndt.setInputSource(scans["ds1"])
+    yaw = 0.01
+    guess = np.eye(4, dtype=np.float32)
+    guess[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+    guess[:3, 3] = [0.7, 0.05, 0.0]
+    for g in (None, guess):
+        ref.align(g)
+        aligned = ndt.align(g, want_aligned=True)
+        T0, T1 = ref.getFinalTransformation(), ndt.getFinalTransformation()
+        assert ndt.hasConverged() == ref.hasConverged()
+        assert ndt.getFinalNumIteration() == ref.getFinalNumIteration(), "same Newton / line-search path"
+        assert np.max(np.abs(T1[:3, 3] - T0[:3, 3])) < TOL_T
+        assert rot_angle(T0[:3, :3], T1[:3, :3]) < TOL_R
+        info = ref.info()
+        res = ndt.getResult()
+        assert res["evaluations"] == int(info[1])
+        assert abs(res["score"] - info[0]) <= 1e-5 * abs(info[0])
+        # aligned cloud = final transform applied to the source
+        ref_al = (scans["ds1"][:, :3] @ T1[:3, :3].T + T1[:3, 3]).astype(np.float32)
+        assert np.max(np.abs(aligned[:, :3] - ref_al)) < 1e-4
+        f0, f1 = ref.getFitnessScore(), ndt.getFitnessScore()
+        assert abs(f1 - f0) <= TOL_FIT * f0
+        f0, f1 = ref.getFitnessScore(4.0), ndt.getFitnessScore(4.0)
+        assert abs(f1 - f0) <= TOL_FIT * f0
+
+
+def test_ndt_recovers_ground_truth(eng, scans):
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0))
+    ndt.setInputTarget(scans["ds0"])
+    ndt.setInputSource(scans["ds1"])
+    ndt.align(None)
+    T = ndt.getFinalTransformation()
+    gt = scans["gt"]
+    assert np.max(np.abs(T[:3, 3] - gt[:3, 3])) < 0.02
+    assert rot_angle(T[:3, :3], gt[:3, :3].astype(np.float32)) < np.deg2rad(0.1)
+
+
+def test_fitness_exact_nn(eng, oracle, scans):
+    """Same transform on both sides: the exact-NN fitness must agree to rounding of the double sum."""
+    ref = oracle.Registration(oracle.NDT, resolution=1.0)
+    reg = eng.NormalDistributionsTransform()
+    ref.setInputTarget(scans["ds0"])
+    reg.setInputTarget(scans["ds0"])
+    ref.setInputSource(scans["ds1"])
+    reg.setInputSource(scans["ds1"])
+    # identity (final_transformation_ before any align) and far-off transforms exercise the
+    # ring search, the max_range gate and the brute-force pass for far outliers
+    assert abs(reg.getFitnessScore() - ref.getFitnessScore()) <= 1e-12 * ref.getFitnessScore()
+    idx, d2 = oracle.knn(scans["ds0"], scans["ds1"], 1)
+    for T in (np.eye(4), scans["gt"], np.array([[1, 0, 0, 30.0], [0, 1, 0, -20.0], [0, 0, 1, 5.0], [0, 0, 0, 1]])):
+        T = np.asarray(T, np.float32)
+        q = np.ones_like(scans["ds1"])
+        # float transform in pcl::transformPoint order
+        for r in range(3):
+            q[:, r] = ((T[r, 0] * scans["ds1"][:, 0] + T[r, 1] * scans["ds1"][:, 1]) + T[r, 2] * scans["ds1"][:, 2]) + T[r, 3]
+        _, d2 = oracle.knn(scans["ds0"], q, 1)
+        d2 = d2[:, 0].astype(np.float64)
+        for max_range in (np.finfo(np.float64).max, 1.0, 0.01):
+            sel = d2 <= max_range
+            want = d2[sel].sum() / sel.sum() if sel.any() else np.finfo(np.float64).max
+            got = reg.calcFitnessScore(T, max_range)
+            assert abs(got - want) <= 1e-12 * want
+        frac = reg.getInlierFraction(0.5)
+        assert 0.0 <= frac <= 1.0
+
+
+def test_odometry_keyframe_promotion(eng, oracle, scans):
+    """setInputTarget(keyframe = last source) must equal uploading the same cloud again."""
+    a = eng.NormalDistributionsTransform()
+    b = eng.NormalDistributionsTransform()
+    for r in (a, b):
+        r.setResolution(1.0)
+        r.setInputTarget(scans["ds0"])
+    src = scans["ds1"]
+    a.setInputSource(src)
+    a.setInputTarget(src)          # promoted on the device
+    b.setInputTarget(src.copy())   # uploaded
+    La, Lb = a.ndt_leaves(), b.ndt_leaves()
+    assert np.array_equal(La["idx"], Lb["idx"]) and np.array_equal(La["n"], Lb["n"])
+    assert np.array_equal(La["icov"], Lb["icov"])
