@@ -8,7 +8,8 @@ the C ABI in include/b200reg.h); this package is the thin host mirror used by te
 """
 from . import _lib
 from ._lib import B200RegError, DIRECT1, DIRECT7, DIRECT26, KDTREE
-from .registration import DBL_MAX, FastGICP, NormalDistributionsTransform, Registration, VoxelGrid, select_registration_method
+from .odometry import Prefilter, ScanMatchingOdometry
+from .registration import DBL_MAX, DeviceCloud, FastGICP, NormalDistributionsTransform, Registration, VoxelGrid, select_registration_method
 
-__all__ = ["B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "FastGICP", "NormalDistributionsTransform", "Registration", "VoxelGrid",
+__all__ = ["B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "Registration", "VoxelGrid",
            "select_registration_method"]

@@ -27,7 +27,7 @@ EXPORTS = [
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
-    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_get_stream",
+    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_get_stream",
 ]
 
 
@@ -96,6 +96,9 @@ def load():
     L.b200reg_ndt_num_leaves.argtypes = [vp, szp]
     L.b200reg_ndt_get_leaves.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, C.POINTER(C.c_double), vp, vp]
+    L.b200reg_get_profile.argtypes = [vp, vp]
+    L.b200reg_set_timing.argtypes = [vp, C.c_int]
+    L.b200reg_get_counters.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.b200reg_get_stream.argtypes = [vp, C.POINTER(vp)]
     # synthetic scan generator (bench / test infrastructure living in the same library)
     L.b200synth_num_rays.argtypes = [C.c_int]

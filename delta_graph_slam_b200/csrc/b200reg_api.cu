@@ -39,6 +39,7 @@ struct b200reg_handle {
   DevBuf<NdtJob> jobs;
   DevBuf<b200reg_result> d_result;
   DevBuf<double> partials, deriv;
+  DevBuf<long long> prof;
   DevBuf<unsigned int> barriers;
   PinnedBuf<unsigned char> pin_small;  // results / jobs staging
 
@@ -49,6 +50,12 @@ struct b200reg_handle {
 
   b200reg_result last;
   bool have_result = false;
+
+  // optional device timing of the align kernel (bench.py roofline leg)
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double align_ms = 0.0;
+  long long n_align = 0;
 
   void set_error(const std::string& s) { err = s; }
 };
@@ -147,7 +154,10 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
   void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers};
-  return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, 0, h->stream);
+  // the staged target grid lives in opt-in dynamic shared memory (one CTA per SM)
+  cudaError_t e = cudaFuncSetAttribute((const void*)k_ndt_align<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 
 cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups) {
@@ -168,6 +178,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   B200_CUDA_TRY(h->jobs.reserve(1));
   B200_CUDA_TRY(h->d_result.reserve(1));
   B200_CUDA_TRY(h->deriv.reserve(64));
+  B200_CUDA_TRY(h->prof.reserve(8));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
   B200_CUDA_TRY(h->barriers.reserve(32));
   B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
@@ -178,6 +189,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   job->grid = h->grid.view();
   job->result = h->d_result.p;
   job->deriv_out = h->deriv.p;
+  job->prof = h->prof.p;
   if (p_eval) {
     job->eval_only = 1;
     for (int i = 0; i < 6; ++i) job->p0[i] = p_eval[i];
@@ -193,7 +205,10 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   }
   B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, job, sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
   B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 32 * sizeof(unsigned int), h->stream));
+  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1));
+  launch_counter() += 1;
+  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   return B200REG_OK;
 }
 
@@ -204,6 +219,12 @@ int fetch_result(b200reg_handle* h) {
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->last = *pr;
   h->have_result = true;
+  if (h->timing) {
+    float ms = 0.f;
+    B200_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->align_ms += (double)ms;
+    h->n_align += 1;
+  }
   return B200REG_OK;
 }
 
@@ -258,9 +279,11 @@ int b200reg_destroy(b200reg_handle* h) {
   if (!h) return B200REG_E_INVALID;
   cudaSetDevice(h->cfg.device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release();
-  h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release();
+  h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
   delete h;
   return B200REG_OK;
@@ -370,6 +393,7 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
   if (aligned_xyzw) {
     B200_CUDA_TRY(h->aligned.reserve(h->n_src));
     B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
+    launch_counter() += 1;
     k_transform_cloud<<<(h->n_src + 255) / 256, 256, 0, h->stream>>>(h->src.p, h->n_src, h->d_result.p, h->aligned.p);
     B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -468,6 +492,7 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_counts.reserve(1));
   B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
+  launch_counter() += 1 + (min_pts > 1 ? 1 : 0);
   k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
                                                 min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
   if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
@@ -591,6 +616,40 @@ int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score,
   if (score) *score = pd[0];
   if (g) memcpy(g, pd + 1, 6 * sizeof(double));
   if (H) memcpy(H, pd + 7, 36 * sizeof(double));
+  return B200REG_OK;
+}
+
+int b200reg_set_timing(b200reg_handle* h, int on) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (on && !h->ev0) {
+    B200_CUDA_TRY(cudaEventCreate(&h->ev0));
+    B200_CUDA_TRY(cudaEventCreate(&h->ev1));
+  }
+  h->timing = on != 0;
+  h->align_ms = 0.0;
+  h->n_align = 0;
+  return B200REG_OK;
+}
+
+int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long* timed_aligns, double* align_kernel_ms) {
+  if (!h) return B200REG_E_INVALID;
+  if (launches_total) *launches_total = launch_counter().load();
+  if (timed_aligns) *timed_aligns = h->n_align;
+  if (align_kernel_ms) *align_kernel_ms = h->align_ms;
+  return B200REG_OK;
+}
+
+int b200reg_get_profile(b200reg_handle* h, long long* out6) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out6) return B200REG_E_INVALID;
+  if (!h->prof.p) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 7 * sizeof(long long), cudaMemcpyDeviceToHost));
   return B200REG_OK;
 }
 

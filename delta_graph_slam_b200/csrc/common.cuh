@@ -4,11 +4,18 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 
 namespace b200 {
 
 constexpr int kNumSM = 148;  // B200; grids are sized in multiples of the SM count
+
+// kernels launched by this library since load (bench.py reports it as gpu_launches)
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
 
 #define B200_CUDA_TRY(expr)                                                                  \
   do {                                                                                       \

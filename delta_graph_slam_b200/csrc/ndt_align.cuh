@@ -9,13 +9,17 @@
 // Newton solve and the More-Thuente line search happen on the device, so an iteration costs no
 // host round trip.  A *group* of G CTAs owns one registration (G = all 148 SMs for a single
 // odometry alignment, a handful for loop-closure batches where many groups run side by side):
+//   stage  : the target's voxel hash + 48-byte voxel records are copied into shared memory once
+//            per registration (they fit the 227 KB of an SM for HDL-64-sized scans; larger grids
+//            are read through L2 instead)
 //   pass   : each thread transforms its source points (float, same operation order as
-//            pcl::transformPoint), probes the DIRECT1/7/26 (or KDTREE-radius) voxels through
-//            the target hash, and accumulates score / gradient / Hessian
+//            pcl::transformPoint), probes the DIRECT1/7/26 (or KDTREE-radius) voxels and
+//            accumulates score / gradient / Hessian; 32-point groups are dealt round-robin to
+//            the group's warps so dense and empty regions of the scan are spread over all SMs
 //   reduce : warp shuffles -> shared memory -> one 29-double partial per CTA in global memory
 //   sync   : a counter barrier among the group's CTAs (co-residency guaranteed by the
 //            cooperative launch), then EVERY CTA sums the partials in the same fixed order
-//   step   : every CTA runs the Newton / More-Thuente state machine redundantly on the
+//   step   : warp 0 of every CTA runs the Newton / More-Thuente state machine redundantly on the
 //            identical totals — bit-identical decisions, so no broadcast and no second barrier.
 //
 // Per-hit arithmetic is float and the sums are double, as upstream.  The per-hit Hessian is
@@ -26,12 +30,15 @@
 #pragma once
 #include "../../include/b200reg.h"
 #include "ndt_grid.cuh"
+#include "small_solve.cuh"
 
 namespace b200 {
 
 constexpr int kAlignThreads = 512;
+constexpr int kAlignWarps = kAlignThreads / 32;
 constexpr int kNumAcc = 29;  // score, g[6], H upper triangle [21], hits
 constexpr int kAccStride = 32;
+constexpr int kStageBytes = 192 * 1024;  // dynamic shared memory for the staged grid
 
 enum NdtPhase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_ITER = 2, PH_HESSIAN = 3, PH_DONE = 4, PH_EVAL_ONLY = 5 };
 
@@ -50,6 +57,7 @@ struct NdtJob {
   int eval_only;    // 1: a single derivative pass at p0 (introspection), T built from p0
   b200reg_result* result;  // device
   double* deriv_out;       // device, 1 + 6 + 36 doubles (eval_only)
+  long long* prof;         // device, optional: SM cycles of CTA 0 per phase {pass, reduce, barrier, total, step, n, stage}
 };
 
 struct NdtShared {
@@ -59,6 +67,7 @@ struct NdtShared {
   float h_ang[15][3];
   int need_hessian;
   int phase;
+  int new_pose;  // the step asked for an evaluation at a new x_t (T / tables must be rebuilt)
   // optimiser state (identical in every CTA of the group)
   double p[6], x_t[6], dir[6];
   double score, g[6], H[36];
@@ -67,18 +76,37 @@ struct NdtShared {
   int nr_iterations, converged, n_eval;
   double hits;
   double gauss_d1, gauss_d2;
+  double trig[6][2];  // sin, cos of: float-rounded angles (T) [0..2], double angles (tables) [3..5]
   double tot[kAccStride];
-  double red[kAlignThreads / 32][kAccStride];
+  double red[kAlignWarps][kAccStride];
 };
+
+// staged (or global) view of the target grid used inside a pass
+struct NdtLookup {
+  const uint2* table;
+  uint32_t mask;
+  const NdtVoxel* voxels;
+  const float4* centroids;
+};
+
+__device__ __forceinline__ int ndt_lookup(const NdtLookup& g, uint32_t key) {
+  uint32_t h = ndt_hash(key, g.mask);
+  while (true) {
+    const uint2 e = g.table[h];
+    if (e.x == key) return (int)e.y;
+    if (e.x == kInvalidKey) return -1;
+    h = (h + 1) & g.mask;
+  }
+}
 
 // ---- the pose -> transform / angle-derivative tables ---------------------------------------
 // T = Translation(p0..2) * Rx(p3) * Ry(p4) * Rz(p5) composed in float exactly like the oracle's
 // m4f_from_xyz_euler (sequence of float 4x4 products with exact zeros and ones collapsed).
-__device__ inline void pose_to_T(const double p[6], float T[12]) {
-  const float rx = (float)p[3], ry = (float)p[4], rz = (float)p[5];
-  const float cx = (float)cos((double)rx), sx = (float)sin((double)rx);
-  const float cy = (float)cos((double)ry), sy = (float)sin((double)ry);
-  const float cz = (float)cos((double)rz), sz = (float)sin((double)rz);
+// trig[0..2] = {sin, cos} of the float-rounded angles, evaluated in double.
+__device__ inline void pose_to_T(const double p[6], const double trig[6][2], float T[12]) {
+  const float sx = (float)trig[0][0], cx = (float)trig[0][1];
+  const float sy = (float)trig[1][0], cy = (float)trig[1][1];
+  const float sz = (float)trig[2][0], cz = (float)trig[2][1];
   const float b10 = __fmul_rn(sx, sy), b12 = -__fmul_rn(sx, cy), b20 = -__fmul_rn(cx, sy), b22 = __fmul_rn(cx, cy);
   T[0] = __fmul_rn(cy, cz); T[1] = -__fmul_rn(cy, sz); T[2] = sy; T[3] = (float)p[0];
   T[4] = __fadd_rn(__fmul_rn(b10, cz), __fmul_rn(cx, sz));
@@ -90,49 +118,73 @@ __device__ inline void pose_to_T(const double p[6], float T[12]) {
 }
 
 // computeAngleDerivatives (A.4): rows of j_ang (8) and h_ang (15) as float; evaluated in double
-// without contraction so the float casts match the oracle.
-__device__ inline void angle_tables(const double p[6], float j_ang[8][3], float h_ang[15][3]) {
-  double cx, cy, cz, sx, sy, sz;
-  if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
-  if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
-  if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
-#define M2(a, b) __dmul_rn(a, b)
-#define M3(a, b, c) __dmul_rn(__dmul_rn(a, b), c)
+// without contraction, sharing sub-products in the order the reference forms them
+// ((a*b)*c), so the float casts match a CPU evaluation of the original expressions.
+// trig[3..5] = {sin, cos} of p[3..5] with the |angle| < 10e-5 -> (0, 1) shortcut applied.
+__device__ inline void angle_tables(const double trig[6][2], float j_ang[8][3], float h_ang[15][3]) {
+  const double sx = trig[3][0], cx = trig[3][1], sy = trig[4][0], cy = trig[4][1], sz = trig[5][0], cz = trig[5][1];
+#define MU(a, b) __dmul_rn(a, b)
 #define AD(a, b) __dadd_rn(a, b)
 #define SB(a, b) __dsub_rn(a, b)
-  const double j[8][3] = {
-      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M2(-sx, cz), M3(cx, sy, sz)), M2(-cx, cy)},
-      {AD(M2(cx, sz), M3(sx, sy, cz)), SB(M2(cx, cz), M3(sx, sy, sz)), M2(-sx, cy)},
-      {M2(-sy, cz), M2(sy, sz), cy},
-      {M3(sx, cy, cz), M3(-sx, cy, sz), M2(sx, sy)},
-      {M3(-cx, cy, cz), M3(cx, cy, sz), M2(-cx, sy)},
-      {M2(-cy, sz), M2(-cy, cz), 0.0},
-      {SB(M2(cx, cz), M3(sx, sy, sz)), SB(M2(-cx, sz), M3(sx, sy, cz)), 0.0},
-      {AD(M2(sx, cz), M3(cx, sy, sz)), SB(M3(cx, sy, cz), M2(sx, sz)), 0.0}};
-  const double h[15][3] = {
-      {SB(M2(-cx, sz), M3(sx, sy, cz)), AD(M2(-cx, cz), M3(sx, sy, sz)), M2(sx, cy)},
-      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M3(-cx, sy, sz), M2(sx, cz)), M2(-cx, cy)},
-      {M3(cx, cy, cz), M3(-cx, cy, sz), M2(cx, sy)},
-      {M3(sx, cy, cz), M3(-sx, cy, sz), M2(sx, sy)},
-      {SB(M2(-sx, cz), M3(cx, sy, sz)), SB(M2(sx, sz), M3(cx, sy, cz)), 0.0},
-      {SB(M2(cx, cz), M3(sx, sy, sz)), SB(M3(-sx, sy, cz), M2(cx, sz)), 0.0},
-      {M2(-cy, cz), M2(cy, sz), sy},  // d1: upstream's (+sy), kept
-      {M3(-sx, sy, cz), M3(sx, sy, sz), M2(sx, cy)},
-      {M3(cx, sy, cz), M3(-cx, sy, sz), M2(-cx, cy)},
-      {M2(sy, sz), M2(sy, cz), 0.0},
-      {M3(-sx, cy, sz), M3(-sx, cy, cz), 0.0},
-      {M3(cx, cy, sz), M3(cx, cy, cz), 0.0},
-      {M2(-cy, cz), M2(cy, sz), 0.0},
-      {SB(M2(-cx, sz), M3(sx, sy, cz)), AD(M2(-cx, cz), M3(sx, sy, sz)), 0.0},
-      {AD(M2(-sx, sz), M3(cx, sy, cz)), SB(M3(-cx, sy, sz), M2(sx, cz)), 0.0}};
-#undef M2
-#undef M3
+  const double cxsy = MU(cx, sy), sxsy = MU(sx, sy), cxcy = MU(cx, cy), sxcy = MU(sx, cy);
+  const double cxsycz = MU(cxsy, cz), cxsysz = MU(cxsy, sz), sxsycz = MU(sxsy, cz), sxsysz = MU(sxsy, sz);
+  const double cxcycz = MU(cxcy, cz), cxcysz = MU(cxcy, sz), sxcycz = MU(sxcy, cz), sxcysz = MU(sxcy, sz);
+  const double sxsz = MU(sx, sz), sxcz = MU(sx, cz), cxsz = MU(cx, sz), cxcz = MU(cx, cz);
+  const double sycz = MU(sy, cz), sysz = MU(sy, sz), cysz = MU(cy, sz), cycz = MU(cy, cz);
+  const double j[8][3] = {{AD(-sxsz, cxsycz), SB(-sxcz, cxsysz), -cxcy},
+                          {AD(cxsz, sxsycz), SB(cxcz, sxsysz), -sxcy},
+                          {-sycz, sysz, cy},
+                          {sxcycz, -sxcysz, sxsy},
+                          {-cxcycz, cxcysz, -cxsy},
+                          {-cysz, -cycz, 0.0},
+                          {SB(cxcz, sxsysz), SB(-cxsz, sxsycz), 0.0},
+                          {AD(sxcz, cxsysz), SB(cxsycz, sxsz), 0.0}};
+  const double h[15][3] = {{SB(-cxsz, sxsycz), AD(-cxcz, sxsysz), sxcy},
+                           {AD(-sxsz, cxsycz), SB(-cxsysz, sxcz), -cxcy},
+                           {cxcycz, -cxcysz, cxsy},
+                           {sxcycz, -sxcysz, sxsy},
+                           {SB(-sxcz, cxsysz), SB(sxsz, cxsycz), 0.0},
+                           {SB(cxcz, sxsysz), SB(-sxsycz, cxsz), 0.0},
+                           {-cycz, cysz, sy},  // d1: upstream's (+sy), kept
+                           {-sxsycz, sxsysz, sxcy},
+                           {cxsycz, -cxsysz, -cxcy},
+                           {sysz, sycz, 0.0},
+                           {-sxcysz, -sxcycz, 0.0},
+                           {cxcysz, cxcycz, 0.0},
+                           {-cycz, cysz, 0.0},
+                           {SB(-cxsz, sxsycz), AD(-cxcz, sxsysz), 0.0},
+                           {AD(-sxsz, cxsycz), SB(-cxsysz, sxcz), 0.0}};
+#undef MU
 #undef AD
 #undef SB
+#pragma unroll
   for (int r = 0; r < 8; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) j_ang[r][c] = (float)j[r][c];
+#pragma unroll
   for (int r = 0; r < 15; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) h_ang[r][c] = (float)h[r][c];
+}
+
+// lanes 0..5 of the calling warp evaluate the six sincos in parallel (the serial chain of twelve
+// double-precision trig calls was the longest part of the optimiser step)
+__device__ __forceinline__ void pose_trig_warp(NdtShared& s, const double x[6], int lane) {
+  if (lane < 6) {
+    const int a = lane < 3 ? lane : lane - 3;
+    double ang = x[3 + a], sn, cs;
+    if (lane < 3) {
+      ang = (double)(float)ang;
+      sincos(ang, &sn, &cs);
+    } else if (fabs(ang) < 10e-5) {
+      sn = 0.0; cs = 1.0;
+    } else {
+      sincos(ang, &sn, &cs);
+    }
+    s.trig[lane][0] = sn;
+    s.trig[lane][1] = cs;
+  }
+  __syncwarp();
 }
 
 // ---- More-Thuente helpers (A.4) ---------------------------------------------------------------
@@ -177,21 +229,16 @@ __device__ inline double mt_trial_value(double a_l, double f_l, double g_l, doub
 // H upper-triangle index of (i, j), i <= j, inside the accumulator vector
 __host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (i - 1)) / 2 + (j - i); }
 
-// ---- the optimiser state machine; runs on one thread after every derivative pass -----------
-// Returns the phase of the next pass (PH_DONE when the registration is finished).
-__device__ __noinline__ void ndt_request_eval(NdtShared& s, const double x_t[6], int phase, int need_hessian) {
-  pose_to_T(x_t, s.T);
-  angle_tables(x_t, s.j_ang, s.h_ang);
-  s.phase = phase;
-  s.need_hessian = need_hessian;
-}
-
-__device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, int n_src) {
+// ---- the optimiser state machine; one lane, after every derivative pass ----------------------
+// Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the next pass
+// must be evaluated at s.x_t (the caller then rebuilds T and the angle tables).
+static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm) {
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
   const double* t = s.tot;
   s.n_eval++;
   s.hits += t[28];
+  s.new_pose = 0;
   bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
   switch (s.phase) {
     case PH_INIT:
@@ -246,7 +293,9 @@ __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, int n_
         s.a_t = fmin(s.a_t, step_max);
         s.a_t = fmax(s.a_t, step_min);
         for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
-        ndt_request_eval(s, s.x_t, PH_MT_ITER, 0);
+        s.phase = PH_MT_ITER;
+        s.need_hessian = 0;
+        s.new_pose = 1;
         return;
       }
       if (s.step_iterations) {  // computeHessian at x_t (same transform and tables as the last pass)
@@ -277,7 +326,8 @@ __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, int n_
         s.phase = PH_DONE;
         return;
       }
-      for (int i = 0; i < 6; ++i) s.dir[i] = dp[i] / nrm;
+      const double inv_nrm = 1.0 / nrm;
+      for (int i = 0; i < 6; ++i) s.dir[i] = dp[i] * inv_nrm;
       // computeStepLengthMT prologue
       s.phi_0 = -s.score;
       double gd = 0;
@@ -304,16 +354,22 @@ __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, int n_
       s.a_t = fmin(s.a_t, step_max);
       s.a_t = fmax(s.a_t, step_min);
       for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
-      ndt_request_eval(s, s.x_t, PH_MT_FIRST, 1);
+      s.phase = PH_MT_FIRST;
+      s.need_hessian = 1;
+      s.new_pose = 1;
       return;
     }
   }
 }
 
 // ---- one source point ------------------------------------------------------------------------
+// Writes the point's 29 contributions (score, g[6], H upper triangle [21], hits) as floats into
+// out[0..28]; the caller reduces them across the warp and accumulates in double.
+// gauss_d1 arrives as an unevaluated float pair (d1h + d1l) so that the reference's
+// float(double(d1) * e) products are reproduced without FP64 conversions in the per-hit path.
 template <int MODE>  // 1, 7, 27 (DIRECT*) or 0 (KDTREE radius search over voxel centroids)
-__device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView& grid, const GridParams& gp, float4 pt, float d1f_unused, double gauss_d1, float gauss_d2,
-                                          float res, int need_hessian, double acc[kNumAcc]) {
+__device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& grid, const GridParams& gp, float4 pt, float d1h, float d1l, float gauss_d2, float res2,
+                                          int need_hessian, float out[32]) {
   const float x0 = pt.x, x1 = pt.y, x2 = pt.z;
   const float xt0 = affine_row(s.T[0], s.T[1], s.T[2], s.T[3], x0, x1, x2);
   const float xt1 = affine_row(s.T[4], s.T[5], s.T[6], s.T[7], x0, x1, x2);
@@ -322,7 +378,7 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView&
   const int c0 = (int)floorf(__fdiv_rn(xt0, gp.leaf[0])), c1 = (int)floorf(__fdiv_rn(xt1, gp.leaf[1])), c2 = (int)floorf(__fdiv_rn(xt2, gp.leaf[2]));
   float v0 = 0.f, v1 = 0.f, v2 = 0.f;                                       // sum e (C q)
   float m00 = 0.f, m01 = 0.f, m02 = 0.f, m11 = 0.f, m12 = 0.f, m22 = 0.f;  // sum e (C - d2 Cq Cq^T)
-  double score = 0.0;
+  float score = 0.f;
   int hits = 0;
   constexpr int NOFF = MODE == 0 ? 27 : MODE;
 #pragma unroll
@@ -338,29 +394,36 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView&
     const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
     if (i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]) continue;
     const uint32_t key = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
-    const int slot = ndt_lookup(grid, key);
+    int slot = ndt_lookup(grid, key);
     if (slot < 0) continue;
-    if (MODE == 0) {  // radiusSearch over the voxel centroids, d2 < resolution^2
-      float4 c = __ldg(grid.centroids + slot);
-      if (!(l2_simple(xt0, xt1, xt2, c.x, c.y, c.z) < __fmul_rn(res, res))) continue;
+    if (slot & (int)kNdtRejected) {  // nr_points = -1 upstream: invisible to DIRECT*, still in the KDTREE cloud
+      if (MODE != 0) continue;
+      slot &= ~(int)kNdtRejected;
     }
-    const double2* vp = reinterpret_cast<const double2*>(grid.voxels + slot);
-    const double2 ma = __ldg(vp), mb = __ldg(vp + 1);  // mean0 mean1 | mean2 (icov0 icov1)
-    const float4 cb = __ldg(reinterpret_cast<const float4*>(vp + 2));
-    const float C00 = __int_as_float(__double2loint(mb.y)), C01 = __int_as_float(__double2hiint(mb.y));
-    const float C02 = cb.x, C11 = cb.y, C12 = cb.z, C22 = cb.w;
+    if (MODE == 0) {  // radiusSearch over the voxel centroids, d2 < resolution^2
+      const float4 c = grid.centroids[slot];
+      if (!(l2_simple(xt0, xt1, xt2, c.x, c.y, c.z) < res2)) continue;
+    }
+    const float4* vp = reinterpret_cast<const float4*>(grid.voxels + slot);
+    const float4 ra = vp[0], rb = vp[1], rc = vp[2];  // hi0 hi1 hi2 lo0 | lo1 lo2 C00 C01 | C02 C11 C12 C22
+    const float C00 = rb.z, C01 = rb.w, C02 = rc.x, C11 = rc.y, C12 = rc.z, C22 = rc.w;
     ++hits;
-    const float q0 = (float)((double)xt0 - ma.x), q1 = (float)((double)xt1 - ma.y), q2 = (float)((double)xt2 - mb.x);
+    // q = float(double(x') - mean): (x' - hi) is exact for points within a few voxels of the mean
+    const float q0 = __fsub_rn(__fsub_rn(xt0, ra.x), ra.w), q1 = __fsub_rn(__fsub_rn(xt1, ra.y), rb.x), q2 = __fsub_rn(__fsub_rn(xt2, ra.z), rb.y);
     const float cq0 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C00), __fmul_rn(q1, C01)), __fmul_rn(q2, C02));
     const float cq1 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C01), __fmul_rn(q1, C11)), __fmul_rn(q2, C12));
     const float cq2 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C02), __fmul_rn(q1, C12)), __fmul_rn(q2, C22));
     const float qCq = __fadd_rn(__fadd_rn(__fmul_rn(q0, cq0), __fmul_rn(q1, cq1)), __fmul_rn(q2, cq2));
-    float e = expf(__fmul_rn(__fmul_rn(-gauss_d2, qCq), 0.5f));
-    const float score_inc = (float)(-gauss_d1 * (double)e);
-    e = __fmul_rn(gauss_d2, e);
+    const float ex = expf(__fmul_rn(__fmul_rn(-gauss_d2, qCq), 0.5f));
+    // score_inc = float(-d1 * e) with d1 = d1h + d1l
+    const float t1 = __fmul_rn(d1h, ex);
+    const float sinc = __fadd_rn(t1, fmaf(d1l, ex, fmaf(d1h, ex, -t1)));
+    float e = __fmul_rn(gauss_d2, ex);
     if (e > 1.f || e < 0.f || e != e) continue;  // upstream returns 0 for this hit (score included)
-    score += (double)score_inc;
-    e = (float)((double)e * gauss_d1);
+    score = __fsub_rn(score, sinc);
+    // e = float(e * d1)
+    const float t2 = __fmul_rn(d1h, e);
+    e = __fadd_rn(t2, fmaf(d1l, e, fmaf(d1h, e, -t2)));
     v0 = fmaf(e, cq0, v0); v1 = fmaf(e, cq1, v1); v2 = fmaf(e, cq2, v2);
     if (need_hessian) {
       const float ed = __fmul_rn(e, gauss_d2);
@@ -368,18 +431,20 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView&
       m11 += e * C11 - ed * cq1 * cq1; m12 += e * C12 - ed * cq1 * cq2; m22 += e * C22 - ed * cq2 * cq2;
     }
   }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) out[k] = 0.f;
   if (!hits) return;
-  acc[28] += (double)hits;
-  acc[0] += score;
+  out[28] = (float)hits;
+  out[0] = score;
   // point_gradient columns 3..5: j3 = (0, a.x, b.x), j4 = (c.x, d.x, e.x), j5 = (f.x, g.x, h.x)
   auto dotj = [&](int r) { return s.j_ang[r][0] * x0 + s.j_ang[r][1] * x1 + s.j_ang[r][2] * x2; };
   const float j3y = dotj(0), j3z = dotj(1);
   const float j4x = dotj(2), j4y = dotj(3), j4z = dotj(4);
   const float j5x = dotj(5), j5y = dotj(6), j5z = dotj(7);
-  acc[1] += (double)v0; acc[2] += (double)v1; acc[3] += (double)v2;
-  acc[4] += (double)(v1 * j3y + v2 * j3z);
-  acc[5] += (double)(v0 * j4x + v1 * j4y + v2 * j4z);
-  acc[6] += (double)(v0 * j5x + v1 * j5y + v2 * j5z);
+  out[1] = v0; out[2] = v1; out[3] = v2;
+  out[4] = v1 * j3y + v2 * j3z;
+  out[5] = v0 * j4x + v1 * j4y + v2 * j4z;
+  out[6] = v0 * j5x + v1 * j5y + v2 * j5z;
   if (!need_hessian) return;
   // M J_k for the rotational columns
   const float a0 = m01 * j3y + m02 * j3z, a1 = m11 * j3y + m12 * j3z, a2 = m12 * j3y + m22 * j3z;                          // M j3
@@ -393,17 +458,32 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtGridView&
   const float vh44 = v0 * doth(6) + v1 * doth(7) + v2 * doth(8);
   const float vh45 = v0 * doth(9) + v1 * doth(10) + v2 * doth(11);
   const float vh55 = v0 * doth(12) + v1 * doth(13) + v2 * doth(14);
-  acc[hidx(0, 0)] += (double)m00; acc[hidx(0, 1)] += (double)m01; acc[hidx(0, 2)] += (double)m02;
-  acc[hidx(1, 1)] += (double)m11; acc[hidx(1, 2)] += (double)m12; acc[hidx(2, 2)] += (double)m22;
-  acc[hidx(0, 3)] += (double)a0; acc[hidx(1, 3)] += (double)a1; acc[hidx(2, 3)] += (double)a2;
-  acc[hidx(0, 4)] += (double)b0; acc[hidx(1, 4)] += (double)b1; acc[hidx(2, 4)] += (double)b2;
-  acc[hidx(0, 5)] += (double)e0; acc[hidx(1, 5)] += (double)e1; acc[hidx(2, 5)] += (double)e2;
-  acc[hidx(3, 3)] += (double)(j3y * a1 + j3z * a2 + vh33);
-  acc[hidx(3, 4)] += (double)(j3y * b1 + j3z * b2 + vh34);
-  acc[hidx(3, 5)] += (double)(j3y * e1 + j3z * e2 + vh35);
-  acc[hidx(4, 4)] += (double)(j4x * b0 + j4y * b1 + j4z * b2 + vh44);
-  acc[hidx(4, 5)] += (double)(j4x * e0 + j4y * e1 + j4z * e2 + vh45);
-  acc[hidx(5, 5)] += (double)(j5x * e0 + j5y * e1 + j5z * e2 + vh55);
+  out[hidx(0, 0)] = m00; out[hidx(0, 1)] = m01; out[hidx(0, 2)] = m02;
+  out[hidx(1, 1)] = m11; out[hidx(1, 2)] = m12; out[hidx(2, 2)] = m22;
+  out[hidx(0, 3)] = a0; out[hidx(1, 3)] = a1; out[hidx(2, 3)] = a2;
+  out[hidx(0, 4)] = b0; out[hidx(1, 4)] = b1; out[hidx(2, 4)] = b2;
+  out[hidx(0, 5)] = e0; out[hidx(1, 5)] = e1; out[hidx(2, 5)] = e2;
+  out[hidx(3, 3)] = j3y * a1 + j3z * a2 + vh33;
+  out[hidx(3, 4)] = j3y * b1 + j3z * b2 + vh34;
+  out[hidx(3, 5)] = j3y * e1 + j3z * e2 + vh35;
+  out[hidx(4, 4)] = j4x * b0 + j4y * b1 + j4z * b2 + vh44;
+  out[hidx(4, 5)] = j4x * e0 + j4y * e1 + j4z * e2 + vh45;
+  out[hidx(5, 5)] = j5x * e0 + j5y * e1 + j5z * e2 + vh55;
+}
+
+// Transposing warp reduction of 32 floats per lane: afterwards lane l holds in v[0] the sum over
+// the warp of value l.  31 shuffles instead of 32 x 5; the summation tree is fixed.
+__device__ __forceinline__ void warp_transpose_reduce32(float v[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
 }
 
 // group barrier: monotonically increasing counter, one arrival per CTA per use
@@ -421,14 +501,10 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
   __syncthreads();
 }
 
-struct NdtWorkspace {       // per group, device
-  double* partials;         // [2][G][kAccStride]
-  unsigned int* barrier;    // counter (zeroed before the launch)
-};
-
 template <int MODE>
 __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers) {
   __shared__ NdtShared s;
+  extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
   const int G = ctas_per_group;
   const int group = blockIdx.x / G, rank = blockIdx.x % G, n_groups = gridDim.x / G;
   double* partials = partials_all + (size_t)group * 2 * G * kAccStride;
@@ -436,88 +512,163 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   unsigned int epoch = 0;
   int parity = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
   for (int jb = group; jb < n_jobs; jb += n_groups) {
     const NdtJob& job = jobs[jb];
     const GridParams gp = job.grid.meta->grid;
     const int n_src = job.n_src;
-    if (tid == 0) {
-      // gauss constants (A.4), recomputed per registration like upstream
-      const double c1 = 10.0 * (1 - prm.outlier_ratio);
-      const double c2 = prm.outlier_ratio / pow((double)(float)prm.resolution, 3);
-      const double d3 = -log(c2);
-      s.gauss_d1 = -log(c1 + c2) - d3;
-      s.gauss_d2 = -2 * log((-log(c1 * exp(-0.5) + c2) - d3) / s.gauss_d1);
-      for (int i = 0; i < 6; ++i) s.p[i] = job.p0[i];
-      s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.hits = 0.0;
-      s.score = 0.0;
-      if (job.eval_only) {
-        ndt_request_eval(s, s.p, PH_EVAL_ONLY, 1);
+    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
+    const long long ts0 = clock64();
+    // ---- stage the target grid in shared memory when it fits
+    NdtLookup look;
+    {
+      const uint32_t n_rec = job.grid.gmeta->n_records, cap = job.grid.gmeta->table_cap;
+      const size_t table_bytes = (size_t)cap * sizeof(uint2), vox_bytes = (size_t)n_rec * sizeof(NdtVoxel);
+      const size_t cen_bytes = MODE == 0 ? (size_t)n_rec * sizeof(float4) : 0;
+      look.mask = cap - 1;
+      if (table_bytes + vox_bytes + cen_bytes <= (size_t)kStageBytes) {
+        if (staged_table != (const void*)job.grid.table) {
+          __syncthreads();
+          const uint4* src_t = reinterpret_cast<const uint4*>(job.grid.table);
+          uint4* dst = reinterpret_cast<uint4*>(stage);
+          const int n_t = (int)(table_bytes / 16), n_v = (int)(vox_bytes / 16), n_c = (int)(cen_bytes / 16);
+          for (int i = tid; i < n_t; i += kAlignThreads) dst[i] = __ldg(src_t + i);
+          const uint4* src_v = reinterpret_cast<const uint4*>(job.grid.voxels);
+          for (int i = tid; i < n_v; i += kAlignThreads) dst[n_t + i] = __ldg(src_v + i);
+          const uint4* src_c = reinterpret_cast<const uint4*>(job.grid.centroids);
+          for (int i = tid; i < n_c; i += kAlignThreads) dst[n_t + n_v + i] = __ldg(src_c + i);
+          staged_table = (const void*)job.grid.table;
+        }
+        look.table = reinterpret_cast<const uint2*>(stage);
+        look.voxels = reinterpret_cast<const NdtVoxel*>(stage + table_bytes);
+        look.centroids = reinterpret_cast<const float4*>(stage + table_bytes + vox_bytes);
       } else {
-        for (int i = 0; i < 12; ++i) s.T[i] = job.guess[i];
-        angle_tables(s.p, s.j_ang, s.h_ang);
-        s.phase = PH_INIT;
+        look.table = job.grid.table;
+        look.voxels = job.grid.voxels;
+        look.centroids = job.grid.centroids;
+      }
+    }
+    if (tid < 32) {
+      if (tid == 0) {
+        // gauss constants (A.4), recomputed per registration like upstream
+        const double c1 = 10.0 * (1 - prm.outlier_ratio);
+        const double c2 = prm.outlier_ratio / pow((double)(float)prm.resolution, 3);
+        const double d3 = -log(c2);
+        s.gauss_d1 = -log(c1 + c2) - d3;
+        s.gauss_d2 = -2 * log((-log(c1 * exp(-0.5) + c2) - d3) / s.gauss_d1);
+        for (int i = 0; i < 6; ++i) s.p[i] = job.p0[i];
+        s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.hits = 0.0;
+        s.score = 0.0;
         s.need_hessian = 1;
+        s.phase = job.eval_only ? PH_EVAL_ONLY : PH_INIT;
+      }
+      __syncwarp();
+      pose_trig_warp(s, s.p, lane);
+      if (tid == 0) {
+        if (job.eval_only) pose_to_T(s.p, s.trig, s.T);
+        else
+          for (int i = 0; i < 12; ++i) s.T[i] = job.guess[i];  // first pass: the guess matrix itself
+        angle_tables(s.trig, s.j_ang, s.h_ang);
       }
     }
     __syncthreads();
+    prof[6] = clock64() - ts0;
+    const int n_groups32 = (n_src + 31) >> 5;
+    const float res2 = __fmul_rn((float)prm.resolution, (float)prm.resolution);
     while (true) {
       // ---- pass
-      double acc[kNumAcc];
-#pragma unroll
-      for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
+      const long long t0 = clock64();
       const int need_h = s.need_hessian;
-      const double gd1 = s.gauss_d1;
+      const float d1h = (float)s.gauss_d1, d1l = (float)(s.gauss_d1 - (double)d1h);
       const float gd2 = (float)s.gauss_d2;
-      const float res = (float)prm.resolution;
+      double accd = 0.0;  // lane l accumulates accumulator l of this warp's point groups
       if (gp.any && !gp.overflow) {
-        for (int i = rank * kAlignThreads + tid; i < n_src; i += G * kAlignThreads) {
-          const float4 pt = __ldg(job.src + i);
-          ndt_point<MODE>(s, job.grid, gp, pt, 0.f, gd1, gd2, res, need_h, acc);
+        // 32-point groups dealt round-robin over the group's warps
+        for (int q = warp * G + rank; q < n_groups32; q += G * kAlignWarps) {
+          const int i = (q << 5) + lane;
+          float vals[32];
+          if (i < n_src) {
+            const float4 pt = __ldg(job.src + i);
+            ndt_point<MODE>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) vals[k] = 0.f;
+          }
+          warp_transpose_reduce32(vals, lane);
+          accd += (double)vals[0];
         }
       }
-      // ---- block reduce
-#pragma unroll
-      for (int k = 0; k < kNumAcc; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s.red[warp][k] = v;
-      }
+      const long long t1 = clock64();
+      // ---- block reduce: warp totals -> shared memory -> one partial row per CTA
+      s.red[warp][lane] = accd;
       __syncthreads();
-      if (tid < kNumAcc) {
+      if (tid < kAccStride) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kAlignThreads / 32; ++w) v += s.red[w][tid];
+        for (int w = 0; w < kAlignWarps; ++w) v += s.red[w][tid];
         partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
       }
       // ---- group sync + redundant fixed-order reduction of the G partials
+      const long long t2 = clock64();
       epoch += (unsigned)G;
       group_barrier(barrier, epoch);
+      const long long t3 = clock64();
       {
-        const int col = tid >> 4, sub = tid & 15;  // 16 threads per accumulator
-        double v = 0.0;
-        if (col < kNumAcc)
-          for (int r = sub; r < G; r += 16) v += __ldcg(partials + ((size_t)parity * G + r) * kAccStride + col);
+        // warp w sums rows w, w+16, ... (each row one coalesced 256-byte read), then the 16 row
+        // groups are combined through shared memory; fixed order -> every CTA gets the same bits
+        const double* base = partials + (size_t)parity * G * kAccStride + lane;
+        double tmp[10];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (col < kNumAcc && sub == 0) s.tot[col] = v;
+        for (int k = 0; k < 10; ++k) {  // all loads in flight before the first add (G <= 160)
+          const int r = warp + kAlignWarps * k;
+          tmp[k] = r < G ? __ldcg(base + (size_t)r * kAccStride) : 0.0;
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v += tmp[k];
+        for (int r = warp + kAlignWarps * 10; r < G; r += kAlignWarps) v += __ldcg(base + (size_t)r * kAccStride);
+        __syncthreads();  // s.red is reused
+        s.red[warp][lane] = v;
+        __syncthreads();
+        if (tid < kAccStride) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < kAlignWarps; ++w) t += s.red[w][tid];
+          s.tot[tid] = t;
+        }
       }
       parity ^= 1;
       __syncthreads();
-      // ---- optimiser step (thread 0 of every CTA, identical inputs -> identical state)
-      if (tid == 0) {
-        if (s.phase == PH_EVAL_ONLY) {
-          s.n_eval++;
-          s.hits += s.tot[28];
-          s.phase = PH_DONE;
-        } else {
-          ndt_step(s, prm, n_src);
+      const long long t4 = clock64();
+      // ---- optimiser step (warp 0 of every CTA, identical inputs -> identical state)
+      if (tid < 32) {
+        if (tid == 0) {
+          if (s.phase == PH_EVAL_ONLY) {
+            s.n_eval++;
+            s.hits += s.tot[28];
+            s.phase = PH_DONE;
+            s.new_pose = 0;
+          } else {
+            ndt_step(s, prm);
+          }
+        }
+        __syncwarp();
+        if (s.new_pose) {
+          pose_trig_warp(s, s.x_t, lane);
+          if (tid == 0) {
+            pose_to_T(s.x_t, s.trig, s.T);
+            angle_tables(s.trig, s.j_ang, s.h_ang);
+          }
         }
       }
       __syncthreads();
+      const long long t5 = clock64();
+      prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += t4 - t3; prof[4] += t5 - t4; prof[5] += 1;
       if (s.phase == PH_DONE) break;
     }
+    if (job.prof && rank == 0 && tid == 0)
+      for (int k = 0; k < 7; ++k) job.prof[k] = prof[k];
     // ---- result
     if (rank == 0 && tid == 0) {
       if (job.eval_only) {

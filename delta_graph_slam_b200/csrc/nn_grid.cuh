@@ -240,6 +240,7 @@ struct NnGrid {
     if ((e = table.reserve(cap)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(table.p, 0xFF, (size_t)cap * sizeof(uint2), st)) != cudaSuccess) return e;
     if (n > 0) {
+      launch_counter() += 2;
       k_nn_reorder<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, sort.vals_a.p, sort.vals_b.p, sort.meta.p, pts.p);
       k_nn_insert<<<kNumSM * 2, 256, 0, st>>>(sort.meta.p, sort.vox_key.p, table.p, cap - 1, 32 - (int)__builtin_ctz(cap));
     }
@@ -258,6 +259,7 @@ struct NnGrid {
     if ((e = cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), st)) != cudaSuccess) return e;
     if (T_colmajor_host && (e = cudaMemcpyAsync(T.p, T_colmajor_host, 64, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if (n_src > 0) {
+      launch_counter() += 2;
       k_nn_search<<<(n_src + 255) / 256, 256, 0, st>>>(view(), d_src, n_src, T.p, T_colmajor_host ? 1 : 0, max_d2, d2.p, idx.p, queries.p, pending.p, n_pending.p);
       k_nn_bruteforce<<<kNumSM * 2, 256, 0, st>>>(view(), queries.p, pending.p, n_pending.p, d2.p, idx.p);
     }
@@ -279,6 +281,7 @@ inline cudaError_t nn_fitness(cudaStream_t st, NnGrid& nn, const float4* d_src, 
   for (int i = 0; i < 16; ++i) pinT[i] = T_colmajor[i];
   if ((e = nn.search(st, d_src, n_src, pinT, max_d2)) != cudaSuccess) return e;
   if ((e = partials.reserve(2 * kFitBlocks)) != cudaSuccess) return e;
+  launch_counter() += 1;
   k_fitness_partial<<<kFitBlocks, 256, 0, st>>>(nn.d2.p, nn.idx.p, n_src, max_range, strict_less ? 1 : 0, partials.p);
   double* hp = reinterpret_cast<double*>(pin.p);
   if ((e = cudaMemcpyAsync(hp, partials.p, 2 * kFitBlocks * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;

@@ -82,7 +82,7 @@ __device__ inline void inverse3(const double a[9], double r[9]) {
 
 // One-sided Jacobi SVD solve of a 6x6 system with Eigen's JacobiSVD rank threshold — the slow,
 // always-safe path (used when the pivoted elimination below meets a near-singular matrix).
-__device__ __noinline__ void svd_solve6(const double* A, const double* b, double* x) {
+static __device__ __noinline__ void svd_solve6(const double* A, const double* b, double* x) {
   double U[36], V[36];
   for (int i = 0; i < 36; ++i) { U[i] = A[i]; V[i] = (i % 7 == 0) ? 1.0 : 0.0; }
   for (int sweep = 0; sweep < 100; ++sweep) {
@@ -133,25 +133,46 @@ __device__ __noinline__ void svd_solve6(const double* A, const double* b, double
 // well-conditioned case; when a pivot collapses (rank-deficient or NaN input) the SVD path
 // reproduces JacobiSVD::solve's minimum-norm answer (e.g. H = 0 -> x = 0), which is what the
 // reference's NDT loop relies on to terminate.
-__device__ __noinline__ void solve6(const double* A, const double* b, double* x) {
+// Every loop is fully unrolled and every index is a compile-time constant (row swaps are
+// predicated exchanges), so the 6x7 tableau lives in registers: this runs on one lane between
+// two derivative passes and its latency is on the critical path of every Newton iteration.
+static __device__ __noinline__ void solve6(const double* A, const double* b, double* x) {
   double M[6][7];
   double amax = 0.0;
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
+#pragma unroll
     for (int j = 0; j < 6; ++j) { M[i][j] = A[6 * i + j]; amax = fmax(amax, fabs(M[i][j])); }
     M[i][6] = b[i];
   }
   bool ok = amax > 0.0 && amax == amax && amax < 1.7e308;
-  for (int k = 0; k < 6 && ok; ++k) {
+  double invs[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
     int piv = k;
     double best = fabs(M[k][k]);
-    for (int i = k + 1; i < 6; ++i)
-      if (fabs(M[i][k]) > best) { best = fabs(M[i][k]); piv = i; }
-    if (!(best > 1e-11 * amax)) { ok = false; break; }
-    if (piv != k)
-      for (int j = k; j < 7; ++j) { double t = M[k][j]; M[k][j] = M[piv][j]; M[piv][j] = t; }
-    double inv = 1.0 / M[k][k];
+#pragma unroll
     for (int i = k + 1; i < 6; ++i) {
-      double f = M[i][k] * inv;
+      const double v = fabs(M[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+    if (!(best > 1e-11 * amax)) ok = false;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const bool sw = (i == piv);
+#pragma unroll
+      for (int j = k; j < 7; ++j) {
+        const double a = M[k][j], c = M[i][j];
+        M[k][j] = sw ? c : a;
+        M[i][j] = sw ? a : c;
+      }
+    }
+    const double inv = 1.0 / M[k][k];
+    invs[k] = inv;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = M[i][k] * inv;
+#pragma unroll
       for (int j = k + 1; j < 7; ++j) M[i][j] -= f * M[k][j];
     }
   }
@@ -159,11 +180,16 @@ __device__ __noinline__ void solve6(const double* A, const double* b, double* x)
     svd_solve6(A, b, x);
     return;
   }
+  double xs[6];
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = M[i][6];
-    for (int j = i + 1; j < 6; ++j) s -= M[i][j] * x[j];
-    x[i] = s / M[i][i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) s -= M[i][j] * xs[j];
+    xs[i] = s * invs[i];
   }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = xs[i];
 }
 
 }  // namespace b200

@@ -26,13 +26,13 @@ struct SortMeta {     // device-resident, written by k_grid_keys / k_seg_scan
 };
 
 // ---- min / max -------------------------------------------------------------
-__global__ void k_minmax_init(int* mm) {
+static __global__ void k_minmax_init(int* mm) {
   if (threadIdx.x < 3) mm[threadIdx.x] = 0x7FFFFFFF;
   else if (threadIdx.x < 6) mm[threadIdx.x] = (int)0x80000000;
   else if (threadIdx.x == 6) mm[6] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_minmax(const float4* __restrict__ pts, int n, int is_dense, int* mm) {
+static __global__ void __launch_bounds__(256) k_minmax(const float4* __restrict__ pts, int n, int is_dense, int* mm) {
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
   float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
   int any = 0;
@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t voxel_key(const GridParams& g, float x, floa
 }
 
 // keys (A.1 step 4) + pass-0 digit histogram per tile
-__global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __restrict__ pts, int n, int is_dense, float lx, float ly, float lz, const int* __restrict__ mm,
+static __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __restrict__ pts, int n, int is_dense, float lx, float ly, float lz, const int* __restrict__ mm,
                                                              SortMeta* meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ point_key) {
   __shared__ GridParams g;
   __shared__ uint32_t s_skip;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __rest
 // ---- radix sort: one pass = hist -> scan -> scatter --------------------------
 // hist[tile][digit] (tile-major so the scan reads coalesced rows)
 template <int ITEMS>
-__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, int n, int pass, const SortMeta* __restrict__ meta, uint32_t* __restrict__ hist) {
+static __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, int n, int pass, const SortMeta* __restrict__ meta, uint32_t* __restrict__ hist) {
   if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
   __shared__ uint32_t s[kRadix];
   s[threadIdx.x] = 0;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __re
 }
 
 // exclusive scan over (digit-major, tile-minor) order, in place
-__global__ void __launch_bounds__(kRadix) k_sort_scan(uint32_t* __restrict__ hist, int n_tiles, int pass, const SortMeta* __restrict__ meta) {
+static __global__ void __launch_bounds__(kRadix) k_sort_scan(uint32_t* __restrict__ hist, int n_tiles, int pass, const SortMeta* __restrict__ meta) {
   if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
   __shared__ uint32_t s_tot[kRadix];
   const int d = threadIdx.x;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kRadix) k_sort_scan(uint32_t* __restrict__ his
 
 // stable scatter: each warp owns a contiguous slice of the tile and walks it in rounds of 32
 template <int ITEMS>
-__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+static __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out, int n, int pass, const SortMeta* __restrict__ meta, const uint32_t* __restrict__ hist) {
   if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
   constexpr int WARPS = kSortThreads / 32;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
 __device__ __forceinline__ bool sorted_in_b(const SortMeta* meta) { return (((meta->nbits + kRadixBits - 1) / kRadixBits) & 1u) != 0; }
 
 // heads per tile
-__global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, const SortMeta* __restrict__ meta,
+static __global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, const SortMeta* __restrict__ meta,
                                                    uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_valid) {
   if (meta->grid.overflow) return;
   const uint32_t* keys = sorted_in_b(meta) ? keys_b : keys_a;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ 
 
 // slot of every head (= exclusive count of heads before it); vox_start[slot] = position of the
 // head in the sorted order; vox_start[n_vox] = n_valid closes the last run
-__global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, SortMeta* meta,
+static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, SortMeta* meta,
                                                   const uint32_t* __restrict__ tile_heads, const uint32_t* __restrict__ tile_valid, int n_tiles,
                                                   uint32_t* __restrict__ vox_start, uint32_t* __restrict__ vox_key) {
   if (meta->grid.overflow) return;
@@ -357,6 +357,7 @@ struct VoxelSort {
     if ((e = tile_valid.reserve(n_seg_tiles)) != cudaSuccess) return e;
 
     k_minmax_init<<<1, 32, 0, st>>>(mm.p);
+    launch_counter() += 4 + (n > 0 ? 1 : 0) + (n > 0 ? 12 : 0);  // init, minmax, keys, 4 x (hist, scan, scatter), 2 x segmentation
     int blocks = n > 0 ? (n + 255) / 256 : 1;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
     if (n > 0) k_minmax<<<blocks, 256, 0, st>>>(d_pts, n, is_dense, mm.p);

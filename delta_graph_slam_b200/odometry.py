@@ -1,0 +1,150 @@
+"""Host-side mirror of ScanMatchingOdometryNodelet::matching and PrefilteringNodelet::downsample.
+
+The frame-to-keyframe state machine of [REF apps/scan_matching_odometry_nodelet.cpp:173-270] and
+its parameters [REF :65-106], with the registration and the down-sampling filters replaced by the
+b200reg engine.  This is host logic only (O(1) per frame); every point-cloud operation is a C-ABI
+call.  ROS plumbing (tf, msf / robot-odometry guesses, publishers) is out of scope: `msf_delta`
+can be passed in by the caller and defaults to identity, which is what the reference uses when
+`enable_imu_frontend` and `enable_robot_odometry_init_guess` are off (every launch file).
+"""
+import sys
+
+import numpy as np
+
+from .registration import DeviceCloud, VoxelGrid, select_registration_method
+
+
+def quaternion_w(R):
+    """w of Eigen::Quaternionf(R) (Eigen's rotation-matrix -> quaternion conversion), float32."""
+    R = np.asarray(R, np.float32)
+    t = np.float32(R[0, 0] + R[1, 1] + R[2, 2])
+    if t > 0:
+        return np.float32(0.5) * np.sqrt(t + np.float32(1.0))
+    i = 0
+    if R[1, 1] > R[0, 0]:
+        i = 1
+    if R[2, 2] > R[i, i]:
+        i = 2
+    j, k = (i + 1) % 3, (i + 2) % 3
+    t = np.sqrt(R[i, i] - R[j, j] - R[k, k] + np.float32(1.0))
+    return (R[k, j] - R[j, k]) * (np.float32(0.5) / t)
+
+
+class Prefilter:
+    """PrefilteringNodelet::downsample [REF apps/prefiltering_nodelet.cpp:55-75,249-260]:
+    downsample_method VOXELGRID (leaf = downsample_resolution) or NONE."""
+
+    def __init__(self, params=None, device=0, out=sys.stdout):
+        p = dict(params or {})
+        method = p.get("downsample_method", "VOXELGRID")
+        res = p.get("downsample_resolution", 0.1)
+        self.filter = None
+        if method == "VOXELGRID":
+            print(f"downsample: VOXELGRID {res:g}", file=out)
+            self.filter = VoxelGrid(device=device)
+            self.filter.setLeafSize(res, res, res)
+        elif method == "APPROX_VOXELGRID":
+            raise NotImplementedError("APPROX_VOXELGRID stays on the reference's pcl::ApproximateVoxelGrid (not on the B200 path)")
+        else:
+            if method != "NONE":
+                print(f"warning: unknown downsampling type ({method})", file=sys.stderr)
+                print("       : use passthrough filter", file=sys.stderr)
+            print("downsample: NONE", file=out)
+
+    def downsample(self, cloud, out=None):
+        if self.filter is None:
+            return cloud
+        # distance_filter hands over is_dense = false [REF apps/prefiltering_nodelet.cpp:286]
+        self.filter.setInputCloud(cloud, is_dense=False)
+        return self.filter.filter(out=out)
+
+
+class ScanMatchingOdometry:
+    """matching(stamp, cloud) -> odom (4x4 float32), state as in the nodelet."""
+
+    def __init__(self, params=None, device=0, out=sys.stdout, registration=None, downsample_filter=None):
+        p = dict(params or {})
+        self.keyframe_delta_trans = p.get("keyframe_delta_trans", 0.25)
+        self.keyframe_delta_angle = p.get("keyframe_delta_angle", 0.15)
+        self.keyframe_delta_time = p.get("keyframe_delta_time", 1.0)
+        self.transform_thresholding = p.get("transform_thresholding", False)
+        self.max_acceptable_trans = p.get("max_acceptable_trans", 1.0)
+        self.max_acceptable_angle = p.get("max_acceptable_angle", 1.0)
+        method = p.get("downsample_method", "VOXELGRID")
+        res = p.get("downsample_resolution", 0.1)
+        self.downsample_filter = None
+        if method == "VOXELGRID":
+            print(f"downsample: VOXELGRID {res:g}", file=out)
+            self.downsample_filter = VoxelGrid(device=device)
+            self.downsample_filter.setLeafSize(res, res, res)
+        elif method == "APPROX_VOXELGRID":
+            raise NotImplementedError("APPROX_VOXELGRID stays on the reference's pcl::ApproximateVoxelGrid (not on the B200 path)")
+        else:
+            if method != "NONE":
+                print(f"warning: unknown downsampling type ({method})", file=sys.stderr)
+                print("       : use passthrough filter", file=sys.stderr)
+            print("downsample: NONE", file=out)
+        if downsample_filter is not None:
+            self.downsample_filter = downsample_filter
+        self.registration = registration if registration is not None else select_registration_method(p, device=device, out=out)
+        self.keyframe = None
+        self.keyframe_pose = np.eye(4, dtype=np.float32)
+        self.keyframe_stamp = 0.0
+        self.prev_trans = np.eye(4, dtype=np.float32)
+        self.prev_time = None
+        self.num_keyframes = 0
+        self.last_converged = True
+
+    def downsample(self, cloud):
+        if self.downsample_filter is None:
+            # pcl::PassThrough without a filter field: a copy of the input (a NEW cloud object)
+            if isinstance(cloud, DeviceCloud):
+                return DeviceCloud(cloud.ptr, cloud.n, cloud.owner)  # the engine copies on setInputSource
+            return np.array(cloud, dtype=np.float32, copy=True)
+        self.downsample_filter.setInputCloud(cloud, is_dense=True)
+        return self.downsample_filter.filter()
+
+    def matching(self, stamp, cloud, msf_delta=None):
+        reg = self.registration
+        if self.keyframe is None:
+            self.prev_time = None
+            self.prev_trans = np.eye(4, dtype=np.float32)
+            self.keyframe_pose = np.eye(4, dtype=np.float32)
+            self.keyframe_stamp = stamp
+            self.keyframe = self.downsample(cloud)
+            reg.setInputTarget(self.keyframe)
+            self.num_keyframes = 1
+            return np.eye(4, dtype=np.float32)
+
+        filtered = self.downsample(cloud)
+        reg.setInputSource(filtered)
+        guess = self.prev_trans if msf_delta is None else (self.prev_trans @ np.asarray(msf_delta, np.float32))
+        reg.align(guess)
+        self.last_converged = reg.hasConverged()
+        if not self.last_converged:
+            # "scan matching has not converged!! ignore this frame": state untouched
+            return self.keyframe_pose @ self.prev_trans
+
+        trans = reg.getFinalTransformation()
+        odom = self.keyframe_pose @ trans
+        if self.transform_thresholding:
+            delta = np.linalg.inv(self.prev_trans) @ trans
+            dx = float(np.linalg.norm(delta[:3, 3]))
+            da = float(np.arccos(np.clip(quaternion_w(delta[:3, :3]), -1.0, 1.0)))
+            if dx > self.max_acceptable_trans or da > self.max_acceptable_angle:
+                return self.keyframe_pose @ self.prev_trans
+
+        self.prev_time = stamp
+        self.prev_trans = trans
+        delta_trans = float(np.linalg.norm(trans[:3, 3]))
+        delta_angle = float(np.arccos(np.clip(quaternion_w(trans[:3, :3]), -1.0, 1.0)))
+        delta_time = stamp - self.keyframe_stamp
+        if delta_trans > self.keyframe_delta_trans or delta_angle > self.keyframe_delta_angle or delta_time > self.keyframe_delta_time:
+            self.keyframe = filtered
+            reg.setInputTarget(self.keyframe)  # the cloud just used as source: promoted on the device
+            self.keyframe_pose = odom
+            self.keyframe_stamp = stamp
+            self.prev_time = stamp
+            self.prev_trans = np.eye(4, dtype=np.float32)
+            self.num_keyframes += 1
+        return odom

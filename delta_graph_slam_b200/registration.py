@@ -17,6 +17,19 @@ from ._lib import B200RegError, Config, Result
 DBL_MAX = float(np.finfo(np.float64).max)
 
 
+class DeviceCloud:
+    """A cloud that already lives on the GPU: raw device pointer to N float4 records.  `owner` keeps
+    whatever allocated the memory (e.g. a torch tensor) alive.  Accepted wherever a host cloud is."""
+
+    def __init__(self, ptr, n, owner=None):
+        self.ptr = int(ptr)
+        self.n = int(n)
+        self.owner = owner
+
+    def __len__(self):
+        return self.n
+
+
 class Registration:
     """pcl::Registration<PointXYZ, PointXYZ> call surface on one b200reg handle."""
 
@@ -66,6 +79,10 @@ class Registration:
 
     # ---- data
     def setInputTarget(self, cloud):
+        if isinstance(cloud, DeviceCloud):
+            if self._src_ref is not None and cloud is self._src_ref:
+                return self.promoteSourceToTarget()
+            return self.setInputTargetDevice(cloud.ptr, cloud.n)
         c = _lib.as_cloud(cloud)
         if len(c) == 0:  # PCL_ERROR + return: the previous target stays
             print("[b200reg::setInputTarget] Invalid or empty point cloud dataset given!", file=sys.stderr)
@@ -79,6 +96,10 @@ class Registration:
         self._ck(_lib.load().b200reg_set_target(self._h, c.ctypes.data, len(c), 16))
 
     def setInputSource(self, cloud):
+        if isinstance(cloud, DeviceCloud):
+            self.setInputSourceDevice(cloud.ptr, cloud.n)
+            self._src_ref = cloud
+            return
         c = _lib.as_cloud(cloud)
         self._ck(_lib.load().b200reg_set_source(self._h, c.ctypes.data if len(c) else None, len(c), 16))
         self._n_src = len(c)
@@ -148,6 +169,19 @@ class Registration:
         return dict(transformation=_lib.from_colmajor(np.array(r.transformation[:], np.float32)), fitness=r.fitness, score=r.score, converged=bool(r.converged),
                     iterations=r.iterations, evaluations=r.evaluations, hits=r.hits)
 
+    def setTiming(self, on=True):
+        self._ck(_lib.load().b200reg_set_timing(self._h, int(on)))
+
+    def counters(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_double()
+        self._ck(_lib.load().b200reg_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(launches_total=a.value, timed_aligns=b.value, align_kernel_ms=c.value)
+
+    def profile(self):
+        v = np.zeros(7, np.int64)
+        self._ck(_lib.load().b200reg_get_profile(self._h, v.ctypes.data))
+        return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage"), v.tolist()))
+
     def stream(self):
         p = C.c_void_p()
         self._ck(_lib.load().b200reg_get_stream(self._h, C.byref(p)))
@@ -162,6 +196,15 @@ class Registration:
         self._ck(_lib.load().b200reg_voxelgrid_filter(self._h, c.ctypes.data if len(c) else None, len(c), 16, leaf3, min_points_per_voxel, int(is_dense), out.ctypes.data,
                                                       len(out), C.byref(n_out)))
         return out[: n_out.value].copy()
+
+    def voxelgrid_filter_device(self, cloud, leaf, out, min_points_per_voxel=0, is_dense=False):
+        """Device-resident filter: `cloud` and `out` are DeviceClouds (out.n = capacity >= cloud.n)."""
+        leaf3 = (C.c_float * 3)(*((leaf,) * 3 if np.isscalar(leaf) else leaf))
+        n_out = C.c_size_t()
+        if out.n < cloud.n:
+            raise ValueError("output buffer smaller than the input cloud")
+        self._ck(_lib.load().b200reg_voxelgrid_filter_device(self._h, cloud.ptr, cloud.n, leaf3, min_points_per_voxel, int(is_dense), out.ptr, C.byref(n_out)))
+        return DeviceCloud(out.ptr, n_out.value, out.owner)
 
     def voxelgrid_last_layout(self, n_voxels, n_points):
         vid = np.zeros(max(n_voxels, 1), np.uint32)
@@ -241,7 +284,9 @@ class VoxelGrid:
     def setMinimumPointsNumberPerVoxel(self, n):
         self.min_points_per_voxel = int(n)
 
-    def filter(self):
+    def filter(self, out=None):
+        if isinstance(self._input, DeviceCloud):
+            return self._reg.voxelgrid_filter_device(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
         return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense)
 
     def last_layout(self, n_voxels, n_points):

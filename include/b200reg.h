@@ -153,6 +153,16 @@ int b200reg_ndt_get_leaves(b200reg_handle* h, uint64_t* idx, int32_t* n, double*
 /* score / gradient / Hessian of the current source at pose p = [t, eulerXYZ] (one derivative pass) */
 int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score, double g[6], double H[36]);
 
+/* Measurement hooks (bench.py).  With timing on, every align kernel launch is bracketed by CUDA
+ * events on the handle's stream.  b200reg_get_counters: kernels launched by the library since it was
+ * loaded (all handles), aligns timed on this handle, and their summed kernel duration in ms. */
+int b200reg_set_timing(b200reg_handle* h, int on);
+int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long* timed_aligns, double* align_kernel_ms);
+
+/* developer counters of the last align: SM cycles spent by CTA 0 in {point pass, block reduce, group
+ * barrier, partial sum, optimiser step}, the number of passes, and the grid staging cycles */
+int b200reg_get_profile(b200reg_handle* h, long long* out7);
+
 /* raw CUDA stream of the handle (cudaStream_t) so a host can time or order work against it */
 int b200reg_get_stream(b200reg_handle* h, void** out_stream);
 

@@ -12,8 +12,14 @@ TOL_FIT = 1e-5  # relative
 
 
 def rot_angle(Ra, Rb):
+    """Rotation angle between two float32 rotation matrices.  arccos of the trace cannot resolve
+    angles below ~3e-4 rad from float32 entries (1 - cos(theta) drops under the float epsilon), so
+    the angle is taken from the skew part, sin(theta) = |vee(R - R^T)| / 2."""
     R = Ra.astype(np.float64).T @ Rb.astype(np.float64)
-    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2.0
+    s = float(np.linalg.norm(w))
+    c = float((np.trace(R) - 1.0) / 2.0)
+    return float(np.arctan2(s, c))
 
 
 @pytest.fixture(scope="module")
@@ -134,6 +140,8 @@ def test_ndt_align_parity(eng, oracle, scans, search):
         ref.align(g)
         aligned = ndt.align(g, want_aligned=True)
         T0, T1 = ref.getFinalTransformation(), ndt.getFinalTransformation()
+        print(f"{search}: iters gpu={ndt.getFinalNumIteration()} ref={ref.getFinalNumIteration()} dt={np.abs(T1[:3, 3] - T0[:3, 3])} dR={rot_angle(T0[:3, :3], T1[:3, :3]):.3e} "
+              f"fit gpu={ndt.getFitnessScore():.10f} ref={ref.getFitnessScore():.10f}")
         assert ndt.hasConverged() == ref.hasConverged()
         assert ndt.getFinalNumIteration() == ref.getFinalNumIteration(), "same Newton / line-search path"
         assert np.max(np.abs(T1[:3, 3] - T0[:3, 3])) < TOL_T

@@ -26,6 +26,7 @@ for search in ("DIRECT7", "DIRECT1", "KDTREE"):
     ndt.setInputSource(v1)
     print(search, "set_source", t(lambda: ndt.setInputSource(v1)))
     print(search, "align(identity)", t(lambda: ndt.align(None)), ndt.getResult()["iterations"], "iters", ndt.getResult()["evaluations"], "evals", ndt.getResult()["hits"], "hits")
+    print(search, "profile(cycles)", ndt.profile())
     print(search, "derivatives", t(lambda: ndt.ndt_derivatives(np.zeros(6))))
     print(search, "fitness", t(lambda: ndt.getFitnessScore()), ndt.getFitnessScore())
     print(search, "T err", np.abs(ndt.getFinalTransformation() - (np.linalg.inv(P0) @ P1)).max())
