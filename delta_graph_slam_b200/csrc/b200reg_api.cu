@@ -178,7 +178,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   B200_CUDA_TRY(h->jobs.reserve(1));
   B200_CUDA_TRY(h->d_result.reserve(1));
   B200_CUDA_TRY(h->deriv.reserve(64));
-  B200_CUDA_TRY(h->prof.reserve(8));
+  B200_CUDA_TRY(h->prof.reserve(16));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
   B200_CUDA_TRY(h->barriers.reserve(32));
   B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
@@ -649,7 +649,7 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   int rc = set_device(h);
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 7 * sizeof(long long), cudaMemcpyDeviceToHost));
+  B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 10 * sizeof(long long), cudaMemcpyDeviceToHost));
   return B200REG_OK;
 }
 

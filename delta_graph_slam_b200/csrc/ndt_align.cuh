@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
     const NdtJob& job = jobs[jb];
     const GridParams gp = job.grid.meta->grid;
     const int n_src = job.n_src;
-    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long ts0 = clock64();
     // ---- stage the target grid in shared memory when it fits
     NdtLookup look;
@@ -653,14 +653,18 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
             ndt_step(s, prm);
           }
         }
+        const long long tb = clock64();
         __syncwarp();
         if (s.new_pose) {
           pose_trig_warp(s, s.x_t, lane);
+          const long long tc = clock64();
           if (tid == 0) {
             pose_to_T(s.x_t, s.trig, s.T);
             angle_tables(s.trig, s.j_ang, s.h_ang);
+            prof[8] += tc - tb; prof[9] += clock64() - tc;
           }
         }
+        if (tid == 0) prof[7] += tb - t4;
       }
       __syncthreads();
       const long long t5 = clock64();
@@ -668,7 +672,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       if (s.phase == PH_DONE) break;
     }
     if (job.prof && rank == 0 && tid == 0)
-      for (int k = 0; k < 7; ++k) job.prof[k] = prof[k];
+      for (int k = 0; k < 10; ++k) job.prof[k] = prof[k];
     // ---- result
     if (rank == 0 && tid == 0) {
       if (job.eval_only) {

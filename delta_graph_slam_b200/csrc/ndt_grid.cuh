@@ -69,11 +69,12 @@ struct NdtLeafArgs {
   double *leaf_mean, *leaf_cov, *leaf_icov;
 };
 // ndt_leaf.cu (-fmad=false): statistics -> records, then the hash over the records
-cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen);
+cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen, double* sums, float* csum);
 
 struct NdtGrid {
   VoxelSort sort;
-  DevBuf<double> leaf_mean, leaf_cov, leaf_icov;
+  DevBuf<double> leaf_mean, leaf_cov, leaf_icov, sums;
+  DevBuf<float> csum;
   DevBuf<int32_t> leaf_n;
   DevBuf<NdtVoxel> voxels, stage_vox;
   DevBuf<float4> centroids, stage_cen;
@@ -84,7 +85,7 @@ struct NdtGrid {
   bool built = false;
 
   void release() {
-    sort.release(); leaf_mean.release(); leaf_cov.release(); leaf_icov.release(); leaf_n.release(); voxels.release(); centroids.release(); stage_vox.release(); stage_cen.release();
+    sort.release(); sums.release(); csum.release(); leaf_mean.release(); leaf_cov.release(); leaf_icov.release(); leaf_n.release(); voxels.release(); centroids.release(); stage_vox.release(); stage_cen.release();
     rec_key.release(); rec_flag.release(); table.release(); gmeta.release();
   }
 
@@ -107,6 +108,8 @@ struct NdtGrid {
     size_t cap = 16;
     while (cap < 2 * max_rec) cap <<= 1;
     if ((e = leaf_mean.reserve(nn * 3)) != cudaSuccess) return e;
+    if ((e = sums.reserve(nn * 9)) != cudaSuccess) return e;
+    if ((e = csum.reserve(nn * 3)) != cudaSuccess) return e;
     if ((e = leaf_cov.reserve(nn * 9)) != cudaSuccess) return e;
     if ((e = leaf_icov.reserve(nn * 9)) != cudaSuccess) return e;
     if ((e = leaf_n.reserve(nn)) != cudaSuccess) return e;
@@ -124,7 +127,7 @@ struct NdtGrid {
     a.min_points = 6; a.eig_mult = 0.01;
     a.gmeta = gmeta.p; a.voxels = voxels.p; a.centroids = centroids.p; a.rec_key = rec_key.p; a.rec_flag = rec_flag.p; a.table = table.p;
     a.leaf_n = leaf_n.p; a.leaf_mean = leaf_mean.p; a.leaf_cov = leaf_cov.p; a.leaf_icov = leaf_icov.p;
-    if ((e = launch_ndt_leaf_stats(st, a, stage_vox.p, stage_cen.p)) != cudaSuccess) return e;
+    if ((e = launch_ndt_leaf_stats(st, a, stage_vox.p, stage_cen.p, sums.p, csum.p)) != cudaSuccess) return e;
     built = true;
     return cudaGetLastError();
   }

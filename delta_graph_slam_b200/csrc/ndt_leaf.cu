@@ -10,22 +10,60 @@
 
 namespace b200 {
 
-// stage: per occupied slot, record + centroid (w: 0 = fewer than min_points, 1 = valid, 2 = rejected)
-static __global__ void __launch_bounds__(128) k_ndt_leaf_stats(NdtLeafArgs a, NdtVoxel* __restrict__ stage_vox, float4* __restrict__ stage_cen) {
+// pass 1: one CTA per occupied voxel (grid-stride).  All 256 threads gather 256 points of the run
+// into shared memory at once (one memory latency, zero padded), then lane a in 0..8 of warp 0 adds
+// statistic a (sum x y z, sum xx xy xz yy yz zz) point by point IN INPUT ORDER — nine independent
+// serial double chains, each bit-identical to the reference's per-leaf accumulation (adding the
+// zero padding changes nothing) — while lanes 9..11 do the float centroid sums.
+static __global__ void __launch_bounds__(256) k_ndt_leaf_sums(NdtLeafArgs a, double* __restrict__ sums /*[n_vox][9]*/, float* __restrict__ csum /*[n_vox][3]*/) {
+  __shared__ float4 s_pts[256];
   const uint32_t* vals = sorted_in_b(a.meta) ? a.vals_b : a.vals_a;
+  const int n_vox = (int)a.meta->n_vox;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // operand selectors of this lane's statistic
+  const int ia = lane < 3 ? lane : lane == 3 || lane == 4 || lane == 5 ? 0 : lane == 6 || lane == 7 ? 1 : 2;
+  const int ib = lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2;
+  const bool is_prod = lane >= 3 && lane < 9;
+  for (int slot = blockIdx.x; slot < n_vox; slot += gridDim.x) {
+    const uint32_t s = a.vox_start[slot], e = a.vox_start[slot + 1];
+    double acc = 0.0;
+    float accf = 0.f;
+    for (uint32_t c = s; c < e; c += 256) {
+      const int cnt = (int)min(256u, e - c);
+      __syncthreads();
+      s_pts[tid] = tid < cnt ? __ldg(a.pts + vals[c + tid]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      if (tid < 32) {
+        const int rounds = (cnt + 31) >> 5;
+        for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 p = s_pts[r * 32 + j];
+            const float fa = ia == 0 ? p.x : ia == 1 ? p.y : p.z;
+            const float fb = ib == 0 ? p.x : ib == 1 ? p.y : p.z;
+            const double term = is_prod ? (double)fa * (double)fb : (double)fa;
+            acc += term;
+            accf += (lane == 9 ? p.x : lane == 10 ? p.y : p.z);
+          }
+        }
+      }
+    }
+    if (tid < 9) sums[(size_t)slot * 9 + tid] = acc;
+    else if (tid < 12) csum[(size_t)slot * 3 + (tid - 9)] = accf;
+  }
+}
+
+// pass 2: one thread per occupied voxel: mean, covariance, eigenvalue clamp, inverse
+// stage: per occupied slot, record + centroid (w: 0 = fewer than min_points, 1 = valid, 2 = rejected)
+static __global__ void __launch_bounds__(64) k_ndt_leaf_stats(NdtLeafArgs a, const double* __restrict__ sums, const float* __restrict__ csum, NdtVoxel* __restrict__ stage_vox,
+                                                             float4* __restrict__ stage_cen) {
   const int n_vox = (int)a.meta->n_vox;
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_vox; slot += gridDim.x * blockDim.x) {
     const uint32_t s = a.vox_start[slot], e = a.vox_start[slot + 1];
     const int n = (int)(e - s);
-    double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    for (uint32_t j = s; j < e; ++j) {
-      const float4 p = __ldg(a.pts + vals[j]);
-      const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-      sx += x; sy += y; sz += z;
-      xx += x * x; xy += x * y; xz += x * z; yy += y * y; yz += y * z; zz += z * z;
-      cx += p.x; cy += p.y; cz += p.z;
-    }
+    const double* S = sums + (size_t)slot * 9;
+    const double sx = S[0], sy = S[1], sz = S[2], xx = S[3], xy = S[4], xz = S[5], yy = S[6], yz = S[7], zz = S[8];
+    const float cx = csum[(size_t)slot * 3], cy = csum[(size_t)slot * 3 + 1], cz = csum[(size_t)slot * 3 + 2];
     const double nd = (double)n;
     const double pt_sum[3] = {sx, sy, sz};
     const double mean[3] = {sx / nd, sy / nd, sz / nd};
@@ -140,9 +178,10 @@ static __global__ void __launch_bounds__(1024) k_ndt_table(NdtLeafArgs a, const 
   }
 }
 
-cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen) {
-  launch_counter() += 2;
-  k_ndt_leaf_stats<<<kNumSM, 128, 0, st>>>(a, stage_vox, stage_cen);
+cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen, double* sums, float* csum) {
+  launch_counter() += 3;
+  k_ndt_leaf_sums<<<kNumSM * 8, 256, 0, st>>>(a, sums, csum);
+  k_ndt_leaf_stats<<<kNumSM, 64, 0, st>>>(a, sums, csum, stage_vox, stage_cen);
   k_ndt_table<<<1, 1024, 0, st>>>(a, stage_vox, stage_cen);
   return cudaGetLastError();
 }

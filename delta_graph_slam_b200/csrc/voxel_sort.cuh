@@ -52,13 +52,26 @@ static __global__ void __launch_bounds__(256) k_minmax(const float4* __restrict_
     }
     any |= __shfl_xor_sync(0xffffffffu, any, o);
   }
-  if ((threadIdx.x & 31) == 0 && any) {
+  __shared__ float s_mn[8][3], s_mx[8][3];
+  __shared__ int s_any[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(mm + a, float_to_ordered(mn[a]));
-      atomicMax(mm + 3 + a, float_to_ordered(mx[a]));
+    for (int a = 0; a < 3; ++a) { s_mn[warp][a] = mn[a]; s_mx[warp][a] = mx[a]; }
+    s_any[warp] = any;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {  // one atomic pair per axis per block
+    const int a = threadIdx.x;
+    float lo = s_mn[0][a], hi = s_mx[0][a];
+    int an = s_any[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, s_mn[w][a]); hi = fmaxf(hi, s_mx[w][a]); an |= s_any[w]; }
+    if (an) {
+      atomicMin(mm + a, float_to_ordered(lo));
+      atomicMax(mm + 3 + a, float_to_ordered(hi));
+      if (a == 0) atomicOr(mm + 6, 1);
     }
-    atomicOr(mm + 6, 1);
   }
 }
 
@@ -132,7 +145,8 @@ static __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4*
 }
 
 // ---- radix sort: one pass = hist -> scan -> scatter --------------------------
-// hist[tile][digit] (tile-major so the scan reads coalesced rows)
+// hist[digit][tile]: digit-major, so the global order of the scatter (digit, then tile) is a flat
+// exclusive scan of the array
 template <int ITEMS>
 static __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, int n, int pass, const SortMeta* __restrict__ meta, uint32_t* __restrict__ hist) {
   if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
@@ -147,32 +161,58 @@ static __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_
     if (i < n) atomicAdd(&s[(keys[i] >> shift) & (kRadix - 1)], 1u);
   }
   __syncthreads();
-  hist[blockIdx.x * kRadix + threadIdx.x] = s[threadIdx.x];
+  hist[threadIdx.x * gridDim.x + blockIdx.x] = s[threadIdx.x];
 }
 
-// exclusive scan over (digit-major, tile-minor) order, in place
-static __global__ void __launch_bounds__(kRadix) k_sort_scan(uint32_t* __restrict__ hist, int n_tiles, int pass, const SortMeta* __restrict__ meta) {
+// exclusive scan of the flat hist[digit][tile] array, in place; one block.  Each thread owns up to
+// 16 consecutive uint4 (all loads issued up front, prefix in registers), the 1024 thread totals are
+// scanned with shuffles.  The array (kRadix * n_tiles <= 65536 counters) is a multiple of 4 long.
+static __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, int n_tiles, int pass, const SortMeta* __restrict__ meta) {
   if ((uint32_t)(pass * kRadixBits) >= meta->nbits) return;
-  __shared__ uint32_t s_tot[kRadix];
-  const int d = threadIdx.x;
-  uint32_t run = 0;
-  for (int t = 0; t < n_tiles; ++t) {
-    uint32_t c = hist[t * kRadix + d];
-    hist[t * kRadix + d] = run;
-    run += c;
+  __shared__ uint32_t s_warp[32];
+  const int N = kRadix * n_tiles;           // multiple of 4 (kRadix is)
+  const int nvec = N >> 2;
+  const int V = (nvec + 1023) / 1024;       // uint4 per thread, <= 16
+  const int vbase = threadIdx.x * V;
+  uint4* h4 = reinterpret_cast<uint4*>(hist);
+  uint4 v[16];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (i < V && vbase + i < nvec) v[i] = h4[vbase + i];
   }
-  s_tot[d] = run;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  // exclusive scan of the 256 digit totals (Hillis-Steele in shared memory)
-  uint32_t v = run;
-  for (int o = 1; o < kRadix; o <<= 1) {
-    uint32_t add = d >= o ? s_tot[d - o] : 0;
-    __syncthreads();
-    s_tot[d] += add;
-    __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
   }
-  uint32_t excl = s_tot[d] - v;
-  for (int t = 0; t < n_tiles; ++t) hist[t * kRadix + d] += excl;
+  __syncthreads();
+  uint32_t run = s_warp[warp] + incl - sum;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint4 o;
+    o.x = run; run += v[i].x;
+    o.y = run; run += v[i].y;
+    o.z = run; run += v[i].z;
+    o.w = run; run += v[i].w;
+    if (i < V && vbase + i < nvec) h4[vbase + i] = o;
+  }
 }
 
 // stable scatter: each warp owns a contiguous slice of the tile and walks it in rounds of 32
@@ -204,7 +244,7 @@ static __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint
   // phase B: digit bases for every warp = global base of (digit, tile) + counts of lower warps
   {
     const int d = threadIdx.x;  // kSortThreads == kRadix
-    uint32_t run = hist[blockIdx.x * kRadix + d];
+    uint32_t run = hist[d * gridDim.x + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
       uint32_t c = cnt[w][d];
@@ -360,7 +400,9 @@ struct VoxelSort {
     launch_counter() += 4 + (n > 0 ? 1 : 0) + (n > 0 ? 12 : 0);  // init, minmax, keys, 4 x (hist, scan, scatter), 2 x segmentation
     int blocks = n > 0 ? (n + 255) / 256 : 1;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
-    if (n > 0) k_minmax<<<blocks, 256, 0, st>>>(d_pts, n, is_dense, mm.p);
+    int mm_blocks = n > 0 ? (n + 1023) / 1024 : 1;
+    if (mm_blocks > kNumSM * 2) mm_blocks = kNumSM * 2;
+    if (n > 0) k_minmax<<<mm_blocks, 256, 0, st>>>(d_pts, n, is_dense, mm.p);
     k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
     if (n > 0) {
       for (int pass = 0; pass < 4; ++pass) {
@@ -372,7 +414,7 @@ struct VoxelSort {
 #define B200_SORT_PASS(IT)                                                                              \
   case IT:                                                                                              \
     k_sort_hist<IT><<<n_tiles, kSortThreads, 0, st>>>(ki, n, pass, meta.p, hist.p);                    \
-    k_sort_scan<<<1, kRadix, 0, st>>>(hist.p, n_tiles, pass, meta.p);                                  \
+    k_sort_scan<<<1, 1024, 0, st>>>(hist.p, n_tiles, pass, meta.p);                                  \
     k_sort_scatter<IT><<<n_tiles, kSortThreads, 0, st>>>(ki, vi, ko, vo, n, pass, meta.p, hist.p);     \
     break;
           B200_SORT_PASS(4)

@@ -178,9 +178,9 @@ class Registration:
         return dict(launches_total=a.value, timed_aligns=b.value, align_kernel_ms=c.value)
 
     def profile(self):
-        v = np.zeros(7, np.int64)
+        v = np.zeros(10, np.int64)
         self._ck(_lib.load().b200reg_get_profile(self._h, v.ctypes.data))
-        return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage"), v.tolist()))
+        return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage", "step_solve_mt", "step_trig", "step_tables"), v.tolist()))
 
     def stream(self):
         p = C.c_void_p()

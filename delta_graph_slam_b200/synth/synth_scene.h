@@ -50,6 +50,7 @@ SYNTH_HD double gauss(uint64_t a, uint64_t b) {
 // ---- scene -----------------------------------------------------------------
 constexpr double kGroundZ = -1.73;
 constexpr double kCellLen = 10.0;
+constexpr double kGroundRange = 30.0;
 
 struct Box { double lo[3], hi[3]; };
 
@@ -108,9 +109,9 @@ SYNTH_HD double cast_ray(uint64_t scene_seed, const double o[3], const double d[
   double best = tmax;
   bool hit = false;
   *fuzzy = false;
-  if (d[2] < -1e-9) {  // ground plane
-    double t = (kGroundZ - o[2]) / d[2];
-    if (t > 0.0 && t < best) { best = t; hit = true; *fuzzy = false; }
+  if (d[2] < -1e-9) {  // ground plane; returns at grazing incidence (beyond kGroundRange) are lost,
+    double t = (kGroundZ - o[2]) / d[2];  // as on a real sensor, which also removes the far ring arcs
+    if (t > 0.0 && t < best && t < kGroundRange) { best = t; hit = true; *fuzzy = false; }
   }
   long c0 = (long)floor((o[0] - tmax) / kCellLen), c1 = (long)floor((o[0] + tmax) / kCellLen);
   for (long c = c0; c <= c1; ++c) {
@@ -151,7 +152,7 @@ SYNTH_HD double cast_ray(uint64_t scene_seed, const double o[3], const double d[
         double t = hit_sphere(bx, by, kGroundZ + 0.6 * br, br, o, d, best);
         if (t > 0.0 && t < best) { best = t; hit = true; *fuzzy = true; }
       }
-      if (uni(scene_seed, key, 5) < 0.4) {  // parked car
+      if (uni(scene_seed, key, 5) < 0.7) {  // parked car
         double cx = x0 + 5.0 * uni(scene_seed, key, 6);
         double cy = sgn * (3.6 + 0.6 * uni(scene_seed, key, 7));
         b.lo[0] = cx; b.hi[0] = cx + 4.5;
@@ -201,12 +202,13 @@ inline void pose_from_xyzrpy(const double v[6], double T[16]) {
   for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c]; T[4 * r + 3] = v[r]; }
   T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
 }
+constexpr double kStep = 0.5;  // 5 m/s at 10 Hz
 inline void traj_kitti_like(long k, uint64_t seed, double T[16]) {
-  // yaw(k) = 0.1 sin(2 pi k / 100); position integrates the heading at 1 m / frame
+  // yaw(k) = 0.1 sin(2 pi k / 100); position integrates the heading at kStep m / frame
   double x = 0.0, y = 0.0;
   for (long i = 0; i < k; ++i) {
     double yaw = 0.1 * sin(6.283185307179586 * (double)i / 100.0);
-    x += cos(yaw); y += sin(yaw);
+    x += kStep * cos(yaw); y += kStep * sin(yaw);
   }
   double v[6];
   v[0] = x; v[1] = y;
