@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""bench.py — scan registrations/sec of the B200 engine on the reference's odometry path.
+"""bench.py — throughput of the B200 scan-registration engine on the reference's two callers.
 
-Workload (BASELINE.json configs[1]): 1000 consecutive synthetic HDL-64-shaped scans (`street_v1`
-scene, `kitti_like` trajectory, ~1.3e5 points each) through PrefilteringNodelet::downsample
-(VoxelGrid 0.1 m) and ScanMatchingOdometryNodelet::matching (NDT_OMP-equivalent: DIRECT7,
-resolution 1.0, epsilon 0.01, 64 iterations; keyframe_delta 1.0 / 1.0 / 10000 as in
-launch/delta_graph_slam.launch).  One "step" is one pass over the whole sequence.
+Headline workload (BASELINE.json configs[1], N = 1): 1000 consecutive synthetic HDL-64-shaped scans
+(`street_v1` scene, `kitti_like` trajectory, ~1.3e5 points each) through
+PrefilteringNodelet::downsample (VoxelGrid 0.1 m) and ScanMatchingOdometryNodelet::matching
+(NDT_OMP-equivalent: DIRECT7, resolution 1.0, epsilon 0.01, 64 iterations; keyframe_delta
+1.0 / 1.0 / 10000 as in launch/delta_graph_slam.launch).  One "step" is one pass over the sequence.
 
   value : registrations/s with the raw scans already resident in HBM (device pointers through the
           C ABI); `e2e`: the same pipeline through the host-buffer calls the reference's nodelets
@@ -15,13 +15,17 @@ launch/delta_graph_slam.launch).  One "step" is one pass over the whole sequence
           (point, voxel) hit) / its CUDA-event duration, against the measured HBM peak.
   cpu_baseline : the oracle restatement of ndt_omp + pcl::VoxelGrid on the host cores, on the first
           frames of the same sequence.
-  --impl reference : that CPU path as its own arm (the reference's libraries cannot be built here).
+  loop_batch : BASELINE.json configs[3] in the same run — 256 new keyframes x 16 candidates = 4096
+          NDT + getFitnessScore pairs (LoopDetector::matching), whole targets sharded over the N
+          ranks, one NCCL all-gather of the result records; pairs/s = 4096 / max-over-ranks time
+          (strong scaling).  `--workload loop` makes this the headline line instead.
+  --impl reference : the CPU path as its own arm (the reference's libraries cannot be built here,
+          so it is the oracle restatement with OpenMP on all host cores).
 
-With N > 1 (torchrun) every rank runs an independent sequence on its own GPU ("replicas only":
-frame k's guess is frame k-1's result); the time is the max over ranks.
+With N > 1 (torchrun) every rank runs an independent odometry sequence on its own GPU ("replicas
+only": frame k's guess is frame k-1's result); times are the max over ranks.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -39,7 +43,9 @@ ODOM_PARAMS = dict(  # launch/delta_graph_slam.launch:50-69 (NDT_OMP instead of 
     registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64,
 )
 PREFILTER_PARAMS = dict(downsample_method="VOXELGRID", downsample_resolution=0.1)
+LOOP_PARAMS = dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64)
 DEVNULL = open(os.devnull, "w")
+DBL_MAX = float(np.finfo(np.float64).max)
 
 
 def load_peaks():
@@ -47,7 +53,7 @@ def load_peaks():
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -90,7 +96,7 @@ class ClockSampler:
 
 
 def run_sequence(pre, odo, clouds, out_buf=None):
-    """Prefilter + matching over a list of clouds; returns (poses, per-align stats)."""
+    """Prefilter + matching over a list of clouds; returns the poses."""
     poses = []
     for k, cloud in enumerate(clouds):
         filtered = pre.downsample(cloud, out=out_buf) if out_buf is not None else pre.downsample(cloud)
@@ -113,7 +119,7 @@ def oracle_odometry(oracle, threads=0):
     return OraclePrefilter(oracle), ScanMatchingOdometry(ODOM_PARAMS, registration=reg, out=DEVNULL)
 
 
-def time_oracle(host_clouds, frames):
+def time_oracle_odometry(host_clouds, frames):
     from oracle import oracle_py as oracle
     pre, odo = oracle_odometry(oracle)
     t0 = time.perf_counter()
@@ -122,29 +128,48 @@ def time_oracle(host_clouds, frames):
     return (frames - 1) / dt, oracle.lib().orc_max_threads(), dt
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=1000, help="scans per sequence (one step = one pass over the sequence)")
-    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the sequence the CPU baseline runs")
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the --impl reference arm")
-    args = ap.parse_args()
+def oracle_loop_pairs(oracle, clouds, pairs):
+    """The reference's serial candidate loop on the CPU: setInputTarget once per target, then per
+    candidate setInputSource + align + getFitnessScore.  Returns seconds."""
+    reg = oracle.Registration(oracle.NDT, resolution=LOOP_PARAMS["reg_resolution"], nn_search=oracle.DIRECT7, trans_eps=LOOP_PARAMS["reg_transformation_epsilon"],
+                              max_iter=LOOP_PARAMS["reg_maximum_iterations"])
+    t0 = time.perf_counter()
+    last = None
+    for p in pairs:
+        if int(p["target_id"]) != last:
+            reg.setInputTarget(clouds[int(p["target_id"])])
+            last = int(p["target_id"])
+        reg.setInputSource(clouds[int(p["source_id"])])
+        reg.align(np.array(p["guess"], np.float32).reshape(4, 4).T)
+        reg.getFitnessScore(DBL_MAX)
+    return time.perf_counter() - t0
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    if args.impl == "reference":
-        # the reference's CPU implementation of the path, restated (oracle); rank 0 only
-        if rank != 0:
-            return 0
-        from oracle import oracle_py as oracle
+def reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle restatement, OpenMP on
+    all host cores) on a bounded sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return 0
+    from oracle import oracle_py as oracle
+    cores = oracle.lib().orc_max_threads()
+    if args.workload == "loop":
+        from delta_graph_slam_b200.loop_batch import make_pairs
+        from delta_graph_slam_b200.synth.loop_scenario import loop_scenario
+        sc = loop_scenario(oracle.synth_traj, n_targets=1, n_candidates=args.loop_cpu_pairs)
+        clouds = {cid: oracle.voxelgrid(oracle.synth_scan(P, noise_seed=ns), 0.1)["out"] for cid, P, ns in sc["targets"] + sc["candidates"]}
+        pairs = make_pairs([(t, c, g) for t, c, g, _ in sc["pairs"]])
+        for _ in range(args.warmup):
+            oracle_loop_pairs(oracle, clouds, pairs)
+        dt = sum(oracle_loop_pairs(oracle, clouds, pairs) for _ in range(args.steps))
+        value = args.steps * len(pairs) / dt
+        metric, unit = "loop pairs/sec (NDT + fitness)", "pairs/s"
+        sample = f"{len(pairs)} candidate pairs of one new keyframe per step (setInputTarget once, then align + getFitnessScore per candidate), oracle restatement of ndt_omp + pcl::Registration"
+        cfg = {"workload": "LoopDetector batch: NDT DIRECT7 + getFitnessScore candidate pairs (BASELINE configs[3])", "pairs_per_step": len(pairs)}
+    else:
         n = args.ref_frames
         clouds = [oracle.synth_scan(oracle.synth_traj(k), noise_seed=1000 + k) for k in range(n)]
         pre, _ = oracle_odometry(oracle)
+
         def one_step():
             _, odo = oracle_odometry(oracle)
             run_sequence(pre, odo, clouds)
@@ -155,26 +180,75 @@ def main():
             one_step()
         dt = time.perf_counter() - t0
         value = args.steps * (n - 1) / dt
-        cores = oracle.lib().orc_max_threads()
+        metric, unit = "scan registrations/sec (NDT keyframe odometry)", "registrations/s"
         sample = f"first {n} frames of the sequence per step (VoxelGrid 0.1 + NDT DIRECT7 keyframe odometry), oracle restatement of pcl::VoxelGrid + ndt_omp"
-        print(json.dumps({
-            "impl": "reference", "metric": "scan registrations/sec (NDT keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
-            "config": {"workload": "scan_matching_odometry NDT DIRECT7, synthetic HDL-64 street_v1 / kitti_like sequence", "frames_per_step": n, "registration": "NDT_OMP DIRECT7 res 1.0 eps 0.01"},
-            "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
-        return 0
+        cfg = {"workload": "scan_matching_odometry: synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])", "frames_per_step": n,
+               "registration": "NDT_OMP DIRECT7 res 1.0 eps 0.01 max_iter 64"}
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak" if args.workload == "odometry" else "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
 
-    import torch
+
+class Ctx:
+    """Per-process bench context: device, rank plumbing, event timing on the engine's stream."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dev = self.local_rank
+        torch.cuda.set_device(self.dev)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.dev))
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return vals
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=f"cuda:{self.dev}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def timed(self, fn, stream_ptr, steps, warmup):
+        """fn(i) -> stats.  (seconds by CUDA events on the engine stream, wall seconds, stats), max over ranks."""
+        torch = self.torch
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        stream = torch.cuda.ExternalStream(stream_ptr, device=f"cuda:{self.dev}")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stats = []
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            stats.append(fn(i))
+        e1.record(stream)
+        e1.synchronize()
+        wall = time.perf_counter() - w0
+        self.barrier()
+        sec, wall = self.max_over_ranks(e0.elapsed_time(e1) * 1e-3, wall)
+        return sec, wall, stats
+
+
+def bench_odometry(ctx):
     import delta_graph_slam_b200 as eng
     from delta_graph_slam_b200 import synth
-
-    dev = local_rank
-    torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    torch, args, dev, rank, world = ctx.torch, ctx.args, ctx.dev, ctx.rank, ctx.world
 
     # ---- synthetic sequence, generated on the device; a pinned host copy feeds the e2e leg
     F = args.frames
@@ -198,43 +272,13 @@ def main():
         odo = eng.ScanMatchingOdometry(ODOM_PARAMS, device=dev, out=DEVNULL)
         return pre, odo
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        """fn(step_index) -> stats; returns (seconds by CUDA events on the engine stream, wall seconds, stats list)."""
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        pre, odo = fn.pipeline
-        stream = torch.cuda.ExternalStream(odo.registration.stream(), device=f"cuda:{dev}")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stats = []
-        w0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(steps):
-            stats.append(fn(i))
-        e1.record(stream)
-        e1.synchronize()
-        wall = time.perf_counter() - w0
-        barrier()
-        sec = e0.elapsed_time(e1) * 1e-3
-        if world > 1:
-            t = torch.tensor([sec, wall], dtype=torch.float64, device=f"cuda:{dev}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec, wall = float(t[0]), float(t[1])
-        return sec, wall, stats
-
     # ---- device-resident leg (value) + roofline of the align kernel
     pre_d, odo_d = new_pipeline()
     odo_d.registration.setTiming(True)
 
     def step_device(i):
         odo_d.keyframe = None  # restart the sequence; engine buffers stay allocated
-        alg_bytes, evals, hits, n_src_tot = 0, 0, 0, 0
+        alg_bytes, evals, hits = 0, 0, 0
         for k, cloud in enumerate(dev_clouds):
             filtered = pre_d.downsample(cloud, out=ds_buf)
             odo_d.matching(0.1 * k, filtered)
@@ -243,19 +287,16 @@ def main():
                 alg_bytes += 16 * filtered.n * r["evaluations"] + 48 * r["hits"]
                 evals += r["evaluations"]
                 hits += r["hits"]
-                n_src_tot += filtered.n
-        return dict(alg_bytes=alg_bytes, evals=evals, hits=hits, n_src=n_src_tot, keyframes=odo_d.num_keyframes)
-    step_device.pipeline = (pre_d, odo_d)
+        return dict(alg_bytes=alg_bytes, evals=evals, hits=hits, keyframes=odo_d.num_keyframes)
 
     sampler = ClockSampler(dev)
     with sampler:
         c0 = odo_d.registration.counters()
-        sec_d, wall_d, st_d = timed(step_device, args.steps, args.warmup)
+        sec_d, wall_d, st_d = ctx.timed(step_device, odo_d.registration.stream(), args.steps, args.warmup)
         c1 = odo_d.registration.counters()
     regs_per_step = F - 1
     value = world * args.steps * regs_per_step / sec_d
-    # the counters also saw the warm-up steps: per-launch averages are over everything timed by the library
-    n_al = c1["timed_aligns"] - 0
+    n_al = c1["timed_aligns"]  # the counters also saw the warm-up steps: per-launch averages over everything the library timed
     align_ms = c1["align_kernel_ms"]
     alg_bytes_per_launch = sum(s["alg_bytes"] for s in st_d) / (args.steps * regs_per_step)
     avg_launch_ms = align_ms / max(n_al, 1)
@@ -275,49 +316,211 @@ def main():
             h2d += cloud.nbytes + filtered.nbytes
             d2h += filtered.nbytes + 128
         return dict(h2d=h2d, d2h=d2h)
-    step_host.pipeline = (pre_h, odo_h)
-    sec_h, wall_h, st_h = timed(step_host, args.steps, max(1, args.warmup // 3))
+    sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), args.steps, args.warmup)
     e2e_value = world * args.steps * regs_per_step / sec_h
 
     # ---- parity of the two legs (same inputs -> same poses) and odometry sanity vs ground truth
+    nchk = min(50, F)
     pre_c, odo_c = new_pipeline()
-    poses_dev = run_sequence(pre_c, odo_c, dev_clouds[:50], out_buf=ds_buf)
+    poses_dev = run_sequence(pre_c, odo_c, dev_clouds[:nchk], out_buf=ds_buf)
     pre_c2, odo_c2 = new_pipeline()
-    poses_host = run_sequence(pre_c2, odo_c2, host_clouds[:50])
+    poses_host = run_sequence(pre_c2, odo_c2, host_clouds[:nchk])
     legs_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_host))
     P0 = synth.traj_kitti_like(5000 * rank)
-    gt = np.linalg.inv(P0) @ synth.traj_kitti_like(49 + 5000 * rank)
-    drift = float(np.linalg.norm(poses_dev[49][:3, 3] - gt[:3, 3]))
+    gt = np.linalg.inv(P0) @ synth.traj_kitti_like(nchk - 1 + 5000 * rank)
+    drift = float(np.linalg.norm(poses_dev[nchk - 1][:3, 3] - gt[:3, 3]))
 
     # ---- CPU baseline (rank 0, N = 1): the oracle on the first frames of the same sequence
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 1:
-        v, cores, dt = time_oracle(host_clouds, min(args.cpu_frames, F))
+        v, cores, dt = time_oracle_odometry(host_clouds, min(args.cpu_frames, F))
         cpu = {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
                "sample": f"first {min(args.cpu_frames, F)} frames of the same sequence ({dt:.1f} s): oracle restatement of pcl::VoxelGrid 0.1 m + ndt_omp DIRECT7 keyframe odometry, OpenMP on all host cores"}
 
-    if rank == 0:
-        out = {
-            "metric": "scan registrations/sec (NDT keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec_d / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
-            "config": {"workload": "scan_matching_odometry: 1000 consecutive synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])",
-                       "frames_per_step": F, "points_per_scan": int(np.mean(counts)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64",
-                       "l2": "each step streams 1000 distinct scans (2.1 GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
-                       "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
-            "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / args.steps,
-                    "wall_ms_per_step": 1e3 * wall_h / args.steps},
-            "gpu_launches": int(launches_timed),
-            "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
-                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms, "launches": int(n_al),
-                         "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / args.steps),
-                         "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
-            "cpu_baseline": cpu,
-            "clocks": sampler.summary(),
-            "checks": {"device_and_host_legs_bit_identical_first_50_frames": bool(legs_equal), "position_error_after_49_m": drift, "wall_ms_per_step": 1e3 * wall_d / args.steps},
-        }
+    out = {
+        "metric": "scan registrations/sec (NDT keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec_d / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
+        "config": {"workload": "scan_matching_odometry: 1000 consecutive synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])",
+                   "frames_per_step": F, "points_per_scan": int(np.mean(counts)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64",
+                   "l2": f"each step streams {F} distinct scans ({F * rays * 16 / 1e9:.1f} GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
+                   "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
+        "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / args.steps,
+                "wall_ms_per_step": 1e3 * wall_h / args.steps},
+        "gpu_launches": int(launches_timed),
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms, "launches": int(n_al),
+                     "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / args.steps),
+                     "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+        "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
+                   "wall_ms_per_step": 1e3 * wall_d / args.steps},
+    }
+    del d_raw, h_raw
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_loop(ctx, steps, warmup):
+    """BASELINE.json configs[3]: the loop-candidate batch, whole targets sharded over the ranks."""
+    import delta_graph_slam_b200 as eng
+    from delta_graph_slam_b200 import loop_batch, synth
+    from delta_graph_slam_b200.synth.loop_scenario import loop_scenario
+    torch, args, dev, rank, world = ctx.torch, ctx.args, ctx.dev, ctx.rank, ctx.world
+
+    sc = loop_scenario(synth.traj_kitti_like, n_targets=args.loop_targets, n_candidates=args.loop_candidates)
+    pairs = loop_batch.make_pairs([(t, c, g) for t, c, g, _ in sc["pairs"]])
+    n_pairs = len(pairs)
+    shards = loop_batch.shard_by_target(pairs["target_id"], world)
+    mine = pairs[shards[rank]]
+    need = set(loop_batch.needed_clouds(pairs, shards[rank]))
+    my_targets = sorted(set(mine["target_id"].tolist()))
+
+    # ---- this rank's keyframe clouds: ray-cast and down-sampled (0.1 m) on the device, packed in one buffer
+    rays = synth.num_rays(synth.HDL64)
+    vg = eng.VoxelGrid(device=dev)
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    d_raw = torch.empty((rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
+    d_tmp = torch.empty((rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
+    specs = [(cid, P, ns) for cid, P, ns in sc["targets"] + sc["candidates"] if cid in need]
+    cap = 70000
+    d_kf = torch.empty((len(specs), cap, 4), dtype=torch.float32, device=f"cuda:{dev}")
+    kf_n, slot_of = [], {}
+    for s, (cid, P, ns) in enumerate(specs):
+        n = synth.scan_to_device(d_raw.data_ptr(), P, synth.HDL64, scene_seed=1, noise_seed=ns, device=dev)
+        vg.setInputCloud(eng.DeviceCloud(d_raw.data_ptr(), n, d_raw), is_dense=False)
+        f = vg.filter(out=eng.DeviceCloud(d_tmp.data_ptr(), rays, d_tmp))
+        if f.n > cap:
+            raise RuntimeError(f"down-sampled keyframe has {f.n} points, more than the bench buffer holds")
+        d_kf[s, : f.n].copy_(d_tmp[: f.n])  # the filter call returned after its stream drained
+        torch.cuda.synchronize()            # d_tmp / d_raw are reused by the next keyframe
+        kf_n.append(f.n)
+        slot_of[cid] = s
+    torch.cuda.synchronize()
+    dev_cloud = {cid: eng.DeviceCloud(d_kf[s].data_ptr(), kf_n[s], d_kf) for cid, s in slot_of.items()}
+    h_kf = torch.empty((len(specs), cap, 4), dtype=torch.float32, pin_memory=True)
+    h_kf.copy_(d_kf)
+    torch.cuda.synchronize()
+    h_np = h_kf.numpy()
+    host_cloud = {cid: h_np[s, : kf_n[s]] for cid, s in slot_of.items()}
+
+    reg = eng.select_registration_method(LOOP_PARAMS, device=dev, out=DEVNULL)
+    reg.setTiming(True)
+    gdev = f"cuda:{dev}"
+
+    # ---- device-resident leg: keyframes already in HBM; a step re-registers the targets (their NDT
+    # grid and NN structure are rebuilt: the setInputTarget of every new keyframe), aligns and scores
+    # this rank's pairs, and gathers all result records
+    for cid in need:
+        reg.cloudPut(cid, dev_cloud[cid])
+    last = {}
+
+    def step_device(i):
+        for t in my_targets:
+            reg.cloudPut(t, dev_cloud[t])
+        local = reg.alignBatch(mine, with_fitness=True, fitness_max_range=DBL_MAX)
+        last["res"] = loop_batch.gather_results(local, shards, rank, world, device=gdev)
+        last["local"] = local
+        return reg.batchTiming()
+    sampler = ClockSampler(dev)
+    with sampler:
+        c0 = reg.counters()
+        sec_d, wall_d, st_d = ctx.timed(step_device, reg.stream(), steps, warmup)
+        c1 = reg.counters()
+    value = steps * n_pairs / sec_d
+    res = last["res"]
+    local = last["local"]
+    alg_bytes = float(sum(16 * kf_n[slot_of[int(p["source_id"])]] * int(r["evaluations"]) + 48 * int(r["hits"]) for p, r in zip(mine, local)))
+    align_ms = float(np.mean([s["align_kernel_ms"] for s in st_d]))
+    fit_ms = float(np.mean([s["fitness_ms"] for s in st_d]))
+    peak, peak_kind = load_peaks()
+    achieved = alg_bytes / (align_ms * 1e-3) / 1e9 if align_ms > 0 else 0.0
+
+    # ---- host-buffer leg (e2e): every keyframe cloud of the share uploaded from pinned host memory each step
+    reg_h = eng.select_registration_method(LOOP_PARAMS, device=dev, out=DEVNULL)
+    h2d = sum(host_cloud[cid].nbytes for cid in need) + mine.nbytes
+
+    def step_host(i):
+        for cid in need:
+            reg_h.cloudPut(cid, host_cloud[cid])
+        local_h = reg_h.alignBatch(mine, with_fitness=True, fitness_max_range=DBL_MAX)
+        last["res_h"] = loop_batch.gather_results(local_h, shards, rank, world, device=gdev)
+        return None
+    sec_h, wall_h, _ = ctx.timed(step_host, reg_h.stream(), steps, warmup)
+    e2e_value = steps * n_pairs / sec_h
+
+    # ---- checks: both legs identical; recovered poses against the scenario's ground truth
+    legs_equal = bool(np.array_equal(res.view(np.uint8), last["res_h"].view(np.uint8)))
+    err_t = []
+    for r, (_, _, _, rel) in zip(res, sc["pairs"]):
+        T = np.array(r["transformation"], np.float32).reshape(4, 4).T
+        err_t.append(float(np.max(np.abs(T[:3, 3] - rel[:3, 3]))))
+    err_t = np.array(err_t)
+
+    cpu = None
+    if rank == 0 and world == 1 and args.loop_cpu_pairs > 0:
+        from oracle import oracle_py as oracle
+        k = min(args.loop_cpu_pairs, args.loop_candidates)
+        sub = pairs[:k]
+        clouds = {int(c): np.array(host_cloud[int(c)]) for c in set(sub["target_id"].tolist()) | set(sub["source_id"].tolist())}
+        dt = oracle_loop_pairs(oracle, clouds, sub)
+        cpu = {"value": k / dt, "unit": "pairs/s", "cores": oracle.lib().orc_max_threads(), "kind": "port",
+               "sample": f"first {k} pairs of the same batch ({dt:.1f} s): setInputTarget once, then align + getFitnessScore per candidate; oracle restatement of ndt_omp + pcl::Registration, OpenMP on all host cores"}
+
+    out = {
+        "metric": "loop pairs/sec (NDT + fitness)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec_d / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
+        "config": {"workload": f"LoopDetector batch: {args.loop_targets} new keyframes x {args.loop_candidates} candidates = {n_pairs} NDT DIRECT7 + getFitnessScore pairs (BASELINE configs[3])",
+                   "points_per_keyframe": int(np.mean(kf_n)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
+                   "sharding": "whole targets per rank, one all-gather of 104-byte result records", "pairs_this_rank": int(len(mine)),
+                   "l2": f"{len(specs)} distinct keyframe clouds ({sum(kf_n) * 16 / 1e9:.2f} GB) per rank: inputs larger than L2",
+                   "passes_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
+        "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7> (one CTA per registration)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+        "checks": {"device_and_host_legs_bit_identical": legs_equal, "median_translation_error_m": float(np.median(err_t)), "pairs_within_5cm_of_ground_truth": float(np.mean(err_t < 0.05)),
+                   "wall_ms_per_step": 1e3 * wall_d / steps},
+    }
+    del d_kf, h_kf
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="odometry", choices=["odometry", "loop"], help="headline line: odometry (configs[1]) or the loop-candidate batch (configs[3])")
+    ap.add_argument("--frames", type=int, default=1000, help="scans per sequence (one odometry step = one pass over the sequence)")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the sequence the CPU baseline runs")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the --impl reference arm")
+    ap.add_argument("--loop-targets", type=int, default=256, help="new keyframes of the loop batch (x candidates = pairs)")
+    ap.add_argument("--loop-candidates", type=int, default=16)
+    ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
+    ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+
+    ctx = Ctx(args)
+    if args.workload == "loop":
+        out = bench_loop(ctx, args.steps, args.warmup)
+    else:
+        out = bench_odometry(ctx)
+        if not args.no_loop:
+            lb = bench_loop(ctx, max(1, min(args.steps, 2)), 3)
+            out["loop_batch"] = {k: lb[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "checks")}
+    if ctx.rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
     return 0
 
 

@@ -9,6 +9,9 @@
 #include <vector>
 
 #include "../../include/b200reg.h"
+#include <map>
+
+#include "loop_batch.cuh"
 #include "ndt_align.cuh"
 #include "nn_grid.cuh"
 #include "voxelgrid.cuh"
@@ -47,6 +50,17 @@ struct b200reg_handle {
   NnGrid nn;
   bool nn_stale = true;
   DevBuf<double> fit_partials;
+
+  // loop-closure batches: keyframe cloud cache + batch staging
+  std::map<long long, CachedCloud> cache;
+  DevBuf<b200reg_result> batch_results;
+  DevBuf<FitJob> fit_jobs;
+  DevBuf<float> batch_d2;
+  DevBuf<uint2> batch_pending;
+  DevBuf<unsigned int> batch_n_pending;
+  PinnedBuf<unsigned char> pin_batch;
+  double batch_align_ms = 0.0;  // last batch: duration of the align kernel (timing on)
+  double batch_fitness_ms = 0.0;
 
   b200reg_result last;
   bool have_result = false;
@@ -153,7 +167,8 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   const NdtJob* jobs = h->jobs.p;
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
-  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers};
+  unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue};
   // the staged target grid lives in opt-in dynamic shared memory (one CTA per SM)
   cudaError_t e = cudaFuncSetAttribute((const void*)k_ndt_align<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
   if (e != cudaSuccess) return e;
@@ -180,7 +195,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   B200_CUDA_TRY(h->deriv.reserve(64));
   B200_CUDA_TRY(h->prof.reserve(16));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
-  B200_CUDA_TRY(h->barriers.reserve(32));
+  B200_CUDA_TRY(h->barriers.reserve(64));
   B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
   NdtJob* job = reinterpret_cast<NdtJob*>(h->pin_small.p);
   memset(job, 0, sizeof(NdtJob));
@@ -204,7 +219,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
     job->p0[3] = eul[0]; job->p0[4] = eul[1]; job->p0[5] = eul[2];
   }
   B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, job, sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
-  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 32 * sizeof(unsigned int), h->stream));
+  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 64 * sizeof(unsigned int), h->stream));
   if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1));
   launch_counter() += 1;
@@ -285,6 +300,9 @@ int b200reg_destroy(b200reg_handle* h) {
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
+  for (auto& kv : h->cache) kv.second.release();
+  h->cache.clear();
+  h->batch_results.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_n_pending.release(); h->pin_batch.release();
   delete h;
   return B200REG_OK;
 }
@@ -559,6 +577,202 @@ int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_
   size_t np = n_points < (size_t)h->vg_last_n ? n_points : (size_t)h->vg_last_n;
   if (key && np) B200_CUDA_TRY(cudaMemcpyAsync(key, h->vg_sort.point_key.p, np * 4, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return B200REG_OK;
+}
+
+// ---- loop-closure batches --------------------------------------------------------------------
+static CachedCloud* cache_find(b200reg_handle* h, long long id) {
+  auto it = h->cache.find(id);
+  return it == h->cache.end() ? nullptr : &it->second;
+}
+
+int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n, size_t stride) {
+  if (!h || (n && !xyzw)) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CachedCloud& c = h->cache[(long long)id];
+  if ((rc = upload_cloud(h, xyzw, n, stride, c.pts))) return rc;
+  c.n = (int)n;
+  c.has_ndt = c.has_nn = false;
+  return B200REG_OK;
+}
+
+int b200reg_cloud_put_device(b200reg_handle* h, int64_t id, const float* d_xyzw, size_t n) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || (n && !d_xyzw)) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  CachedCloud& c = h->cache[(long long)id];
+  B200_CUDA_TRY(c.pts.reserve(n ? n : 1));
+  if (n) B200_CUDA_TRY(cudaMemcpyAsync(c.pts.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
+  c.n = (int)n;
+  c.has_ndt = c.has_nn = false;
+  return B200REG_OK;
+}
+
+int b200reg_cloud_drop(b200reg_handle* h, int64_t id) {
+  if (!h) return B200REG_E_INVALID;
+  auto it = h->cache.find((long long)id);
+  if (it == h->cache.end()) return B200REG_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  it->second.release();
+  h->cache.erase(it);
+  return B200REG_OK;
+}
+
+int b200reg_cloud_clear(b200reg_handle* h) {
+  if (!h) return B200REG_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->cache) kv.second.release();
+  h->cache.clear();
+  return B200REG_OK;
+}
+
+int b200reg_cloud_count(b200reg_handle* h, size_t* out) {
+  if (!h || !out) return B200REG_E_INVALID;
+  *out = h->cache.size();
+  return B200REG_OK;
+}
+
+int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || (n_pairs && (!pairs || !results))) return B200REG_E_INVALID;
+  if (!n_pairs) return B200REG_OK;
+  if (h->cfg.method != B200REG_METHOD_NDT) { h->err = "align_batch: this handle's registration method has no batch path"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  const float res = (float)h->cfg.resolution;
+  // ---- look up the clouds; build the target products once per distinct target
+  std::vector<CachedCloud*> tgt(n_pairs), src(n_pairs);
+  for (size_t i = 0; i < n_pairs; ++i) {
+    tgt[i] = cache_find(h, pairs[i].target_id);
+    src[i] = cache_find(h, pairs[i].source_id);
+    if (!tgt[i] || !src[i]) { h->err = "align_batch: pair " + std::to_string(i) + " names a cloud id that was never put"; return B200REG_E_INVALID; }
+    if (tgt[i]->n == 0) { h->err = "align_batch: pair " + std::to_string(i) + ": Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
+  }
+  for (size_t i = 0; i < n_pairs; ++i) {
+    CachedCloud& c = *tgt[i];
+    if (!c.has_ndt || c.ndt_res != res) {
+      B200_CUDA_TRY(cache_build_ndt(h->stream, h->grid, c, res));
+      h->grid_stale = true;
+    }
+    if (with_fitness && !c.has_nn) {
+      B200_CUDA_TRY(cache_build_nn(h->stream, h->nn, c));
+      h->nn_stale = true;
+    }
+  }
+  // ---- jobs (pairs with an empty source never reach the kernel: PCL's initCompute fails, converged_ stays false)
+  B200_CUDA_TRY(h->pin_batch.reserve(n_pairs * (sizeof(NdtJob) + sizeof(FitJob) + sizeof(b200reg_result))));
+  NdtJob* hj = reinterpret_cast<NdtJob*>(h->pin_batch.p);
+  FitJob* hf = reinterpret_cast<FitJob*>(h->pin_batch.p + n_pairs * sizeof(NdtJob));
+  b200reg_result* hr = reinterpret_cast<b200reg_result*>(h->pin_batch.p + n_pairs * (sizeof(NdtJob) + sizeof(FitJob)));
+  B200_CUDA_TRY(h->jobs.reserve(n_pairs));
+  B200_CUDA_TRY(h->batch_results.reserve(n_pairs));
+  int n_jobs = 0;
+  std::vector<int> job_pair;
+  job_pair.reserve(n_pairs);
+  for (size_t i = 0; i < n_pairs; ++i) {
+    b200reg_result& r = hr[i];
+    memset(&r, 0, sizeof(r));
+    memcpy(r.transformation, pairs[i].guess, 64);
+    r.fitness = 1.7976931348623157e308;
+    if (src[i]->n == 0) continue;
+    NdtJob& j = hj[n_jobs];
+    memset(&j, 0, sizeof(j));
+    j.src = src[i]->pts.p;
+    j.n_src = src[i]->n;
+    j.grid = tgt[i]->ndt_view();
+    j.result = h->batch_results.p + i;
+    const float* g = pairs[i].guess;
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 4; ++c) j.guess[4 * rr + c] = g[4 * c + rr];
+    float eul[3];
+    euler_xyz_from_colmajor(g, eul);
+    j.p0[0] = g[12]; j.p0[1] = g[13]; j.p0[2] = g[14];
+    j.p0[3] = eul[0]; j.p0[4] = eul[1]; j.p0[5] = eul[2];
+    job_pair.push_back((int)i);
+    ++n_jobs;
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(h->batch_results.p, hr, n_pairs * sizeof(b200reg_result), cudaMemcpyHostToDevice, h->stream));
+  h->batch_align_ms = h->batch_fitness_ms = 0.0;
+  if (n_jobs) {
+    B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, hj, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
+    // few pairs: several SMs cooperate on each; a full batch: one SM per registration, no grid-wide sync at all
+    int G = h->num_sm / n_jobs;
+    if (G < 1) G = 1;
+    const int n_groups = h->num_sm / G;
+    B200_CUDA_TRY(h->partials.reserve((size_t)n_groups * 2 * G * kAccStride));
+    B200_CUDA_TRY(h->barriers.reserve((size_t)(n_groups + 1) * 32));
+    B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, (size_t)(n_groups + 1) * 32 * sizeof(unsigned int), h->stream));
+    if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups));
+    launch_counter() += 1;
+    if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  }
+  // ---- getFitnessScore(max_range) for every pair, in chunks that bound the d2 scratch
+  cudaEvent_t evf0 = nullptr, evf1 = nullptr;
+  if (with_fitness && n_jobs) {
+    const float max_d2 = fitness_max_range >= 3.0e38 ? 3.402823466e+38f : (float)fitness_max_range * 1.0001f + 1e-6f;
+    const long long kChunkPoints = 32ll << 20;
+    B200_CUDA_TRY(h->fit_jobs.reserve(n_jobs));
+    B200_CUDA_TRY(h->batch_n_pending.reserve(1));
+    if (h->timing) { B200_CUDA_TRY(cudaEventCreate(&evf0)); B200_CUDA_TRY(cudaEventCreate(&evf1)); B200_CUDA_TRY(cudaEventRecord(evf0, h->stream)); }
+    int j0 = 0;
+    while (j0 < n_jobs) {
+      long long pts = 0;
+      int j1 = j0, max_n = 0;
+      while (j1 < n_jobs && j1 - j0 < 65535 && (j1 == j0 || pts + src[job_pair[j1]]->n <= kChunkPoints)) {
+        const int i = job_pair[j1];
+        FitJob& f = hf[j1];
+        f.view = tgt[i]->nn_view();
+        f.src = src[i]->pts.p;
+        f.n_src = src[i]->n;
+        f.result = i;
+        f.d2_offset = pts;
+        pts += src[i]->n;
+        if (src[i]->n > max_n) max_n = src[i]->n;
+        ++j1;
+      }
+      const int nj = j1 - j0;
+      B200_CUDA_TRY(h->batch_d2.reserve((size_t)pts));
+      B200_CUDA_TRY(h->batch_pending.reserve((size_t)pts));
+      B200_CUDA_TRY(cudaMemcpyAsync(h->fit_jobs.p + j0, hf + j0, (size_t)nj * sizeof(FitJob), cudaMemcpyHostToDevice, h->stream));
+      B200_CUDA_TRY(cudaMemsetAsync(h->batch_n_pending.p, 0, sizeof(unsigned int), h->stream));
+      launch_counter() += 3;
+      k_nn_search_batch<<<dim3((max_n + 255) / 256, nj), 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, max_d2, h->batch_d2.p, h->batch_pending.p, h->batch_n_pending.p);
+      k_nn_bruteforce_batch<<<kNumSM * 4, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending.p, h->batch_n_pending.p, h->batch_d2.p);
+      k_fitness_batch<<<nj, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_d2.p, fitness_max_range, h->batch_results.p);
+      B200_CUDA_TRY(cudaGetLastError());
+      j0 = j1;
+    }
+    if (h->timing) B200_CUDA_TRY(cudaEventRecord(evf1, h->stream));
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(hr, h->batch_results.p, n_pairs * sizeof(b200reg_result), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  memcpy(results, hr, n_pairs * sizeof(b200reg_result));
+  if (!with_fitness)
+    for (size_t i = 0; i < n_pairs; ++i) results[i].fitness = 1.7976931348623157e308;
+  if (h->timing && n_jobs) {
+    float ms = 0.f;
+    B200_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->batch_align_ms = (double)ms;
+    h->align_ms += (double)ms;
+    h->n_align += 1;
+    if (evf0) {
+      B200_CUDA_TRY(cudaEventElapsedTime(&ms, evf0, evf1));
+      h->batch_fitness_ms = (double)ms;
+    }
+  }
+  if (evf0) { cudaEventDestroy(evf0); cudaEventDestroy(evf1); }
+  return B200REG_OK;
+}
+
+int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double* fitness_ms) {
+  if (!h) return B200REG_E_INVALID;
+  if (align_kernel_ms) *align_kernel_ms = h->batch_align_ms;
+  if (fitness_ms) *fitness_ms = h->batch_fitness_ms;
   return B200REG_OK;
 }
 

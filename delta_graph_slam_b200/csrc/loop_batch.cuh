@@ -1,0 +1,179 @@
+// b200reg — loop-closure batches: the B200 replacement of the serial candidate loop of
+// LoopDetector::matching [REF include/hdl_graph_slam/loop_detector.hpp:119-173], where every
+// candidate keyframe is aligned against the new keyframe (:138-145) and scored with
+// getFitnessScore(fitness_score_max_range) (:148).
+//
+// Keyframe clouds live in a device-side cache keyed by the caller's keyframe id (the reference
+// keeps every KeyFrame::cloud for the whole run [REF include/hdl_graph_slam/keyframe.hpp:25-59]).
+// For a cloud used as a target the cache also keeps the two search structures derived from it:
+//   NDT product : compact voxel records + hash table (what k_ndt_align stages in shared memory)
+//   NN product  : cell-ordered copy of the points + cell hash (exact nearest neighbour)
+// both built once per target — the hoisted setInputTarget of loop_detector.hpp:124 — by the same
+// builders the single-registration path uses; the products are a few MB per keyframe.
+//
+// A batch is one launch of k_ndt_align (one CTA group per registration, jobs handed out from a
+// device-side queue) followed by one exact-NN search + fitness reduction over all pairs; the
+// transforms never leave the device between the two.
+#pragma once
+#include "ndt_grid.cuh"
+#include "nn_grid.cuh"
+
+namespace b200 {
+
+struct CachedCloud {
+  DevBuf<float4> pts;
+  int n = 0;
+  // NDT product
+  bool has_ndt = false;
+  float ndt_res = 0.f;
+  DevBuf<NdtVoxel> voxels;
+  DevBuf<float4> centroids;
+  DevBuf<uint2> table;
+  DevBuf<NdtGridMeta> gmeta;
+  DevBuf<SortMeta> meta;
+  // NN product
+  bool has_nn = false;
+  DevBuf<float4> nn_pts;
+  DevBuf<uint2> nn_table;
+  DevBuf<uint32_t> nn_cell_start;
+  DevBuf<SortMeta> nn_meta;
+  uint32_t nn_cap = 0;
+
+  void release() {
+    pts.release(); voxels.release(); centroids.release(); table.release(); gmeta.release(); meta.release();
+    nn_pts.release(); nn_table.release(); nn_cell_start.release(); nn_meta.release();
+    has_ndt = has_nn = false;
+    n = 0;
+  }
+  NdtGridView ndt_view() const {
+    NdtGridView v;
+    v.meta = meta.p; v.gmeta = gmeta.p; v.table = table.p; v.voxels = voxels.p; v.centroids = centroids.p;
+    return v;
+  }
+  NnView nn_view() const {
+    NnView v;
+    v.meta = nn_meta.p; v.table = nn_table.p; v.table_mask = nn_cap - 1; v.table_shift = 32 - (int)__builtin_ctz(nn_cap);
+    v.cell_start = nn_cell_start.p; v.pts = nn_pts.p; v.n = n;
+    return v;
+  }
+};
+
+// Build the products with the handle's builders, then swap the freshly written arrays into the
+// cache entry (pointer swaps; the builder re-grows its own buffers on its next use).
+inline cudaError_t cache_build_ndt(cudaStream_t st, NdtGrid& builder, CachedCloud& c, float resolution) {
+  std::swap(builder.voxels, c.voxels); std::swap(builder.centroids, c.centroids); std::swap(builder.table, c.table);
+  std::swap(builder.gmeta, c.gmeta); std::swap(builder.sort.meta, c.meta);
+  cudaError_t e = builder.build(st, c.pts.p, c.n, resolution);
+  std::swap(builder.voxels, c.voxels); std::swap(builder.centroids, c.centroids); std::swap(builder.table, c.table);
+  std::swap(builder.gmeta, c.gmeta); std::swap(builder.sort.meta, c.meta);
+  builder.built = false;  // the builder's own view is now stale
+  if (e == cudaSuccess) { c.has_ndt = true; c.ndt_res = resolution; }
+  return e;
+}
+
+inline cudaError_t cache_build_nn(cudaStream_t st, NnGrid& builder, CachedCloud& c) {
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.vox_start, c.nn_cell_start); std::swap(builder.sort.meta, c.nn_meta);
+  cudaError_t e = builder.build(st, c.pts.p, c.n);
+  c.nn_cap = builder.table_cap;
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.vox_start, c.nn_cell_start); std::swap(builder.sort.meta, c.nn_meta);
+  builder.built = false;
+  if (e == cudaSuccess) c.has_nn = true;
+  return e;
+}
+
+// ---- batched getFitnessScore ------------------------------------------------------------------
+struct FitJob {
+  NnView view;          // exact-NN structure of the pair's target
+  const float4* src;    // the pair's source cloud
+  int n_src;
+  int result;           // index into the result array (transform in, fitness out)
+  long long d2_offset;  // first slot of this pair in the d2 array
+};
+
+constexpr float kNoNeighbour = __builtin_huge_valf();  // d2 of a query with nothing inside max_range
+
+// blockIdx.y = job, blockIdx.x = 256-point slice of its source.  Transform by the pair's final
+// transformation (float, pcl::transformPoint order) and search; unresolved far queries go to `pending`.
+__global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, float max_d2, float* __restrict__ d2_out,
+                                                         uint2* __restrict__ pending, unsigned int* __restrict__ n_pending) {
+  const FitJob& job = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= job.n_src) return;
+  __shared__ float T[16];
+  if (threadIdx.x < 16) T[threadIdx.x] = results[job.result].transformation[threadIdx.x];
+  __syncthreads();
+  if (i >= job.n_src) return;
+  const GridParams gp = job.view.meta->grid;
+  const float4 p = __ldg(job.src + i);
+  const float qx = affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z);
+  const float qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
+  const float qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
+  float best = 3.402823466e+38f;
+  int best_idx = -1;
+  bool ok = true;
+  if (job.view.n > 0 && gp.any && !gp.overflow) ok = nn_query(job.view, gp, qx, qy, qz, max_d2, best, best_idx);
+  d2_out[job.d2_offset + i] = best_idx >= 0 ? best : kNoNeighbour;
+  if (!ok) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i);
+}
+
+// far outliers: one warp per pending (job, point) scans the pair's whole target
+__global__ void __launch_bounds__(256) k_nn_bruteforce_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, const uint2* __restrict__ pending,
+                                                             const unsigned int* __restrict__ n_pending, float* __restrict__ d2_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int np = (int)*n_pending;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < np; w += warps) {
+    const uint2 pe = pending[w];
+    const FitJob& job = jobs[pe.x];
+    const float* T = results[job.result].transformation;
+    const float4 p = __ldg(job.src + pe.y);
+    const float qx = affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z);
+    const float qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
+    const float qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
+    float best = 3.402823466e+38f;
+    bool found = false;
+    for (int j = lane; j < job.view.n; j += 32) {
+      const float4 t = __ldg(job.view.pts + j);
+      const float d = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+      if (!found || d < best) { best = d; found = true; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int of = __shfl_xor_sync(0xffffffffu, (int)found, o);
+      if (of && (!found || ob < best)) { best = ob; found = true; }
+    }
+    if (lane == 0) d2_out[job.d2_offset + pe.y] = found ? best : kNoNeighbour;
+  }
+}
+
+// one CTA per pair: mean of the squared distances <= max_range over the points that have a
+// neighbour, DBL_MAX when none [REF src/hdl_graph_slam/information_matrix_calculator.cpp:96-107];
+// fixed summation order (thread-strided double sums, shuffle tree, 8 warps in order)
+__global__ void __launch_bounds__(256) k_fitness_batch(const FitJob* __restrict__ jobs, const float* __restrict__ d2, double max_range, b200reg_result* __restrict__ results) {
+  const FitJob& job = jobs[blockIdx.x];
+  __shared__ double s_sum[8], s_cnt[8];
+  double sum = 0.0, cnt = 0.0;
+  const float* d = d2 + job.d2_offset;
+  for (int i = threadIdx.x; i < job.n_src; i += 256) {
+    const float v = d[i];
+    if (v == kNoNeighbour) continue;
+    const double dv = (double)v;
+    if (dv <= max_range) { sum += dv; cnt += 1.0; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += s_sum[w]; b += s_cnt[w]; }
+    results[job.result].fitness = b > 0 ? a / b : 1.7976931348623157e308;
+  }
+}
+
+}  // namespace b200

@@ -502,19 +502,45 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers) {
+__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers,
+                                                                unsigned int* queue) {
   __shared__ NdtShared s;
+  __shared__ int s_job;
   extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
   const int G = ctas_per_group;
-  const int group = blockIdx.x / G, rank = blockIdx.x % G, n_groups = gridDim.x / G;
+  const int group = blockIdx.x / G, rank = blockIdx.x % G;
   double* partials = partials_all + (size_t)group * 2 * G * kAccStride;
-  unsigned int* barrier = barriers + group * 32;  // one 128-byte line per group
+  unsigned int* barrier = barriers + group * 32;  // one 128-byte line per group: [0] arrival counter, [1..2] job mailbox
   unsigned int epoch = 0;
   int parity = 0;
+  unsigned int fetched = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
-  for (int jb = group; jb < n_jobs; jb += n_groups) {
+  // Jobs are handed out from one global counter: registrations differ in their number of passes,
+  // so a static split would leave groups idle behind the slowest one.  Rank 0 of the group takes
+  // the ticket; the other CTAs of the group read it from the mailbox after the group barrier.
+  while (true) {
+    int jb;
+    if (G == 1) {
+      if (tid == 0) s_job = (int)atomicAdd(queue, 1u);
+      __syncthreads();
+      jb = s_job;
+      __syncthreads();
+    } else {
+      unsigned int* mailbox = barrier + 1 + (fetched & 1u);
+      if (rank == 0 && tid == 0) {
+        const unsigned int j = atomicAdd(queue, 1u);
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(mailbox), "r"(j) : "memory");
+      }
+      epoch += (unsigned)G;
+      group_barrier(barrier, epoch);
+      unsigned int j;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(j) : "l"(mailbox) : "memory");
+      jb = (int)j;
+      ++fetched;
+    }
+    if (jb >= n_jobs) break;
     const NdtJob& job = jobs[jb];
     const GridParams gp = job.grid.meta->grid;
     const int n_src = job.n_src;
@@ -607,14 +633,16 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kAlignWarps; ++w) v += s.red[w][tid];
-        partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
+        if (G == 1) s.tot[tid] = v;  // a one-CTA group (loop-closure batches): no global round trip, no barrier
+        else partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
       }
       // ---- group sync + redundant fixed-order reduction of the G partials
       const long long t2 = clock64();
-      epoch += (unsigned)G;
-      group_barrier(barrier, epoch);
-      const long long t3 = clock64();
-      {
+      long long t3 = t2;
+      if (G > 1) {
+        epoch += (unsigned)G;
+        group_barrier(barrier, epoch);
+        t3 = clock64();
         // warp w sums rows w, w+16, ... (each row one coalesced 256-byte read), then the 16 row
         // groups are combined through shared memory; fixed order -> every CTA gets the same bits
         const double* base = partials + (size_t)parity * G * kAccStride + lane;

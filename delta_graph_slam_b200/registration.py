@@ -169,6 +169,46 @@ class Registration:
         return dict(transformation=_lib.from_colmajor(np.array(r.transformation[:], np.float32)), fitness=r.fitness, score=r.score, converged=bool(r.converged),
                     iterations=r.iterations, evaluations=r.evaluations, hits=r.hits)
 
+    # ---- loop-closure batches (LoopDetector::matching, many candidates in one call)
+    def cloudPut(self, cloud_id, cloud):
+        """Cache a keyframe cloud on the device under `cloud_id` (host array or DeviceCloud)."""
+        if isinstance(cloud, DeviceCloud):
+            self._ck(_lib.load().b200reg_cloud_put_device(self._h, int(cloud_id), cloud.ptr, cloud.n))
+            return
+        c = _lib.as_cloud(cloud)
+        self._ck(_lib.load().b200reg_cloud_put(self._h, int(cloud_id), c.ctypes.data if len(c) else None, len(c), 16))
+
+    def cloudDrop(self, cloud_id):
+        self._ck(_lib.load().b200reg_cloud_drop(self._h, int(cloud_id)))
+
+    def cloudClear(self):
+        self._ck(_lib.load().b200reg_cloud_clear(self._h))
+
+    def cloudCount(self):
+        n = C.c_size_t()
+        self._ck(_lib.load().b200reg_cloud_count(self._h, C.byref(n)))
+        return n.value
+
+    def alignBatch(self, pairs, with_fitness=True, fitness_max_range=DBL_MAX):
+        """pairs: iterable of (target_id, source_id, guess 4x4) or a PAIR_DTYPE array.  Returns a
+        RESULT_DTYPE structured array, one record per pair (transformation column-major)."""
+        if isinstance(pairs, np.ndarray) and pairs.dtype == _lib.PAIR_DTYPE:
+            arr = np.ascontiguousarray(pairs)
+        else:
+            pairs = list(pairs)
+            arr = np.zeros(len(pairs), _lib.PAIR_DTYPE)
+            for i, (t, s, g) in enumerate(pairs):
+                arr[i] = (int(t), int(s), _lib.colmajor(np.eye(4) if g is None else g))
+        out = np.zeros(len(arr), _lib.RESULT_DTYPE)
+        if len(arr):
+            self._ck(_lib.load().b200reg_align_batch(self._h, arr.ctypes.data, len(arr), int(with_fitness), float(fitness_max_range), out.ctypes.data))
+        return out
+
+    def batchTiming(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(_lib.load().b200reg_get_batch_timing(self._h, C.byref(a), C.byref(b)))
+        return dict(align_kernel_ms=a.value, fitness_ms=b.value)
+
     def setTiming(self, on=True):
         self._ck(_lib.load().b200reg_set_timing(self._h, int(on)))
 

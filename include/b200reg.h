@@ -145,6 +145,29 @@ int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size
  * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);
 
+/* ---- loop-closure batches: LoopDetector::matching [REF include/hdl_graph_slam/loop_detector.hpp:119-173] ----
+ * The reference aligns every candidate keyframe against the new keyframe in a serial loop
+ * (setInputTarget once :124; per candidate setInputSource :138, align :145, getFitnessScore :148).
+ * Here keyframe clouds are cached on the device under the caller's keyframe id and a whole list of
+ * (target, source, guess) pairs is registered in one call; pairs that share a target share its
+ * NDT grid and exact-NN structure, built once.  results[i] belongs to pairs[i]:
+ * transformation / converged / iterations as after align, fitness = getFitnessScore(max_range)
+ * (DBL_MAX when with_fitness == 0).  A pair whose source cloud is empty comes back un-converged
+ * with its guess; an unknown id or an empty target is B200REG_E_INVALID.  NDT handles only. */
+typedef struct b200reg_pair {
+  int64_t target_id; /* new_keyframe  (setInputTarget) */
+  int64_t source_id; /* candidate     (setInputSource) */
+  float guess[16];   /* column-major initial guess (transform2Dto3D of the 2-D relative pose, :139-143) */
+} b200reg_pair;
+int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n, size_t stride_bytes);
+int b200reg_cloud_put_device(b200reg_handle* h, int64_t id, const float* d_xyzw, size_t n);
+int b200reg_cloud_drop(b200reg_handle* h, int64_t id);
+int b200reg_cloud_clear(b200reg_handle* h);
+int b200reg_cloud_count(b200reg_handle* h, size_t* out);
+int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results);
+/* with timing on: CUDA-event durations of the last batch's align kernel and fitness kernels */
+int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double* fitness_ms);
+
 /* introspection of the NDT target grid (parity tests): number of occupied voxels, then per
  * voxel (ascending linear index): index, point count (-1 = rejected by the eigenvalue test),
  * mean[3], cov[9], icov[9] (row-major doubles), centroid[3] floats.  Any pointer may be NULL. */

@@ -1,0 +1,167 @@
+"""GPU parity tests of the loop-closure batch path (LoopDetector::matching as one engine call)
+against the oracle driven through the reference's serial candidate loop
+[REF include/hdl_graph_slam/loop_detector.hpp:119-173].  Bars as in test_gpu_parity.py."""
+import io
+
+import numpy as np
+import pytest
+
+from helpers import OracleBatchEngine, rot_angle, small_loop_scenario
+
+pytestmark = pytest.mark.gpu
+
+TOL_T, TOL_R, TOL_FIT = 1e-4, 1e-4, 1e-5
+
+
+def T_of(rec):
+    return np.array(rec["transformation"], np.float32).reshape(4, 4).T
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import delta_graph_slam_b200 as d
+    return d
+
+
+@pytest.fixture(scope="module")
+def scenario(oracle):
+    clouds, pairs, rels = small_loop_scenario(oracle)
+    ref = OracleBatchEngine(oracle)
+    for k, v in clouds.items():
+        ref.cloudPut(k, v)
+    return dict(clouds=clouds, pairs=pairs, rels=rels, ref=ref.alignBatch(pairs), ref_engine=ref)
+
+
+def check_against(res, ref, same_path=True):
+    assert len(res) == len(ref)
+    for i, (a, b) in enumerate(zip(res, ref)):
+        assert a["converged"] == b["converged"], f"pair {i}"
+        if same_path:
+            assert a["iterations"] == b["iterations"] and a["evaluations"] == b["evaluations"], f"pair {i}: same Newton / line-search path"
+        Ta, Tb = T_of(a), T_of(b)
+        assert np.max(np.abs(Ta[:3, 3] - Tb[:3, 3])) < TOL_T, f"pair {i}"
+        assert rot_angle(Ta[:3, :3], Tb[:3, :3]) < TOL_R, f"pair {i}"
+        assert abs(a["fitness"] - b["fitness"]) <= TOL_FIT * abs(b["fitness"]), f"pair {i}"
+
+
+def new_engine(eng, sc):
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7"), out=io.StringIO())
+    for k, v in sc["clouds"].items():
+        ndt.cloudPut(k, v)
+    return ndt
+
+
+def test_batch_matches_oracle_serial_loop(eng, scenario):
+    """12 pairs -> groups of 12 SMs per registration (the cooperative multi-CTA path)."""
+    ndt = new_engine(eng, scenario)
+    assert ndt.cloudCount() == len(scenario["clouds"])
+    res = ndt.alignBatch(scenario["pairs"])
+    check_against(res, scenario["ref"])
+    # recovered poses are next to the ground truth of the scenario
+    good = 0
+    for r, rel in zip(res, scenario["rels"]):
+        good += np.max(np.abs(T_of(r)[:3, 3] - rel[:3, 3])) < 0.05
+    assert good >= len(res) - 3
+
+
+def test_full_batch_one_sm_per_registration(eng, scenario):
+    """More pairs than SMs: one CTA per registration, jobs from the device-side queue.  Every copy
+    of a pair must come back bit-identical (fixed summation order), and within tolerance of the oracle."""
+    ndt = new_engine(eng, scenario)
+    reps = 14
+    big = np.concatenate([scenario["pairs"]] * reps)  # 168 pairs > 148 SMs
+    res = ndt.alignBatch(big)
+    n = len(scenario["pairs"])
+    for k in range(1, reps):
+        assert np.array_equal(res[:n].view(np.uint8), res[k * n:(k + 1) * n].view(np.uint8))
+    check_against(res[:n], scenario["ref"])
+
+
+def test_batch_matches_single_registration_calls(eng, scenario):
+    """The same pairs through setInputTarget / setInputSource / align / getFitnessScore."""
+    ndt = new_engine(eng, scenario)
+    res = ndt.alignBatch(scenario["pairs"], fitness_max_range=4.0)
+    single = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7"), out=io.StringIO())
+    last = None
+    for r, p in zip(res, scenario["pairs"]):
+        if p["target_id"] != last:
+            single.setInputTarget(scenario["clouds"][int(p["target_id"])])
+            last = p["target_id"]
+        single.setInputSource(scenario["clouds"][int(p["source_id"])])
+        single.align(np.array(p["guess"]).reshape(4, 4).T)
+        assert bool(r["converged"]) == single.hasConverged()
+        T1 = single.getFinalTransformation()
+        assert np.max(np.abs(T_of(r)[:3, 3] - T1[:3, 3])) < TOL_T and rot_angle(T_of(r)[:3, :3], T1[:3, :3]) < TOL_R
+        f = single.getFitnessScore(4.0)
+        assert abs(r["fitness"] - f) <= TOL_FIT * f
+
+
+def test_batch_edge_cases(eng, scenario):
+    ndt = new_engine(eng, scenario)
+    dbl_max = np.finfo(np.float64).max
+    # no fitness requested -> DBL_MAX, transforms unchanged
+    a = ndt.alignBatch(scenario["pairs"][:3], with_fitness=False)
+    b = ndt.alignBatch(scenario["pairs"][:3], with_fitness=True)
+    assert np.all(a["fitness"] == dbl_max)
+    assert np.array_equal(a["transformation"], b["transformation"])
+    # an empty source: un-converged, guess returned, DBL_MAX; its neighbours are unaffected
+    ndt.cloudPut(9999, np.zeros((0, 4), np.float32))
+    pairs = scenario["pairs"][:3].copy()
+    pairs[1]["source_id"] = 9999
+    r = ndt.alignBatch(pairs)
+    assert r[1]["converged"] == 0 and r[1]["fitness"] == dbl_max and np.array_equal(r[1]["transformation"], pairs[1]["guess"])
+    assert np.array_equal(r[0].tobytes(), b[0].tobytes()) and np.array_equal(r[2].tobytes(), b[2].tobytes())
+    # unknown id / empty target are errors, an empty batch is not
+    pairs[1]["source_id"] = 123456
+    with pytest.raises(eng.B200RegError):
+        ndt.alignBatch(pairs)
+    pairs[1]["source_id"] = scenario["pairs"][1]["source_id"]
+    pairs[1]["target_id"] = 9999
+    with pytest.raises(eng.B200RegError):
+        ndt.alignBatch(pairs)
+    assert len(ndt.alignBatch(scenario["pairs"][:0])) == 0
+    # dropping a cloud
+    ndt.cloudDrop(9999)
+    assert ndt.cloudCount() == len(scenario["clouds"])
+    # a changed resolution rebuilds the cached target grids
+    ndt.setResolution(2.0)
+    c = ndt.alignBatch(scenario["pairs"][:3])
+    assert not np.array_equal(c["transformation"], b["transformation"])
+    # tiny max_range: nothing qualifies -> DBL_MAX
+    ndt.setResolution(1.0)
+    d = ndt.alignBatch(scenario["pairs"][:2], fitness_max_range=1e-12)
+    assert np.all(d["fitness"] == dbl_max)
+
+
+def test_loop_detector_batch_equals_reference_serial_loop(eng, oracle, scenario):
+    """LoopDetector over the engine's batch call picks the same loop as LoopDetector over a plain
+    pcl::Registration surface (the oracle) driven candidate by candidate.  The 2-D graph estimates
+    are laid out so that candidate_guess() reproduces the scenario's initial guesses."""
+    from delta_graph_slam_b200.loop_detector import KeyFrame, LoopDetector, isometry2d
+    clouds, pairs = scenario["clouds"], scenario["pairs"]
+    params = dict(distance_thresh=35.0, accum_distance_thresh=8.0, min_edge_interval=1.0, fitness_score_thresh=0.5, registration_method="NDT_OMP", reg_resolution=1.0,
+                  reg_nn_search_method="DIRECT7")
+    ref_reg = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=oracle.DIRECT7, trans_eps=0.01, max_iter=64)
+    ld_ref = LoopDetector(params, registration=ref_reg, out=io.StringIO())
+    ld_gpu = LoopDetector(params, out=io.StringIO())
+    for t in (0, 1):
+        new_est = isometry2d(3.0 + t, -1.0, 0.2)
+        new = KeyFrame(t, clouds[t], new_est, accum_distance=100.0 + 10 * t)
+        old = []
+        for p in pairs[pairs["target_id"] == t]:
+            g = np.array(p["guess"], np.float64).reshape(4, 4).T
+            g2 = np.array([[g[0, 0], g[0, 1], g[0, 3]], [g[1, 0], g[1, 1], g[1, 3]], [0, 0, 1.0]])
+            old.append(KeyFrame(int(p["source_id"]), clouds[int(p["source_id"])], new_est @ g2, accum_distance=1.0))
+        cands = ld_ref.find_candidates(old, new)
+        assert len(cands) == len(old)
+        c0, s0, T0 = ld_ref.register_candidates(cands, new)
+        c1, s1, T1 = ld_gpu.register_candidates(cands, new)
+        assert c0 == c1
+        for a, b in zip(s0, s1):
+            assert abs(a - b) <= TOL_FIT * abs(a)
+        for a, b in zip(T0, T1):
+            assert np.max(np.abs(a[:3, 3] - b[:3, 3])) < TOL_T and rot_angle(a[:3, :3], b[:3, :3]) < TOL_R
+        la, lb = ld_ref.matching(cands, new), ld_gpu.matching(cands, new)
+        assert (la is None) == (lb is None)
+        if la is not None:
+            assert la.key2.id == lb.key2.id
