@@ -1,0 +1,102 @@
+"""Golden vectors (tests/golden/*.npz, made by tools/make_golden.py with the oracle at fixed seeds).
+CPU: the oracle must still reproduce them (guards the checker against drift).  GPU: the engine
+through the C ABI against the same vectors — bit-exact for voxel work, 1e-4 m / 1e-4 rad / 1e-5
+relative fitness for registrations."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import rot_angle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def close_T(Ta, Tb, tol_t=1e-4, tol_r=1e-4):
+    return np.max(np.abs(Ta[:3, 3] - Tb[:3, 3])) < tol_t and rot_angle(Ta[:3, :3], Tb[:3, :3]) < tol_r
+
+
+# ---------------------------------------------------------------- CPU: oracle vs golden
+def test_oracle_voxelgrid_golden(oracle):
+    g = load("voxelgrid.npz")
+    r = oracle.voxelgrid(g["pts"], tuple(g["leaf"]), is_dense=False)
+    for k in ("voxel_id", "count", "key", "min_b", "div_b"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["out"].view(np.uint32), g["out"].view(np.uint32))
+    r2 = oracle.voxelgrid(g["pts"], 0.25, min_points_per_voxel=2, is_dense=False)
+    assert np.array_equal(r2["out"].view(np.uint32), g["out_min2"].view(np.uint32)) and np.array_equal(r2["count"], g["count_min2"])
+
+
+@pytest.mark.parametrize("name,code", [("direct7", 2), ("direct1", 3), ("kdtree", 0)])
+def test_oracle_ndt_golden(oracle, name, code):
+    g = load("ndt.npz")
+    reg = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=code, trans_eps=0.01, max_iter=64)
+    reg.setInputTarget(g["tgt"])
+    reg.setInputSource(g["src"])
+    reg.align(g["guess"])
+    meta = g[f"{name}_meta"]
+    assert [int(reg.hasConverged()), reg.getFinalNumIteration(), int(reg.info()[1])] == meta[:3].tolist()
+    assert close_T(reg.getFinalTransformation(), g[f"{name}_T"], 1e-6, 1e-6)  # OpenMP summation order may move the last bits
+    sc = g[f"{name}_score"]
+    assert abs(reg.getFitnessScore() - sc[1]) <= 1e-9 * sc[1] and abs(reg.getFitnessScore(1.0) - sc[2]) <= 1e-9 * sc[2]
+    s, gr, H = reg.ndt_derivatives(np.array([0.4, -0.1, 0.03, 0.01, -0.02, 0.05]))
+    want = g[f"{name}_deriv"]
+    assert np.allclose(np.concatenate([[s], gr, H.ravel()]), want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("name,lsq", [("lm", 1), ("gn", 0)])
+def test_oracle_gicp_golden(oracle, name, lsq):
+    g, n = load("gicp.npz"), load("ndt.npz")
+    reg = oracle.Registration(oracle.GICP, trans_eps=0.01, max_iter=64, max_corr_dist=2.5, k_corr=20, lsq=lsq)
+    reg.setInputTarget(n["tgt"])
+    reg.setInputSource(n["src"])
+    reg.align(g["guess"])
+    assert [int(reg.hasConverged()), reg.getFinalNumIteration()] == g[f"{name}_meta"].tolist()
+    assert close_T(reg.getFinalTransformation(), g[f"{name}_T"], 1e-6, 1e-6)
+    if lsq == 1:
+        assert np.allclose(reg.gicp_covariances(0, len(n["src"]))[::50], g["cov_src"], atol=1e-12)
+
+
+# ---------------------------------------------------------------- GPU: engine vs golden
+@pytest.mark.gpu
+def test_engine_voxelgrid_golden():
+    import delta_graph_slam_b200 as eng
+    g = load("voxelgrid.npz")
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(*[float(x) for x in g["leaf"]])
+    vg.setInputCloud(g["pts"], is_dense=False)
+    out = vg.filter()
+    lay = vg.last_layout(len(out), len(g["pts"]))
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+    for k in ("voxel_id", "count", "key", "min_b", "div_b"):
+        assert np.array_equal(lay[k], g[k]), k
+    vg.setLeafSize(0.25, 0.25, 0.25)
+    vg.setMinimumPointsNumberPerVoxel(2)
+    vg.setInputCloud(g["pts"], is_dense=False)
+    assert np.array_equal(vg.filter().view(np.uint32), g["out_min2"].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["direct7", "direct1", "kdtree"])
+def test_engine_ndt_golden(name):
+    import io
+    import delta_graph_slam_b200 as eng
+    g = load("ndt.npz")
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method=name.upper()), out=io.StringIO())
+    ndt.setInputTarget(g["tgt"])
+    ndt.setInputSource(g["src"])
+    ndt.align(g["guess"])
+    meta = g[f"{name}_meta"]
+    res = ndt.getResult()
+    assert [int(res["converged"]), res["iterations"], res["evaluations"]] == meta[:3].tolist()
+    assert close_T(ndt.getFinalTransformation(), g[f"{name}_T"])
+    sc = g[f"{name}_score"]
+    assert abs(res["score"] - sc[0]) <= 1e-5 * abs(sc[0])
+    assert abs(ndt.getFitnessScore() - sc[1]) <= 1e-5 * sc[1] and abs(ndt.getFitnessScore(1.0) - sc[2]) <= 1e-5 * sc[2]
+    L = ndt.ndt_leaves()
+    assert np.array_equal(L["idx"], g["leaf_idx"]) and np.array_equal(L["n"], g["leaf_n"])
+    assert np.allclose(L["mean"], g["leaf_mean"], rtol=0, atol=1e-12)
