@@ -306,12 +306,15 @@ def bench_odometry(ctx):
 
     # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out
     pre_h, odo_h = new_pipeline()
+    # caller-owned output clouds of the filter (pcl::Filter::filter(output)), page-locked; three in
+    # rotation because the odometry keeps the keyframe's cloud while the next scans are filtered
+    h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
 
     def step_host(i):
         odo_h.keyframe = None
         h2d = d2h = 0
         for k, cloud in enumerate(host_clouds):
-            filtered = pre_h.downsample(cloud)
+            filtered = pre_h.downsample(cloud, out=h_out[k % 3])
             odo_h.matching(0.1 * k, filtered)
             h2d += cloud.nbytes + filtered.nbytes
             d2h += filtered.nbytes + 128

@@ -22,13 +22,13 @@ LSQ_GN, LSQ_LM = 0, 1
 EXPORTS = [
     "b200reg_default_config", "b200reg_create", "b200reg_destroy", "b200reg_last_error", "b200reg_version",
     "b200reg_set_resolution", "b200reg_set_nn_search", "b200reg_set_transformation_epsilon", "b200reg_set_maximum_iterations",
-    "b200reg_set_max_correspondence_distance", "b200reg_set_correspondence_randomness",
+    "b200reg_set_max_correspondence_distance", "b200reg_set_correspondence_randomness", "b200reg_set_gicp_options", "b200reg_gicp_get_covariances",
     "b200reg_set_target", "b200reg_set_source", "b200reg_set_target_device", "b200reg_set_source_device", "b200reg_promote_source_to_target",
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
     "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_get_batch_timing",
-    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_get_stream",
+    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
                         ("b200reg_set_maximum_iterations", C.c_int), ("b200reg_set_max_correspondence_distance", C.c_double),
                         ("b200reg_set_correspondence_randomness", C.c_int)]:
         getattr(L, name).argtypes = [vp, extra]
+    L.b200reg_set_gicp_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.b200reg_gicp_get_covariances.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.b200reg_set_target.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
     L.b200reg_set_source.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
     L.b200reg_set_target_device.argtypes = [vp, vp, C.c_size_t]
@@ -115,6 +117,7 @@ def load():
     L.b200reg_ndt_get_leaves.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, C.POINTER(C.c_double), vp, vp]
     L.b200reg_get_profile.argtypes = [vp, vp]
+    L.b200reg_get_nn_stats.argtypes = [vp, vp]
     L.b200reg_set_timing.argtypes = [vp, C.c_int]
     L.b200reg_get_counters.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.b200reg_get_stream.argtypes = [vp, C.POINTER(vp)]

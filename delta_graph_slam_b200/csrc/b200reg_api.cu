@@ -11,6 +11,7 @@
 #include "../../include/b200reg.h"
 #include <map>
 
+#include "gicp.cuh"
 #include "loop_batch.cuh"
 #include "ndt_align.cuh"
 #include "nn_grid.cuh"
@@ -51,12 +52,20 @@ struct b200reg_handle {
   bool nn_stale = true;
   DevBuf<double> fit_partials;
 
+  // FAST_GICP: the source's own NN structure, per-point covariances, correspondence scratch
+  NnGrid nn_src;
+  bool nn_src_stale = true;
+  DevBuf<double> cov_src, cov_tgt, gicp_mahal;
+  bool cov_src_ok = false, cov_tgt_ok = false;
+  DevBuf<int> gicp_corr;
+  DevBuf<GicpJob> gicp_jobs;
+
   // loop-closure batches: keyframe cloud cache + batch staging
   std::map<long long, CachedCloud> cache;
   DevBuf<b200reg_result> batch_results;
   DevBuf<FitJob> fit_jobs;
   DevBuf<float> batch_d2;
-  DevBuf<uint2> batch_pending;
+  DevBuf<uint2> batch_pending, batch_pending2;
   DevBuf<unsigned int> batch_n_pending;
   PinnedBuf<unsigned char> pin_batch;
   double batch_align_ms = 0.0;  // last batch: duration of the align kernel (timing on)
@@ -87,6 +96,16 @@ int set_device(b200reg_handle* h) {
   return B200REG_OK;
 }
 
+// true when p is page-locked host memory the copy engines can read or write directly
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();  // pageable memory is not an error for us
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
 // host cloud (any stride) -> device float4 buffer on the handle's stream
 int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, DevBuf<float4>& dst) {
   auto set_error = [&](const std::string& s) { h->err = s; };
@@ -96,6 +115,12 @@ int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_b
   }
   B200_CUDA_TRY(dst.reserve(n ? n : 1));
   if (!n) return B200REG_OK;
+  if (stride_bytes == 16 && is_pinned_host(xyzw)) {
+    // page-locked caller memory (cudaHostAlloc / cudaHostRegister): DMA straight from it
+    B200_CUDA_TRY(cudaMemcpyAsync(dst.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer after the call returns
+    return B200REG_OK;
+  }
   B200_CUDA_TRY(h->pin_in.reserve(n));
   if (stride_bytes == 16) {
     memcpy(h->pin_in.p, xyzw, n * 16);
@@ -196,7 +221,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   B200_CUDA_TRY(h->prof.reserve(16));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
   B200_CUDA_TRY(h->barriers.reserve(64));
-  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
   NdtJob* job = reinterpret_cast<NdtJob*>(h->pin_small.p);
   memset(job, 0, sizeof(NdtJob));
   job->src = h->src.p;
@@ -222,6 +247,93 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 64 * sizeof(unsigned int), h->stream));
   if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1));
+  launch_counter() += 1;
+  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  return B200REG_OK;
+}
+
+// ---- FAST_GICP ---------------------------------------------------------------------------------
+cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const float4* pts, int n, double* covs) {
+  if (n <= 0) return cudaSuccess;
+  const int k = h->cfg.correspondence_randomness, reg = h->cfg.regularization;
+  const int blocks = (n + 127) / 128;
+  launch_counter() += 1;
+  if (k <= 8) k_gicp_covariances<8><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
+  else if (k <= 24) k_gicp_covariances<24><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
+  else k_gicp_covariances<48><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
+  return cudaGetLastError();
+}
+
+// source_covs_ / target_covs_ are computed lazily at the first align after a cloud changed (A.5)
+int ensure_gicp_structures(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  int rc = ensure_nn_grid(h);
+  if (rc) return rc;
+  if (h->cfg.correspondence_randomness > 48) { h->err = "reg_correspondence_randomness above 48 is not supported by the device k-NN"; return B200REG_E_INVALID; }
+  if (!h->cov_tgt_ok) {
+    B200_CUDA_TRY(h->cov_tgt.reserve((size_t)h->n_tgt * 6));
+    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn, h->tgt.p, h->n_tgt, h->cov_tgt.p));
+    h->cov_tgt_ok = true;
+  }
+  if (!h->cov_src_ok) {
+    if (h->nn_src_stale || !h->nn_src.built) {
+      B200_CUDA_TRY(h->nn_src.build(h->stream, h->src.p, h->n_src));
+      h->nn_src_stale = false;
+    }
+    B200_CUDA_TRY(h->cov_src.reserve((size_t)(h->n_src > 0 ? h->n_src : 1) * 6));
+    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn_src, h->src.p, h->n_src, h->cov_src.p));
+    h->cov_src_ok = true;
+  }
+  return B200REG_OK;
+}
+
+int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  int rc = ensure_gicp_structures(h);
+  if (rc) return rc;
+  const int G = h->num_sm;
+  const size_t ns = (size_t)(h->n_src > 0 ? h->n_src : 1);
+  B200_CUDA_TRY(h->gicp_jobs.reserve(1));
+  B200_CUDA_TRY(h->d_result.reserve(1));
+  B200_CUDA_TRY(h->gicp_corr.reserve(ns));
+  B200_CUDA_TRY(h->gicp_mahal.reserve(ns * 6));
+  B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kGicpStride));
+  B200_CUDA_TRY(h->barriers.reserve(64));
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
+  GicpJob* job = reinterpret_cast<GicpJob*>(h->pin_small.p + sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double));
+  memset(job, 0, sizeof(GicpJob));
+  job->src = h->src.p;
+  job->n_src = h->n_src;
+  job->cov_src = h->cov_src.p;
+  job->tgt = h->nn.view();
+  job->tgt_pts = h->tgt.p;
+  job->cov_tgt = h->cov_tgt.p;
+  const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memcpy(job->guess, guess_colmajor ? guess_colmajor : I, 64);
+  job->corr = h->gicp_corr.p;
+  job->mahal = h->gicp_mahal.p;
+  job->result = h->d_result.p;
+  GicpParams prm;
+  const double d = h->cfg.max_correspondence_distance;
+  prm.corr_dist2 = d * d;
+  prm.search_d2 = prm.corr_dist2 >= 3.0e38 ? 3.402823466e+38f : (float)prm.corr_dist2 * 1.0001f + 1e-6f;
+  const double rings = ceil(d / (double)kNnCell) + 1.0;
+  prm.far_ring = rings > (double)kFarRing ? kFarRing : (int)rings;
+  prm.trans_eps = h->cfg.transformation_epsilon;
+  prm.rot_eps = h->cfg.rotation_epsilon;
+  prm.max_iterations = h->cfg.maximum_iterations;
+  prm.lsq = h->cfg.lsq_optimizer;
+  prm.lm_max_iterations = 10;
+  prm.lm_init_lambda_factor = 1e-9;
+  B200_CUDA_TRY(cudaMemcpyAsync(h->gicp_jobs.p, job, sizeof(GicpJob), cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 64 * sizeof(unsigned int), h->stream));
+  const GicpJob* jobs = h->gicp_jobs.p;
+  int g = G;
+  double* partials = h->partials.p;
+  unsigned int* barrier = h->barriers.p;
+  void* args[] = {(void*)&jobs, (void*)&g, (void*)&prm, (void*)&partials, (void*)&barrier};
+  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  B200_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_gicp_align, dim3(G), dim3(kGicpThreads), args, 0, h->stream));
   launch_counter() += 1;
   if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   return B200REG_OK;
@@ -300,9 +412,10 @@ int b200reg_destroy(b200reg_handle* h) {
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
+  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_jobs.release();
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
-  h->batch_results.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_n_pending.release(); h->pin_batch.release();
+  h->batch_results.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
   delete h;
   return B200REG_OK;
 }
@@ -323,7 +436,21 @@ int b200reg_set_nn_search(b200reg_handle* h, int m) {
 int b200reg_set_transformation_epsilon(b200reg_handle* h, double e) { if (!h) return B200REG_E_INVALID; h->cfg.transformation_epsilon = e; return B200REG_OK; }
 int b200reg_set_maximum_iterations(b200reg_handle* h, int n) { if (!h) return B200REG_E_INVALID; h->cfg.maximum_iterations = n; return B200REG_OK; }
 int b200reg_set_max_correspondence_distance(b200reg_handle* h, double d) { if (!h) return B200REG_E_INVALID; h->cfg.max_correspondence_distance = d; return B200REG_OK; }
-int b200reg_set_correspondence_randomness(b200reg_handle* h, int k) { if (!h || k < 1) return B200REG_E_INVALID; h->cfg.correspondence_randomness = k; return B200REG_OK; }
+int b200reg_set_correspondence_randomness(b200reg_handle* h, int k) {
+  if (!h || k < 1) return B200REG_E_INVALID;
+  if (k != h->cfg.correspondence_randomness) h->cov_src_ok = h->cov_tgt_ok = false;
+  h->cfg.correspondence_randomness = k;
+  return B200REG_OK;
+}
+int b200reg_set_gicp_options(b200reg_handle* h, int regularization, int lsq_optimizer, double rotation_epsilon) {
+  if (!h || regularization < B200REG_REG_NONE || regularization > B200REG_REG_FROBENIUS || lsq_optimizer < B200REG_LSQ_GN || lsq_optimizer > B200REG_LSQ_LM || !(rotation_epsilon > 0))
+    return B200REG_E_INVALID;
+  if (regularization != h->cfg.regularization) h->cov_src_ok = h->cov_tgt_ok = false;
+  h->cfg.regularization = regularization;
+  h->cfg.lsq_optimizer = lsq_optimizer;
+  h->cfg.rotation_epsilon = rotation_epsilon;
+  return B200REG_OK;
+}
 
 int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t stride) {
   if (!h) return B200REG_E_INVALID;
@@ -335,6 +462,7 @@ int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   h->have_tgt = true;
   h->grid_stale = true;
   h->nn_stale = true;
+  h->cov_tgt_ok = false;
   if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);  // ndt->setInputTarget builds the grid eagerly
   return B200REG_OK;
 }
@@ -346,6 +474,8 @@ int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   if ((rc = upload_cloud(h, xyzw, n, stride, h->src))) return rc;
   h->n_src = (int)n;
   h->have_src = true;
+  h->nn_src_stale = true;
+  h->cov_src_ok = false;
   return B200REG_OK;
 }
 
@@ -361,6 +491,7 @@ int b200reg_set_target_device(b200reg_handle* h, const float* d_xyzw, size_t n) 
   h->have_tgt = true;
   h->grid_stale = true;
   h->nn_stale = true;
+  h->cov_tgt_ok = false;
   if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);
   return B200REG_OK;
 }
@@ -374,6 +505,8 @@ int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n) 
   if (n) B200_CUDA_TRY(cudaMemcpyAsync(h->src.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
   h->n_src = (int)n;
   h->have_src = true;
+  h->nn_src_stale = true;
+  h->cov_src_ok = false;
   return B200REG_OK;
 }
 
@@ -389,7 +522,13 @@ int b200reg_promote_source_to_target(b200reg_handle* h) {
   h->have_src = false;
   h->n_src = 0;
   h->grid_stale = true;
-  h->nn_stale = true;
+  // GICP: the cloud keeps its NN structure and covariances when it changes role (same cloud, same values)
+  std::swap(h->nn, h->nn_src);
+  h->nn_stale = h->nn_src_stale || !h->nn.built;
+  h->nn_src_stale = true;
+  std::swap(h->cov_tgt, h->cov_src);
+  h->cov_tgt_ok = h->cov_src_ok;
+  h->cov_src_ok = false;
   if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);
   return B200REG_OK;
 }
@@ -404,6 +543,8 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
   if (rc) return rc;
   if (h->cfg.method == B200REG_METHOD_NDT) {
     if ((rc = run_ndt_single(h, guess, nullptr))) return rc;
+  } else if (h->cfg.method == B200REG_METHOD_GICP) {
+    if ((rc = run_gicp_single(h, guess))) return rc;
   } else {
     h->err = "align: registration method not available on this handle";
     return B200REG_E_STATE;
@@ -526,7 +667,7 @@ int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = vg_run(h, (const float4*)d_xyzw, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
-  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
   VgCounts* pc = reinterpret_cast<VgCounts*>(h->pin_small.p);
   B200_CUDA_TRY(cudaMemcpyAsync(pc, h->vg_counts.p, sizeof(VgCounts), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -551,10 +692,15 @@ int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, siz
   if (m > cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
   if (m) {
     if (!out) return B200REG_E_INVALID;
-    B200_CUDA_TRY(h->pin_out.reserve(m));
-    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    memcpy(out, h->pin_out.p, m * 16);
+    if (is_pinned_host(out)) {
+      B200_CUDA_TRY(cudaMemcpyAsync(out, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+      B200_CUDA_TRY(h->pin_out.reserve(m));
+      B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      memcpy(out, h->pin_out.p, m * 16);
+    }
   }
   return B200REG_OK;
 }
@@ -717,7 +863,7 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     const float max_d2 = fitness_max_range >= 3.0e38 ? 3.402823466e+38f : (float)fitness_max_range * 1.0001f + 1e-6f;
     const long long kChunkPoints = 32ll << 20;
     B200_CUDA_TRY(h->fit_jobs.reserve(n_jobs));
-    B200_CUDA_TRY(h->batch_n_pending.reserve(1));
+    B200_CUDA_TRY(h->batch_n_pending.reserve(2));
     if (h->timing) { B200_CUDA_TRY(cudaEventCreate(&evf0)); B200_CUDA_TRY(cudaEventCreate(&evf1)); B200_CUDA_TRY(cudaEventRecord(evf0, h->stream)); }
     int j0 = 0;
     while (j0 < n_jobs) {
@@ -738,11 +884,14 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
       const int nj = j1 - j0;
       B200_CUDA_TRY(h->batch_d2.reserve((size_t)pts));
       B200_CUDA_TRY(h->batch_pending.reserve((size_t)pts));
+      B200_CUDA_TRY(h->batch_pending2.reserve((size_t)pts));
       B200_CUDA_TRY(cudaMemcpyAsync(h->fit_jobs.p + j0, hf + j0, (size_t)nj * sizeof(FitJob), cudaMemcpyHostToDevice, h->stream));
-      B200_CUDA_TRY(cudaMemsetAsync(h->batch_n_pending.p, 0, sizeof(unsigned int), h->stream));
-      launch_counter() += 3;
+      B200_CUDA_TRY(cudaMemsetAsync(h->batch_n_pending.p, 0, 2 * sizeof(unsigned int), h->stream));
+      launch_counter() += 4;
       k_nn_search_batch<<<dim3((max_n + 255) / 256, nj), 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, max_d2, h->batch_d2.p, h->batch_pending.p, h->batch_n_pending.p);
-      k_nn_bruteforce_batch<<<kNumSM * 4, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending.p, h->batch_n_pending.p, h->batch_d2.p);
+      k_nn_far_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending.p, h->batch_n_pending.p, max_d2, h->batch_d2.p, h->batch_pending2.p,
+                                                         h->batch_n_pending.p + 1);
+      k_nn_bruteforce_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending2.p, h->batch_n_pending.p + 1, h->batch_d2.p);
       k_fitness_batch<<<nj, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_d2.p, fitness_max_range, h->batch_results.p);
       B200_CUDA_TRY(cudaGetLastError());
       j0 = j1;
@@ -773,6 +922,27 @@ int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double*
   if (!h) return B200REG_E_INVALID;
   if (align_kernel_ms) *align_kernel_ms = h->batch_align_ms;
   if (fitness_ms) *fitness_ms = h->batch_fitness_ms;
+  return B200REG_OK;
+}
+
+// ---- GICP introspection ----------------------------------------------------------------------
+int b200reg_gicp_get_covariances(b200reg_handle* h, int which, double* out9, size_t n_points) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out9) return B200REG_E_INVALID;
+  if (h->cfg.method != B200REG_METHOD_GICP || !h->have_tgt || !h->have_src) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ensure_gicp_structures(h))) return rc;
+  const size_t n = which == 0 ? (size_t)h->n_src : (size_t)h->n_tgt;
+  if (n_points < n) return B200REG_E_CAPACITY;
+  std::vector<double> c6(n * 6 + 1);
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (n) B200_CUDA_TRY(cudaMemcpy(c6.data(), which == 0 ? h->cov_src.p : h->cov_tgt.p, n * 48, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    const double* c = &c6[6 * i];
+    double* o = out9 + 9 * i;
+    o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[1]; o[4] = c[3]; o[5] = c[4]; o[6] = c[2]; o[7] = c[4]; o[8] = c[5];
+  }
   return B200REG_OK;
 }
 
@@ -811,7 +981,7 @@ int b200reg_ndt_get_leaves(b200reg_handle* h, uint64_t* idx, int32_t* n, double*
   if (icov9) B200_CUDA_TRY(cudaMemcpy(icov9, h->grid.leaf_icov.p, nv * 72, cudaMemcpyDeviceToHost));
   if (centroid3) {
     std::vector<float4> c(nv);
-    B200_CUDA_TRY(cudaMemcpy(c.data(), h->grid.centroids.p, nv * 16, cudaMemcpyDeviceToHost));
+    B200_CUDA_TRY(cudaMemcpy(c.data(), h->grid.stage_cen.p, nv * 16, cudaMemcpyDeviceToHost));  // per OCCUPIED voxel (the compact array holds records only)
     for (size_t i = 0; i < nv; ++i) { centroid3[3 * i] = c[i].x; centroid3[3 * i + 1] = c[i].y; centroid3[3 * i + 2] = c[i].z; }
   }
   return B200REG_OK;
@@ -864,6 +1034,22 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B200REG_OK;
+}
+
+int b200reg_get_nn_stats(b200reg_handle* h, long long* out2 /*[3]*/) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !out2) return B200REG_E_INVALID;
+  out2[0] = out2[1] = out2[2] = 0;
+  if (!h->nn.n_pending.p) return B200REG_OK;
+  int rc = set_device(h);
+  if (rc) return rc;
+  unsigned int np[2] = {0, 0};
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  B200_CUDA_TRY(cudaMemcpy(np, h->nn.n_pending.p, sizeof(np), cudaMemcpyDeviceToHost));
+  out2[0] = h->n_src;
+  out2[1] = np[0];
+  out2[2] = np[1];
   return B200REG_OK;
 }
 

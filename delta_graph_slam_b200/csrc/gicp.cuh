@@ -1,0 +1,565 @@
+// b200reg — FAST_GICP on the device: the B200 replacement of fast_gicp::FastGICP on
+// fast_gicp::LsqRegistration as configured by the reference's factory
+// [REF src/hdl_graph_slam/registrations.cpp:27-36] (k = 20 neighbours, PLANE regularisation,
+// Levenberg-Marquardt, max correspondence distance 2.5 m / 2.0 m in the launch files).
+//
+//   k_gicp_covariances : calculate_covariances — per point the k nearest neighbours (exact, found
+//                        on the cloud's own cell grid), their covariance in double, and the
+//                        regularised 3x3 (stored as 6 doubles)
+//   k_gicp_align       : LsqRegistration::computeTransformation — one persistent cooperative
+//                        kernel per registration.  A pass is either `linearize` (1-NN correspondence
+//                        of every transformed source point inside the distance gate, fused
+//                        Mahalanobis matrix (C_B + R C_A R^T)^-1, residual, H = sum J^T M J,
+//                        b = sum J^T M e) or `compute_error` (residual sum with the stored
+//                        correspondences and Mahalanobis matrices); between passes one lane of every
+//                        CTA runs the LM / GN state machine redundantly on identical totals, exactly
+//                        like the NDT kernel, so an iteration needs no host round trip.
+// Arithmetic is double throughout except the point storage and the NN search (float), as upstream.
+#pragma once
+#include "../../include/b200reg.h"
+#include "nn_grid.cuh"
+#include "small_solve.cuh"
+
+namespace b200 {
+
+// ---- k nearest neighbours -----------------------------------------------------------------------
+// fixed-size sorted list in registers: ascending (d2, index); slots >= count hold (+inf, kNoIndex)
+template <int KMAX>
+__device__ __forceinline__ void knn_offer(float (&bd)[KMAX], int (&bi)[KMAX], float d, int idx) {
+  float cd = d;
+  int ci = idx;
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) {
+    const bool lt = cd < bd[s] || (cd == bd[s] && ci < bi[s]);
+    const float td = bd[s];
+    const int ti = bi[s];
+    bd[s] = lt ? cd : td;
+    bi[s] = lt ? ci : ti;
+    cd = lt ? td : cd;
+    ci = lt ? ti : ci;
+  }
+}
+
+template <int KMAX>
+__device__ __forceinline__ void knn_kth(const float (&bd)[KMAX], const int (&bi)[KMAX], int km1, float& worst, int& worst_idx) {
+  worst = 3.402823466e+38f;
+  worst_idx = kNoIndex;
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s)
+    if (s == km1) { worst = bd[s]; worst_idx = bi[s]; }
+}
+
+// exact k-NN of (qx, qy, qz) on the grid: rings until the k-th best cannot be beaten from outside
+// the examined block, or the block covers the occupied lattice
+template <int KMAX>
+__device__ __forceinline__ void knn_query(const NnView& g, const GridParams& gp, float qx, float qy, float qz, int k, float (&bd)[KMAX], int (&bi)[KMAX]) {
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) { bd[s] = 3.402823466e+38f; bi[s] = kNoIndex; }
+  const NnQuery q = nn_make_query(gp, qx, qy, qz);
+  float worst = 3.402823466e+38f;
+  int worst_idx = kNoIndex;
+  for (int r = 0;; ++r) {
+    if (r >= 1 && nn_settled(gp, q, r, worst_idx == kNoIndex ? 3.402823466e+38f : worst, 3.402823466e+38f)) break;
+    const int z0 = max(q.cz - r, gp.min_b[2]), z1 = min(q.cz + r, gp.max_b[2]);
+    const int y0 = max(q.cy - r, gp.min_b[1]), y1 = min(q.cy + r, gp.max_b[1]);
+    for (int iz = z0; iz <= z1; ++iz) {
+      const bool zface = (iz == q.cz - r) || (iz == q.cz + r);
+      for (int iy = y0; iy <= y1; ++iy) {
+        const bool face = zface || (iy == q.cy - r) || (iy == q.cy + r);
+        const int xstep = face ? 1 : (r == 0 ? 1 : 2 * r);
+        for (int ix = q.cx - r; ix <= q.cx + r; ix += xstep) {
+          if (ix < gp.min_b[0] || ix > gp.max_b[0]) continue;
+          if (worst_idx != kNoIndex && nn_box_d2(gp, q, ix, iy, iz) > worst) continue;
+          const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+          const uint2 run = nn_lookup(g, key);
+          for (uint32_t j = run.x; j < run.y; ++j) {
+            const float4 p = __ldg(g.pts + j);
+            const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+            const int idx = __float_as_int(p.w);
+            if (worst_idx == kNoIndex || nn_better(d, idx, worst, worst_idx)) {
+              knn_offer<KMAX>(bd, bi, d, idx);
+              knn_kth<KMAX>(bd, bi, k - 1, worst, worst_idx);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// calculate_covariances (A.5).  covs[i] = {xx, xy, xz, yy, yz, zz} of the regularised covariance.
+template <int KMAX>
+__global__ void __launch_bounds__(128) k_gicp_covariances(NnView g, const float4* __restrict__ pts, int n, int k, int reg_method, double* __restrict__ covs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GridParams gp = g.meta->grid;
+  const float4 p = __ldg(pts + i);
+  float bd[KMAX];
+  int bi[KMAX];
+  knn_query<KMAX>(g, gp, p.x, p.y, p.z, k, bd, bi);
+  // neighbours as columns, minus the row-wise mean over the k REQUESTED columns, cov = N N^T / k
+  double mean[3] = {0, 0, 0};
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s)
+    if (s < k && bi[s] != kNoIndex) {
+      const float4 q = __ldg(pts + bi[s]);
+      mean[0] += (double)q.x; mean[1] += (double)q.y; mean[2] += (double)q.z;
+    }
+  const double kd = (double)k;
+  mean[0] /= kd; mean[1] /= kd; mean[2] /= kd;
+  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s)
+    if (s < k && bi[s] != kNoIndex) {
+      const float4 q = __ldg(pts + bi[s]);
+      const double v[3] = {(double)q.x - mean[0], (double)q.y - mean[1], (double)q.z - mean[2]};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) c[3 * a + b] += v[a] * v[b];
+    }
+#pragma unroll
+  for (int a = 0; a < 9; ++a) c[a] /= kd;
+  double out[9];
+  if (reg_method == B200REG_REG_NONE) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) out[a] = c[a];
+  } else if (reg_method == B200REG_REG_FROBENIUS) {
+    const double lambda = 1e-3;
+    double C[9], Ci[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) C[a] = c[a] + ((a % 4 == 0) ? lambda : 0.0);
+    inverse3(C, Ci);
+    double fro = 0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) fro += Ci[a] * Ci[a];
+    fro = sqrt(fro);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) Ci[a] /= fro;
+    inverse3(Ci, out);
+  } else {
+    // JacobiSVD of a symmetric PSD 3x3: U = V = eigenvectors, singular values descending
+    double ev[3], V[9];
+    sym_eigen3(c, ev, V);  // ascending, eigenvectors in columns
+    double values[3];
+    if (reg_method == B200REG_REG_PLANE) {
+      values[0] = 1.0; values[1] = 1.0; values[2] = 1e-3;
+    } else if (reg_method == B200REG_REG_MIN_EIG) {
+      values[0] = fmax(fabs(ev[2]), 1e-3); values[1] = fmax(fabs(ev[1]), 1e-3); values[2] = fmax(fabs(ev[0]), 1e-3);
+    } else {
+      const double smax = fabs(ev[2]);
+      values[0] = fmax(fabs(ev[2]) / smax, 1e-3); values[1] = fmax(fabs(ev[1]) / smax, 1e-3); values[2] = fmax(fabs(ev[0]) / smax, 1e-3);
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) out[a] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int col = 2 - s;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) out[3 * a + b] += values[s] * V[3 * a + col] * V[3 * b + col];
+    }
+  }
+  double* o = covs + (size_t)i * 6;
+  o[0] = out[0]; o[1] = out[1]; o[2] = out[2]; o[3] = out[4]; o[4] = out[5]; o[5] = out[8];
+}
+
+// ---- the alignment kernel -------------------------------------------------------------------------
+constexpr int kGicpThreads = 512;
+constexpr int kGicpWarps = kGicpThreads / 32;
+constexpr int kGicpAcc = 29;  // H upper triangle [21], b [6], sum of errors, correspondences
+constexpr int kGicpStride = 32;
+
+enum GicpPhase { GP_LINEARIZE = 0, GP_ERROR = 1, GP_DONE = 2 };
+
+struct GicpParams {
+  double corr_dist2;  // corr_dist_threshold_^2 (double)
+  float search_d2;    // float bound handed to the NN search (>= corr_dist2)
+  int far_ring;       // rings that cover the gate (capped at kFarRing; beyond that brute force)
+  double trans_eps, rot_eps;
+  int max_iterations, lsq, lm_max_iterations;
+  double lm_init_lambda_factor;
+};
+
+struct GicpJob {
+  const float4* src;
+  int n_src;
+  const double* cov_src;   // [n_src][6]
+  NnView tgt;              // exact-NN structure of the target
+  const float4* tgt_pts;   // target in original order
+  const double* cov_tgt;   // [n_tgt][6]
+  float guess[16];         // column-major
+  int* corr;               // [n_src] scratch: correspondences_
+  double* mahal;           // [n_src][6] scratch: mahalanobis_
+  b200reg_result* result;
+};
+
+struct GicpShared {
+  double R[9], t[3];    // pose of the current pass
+  float Tf[12];         // the same, cast to float (row-major 3x4)
+  double x0R[9], x0t[3];
+  double H[36], b[6], d[6], dR[9], dt[3];
+  double y0, lambda, nu, last_err;
+  int phase, lm_k, iter, nr_iterations, converged, n_lin, n_err;
+  double hits;
+  double tot[kGicpStride];
+  double red[kGicpWarps][kGicpStride];
+};
+
+__device__ inline void iso_mul(const double* aR, const double* at, const double* bR, const double* bt, double* cR, double* ct) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) cR[3 * i + j] = aR[3 * i] * bR[j] + aR[3 * i + 1] * bR[3 + j] + aR[3 * i + 2] * bR[6 + j];
+    ct[i] = aR[3 * i] * bt[0] + aR[3 * i + 1] * bt[1] + aR[3 * i + 2] * bt[2] + at[i];
+  }
+}
+
+// so3_exp / se3_exp of fast_gicp/so3/so3.hpp (A.5): a = [rotation(3), translation(3)]
+__device__ inline void se3_exp(const double a[6], double R[9], double t[3]) {
+  const double w0 = a[0], w1 = a[1], w2 = a[2];
+  const double theta_sq = w0 * w0 + w1 * w1 + w2 * w2;
+  const double theta = sqrt(theta_sq);
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    const double theta_quad = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
+  } else {
+    const double half = 0.5 * theta;
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  const double qw = real, qx = imag * w0, qy = imag * w1, qz = imag * w2;
+  const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+  double V[9];
+  if (theta < 1e-10) {
+    for (int k = 0; k < 9; ++k) V[k] = R[k];
+  } else {
+    const double O[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+    double O2[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+    const double c1 = (1.0 - cos(theta)) / theta_sq, c2 = (theta - sin(theta)) / (theta_sq * theta);
+    for (int k = 0; k < 9; ++k) V[k] = ((k % 4 == 0) ? 1.0 : 0.0) + c1 * O[k] + c2 * O2[k];
+  }
+  for (int i = 0; i < 3; ++i) t[i] = V[3 * i] * a[3] + V[3 * i + 1] * a[4] + V[3 * i + 2] * a[5];
+}
+
+__device__ inline bool gicp_is_converged(const double* dR, const double* dt, double rot_eps, double trans_eps) {
+  double rmax = 0, tmax = 0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) rmax = fmax(rmax, fabs(dR[3 * i + j] - (i == j ? 1.0 : 0.0)));
+    tmax = fmax(tmax, fabs(dt[i]));
+  }
+  return fmax(rmax / rot_eps, tmax / trans_eps) < 1;
+}
+
+__device__ inline void gicp_set_pose(GicpShared& s, const double* R, const double* t) {
+  for (int k = 0; k < 9; ++k) s.R[k] = R[k];
+  for (int k = 0; k < 3; ++k) s.t[k] = t[k];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) s.Tf[4 * i + j] = (float)R[3 * i + j];
+    s.Tf[4 * i + 3] = (float)t[i];
+  }
+}
+
+__host__ __device__ constexpr int gicp_hidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  // i <= j, 0..20
+
+// LM / GN state machine (step_lm / step_gn / the outer loop of computeTransformation), one lane
+static __device__ __noinline__ void gicp_step(GicpShared& s, const GicpParams& prm) {
+  const double* T = s.tot;
+  bool step_done = false, step_ok = true, try_lm = false;
+  if (s.phase == GP_LINEARIZE) {
+    s.n_lin++;
+    s.hits += T[28];
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = T[gicp_hidx(i, j)];
+    for (int i = 0; i < 6; ++i) s.b[i] = T[21 + i];
+    s.y0 = T[27];
+    s.last_err = s.y0;
+    if (prm.lsq == B200REG_LSQ_GN) {
+      double nb[6];
+      for (int k = 0; k < 6; ++k) nb[k] = -s.b[k];
+      solve6(s.H, nb, s.d);
+      se3_exp(s.d, s.dR, s.dt);
+      double nR[9], nt[3];
+      iso_mul(s.dR, s.dt, s.x0R, s.x0t, nR, nt);
+      for (int k = 0; k < 9; ++k) s.x0R[k] = nR[k];
+      for (int k = 0; k < 3; ++k) s.x0t[k] = nt[k];
+      step_done = true;
+    } else {
+      if (s.lambda < 0.0) {
+        double mx = 0;
+        for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(s.H[6 * i + i]));
+        s.lambda = prm.lm_init_lambda_factor * mx;
+      }
+      s.nu = 2.0;
+      s.lm_k = 0;
+      try_lm = true;
+    }
+  } else if (s.phase == GP_ERROR) {
+    s.n_err++;
+    const double yi = T[27];
+    double denom = 0;
+    for (int k = 0; k < 6; ++k) denom += s.d[k] * (s.lambda * s.d[k] - s.b[k]);
+    const double rho = (s.y0 - yi) / denom;
+    if (rho < 0) {
+      if (gicp_is_converged(s.dR, s.dt, prm.rot_eps, prm.trans_eps)) {
+        step_done = true;
+      } else {
+        s.lambda = s.nu * s.lambda;
+        s.nu = 2 * s.nu;
+        s.lm_k++;
+        if (s.lm_k < prm.lm_max_iterations) try_lm = true;
+        else { step_done = true; step_ok = false; }  // "lm not converged!!"
+      }
+    } else {
+      for (int k = 0; k < 9; ++k) s.x0R[k] = s.R[k];
+      for (int k = 0; k < 3; ++k) s.x0t[k] = s.t[k];
+      const double c = 2 * rho - 1;
+      const double f = 1 - c * c * c;
+      s.lambda = s.lambda * ((1.0 / 3.0 < f) ? f : 1.0 / 3.0);  // std::max(1/3, f): NaN keeps 1/3
+      s.last_err = yi;
+      step_done = true;
+    }
+  }
+  if (try_lm) {
+    double A[36], nb[6];
+    for (int k = 0; k < 36; ++k) A[k] = s.H[k];
+    for (int k = 0; k < 6; ++k) { A[7 * k] += s.lambda; nb[k] = -s.b[k]; }
+    solve6(A, nb, s.d);
+    se3_exp(s.d, s.dR, s.dt);
+    double nR[9], nt[3];
+    iso_mul(s.dR, s.dt, s.x0R, s.x0t, nR, nt);
+    gicp_set_pose(s, nR, nt);
+    s.phase = GP_ERROR;
+    return;
+  }
+  if (step_done) {
+    if (!step_ok) { s.phase = GP_DONE; return; }
+    s.converged = gicp_is_converged(s.dR, s.dt, prm.rot_eps, prm.trans_eps) ? 1 : 0;
+    s.iter++;
+    if (s.converged || s.iter >= prm.max_iterations) { s.phase = GP_DONE; return; }
+    s.nr_iterations = s.iter;
+    gicp_set_pose(s, s.x0R, s.x0t);
+    s.phase = GP_LINEARIZE;
+  }
+}
+
+// the residual of one correspondence; accumulates into acc[0..27] when LIN (H, b, error) else acc[27]
+template <bool LIN>
+__device__ __forceinline__ void gicp_residual(const GicpShared& s, const float4 p, const float4 tq, const double M[6], double (&acc)[kGicpAcc]) {
+  const double a0 = (double)p.x, a1 = (double)p.y, a2 = (double)p.z;
+  const double x = s.R[0] * a0 + s.R[1] * a1 + s.R[2] * a2 + s.t[0];
+  const double y = s.R[3] * a0 + s.R[4] * a1 + s.R[5] * a2 + s.t[1];
+  const double z = s.R[6] * a0 + s.R[7] * a1 + s.R[8] * a2 + s.t[2];
+  const double e0 = (double)tq.x - x, e1 = (double)tq.y - y, e2 = (double)tq.z - z;
+  const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[3], m12 = M[4], m22 = M[5];
+  const double Me0 = m00 * e0 + m01 * e1 + m02 * e2, Me1 = m01 * e0 + m11 * e1 + m12 * e2, Me2 = m02 * e0 + m12 * e1 + m22 * e2;
+  acc[27] += e0 * Me0 + e1 * Me1 + e2 * Me2;
+  if (!LIN) return;
+  acc[28] += 1.0;
+  // J = [ skew(ta) | -I ],  skew(ta) = S = [[0,-z,y],[z,0,-x],[-y,x,0]]
+  // A = M S (columns of S):  S col0 = (0, z, -y), col1 = (-z, 0, x), col2 = (y, -x, 0)
+  const double A00 = m01 * z - m02 * y, A01 = -m00 * z + m02 * x, A02 = m00 * y - m01 * x;
+  const double A10 = m11 * z - m12 * y, A11 = -m01 * z + m12 * x, A12 = m01 * y - m11 * x;
+  const double A20 = m12 * z - m22 * y, A21 = -m02 * z + m22 * x, A22 = m02 * y - m12 * x;
+  // H_rr = S^T A ; rows of S^T = columns of S
+  acc[gicp_hidx(0, 0)] += z * A10 - y * A20;
+  acc[gicp_hidx(0, 1)] += z * A11 - y * A21;
+  acc[gicp_hidx(0, 2)] += z * A12 - y * A22;
+  acc[gicp_hidx(1, 1)] += -z * A01 + x * A21;
+  acc[gicp_hidx(1, 2)] += -z * A02 + x * A22;
+  acc[gicp_hidx(2, 2)] += y * A02 - x * A12;
+  // H_rt = S^T M (-I) = -(M S)^T = -A^T
+  acc[gicp_hidx(0, 3)] -= A00; acc[gicp_hidx(0, 4)] -= A10; acc[gicp_hidx(0, 5)] -= A20;
+  acc[gicp_hidx(1, 3)] -= A01; acc[gicp_hidx(1, 4)] -= A11; acc[gicp_hidx(1, 5)] -= A21;
+  acc[gicp_hidx(2, 3)] -= A02; acc[gicp_hidx(2, 4)] -= A12; acc[gicp_hidx(2, 5)] -= A22;
+  // H_tt = M
+  acc[gicp_hidx(3, 3)] += m00; acc[gicp_hidx(3, 4)] += m01; acc[gicp_hidx(3, 5)] += m02;
+  acc[gicp_hidx(4, 4)] += m11; acc[gicp_hidx(4, 5)] += m12; acc[gicp_hidx(5, 5)] += m22;
+  // b = J^T M e:  b_r = S^T Me, b_t = -Me
+  acc[21] += z * Me1 - y * Me2;
+  acc[22] += -z * Me0 + x * Me2;
+  acc[23] += y * Me0 - x * Me1;
+  acc[24] -= Me0; acc[25] -= Me1; acc[26] -= Me2;
+}
+
+// mahalanobis_[i] = (C_B + R C_A R^T)^-1 as 6 doubles
+__device__ __forceinline__ void gicp_mahalanobis(const double* R, const double* CA, const double* CB, double M[6]) {
+  const double a[9] = {CA[0], CA[1], CA[2], CA[1], CA[3], CA[4], CA[2], CA[4], CA[5]};
+  double RA[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) RA[3 * i + j] = R[3 * i] * a[j] + R[3 * i + 1] * a[3 + j] + R[3 * i + 2] * a[6 + j];
+  double S[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[3 * i + j] = RA[3 * i] * R[3 * j] + RA[3 * i + 1] * R[3 * j + 1] + RA[3 * i + 2] * R[3 * j + 2];
+  S[0] += CB[0]; S[1] += CB[1]; S[2] += CB[2]; S[3] += CB[1]; S[4] += CB[3]; S[5] += CB[4]; S[6] += CB[2]; S[7] += CB[4]; S[8] += CB[5];
+  double Si[9];
+  inverse3(S, Si);
+  M[0] = Si[0]; M[1] = Si[1]; M[2] = Si[2]; M[3] = Si[4]; M[4] = Si[5]; M[5] = Si[8];
+}
+
+__device__ __forceinline__ void gicp_group_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const GicpJob* __restrict__ jobs, int G, GicpParams prm, double* partials, unsigned int* barrier) {
+  __shared__ GicpShared s;
+  const GicpJob& job = jobs[0];
+  const int rank = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_src = job.n_src;
+  const GridParams gp = job.tgt.meta->grid;
+  const bool grid_ok = job.tgt.n > 0 && gp.any && !gp.overflow;
+  unsigned int epoch = 0;
+  int parity = 0;
+  if (tid == 0) {
+    // x0 = Isometry3d(guess.cast<double>())
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) s.x0R[3 * i + j] = (double)job.guess[4 * j + i];
+      s.x0t[i] = (double)job.guess[12 + i];
+    }
+    for (int k = 0; k < 9; ++k) s.dR[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    s.dt[0] = s.dt[1] = s.dt[2] = 0.0;
+    s.lambda = -1.0; s.nu = 2.0; s.y0 = 0.0; s.last_err = 0.0;
+    s.lm_k = 0; s.iter = 0; s.nr_iterations = 0; s.converged = 0; s.n_lin = 0; s.n_err = 0; s.hits = 0.0;
+    gicp_set_pose(s, s.x0R, s.x0t);
+    s.phase = (prm.max_iterations > 0 && n_src > 0) ? GP_LINEARIZE : GP_DONE;
+  }
+  __syncthreads();
+  while (s.phase != GP_DONE) {
+    const int phase = s.phase;
+    double acc[kGicpAcc];
+#pragma unroll
+    for (int k = 0; k < kGicpAcc; ++k) acc[k] = 0.0;
+    // ---- pass over the source points: whole warps stay together so a far query can use all lanes
+    const int stride = G * kGicpThreads;
+    for (int base = rank * kGicpThreads + warp * 32; base < n_src; base += stride) {
+      const int i = base + lane;
+      const bool active = i < n_src;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) p = __ldg(job.src + i);
+      if (phase == GP_LINEARIZE) {
+        // update_correspondences: float transform, exact 1-NN, gate on the squared distance
+        const float qx = affine_row(s.Tf[0], s.Tf[1], s.Tf[2], s.Tf[3], p.x, p.y, p.z);
+        const float qy = affine_row(s.Tf[4], s.Tf[5], s.Tf[6], s.Tf[7], p.x, p.y, p.z);
+        const float qz = affine_row(s.Tf[8], s.Tf[9], s.Tf[10], s.Tf[11], p.x, p.y, p.z);
+        float best = 3.402823466e+38f;
+        int best_idx = kNoIndex;
+        bool ok = true;
+        if (active && grid_ok) ok = nn_query_near(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
+        // the few queries the near phase left open: the warp finishes them one by one, all lanes helping
+        unsigned open = __ballot_sync(0xffffffffu, !ok);
+        while (open) {
+          const int src_lane = __ffs(open) - 1;
+          open &= open - 1;
+          const float fx = __shfl_sync(0xffffffffu, qx, src_lane), fy = __shfl_sync(0xffffffffu, qy, src_lane), fz = __shfl_sync(0xffffffffu, qz, src_lane);
+          float fb = __shfl_sync(0xffffffffu, best, src_lane);
+          int fi = __shfl_sync(0xffffffffu, best_idx, src_lane);
+          const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, fx, fy, fz), prm.search_d2, prm.far_ring, lane, fb, fi);
+          if (!done) nn_query_brute_warp(job.tgt, fx, fy, fz, lane, fb, fi);
+          if (lane == src_lane) { best = fb; best_idx = fi; }
+        }
+        int c = -1;
+        if (active && best_idx != kNoIndex && (double)best < prm.corr_dist2) c = best_idx;
+        if (active) job.corr[i] = c;
+        if (c >= 0) {
+          double CA[6], CB[6], M[6];
+          const double* pa = job.cov_src + (size_t)i * 6;
+          const double* pb = job.cov_tgt + (size_t)c * 6;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { CA[k] = pa[k]; CB[k] = __ldg(pb + k); }
+          gicp_mahalanobis(s.R, CA, CB, M);
+          double* pm = job.mahal + (size_t)i * 6;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) pm[k] = M[k];
+          gicp_residual<true>(s, p, __ldg(job.tgt_pts + c), M, acc);
+        }
+      } else {
+        const int c = active ? job.corr[i] : -1;
+        if (c >= 0) {
+          double M[6];
+          const double* pm = job.mahal + (size_t)i * 6;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) M[k] = pm[k];
+          gicp_residual<false>(s, p, __ldg(job.tgt_pts + c), M, acc);
+        }
+      }
+    }
+    // ---- reduce: warp shuffles -> shared memory -> one partial row per CTA -> group
+#pragma unroll
+    for (int k = 0; k < kGicpAcc; ++k) {
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s.red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < kGicpAcc) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kGicpWarps; ++w) v += s.red[w][tid];
+      if (G == 1) s.tot[tid] = v;
+      else partials[((size_t)parity * G + rank) * kGicpStride + tid] = v;
+    }
+    if (G > 1) {
+      epoch += (unsigned)G;
+      gicp_group_barrier(barrier, epoch);
+      const double* base = partials + (size_t)parity * G * kGicpStride + lane;
+      double v = 0.0;
+      if (lane < kGicpAcc)
+        for (int r = warp; r < G; r += kGicpWarps) v += __ldcg(base + (size_t)r * kGicpStride);
+      __syncthreads();
+      s.red[warp][lane] = v;
+      __syncthreads();
+      if (tid < kGicpAcc) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kGicpWarps; ++w) t += s.red[w][tid];
+        s.tot[tid] = t;
+      }
+    }
+    parity ^= 1;
+    __syncthreads();
+    if (tid == 0) gicp_step(s, prm);
+    __syncthreads();
+  }
+  if (rank == 0 && tid == 0) {
+    b200reg_result r;
+    for (int c = 0; c < 3; ++c) {
+      for (int rr = 0; rr < 3; ++rr) r.transformation[4 * c + rr] = (float)s.x0R[3 * rr + c];
+      r.transformation[4 * c + 3] = 0.f;
+    }
+    for (int rr = 0; rr < 3; ++rr) r.transformation[12 + rr] = (float)s.x0t[rr];
+    r.transformation[15] = 1.f;
+    r.fitness = 0.0;
+    r.score = s.last_err;
+    r.converged = s.converged;
+    r.iterations = s.nr_iterations;
+    r.evaluations = s.n_lin + s.n_err;
+    r.reserved = 0;
+    r.hits = (long long)s.hits;
+    *job.result = r;
+  }
+}
+
+}  // namespace b200

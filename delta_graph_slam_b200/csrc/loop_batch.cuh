@@ -34,14 +34,13 @@ struct CachedCloud {
   // NN product
   bool has_nn = false;
   DevBuf<float4> nn_pts;
-  DevBuf<uint2> nn_table;
-  DevBuf<uint32_t> nn_cell_start;
+  DevBuf<uint4> nn_table;
   DevBuf<SortMeta> nn_meta;
   uint32_t nn_cap = 0;
 
   void release() {
     pts.release(); voxels.release(); centroids.release(); table.release(); gmeta.release(); meta.release();
-    nn_pts.release(); nn_table.release(); nn_cell_start.release(); nn_meta.release();
+    nn_pts.release(); nn_table.release(); nn_meta.release();
     has_ndt = has_nn = false;
     n = 0;
   }
@@ -53,7 +52,7 @@ struct CachedCloud {
   NnView nn_view() const {
     NnView v;
     v.meta = nn_meta.p; v.table = nn_table.p; v.table_mask = nn_cap - 1; v.table_shift = 32 - (int)__builtin_ctz(nn_cap);
-    v.cell_start = nn_cell_start.p; v.pts = nn_pts.p; v.n = n;
+    v.pts = nn_pts.p; v.n = n;
     return v;
   }
 };
@@ -72,10 +71,10 @@ inline cudaError_t cache_build_ndt(cudaStream_t st, NdtGrid& builder, CachedClou
 }
 
 inline cudaError_t cache_build_nn(cudaStream_t st, NnGrid& builder, CachedCloud& c) {
-  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.vox_start, c.nn_cell_start); std::swap(builder.sort.meta, c.nn_meta);
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta);
   cudaError_t e = builder.build(st, c.pts.p, c.n);
   c.nn_cap = builder.table_cap;
-  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.vox_start, c.nn_cell_start); std::swap(builder.sort.meta, c.nn_meta);
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta);
   builder.built = false;
   if (e == cudaSuccess) c.has_nn = true;
   return e;
@@ -92,8 +91,15 @@ struct FitJob {
 
 constexpr float kNoNeighbour = __builtin_huge_valf();  // d2 of a query with nothing inside max_range
 
-// blockIdx.y = job, blockIdx.x = 256-point slice of its source.  Transform by the pair's final
-// transformation (float, pcl::transformPoint order) and search; unresolved far queries go to `pending`.
+__device__ __forceinline__ void fit_transform(const float* T, const float4 p, float& qx, float& qy, float& qz) {
+  qx = affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z);
+  qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
+  qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
+}
+
+// near phase: blockIdx.y = job, blockIdx.x = 256-point slice of its source.  Transform by the pair's
+// final transformation (float, pcl::transformPoint order) and search rings 0..1; unresolved queries
+// go to `pending` with their best-so-far in d2_out.
 __global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, float max_d2, float* __restrict__ d2_out,
                                                          uint2* __restrict__ pending, unsigned int* __restrict__ n_pending) {
   const FitJob& job = jobs[blockIdx.y];
@@ -104,46 +110,54 @@ __global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restric
   __syncthreads();
   if (i >= job.n_src) return;
   const GridParams gp = job.view.meta->grid;
-  const float4 p = __ldg(job.src + i);
-  const float qx = affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z);
-  const float qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
-  const float qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
+  float qx, qy, qz;
+  fit_transform(T, __ldg(job.src + i), qx, qy, qz);
   float best = 3.402823466e+38f;
-  int best_idx = -1;
+  int best_idx = kNoIndex;
   bool ok = true;
-  if (job.view.n > 0 && gp.any && !gp.overflow) ok = nn_query(job.view, gp, qx, qy, qz, max_d2, best, best_idx);
-  d2_out[job.d2_offset + i] = best_idx >= 0 ? best : kNoNeighbour;
+  if (job.view.n > 0 && gp.any && !gp.overflow) ok = nn_query_near(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  d2_out[job.d2_offset + i] = best_idx != kNoIndex ? best : kNoNeighbour;
   if (!ok) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i);
 }
 
-// far outliers: one warp per pending (job, point) scans the pair's whole target
-__global__ void __launch_bounds__(256) k_nn_bruteforce_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, const uint2* __restrict__ pending,
-                                                             const unsigned int* __restrict__ n_pending, float* __restrict__ d2_out) {
+// far phase: one warp per pending (job, point); still-open queries move to pending2
+__global__ void __launch_bounds__(256) k_nn_far_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, const uint2* __restrict__ pending,
+                                                      const unsigned int* __restrict__ n_pending, float max_d2, float* __restrict__ d2_out, uint2* __restrict__ pending2,
+                                                      unsigned int* __restrict__ n_pending2) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int np = (int)*n_pending;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < np; w += warps) {
     const uint2 pe = pending[w];
     const FitJob& job = jobs[pe.x];
-    const float* T = results[job.result].transformation;
-    const float4 p = __ldg(job.src + pe.y);
-    const float qx = affine_row(T[0], T[4], T[8], T[12], p.x, p.y, p.z);
-    const float qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
-    const float qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
-    float best = 3.402823466e+38f;
-    bool found = false;
-    for (int j = lane; j < job.view.n; j += 32) {
-      const float4 t = __ldg(job.view.pts + j);
-      const float d = l2_simple(qx, qy, qz, t.x, t.y, t.z);
-      if (!found || d < best) { best = d; found = true; }
+    const GridParams gp = job.view.meta->grid;
+    float qx, qy, qz;
+    fit_transform(results[job.result].transformation, __ldg(job.src + pe.y), qx, qy, qz);
+    const float prev = d2_out[job.d2_offset + pe.y];
+    float best = prev == kNoNeighbour ? 3.402823466e+38f : prev;
+    int best_idx = prev == kNoNeighbour ? kNoIndex : 0;  // the index itself is not needed for the score
+    const bool ok = nn_query_far_warp(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, kFarRing, lane, best, best_idx);
+    __syncwarp();
+    if (lane == 0) {
+      d2_out[job.d2_offset + pe.y] = best_idx != kNoIndex ? best : kNoNeighbour;
+      if (!ok) pending2[atomicAdd(n_pending2, 1u)] = pe;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int of = __shfl_xor_sync(0xffffffffu, (int)found, o);
-      if (of && (!found || ob < best)) { best = ob; found = true; }
-    }
-    if (lane == 0) d2_out[job.d2_offset + pe.y] = found ? best : kNoNeighbour;
+  }
+}
+
+// brute phase: one CTA per still-open (job, point) scans the pair's whole target
+__global__ void __launch_bounds__(256) k_nn_bruteforce_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, const uint2* __restrict__ pending,
+                                                             const unsigned int* __restrict__ n_pending, float* __restrict__ d2_out) {
+  const int np = (int)*n_pending;
+  for (int w = blockIdx.x; w < np; w += gridDim.x) {
+    const uint2 pe = pending[w];
+    const FitJob& job = jobs[pe.x];
+    float qx, qy, qz;
+    fit_transform(results[job.result].transformation, __ldg(job.src + pe.y), qx, qy, qz);
+    float best;
+    int best_idx;
+    nn_query_brute_block(job.view, qx, qy, qz, best, best_idx);
+    if (threadIdx.x == 0) d2_out[job.d2_offset + pe.y] = best_idx != kNoIndex ? best : kNoNeighbour;
   }
 }
 

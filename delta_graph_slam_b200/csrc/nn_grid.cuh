@@ -1,40 +1,48 @@
-// b200reg — exact nearest-neighbour search on the target cloud: the B200 replacement of the FLANN
-// kd-tree that pcl::Registration::initCompute builds and getFitnessScore queries,
+// b200reg — exact nearest-neighbour search on a cloud: the B200 replacement of the FLANN kd-tree
+// that pcl::Registration::initCompute builds and getFitnessScore queries,
 // [REF include/hdl_graph_slam/loop_detector.hpp:148; apps/scan_matching_odometry_nodelet.cpp:318-332;
-//  src/hdl_graph_slam/information_matrix_calculator.cpp:77-108].
+//  src/hdl_graph_slam/information_matrix_calculator.cpp:77-108], and of fast_gicp's source / target
+// kd-trees (1-NN correspondences, k-NN covariances).
 //
-// Structure: a uniform cell grid over the target.  Points are re-ordered by cell with the same
+// Structure: a uniform 0.5 m cell grid over the cloud.  Points are re-ordered by cell with the same
 // key / radix-sort / segmentation machinery as VoxelGrid (w of each re-ordered float4 carries the
-// original index), and an open-addressing hash maps cell -> run.  A query walks Chebyshev rings
-// of cells around its own cell, prunes cells by box distance, and stops when nothing outside the
-// examined block can beat the best distance: the result is EXACT, with FLANN's float metric
-// ((dx*dx)+dy*dy)+dz*dz and ties broken by lowest index (the oracle's convention).  Queries that
-// are still open after kMaxRing rings (far outliers; max_range defaults to DBL_MAX upstream) are
-// finished by a warp-per-query brute-force kernel, so the search is exact at any range.
+// original index) and an open-addressing hash maps cell -> (first point, end point), so a probe is
+// ONE 16-byte load.  Results are EXACT, with FLANN's float metric ((dx*dx)+dy*dy)+dz*dz and ties
+// broken by lowest index (the oracle's convention).
+//
+// A query runs in up to three phases so that the rare far queries cannot stretch the kernel:
+//   near  : one thread per query walks the Chebyshev rings 0 and 1 (27 cells, pruned by box
+//           distance); ~98 % of the queries of an aligned scan pair finish here
+//   far   : one WARP per remaining query: the 32 lanes take the cells of ring 2, 3, ... in
+//           parallel, merge their best after every ring and stop as soon as nothing outside the
+//           examined block can win, lies beyond max_d2, or the block covers the occupied lattice
+//   brute : (unbounded range only) queries still open after kFarRing rings are finished by a
+//           CTA-per-query scan of the whole cloud, with several loads in flight per thread
 #pragma once
 #include "voxel_sort.cuh"
 
 namespace b200 {
 
-constexpr int kMaxRing = 4;
+constexpr int kNearRing = 1;   // rings walked by the thread-per-query phase
+constexpr int kFarRing = 8;    // rings walked by the warp-per-query phase before the brute-force pass (4 m)
 constexpr float kNnCell = 0.5f;
 
 struct NnView {
   const SortMeta* meta;
-  const uint2* table;
+  const uint4* table;  // (cell key, first point, end point, -)
   uint32_t table_mask;
   int table_shift;
-  const uint32_t* cell_start;  // [n_cells + 1]
-  const float4* pts;           // re-ordered by cell; w = original index (int bits)
+  const float4* pts;  // re-ordered by cell; w = original index (int bits)
   int n;
 };
 
-__device__ __forceinline__ int nn_lookup(const NnView& g, uint32_t key) {
+// (first, end) of the cell's run, or first == end when the cell is empty
+__device__ __forceinline__ uint2 nn_lookup(const NnView& g, uint32_t key) {
   uint32_t h = (key * 2654435761u) >> g.table_shift;
   while (true) {
-    uint2 e = __ldg(g.table + h);
-    if (e.x == key) return (int)e.y;
-    if (e.x == kInvalidKey) return -1;
+    const uint4 e = __ldg(g.table + h);
+    if (e.x == key) return make_uint2(e.y, e.z);
+    if (e.x == kInvalidKey) return make_uint2(0u, 0u);
     h = (h + 1) & g.table_mask;
   }
 }
@@ -50,79 +58,170 @@ __global__ void __launch_bounds__(256) k_nn_reorder(const float4* __restrict__ p
   out[i] = p;
 }
 
-__global__ void __launch_bounds__(256) k_nn_insert(const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_key, uint2* __restrict__ table, uint32_t mask, int shift) {
+__global__ void __launch_bounds__(256) k_nn_insert(const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_key, const uint32_t* __restrict__ vox_start, uint4* __restrict__ table,
+                                                   uint32_t mask, int shift) {
   const int n_vox = (int)meta->n_vox;
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_vox; slot += gridDim.x * blockDim.x) {
     const uint32_t key = vox_key[slot];
     uint32_t h = (key * 2654435761u) >> shift;
     while (true) {
       uint32_t old = atomicCAS(&table[h].x, kInvalidKey, key);
-      if (old == kInvalidKey) { table[h].y = (uint32_t)slot; break; }
+      if (old == kInvalidKey) {
+        table[h].y = vox_start[slot];
+        table[h].z = vox_start[slot + 1];
+        break;
+      }
       h = (h + 1) & mask;
     }
   }
 }
 
-// exact 1-NN of q.  Returns true when resolved (best / best_idx final, best_idx = -1 if nothing
-// lies within max_d2); false when the ring budget ran out (caller defers to the brute-force pass).
-__device__ __forceinline__ bool nn_query(const NnView& g, const GridParams& gp, float qx, float qy, float qz, float max_d2, float& best, int& best_idx) {
+// ---- the search --------------------------------------------------------------------------------
+struct NnQuery {
+  float qx, qy, qz;
+  int cx, cy, cz;
+  float margin;
+};
+
+__device__ __forceinline__ NnQuery nn_make_query(const GridParams& gp, float qx, float qy, float qz) {
+  NnQuery q;
+  q.qx = qx; q.qy = qy; q.qz = qz;
+  q.cx = (int)floorf(__fmul_rn(qx, gp.inv_leaf[0]));
+  q.cy = (int)floorf(__fmul_rn(qy, gp.inv_leaf[1]));
+  q.cz = (int)floorf(__fmul_rn(qz, gp.inv_leaf[2]));
+  q.margin = 1e-3f * gp.leaf[0] + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+  return q;
+}
+
+// true when every point outside the (2r-1)^3 block of cells around the query cell is provably no
+// better than `best`, lies beyond max_d2, or does not exist (the block covers the occupied lattice)
+__device__ __forceinline__ bool nn_settled(const GridParams& gp, const NnQuery& q, int r, float best, float max_d2) {
   const float c = gp.leaf[0];
-  const int cx = (int)floorf(__fmul_rn(qx, gp.inv_leaf[0])), cy = (int)floorf(__fmul_rn(qy, gp.inv_leaf[1])), cz = (int)floorf(__fmul_rn(qz, gp.inv_leaf[2]));
-  const float margin = 1e-3f * c + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+  const float gx = fminf(q.qx - (float)(q.cx - (r - 1)) * c, (float)(q.cx + r) * c - q.qx);
+  const float gy = fminf(q.qy - (float)(q.cy - (r - 1)) * c, (float)(q.cy + r) * c - q.qy);
+  const float gz = fminf(q.qz - (float)(q.cz - (r - 1)) * c, (float)(q.cz + r) * c - q.qz);
+  const float gap = fmaxf(fminf(gx, fminf(gy, gz)) - q.margin, 0.f);
+  const float gap2 = gap * gap;
+  if (best <= gap2 || gap2 > max_d2) return true;
+  return q.cx - (r - 1) <= gp.min_b[0] && q.cx + (r - 1) >= gp.max_b[0] && q.cy - (r - 1) <= gp.min_b[1] && q.cy + (r - 1) >= gp.max_b[1] && q.cz - (r - 1) <= gp.min_b[2] &&
+         q.cz + (r - 1) >= gp.max_b[2];
+}
+
+// lower bound of the squared distance from the query to cell (ix, iy, iz)
+__device__ __forceinline__ float nn_box_d2(const GridParams& gp, const NnQuery& q, int ix, int iy, int iz) {
+  const float c = gp.leaf[0];
+  const float dx = fmaxf(fmaxf((float)ix * c - q.margin - q.qx, q.qx - ((float)(ix + 1) * c + q.margin)), 0.f);
+  const float dy = fmaxf(fmaxf((float)iy * c - q.margin - q.qy, q.qy - ((float)(iy + 1) * c + q.margin)), 0.f);
+  const float dz = fmaxf(fmaxf((float)iz * c - q.margin - q.qz, q.qz - ((float)(iz + 1) * c + q.margin)), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ bool nn_better(float d, int idx, float best, int best_idx) { return d < best || (d == best && idx < best_idx); }
+
+// scan one cell; best_idx = INT_MAX-style sentinel 0x7FFFFFFF while nothing was found
+__device__ __forceinline__ void nn_scan_cell(const NnView& g, const GridParams& gp, const NnQuery& q, int ix, int iy, int iz, float& best, int& best_idx) {
+  const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+  const uint2 run = nn_lookup(g, key);
+#pragma unroll 4
+  for (uint32_t j = run.x; j < run.y; ++j) {
+    const float4 p = __ldg(g.pts + j);
+    const float d = l2_simple(q.qx, q.qy, q.qz, p.x, p.y, p.z);
+    const int idx = __float_as_int(p.w);
+    if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+  }
+}
+
+constexpr int kNoIndex = 0x7FFFFFFF;
+
+// near phase, one thread: rings 0..kNearRing.  Returns true when the query is resolved.
+__device__ __forceinline__ bool nn_query_near(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, float& best, int& best_idx) {
   best = 3.402823466e+38f;
-  best_idx = -1;
-  // true when every point outside the (2r-1)^3 block around the query cell is provably no better
-  // than `best`, lies beyond max_d2, or does not exist (block covers the occupied lattice)
-  auto settled = [&](int r) {
-    const float gx = fminf(qx - (float)(cx - (r - 1)) * c, (float)(cx + r) * c - qx);
-    const float gy = fminf(qy - (float)(cy - (r - 1)) * c, (float)(cy + r) * c - qy);
-    const float gz = fminf(qz - (float)(cz - (r - 1)) * c, (float)(cz + r) * c - qz);
-    const float gap = fmaxf(fminf(gx, fminf(gy, gz)) - margin, 0.f);
-    const float gap2 = gap * gap;
-    if (best <= gap2 || gap2 > max_d2) return true;
-    return cx - (r - 1) <= gp.min_b[0] && cx + (r - 1) >= gp.max_b[0] && cy - (r - 1) <= gp.min_b[1] && cy + (r - 1) >= gp.max_b[1] && cz - (r - 1) <= gp.min_b[2] &&
-           cz + (r - 1) >= gp.max_b[2];
-  };
-  for (int r = 0; r <= kMaxRing; ++r) {
-    if (r >= 1 && settled(r)) return true;
-    const int z0 = max(cz - r, gp.min_b[2]), z1 = min(cz + r, gp.max_b[2]);
-    const int y0 = max(cy - r, gp.min_b[1]), y1 = min(cy + r, gp.max_b[1]);
+  best_idx = kNoIndex;
+  for (int r = 0; r <= kNearRing; ++r) {
+    if (r >= 1 && nn_settled(gp, q, r, best, max_d2)) return true;
+    const int z0 = max(q.cz - r, gp.min_b[2]), z1 = min(q.cz + r, gp.max_b[2]);
+    const int y0 = max(q.cy - r, gp.min_b[1]), y1 = min(q.cy + r, gp.max_b[1]);
     for (int iz = z0; iz <= z1; ++iz) {
-      const float dzl = (float)iz * c - margin - qz, dzh = qz - ((float)(iz + 1) * c + margin);
-      const float dz = fmaxf(fmaxf(dzl, dzh), 0.f);
-      const bool zface = (iz == cz - r) || (iz == cz + r);
+      const bool zface = (iz == q.cz - r) || (iz == q.cz + r);
       for (int iy = y0; iy <= y1; ++iy) {
-        const float dyl = (float)iy * c - margin - qy, dyh = qy - ((float)(iy + 1) * c + margin);
-        const float dy = fmaxf(fmaxf(dyl, dyh), 0.f);
-        const float dyz2 = dz * dz + dy * dy;
-        if (dyz2 > best) continue;
-        const bool face = zface || (iy == cy - r) || (iy == cy + r);
+        const bool face = zface || (iy == q.cy - r) || (iy == q.cy + r);
         const int xstep = face ? 1 : (r == 0 ? 1 : 2 * r);
-        for (int ix = cx - r; ix <= cx + r; ix += xstep) {
+        for (int ix = q.cx - r; ix <= q.cx + r; ix += xstep) {
           if (ix < gp.min_b[0] || ix > gp.max_b[0]) continue;
-          const float dxl = (float)ix * c - margin - qx, dxh = qx - ((float)(ix + 1) * c + margin);
-          const float dx = fmaxf(fmaxf(dxl, dxh), 0.f);
-          if (dyz2 + dx * dx > best) continue;
-          const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
-          const int slot = nn_lookup(g, key);
-          if (slot < 0) continue;
-          const uint32_t s = __ldg(g.cell_start + slot), e = __ldg(g.cell_start + slot + 1);
-          for (uint32_t j = s; j < e; ++j) {
-            const float4 p = __ldg(g.pts + j);
-            const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-            const int idx = __float_as_int(p.w);
-            if (d < best || (d == best && idx < best_idx)) { best = d; best_idx = idx; }
-          }
+          if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+          nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
         }
       }
     }
   }
-  return settled(kMaxRing + 1);
+  return nn_settled(gp, q, kNearRing + 1, best, max_d2);
 }
 
-// One thread per source point: transform by T (column-major 4x4, float, pcl::transformPoint order)
-// and search.  d2_out[i] = squared NN distance (float), idx_out[i] = target index or -1; unresolved
-// queries are appended to `pending`.
+__device__ __forceinline__ void nn_warp_merge(float& best, int& best_idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (nn_better(ob, oi, best, best_idx)) { best = ob; best_idx = oi; }
+  }
+}
+
+// far phase, one warp (all 32 lanes call with the same query and the near phase's best): rings
+// kNearRing+1 .. max_ring.  Returns true when resolved; best / best_idx are warp-uniform on return.
+__device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int max_ring, int lane, float& best, int& best_idx) {
+  for (int r = kNearRing + 1; r <= max_ring; ++r) {
+    if (nn_settled(gp, q, r, best, max_d2)) return true;
+    // the shell of ring r: two z faces (side^2), two y faces (side x inner), two x faces (inner^2)
+    const int side = 2 * r + 1, inner = 2 * r - 1;
+    const int nz = 2 * side * side, ny = 2 * side * inner, total = nz + ny + 2 * inner * inner;
+    for (int c = lane; c < total; c += 32) {
+      int dx, dy, dz;
+      if (c < nz) {
+        const int f = c / (side * side), rem = c - f * side * side;
+        dz = f ? r : -r; dx = rem % side - r; dy = rem / side - r;
+      } else if (c < nz + ny) {
+        const int cc = c - nz, f = cc / (side * inner), rem = cc - f * side * inner;
+        dy = f ? r : -r; dx = rem % side - r; dz = rem / side - (r - 1);
+      } else {
+        const int cc = c - nz - ny, f = cc / (inner * inner), rem = cc - f * inner * inner;
+        dx = f ? r : -r; dy = rem % inner - (r - 1); dz = rem / inner - (r - 1);
+      }
+      const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
+      if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
+      if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+      nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
+    }
+    nn_warp_merge(best, best_idx);
+  }
+  return nn_settled(gp, q, max_ring + 1, best, max_d2);
+}
+
+// brute phase, one warp: the whole cloud, four loads in flight per lane
+__device__ __forceinline__ void nn_query_brute_warp(const NnView& g, float qx, float qy, float qz, int lane, float& best, int& best_idx) {
+  best = 3.402823466e+38f;
+  best_idx = kNoIndex;
+  int j = lane;
+  for (; j + 96 < g.n; j += 128) {
+    const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 32), p2 = __ldg(g.pts + j + 64), p3 = __ldg(g.pts + j + 96);
+    const float d0 = l2_simple(qx, qy, qz, p0.x, p0.y, p0.z), d1 = l2_simple(qx, qy, qz, p1.x, p1.y, p1.z);
+    const float d2 = l2_simple(qx, qy, qz, p2.x, p2.y, p2.z), d3 = l2_simple(qx, qy, qz, p3.x, p3.y, p3.z);
+    if (nn_better(d0, __float_as_int(p0.w), best, best_idx)) { best = d0; best_idx = __float_as_int(p0.w); }
+    if (nn_better(d1, __float_as_int(p1.w), best, best_idx)) { best = d1; best_idx = __float_as_int(p1.w); }
+    if (nn_better(d2, __float_as_int(p2.w), best, best_idx)) { best = d2; best_idx = __float_as_int(p2.w); }
+    if (nn_better(d3, __float_as_int(p3.w), best, best_idx)) { best = d3; best_idx = __float_as_int(p3.w); }
+  }
+  for (; j < g.n; j += 32) {
+    const float4 p = __ldg(g.pts + j);
+    const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    if (nn_better(d, __float_as_int(p.w), best, best_idx)) { best = d; best_idx = __float_as_int(p.w); }
+  }
+  nn_warp_merge(best, best_idx);
+}
+
+// ---- single-pair kernels (getFitnessScore / inlier fraction on one handle) ----------------------
+// near: one thread per source point: transform by T (column-major 4x4, float, pcl::transformPoint
+// order) and search.  d2_out[i] = squared NN distance, idx_out[i] = target index or -1; unresolved
+// queries are appended to `pending` with their best-so-far kept in d2_out / idx_out.
 __global__ void __launch_bounds__(256) k_nn_search(NnView g, const float4* __restrict__ src, int n_src, const float* __restrict__ T16, int use_T, float max_d2,
                                                    float* __restrict__ d2_out, int* __restrict__ idx_out, float4* __restrict__ q_out, int* __restrict__ pending,
                                                    unsigned int* __restrict__ n_pending) {
@@ -139,40 +238,80 @@ __global__ void __launch_bounds__(256) k_nn_search(NnView g, const float4* __res
     qy = affine_row(T[1], T[5], T[9], T[13], p.x, p.y, p.z);
     qz = affine_row(T[2], T[6], T[10], T[14], p.x, p.y, p.z);
   }
-  if (q_out) q_out[i] = make_float4(qx, qy, qz, 1.f);
+  q_out[i] = make_float4(qx, qy, qz, 1.f);
   float best = 3.402823466e+38f;
-  int best_idx = -1;
+  int best_idx = kNoIndex;
   bool ok = true;
-  if (g.n > 0 && gp.any && !gp.overflow) ok = nn_query(g, gp, qx, qy, qz, max_d2, best, best_idx);
+  if (g.n > 0 && gp.any && !gp.overflow) ok = nn_query_near(g, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
   d2_out[i] = best;
-  idx_out[i] = best_idx;
+  idx_out[i] = best_idx == kNoIndex ? -1 : best_idx;
   if (!ok) pending[atomicAdd(n_pending, 1u)] = i;
 }
 
-// far outliers: one warp per pending query scans the whole target (exact, same metric and tie rule)
-__global__ void __launch_bounds__(256) k_nn_bruteforce(NnView g, const float4* __restrict__ queries, const int* __restrict__ pending, const unsigned int* __restrict__ n_pending,
-                                                       float* __restrict__ d2_out, int* __restrict__ idx_out) {
+// far: one warp per pending query; what is still open afterwards moves to pending2
+__global__ void __launch_bounds__(256) k_nn_far(NnView g, const float4* __restrict__ queries, const int* __restrict__ pending, const unsigned int* __restrict__ n_pending, float max_d2,
+                                                float* __restrict__ d2_out, int* __restrict__ idx_out, int* __restrict__ pending2, unsigned int* __restrict__ n_pending2) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int np = (int)*n_pending;
+  const GridParams gp = g.meta->grid;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < np; w += warps) {
     const int i = pending[w];
     const float4 q = queries[i];
-    float best = 3.402823466e+38f;
-    int best_idx = 0x7FFFFFFF;
-    for (int j = lane; j < g.n; j += 32) {
-      const float4 p = __ldg(g.pts + j);
-      const float d = l2_simple(q.x, q.y, q.z, p.x, p.y, p.z);
-      const int idx = __float_as_int(p.w);
-      if (d < best || (d == best && idx < best_idx)) { best = d; best_idx = idx; }
+    float best = d2_out[i];
+    int best_idx = idx_out[i] < 0 ? kNoIndex : idx_out[i];
+    const bool ok = nn_query_far_warp(g, gp, nn_make_query(gp, q.x, q.y, q.z), max_d2, kFarRing, lane, best, best_idx);
+    __syncwarp();
+    if (lane == 0) {
+      d2_out[i] = best;
+      idx_out[i] = best_idx == kNoIndex ? -1 : best_idx;
+      if (!ok) pending2[atomicAdd(n_pending2, 1u)] = i;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-      if (ob < best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
-    }
-    if (lane == 0) { d2_out[i] = best; idx_out[i] = best_idx == 0x7FFFFFFF ? -1 : best_idx; }
+  }
+}
+
+// block-wide version for the stand-alone brute-force kernels: 256 threads scan the cloud, four loads
+// in flight per thread; the result is valid in thread 0
+__device__ __forceinline__ void nn_query_brute_block(const NnView& g, float qx, float qy, float qz, float& best, int& best_idx) {
+  __shared__ float s_b[8];
+  __shared__ int s_i[8];
+  best = 3.402823466e+38f;
+  best_idx = kNoIndex;
+  int j = threadIdx.x;
+  for (; j + 768 < g.n; j += 1024) {
+    const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 256), p2 = __ldg(g.pts + j + 512), p3 = __ldg(g.pts + j + 768);
+    const float d0 = l2_simple(qx, qy, qz, p0.x, p0.y, p0.z), d1 = l2_simple(qx, qy, qz, p1.x, p1.y, p1.z);
+    const float d2 = l2_simple(qx, qy, qz, p2.x, p2.y, p2.z), d3 = l2_simple(qx, qy, qz, p3.x, p3.y, p3.z);
+    if (nn_better(d0, __float_as_int(p0.w), best, best_idx)) { best = d0; best_idx = __float_as_int(p0.w); }
+    if (nn_better(d1, __float_as_int(p1.w), best, best_idx)) { best = d1; best_idx = __float_as_int(p1.w); }
+    if (nn_better(d2, __float_as_int(p2.w), best, best_idx)) { best = d2; best_idx = __float_as_int(p2.w); }
+    if (nn_better(d3, __float_as_int(p3.w), best, best_idx)) { best = d3; best_idx = __float_as_int(p3.w); }
+  }
+  for (; j < g.n; j += 256) {
+    const float4 p = __ldg(g.pts + j);
+    const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    if (nn_better(d, __float_as_int(p.w), best, best_idx)) { best = d; best_idx = __float_as_int(p.w); }
+  }
+  nn_warp_merge(best, best_idx);
+  __syncthreads();  // s_b / s_i may still be read by the previous query's thread 0
+  if ((threadIdx.x & 31) == 0) { s_b[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = best_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < 8; ++w)
+      if (nn_better(s_b[w], s_i[w], best, best_idx)) { best = s_b[w]; best_idx = s_i[w]; }
+}
+
+// brute: one CTA per still-open query scans the whole target (exact, same metric and tie rule)
+__global__ void __launch_bounds__(256) k_nn_bruteforce(NnView g, const float4* __restrict__ queries, const int* __restrict__ pending, const unsigned int* __restrict__ n_pending,
+                                                       float* __restrict__ d2_out, int* __restrict__ idx_out) {
+  const int np = (int)*n_pending;
+  for (int w = blockIdx.x; w < np; w += gridDim.x) {
+    const int i = pending[w];
+    const float4 q = queries[i];
+    float best;
+    int best_idx;
+    nn_query_brute_block(g, q.x, q.y, q.z, best, best_idx);
+    if (threadIdx.x == 0) { d2_out[i] = best; idx_out[i] = best_idx == kNoIndex ? -1 : best_idx; }
   }
 }
 
@@ -206,17 +345,17 @@ __global__ void __launch_bounds__(256) k_fitness_partial(const float* __restrict
 struct NnGrid {
   VoxelSort sort;
   DevBuf<float4> pts, queries;
-  DevBuf<uint2> table;
+  DevBuf<uint4> table;
   DevBuf<float> d2;
-  DevBuf<int> idx, pending;
-  DevBuf<unsigned int> n_pending;
+  DevBuf<int> idx, pending, pending2;
+  DevBuf<unsigned int> n_pending;  // [0] after the near phase, [1] after the far phase
   DevBuf<float> T;
   uint32_t table_cap = 0;
   int n = 0;
   bool built = false;
 
   void release() {
-    sort.release(); pts.release(); queries.release(); table.release(); d2.release(); idx.release(); pending.release(); n_pending.release(); T.release();
+    sort.release(); pts.release(); queries.release(); table.release(); d2.release(); idx.release(); pending.release(); pending2.release(); n_pending.release(); T.release();
   }
   NnView view() const {
     NnView v;
@@ -224,25 +363,27 @@ struct NnGrid {
     v.table = table.p;
     v.table_mask = table_cap - 1;
     v.table_shift = 32 - (int)__builtin_ctz(table_cap);
-    v.cell_start = sort.vox_start.p;
     v.pts = pts.p;
     v.n = n;
     return v;
+  }
+  static uint32_t capacity_for(int n_points) {
+    uint32_t cap = 64;
+    while (cap < (uint32_t)(2 * n_points + 1)) cap <<= 1;
+    return cap;
   }
   cudaError_t build(cudaStream_t st, const float4* d_pts, int n_points) {
     cudaError_t e;
     n = n_points;
     if ((e = sort.run(st, d_pts, n, 1, kNnCell, kNnCell, kNnCell, false)) != cudaSuccess) return e;
     if ((e = pts.reserve(n > 0 ? n : 1)) != cudaSuccess) return e;
-    uint32_t cap = 64;
-    while (cap < (uint32_t)(2 * n + 1)) cap <<= 1;
-    table_cap = cap;
-    if ((e = table.reserve(cap)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(table.p, 0xFF, (size_t)cap * sizeof(uint2), st)) != cudaSuccess) return e;
+    table_cap = capacity_for(n);
+    if ((e = table.reserve(table_cap)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(table.p, 0xFF, (size_t)table_cap * sizeof(uint4), st)) != cudaSuccess) return e;
     if (n > 0) {
       launch_counter() += 2;
       k_nn_reorder<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, sort.vals_a.p, sort.vals_b.p, sort.meta.p, pts.p);
-      k_nn_insert<<<kNumSM * 2, 256, 0, st>>>(sort.meta.p, sort.vox_key.p, table.p, cap - 1, 32 - (int)__builtin_ctz(cap));
+      k_nn_insert<<<kNumSM * 2, 256, 0, st>>>(sort.meta.p, sort.vox_key.p, sort.vox_start.p, table.p, table_cap - 1, 32 - (int)__builtin_ctz(table_cap));
     }
     built = true;
     return cudaGetLastError();
@@ -250,18 +391,21 @@ struct NnGrid {
   // d2 / idx of every source point under T (nullptr = identity), on the stream
   cudaError_t search(cudaStream_t st, const float4* d_src, int n_src, const float* T_colmajor_host, float max_d2) {
     cudaError_t e;
-    if ((e = d2.reserve(n_src > 0 ? n_src : 1)) != cudaSuccess) return e;
-    if ((e = idx.reserve(n_src > 0 ? n_src : 1)) != cudaSuccess) return e;
-    if ((e = pending.reserve(n_src > 0 ? n_src : 1)) != cudaSuccess) return e;
-    if ((e = queries.reserve(n_src > 0 ? n_src : 1)) != cudaSuccess) return e;
-    if ((e = n_pending.reserve(1)) != cudaSuccess) return e;
+    const size_t m = n_src > 0 ? n_src : 1;
+    if ((e = d2.reserve(m)) != cudaSuccess) return e;
+    if ((e = idx.reserve(m)) != cudaSuccess) return e;
+    if ((e = pending.reserve(m)) != cudaSuccess) return e;
+    if ((e = pending2.reserve(m)) != cudaSuccess) return e;
+    if ((e = queries.reserve(m)) != cudaSuccess) return e;
+    if ((e = n_pending.reserve(2)) != cudaSuccess) return e;
     if ((e = T.reserve(16)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(n_pending.p, 0, 2 * sizeof(unsigned int), st)) != cudaSuccess) return e;
     if (T_colmajor_host && (e = cudaMemcpyAsync(T.p, T_colmajor_host, 64, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if (n_src > 0) {
-      launch_counter() += 2;
+      launch_counter() += 3;
       k_nn_search<<<(n_src + 255) / 256, 256, 0, st>>>(view(), d_src, n_src, T.p, T_colmajor_host ? 1 : 0, max_d2, d2.p, idx.p, queries.p, pending.p, n_pending.p);
-      k_nn_bruteforce<<<kNumSM * 2, 256, 0, st>>>(view(), queries.p, pending.p, n_pending.p, d2.p, idx.p);
+      k_nn_far<<<kNumSM * 4, 256, 0, st>>>(view(), queries.p, pending.p, n_pending.p, max_d2, d2.p, idx.p, pending2.p, n_pending.p + 1);
+      k_nn_bruteforce<<<kNumSM * 4, 256, 0, st>>>(view(), queries.p, pending2.p, n_pending.p + 1, d2.p, idx.p);
     }
     return cudaGetLastError();
   }

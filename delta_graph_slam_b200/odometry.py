@@ -97,10 +97,13 @@ class ScanMatchingOdometry:
 
     def downsample(self, cloud):
         if self.downsample_filter is None:
-            # pcl::PassThrough without a filter field: a copy of the input (a NEW cloud object)
+            # pcl::PassThrough without a filter field copies the input into a NEW cloud object.  The
+            # engine copies the cloud to its own device buffer on setInputSource, which gives the same
+            # isolation from the caller's buffer, so the host-side copy is elided (a new view object
+            # keeps the "keyframe is filtered" identity test of matching() working).
             if isinstance(cloud, DeviceCloud):
-                return DeviceCloud(cloud.ptr, cloud.n, cloud.owner)  # the engine copies on setInputSource
-            return np.array(cloud, dtype=np.float32, copy=True)
+                return DeviceCloud(cloud.ptr, cloud.n, cloud.owner)
+            return np.asarray(cloud, dtype=np.float32).view()
         self.downsample_filter.setInputCloud(cloud, is_dense=True)
         return self.downsample_filter.filter()
 

@@ -222,20 +222,31 @@ class Registration:
         self._ck(_lib.load().b200reg_get_profile(self._h, v.ctypes.data))
         return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage", "step_solve_mt", "step_trig", "step_tables"), v.tolist()))
 
+    def nn_stats(self):
+        v = np.zeros(3, np.int64)
+        self._ck(_lib.load().b200reg_get_nn_stats(self._h, v.ctypes.data))
+        return dict(queries=int(v[0]), far_pass=int(v[1]), brute_pass=int(v[2]))
+
     def stream(self):
         p = C.c_void_p()
         self._ck(_lib.load().b200reg_get_stream(self._h, C.byref(p)))
         return p.value
 
     # ---- pcl::VoxelGrid on the same device / stream
-    def voxelgrid_filter(self, cloud, leaf, min_points_per_voxel=0, is_dense=False):
+    def voxelgrid_filter(self, cloud, leaf, min_points_per_voxel=0, is_dense=False, out=None):
+        """pcl::Filter::filter(output).  With `out` (a caller-owned (M, 4) float32 array, M >= len(cloud);
+        page-locked memory is written by DMA without staging) the result is the view out[:n]."""
         c = _lib.as_cloud(cloud)
         leaf3 = (C.c_float * 3)(*((leaf,) * 3 if np.isscalar(leaf) else leaf))
-        out = np.empty((max(len(c), 1), 4), np.float32)
+        own = out is None
+        if own:
+            out = np.empty((max(len(c), 1), 4), np.float32)
+        elif out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
         n_out = C.c_size_t()
         self._ck(_lib.load().b200reg_voxelgrid_filter(self._h, c.ctypes.data if len(c) else None, len(c), 16, leaf3, min_points_per_voxel, int(is_dense), out.ctypes.data,
                                                       len(out), C.byref(n_out)))
-        return out[: n_out.value].copy()
+        return out[: n_out.value].copy() if own else out[: n_out.value]
 
     def voxelgrid_filter_device(self, cloud, leaf, out, min_points_per_voxel=0, is_dense=False):
         """Device-resident filter: `cloud` and `out` are DeviceClouds (out.n = capacity >= cloud.n)."""
@@ -302,6 +313,16 @@ class FastGICP(Registration):
     def setCorrespondenceRandomness(self, k):
         self._ck(_lib.load().b200reg_set_correspondence_randomness(self._h, int(k)))
 
+    def setOptions(self, regularization=_lib.REG_PLANE, lsq_optimizer=_lib.LSQ_LM, rotation_epsilon=2e-3):
+        """setRegularizationMethod / setLSQType / setRotationEpsilon of fast_gicp (never called by the reference)."""
+        self._ck(_lib.load().b200reg_set_gicp_options(self._h, int(regularization), int(lsq_optimizer), float(rotation_epsilon)))
+
+    def covariances(self, which, n):
+        """3x3 covariances of the source (which = 0) or target (1) cloud, (n, 3, 3) float64."""
+        out = np.zeros((max(n, 1), 9))
+        self._ck(_lib.load().b200reg_gicp_get_covariances(self._h, int(which), out.ctypes.data, n))
+        return out[:n].reshape(-1, 3, 3)
+
 
 class VoxelGrid:
     """pcl::VoxelGrid<PointXYZ> as the nodelets use it: setLeafSize + setInputCloud + filter
@@ -327,7 +348,7 @@ class VoxelGrid:
     def filter(self, out=None):
         if isinstance(self._input, DeviceCloud):
             return self._reg.voxelgrid_filter_device(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
-        return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense)
+        return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense, out=out)
 
     def last_layout(self, n_voxels, n_points):
         return self._reg.voxelgrid_last_layout(n_voxels, n_points)

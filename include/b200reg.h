@@ -98,6 +98,8 @@ int b200reg_set_transformation_epsilon(b200reg_handle* h, double eps);
 int b200reg_set_maximum_iterations(b200reg_handle* h, int n);
 int b200reg_set_max_correspondence_distance(b200reg_handle* h, double d);
 int b200reg_set_correspondence_randomness(b200reg_handle* h, int k);
+/* fast_gicp setters the reference never calls (RegularizationMethod, LSQ optimiser, rotation epsilon); upstream defaults PLANE / LM / 2e-3 */
+int b200reg_set_gicp_options(b200reg_handle* h, int regularization, int lsq_optimizer, double rotation_epsilon);
 
 /* pcl::Registration::setInputTarget / setInputSource
  * [REF apps/scan_matching_odometry_nodelet.cpp:180,185,254; include/hdl_graph_slam/loop_detector.hpp:124,138].
@@ -173,6 +175,9 @@ int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double*
  * mean[3], cov[9], icov[9] (row-major doubles), centroid[3] floats.  Any pointer may be NULL. */
 int b200reg_ndt_num_leaves(b200reg_handle* h, size_t* out);
 int b200reg_ndt_get_leaves(b200reg_handle* h, uint64_t* idx, int32_t* n, double* mean3, double* cov9, double* icov9, float* centroid3, int32_t* grid6);
+/* introspection of FAST_GICP's per-point covariances (parity tests): which = 0 source, 1 target;
+ * out9 receives n row-major 3x3 doubles in input order */
+int b200reg_gicp_get_covariances(b200reg_handle* h, int which, double* out9, size_t n_points);
 /* score / gradient / Hessian of the current source at pose p = [t, eulerXYZ] (one derivative pass) */
 int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score, double g[6], double H[36]);
 
@@ -185,6 +190,10 @@ int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long
 /* developer counters of the last align: SM cycles spent by CTA 0 in {point pass, block reduce, group
  * barrier, partial sum, optimiser step}, the number of passes, and the grid staging cycles */
 int b200reg_get_profile(b200reg_handle* h, long long* out7);
+
+/* developer counters of the last getFitnessScore / inlier-fraction search: {queries, queries the
+ * thread-per-query near phase left open (warp-per-query far phase), queries finished by the brute-force pass} */
+int b200reg_get_nn_stats(b200reg_handle* h, long long* out3);
 
 /* raw CUDA stream of the handle (cudaStream_t) so a host can time or order work against it */
 int b200reg_get_stream(b200reg_handle* h, void** out_stream);

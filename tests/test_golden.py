@@ -100,3 +100,22 @@ def test_engine_ndt_golden(name):
     L = ndt.ndt_leaves()
     assert np.array_equal(L["idx"], g["leaf_idx"]) and np.array_equal(L["n"], g["leaf_n"])
     assert np.allclose(L["mean"], g["leaf_mean"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,lsq", [("lm", 1), ("gn", 0)])
+def test_engine_gicp_golden(name, lsq):
+    import io
+    import delta_graph_slam_b200 as eng
+    g, n = load("gicp.npz"), load("ndt.npz")
+    reg = eng.select_registration_method(dict(registration_method="FAST_GICP", reg_transformation_epsilon=0.01, reg_maximum_iterations=64, reg_max_correspondence_distance=2.5,
+                                              reg_correspondence_randomness=20), out=io.StringIO())
+    reg.setOptions(lsq_optimizer=lsq)
+    reg.setInputTarget(n["tgt"])
+    reg.setInputSource(n["src"])
+    reg.align(g["guess"])
+    assert [int(reg.hasConverged()), reg.getFinalNumIteration()] == g[f"{name}_meta"].tolist()
+    assert close_T(reg.getFinalTransformation(), g[f"{name}_T"])
+    assert abs(reg.getFitnessScore() - g[f"{name}_fitness"][0]) <= 1e-5 * g[f"{name}_fitness"][0]
+    if lsq == 1:
+        assert np.allclose(reg.covariances(0, len(n["src"]))[::50], g["cov_src"], atol=1e-6)
