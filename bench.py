@@ -43,6 +43,10 @@ ODOM_PARAMS = dict(  # launch/delta_graph_slam.launch:50-69 (NDT_OMP instead of 
     registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64,
 )
 PREFILTER_PARAMS = dict(downsample_method="VOXELGRID", downsample_resolution=0.1)
+GICP_ODOM_PARAMS = dict(  # BASELINE configs[2]: FAST_GICP with the factory's code defaults [REF src/hdl_graph_slam/registrations.cpp:27-36]
+    keyframe_delta_trans=1.0, keyframe_delta_angle=1.0, keyframe_delta_time=10000.0, downsample_method="NONE",
+    registration_method="FAST_GICP", reg_transformation_epsilon=0.01, reg_maximum_iterations=64, reg_max_correspondence_distance=2.5, reg_correspondence_randomness=20,
+)
 LOOP_PARAMS = dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64)
 DEVNULL = open(os.devnull, "w")
 DBL_MAX = float(np.finfo(np.float64).max)
@@ -112,16 +116,21 @@ class OraclePrefilter:
         return self.oracle.voxelgrid(cloud, PREFILTER_PARAMS["downsample_resolution"], is_dense=False)["out"]
 
 
-def oracle_odometry(oracle, threads=0):
+def oracle_odometry(oracle, threads=0, params=None):
     from delta_graph_slam_b200.odometry import ScanMatchingOdometry
-    reg = oracle.Registration(oracle.NDT, resolution=ODOM_PARAMS["reg_resolution"], nn_search=oracle.DIRECT7, trans_eps=ODOM_PARAMS["reg_transformation_epsilon"],
-                              max_iter=ODOM_PARAMS["reg_maximum_iterations"], num_threads=threads)
-    return OraclePrefilter(oracle), ScanMatchingOdometry(ODOM_PARAMS, registration=reg, out=DEVNULL)
+    params = params or ODOM_PARAMS
+    if params["registration_method"] == "FAST_GICP":
+        reg = oracle.Registration(oracle.GICP, trans_eps=params["reg_transformation_epsilon"], max_iter=params["reg_maximum_iterations"],
+                                  max_corr_dist=params["reg_max_correspondence_distance"], k_corr=params["reg_correspondence_randomness"], num_threads=threads)
+    else:
+        reg = oracle.Registration(oracle.NDT, resolution=params["reg_resolution"], nn_search=oracle.DIRECT7, trans_eps=params["reg_transformation_epsilon"],
+                                  max_iter=params["reg_maximum_iterations"], num_threads=threads)
+    return OraclePrefilter(oracle), ScanMatchingOdometry(params, registration=reg, out=DEVNULL)
 
 
-def time_oracle_odometry(host_clouds, frames):
+def time_oracle_odometry(host_clouds, frames, params=None):
     from oracle import oracle_py as oracle
-    pre, odo = oracle_odometry(oracle)
+    pre, odo = oracle_odometry(oracle, params=params)
     t0 = time.perf_counter()
     run_sequence(pre, odo, host_clouds[:frames])
     dt = time.perf_counter() - t0
@@ -245,13 +254,18 @@ class Ctx:
         return sec, wall, stats
 
 
-def bench_odometry(ctx):
+def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, label="NDT", cpu_frames=None):
     import delta_graph_slam_b200 as eng
     from delta_graph_slam_b200 import synth
     torch, args, dev, rank, world = ctx.torch, ctx.args, ctx.dev, ctx.rank, ctx.world
+    odom_params = odom_params or ODOM_PARAMS
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    cpu_frames = args.cpu_frames if cpu_frames is None else cpu_frames
+    is_ndt = odom_params["registration_method"] == "NDT_OMP"
 
     # ---- synthetic sequence, generated on the device; a pinned host copy feeds the e2e leg
-    F = args.frames
+    F = frames or args.frames
     rays = synth.num_rays(synth.HDL64)
     d_raw = torch.empty((F, rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
     counts = []
@@ -269,7 +283,7 @@ def bench_odometry(ctx):
 
     def new_pipeline():
         pre = eng.Prefilter(PREFILTER_PARAMS, device=dev, out=DEVNULL)
-        odo = eng.ScanMatchingOdometry(ODOM_PARAMS, device=dev, out=DEVNULL)
+        odo = eng.ScanMatchingOdometry(odom_params, device=dev, out=DEVNULL)
         return pre, odo
 
     # ---- device-resident leg (value) + roofline of the align kernel
@@ -284,7 +298,11 @@ def bench_odometry(ctx):
             odo_d.matching(0.1 * k, filtered)
             if k > 0:
                 r = odo_d.registration.getResult()
-                alg_bytes += 16 * filtered.n * r["evaluations"] + 48 * r["hits"]
+                # NDT pass: 16 B per source point + 48 B per (point, voxel) hit.  GICP: a linearize pass reads the
+                # point, its covariance, the correspondence's point and covariance and writes the Mahalanobis
+                # matrix (16 + 48 + 16 + 48 + 48 B per correspondence); an error pass re-reads 16 + 16 + 48 B
+                # (GICP outer iteration) — approximated with hits = linearize correspondences
+                alg_bytes += (16 * filtered.n * r["evaluations"] + 48 * r["hits"]) if is_ndt else (16 * filtered.n * r["evaluations"] + 160 * r["hits"])
                 evals += r["evaluations"]
                 hits += r["hits"]
         return dict(alg_bytes=alg_bytes, evals=evals, hits=hits, keyframes=odo_d.num_keyframes)
@@ -292,17 +310,17 @@ def bench_odometry(ctx):
     sampler = ClockSampler(dev)
     with sampler:
         c0 = odo_d.registration.counters()
-        sec_d, wall_d, st_d = ctx.timed(step_device, odo_d.registration.stream(), args.steps, args.warmup)
+        sec_d, wall_d, st_d = ctx.timed(step_device, odo_d.registration.stream(), steps, warmup)
         c1 = odo_d.registration.counters()
     regs_per_step = F - 1
-    value = world * args.steps * regs_per_step / sec_d
+    value = world * steps * regs_per_step / sec_d
     n_al = c1["timed_aligns"]  # the counters also saw the warm-up steps: per-launch averages over everything the library timed
     align_ms = c1["align_kernel_ms"]
-    alg_bytes_per_launch = sum(s["alg_bytes"] for s in st_d) / (args.steps * regs_per_step)
+    alg_bytes_per_launch = sum(s["alg_bytes"] for s in st_d) / (steps * regs_per_step)
     avg_launch_ms = align_ms / max(n_al, 1)
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
     peak, peak_kind = load_peaks()
-    launches_timed = (c1["launches_total"] - c0["launches_total"]) * args.steps // (args.steps + args.warmup)
+    launches_timed = (c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)
 
     # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out
     pre_h, odo_h = new_pipeline()
@@ -319,8 +337,8 @@ def bench_odometry(ctx):
             h2d += cloud.nbytes + filtered.nbytes
             d2h += filtered.nbytes + 128
         return dict(h2d=h2d, d2h=d2h)
-    sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), args.steps, args.warmup)
-    e2e_value = world * args.steps * regs_per_step / sec_h
+    sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), steps, warmup)
+    e2e_value = world * steps * regs_per_step / sec_h
 
     # ---- parity of the two legs (same inputs -> same poses) and odometry sanity vs ground truth
     nchk = min(50, F)
@@ -335,29 +353,31 @@ def bench_odometry(ctx):
 
     # ---- CPU baseline (rank 0, N = 1): the oracle on the first frames of the same sequence
     cpu = None
-    if rank == 0 and world == 1 and args.cpu_frames > 1:
-        v, cores, dt = time_oracle_odometry(host_clouds, min(args.cpu_frames, F))
+    if rank == 0 and world == 1 and cpu_frames > 1:
+        v, cores, dt = time_oracle_odometry(host_clouds, min(cpu_frames, F), odom_params)
         cpu = {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
-               "sample": f"first {min(args.cpu_frames, F)} frames of the same sequence ({dt:.1f} s): oracle restatement of pcl::VoxelGrid 0.1 m + ndt_omp DIRECT7 keyframe odometry, OpenMP on all host cores"}
+               "sample": f"first {min(cpu_frames, F)} frames of the same sequence ({dt:.1f} s): oracle restatement of pcl::VoxelGrid 0.1 m + {'ndt_omp DIRECT7' if is_ndt else 'fast_gicp'} keyframe odometry, OpenMP on all host cores"}
 
     out = {
-        "metric": "scan registrations/sec (NDT keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec_d / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
-        "config": {"workload": "scan_matching_odometry: 1000 consecutive synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])",
-                   "frames_per_step": F, "points_per_scan": int(np.mean(counts)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64",
+        "metric": f"scan registrations/sec ({label} keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * sec_d / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums" if is_ndt else "f64 (f32 points and NN search)",
+        "data": "synthetic",
+        "config": {"workload": f"scan_matching_odometry: {F} consecutive synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + {label} keyframe odometry (BASELINE configs[{1 if is_ndt else 2}])",
+                   "frames_per_step": F, "points_per_scan": int(np.mean(counts)),
+                   "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64" if is_ndt else "FAST_GICP-equivalent k 20, max corr 2.5 m, eps 0.01, max_iter 64, LM, PLANE",
                    "l2": f"each step streams {F} distinct scans ({F * rays * 16 / 1e9:.1f} GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
                    "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
-        "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / args.steps,
-                "wall_ms_per_step": 1e3 * wall_h / args.steps},
+        "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
+                "wall_ms_per_step": 1e3 * wall_h / steps},
         "gpu_launches": int(launches_timed),
-        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms, "launches": int(n_al),
-                     "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / args.steps),
+                     "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / steps),
                      "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
-                   "wall_ms_per_step": 1e3 * wall_d / args.steps},
+                   "wall_ms_per_step": 1e3 * wall_d / steps},
     }
     del d_raw, h_raw
     torch.cuda.empty_cache()
@@ -506,6 +526,8 @@ def main():
     ap.add_argument("--loop-candidates", type=int, default=16)
     ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
+    ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
+    ap.add_argument("--gicp-frames", type=int, default=300, help="frames of the sequence the FAST_GICP leg runs per step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -517,9 +539,13 @@ def main():
         out = bench_loop(ctx, args.steps, args.warmup)
     else:
         out = bench_odometry(ctx)
+        keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "checks")
         if not args.no_loop:
             lb = bench_loop(ctx, max(1, min(args.steps, 2)), 3)
-            out["loop_batch"] = {k: lb[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "checks")}
+            out["loop_batch"] = {k: lb[k] for k in keys}
+        if not args.no_gicp:
+            gb = bench_odometry(ctx, GICP_ODOM_PARAMS, frames=min(args.frames, args.gicp_frames), steps=max(1, min(args.steps, 2)), warmup=3, label="FAST_GICP", cpu_frames=min(args.cpu_frames, 12))
+            out["gicp_odometry"] = {k: gb[k] for k in keys}
     if ctx.rank == 0:
         print(json.dumps(out))
     if ctx.dist is not None:

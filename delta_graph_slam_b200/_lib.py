@@ -28,7 +28,7 @@ EXPORTS = [
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
     "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_get_batch_timing",
-    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_get_nn_stats", "b200reg_get_stream",
+    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
 
 
@@ -118,6 +118,7 @@ def load():
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, C.POINTER(C.c_double), vp, vp]
     L.b200reg_get_profile.argtypes = [vp, vp]
     L.b200reg_get_nn_stats.argtypes = [vp, vp]
+    L.b200reg_set_sort_path.argtypes = [C.c_int]
     L.b200reg_set_timing.argtypes = [vp, C.c_int]
     L.b200reg_get_counters.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.b200reg_get_stream.argtypes = [vp, C.POINTER(vp)]

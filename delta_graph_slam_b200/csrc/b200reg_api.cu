@@ -15,6 +15,7 @@
 #include "loop_batch.cuh"
 #include "ndt_align.cuh"
 #include "nn_grid.cuh"
+#include "voxel_coop.cuh"
 #include "voxelgrid.cuh"
 
 using namespace b200;
@@ -256,11 +257,9 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
 cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const float4* pts, int n, double* covs) {
   if (n <= 0) return cudaSuccess;
   const int k = h->cfg.correspondence_randomness, reg = h->cfg.regularization;
-  const int blocks = (n + 127) / 128;
+  const int blocks = (n + 7) / 8;  // one warp per query, 8 warps per CTA
   launch_counter() += 1;
-  if (k <= 8) k_gicp_covariances<8><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
-  else if (k <= 24) k_gicp_covariances<24><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
-  else k_gicp_covariances<48><<<blocks, 128, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
+  k_gicp_covariances<<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
   return cudaGetLastError();
 }
 
@@ -269,7 +268,7 @@ int ensure_gicp_structures(b200reg_handle* h) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   int rc = ensure_nn_grid(h);
   if (rc) return rc;
-  if (h->cfg.correspondence_randomness > 48) { h->err = "reg_correspondence_randomness above 48 is not supported by the device k-NN"; return B200REG_E_INVALID; }
+  if (h->cfg.correspondence_randomness > 32) { h->err = "reg_correspondence_randomness above 32 is not supported by the device k-NN (one neighbour per warp lane)"; return B200REG_E_INVALID; }
   if (!h->cov_tgt_ok) {
     B200_CUDA_TRY(h->cov_tgt.reserve((size_t)h->n_tgt * 6));
     B200_CUDA_TRY(launch_gicp_covariances(h, h->nn, h->tgt.p, h->n_tgt, h->cov_tgt.p));
@@ -1034,6 +1033,12 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B200REG_OK;
+}
+
+int b200reg_set_sort_path(int path) {
+  if (path < 0 || path > 1) return B200REG_E_INVALID;
+  sort_path_override() = path;
   return B200REG_OK;
 }
 

@@ -22,104 +22,151 @@
 
 namespace b200 {
 
-// ---- k nearest neighbours -----------------------------------------------------------------------
-// fixed-size sorted list in registers: ascending (d2, index); slots >= count hold (+inf, kNoIndex)
-template <int KMAX>
-__device__ __forceinline__ void knn_offer(float (&bd)[KMAX], int (&bi)[KMAX], float d, int idx) {
-  float cd = d;
-  int ci = idx;
+// ---- k nearest neighbours ---------------------------------------------------------------------
+// One WARP per query.  The running k-best list (k <= 32) is held distributed over the lanes: lane l
+// owns the l-th smallest (d2, index) so far.  The lanes probe 32 cells of the current Chebyshev ring
+// at once (one 16-byte hash load each); the points of every non-empty cell are then taken 32 at a
+// time, one per lane, and merged into the list with a bitonic network (sort the 32 candidates,
+// min against the reversed list, re-sort: ~20 shuffle steps for 32 candidates).  Batches in which no
+// candidate beats the current k-th are skipped with one ballot.  Rings grow until nothing outside
+// the examined block can beat the k-th (or the block covers the lattice); a query still open after
+// kKnnMaxRing rings (an isolated point) restarts as a linear scan of the whole cloud.  Exact; ties
+// by lowest index, as the oracle's kd-tree.
+constexpr int kKnnMaxRing = 6;
+
+// one compare-exchange step of a bitonic network over the lanes: partner = lane ^ j; in an ascending
+// block the lower lane of the pair keeps the smaller entry.  (d, i) pairs are totally ordered.
+__device__ __forceinline__ void bitonic_cmpex(float& d, int& i, int lane, int j, bool up) {
+  const float od = __shfl_xor_sync(0xffffffffu, d, j);
+  const int oi = __shfl_xor_sync(0xffffffffu, i, j);
+  const bool keep_min = ((lane & j) == 0) == up;
+  const bool take = keep_min ? nn_better(od, oi, d, i) : nn_better(d, i, od, oi);
+  if (take) { d = od; i = oi; }
+}
+
+// ascending bitonic sort of one (d, i) per lane
+__device__ __forceinline__ void warp_sort32(float& d, int& i, int lane) {
 #pragma unroll
-  for (int s = 0; s < KMAX; ++s) {
-    const bool lt = cd < bd[s] || (cd == bd[s] && ci < bi[s]);
-    const float td = bd[s];
-    const int ti = bi[s];
-    bd[s] = lt ? cd : td;
-    bi[s] = lt ? ci : ti;
-    cd = lt ? td : cd;
-    ci = lt ? ti : ci;
+  for (int k = 2; k <= 32; k <<= 1) {
+    const bool up = (lane & k) == 0 || k == 32;
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) bitonic_cmpex(d, i, lane, j, up);
   }
 }
 
-template <int KMAX>
-__device__ __forceinline__ void knn_kth(const float (&bd)[KMAX], const int (&bi)[KMAX], int km1, float& worst, int& worst_idx) {
-  worst = 3.402823466e+38f;
-  worst_idx = kNoIndex;
+// merge 32 candidates (one per lane, +inf when absent) into the distributed sorted list
+__device__ __forceinline__ void knn_merge32(float& td, int& ti, float cd, int ci, int lane) {
+  warp_sort32(cd, ci, lane);
+  const float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
+  const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+  if (nn_better(rd, ri, td, ti)) { td = rd; ti = ri; }  // the 32 smallest of the 64, as a bitonic sequence
 #pragma unroll
-  for (int s = 0; s < KMAX; ++s)
-    if (s == km1) { worst = bd[s]; worst_idx = bi[s]; }
+  for (int j = 16; j > 0; j >>= 1) bitonic_cmpex(td, ti, lane, j, true);
 }
 
-// exact k-NN of (qx, qy, qz) on the grid: rings until the k-th best cannot be beaten from outside
-// the examined block, or the block covers the occupied lattice
-template <int KMAX>
-__device__ __forceinline__ void knn_query(const NnView& g, const GridParams& gp, float qx, float qy, float qz, int k, float (&bd)[KMAX], int (&bi)[KMAX]) {
-#pragma unroll
-  for (int s = 0; s < KMAX; ++s) { bd[s] = 3.402823466e+38f; bi[s] = kNoIndex; }
-  const NnQuery q = nn_make_query(gp, qx, qy, qz);
-  float worst = 3.402823466e+38f;
-  int worst_idx = kNoIndex;
-  for (int r = 0;; ++r) {
-    if (r >= 1 && nn_settled(gp, q, r, worst_idx == kNoIndex ? 3.402823466e+38f : worst, 3.402823466e+38f)) break;
-    const int z0 = max(q.cz - r, gp.min_b[2]), z1 = min(q.cz + r, gp.max_b[2]);
-    const int y0 = max(q.cy - r, gp.min_b[1]), y1 = min(q.cy + r, gp.max_b[1]);
-    for (int iz = z0; iz <= z1; ++iz) {
-      const bool zface = (iz == q.cz - r) || (iz == q.cz + r);
-      for (int iy = y0; iy <= y1; ++iy) {
-        const bool face = zface || (iy == q.cy - r) || (iy == q.cy + r);
-        const int xstep = face ? 1 : (r == 0 ? 1 : 2 * r);
-        for (int ix = q.cx - r; ix <= q.cx + r; ix += xstep) {
-          if (ix < gp.min_b[0] || ix > gp.max_b[0]) continue;
-          if (worst_idx != kNoIndex && nn_box_d2(gp, q, ix, iy, iz) > worst) continue;
-          const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
-          const uint2 run = nn_lookup(g, key);
-          for (uint32_t j = run.x; j < run.y; ++j) {
-            const float4 p = __ldg(g.pts + j);
-            const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-            const int idx = __float_as_int(p.w);
-            if (worst_idx == kNoIndex || nn_better(d, idx, worst, worst_idx)) {
-              knn_offer<KMAX>(bd, bi, d, idx);
-              knn_kth<KMAX>(bd, bi, k - 1, worst, worst_idx);
-            }
-          }
-        }
-      }
+// offer the points [s, e) of the cell-ordered array to the list
+__device__ __forceinline__ void knn_offer_run(const NnView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, int km1, int lane, float& td, int& ti) {
+  for (uint32_t j0 = s; j0 < e; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    float cd = 3.402823466e+38f;
+    int ci = kNoIndex;
+    if (j < e) {
+      const float4 p = __ldg(g.pts + j);
+      cd = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+      ci = __float_as_int(p.w);
     }
+    const float kd = __shfl_sync(0xffffffffu, td, km1);
+    const int ki = __shfl_sync(0xffffffffu, ti, km1);
+    if (__ballot_sync(0xffffffffu, nn_better(cd, ci, kd, ki)) == 0u) continue;
+    knn_merge32(td, ti, cd, ci, lane);
   }
 }
 
 // calculate_covariances (A.5).  covs[i] = {xx, xy, xz, yy, yz, zz} of the regularised covariance.
-template <int KMAX>
-__global__ void __launch_bounds__(128) k_gicp_covariances(NnView g, const float4* __restrict__ pts, int n, int k, int reg_method, double* __restrict__ covs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4* __restrict__ pts, int n, int k, int reg_method, double* __restrict__ covs) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // queries are taken in cell order: neighbouring warps touch neighbouring cells
+  if (w >= n) return;
   const GridParams gp = g.meta->grid;
-  const float4 p = __ldg(pts + i);
-  float bd[KMAX];
-  int bi[KMAX];
-  knn_query<KMAX>(g, gp, p.x, p.y, p.z, k, bd, bi);
+  const float4 qp = __ldg(g.pts + w);
+  const int qi = __float_as_int(qp.w);
+  const float qx = qp.x, qy = qp.y, qz = qp.z;
+  const NnQuery q = nn_make_query(gp, qx, qy, qz);
+  const int km1 = k - 1;
+  float td = 3.402823466e+38f;
+  int ti = kNoIndex;
+  bool open = true;
+  for (int r = 0; r <= kKnnMaxRing && open; ++r) {
+    const float kd = __shfl_sync(0xffffffffu, td, km1);
+    const int ki = __shfl_sync(0xffffffffu, ti, km1);
+    if (r >= 1 && nn_settled(gp, q, r, ki == kNoIndex ? 3.402823466e+38f : kd, 3.402823466e+38f)) { open = false; break; }
+    const int side = 2 * r + 1, inner = 2 * r - 1;
+    const int nz = r == 0 ? 1 : 2 * side * side, ny = r == 0 ? 0 : 2 * side * inner, total = r == 0 ? 1 : nz + ny + 2 * inner * inner;
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      uint2 run = make_uint2(0u, 0u);
+      if (c < total) {
+        int dx = 0, dy = 0, dz = 0;
+        if (r > 0) {
+          if (c < nz) {
+            const int f = c / (side * side), rem = c - f * side * side;
+            dz = f ? r : -r; dx = rem % side - r; dy = rem / side - r;
+          } else if (c < nz + ny) {
+            const int cc = c - nz, f = cc / (side * inner), rem = cc - f * side * inner;
+            dy = f ? r : -r; dx = rem % side - r; dz = rem / side - (r - 1);
+          } else {
+            const int cc = c - nz - ny, f = cc / (inner * inner), rem = cc - f * inner * inner;
+            dx = f ? r : -r; dy = rem % inner - (r - 1); dz = rem / inner - (r - 1);
+          }
+        }
+        const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
+        const bool in = ix >= gp.min_b[0] && ix <= gp.max_b[0] && iy >= gp.min_b[1] && iy <= gp.max_b[1] && iz >= gp.min_b[2] && iz <= gp.max_b[2];
+        if (in && (ki == kNoIndex || nn_box_d2(gp, q, ix, iy, iz) <= kd)) {
+          const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+          run = nn_lookup(g, key);
+        }
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, run.y > run.x);
+      while (mask) {
+        const int L = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t s = __shfl_sync(0xffffffffu, run.x, L), e = __shfl_sync(0xffffffffu, run.y, L);
+        knn_offer_run(g, s, e, qx, qy, qz, km1, lane, td, ti);
+      }
+    }
+  }
+  if (open) {
+    const float kd = __shfl_sync(0xffffffffu, td, km1);
+    const int ki = __shfl_sync(0xffffffffu, ti, km1);
+    if (!nn_settled(gp, q, kKnnMaxRing + 1, ki == kNoIndex ? 3.402823466e+38f : kd, 3.402823466e+38f)) {
+      td = 3.402823466e+38f;  // an isolated point: start over as a linear scan of the whole cloud
+      ti = kNoIndex;
+      knn_offer_run(g, 0u, (uint32_t)g.n, qx, qy, qz, km1, lane, td, ti);
+    }
+  }
   // neighbours as columns, minus the row-wise mean over the k REQUESTED columns, cov = N N^T / k
-  double mean[3] = {0, 0, 0};
-#pragma unroll
-  for (int s = 0; s < KMAX; ++s)
-    if (s < k && bi[s] != kNoIndex) {
-      const float4 q = __ldg(pts + bi[s]);
-      mean[0] += (double)q.x; mean[1] += (double)q.y; mean[2] += (double)q.z;
-    }
+  const bool have = lane < k && ti != kNoIndex;
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (have) nb = __ldg(pts + ti);
   const double kd = (double)k;
-  mean[0] /= kd; mean[1] /= kd; mean[2] /= kd;
-  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double m0 = have ? (double)nb.x : 0.0, m1 = have ? (double)nb.y : 0.0, m2 = have ? (double)nb.z : 0.0;
 #pragma unroll
-  for (int s = 0; s < KMAX; ++s)
-    if (s < k && bi[s] != kNoIndex) {
-      const float4 q = __ldg(pts + bi[s]);
-      const double v[3] = {(double)q.x - mean[0], (double)q.y - mean[1], (double)q.z - mean[2]};
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  }
+  m0 /= kd; m1 /= kd; m2 /= kd;
+  const double v0 = have ? (double)nb.x - m0 : 0.0, v1 = have ? (double)nb.y - m1 : 0.0, v2 = have ? (double)nb.z - m2 : 0.0;
+  double c6[6] = {v0 * v0, v0 * v1, v0 * v2, v1 * v1, v1 * v2, v2 * v2};
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 6; ++a) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) c[3 * a + b] += v[a] * v[b];
-    }
-#pragma unroll
-  for (int a = 0; a < 9; ++a) c[a] /= kd;
+    for (int o = 16; o > 0; o >>= 1) c6[a] += __shfl_xor_sync(0xffffffffu, c6[a], o);
+    c6[a] /= kd;
+  }
+  if (lane != 0) return;
+  const double c[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
   double out[9];
   if (reg_method == B200REG_REG_NONE) {
 #pragma unroll
@@ -161,7 +208,7 @@ __global__ void __launch_bounds__(128) k_gicp_covariances(NnView g, const float4
         for (int b = 0; b < 3; ++b) out[3 * a + b] += values[s] * V[3 * a + col] * V[3 * b + col];
     }
   }
-  double* o = covs + (size_t)i * 6;
+  double* o = covs + (size_t)qi * 6;
   o[0] = out[0]; o[1] = out[1]; o[2] = out[2]; o[3] = out[4]; o[4] = out[5]; o[5] = out[8];
 }
 

@@ -361,15 +361,25 @@ static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restr
 }
 
 // ---- host driver -------------------------------------------------------------
+struct VoxelSort;
+// voxel_coop.cuh: the whole pipeline as one cooperative kernel; false = cloud too large, take the multi-kernel path
+bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err);
+// 0 = cooperative single kernel when the cloud fits (default), 1 = always the multi-kernel path (A/B tests)
+inline int& sort_path_override() {
+  static int v = 0;
+  return v;
+}
+
 struct VoxelSort {
   DevBuf<uint32_t> keys_a, keys_b, vals_a, vals_b, hist, tile_heads, tile_valid, vox_start, vox_key, point_key;
   DevBuf<int> mm;
+  DevBuf<unsigned int> coop_bar;
   DevBuf<SortMeta> meta;
   int n = 0;
 
   void release() {
     keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); hist.release(); tile_heads.release(); tile_valid.release();
-    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release();
+    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release(); coop_bar.release();
   }
 
   // enqueue: keys -> sort -> segmentation.  Afterwards (on the stream):
@@ -387,6 +397,10 @@ struct VoxelSort {
     if ((e = mm.reserve(8)) != cudaSuccess) return e;
     if ((e = meta.reserve(1)) != cudaSuccess) return e;
     if (keep_point_keys && (e = point_key.reserve(nn)) != cudaSuccess) return e;
+    if (sort_path_override() == 0) {
+      cudaError_t ce = cudaSuccess;
+      if (launch_voxel_sort_coop(*this, st, d_pts, n, is_dense, lx, ly, lz, keep_point_keys, &ce)) return ce;
+    }
     int items = 4;
     while (items < 32 && (n + kSortThreads * items - 1) / (kSortThreads * items) > 256) items *= 2;
     const int tile = kSortThreads * items;

@@ -191,6 +191,10 @@ int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long
  * barrier, partial sum, optimiser step}, the number of passes, and the grid staging cycles */
 int b200reg_get_profile(b200reg_handle* h, long long* out7);
 
+/* A/B switch for tests (process-wide): 0 = the voxel key / sort / segmentation pipeline runs as one
+ * cooperative kernel when the cloud fits one tile per SM (default), 1 = always the multi-kernel path */
+int b200reg_set_sort_path(int path);
+
 /* developer counters of the last getFitnessScore / inlier-fraction search: {queries, queries the
  * thread-per-query near phase left open (warp-per-query far phase), queries finished by the brute-force pass} */
 int b200reg_get_nn_stats(b200reg_handle* h, long long* out3);

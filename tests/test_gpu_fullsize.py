@@ -1,0 +1,109 @@
+"""GPU tests at BASELINE.json's full sizes (configs[0] HDL-64 ~1.3e5 points, configs[4] 128-beam
+~1e6 points): the oracle still finishes in seconds at these sizes, so parity is checked directly,
+plus the size-independent properties of the domain (counts add up, output sorted by voxel index,
+centroids stay in their voxel, filtering is idempotent on voxel occupancy)."""
+import io
+
+import numpy as np
+import pytest
+
+from helpers import OracleBatchEngine, rot_angle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import delta_graph_slam_b200 as d
+    return d
+
+
+@pytest.fixture(scope="module")
+def dense(oracle):
+    P0, P1 = oracle.synth_traj(0), oracle.synth_traj(1)
+    s0 = oracle.synth_scan(P0, sensor=oracle.DENSE128, noise_seed=5000)
+    s1 = oracle.synth_scan(P1, sensor=oracle.DENSE128, noise_seed=5001)
+    return dict(raw0=s0, raw1=s1, gt=np.linalg.inv(P0) @ P1)
+
+
+def test_dense_voxelgrid_full_size(eng, oracle, dense):
+    raw = dense["raw0"]
+    assert len(raw) > 700_000
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    vg.setInputCloud(raw, is_dense=False)
+    out = vg.filter()
+    lay = vg.last_layout(len(out), len(raw))
+    # properties
+    assert int(lay["count"].sum()) == len(raw)
+    assert np.all(np.diff(lay["voxel_id"].astype(np.int64)) > 0)
+    inv = np.float32(1.0) / np.float32(0.1)
+    ijk = np.floor(out[:, :3] * inv).astype(np.int64) - lay["min_b"].astype(np.int64)
+    key = ijk[:, 0] + ijk[:, 1] * int(lay["div_b"][0]) + ijk[:, 2] * int(lay["div_b"][0]) * int(lay["div_b"][1])
+    inside = key == lay["voxel_id"].astype(np.int64)
+    assert inside.mean() > 0.999, "centroids lie in their own voxel (up to float rounding on a voxel face)"
+    vg.setInputCloud(out, is_dense=True)
+    again = vg.filter()
+    assert abs(len(again) - len(out)) <= (~inside).sum() + 2
+    # parity, bit for bit
+    ref = oracle.voxelgrid(raw, 0.1, is_dense=False)
+    assert np.array_equal(lay["key"], ref["key"]) and np.array_equal(lay["count"], ref["count"]) and np.array_equal(lay["voxel_id"], ref["voxel_id"])
+    assert np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+
+
+@pytest.mark.parametrize("search", ["DIRECT1", "DIRECT7"])
+def test_dense_ndt_full_size(eng, oracle, dense, search):
+    """configs[4]: 1M-point scans, VoxelGrid 0.1 -> NDT.  The target grid (~5k voxels) no longer fits
+    the shared-memory stage: the L2 path of the align kernel is the one under test."""
+    ds0 = oracle.voxelgrid(dense["raw0"], 0.1)["out"]
+    ds1 = oracle.voxelgrid(dense["raw1"], 0.1)["out"]
+    assert len(ds0) > 100_000
+    code = dict(DIRECT7=2, DIRECT1=3)[search]
+    ref = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=code, trans_eps=0.01, max_iter=64)
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method=search), out=io.StringIO())
+    for r in (ref, ndt):
+        r.setInputTarget(ds0)
+        r.setInputSource(ds1)
+        r.align(None)
+    T0, T1 = ref.getFinalTransformation(), ndt.getFinalTransformation()
+    assert ndt.getFinalNumIteration() == ref.getFinalNumIteration()
+    assert np.max(np.abs(T1[:3, 3] - T0[:3, 3])) < 1e-4 and rot_angle(T0[:3, :3], T1[:3, :3]) < 1e-4
+    f0, f1 = ref.getFitnessScore(), ndt.getFitnessScore()
+    assert abs(f1 - f0) <= 1e-5 * f0
+    gt = dense["gt"]
+    assert np.max(np.abs(T1[:3, 3] - gt[:3, 3])) < 0.03
+    L0, L1 = ref.ndt_leaves(), ndt.ndt_leaves()
+    assert np.array_equal(L0["idx"], L1["idx"]) and np.array_equal(L0["n"], L1["n"])
+    assert (L0["n"] >= 6).sum() > 3000
+
+
+def test_dense_loop_batch(eng, oracle, dense):
+    ds0 = oracle.voxelgrid(dense["raw0"], 0.1)["out"]
+    ds1 = oracle.voxelgrid(dense["raw1"], 0.1)["out"]
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT1"), out=io.StringIO())
+    ref = OracleBatchEngine(oracle, nn_search=3)
+    for e in (ndt, ref):
+        e.cloudPut(0, ds0)
+        e.cloudPut(1, ds1)
+    g = np.eye(4, dtype=np.float32)
+    g[0, 3] = 0.3
+    pairs = [(0, 1, g), (1, 0, np.linalg.inv(g).astype(np.float32)), (0, 1, None)]
+    a, b = ref.alignBatch(pairs), ndt.alignBatch(pairs)
+    for x, y in zip(a, b):
+        Tx, Ty = np.array(x["transformation"]).reshape(4, 4).T, np.array(y["transformation"]).reshape(4, 4).T
+        assert x["iterations"] == y["iterations"]
+        assert np.max(np.abs(Tx[:3, 3] - Ty[:3, 3])) < 1e-4 and rot_angle(Tx[:3, :3], Ty[:3, :3]) < 1e-4
+        assert abs(x["fitness"] - y["fitness"]) <= 1e-5 * x["fitness"]
+
+
+def test_hdl64_gicp_full_size(eng, oracle, scans):
+    """configs[2] at full HDL-64 size: one FAST_GICP registration, engine vs oracle."""
+    ref = oracle.Registration(oracle.GICP, trans_eps=0.01, max_iter=64, max_corr_dist=2.5, k_corr=20)
+    g = eng.select_registration_method(dict(registration_method="FAST_GICP"), out=io.StringIO())
+    for r in (ref, g):
+        r.setInputTarget(scans["ds0"])
+        r.setInputSource(scans["ds1"])
+        r.align(None)
+    T0, T1 = ref.getFinalTransformation(), g.getFinalTransformation()
+    assert g.getFinalNumIteration() == ref.getFinalNumIteration()
+    assert np.max(np.abs(T1[:3, 3] - T0[:3, 3])) < 1e-4 and rot_angle(T0[:3, :3], T1[:3, :3]) < 1e-4

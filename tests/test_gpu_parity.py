@@ -213,3 +213,42 @@ def test_odometry_keyframe_promotion(eng, oracle, scans):
     La, Lb = a.ndt_leaves(), b.ndt_leaves()
     assert np.array_equal(La["idx"], Lb["idx"]) and np.array_equal(La["n"], Lb["n"])
     assert np.array_equal(La["icov"], Lb["icov"])
+
+
+def test_cooperative_and_multi_kernel_sort_paths_agree(eng, oracle, scans):
+    """The voxel key / sort / segmentation pipeline as ONE cooperative kernel (default) against the
+    multi-kernel path: identical keys, order, runs, centroids and NDT leaves, bit for bit."""
+    from delta_graph_slam_b200 import _lib
+    L = _lib.load()
+    outs = []
+    try:
+        for path in (0, 1):
+            assert L.b200reg_set_sort_path(path) == 0
+            vg = eng.VoxelGrid()
+            vg.setLeafSize(0.1, 0.1, 0.1)
+            raw = scans["raw0"].copy()
+            raw[::17, 0] = np.nan
+            vg.setInputCloud(raw, is_dense=False)
+            out = vg.filter()
+            lay = vg.last_layout(len(out), len(raw))
+            ndt = eng.NormalDistributionsTransform()
+            ndt.setResolution(1.0)
+            ndt.setInputTarget(scans["ds0"])
+            G = ndt.ndt_leaves()
+            small = eng.VoxelGrid()
+            small.setLeafSize(0.5, 0.5, 0.5)
+            small.setInputCloud(scans["ds1"][:777], is_dense=True)
+            outs.append((out, lay, G, small.filter()))
+    finally:
+        L.b200reg_set_sort_path(0)
+    (o0, l0, g0, s0), (o1, l1, g1, s1) = outs
+    assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+    for k in ("voxel_id", "count", "key", "min_b", "div_b"):
+        assert np.array_equal(l0[k], l1[k]), k
+    for k in ("idx", "n", "mean", "cov", "icov"):
+        assert np.array_equal(g0[k], g1[k]), k
+    ref = oracle.voxelgrid(scans["raw0"], 0.1, is_dense=False)
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    vg.setInputCloud(scans["raw0"], is_dense=False)
+    assert np.array_equal(vg.filter().view(np.uint32), ref["out"].view(np.uint32))
