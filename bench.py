@@ -154,7 +154,7 @@ def oracle_loop_pairs(oracle, clouds, pairs):
     return time.perf_counter() - t0
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, emit=print):
     """--impl reference: the reference's CPU implementation of the path (oracle restatement, OpenMP on
     all host cores) on a bounded sample of the same workload.  Rank 0 only."""
     if rank != 0:
@@ -193,7 +193,7 @@ def reference_arm(args, rank):
         sample = f"first {n} frames of the sequence per step (VoxelGrid 0.1 + NDT DIRECT7 keyframe odometry), oracle restatement of pcl::VoxelGrid + ndt_omp"
         cfg = {"workload": "scan_matching_odometry: synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])", "frames_per_step": n,
                "registration": "NDT_OMP DIRECT7 res 1.0 eps 0.01 max_iter 64"}
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak" if args.workload == "odometry" else "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
@@ -531,8 +531,16 @@ def main():
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner,
+    # OpenMP notices) is sent to stderr instead, and the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (line + "\n").encode())
     if args.impl == "reference":
-        return reference_arm(args, rank)
+        return reference_arm(args, rank, emit)
 
     ctx = Ctx(args)
     if args.workload == "loop":
@@ -547,7 +555,7 @@ def main():
             gb = bench_odometry(ctx, GICP_ODOM_PARAMS, frames=min(args.frames, args.gicp_frames), steps=max(1, min(args.steps, 2)), warmup=3, label="FAST_GICP", cpu_frames=min(args.cpu_frames, 12))
             out["gicp_odometry"] = {k: gb[k] for k in keys}
     if ctx.rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if ctx.dist is not None:
         ctx.dist.destroy_process_group()
     return 0

@@ -1,8 +1,11 @@
 // b200reg — C ABI implementation (include/b200reg.h).  Host side is plain C++; the device work is
 // the hand-written sm_100a kernels in the .cuh files next to this one.  There is no CPU
 // fallback anywhere: a missing device or a CUDA error surfaces as B200REG_E_CUDA.
+#include <immintrin.h>
 #include <math.h>
 #include <string.h>
+
+#include <atomic>
 
 #include <new>
 #include <string>
@@ -20,6 +23,15 @@
 
 using namespace b200;
 
+// page-locked host memory mapped into the device address space: results of single calls land here
+// and the host polls the sequence flags instead of copying + synchronising the stream
+struct HostMailbox {
+  b200reg_result result;
+  VgCounts vg;
+  volatile unsigned int align_seq;
+  volatile unsigned int vg_seq;
+};
+
 struct b200reg_handle {
   b200reg_config cfg;
   cudaStream_t stream = nullptr;
@@ -36,6 +48,7 @@ struct b200reg_handle {
   VoxelSort vg_sort;
   DevBuf<uint32_t> vg_id, vg_count;
   DevBuf<VgCounts> vg_counts;
+  DevBuf<unsigned int> vg_done;
   int vg_last_n = 0, vg_last_out = 0;
 
   // NDT
@@ -72,12 +85,21 @@ struct b200reg_handle {
   double batch_align_ms = 0.0;  // last batch: duration of the align kernel (timing on)
   double batch_fitness_ms = 0.0;
 
+  HostMailbox* mail = nullptr;  // cudaHostAllocMapped
+  unsigned int align_seq = 0, vg_seq = 0, launch_tag = 0;
+  size_t barriers_zeroed = 0;   // entries of `barriers` known to be zero (kernels restore them on exit)
+
   b200reg_result last;
   bool have_result = false;
 
-  // optional device timing of the align kernel (bench.py roofline leg)
+  // optional device timing of the align kernel (bench.py roofline leg): CUDA events around every
+  // launch, resolved lazily (when a pair is reused or the counters are read) so that timing never
+  // puts an event synchronisation on the critical path of a call
   bool timing = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // aliases of the pair of the launch in flight
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_pending;
+  int ev_next = 0;
   double align_ms = 0.0;
   long long n_align = 0;
 
@@ -181,8 +203,115 @@ int ensure_nn_grid(b200reg_handle* h) {
   return B200REG_OK;
 }
 
+// Kernel attributes, once per device: the align kernels opt in to 192 KB of dynamic shared memory
+// (the staged target grid), and EVERY kernel of the library asks for the maximum shared-memory
+// carve-out, so that consecutive kernels of a frame never make the SMs re-partition L1 / shared
+// memory between launches.
+template <typename F>
+cudaError_t prefer_shared(F* fn) { return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+
+cudaError_t init_kernel_attributes(int device) {
+  static std::atomic<unsigned long long> done{0};
+  if (device < 64 && (done.load() >> device) & 1ull) return cudaSuccess;
+  cudaError_t e;
+#define B200_ATTR(expr) if ((e = (expr)) != cudaSuccess) return e
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(prefer_shared(k_ndt_align<1>)); B200_ATTR(prefer_shared(k_ndt_align<7>)); B200_ATTR(prefer_shared(k_ndt_align<27>)); B200_ATTR(prefer_shared(k_ndt_align<0>));
+  B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
+  B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
+  B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
+  B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
+  B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
+  B200_ATTR(prefer_shared(k_gicp_covariances)); B200_ATTR(prefer_shared(k_gicp_align));
+  B200_ATTR(ndt_leaf_prefer_shared());
+#undef B200_ATTR
+  if (device < 64) done.fetch_or(1ull << device);
+  return cudaSuccess;
+}
+
+// ---- lazy event timing ---------------------------------------------------------------------------
+int drain_events(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  for (int idx : h->ev_pending) {
+    B200_CUDA_TRY(cudaEventSynchronize(h->ev_pool[idx].second));
+    float ms = 0.f;
+    B200_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_pool[idx].first, h->ev_pool[idx].second));
+    h->align_ms += (double)ms;
+    h->n_align += 1;
+  }
+  h->ev_pending.clear();
+  return B200REG_OK;
+}
+
+// next event pair for a launch (timing on); its elapsed time is added to the counters later
+int begin_timed_launch(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h->timing) return B200REG_OK;
+  if (h->ev_pool.empty()) {
+    h->ev_pool.resize(64);
+    for (auto& pr : h->ev_pool) {
+      B200_CUDA_TRY(cudaEventCreate(&pr.first));
+      B200_CUDA_TRY(cudaEventCreate(&pr.second));
+    }
+  }
+  if (h->ev_pending.size() >= h->ev_pool.size()) {
+    int rc = drain_events(h);
+    if (rc) return rc;
+  }
+  const int idx = h->ev_next;
+  h->ev_next = (h->ev_next + 1) % (int)h->ev_pool.size();
+  h->ev0 = h->ev_pool[idx].first;
+  h->ev1 = h->ev_pool[idx].second;
+  h->ev_pending.push_back(idx);
+  B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  return B200REG_OK;
+}
+int end_timed_launch(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  return B200REG_OK;
+}
+
+// barrier lines / job counters: zero when (re)allocated, afterwards every kernel restores them on exit
+int ensure_barriers(b200reg_handle* h, size_t entries) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  const unsigned int* before = h->barriers.p;
+  B200_CUDA_TRY(h->barriers.reserve(entries));
+  if (h->barriers.p != before || h->barriers_zeroed < entries) {
+    B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, h->barriers.cap * sizeof(unsigned int), h->stream));
+    h->barriers_zeroed = h->barriers.cap;
+  }
+  return B200REG_OK;
+}
+
+// wait for the kernel of a single call to publish its result in the mailbox
+int wait_mail(b200reg_handle* h, volatile unsigned int* flag, unsigned int want) {
+  unsigned long long spins = 0;
+  while (*flag != want) {
+    _mm_pause();
+    if ((++spins & 0x3FFFull) == 0) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) {
+        h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+        return B200REG_E_CUDA;
+      }
+      if (*flag != want) {  // stream drained without the flag: should not happen
+        h->err = "kernel finished without publishing its result";
+        return B200REG_E_CUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return B200REG_OK;
+}
+
 template <int MODE>
-cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups) {
+cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups, const NdtJob* single) {
   NdtParams prm;
   prm.search = h->cfg.nn_search;
   prm.resolution = h->cfg.resolution;
@@ -190,23 +319,23 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   prm.outlier_ratio = h->cfg.outlier_ratio;
   prm.trans_eps = h->cfg.transformation_epsilon;
   prm.max_iterations = h->cfg.maximum_iterations;
-  const NdtJob* jobs = h->jobs.p;
+  static const NdtJob kNoJob = {};
+  const NdtJob* jobs = single ? nullptr : h->jobs.p;  // one registration: the job rides in the kernel parameters
+  const NdtJob& sj = single ? *single : kNoJob;
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
   unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
-  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue};
-  // the staged target grid lives in opt-in dynamic shared memory (one CTA per SM)
-  cudaError_t e = cudaFuncSetAttribute((const void*)k_ndt_align<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
-  if (e != cudaSuccess) return e;
+  unsigned int launch_tag = ++h->launch_tag;  // tags the partial rows of this launch (stale rows of earlier launches never match)
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&launch_tag, (void*)&sj};
   return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 
-cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups) {
+cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr) {
   switch (h->cfg.nn_search) {
-    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups);
-    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups);
-    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups);
-    default: return launch_ndt<7>(h, n_jobs, G, n_groups);
+    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups, single);
+    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups, single);
+    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups, single);
+    default: return launch_ndt<7>(h, n_jobs, G, n_groups, single);
   }
 }
 
@@ -216,19 +345,21 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   int rc = ensure_ndt_grid(h);
   if (rc) return rc;
   const int G = h->num_sm;
-  B200_CUDA_TRY(h->jobs.reserve(1));
   B200_CUDA_TRY(h->d_result.reserve(1));
   B200_CUDA_TRY(h->deriv.reserve(64));
   B200_CUDA_TRY(h->prof.reserve(16));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kAccStride));
-  B200_CUDA_TRY(h->barriers.reserve(64));
-  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
-  NdtJob* job = reinterpret_cast<NdtJob*>(h->pin_small.p);
+  if ((rc = ensure_barriers(h, 64))) return rc;
+  NdtJob jobv;
+  NdtJob* job = &jobv;
   memset(job, 0, sizeof(NdtJob));
   job->src = h->src.p;
   job->n_src = h->n_src;
   job->grid = h->grid.view();
   job->result = h->d_result.p;
+  job->result_host = &h->mail->result;
+  job->done_flag = const_cast<unsigned int*>(&h->mail->align_seq);
+  job->done_seq = ++h->align_seq;
   job->deriv_out = h->deriv.p;
   job->prof = h->prof.p;
   if (p_eval) {
@@ -244,12 +375,10 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
     job->p0[0] = g[12]; job->p0[1] = g[13]; job->p0[2] = g[14];
     job->p0[3] = eul[0]; job->p0[4] = eul[1]; job->p0[5] = eul[2];
   }
-  B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, job, sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
-  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 64 * sizeof(unsigned int), h->stream));
-  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1));
+  if ((rc = begin_timed_launch(h))) return rc;
+  B200_CUDA_TRY(launch_ndt_mode(h, 1, G, 1, job));
   launch_counter() += 1;
-  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  if ((rc = end_timed_launch(h))) return rc;
   return B200REG_OK;
 }
 
@@ -292,15 +421,17 @@ int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
   if (rc) return rc;
   const int G = h->num_sm;
   const size_t ns = (size_t)(h->n_src > 0 ? h->n_src : 1);
-  B200_CUDA_TRY(h->gicp_jobs.reserve(1));
   B200_CUDA_TRY(h->d_result.reserve(1));
   B200_CUDA_TRY(h->gicp_corr.reserve(ns));
   B200_CUDA_TRY(h->gicp_mahal.reserve(ns * 6));
   B200_CUDA_TRY(h->partials.reserve((size_t)2 * G * kGicpStride));
-  B200_CUDA_TRY(h->barriers.reserve(64));
-  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
-  GicpJob* job = reinterpret_cast<GicpJob*>(h->pin_small.p + sizeof(NdtJob) + sizeof(b200reg_result) + 64 * sizeof(double));
+  if ((rc = ensure_barriers(h, 64))) return rc;
+  GicpJob jobv;
+  GicpJob* job = &jobv;
   memset(job, 0, sizeof(GicpJob));
+  job->result_host = &h->mail->result;
+  job->done_flag = const_cast<unsigned int*>(&h->mail->align_seq);
+  job->done_seq = ++h->align_seq;
   job->src = h->src.p;
   job->n_src = h->n_src;
   job->cov_src = h->cov_src.p;
@@ -324,33 +455,29 @@ int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
   prm.lsq = h->cfg.lsq_optimizer;
   prm.lm_max_iterations = 10;
   prm.lm_init_lambda_factor = 1e-9;
-  B200_CUDA_TRY(cudaMemcpyAsync(h->gicp_jobs.p, job, sizeof(GicpJob), cudaMemcpyHostToDevice, h->stream));
-  B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, 64 * sizeof(unsigned int), h->stream));
-  const GicpJob* jobs = h->gicp_jobs.p;
   int g = G;
   double* partials = h->partials.p;
   unsigned int* barrier = h->barriers.p;
-  void* args[] = {(void*)&jobs, (void*)&g, (void*)&prm, (void*)&partials, (void*)&barrier};
-  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  void* args[] = {(void*)job, (void*)&g, (void*)&prm, (void*)&partials, (void*)&barrier};
+  if ((rc = begin_timed_launch(h))) return rc;
   B200_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_gicp_align, dim3(G), dim3(kGicpThreads), args, 0, h->stream));
   launch_counter() += 1;
-  if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  if ((rc = end_timed_launch(h))) return rc;
   return B200REG_OK;
 }
 
-int fetch_result(b200reg_handle* h) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  b200reg_result* pr = reinterpret_cast<b200reg_result*>(h->pin_small.p + sizeof(NdtJob));
-  B200_CUDA_TRY(cudaMemcpyAsync(pr, h->d_result.p, sizeof(b200reg_result), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  h->last = *pr;
-  h->have_result = true;
-  if (h->timing) {
-    float ms = 0.f;
-    B200_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->align_ms += (double)ms;
-    h->n_align += 1;
+// result of the single call in flight: polled from the mailbox the kernel writes through the mapped
+// host pointer.  `synced` = the caller has already synchronised the stream (aligned-cloud path).
+int fetch_result(b200reg_handle* h, bool synced = false) {
+  if (!synced) {
+    int rc = wait_mail(h, &h->mail->align_seq, h->align_seq);
+    if (rc) return rc;
+  } else if (h->mail->align_seq != h->align_seq) {
+    h->err = "kernel finished without publishing its result";
+    return B200REG_E_CUDA;
   }
+  memcpy(&h->last, const_cast<b200reg_result*>(&h->mail->result), sizeof(b200reg_result));
+  h->have_result = true;
   return B200REG_OK;
 }
 
@@ -397,6 +524,9 @@ int b200reg_create(const b200reg_config* cfg, b200reg_handle** out) {
   if (prop.major < 10 || !coop) { delete h; return B200REG_E_CUDA; }  // sm_100a only
   h->num_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return B200REG_E_CUDA; }
+  if (init_kernel_attributes(cfg->device) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return B200REG_E_CUDA; }
+  if (cudaHostAlloc((void**)&h->mail, sizeof(HostMailbox), cudaHostAllocMapped) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return B200REG_E_CUDA; }
+  memset((void*)h->mail, 0, sizeof(HostMailbox));
   *out = h;
   return B200REG_OK;
 }
@@ -405,10 +535,10 @@ int b200reg_destroy(b200reg_handle* h) {
   if (!h) return B200REG_E_INVALID;
   cudaSetDevice(h->cfg.device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& pr : h->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (h->mail) cudaFreeHost((void*)h->mail);
   h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
-  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release();
+  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
   h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_jobs.release();
@@ -555,7 +685,8 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
     k_transform_cloud<<<(h->n_src + 255) / 256, 256, 0, h->stream>>>(h->src.p, h->n_src, h->d_result.p, h->aligned.p);
     B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
   }
-  if ((rc = fetch_result(h))) return rc;
+  if (aligned_xyzw) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
   if (aligned_xyzw) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
   return B200REG_OK;
 }
@@ -651,27 +782,31 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   launch_counter() += 1 + (min_pts > 1 ? 1 : 0);
+  // the overflow case publishes from k_vg_centroids even when a compaction pass follows
+  VgCounts* hc = const_cast<VgCounts*>(&h->mail->vg);
+  unsigned int* hf = const_cast<unsigned int*>(&h->mail->vg_seq);
+  const unsigned int seq = ++h->vg_seq;
+  if (!h->vg_done.p) {  // completion counter of k_vg_centroids: zeroed once, the last block restores it
+    B200_CUDA_TRY(h->vg_done.reserve(1));
+    B200_CUDA_TRY(cudaMemsetAsync(h->vg_done.p, 0, h->vg_done.cap * sizeof(unsigned int), h->stream));
+  }
   k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
-                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
-  if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p);
+                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1);
+  if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq);
   B200_CUDA_TRY(cudaGetLastError());
   h->vg_last_n = (int)n;
   return B200REG_OK;
 }
 
 int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out, size_t* n_out) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || !leaf || !n_out || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
   if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = vg_run(h, (const float4*)d_xyzw, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
-  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
-  VgCounts* pc = reinterpret_cast<VgCounts*>(h->pin_small.p);
-  B200_CUDA_TRY(cudaMemcpyAsync(pc, h->vg_counts.p, sizeof(VgCounts), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  *n_out = pc->n_out;
-  h->vg_last_out = (int)pc->n_out;
+  if ((rc = wait_mail(h, &h->mail->vg_seq, h->vg_seq))) return rc;
+  *n_out = h->mail->vg.n_out;
+  h->vg_last_out = (int)h->mail->vg.n_out;
   return B200REG_OK;
 }
 
@@ -849,12 +984,12 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     if (G < 1) G = 1;
     const int n_groups = h->num_sm / G;
     B200_CUDA_TRY(h->partials.reserve((size_t)n_groups * 2 * G * kAccStride));
-    B200_CUDA_TRY(h->barriers.reserve((size_t)(n_groups + 1) * 32));
-    B200_CUDA_TRY(cudaMemsetAsync(h->barriers.p, 0, (size_t)(n_groups + 1) * 32 * sizeof(unsigned int), h->stream));
-    if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = ensure_barriers(h, (size_t)(n_groups + 1) * 32))) return rc;
+    if ((rc = drain_events(h))) return rc;
+    if ((rc = begin_timed_launch(h))) return rc;
     B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups));
     launch_counter() += 1;
-    if (h->timing) B200_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = end_timed_launch(h))) return rc;
   }
   // ---- getFitnessScore(max_range) for every pair, in chunks that bound the d2 scratch
   cudaEvent_t evf0 = nullptr, evf1 = nullptr;
@@ -903,12 +1038,11 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
   if (!with_fitness)
     for (size_t i = 0; i < n_pairs; ++i) results[i].fitness = 1.7976931348623157e308;
   if (h->timing && n_jobs) {
-    float ms = 0.f;
-    B200_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->batch_align_ms = (double)ms;
-    h->align_ms += (double)ms;
-    h->n_align += 1;
+    const double before = h->align_ms;
+    if ((rc = drain_events(h))) return rc;
+    h->batch_align_ms = h->align_ms - before;
     if (evf0) {
+      float ms = 0.f;
       B200_CUDA_TRY(cudaEventElapsedTime(&ms, evf0, evf1));
       h->batch_fitness_ms = (double)ms;
     }
@@ -992,6 +1126,7 @@ int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score,
   if (h->cfg.method != B200REG_METHOD_NDT || !h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_E_STATE;
   int rc = set_device(h);
   if (rc) return rc;
+  B200_CUDA_TRY(h->pin_small.reserve(sizeof(NdtJob) + sizeof(GicpJob) + sizeof(b200reg_result) + 64 * sizeof(double)));
   if ((rc = run_ndt_single(h, nullptr, p))) return rc;
   double* pd = reinterpret_cast<double*>(h->pin_small.p + sizeof(NdtJob) + sizeof(b200reg_result));
   B200_CUDA_TRY(cudaMemcpyAsync(pd, h->deriv.p, 43 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1003,14 +1138,10 @@ int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score,
 }
 
 int b200reg_set_timing(b200reg_handle* h, int on) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h) return B200REG_E_INVALID;
   int rc = set_device(h);
   if (rc) return rc;
-  if (on && !h->ev0) {
-    B200_CUDA_TRY(cudaEventCreate(&h->ev0));
-    B200_CUDA_TRY(cudaEventCreate(&h->ev1));
-  }
+  if ((rc = drain_events(h))) return rc;
   h->timing = on != 0;
   h->align_ms = 0.0;
   h->n_align = 0;
@@ -1019,6 +1150,7 @@ int b200reg_set_timing(b200reg_handle* h, int on) {
 
 int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long* timed_aligns, double* align_kernel_ms) {
   if (!h) return B200REG_E_INVALID;
+  if (set_device(h) == B200REG_OK) drain_events(h);
   if (launches_total) *launches_total = launch_counter().load();
   if (timed_aligns) *timed_aligns = h->n_align;
   if (align_kernel_ms) *align_kernel_ms = h->align_ms;

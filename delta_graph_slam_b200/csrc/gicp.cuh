@@ -240,6 +240,9 @@ struct GicpJob {
   int* corr;               // [n_src] scratch: correspondences_
   double* mahal;           // [n_src][6] scratch: mahalanobis_
   b200reg_result* result;
+  b200reg_result* result_host;  // mapped host copy + completion flag (see NdtJob)
+  unsigned int* done_flag;
+  unsigned int done_seq;
 };
 
 struct GicpShared {
@@ -470,9 +473,8 @@ __device__ __forceinline__ void gicp_group_barrier(unsigned int* counter, unsign
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const GicpJob* __restrict__ jobs, int G, GicpParams prm, double* partials, unsigned int* barrier) {
+__global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_constant__ GicpJob job, int G, GicpParams prm, double* partials, unsigned int* barrier) {
   __shared__ GicpShared s;
-  const GicpJob& job = jobs[0];
   const int rank = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_src = job.n_src;
   const GridParams gp = job.tgt.meta->grid;
@@ -606,6 +608,21 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const GicpJob* _
     r.reserved = 0;
     r.hits = (long long)s.hits;
     *job.result = r;
+    if (job.result_host) {
+      *job.result_host = r;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int*>(job.done_flag) = job.done_seq;
+    }
+  }
+  // the last CTA to leave zeroes the barrier counter and the exit counter for the next launch
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(barrier + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      barrier[0] = 0u;
+      barrier[1] = 0u;
+      __threadfence();
+    }
   }
 }
 

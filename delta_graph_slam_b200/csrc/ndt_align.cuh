@@ -56,6 +56,12 @@ struct NdtJob {
   double p0[6];     // [t, eulerXYZ] of the guess (host: Eigen eulerAngles(0,1,2) restated, A.6)
   int eval_only;    // 1: a single derivative pass at p0 (introspection), T built from p0
   b200reg_result* result;  // device
+  // single registrations: a second copy of the record goes straight to page-locked host memory mapped
+  // into the device address space, followed by a completion flag the host polls — no D2H copy, no
+  // stream synchronisation on the critical path of a frame
+  b200reg_result* result_host;
+  unsigned int* done_flag;
+  unsigned int done_seq;
   double* deriv_out;       // device, 1 + 6 + 36 doubles (eval_only)
   long long* prof;         // device, optional: SM cycles of CTA 0 per phase {pass, reduce, barrier, total, step, n, stage}
 };
@@ -381,20 +387,54 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
   float score = 0.f;
   int hits = 0;
   constexpr int NOFF = MODE == 0 ? 27 : MODE;
+  // DIRECT1 / DIRECT7: the keys and FIRST hash probes of all neighbours are issued before any of them
+  // is consumed, so the shared-memory loads of the seven look-ups are in flight together instead of
+  // seven dependent probe loops back to back (a pass has ~1 point per thread: latency is the cost).
+  constexpr bool kBatchProbes = NOFF <= 7;
+  int pre_slot[kBatchProbes ? NOFF : 1];
+  if (kBatchProbes) {
+    uint32_t pkey[NOFF], ph[NOFF];
+    uint2 pe[NOFF];
+    bool pin[NOFF];
+#pragma unroll
+    for (int o = 0; o < NOFF; ++o) {
+      const int dx = NOFF == 1 ? 0 : (o == 1 ? 1 : o == 2 ? -1 : 0), dy = NOFF == 1 ? 0 : (o == 3 ? 1 : o == 4 ? -1 : 0), dz = NOFF == 1 ? 0 : (o == 5 ? 1 : o == 6 ? -1 : 0);
+      const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
+      pin[o] = !(i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]);
+      pkey[o] = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
+      ph[o] = ndt_hash(pkey[o], grid.mask);
+      pe[o] = pin[o] ? grid.table[ph[o]] : make_uint2(kInvalidKey, 0u);
+    }
+#pragma unroll
+    for (int o = 0; o < NOFF; ++o) {
+      int sl = -1;
+      if (pin[o]) {
+        if (pe[o].x == pkey[o]) sl = (int)pe[o].y;
+        else if (pe[o].x != kInvalidKey) {  // collision: walk on from the next cell
+          uint32_t h = (ph[o] + 1) & grid.mask;
+          while (true) {
+            const uint2 e = grid.table[h];
+            if (e.x == pkey[o]) { sl = (int)e.y; break; }
+            if (e.x == kInvalidKey) break;
+            h = (h + 1) & grid.mask;
+          }
+        }
+      }
+      pre_slot[o] = sl;
+    }
+  }
 #pragma unroll
   for (int o = 0; o < NOFF; ++o) {
-    int dx, dy, dz;
-    if (NOFF == 1) { dx = dy = dz = 0; }
-    else if (NOFF == 7) {
-      // (0,0,0), (+1,0,0), (-1,0,0), (0,+1,0), (0,-1,0), (0,0,+1), (0,0,-1)
-      dx = o == 1 ? 1 : o == 2 ? -1 : 0;
-      dy = o == 3 ? 1 : o == 4 ? -1 : 0;
-      dz = o == 5 ? 1 : o == 6 ? -1 : 0;
-    } else { dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1; }
-    const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
-    if (i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]) continue;
-    const uint32_t key = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
-    int slot = ndt_lookup(grid, key);
+    int slot;
+    if (kBatchProbes) {
+      slot = pre_slot[o];
+    } else {
+      const int dx = o / 9 - 1, dy = (o / 3) % 3 - 1, dz = o % 3 - 1;
+      const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
+      if (i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]) continue;
+      const uint32_t key = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
+      slot = ndt_lookup(grid, key);
+    }
     if (slot < 0) continue;
     if (slot & (int)kNdtRejected) {  // nr_points = -1 upstream: invisible to DIRECT*, still in the KDTREE cloud
       if (MODE != 0) continue;
@@ -503,7 +543,7 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 
 template <int MODE>
 __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers,
-                                                                unsigned int* queue) {
+                                                                unsigned int* queue, unsigned int launch_tag, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
   __shared__ int s_job;
   extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
@@ -514,6 +554,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   unsigned int epoch = 0;
   int parity = 0;
   unsigned int fetched = 0;
+  unsigned int pass_no = 0;  // passes of this group since the launch: (launch_tag, pass_no) tags the partial rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
@@ -541,7 +582,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       ++fetched;
     }
     if (jb >= n_jobs) break;
-    const NdtJob& job = jobs[jb];
+    const NdtJob& job = jobs ? jobs[jb] : single;  // one registration: the job rides in the kernel parameters
     const GridParams gp = job.grid.meta->grid;
     const int n_src = job.n_src;
     long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -626,36 +667,56 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         }
       }
       const long long t1 = clock64();
-      // ---- block reduce: warp totals -> shared memory -> one partial row per CTA
+      // ---- block reduce: warp totals -> shared memory -> one partial row per CTA.  The row carries
+      // its own arrival flag in slot 31: lanes 0..30 of warp 0 store the sums, fence, and lane 31
+      // releases the (launch, pass) tag — the cross-CTA reduction below waits on the flags of the
+      // rows it reads, so there is no separate counter barrier (and no atomic hot spot) per pass.
       s.red[warp][lane] = accd;
       __syncthreads();
+      ++pass_no;
+      const unsigned long long tag = ((unsigned long long)launch_tag << 32) | (unsigned long long)pass_no;
       if (tid < kAccStride) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kAlignWarps; ++w) v += s.red[w][tid];
-        if (G == 1) s.tot[tid] = v;  // a one-CTA group (loop-closure batches): no global round trip, no barrier
-        else partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
+        if (G == 1) {
+          s.tot[tid] = v;  // a one-CTA group (loop-closure batches): no global round trip at all
+        } else {
+          double* row = partials + ((size_t)parity * G + rank) * kAccStride;
+          if (tid < 31) __stcg(row + tid, v);
+          __threadfence();
+          __syncwarp();
+          if (tid == 31) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(row + 31), "l"(tag) : "memory");
+        }
       }
-      // ---- group sync + redundant fixed-order reduction of the G partials
+      // ---- redundant fixed-order reduction of the G partial rows in every CTA
       const long long t2 = clock64();
       long long t3 = t2;
       if (G > 1) {
-        epoch += (unsigned)G;
-        group_barrier(barrier, epoch);
-        t3 = clock64();
         // warp w sums rows w, w+16, ... (each row one coalesced 256-byte read), then the 16 row
         // groups are combined through shared memory; fixed order -> every CTA gets the same bits
-        const double* base = partials + (size_t)parity * G * kAccStride + lane;
+        const double* base = partials + (size_t)parity * G * kAccStride;
+        if (lane == 31) {
+          for (int r = warp; r < G; r += kAlignWarps) {
+            const double* flag = base + (size_t)r * kAccStride + 31;
+            unsigned long long seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+            } while (seen != tag);
+          }
+        }
+        __syncwarp();
+        t3 = clock64();
         double tmp[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {  // all loads in flight before the first add (G <= 160)
           const int r = warp + kAlignWarps * k;
-          tmp[k] = r < G ? __ldcg(base + (size_t)r * kAccStride) : 0.0;
+          tmp[k] = (r < G && lane < 31) ? __ldcg(base + (size_t)r * kAccStride + lane) : 0.0;
         }
         double v = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) v += tmp[k];
-        for (int r = warp + kAlignWarps * 10; r < G; r += kAlignWarps) v += __ldcg(base + (size_t)r * kAccStride);
+        for (int r = warp + kAlignWarps * 10; r < G; r += kAlignWarps) v += lane < 31 ? __ldcg(base + (size_t)r * kAccStride + lane) : 0.0;
         __syncthreads();  // s.red is reused
         s.red[warp][lane] = v;
         __syncthreads();
@@ -724,8 +785,26 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       r.reserved = 0;
       r.hits = (long long)s.hits;
       *job.result = r;
+      if (job.result_host) {
+        *job.result_host = r;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(job.done_flag) = job.done_seq;
+      }
     }
     __syncthreads();
+  }
+  // the last CTA to leave puts the barrier lines, the job counter and the exit counter back to
+  // zero, so the next launch needs no memset in front of it
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(queue + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      const int n_groups = (int)gridDim.x / G;
+      for (int gq = 0; gq < n_groups; ++gq) { barriers[gq * 32] = 0u; barriers[gq * 32 + 1] = 0u; barriers[gq * 32 + 2] = 0u; }
+      queue[0] = 0u;
+      queue[1] = 0u;
+      __threadfence();
+    }
   }
 }
 

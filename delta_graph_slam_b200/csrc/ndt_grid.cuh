@@ -69,6 +69,7 @@ struct NdtLeafArgs {
   double *leaf_mean, *leaf_cov, *leaf_icov;
 };
 // ndt_leaf.cu (-fmad=false): statistics -> records, then the hash over the records
+cudaError_t ndt_leaf_prefer_shared();  // maximum shared-memory carve-out for the kernels of ndt_leaf.cu (see init_kernel_attributes)
 cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen, double* sums, float* csum);
 
 struct NdtGrid {

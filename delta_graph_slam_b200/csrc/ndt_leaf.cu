@@ -178,6 +178,13 @@ static __global__ void __launch_bounds__(1024) k_ndt_table(NdtLeafArgs a, const 
   }
 }
 
+cudaError_t ndt_leaf_prefer_shared() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute((const void*)k_ndt_leaf_sums, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute((const void*)k_ndt_leaf_stats, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)k_ndt_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen, double* sums, float* csum) {
   launch_counter() += 3;
   k_ndt_leaf_sums<<<kNumSM * 8, 256, 0, st>>>(a, sums, csum);

@@ -52,6 +52,20 @@ __device__ __forceinline__ void coop_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// the last CTA to leave zeroes the barrier counter (word 0) and the exit counter (word 1), so the
+// next launch needs no memset in front of it
+__device__ __forceinline__ void coop_exit(unsigned int* counter) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(counter + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      counter[0] = 0u;
+      counter[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
 // exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix,
 // *total receives the block sum
 __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* s_warp /*[8]*/, uint32_t* total) {
@@ -171,7 +185,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_voxel_sort_coop(CoopSortArg
     }
   }
   __syncthreads();
-  if (g.overflow) return;  // "leaf size too small": the callers copy the input instead (uniform exit)
+  if (g.overflow) {  // "leaf size too small": the callers copy the input instead (uniform exit)
+    coop_exit(a.barrier);
+    return;
+  }
   const uint32_t skip = s_skip, nbits = s_nbits;
   const int wbase = tile * TILE + warp * (32 * ITEMS);
   uint32_t k[ITEMS], v[ITEMS];
@@ -329,6 +346,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_voxel_sort_coop(CoopSortArg
       a.vox_start[TH] = TV;
     }
   }
+  coop_exit(a.barrier);
 }
 
 // host side: launch when the cloud fits one tile per CTA; returns false when the caller must take
@@ -351,8 +369,10 @@ inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4*
   if ((e = vs.hist.reserve((size_t)kNumSM * kRadix)) != cudaSuccess) { *err = e; return true; }
   if ((e = vs.tile_heads.reserve((size_t)2 * kNumSM)) != cudaSuccess) { *err = e; return true; }
   if ((e = vs.mm.reserve((size_t)8 * kNumSM)) != cudaSuccess) { *err = e; return true; }
-  if ((e = vs.coop_bar.reserve(32)) != cudaSuccess) { *err = e; return true; }
-  if ((e = cudaMemsetAsync(vs.coop_bar.p, 0, sizeof(unsigned int), st)) != cudaSuccess) { *err = e; return true; }
+  if (!vs.coop_bar.p) {  // zeroed once; every kernel restores the counters on exit
+    if ((e = vs.coop_bar.reserve(32)) != cudaSuccess) { *err = e; return true; }
+    if ((e = cudaMemsetAsync(vs.coop_bar.p, 0, vs.coop_bar.cap * sizeof(unsigned int), st)) != cudaSuccess) { *err = e; return true; }
+  }
   CoopSortArgs a;
   a.pts = d_pts; a.n = n; a.is_dense = is_dense; a.lx = lx; a.ly = ly; a.lz = lz;
   a.meta = vs.meta.p; a.keys_a = vs.keys_a.p; a.vals_a = vs.vals_a.p; a.keys_b = vs.keys_b.p; a.vals_b = vs.vals_b.p;

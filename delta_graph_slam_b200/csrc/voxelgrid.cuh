@@ -16,34 +16,52 @@ struct VgCounts {  // device-resident summary of the last filter call
 __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__ pts, int n, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
                                                       const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_start, const uint32_t* __restrict__ vox_key,
                                                       unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id, uint32_t* __restrict__ out_count,
-                                                      VgCounts* __restrict__ counts) {
+                                                      VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq,
+                                                      unsigned int* done_blocks, int publish_here) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (meta->grid.overflow) {  // "Leaf size is too small for the input dataset": output = *input_
-    if (i < n) out[i] = pts[i];
-    if (i == 0) { counts->n_out = (uint32_t)n; counts->overflow = 1; }
-    return;
-  }
-  const uint32_t* vals = sorted_in_b(meta) ? vals_b : vals_a;
+  const bool overflow = meta->grid.overflow != 0;  // "Leaf size is too small for the input dataset": output = *input_
   const int n_vox = (int)meta->n_vox;
-  if (i == 0 && min_points <= 1) { counts->n_out = (uint32_t)n_vox; counts->overflow = 0; }
-  if (i >= n_vox) return;
-  const uint32_t s = vox_start[i], e = vox_start[i + 1];
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  for (uint32_t j = s; j < e; ++j) {
-    const float4 p = __ldg(pts + vals[j]);
-    ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
+  if (overflow) {
+    if (i < n) out[i] = pts[i];
+  } else if (i < n_vox) {
+    const uint32_t* vals = sorted_in_b(meta) ? vals_b : vals_a;
+    const uint32_t s = vox_start[i], e = vox_start[i + 1];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (uint32_t j = s; j < e; ++j) {
+      const float4 p = __ldg(pts + vals[j]);
+      ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
+    }
+    const float cnt = (float)(e - s);
+    out[i] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
+    if (out_id) out_id[i] = vox_key[i];
+    if (out_count) out_count[i] = e - s;
   }
-  const float cnt = (float)(e - s);
-  out[i] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
-  if (out_id) out_id[i] = vox_key[i];
-  if (out_count) out_count[i] = e - s;
+  // The point count goes to the device summary and, for the caller waiting on the host, straight into
+  // mapped page-locked memory followed by a sequence flag.  The LAST block to finish publishes it:
+  // when the host sees the flag every centroid is written and fenced, so a consumer on another
+  // stream (the registration handle copying this cloud) may read the output right away.
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(done_blocks, 1u) != gridDim.x - 1) return;
+  *done_blocks = 0u;
+  if (!publish_here && !overflow) return;  // a compaction pass follows and publishes instead
+  const uint32_t n_out = overflow ? (uint32_t)n : (uint32_t)n_vox;
+  counts->n_out = n_out;
+  counts->overflow = overflow ? 1u : 0u;
+  if (host_counts) {
+    host_counts->n_out = n_out;
+    host_counts->overflow = overflow ? 1u : 0u;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
+  }
 }
 
 // min_points_per_voxel > 1 (never set by the reference): drop sparse voxels, keeping the order.
 // Single block; voxel counts are at most the point count.
 __global__ void __launch_bounds__(1024) k_vg_compact(const SortMeta* __restrict__ meta, unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id,
-                                                     uint32_t* __restrict__ out_count, VgCounts* __restrict__ counts) {
-  if (meta->grid.overflow) return;
+                                                     uint32_t* __restrict__ out_count, VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq) {
+  if (meta->grid.overflow) return;  // published by k_vg_centroids
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_base;
   const int n_vox = (int)meta->n_vox;
@@ -67,7 +85,16 @@ __global__ void __launch_bounds__(1024) k_vg_compact(const SortMeta* __restrict_
     if (threadIdx.x == 1023) s_base = off + __popc(bal);
     __syncthreads();
   }
-  if (threadIdx.x == 0) { counts->n_out = s_base; counts->overflow = 0; }
+  if (threadIdx.x == 0) {
+    counts->n_out = s_base;
+    counts->overflow = 0;
+    if (host_counts) {
+      host_counts->n_out = s_base;
+      host_counts->overflow = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
+    }
+  }
 }
 
 }  // namespace b200
