@@ -86,7 +86,7 @@ struct b200reg_handle {
   double batch_fitness_ms = 0.0;
 
   HostMailbox* mail = nullptr;  // cudaHostAllocMapped
-  unsigned int align_seq = 0, vg_seq = 0, launch_tag = 0;
+  unsigned int align_seq = 0, vg_seq = 0;
   size_t barriers_zeroed = 0;   // entries of `barriers` known to be zero (kernels restore them on exit)
 
   b200reg_result last;
@@ -325,8 +325,7 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
   unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
-  unsigned int launch_tag = ++h->launch_tag;  // tags the partial rows of this launch (stale rows of earlier launches never match)
-  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&launch_tag, (void*)&sj};
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
   return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 

@@ -475,6 +475,9 @@ __device__ __forceinline__ void gicp_group_barrier(unsigned int* counter, unsign
 
 __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_constant__ GicpJob job, int G, GicpParams prm, double* partials, unsigned int* barrier) {
   __shared__ GicpShared s;
+  __shared__ float4 s_q[kGicpThreads];   // far-query queue of the current slice: transformed point, w = source index
+  __shared__ float2 s_qb[kGicpThreads];  // best so far (d2, index bits)
+  __shared__ int s_wq[kGicpWarps];
   const int rank = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_src = job.n_src;
   const GridParams gp = job.tgt.meta->grid;
@@ -500,10 +503,29 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     double acc[kGicpAcc];
 #pragma unroll
     for (int k = 0; k < kGicpAcc; ++k) acc[k] = 0.0;
-    // ---- pass over the source points: whole warps stay together so a far query can use all lanes
+    // ---- pass over the source points.  linearize: every thread resolves its own query in the near
+    // phase (rings 0-1) and finishes the point; the few queries left open are queued in shared memory
+    // and, after a block barrier, dealt round-robin to the CTA's 16 warps for the cooperative far
+    // search — so a warp that happened to draw several far points does not hold up the pass.
     const int stride = G * kGicpThreads;
-    for (int base = rank * kGicpThreads + warp * 32; base < n_src; base += stride) {
-      const int i = base + lane;
+    auto finish_point = [&](int i, const float4 p, float best, int best_idx) {
+      int c = -1;
+      if (best_idx != kNoIndex && (double)best < prm.corr_dist2) c = best_idx;
+      job.corr[i] = c;
+      if (c < 0) return;
+      double CA[6], CB[6], M[6];
+      const double* pa = job.cov_src + (size_t)i * 6;
+      const double* pb = job.cov_tgt + (size_t)c * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { CA[k] = pa[k]; CB[k] = __ldg(pb + k); }
+      gicp_mahalanobis(s.R, CA, CB, M);
+      double* pm = job.mahal + (size_t)i * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pm[k] = M[k];
+      gicp_residual<true>(s, p, __ldg(job.tgt_pts + c), M, acc);
+    };
+    for (int b0 = rank * kGicpThreads; b0 < n_src; b0 += stride) {
+      const int i = b0 + tid;
       const bool active = i < n_src;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) p = __ldg(job.src + i);
@@ -516,33 +538,38 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         int best_idx = kNoIndex;
         bool ok = true;
         if (active && grid_ok) ok = nn_query_near(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
-        // the few queries the near phase left open: the warp finishes them one by one, all lanes helping
-        unsigned open = __ballot_sync(0xffffffffu, !ok);
-        while (open) {
-          const int src_lane = __ffs(open) - 1;
-          open &= open - 1;
-          const float fx = __shfl_sync(0xffffffffu, qx, src_lane), fy = __shfl_sync(0xffffffffu, qy, src_lane), fz = __shfl_sync(0xffffffffu, qz, src_lane);
-          float fb = __shfl_sync(0xffffffffu, best, src_lane);
-          int fi = __shfl_sync(0xffffffffu, best_idx, src_lane);
-          const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, fx, fy, fz), prm.search_d2, prm.far_ring, lane, fb, fi);
-          if (!done) nn_query_brute_warp(job.tgt, fx, fy, fz, lane, fb, fi);
-          if (lane == src_lane) { best = fb; best_idx = fi; }
-        }
-        int c = -1;
-        if (active && best_idx != kNoIndex && (double)best < prm.corr_dist2) c = best_idx;
-        if (active) job.corr[i] = c;
-        if (c >= 0) {
-          double CA[6], CB[6], M[6];
-          const double* pa = job.cov_src + (size_t)i * 6;
-          const double* pb = job.cov_tgt + (size_t)c * 6;
+        // queue slots in thread order (ballot compaction): the far points are always dealt to the same
+        // warps, so the summation order — and with it the result — is reproducible bit for bit
+        const unsigned open = __ballot_sync(0xffffffffu, active && !ok);
+        if (lane == 0) s_wq[warp] = __popc(open);
+        if (active && ok) finish_point(i, p, best, best_idx);
+        __syncthreads();
+        int qbase = 0, nq = 0;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) { CA[k] = pa[k]; CB[k] = __ldg(pb + k); }
-          gicp_mahalanobis(s.R, CA, CB, M);
-          double* pm = job.mahal + (size_t)i * 6;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) pm[k] = M[k];
-          gicp_residual<true>(s, p, __ldg(job.tgt_pts + c), M, acc);
+        for (int w = 0; w < kGicpWarps; ++w) {
+          const int c = s_wq[w];
+          if (w < warp) qbase += c;
+          nq += c;
         }
+        if (active && !ok) {
+          const int slot = qbase + __popc(open & ((1u << lane) - 1u));
+          s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i));
+          s_qb[slot] = make_float2(best, __int_as_float(best_idx));
+        }
+        __syncthreads();
+        for (int e = warp; e < nq; e += kGicpWarps) {
+          const float4 q = s_q[e];
+          const float2 qb = s_qb[e];
+          float fb = qb.x;
+          int fi = __float_as_int(qb.y);
+          const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, q.x, q.y, q.z), prm.search_d2, prm.far_ring, lane, fb, fi);
+          if (!done) nn_query_brute_warp(job.tgt, q.x, q.y, q.z, lane, fb, fi);
+          if (lane == 0) {
+            const int qi = __float_as_int(q.w);
+            finish_point(qi, __ldg(job.src + qi), fb, fi);
+          }
+        }
+        __syncthreads();  // the queue is reused by the next slice
       } else {
         const int c = active ? job.corr[i] : -1;
         if (c >= 0) {

@@ -543,7 +543,7 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 
 template <int MODE>
 __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers,
-                                                                unsigned int* queue, unsigned int launch_tag, const __grid_constant__ NdtJob single) {
+                                                                unsigned int* queue, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
   __shared__ int s_job;
   extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
@@ -554,7 +554,6 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   unsigned int epoch = 0;
   int parity = 0;
   unsigned int fetched = 0;
-  unsigned int pass_no = 0;  // passes of this group since the launch: (launch_tag, pass_no) tags the partial rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
@@ -667,56 +666,38 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         }
       }
       const long long t1 = clock64();
-      // ---- block reduce: warp totals -> shared memory -> one partial row per CTA.  The row carries
-      // its own arrival flag in slot 31: lanes 0..30 of warp 0 store the sums, fence, and lane 31
-      // releases the (launch, pass) tag — the cross-CTA reduction below waits on the flags of the
-      // rows it reads, so there is no separate counter barrier (and no atomic hot spot) per pass.
+      // ---- block reduce: warp totals -> shared memory -> one partial row per CTA
       s.red[warp][lane] = accd;
       __syncthreads();
-      ++pass_no;
-      const unsigned long long tag = ((unsigned long long)launch_tag << 32) | (unsigned long long)pass_no;
       if (tid < kAccStride) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kAlignWarps; ++w) v += s.red[w][tid];
-        if (G == 1) {
-          s.tot[tid] = v;  // a one-CTA group (loop-closure batches): no global round trip at all
-        } else {
-          double* row = partials + ((size_t)parity * G + rank) * kAccStride;
-          if (tid < 31) __stcg(row + tid, v);
-          __threadfence();
-          __syncwarp();
-          if (tid == 31) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(row + 31), "l"(tag) : "memory");
-        }
+        if (G == 1) s.tot[tid] = v;  // a one-CTA group (loop-closure batches): no global round trip, no barrier
+        else partials[((size_t)parity * G + rank) * kAccStride + tid] = v;
       }
-      // ---- redundant fixed-order reduction of the G partial rows in every CTA
+      // ---- group sync + redundant fixed-order reduction of the G partials.  (Tagging every row with
+      // its own arrival flag instead of one counter barrier was measured: 2368 polling lanes cost more
+      // than 148 spinners on one line — 288 us vs 223 us per registration.)
       const long long t2 = clock64();
       long long t3 = t2;
       if (G > 1) {
+        epoch += (unsigned)G;
+        group_barrier(barrier, epoch);
+        t3 = clock64();
         // warp w sums rows w, w+16, ... (each row one coalesced 256-byte read), then the 16 row
         // groups are combined through shared memory; fixed order -> every CTA gets the same bits
-        const double* base = partials + (size_t)parity * G * kAccStride;
-        if (lane == 31) {
-          for (int r = warp; r < G; r += kAlignWarps) {
-            const double* flag = base + (size_t)r * kAccStride + 31;
-            unsigned long long seen;
-            do {
-              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-            } while (seen != tag);
-          }
-        }
-        __syncwarp();
-        t3 = clock64();
+        const double* base = partials + (size_t)parity * G * kAccStride + lane;
         double tmp[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {  // all loads in flight before the first add (G <= 160)
           const int r = warp + kAlignWarps * k;
-          tmp[k] = (r < G && lane < 31) ? __ldcg(base + (size_t)r * kAccStride + lane) : 0.0;
+          tmp[k] = r < G ? __ldcg(base + (size_t)r * kAccStride) : 0.0;
         }
         double v = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) v += tmp[k];
-        for (int r = warp + kAlignWarps * 10; r < G; r += kAlignWarps) v += lane < 31 ? __ldcg(base + (size_t)r * kAccStride + lane) : 0.0;
+        for (int r = warp + kAlignWarps * 10; r < G; r += kAlignWarps) v += __ldcg(base + (size_t)r * kAccStride);
         __syncthreads();  // s.red is reused
         s.red[warp][lane] = v;
         __syncthreads();
