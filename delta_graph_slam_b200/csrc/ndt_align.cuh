@@ -39,6 +39,7 @@ constexpr int kAlignWarps = kAlignThreads / 32;
 constexpr int kNumAcc = 29;  // score, g[6], H upper triangle [21], hits
 constexpr int kAccStride = 32;
 constexpr int kStageBytes = 192 * 1024;  // dynamic shared memory for the staged grid
+constexpr int kLaneGroup = 4;             // points a lane sums in float before the warp reduction (batch mode)
 
 enum NdtPhase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_ITER = 2, PH_HESSIAN = 3, PH_DONE = 4, PH_EVAL_ONLY = 5 };
 
@@ -87,18 +88,42 @@ struct NdtShared {
   double red[kAlignWarps][kAccStride];
 };
 
-// staged (or global) view of the target grid used inside a pass
+// staged (or global) view of the target grid used inside a pass.  When the grid sits in shared
+// memory the loads are issued as explicit ld.shared on 32-bit shared-window addresses: through the
+// generic pointers the compiler could not prove the address space and emitted generic LDs, which
+// cost an address-space check and sit on the long scoreboard (ncu: the top stall of the pass).
 struct NdtLookup {
   const uint2* table;
   uint32_t mask;
   const NdtVoxel* voxels;
   const float4* centroids;
+  uint32_t s_table, s_voxels, s_centroids;  // shared-window byte addresses (staged grids)
 };
 
+template <bool STAGED>
+__device__ __forceinline__ uint2 lk_table(const NdtLookup& g, uint32_t h) {
+  if (STAGED) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(g.s_table + h * 8u));
+    return v;
+  }
+  return g.table[h];
+}
+template <bool STAGED>
+__device__ __forceinline__ float4 lk_f4(const NdtLookup& g, uint32_t s_base, const float4* p_base, uint32_t index16) {
+  if (STAGED) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(s_base + index16 * 16u));
+    return v;
+  }
+  return p_base[index16];
+}
+
+template <bool STAGED>
 __device__ __forceinline__ int ndt_lookup(const NdtLookup& g, uint32_t key) {
   uint32_t h = ndt_hash(key, g.mask);
   while (true) {
-    const uint2 e = g.table[h];
+    const uint2 e = lk_table<STAGED>(g, h);
     if (e.x == key) return (int)e.y;
     if (e.x == kInvalidKey) return -1;
     h = (h + 1) & g.mask;
@@ -369,11 +394,11 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
 }
 
 // ---- one source point ------------------------------------------------------------------------
-// Writes the point's 29 contributions (score, g[6], H upper triangle [21], hits) as floats into
+// ADDS the point's 29 contributions (score, g[6], H upper triangle [21], hits) as floats to
 // out[0..28]; the caller reduces them across the warp and accumulates in double.
 // gauss_d1 arrives as an unevaluated float pair (d1h + d1l) so that the reference's
 // float(double(d1) * e) products are reproduced without FP64 conversions in the per-hit path.
-template <int MODE>  // 1, 7, 27 (DIRECT*) or 0 (KDTREE radius search over voxel centroids)
+template <int MODE, bool STAGED>  // MODE: 1, 7, 27 (DIRECT*) or 0 (KDTREE radius search over voxel centroids)
 __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& grid, const GridParams& gp, float4 pt, float d1h, float d1l, float gauss_d2, float res2,
                                           int need_hessian, float out[32]) {
   const float x0 = pt.x, x1 = pt.y, x2 = pt.z;
@@ -403,7 +428,7 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
       pin[o] = !(i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]);
       pkey[o] = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
       ph[o] = ndt_hash(pkey[o], grid.mask);
-      pe[o] = pin[o] ? grid.table[ph[o]] : make_uint2(kInvalidKey, 0u);
+      pe[o] = pin[o] ? lk_table<STAGED>(grid, ph[o]) : make_uint2(kInvalidKey, 0u);
     }
 #pragma unroll
     for (int o = 0; o < NOFF; ++o) {
@@ -413,7 +438,7 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
         else if (pe[o].x != kInvalidKey) {  // collision: walk on from the next cell
           uint32_t h = (ph[o] + 1) & grid.mask;
           while (true) {
-            const uint2 e = grid.table[h];
+            const uint2 e = lk_table<STAGED>(grid, h);
             if (e.x == pkey[o]) { sl = (int)e.y; break; }
             if (e.x == kInvalidKey) break;
             h = (h + 1) & grid.mask;
@@ -433,21 +458,33 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
       const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
       if (i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]) continue;
       const uint32_t key = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
-      slot = ndt_lookup(grid, key);
+      slot = ndt_lookup<STAGED>(grid, key);
     }
-    if (slot < 0) continue;
-    if (slot & (int)kNdtRejected) {  // nr_points = -1 upstream: invisible to DIRECT*, still in the KDTREE cloud
-      if (MODE != 0) continue;
-      slot &= ~(int)kNdtRejected;
+    // DIRECT1 / DIRECT7 run branch-free: a neighbour without a usable voxel still goes through the
+    // arithmetic on record 0 and every update is a select.  At warp level the body executed for all
+    // seven neighbours anyway (some lane always has a hit); without the divergence bookkeeping
+    // (BSSY / BSYNC / BRA were 14 % of the instructions) the seven bodies also overlap.
+    bool valid = true;
+    if (kBatchProbes) {
+      valid = slot >= 0 && !(slot & (int)kNdtRejected);  // nr_points = -1 upstream: invisible to DIRECT*
+      slot = valid ? slot : 0;
+    } else {
+      if (slot < 0) continue;
+      if (slot & (int)kNdtRejected) {  // ... but still in the KDTREE cloud
+        if (MODE != 0) continue;
+        slot &= ~(int)kNdtRejected;
+      }
+      if (MODE == 0) {  // radiusSearch over the voxel centroids, d2 < resolution^2
+        const float4 c = lk_f4<STAGED>(grid, grid.s_centroids, grid.centroids, (uint32_t)slot);
+        if (!(l2_simple(xt0, xt1, xt2, c.x, c.y, c.z) < res2)) continue;
+      }
     }
-    if (MODE == 0) {  // radiusSearch over the voxel centroids, d2 < resolution^2
-      const float4 c = grid.centroids[slot];
-      if (!(l2_simple(xt0, xt1, xt2, c.x, c.y, c.z) < res2)) continue;
-    }
-    const float4* vp = reinterpret_cast<const float4*>(grid.voxels + slot);
-    const float4 ra = vp[0], rb = vp[1], rc = vp[2];  // hi0 hi1 hi2 lo0 | lo1 lo2 C00 C01 | C02 C11 C12 C22
+    const float4* vp = reinterpret_cast<const float4*>(grid.voxels);
+    const uint32_t v16 = (uint32_t)slot * 3u;  // 48-byte records = 3 x 16 bytes
+    const float4 ra = lk_f4<STAGED>(grid, grid.s_voxels, vp, v16), rb = lk_f4<STAGED>(grid, grid.s_voxels, vp, v16 + 1u),
+                 rc = lk_f4<STAGED>(grid, grid.s_voxels, vp, v16 + 2u);  // hi0 hi1 hi2 lo0 | lo1 lo2 C00 C01 | C02 C11 C12 C22
     const float C00 = rb.z, C01 = rb.w, C02 = rc.x, C11 = rc.y, C12 = rc.z, C22 = rc.w;
-    ++hits;
+    hits += valid ? 1 : 0;
     // q = float(double(x') - mean): (x' - hi) is exact for points within a few voxels of the mean
     const float q0 = __fsub_rn(__fsub_rn(xt0, ra.x), ra.w), q1 = __fsub_rn(__fsub_rn(xt1, ra.y), rb.x), q2 = __fsub_rn(__fsub_rn(xt2, ra.z), rb.y);
     const float cq0 = __fadd_rn(__fadd_rn(__fmul_rn(q0, C00), __fmul_rn(q1, C01)), __fmul_rn(q2, C02));
@@ -459,32 +496,35 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
     const float t1 = __fmul_rn(d1h, ex);
     const float sinc = __fadd_rn(t1, fmaf(d1l, ex, fmaf(d1h, ex, -t1)));
     float e = __fmul_rn(gauss_d2, ex);
-    if (e > 1.f || e < 0.f || e != e) continue;  // upstream returns 0 for this hit (score included)
-    score = __fsub_rn(score, sinc);
+    const bool ok = valid && !(e > 1.f || e < 0.f || e != e);  // upstream returns 0 for such a hit (score included)
+    if (!kBatchProbes && !ok) continue;
+    const float nscore = __fsub_rn(score, sinc);
     // e = float(e * d1)
     const float t2 = __fmul_rn(d1h, e);
     e = __fadd_rn(t2, fmaf(d1l, e, fmaf(d1h, e, -t2)));
-    v0 = fmaf(e, cq0, v0); v1 = fmaf(e, cq1, v1); v2 = fmaf(e, cq2, v2);
+    const float n0 = fmaf(e, cq0, v0), n1 = fmaf(e, cq1, v1), n2 = fmaf(e, cq2, v2);
+    score = ok ? nscore : score;
+    v0 = ok ? n0 : v0; v1 = ok ? n1 : v1; v2 = ok ? n2 : v2;
     if (need_hessian) {
       const float ed = __fmul_rn(e, gauss_d2);
-      m00 += e * C00 - ed * cq0 * cq0; m01 += e * C01 - ed * cq0 * cq1; m02 += e * C02 - ed * cq0 * cq2;
-      m11 += e * C11 - ed * cq1 * cq1; m12 += e * C12 - ed * cq1 * cq2; m22 += e * C22 - ed * cq2 * cq2;
+      const float h00 = m00 + (e * C00 - ed * cq0 * cq0), h01 = m01 + (e * C01 - ed * cq0 * cq1), h02 = m02 + (e * C02 - ed * cq0 * cq2);
+      const float h11 = m11 + (e * C11 - ed * cq1 * cq1), h12 = m12 + (e * C12 - ed * cq1 * cq2), h22 = m22 + (e * C22 - ed * cq2 * cq2);
+      m00 = ok ? h00 : m00; m01 = ok ? h01 : m01; m02 = ok ? h02 : m02;
+      m11 = ok ? h11 : m11; m12 = ok ? h12 : m12; m22 = ok ? h22 : m22;
     }
   }
-#pragma unroll
-  for (int k = 0; k < 32; ++k) out[k] = 0.f;
   if (!hits) return;
-  out[28] = (float)hits;
-  out[0] = score;
+  out[28] += (float)hits;
+  out[0] += score;
   // point_gradient columns 3..5: j3 = (0, a.x, b.x), j4 = (c.x, d.x, e.x), j5 = (f.x, g.x, h.x)
   auto dotj = [&](int r) { return s.j_ang[r][0] * x0 + s.j_ang[r][1] * x1 + s.j_ang[r][2] * x2; };
   const float j3y = dotj(0), j3z = dotj(1);
   const float j4x = dotj(2), j4y = dotj(3), j4z = dotj(4);
   const float j5x = dotj(5), j5y = dotj(6), j5z = dotj(7);
-  out[1] = v0; out[2] = v1; out[3] = v2;
-  out[4] = v1 * j3y + v2 * j3z;
-  out[5] = v0 * j4x + v1 * j4y + v2 * j4z;
-  out[6] = v0 * j5x + v1 * j5y + v2 * j5z;
+  out[1] += v0; out[2] += v1; out[3] += v2;
+  out[4] += v1 * j3y + v2 * j3z;
+  out[5] += v0 * j4x + v1 * j4y + v2 * j4z;
+  out[6] += v0 * j5x + v1 * j5y + v2 * j5z;
   if (!need_hessian) return;
   // M J_k for the rotational columns
   const float a0 = m01 * j3y + m02 * j3z, a1 = m11 * j3y + m12 * j3z, a2 = m12 * j3y + m22 * j3z;                          // M j3
@@ -498,17 +538,17 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
   const float vh44 = v0 * doth(6) + v1 * doth(7) + v2 * doth(8);
   const float vh45 = v0 * doth(9) + v1 * doth(10) + v2 * doth(11);
   const float vh55 = v0 * doth(12) + v1 * doth(13) + v2 * doth(14);
-  out[hidx(0, 0)] = m00; out[hidx(0, 1)] = m01; out[hidx(0, 2)] = m02;
-  out[hidx(1, 1)] = m11; out[hidx(1, 2)] = m12; out[hidx(2, 2)] = m22;
-  out[hidx(0, 3)] = a0; out[hidx(1, 3)] = a1; out[hidx(2, 3)] = a2;
-  out[hidx(0, 4)] = b0; out[hidx(1, 4)] = b1; out[hidx(2, 4)] = b2;
-  out[hidx(0, 5)] = e0; out[hidx(1, 5)] = e1; out[hidx(2, 5)] = e2;
-  out[hidx(3, 3)] = j3y * a1 + j3z * a2 + vh33;
-  out[hidx(3, 4)] = j3y * b1 + j3z * b2 + vh34;
-  out[hidx(3, 5)] = j3y * e1 + j3z * e2 + vh35;
-  out[hidx(4, 4)] = j4x * b0 + j4y * b1 + j4z * b2 + vh44;
-  out[hidx(4, 5)] = j4x * e0 + j4y * e1 + j4z * e2 + vh45;
-  out[hidx(5, 5)] = j5x * e0 + j5y * e1 + j5z * e2 + vh55;
+  out[hidx(0, 0)] += m00; out[hidx(0, 1)] += m01; out[hidx(0, 2)] += m02;
+  out[hidx(1, 1)] += m11; out[hidx(1, 2)] += m12; out[hidx(2, 2)] += m22;
+  out[hidx(0, 3)] += a0; out[hidx(1, 3)] += a1; out[hidx(2, 3)] += a2;
+  out[hidx(0, 4)] += b0; out[hidx(1, 4)] += b1; out[hidx(2, 4)] += b2;
+  out[hidx(0, 5)] += e0; out[hidx(1, 5)] += e1; out[hidx(2, 5)] += e2;
+  out[hidx(3, 3)] += j3y * a1 + j3z * a2 + vh33;
+  out[hidx(3, 4)] += j3y * b1 + j3z * b2 + vh34;
+  out[hidx(3, 5)] += j3y * e1 + j3z * e2 + vh35;
+  out[hidx(4, 4)] += j4x * b0 + j4y * b1 + j4z * b2 + vh44;
+  out[hidx(4, 5)] += j4x * e0 + j4y * e1 + j4z * e2 + vh45;
+  out[hidx(5, 5)] += j5x * e0 + j5y * e1 + j5z * e2 + vh55;
 }
 
 // Transposing warp reduction of 32 floats per lane: afterwards lane l holds in v[0] the sum over
@@ -588,6 +628,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
     const long long ts0 = clock64();
     // ---- stage the target grid in shared memory when it fits
     NdtLookup look;
+    bool grid_staged = false;
     {
       const uint32_t n_rec = job.grid.gmeta->n_records, cap = job.grid.gmeta->table_cap;
       const size_t table_bytes = (size_t)cap * sizeof(uint2), vox_bytes = (size_t)n_rec * sizeof(NdtVoxel);
@@ -609,10 +650,16 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         look.table = reinterpret_cast<const uint2*>(stage);
         look.voxels = reinterpret_cast<const NdtVoxel*>(stage + table_bytes);
         look.centroids = reinterpret_cast<const float4*>(stage + table_bytes + vox_bytes);
+        look.s_table = (uint32_t)__cvta_generic_to_shared(stage);
+        look.s_voxels = look.s_table + (uint32_t)table_bytes;
+        look.s_centroids = look.s_voxels + (uint32_t)vox_bytes;
+        grid_staged = true;
       } else {
         look.table = job.grid.table;
         look.voxels = job.grid.voxels;
         look.centroids = job.grid.centroids;
+        look.s_table = look.s_voxels = look.s_centroids = 0u;
+        grid_staged = false;
       }
     }
     if (tid < 32) {
@@ -650,17 +697,40 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       const float gd2 = (float)s.gauss_d2;
       double accd = 0.0;  // lane l accumulates accumulator l of this warp's point groups
       if (gp.any && !gp.overflow) {
-        // 32-point groups dealt round-robin over the group's warps
-        for (int q = warp * G + rank; q < n_groups32; q += G * kAlignWarps) {
+        // 32-point groups dealt round-robin over the group's warps.  A lane keeps float partial sums
+        // of up to kLaneGroup of its points before the warp-transposed reduction folds them into the
+        // double accumulator: with one SM per registration a lane sees ~90 points per pass and the
+        // 31-shuffle reduction is paid once per kLaneGroup of them.  (With all 148 SMs on one
+        // registration a warp has at most one group per pass: nothing changes there, bit for bit.)
+        float vals[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) vals[k] = 0.f;
+        int pending = 0;
+        // the source point of the NEXT group is requested before the current one is processed: with
+        // 16 warps per SM an L2 / HBM load issued at the point of use is not hidden (ncu: long
+        // scoreboard was the top stall of the one-CTA-per-registration configuration)
+        const int qstride = G * kAlignWarps;
+        int q = warp * G + rank;
+        float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < n_groups32 && (q << 5) + lane < n_src) pt_next = __ldg(job.src + (q << 5) + lane);
+        for (; q < n_groups32; q += qstride) {
           const int i = (q << 5) + lane;
-          float vals[32];
+          const float4 pt = pt_next;
+          const int in = ((q + qstride) << 5) + lane;
+          if (q + qstride < n_groups32 && in < n_src) pt_next = __ldg(job.src + in);
           if (i < n_src) {
-            const float4 pt = __ldg(job.src + i);
-            ndt_point<MODE>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);
-          } else {
+            if (grid_staged) ndt_point<MODE, true>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);
+            else ndt_point<MODE, false>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);
+          }
+          if (++pending == kLaneGroup) {
+            warp_transpose_reduce32(vals, lane);
+            accd += (double)vals[0];
 #pragma unroll
             for (int k = 0; k < 32; ++k) vals[k] = 0.f;
+            pending = 0;
           }
+        }
+        if (pending) {
           warp_transpose_reduce32(vals, lane);
           accd += (double)vals[0];
         }

@@ -197,6 +197,14 @@ def test_fitness_exact_nn(eng, oracle, scans):
             assert abs(got - want) <= 1e-12 * want
         frac = reg.getInlierFraction(0.5)
         assert 0.0 <= frac <= 1.0
+    # publish_scan_matching_status [REF apps/scan_matching_odometry_nodelet.cpp:318-332]: matching_error
+    # and inlier fraction (k_sq_dists[0] < 0.5^2) of the aligned cloud after a real align
+    ref.align(None)
+    aligned = reg.align(None, want_aligned=True)
+    for max_dist in (0.5, 0.1):
+        want = ref.inlierFraction(aligned, max_dist)
+        got = reg.getInlierFraction(max_dist)
+        assert abs(got - want) <= 2.0 / len(aligned), (got, want)
 
 
 def test_odometry_keyframe_promotion(eng, oracle, scans):

@@ -27,6 +27,9 @@ def wrap(obj, name):
 for n in ("setInputTarget", "setInputSource", "align", "hasConverged", "getFinalTransformation", "promoteSourceToTarget"):
     wrap(reg, n)
 wrap(pre, "downsample")
+timing = len(sys.argv) > 2 and sys.argv[2] == "timing"
+if timing:
+    reg.setTiming(True)
 for rep in range(2):
     acc.clear(); cnt.clear()
     odo.keyframe = None
@@ -36,6 +39,9 @@ for rep in range(2):
         odo.matching(0.1 * k, f)
     tot = time.perf_counter() - t0
 print(f"{frames} frames: {tot / frames * 1e6:.1f} us / frame")
+if timing:
+    c = reg.counters()
+    print(f"event-timed align kernel: {c['align_kernel_ms'] / c['timed_aligns'] * 1e3:.1f} us over {c['timed_aligns']} launches")
 for k, v in sorted(acc.items(), key=lambda x: -x[1]):
     print(f"  {k:28s} calls {cnt[k]:5d}  {v / frames * 1e6:8.1f} us/frame  {v / cnt[k] * 1e6:8.1f} us/call")
 print(f"  python + numpy outside the calls: {(tot - sum(acc.values())) / frames * 1e6:.1f} us/frame")
