@@ -5,6 +5,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include <new>
@@ -74,7 +75,18 @@ struct b200reg_handle {
   DevBuf<int> gicp_corr;
   DevBuf<GicpJob> gicp_jobs;
 
-  // loop-closure batches: keyframe cloud cache + batch staging
+  // loop-closure batches: keyframe cloud cache + batch staging.  Target structures of different
+  // keyframes are independent and each build is a short chain of latency-bound kernels, so they are
+  // issued round-robin on kBuildLanes side streams, each with its own builders.
+  static constexpr int kBuildLanes = 4;
+  struct BuildLane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    NdtGrid grid;
+    NnGrid nn;
+  };
+  BuildLane lanes[kBuildLanes];
+  cudaEvent_t ev_fork = nullptr;
   std::map<long long, CachedCloud> cache;
   DevBuf<b200reg_result> batch_results;
   DevBuf<FitJob> fit_jobs;
@@ -543,6 +555,13 @@ int b200reg_destroy(b200reg_handle* h) {
   h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_jobs.release();
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
+  for (auto& ln : h->lanes) {
+    if (ln.st) { cudaStreamSynchronize(ln.st); cudaStreamDestroy(ln.st); }
+    if (ln.done) cudaEventDestroy(ln.done);
+    ln.grid.release();
+    ln.nn.release();
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   h->batch_results.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
   delete h;
   return B200REG_OK;
@@ -931,15 +950,36 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     if (!tgt[i] || !src[i]) { h->err = "align_batch: pair " + std::to_string(i) + " names a cloud id that was never put"; return B200REG_E_INVALID; }
     if (tgt[i]->n == 0) { h->err = "align_batch: pair " + std::to_string(i) + ": Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
   }
-  for (size_t i = 0; i < n_pairs; ++i) {
-    CachedCloud& c = *tgt[i];
-    if (!c.has_ndt || c.ndt_res != res) {
-      B200_CUDA_TRY(cache_build_ndt(h->stream, h->grid, c, res));
-      h->grid_stale = true;
+  {
+    // fork: the lanes start after everything already queued on the handle's stream (cloud uploads)
+    std::vector<CachedCloud*> todo;
+    for (size_t i = 0; i < n_pairs; ++i) {
+      CachedCloud& c = *tgt[i];
+      const bool need = !c.has_ndt || c.ndt_res != res || (with_fitness && !c.has_nn);
+      if (need && std::find(todo.begin(), todo.end(), &c) == todo.end()) todo.push_back(&c);
     }
-    if (with_fitness && !c.has_nn) {
-      B200_CUDA_TRY(cache_build_nn(h->stream, h->nn, c));
-      h->nn_stale = true;
+    if (!todo.empty()) {
+      if (!h->ev_fork) B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      B200_CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+      const int n_lanes = (int)std::min<size_t>(todo.size(), (size_t)b200reg_handle::kBuildLanes);
+      for (int l = 0; l < n_lanes; ++l) {
+        auto& ln = h->lanes[l];
+        if (!ln.st) {
+          B200_CUDA_TRY(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+          B200_CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        }
+        B200_CUDA_TRY(cudaStreamWaitEvent(ln.st, h->ev_fork, 0));
+      }
+      for (size_t k = 0; k < todo.size(); ++k) {
+        auto& ln = h->lanes[k % n_lanes];
+        CachedCloud& c = *todo[k];
+        if (!c.has_ndt || c.ndt_res != res) B200_CUDA_TRY(cache_build_ndt(ln.st, ln.grid, c, res));
+        if (with_fitness && !c.has_nn) B200_CUDA_TRY(cache_build_nn(ln.st, ln.nn, c));
+      }
+      for (int l = 0; l < n_lanes; ++l) {  // join
+        B200_CUDA_TRY(cudaEventRecord(h->lanes[l].done, h->lanes[l].st));
+        B200_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->lanes[l].done, 0));
+      }
     }
   }
   // ---- jobs (pairs with an empty source never reach the kernel: PCL's initCompute fails, converged_ stays false)
