@@ -278,34 +278,42 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     h_np = h_raw.numpy()
     host_clouds = [h_np[k, : counts[k]] for k in range(F)]
     dev_clouds = [eng.DeviceCloud(d_raw[k].data_ptr(), counts[k], d_raw) for k in range(F)]
-    d_ds = torch.empty((rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
-    ds_buf = eng.DeviceCloud(d_ds.data_ptr(), rays, d_ds)
+    d_ds = torch.empty((3, rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
+    ds_bufs = [eng.DeviceCloud(d_ds[j].data_ptr(), rays, d_ds) for j in range(3)]
+    ds_buf = ds_bufs[0]
 
     def new_pipeline():
         pre = eng.Prefilter(PREFILTER_PARAMS, device=dev, out=DEVNULL)
         odo = eng.ScanMatchingOdometry(odom_params, device=dev, out=DEVNULL)
         return pre, odo
 
+    # The front end runs as the reference runs it: prefiltering and scan matching are two nodelets
+    # joined by a topic, so the filter of scan k+1 is in flight while scan k is matched (eng.FrontEnd).
+    # The filter handle's persistent kernel is given args.filter_sms SMs, the registration the rest.
+    def new_front_end(bufs):
+        pre, odo = new_pipeline()
+        return eng.FrontEnd(pre, odo, bufs, filter_sms=args.filter_sms), pre, odo
+
     # ---- device-resident leg (value) + roofline of the align kernel
-    pre_d, odo_d = new_pipeline()
+    fe_d, pre_d, odo_d = new_front_end(ds_bufs)
     odo_d.registration.setTiming(True)
 
     def step_device(i):
         odo_d.keyframe = None  # restart the sequence; engine buffers stay allocated
-        alg_bytes, evals, hits = 0, 0, 0
-        for k, cloud in enumerate(dev_clouds):
-            filtered = pre_d.downsample(cloud, out=ds_buf)
-            odo_d.matching(0.1 * k, filtered)
+        acc = dict(alg_bytes=0, evals=0, hits=0)
+
+        def on_frame(k, filtered):
             if k > 0:
                 r = odo_d.registration.getResult()
                 # NDT pass: 16 B per source point + 48 B per (point, voxel) hit.  GICP: a linearize pass reads the
                 # point, its covariance, the correspondence's point and covariance and writes the Mahalanobis
                 # matrix (16 + 48 + 16 + 48 + 48 B per correspondence); an error pass re-reads 16 + 16 + 48 B
                 # (GICP outer iteration) — approximated with hits = linearize correspondences
-                alg_bytes += (16 * filtered.n * r["evaluations"] + 48 * r["hits"]) if is_ndt else (16 * filtered.n * r["evaluations"] + 160 * r["hits"])
-                evals += r["evaluations"]
-                hits += r["hits"]
-        return dict(alg_bytes=alg_bytes, evals=evals, hits=hits, keyframes=odo_d.num_keyframes)
+                acc["alg_bytes"] += (16 * filtered.n * r["passes"] + 48 * r["hits"]) if is_ndt else (16 * filtered.n * r["passes"] + 160 * r["hits"])
+                acc["evals"] += r["passes"]
+                acc["hits"] += r["hits"]
+        fe_d.run(dev_clouds, on_frame=on_frame)
+        return dict(alg_bytes=acc["alg_bytes"], evals=acc["evals"], hits=acc["hits"], keyframes=odo_d.num_keyframes)
 
     sampler = ClockSampler(dev)
     with sampler:
@@ -323,30 +331,39 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     launches_timed = (c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)
 
     # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out
-    pre_h, odo_h = new_pipeline()
     # caller-owned output clouds of the filter (pcl::Filter::filter(output)), page-locked; three in
     # rotation because the odometry keeps the keyframe's cloud while the next scans are filtered
     h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
+    fe_h, pre_h, odo_h = new_front_end([h_out[j] for j in range(3)])
 
     def step_host(i):
         odo_h.keyframe = None
-        h2d = d2h = 0
-        for k, cloud in enumerate(host_clouds):
-            filtered = pre_h.downsample(cloud, out=h_out[k % 3])
-            odo_h.matching(0.1 * k, filtered)
-            h2d += cloud.nbytes + filtered.nbytes
-            d2h += filtered.nbytes + 128
-        return dict(h2d=h2d, d2h=d2h)
+        acc = dict(h2d=0, d2h=0)
+
+        def on_frame(k, filtered):
+            # raw scan up, filtered cloud down (the /filtered_points message), filtered cloud up again
+            # (setInputSource of the odometry nodelet), result record down
+            acc["h2d"] += host_clouds[k].nbytes + filtered.nbytes
+            acc["d2h"] += filtered.nbytes + 128
+        fe_h.run(host_clouds, on_frame=on_frame)
+        return acc
     sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), steps, warmup)
     e2e_value = world * steps * regs_per_step / sec_h
 
     # ---- parity of the two legs (same inputs -> same poses) and odometry sanity vs ground truth
     nchk = min(50, F)
-    pre_c, odo_c = new_pipeline()
-    poses_dev = run_sequence(pre_c, odo_c, dev_clouds[:nchk], out_buf=ds_buf)
-    pre_c2, odo_c2 = new_pipeline()
-    poses_host = run_sequence(pre_c2, odo_c2, host_clouds[:nchk])
+    fe_c, _, _ = new_front_end(ds_bufs)
+    poses_dev = fe_c.run(dev_clouds[:nchk])
+    fe_c2, _, _ = new_front_end([h_out[j] for j in range(3)])
+    poses_host = fe_c2.run(host_clouds[:nchk])
     legs_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_host))
+    # the pipelined front end against the plain loop (filter, then match, one scan at a time) on the same SM budgets
+    pre_s, odo_s = new_pipeline()
+    if pre_s.filter is not None and args.filter_sms:
+        pre_s.filter.setSmBudget(args.filter_sms)
+        odo_s.registration.setSmBudget(148 - args.filter_sms)
+    poses_seq = run_sequence(pre_s, odo_s, dev_clouds[:nchk], out_buf=ds_buf)
+    pipeline_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_seq))
     P0 = synth.traj_kitti_like(5000 * rank)
     gt = np.linalg.inv(P0) @ synth.traj_kitti_like(nchk - 1 + 5000 * rank)
     drift = float(np.linalg.norm(poses_dev[nchk - 1][:3, 3] - gt[:3, 3]))
@@ -366,6 +383,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                    "frames_per_step": F, "points_per_scan": int(np.mean(counts)),
                    "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64" if is_ndt else "FAST_GICP-equivalent k 20, max corr 2.5 m, eps 0.01, max_iter 64, LM, PLANE",
                    "l2": f"each step streams {F} distinct scans ({F * rays * 16 / 1e9:.1f} GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
+                   "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms} SMs, registration {148 - args.filter_sms} SMs" if args.filter_sms else "sequential: filter, then match",
                    "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
         "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
                 "wall_ms_per_step": 1e3 * wall_h / steps},
@@ -376,7 +394,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                      "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
-        "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
+        "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "pipelined_equals_sequential_first_frames": bool(pipeline_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
                    "wall_ms_per_step": 1e3 * wall_d / steps},
     }
     del d_raw, h_raw
@@ -453,7 +471,7 @@ def bench_loop(ctx, steps, warmup):
     value = steps * n_pairs / sec_d
     res = last["res"]
     local = last["local"]
-    alg_bytes = float(sum(16 * kf_n[slot_of[int(p["source_id"])]] * int(r["evaluations"]) + 48 * int(r["hits"]) for p, r in zip(mine, local)))
+    alg_bytes = float(sum(16 * kf_n[slot_of[int(p["source_id"])]] * int(r["passes"]) + 48 * int(r["hits"]) for p, r in zip(mine, local)))
     align_ms = float(np.mean([s["align_kernel_ms"] for s in st_d]))
     fit_ms = float(np.mean([s["fitness_ms"] for s in st_d]))
     peak, peak_kind = load_peaks()
@@ -497,7 +515,7 @@ def bench_loop(ctx, steps, warmup):
                    "points_per_keyframe": int(np.mean(kf_n)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
                    "sharding": "whole targets per rank, one all-gather of 104-byte result records", "pairs_this_rank": int(len(mine)),
                    "l2": f"{len(specs)} distinct keyframe clouds ({sum(kf_n) * 16 / 1e9:.2f} GB) per rank: inputs larger than L2",
-                   "passes_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
+                   "passes_per_registration": float(np.mean(res["passes"])), "reference_evaluations_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
         "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7> (one CTA per registration)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
@@ -527,6 +545,7 @@ def main():
     ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
     ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
+    ap.add_argument("--filter-sms", type=int, default=40, help="SMs given to the prefilter handle's persistent kernel in the pipelined front end (the registration takes the rest)")
     ap.add_argument("--gicp-frames", type=int, default=300, help="frames of the sequence the FAST_GICP leg runs per step")
     args = ap.parse_args()
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
+    "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_end", "b200reg_set_sm_budget",
     "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_get_batch_timing",
     "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
@@ -44,7 +45,7 @@ class Config(C.Structure):
 class Result(C.Structure):
     _fields_ = [
         ("transformation", C.c_float * 16), ("fitness", C.c_double), ("score", C.c_double), ("converged", C.c_int32),
-        ("iterations", C.c_int32), ("evaluations", C.c_int32), ("reserved", C.c_int32), ("hits", C.c_int64),
+        ("iterations", C.c_int32), ("evaluations", C.c_int32), ("passes", C.c_int32), ("hits", C.c_int64),
     ]
 
 
@@ -53,7 +54,7 @@ class Pair(C.Structure):
 
 
 RESULT_DTYPE = np.dtype([("transformation", np.float32, (16,)), ("fitness", np.float64), ("score", np.float64), ("converged", np.int32), ("iterations", np.int32),
-                         ("evaluations", np.int32), ("reserved", np.int32), ("hits", np.int64)])
+                         ("evaluations", np.int32), ("passes", np.int32), ("hits", np.int64)])
 PAIR_DTYPE = np.dtype([("target_id", np.int64), ("source_id", np.int64), ("guess", np.float32, (16,))])
 assert RESULT_DTYPE.itemsize == C.sizeof(Result) and PAIR_DTYPE.itemsize == C.sizeof(Pair)
 
@@ -105,6 +106,10 @@ def load():
     L.b200reg_get_inlier_fraction.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.b200reg_voxelgrid_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp, C.c_size_t, szp]
     L.b200reg_voxelgrid_filter_device.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp, szp]
+    L.b200reg_voxelgrid_filter_begin.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp, C.c_size_t]
+    L.b200reg_voxelgrid_filter_device_begin.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp]
+    L.b200reg_voxelgrid_filter_end.argtypes = [vp, szp]
+    L.b200reg_set_sm_budget.argtypes = [vp, C.c_int]
     L.b200reg_voxelgrid_last_layout.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.POINTER(C.c_int)]
     L.b200reg_cloud_put.argtypes = [vp, C.c_int64, vp, C.c_size_t, C.c_size_t]
     L.b200reg_cloud_put_device.argtypes = [vp, C.c_int64, vp, C.c_size_t]

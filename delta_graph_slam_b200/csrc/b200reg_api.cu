@@ -37,7 +37,8 @@ struct b200reg_handle {
   b200reg_config cfg;
   cudaStream_t stream = nullptr;
   std::string err;
-  int num_sm = kNumSM;
+  int num_sm = kNumSM;  // CTAs the cooperative kernels of this handle use (b200reg_set_sm_budget)
+  int dev_sm = kNumSM;  // SMs of the device
 
   // clouds (device, float4)
   DevBuf<float4> src, tgt, stage_in, stage_out, aligned;
@@ -51,6 +52,13 @@ struct b200reg_handle {
   DevBuf<VgCounts> vg_counts;
   DevBuf<unsigned int> vg_done;
   int vg_last_n = 0, vg_last_out = 0;
+  // filter call in flight (b200reg_voxelgrid_filter_begin .. _end)
+  struct VgPending {
+    bool active = false;
+    float* host_out = nullptr;  // caller's output cloud (host variant), nullptr for the device variant
+    size_t cap = 0;
+    bool zero_copy = false;     // the kernel stores the centroids straight into host_out (page-locked)
+  } vg_pending;
 
   // NDT
   NdtGrid grid;
@@ -533,7 +541,7 @@ int b200reg_create(const b200reg_config* cfg, b200reg_handle** out) {
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
   if (prop.major < 10 || !coop) { delete h; return B200REG_E_CUDA; }  // sm_100a only
-  h->num_sm = prop.multiProcessorCount;
+  h->num_sm = h->dev_sm = prop.multiProcessorCount < kNumSM ? prop.multiProcessorCount : kNumSM;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return B200REG_E_CUDA; }
   if (init_kernel_attributes(cfg->device) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return B200REG_E_CUDA; }
   if (cudaHostAlloc((void**)&h->mail, sizeof(HostMailbox), cudaHostAllocMapped) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return B200REG_E_CUDA; }
@@ -792,7 +800,7 @@ int b200reg_get_inlier_fraction(b200reg_handle* h, double max_dist, double* out)
 }
 
 // ---- VoxelGrid -------------------------------------------------------------------------------
-static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float leaf[3], unsigned min_pts, int dense, float4* d_out) {
+static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float leaf[3], unsigned min_pts, int dense, float4* d_out, float4* host_out = nullptr, size_t host_cap = 0) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   B200_CUDA_TRY(h->vg_id.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
@@ -809,52 +817,114 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
     B200_CUDA_TRY(cudaMemsetAsync(h->vg_done.p, 0, h->vg_done.cap * sizeof(unsigned int), h->stream));
   }
   k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
-                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1);
+                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1, host_out,
+                                                (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap));
   if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq);
   B200_CUDA_TRY(cudaGetLastError());
   h->vg_last_n = (int)n;
   return B200REG_OK;
 }
 
-int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out, size_t* n_out) {
-  if (!h || !leaf || !n_out || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
+// The filter as two halves.  begin: everything is enqueued on the handle's stream and the call
+// returns; end: wait for the point count the last kernel publishes through the mailbox.  The
+// synchronous entry points below are begin + end.
+int b200reg_voxelgrid_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out) {
+  if (!h || !leaf || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
   if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = vg_run(h, (const float4*)d_xyzw, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
-  if ((rc = wait_mail(h, &h->mail->vg_seq, h->vg_seq))) return rc;
-  *n_out = h->mail->vg.n_out;
-  h->vg_last_out = (int)h->mail->vg.n_out;
+  h->vg_pending = b200reg_handle::VgPending();
+  h->vg_pending.active = true;
   return B200REG_OK;
+}
+
+int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* out, size_t cap) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !leaf || (n && !xyzw)) return B200REG_E_INVALID;
+  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
+  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  // input: page-locked caller memory is read by DMA while this call has already returned (the caller
+  // keeps it unchanged until _end); pageable memory goes through the handle's pinned staging buffer,
+  // which is not touched again before the next _begin
+  B200_CUDA_TRY(h->stage_in.reserve(n ? n : 1));
+  B200_CUDA_TRY(h->stage_out.reserve(n ? n : 1));
+  if (n) {
+    if (stride == 16 && is_pinned_host(xyzw)) {
+      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      B200_CUDA_TRY(h->pin_in.reserve(n));
+      if (stride == 16) {
+        memcpy(h->pin_in.p, xyzw, n * 16);
+      } else {
+        const unsigned char* b = (const unsigned char*)xyzw;
+        for (size_t i = 0; i < n; ++i) {
+          const float* p = (const float*)(b + i * stride);
+          h->pin_in.p[i] = make_float4(p[0], p[1], p[2], 1.0f);
+        }
+      }
+      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, h->pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  // output: a page-locked caller cloud is written by the centroid kernel itself (mapped memory);
+  // min_points_per_voxel > 1 compacts on the device first, and pageable memory needs staging: both
+  // copy in _end
+  const bool zero_copy = out && cap && min_pts <= 1 && is_pinned_host(out);
+  if ((rc = vg_run(h, h->stage_in.p, n, leaf, min_pts, dense, h->stage_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
+  h->vg_pending.active = true;
+  h->vg_pending.host_out = out;
+  h->vg_pending.cap = cap;
+  h->vg_pending.zero_copy = zero_copy;
+  return B200REG_OK;
+}
+
+int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  if (!h->vg_pending.active) { h->err = "no filter call in flight on this handle"; return B200REG_E_STATE; }
+  const b200reg_handle::VgPending pend = h->vg_pending;
+  h->vg_pending.active = false;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = wait_mail(h, &h->mail->vg_seq, h->vg_seq))) return rc;
+  const size_t m = h->mail->vg.n_out;
+  *n_out = m;
+  h->vg_last_out = (int)m;
+  if (!pend.host_out && !pend.cap) return B200REG_OK;  // device variant
+  if (m > pend.cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
+  if (!m || pend.zero_copy) return B200REG_OK;
+  if (!pend.host_out) return B200REG_E_INVALID;
+  if (is_pinned_host(pend.host_out)) {
+    B200_CUDA_TRY(cudaMemcpyAsync(pend.host_out, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  } else {
+    B200_CUDA_TRY(h->pin_out.reserve(m));
+    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(pend.host_out, h->pin_out.p, m * 16);
+  }
+  return B200REG_OK;
+}
+
+int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  int rc = b200reg_voxelgrid_filter_device_begin(h, d_xyzw, n, leaf, min_pts, dense, d_out);
+  if (rc) return rc;
+  return b200reg_voxelgrid_filter_end(h, n_out);
 }
 
 int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* out, size_t cap,
                              size_t* n_out) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !leaf || !n_out || (n && !xyzw)) return B200REG_E_INVALID;
-  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  if (!n_out) return B200REG_E_INVALID;
   *n_out = 0;
-  int rc = set_device(h);
+  int rc = b200reg_voxelgrid_filter_begin(h, xyzw, n, stride, leaf, min_pts, dense, out, cap);
   if (rc) return rc;
-  if ((rc = upload_cloud(h, xyzw, n, stride, h->stage_in))) return rc;
-  B200_CUDA_TRY(h->stage_out.reserve(n ? n : 1));
-  size_t m = 0;
-  if ((rc = b200reg_voxelgrid_filter_device(h, (const float*)h->stage_in.p, n, leaf, min_pts, dense, (float*)h->stage_out.p, &m))) return rc;
-  *n_out = m;
-  if (m > cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
-  if (m) {
-    if (!out) return B200REG_E_INVALID;
-    if (is_pinned_host(out)) {
-      B200_CUDA_TRY(cudaMemcpyAsync(out, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-      B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    } else {
-      B200_CUDA_TRY(h->pin_out.reserve(m));
-      B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-      B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-      memcpy(out, h->pin_out.p, m * 16);
-    }
-  }
-  return B200REG_OK;
+  return b200reg_voxelgrid_filter_end(h, n_out);
 }
 
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_vox, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow) {
@@ -1204,6 +1274,17 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B200REG_OK;
+}
+
+int b200reg_set_sm_budget(b200reg_handle* h, int n_sm) {
+  if (!h || n_sm < 1) return B200REG_E_INVALID;
+  if (n_sm > h->dev_sm) n_sm = h->dev_sm;
+  h->num_sm = n_sm;
+  h->vg_sort.max_ctas = n_sm;
+  h->grid.sort.max_ctas = n_sm;
+  h->nn.sort.max_ctas = n_sm;
+  h->nn_src.sort.max_ctas = n_sm;
   return B200REG_OK;
 }
 

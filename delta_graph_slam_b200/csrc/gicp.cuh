@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     r.converged = s.converged;
     r.iterations = s.nr_iterations;
     r.evaluations = s.n_lin + s.n_err;
-    r.reserved = 0;
+    r.passes = s.n_lin + s.n_err;
     r.hits = (long long)s.hits;
     *job.result = r;
     if (job.result_host) {

@@ -41,7 +41,7 @@ constexpr int kAccStride = 32;
 constexpr int kStageBytes = 192 * 1024;  // dynamic shared memory for the staged grid
 constexpr int kLaneGroup = 4;             // points a lane sums in float before the warp reduction (batch mode)
 
-enum NdtPhase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_ITER = 2, PH_HESSIAN = 3, PH_DONE = 4, PH_EVAL_ONLY = 5 };
+enum NdtPhase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_ITER = 2, PH_DONE = 4, PH_EVAL_ONLY = 5 };
 
 struct NdtParams {
   int search;  // b200reg_nn_search
@@ -80,7 +80,7 @@ struct NdtShared {
   double score, g[6], H[36];
   double phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t, psi_t, d_psi_t;
   int step_iterations, open_interval, interval_converged;
-  int nr_iterations, converged, n_eval;
+  int nr_iterations, converged, n_eval, n_pass;
   double hits;
   double gauss_d1, gauss_d2;
   double trig[6][2];  // sin, cos of: float-rounded angles (T) [0..2], double angles (tables) [3..5]
@@ -268,6 +268,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
   const double* t = s.tot;
   s.n_eval++;
+  s.n_pass++;
   s.hits += t[28];
   s.new_pose = 0;
   bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
@@ -282,14 +283,16 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
       else go_loop_check = true;
       break;
     case PH_MT_ITER:
+      // A trial pass evaluates the Hessian as well: upstream ends the line search with
+      // computeHessian(x_t) at the LAST trial point — a whole extra pass over the cloud at the pose that
+      // was just evaluated.  Here that Hessian is already in the totals of the last trial pass (same
+      // transform, same tables, same arithmetic as a pass of its own), so the extra pass never runs;
+      // the Hessian of a trial that is not the last one is simply overwritten by the next.
       s.score = t[0];
       for (int i = 0; i < 6; ++i) s.g[i] = t[1 + i];
-      go_loop_check = true;
-      break;
-    case PH_HESSIAN:
       for (int i = 0; i < 6; ++i)
         for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = t[hidx(i, j)];
-      go_newton_end = true;
+      go_loop_check = true;
       break;
     default:
       return;
@@ -325,15 +328,13 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
         s.a_t = fmax(s.a_t, step_min);
         for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
         s.phase = PH_MT_ITER;
-        s.need_hessian = 0;
+        s.need_hessian = 1;
         s.new_pose = 1;
         return;
       }
-      if (s.step_iterations) {  // computeHessian at x_t (same transform and tables as the last pass)
-        s.phase = PH_HESSIAN;
-        s.need_hessian = 1;
-        return;
-      }
+      // computeHessian at x_t: taken from the last trial pass (see PH_MT_ITER above); it counts as an
+      // evaluation of the reference's algorithm, not as a pass of ours
+      if (s.step_iterations) s.n_eval++;
       go_newton_end = true;
     }
     if (go_newton_end) {
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         s.gauss_d1 = -log(c1 + c2) - d3;
         s.gauss_d2 = -2 * log((-log(c1 * exp(-0.5) + c2) - d3) / s.gauss_d1);
         for (int i = 0; i < 6; ++i) s.p[i] = job.p0[i];
-        s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.hits = 0.0;
+        s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.n_pass = 0; s.hits = 0.0;
         s.score = 0.0;
         s.need_hessian = 1;
         s.phase = job.eval_only ? PH_EVAL_ONLY : PH_INIT;
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
     while (true) {
       // ---- pass
       const long long t0 = clock64();
-      const int need_h = s.need_hessian;
+      constexpr int need_h = 1;  // every pass evaluates the Hessian (see ndt_step, PH_MT_ITER)
       const float d1h = (float)s.gauss_d1, d1l = (float)(s.gauss_d1 - (double)d1h);
       const float gd2 = (float)s.gauss_d2;
       double accd = 0.0;  // lane l accumulates accumulator l of this warp's point groups
@@ -786,6 +787,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         if (tid == 0) {
           if (s.phase == PH_EVAL_ONLY) {
             s.n_eval++;
+            s.n_pass++;
             s.hits += s.tot[28];
             s.phase = PH_DONE;
             s.new_pose = 0;
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       r.converged = s.converged;
       r.iterations = s.nr_iterations;
       r.evaluations = s.n_eval;
-      r.reserved = 0;
+      r.passes = s.n_pass;
       r.hits = (long long)s.hits;
       *job.result = r;
       if (job.result_host) {

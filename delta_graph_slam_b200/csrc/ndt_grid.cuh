@@ -62,8 +62,7 @@ struct NdtLeafArgs {
   NdtGridMeta* gmeta;
   NdtVoxel* voxels;
   float4* centroids;
-  uint32_t* rec_key;   // per record: linear voxel index
-  uint32_t* rec_flag;  // per record: 0 or kNdtRejected
+  uint32_t* rec_key;   // scratch, one entry per occupied slot: record index | kNdtRejected, or 0xFFFFFFFF (k_ndt_table)
   uint2* table;
   int32_t* leaf_n;
   double *leaf_mean, *leaf_cov, *leaf_icov;
@@ -79,7 +78,7 @@ struct NdtGrid {
   DevBuf<int32_t> leaf_n;
   DevBuf<NdtVoxel> voxels, stage_vox;
   DevBuf<float4> centroids, stage_cen;
-  DevBuf<uint32_t> rec_key, rec_flag;
+  DevBuf<uint32_t> rec_key;
   DevBuf<uint2> table;
   DevBuf<NdtGridMeta> gmeta;
   int n_points = 0;
@@ -87,7 +86,7 @@ struct NdtGrid {
 
   void release() {
     sort.release(); sums.release(); csum.release(); leaf_mean.release(); leaf_cov.release(); leaf_icov.release(); leaf_n.release(); voxels.release(); centroids.release(); stage_vox.release(); stage_cen.release();
-    rec_key.release(); rec_flag.release(); table.release(); gmeta.release();
+    rec_key.release(); table.release(); gmeta.release();
   }
 
   NdtGridView view() const {
@@ -118,15 +117,14 @@ struct NdtGrid {
     if ((e = stage_vox.reserve(nn)) != cudaSuccess) return e;
     if ((e = stage_cen.reserve(nn)) != cudaSuccess) return e;
     if ((e = centroids.reserve(max_rec)) != cudaSuccess) return e;
-    if ((e = rec_key.reserve(max_rec)) != cudaSuccess) return e;
-    if ((e = rec_flag.reserve(max_rec)) != cudaSuccess) return e;
+    if ((e = rec_key.reserve(nn)) != cudaSuccess) return e;
     if ((e = table.reserve(cap)) != cudaSuccess) return e;
     if ((e = gmeta.reserve(1)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(gmeta.p, 0, sizeof(NdtGridMeta), st)) != cudaSuccess) return e;
     NdtLeafArgs a;
     a.pts = d_pts; a.vals_a = sort.vals_a.p; a.vals_b = sort.vals_b.p; a.meta = sort.meta.p; a.vox_start = sort.vox_start.p; a.vox_key = sort.vox_key.p;
     a.min_points = 6; a.eig_mult = 0.01;
-    a.gmeta = gmeta.p; a.voxels = voxels.p; a.centroids = centroids.p; a.rec_key = rec_key.p; a.rec_flag = rec_flag.p; a.table = table.p;
+    a.gmeta = gmeta.p; a.voxels = voxels.p; a.centroids = centroids.p; a.rec_key = rec_key.p; a.table = table.p;
     a.leaf_n = leaf_n.p; a.leaf_mean = leaf_mean.p; a.leaf_cov = leaf_cov.p; a.leaf_icov = leaf_icov.p;
     if ((e = launch_ndt_leaf_stats(st, a, stage_vox.p, stage_cen.p, sums.p, csum.p)) != cudaSuccess) return e;
     built = true;

@@ -10,46 +10,70 @@
 
 namespace b200 {
 
-// pass 1: one CTA per occupied voxel (grid-stride).  All 256 threads gather 256 points of the run
-// into shared memory at once (one memory latency, zero padded), then lane a in 0..8 of warp 0 adds
-// statistic a (sum x y z, sum xx xy xz yy yz zz) point by point IN INPUT ORDER — nine independent
-// serial double chains, each bit-identical to the reference's per-leaf accumulation (adding the
-// zero padding changes nothing) — while lanes 9..11 do the float centroid sums.
-static __global__ void __launch_bounds__(256) k_ndt_leaf_sums(NdtLeafArgs a, double* __restrict__ sums /*[n_vox][9]*/, float* __restrict__ csum /*[n_vox][3]*/) {
-  __shared__ float4 s_pts[256];
+// pass 1: one WARP per occupied voxel (grid-stride over warps).  The warp gathers up to 128 points of
+// the run at once (one memory latency, four independent loads per lane) into its own shared-memory
+// row and requests the NEXT 128 before it starts on these; lane a in 0..8 then adds statistic a
+// (sum x y z, sum xx xy xz yy yz zz) point by point IN INPUT ORDER — nine independent serial double
+// chains, each bit-identical to the reference's per-leaf accumulation — while lanes 9..11 do the
+// float centroid sums.  Eight points per step are prepared (LDS, F2F, DMUL) ahead of the dependent
+// DADD chain, which is what bounds a voxel: ~11 cycles per point (the densest 1 m voxel of an HDL-64
+// scan holds ~500 points).  Rows are zero padded to a multiple of eight: x + (+0) = x exactly.
+constexpr int kLeafWarps = 8;
+constexpr int kLeafChunk = 128;
+static __global__ void __launch_bounds__(kLeafWarps * 32) k_ndt_leaf_sums(NdtLeafArgs a, double* __restrict__ sums /*[n_vox][9]*/, float* __restrict__ csum /*[n_vox][3]*/) {
+  __shared__ __align__(16) float s_pts[kLeafWarps][kLeafChunk * 4];
   const uint32_t* vals = sorted_in_b(a.meta) ? a.vals_b : a.vals_a;
   const int n_vox = (int)a.meta->n_vox;
-  const int tid = threadIdx.x, lane = tid & 31;
-  // operand selectors of this lane's statistic
-  const int ia = lane < 3 ? lane : lane == 3 || lane == 4 || lane == 5 ? 0 : lane == 6 || lane == 7 ? 1 : 2;
-  const int ib = lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* row = s_pts[warp];
+  // operand selectors of this lane's statistic (lanes 9..11: the float centroid sums of x, y, z)
+  const int ia = lane < 3 ? lane : lane < 6 ? 0 : lane < 8 ? 1 : lane == 8 ? 2 : lane < 12 ? lane - 9 : 0;
+  const int ib = lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : 2;
   const bool is_prod = lane >= 3 && lane < 9;
-  for (int slot = blockIdx.x; slot < n_vox; slot += gridDim.x) {
+  const int n_warps = gridDim.x * kLeafWarps;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int slot = blockIdx.x * kLeafWarps + warp; slot < n_vox; slot += n_warps) {
     const uint32_t s = a.vox_start[slot], e = a.vox_start[slot + 1];
     double acc = 0.0;
     float accf = 0.f;
-    for (uint32_t c = s; c < e; c += 256) {
-      const int cnt = (int)min(256u, e - c);
-      __syncthreads();
-      s_pts[tid] = tid < cnt ? __ldg(a.pts + vals[c + tid]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncthreads();
-      if (tid < 32) {
-        const int rounds = (cnt + 31) >> 5;
-        for (int r = 0; r < rounds; ++r) {
+    float4 pre[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4 p = s_pts[r * 32 + j];
-            const float fa = ia == 0 ? p.x : ia == 1 ? p.y : p.z;
-            const float fb = ib == 0 ? p.x : ib == 1 ? p.y : p.z;
-            const double term = is_prod ? (double)fa * (double)fb : (double)fa;
-            acc += term;
-            accf += (lane == 9 ? p.x : lane == 10 ? p.y : p.z);
-          }
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t i = s + 32u * q + lane;
+      pre[q] = i < e ? __ldg(a.pts + vals[i]) : zero4;
+    }
+    for (uint32_t c = s; c < e; c += kLeafChunk) {
+      const int cnt = (int)min((uint32_t)kLeafChunk, e - c);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(row)[32 * q + lane] = pre[q];
+      __syncwarp();
+      if (c + kLeafChunk < e) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t i = c + kLeafChunk + 32u * q + lane;
+          pre[q] = i < e ? __ldg(a.pts + vals[i]) : zero4;
+        }
+      }
+      const int cnt8 = (cnt + 7) & ~7;
+      for (int j = 0; j < cnt8; j += 8) {
+        double term[8];
+        float fas[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float fa = row[4 * (j + u) + ia], fb = row[4 * (j + u) + ib];
+          fas[u] = fa;
+          term[u] = is_prod ? (double)fa * (double)fb : (double)fa;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc += term[u];
+          accf += fas[u];
         }
       }
     }
-    if (tid < 9) sums[(size_t)slot * 9 + tid] = acc;
-    else if (tid < 12) csum[(size_t)slot * 3 + (tid - 9)] = accf;
+    if (lane < 9) sums[(size_t)slot * 9 + lane] = acc;
+    else if (lane < 12) csum[(size_t)slot * 3 + (lane - 9)] = accf;
   }
 }
 
@@ -132,47 +156,87 @@ static __global__ void __launch_bounds__(64) k_ndt_leaf_stats(NdtLeafArgs a, con
 }
 
 // One CTA: compact the records in ascending voxel order, size the hash on the device, fill it.
+//   1  thread t owns the contiguous slots [t K, (t + 1) K): their keep flags are loaded together and
+//      ONE block scan gives the record index of every kept slot, written to a slot -> record map
+//   2  the table is cleared (its capacity follows from the record count)
+//   3  slot-strided: map, centroid, key and the 48-byte record of a slot are loaded together
+//      (coalesced, one latency), stored to the record arrays, and the key is inserted
+// — three memory latencies in all instead of a serial load / scan / store round per 1024 slots.
 static __global__ void __launch_bounds__(1024) k_ndt_table(NdtLeafArgs a, const NdtVoxel* __restrict__ stage_vox, const float4* __restrict__ stage_cen) {
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_base;
+  __shared__ uint32_t s_total;
+  constexpr int kMaxOwn = 8;  // slots per thread whose flags stay in registers; beyond that they are re-read
+  constexpr uint32_t kNone = 0xFFFFFFFFu;
   const int n_vox = (int)a.meta->n_vox;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (int base = 0; base < n_vox; base += 1024) {
-    const int slot = base + threadIdx.x;
-    float4 c = make_float4(0, 0, 0, 0);
-    if (slot < n_vox) c = stage_cen[slot];
-    const int keep = c.w != 0.f;
-    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t off = s_base;
-    for (int w = 0; w < warp; ++w) off += s_warp[w];
-    const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
-    if (keep) {
-      a.voxels[dst] = stage_vox[slot];
-      a.centroids[dst] = c;
-      a.rec_key[dst] = a.vox_key[slot];
-      a.rec_flag[dst] = c.w == 2.f ? kNdtRejected : 0u;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_base = off + __popc(bal);
-    __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = (n_vox + 1023) / 1024;
+  const int first = tid * K, last = min(first + K, n_vox);
+  uint32_t* slot_rec = a.rec_key;  // [n_vox] scratch: record index | kNdtRejected, or kNone
+  float flag[kMaxOwn];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxOwn; ++k) {
+    flag[k] = 0.f;
+    if (k < K && first + k < last) flag[k] = stage_cen[first + k].w;
   }
-  const uint32_t n_rec = s_base;
+#pragma unroll
+  for (int k = 0; k < kMaxOwn; ++k) mine += flag[k] != 0.f;
+  for (int slot = first + kMaxOwn; slot < last; ++slot) mine += stage_cen[slot].w != 0.f;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = s_warp[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    if (lane == 31) s_total = wi;
+  }
+  __syncthreads();
+  uint32_t dst = s_warp[warp] + incl - mine;
+  const uint32_t n_rec = s_total;
   uint32_t cap = 16;
   while (cap < 2 * n_rec) cap <<= 1;
-  if (threadIdx.x == 0) { a.gmeta->n_records = n_rec; a.gmeta->table_cap = cap; }
-  for (uint32_t i = threadIdx.x; i < cap; i += 1024) a.table[i] = make_uint2(kInvalidKey, 0u);
+  if (tid == 0) { a.gmeta->n_records = n_rec; a.gmeta->table_cap = cap; }
+#pragma unroll
+  for (int k = 0; k < kMaxOwn; ++k) {
+    if (k < K && first + k < last) {
+      slot_rec[first + k] = flag[k] != 0.f ? (dst | (flag[k] == 2.f ? kNdtRejected : 0u)) : kNone;
+      dst += flag[k] != 0.f;
+    }
+  }
+  for (int slot = first + kMaxOwn; slot < last; ++slot) {
+    const float w = stage_cen[slot].w;
+    slot_rec[slot] = w != 0.f ? (dst | (w == 2.f ? kNdtRejected : 0u)) : kNone;
+    dst += w != 0.f;
+  }
+  for (uint32_t i = tid; i < cap; i += 1024) a.table[i] = make_uint2(kInvalidKey, 0u);
   __threadfence_block();
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n_rec; i += 1024) {
-    const uint32_t key = a.rec_key[i];
+  for (int slot = tid; slot < n_vox; slot += 1024) {
+    const uint32_t rec = __ldcg(slot_rec + slot);
+    const float4 c = stage_cen[slot];
+    const uint32_t key = a.vox_key[slot];
+    const float4* vsrc = reinterpret_cast<const float4*>(stage_vox + slot);
+    const float4 v0 = vsrc[0], v1 = vsrc[1], v2 = vsrc[2];
+    if (rec == kNone) continue;
+    const uint32_t d = rec & ~kNdtRejected;
+    float4* vdst = reinterpret_cast<float4*>(a.voxels + d);
+    vdst[0] = v0; vdst[1] = v1; vdst[2] = v2;
+    a.centroids[d] = c;
     uint32_t h = ndt_hash(key, cap - 1);
     while (true) {
       const uint32_t old = atomicCAS(&a.table[h].x, kInvalidKey, key);
-      if (old == kInvalidKey) { a.table[h].y = i | a.rec_flag[i]; break; }
+      if (old == kInvalidKey) { a.table[h].y = rec; break; }
       h = (h + 1) & (cap - 1);
     }
   }
@@ -187,7 +251,7 @@ cudaError_t ndt_leaf_prefer_shared() {
 
 cudaError_t launch_ndt_leaf_stats(cudaStream_t st, const NdtLeafArgs& a, NdtVoxel* stage_vox, float4* stage_cen, double* sums, float* csum) {
   launch_counter() += 3;
-  k_ndt_leaf_sums<<<kNumSM * 8, 256, 0, st>>>(a, sums, csum);
+  k_ndt_leaf_sums<<<kNumSM * 4, kLeafWarps * 32, 0, st>>>(a, sums, csum);
   k_ndt_leaf_stats<<<kNumSM, 64, 0, st>>>(a, sums, csum, stage_vox, stage_cen);
   k_ndt_table<<<1, 1024, 0, st>>>(a, stage_vox, stage_cen);
   return cudaGetLastError();

@@ -361,7 +361,7 @@ inline bool coop_sort_items(int n, int num_sm, int* items_out) {
 
 inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err) {
   int items = 2;
-  if (!coop_sort_items(n, kNumSM, &items)) return false;
+  if (!coop_sort_items(n, vs.max_ctas, &items)) return false;
   const int tile = kSortThreads * items;
   const int n_tiles = n > 0 ? (n + tile - 1) / tile : 1;
   cudaError_t e;

@@ -376,6 +376,7 @@ struct VoxelSort {
   DevBuf<unsigned int> coop_bar;
   DevBuf<SortMeta> meta;
   int n = 0;
+  int max_ctas = kNumSM;  // CTAs the cooperative path may occupy (b200reg_set_sm_budget)
 
   void release() {
     keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); hist.release(); tile_heads.release(); tile_valid.release();

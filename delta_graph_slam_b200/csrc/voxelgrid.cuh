@@ -17,12 +17,19 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
                                                       const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_start, const uint32_t* __restrict__ vox_key,
                                                       unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id, uint32_t* __restrict__ out_count,
                                                       VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq,
-                                                      unsigned int* done_blocks, int publish_here) {
+                                                      unsigned int* done_blocks, int publish_here, float4* host_out, unsigned host_cap) {
+  // host_out (optional): the caller's page-locked output cloud, mapped into the device address space.
+  // The centroids are stored there as well (coalesced 16-byte stores over PCIe), so the host needs
+  // no D2H copy after the count arrives — the stores are fenced before the flag below.
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool overflow = meta->grid.overflow != 0;  // "Leaf size is too small for the input dataset": output = *input_
   const int n_vox = (int)meta->n_vox;
   if (overflow) {
-    if (i < n) out[i] = pts[i];
+    if (i < n) {
+      const float4 p = pts[i];
+      out[i] = p;
+      if (host_out && (unsigned)i < host_cap) host_out[i] = p;
+    }
   } else if (i < n_vox) {
     const uint32_t* vals = sorted_in_b(meta) ? vals_b : vals_a;
     const uint32_t s = vox_start[i], e = vox_start[i + 1];
@@ -32,7 +39,9 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
       ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
     }
     const float cnt = (float)(e - s);
-    out[i] = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
+    const float4 c = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
+    out[i] = c;
+    if (host_out && (unsigned)i < host_cap) host_out[i] = c;
     if (out_id) out_id[i] = vox_key[i];
     if (out_count) out_count[i] = e - s;
   }
@@ -40,6 +49,7 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
   // mapped page-locked memory followed by a sequence flag.  The LAST block to finish publishes it:
   // when the host sees the flag every centroid is written and fenced, so a consumer on another
   // stream (the registration handle copying this cloud) may read the output right away.
+  if (host_out) __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
   __threadfence();

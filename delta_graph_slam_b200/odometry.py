@@ -59,6 +59,59 @@ class Prefilter:
         return self.filter.filter(out=out)
 
 
+    def downsample_begin(self, cloud, out):
+        """downsample() split in two: enqueue the filter of `cloud` into the caller-owned `out` ..."""
+        if self.filter is None:
+            self._passthrough = cloud
+            return
+        self.filter.setInputCloud(cloud, is_dense=False)
+        self.filter.filter_begin(out)
+
+    def downsample_end(self):
+        """... and collect the filtered cloud."""
+        if self.filter is None:
+            return self._passthrough
+        return self.filter.filter_end()
+
+
+class FrontEnd:
+    """prefiltering_nodelet -> /filtered_points -> scan_matching_odometry_nodelet as the pipeline it is in
+    the reference: the two nodelets are loaded into one nodelet manager and joined by a topic
+    [REF launch/delta_graph_slam.launch:26,46; apps/prefiltering_nodelet.cpp:48,51;
+    apps/scan_matching_odometry_nodelet.cpp:53], so scan k+1 is being down-sampled while scan k is matched.
+
+    Here the filter of scan k+1 is enqueued on the prefilter handle's stream before matching(k) starts and
+    collected after it returns.  `out_bufs`: at least three caller-owned output clouds used in rotation
+    (the odometry holds the keyframe's cloud by reference while the next two scans are filtered).
+    `filter_sms`: SMs left to the filter handle; the registration handle's persistent kernel takes the
+    rest, so both are resident together.  The poses are those of the sequential loop
+    (`for cloud: matching(stamp, downsample(cloud))`) run with the same SM budgets."""
+
+    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148):
+        if len(out_bufs) < 3:
+            raise ValueError("the pipelined front end needs three output clouds in rotation")
+        self.prefilter, self.odometry, self.out_bufs = prefilter, odometry, list(out_bufs)
+        if prefilter.filter is not None and filter_sms:
+            prefilter.filter.setSmBudget(filter_sms)
+            odometry.registration.setSmBudget(total_sms - filter_sms)
+
+    def run(self, clouds, stamps=None, on_frame=None):
+        pre, odo, bufs = self.prefilter, self.odometry, self.out_bufs
+        poses = []
+        n = len(clouds)
+        if n == 0:
+            return poses
+        pre.downsample_begin(clouds[0], bufs[0])
+        for k in range(n):
+            filtered = pre.downsample_end()
+            if k + 1 < n:
+                pre.downsample_begin(clouds[k + 1], bufs[(k + 1) % len(bufs)])
+            poses.append(odo.matching(0.1 * k if stamps is None else stamps[k], filtered))
+            if on_frame is not None:
+                on_frame(k, filtered)
+        return poses
+
+
 class ScanMatchingOdometry:
     """matching(stamp, cloud) -> odom (4x4 float32), state as in the nodelet."""
 

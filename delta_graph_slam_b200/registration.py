@@ -167,7 +167,7 @@ class Registration:
         r = Result()
         self._ck(_lib.load().b200reg_get_result(self._h, C.byref(r)))
         return dict(transformation=_lib.from_colmajor(np.array(r.transformation[:], np.float32)), fitness=r.fitness, score=r.score, converged=bool(r.converged),
-                    iterations=r.iterations, evaluations=r.evaluations, hits=r.hits)
+                    iterations=r.iterations, evaluations=r.evaluations, passes=r.passes, hits=r.hits)
 
     # ---- loop-closure batches (LoopDetector::matching, many candidates in one call)
     def cloudPut(self, cloud_id, cloud):
@@ -256,6 +256,36 @@ class Registration:
             raise ValueError("output buffer smaller than the input cloud")
         self._ck(_lib.load().b200reg_voxelgrid_filter_device(self._h, cloud.ptr, cloud.n, leaf3, min_points_per_voxel, int(is_dense), out.ptr, C.byref(n_out)))
         return DeviceCloud(out.ptr, n_out.value, out.owner)
+
+    def voxelgrid_filter_begin(self, cloud, leaf, out, min_points_per_voxel=0, is_dense=False):
+        """First half of the filter: enqueue and return (b200reg_voxelgrid_filter_begin / _device_begin).
+        `cloud` / `out` are both host arrays or both DeviceClouds; they stay untouched until the end call."""
+        leaf3 = (C.c_float * 3)(*((leaf,) * 3 if np.isscalar(leaf) else leaf))
+        if isinstance(cloud, DeviceCloud):
+            if out.n < cloud.n:
+                raise ValueError("output buffer smaller than the input cloud")
+            self._ck(_lib.load().b200reg_voxelgrid_filter_device_begin(self._h, cloud.ptr, cloud.n, leaf3, min_points_per_voxel, int(is_dense), out.ptr))
+            self._vg_pending = (cloud, out)
+            return
+        c = _lib.as_cloud(cloud)
+        if out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
+        self._ck(_lib.load().b200reg_voxelgrid_filter_begin(self._h, c.ctypes.data if len(c) else None, len(c), 16, leaf3, min_points_per_voxel, int(is_dense), out.ctypes.data, len(out)))
+        self._vg_pending = (c, out)
+
+    def voxelgrid_filter_end(self):
+        """Second half: wait for the filter in flight; returns the filtered cloud (a view of `out`)."""
+        _, out = self._vg_pending
+        self._vg_pending = None
+        n_out = C.c_size_t()
+        self._ck(_lib.load().b200reg_voxelgrid_filter_end(self._h, C.byref(n_out)))
+        if isinstance(out, DeviceCloud):
+            return DeviceCloud(out.ptr, n_out.value, out.owner)
+        return out[: n_out.value]
+
+    def setSmBudget(self, n_sm):
+        """At most n_sm CTAs (one per SM) for this handle's persistent kernels (b200reg_set_sm_budget)."""
+        self._ck(_lib.load().b200reg_set_sm_budget(self._h, int(n_sm)))
 
     def voxelgrid_last_layout(self, n_voxels, n_points):
         vid = np.zeros(max(n_voxels, 1), np.uint32)
@@ -349,6 +379,16 @@ class VoxelGrid:
         if isinstance(self._input, DeviceCloud):
             return self._reg.voxelgrid_filter_device(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
         return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense, out=out)
+
+    def filter_begin(self, out):
+        """filter() split in two for a pipelined front end: enqueue now, collect with filter_end()."""
+        self._reg.voxelgrid_filter_begin(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
+
+    def filter_end(self):
+        return self._reg.voxelgrid_filter_end()
+
+    def setSmBudget(self, n_sm):
+        self._reg.setSmBudget(n_sm)
 
     def last_layout(self, n_voxels, n_points):
         return self._reg.voxelgrid_last_layout(n_voxels, n_points)

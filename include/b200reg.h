@@ -80,8 +80,8 @@ typedef struct b200reg_result {
   double score;             /* NDT: getTransformationProbability(); GICP: last sum of errors */
   int32_t converged;        /* hasConverged() */
   int32_t iterations;       /* getFinalNumIteration() */
-  int32_t evaluations;      /* derivative passes (NDT) / linearize + error passes (GICP) */
-  int32_t reserved;
+  int32_t evaluations;      /* evaluations of the reference's algorithm: computeDerivatives + computeHessian calls (NDT) / linearize + error passes (GICP) */
+  int32_t passes;           /* passes over the source cloud the device actually ran (NDT: the computeHessian that closes a line search rides in its last trial pass, so passes <= evaluations) */
   int64_t hits;             /* (point, voxel) pairs visited (NDT) / correspondences evaluated (GICP) */
 } b200reg_result;
 
@@ -143,6 +143,26 @@ int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, siz
 /* device-resident variant: d_out must hold n points; *n_out is written on the host after a stream sync */
 int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_points_per_voxel, int input_is_dense,
                                     float* d_out_xyzw, size_t* n_out);
+/* The same filter as two halves.  In the reference the prefiltering nodelet and the scan-matching
+ * nodelet are separate nodelets of one manager, joined by the /filtered_points topic [REF
+ * apps/prefiltering_nodelet.cpp:48,51; apps/scan_matching_odometry_nodelet.cpp:53; launch/delta_graph_slam.launch:26,46]: scan k+1 is down-sampled while scan k is being
+ * matched.  _begin enqueues the whole filter (H2D of the raw scan, key / sort / centroid kernels) on
+ * the handle's stream and returns; _end waits for it and returns the point count.  One filter call in
+ * flight per handle (a second _begin is B200REG_E_STATE).  Page-locked `xyzw` / `out` are read by DMA
+ * and written by the centroid kernel directly (mapped memory) and must stay untouched until _end;
+ * pageable buffers are staged (input copied inside _begin, output copied inside _end). */
+int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, const float leaf[3], unsigned min_points_per_voxel,
+                                   int input_is_dense, float* out_xyzw, size_t out_capacity);
+int b200reg_voxelgrid_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_points_per_voxel, int input_is_dense,
+                                          float* d_out_xyzw);
+int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out);
+/* Share of the GPU a handle's persistent (cooperative) kernels occupy: at most n_sm CTAs, one per SM.
+ * Default: every SM.  A front end that overlaps the filter of scan k+1 with the registration of
+ * scan k gives the filter handle a few SMs and the registration handle the rest, so both kernels
+ * are resident at once (each is latency bound; neither needs the whole GPU).  Results do not depend
+ * on the budget for the filter (bit-exact); NDT / GICP sums are taken in a budget-dependent order
+ * (last-bit differences, as between OpenMP thread counts upstream). */
+int b200reg_set_sm_budget(b200reg_handle* h, int n_sm);
 /* introspection of the last filter call (parity tests): per output voxel linear index and point
  * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);

@@ -57,3 +57,15 @@ def small_loop_scenario(oracle, n_targets=3, n_candidates=4, leaf=0.2, stride=2,
         clouds[cid] = oracle.voxelgrid(raw, leaf)["out"]
     pairs = make_pairs([(t, c, g) for t, c, g, _ in sc["pairs"]])
     return clouds, pairs, [rel for _, _, _, rel in sc["pairs"]]
+
+
+def bits_equal(a, b):
+    """Same shape and the same float32 bit patterns."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def transform_delta(Ta, Tb):
+    """(max |dt| in metres, rotation angle in radians) between two 4x4 transforms."""
+    Ta, Tb = np.asarray(Ta), np.asarray(Tb)
+    return float(np.max(np.abs(Ta[:3, 3].astype(np.float64) - Tb[:3, 3].astype(np.float64)))), rot_angle(Ta[:3, :3], Tb[:3, :3])
