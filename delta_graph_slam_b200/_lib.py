@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200reg.so")
+LIB_PATH = os.environ.get("B200REG_LIB") or os.path.join(_HERE, "libb200reg.so")  # B200REG_LIB: developer override (A/B builds of the same engine)
 
 OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY = 0, -1, -2, -3, -4
 METHOD_NONE, METHOD_NDT, METHOD_GICP = 0, 1, 2

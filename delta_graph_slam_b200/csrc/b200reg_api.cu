@@ -1273,7 +1273,7 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   int rc = set_device(h);
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  B200_CUDA_TRY(cudaMemcpy(out6, h->prof.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return B200REG_OK;
 }
 

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4
   float td = 3.402823466e+38f;
   int ti = kNoIndex;
   bool open = true;
+  const bool use_occ = nn_occ_valid(g);
   for (int r = 0; r <= kKnnMaxRing && open; ++r) {
     const float kd = __shfl_sync(0xffffffffu, td, km1);
     const int ki = __shfl_sync(0xffffffffu, ti, km1);
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4
         const bool in = ix >= gp.min_b[0] && ix <= gp.max_b[0] && iy >= gp.min_b[1] && iy <= gp.max_b[1] && iz >= gp.min_b[2] && iz <= gp.max_b[2];
         if (in && (ki == kNoIndex || nn_box_d2(gp, q, ix, iy, iz) <= kd)) {
           const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
-          run = nn_lookup(g, key);
+          if (!use_occ || nn_occ_bit(g, key)) run = nn_lookup(g, key);  // most cells of a ring are empty: one bitmap bit instead of a hash walk
         }
       }
       unsigned mask = __ballot_sync(0xffffffffu, run.y > run.x);

@@ -36,11 +36,12 @@ struct CachedCloud {
   DevBuf<float4> nn_pts;
   DevBuf<uint4> nn_table;
   DevBuf<SortMeta> nn_meta;
+  DevBuf<uint32_t> nn_occ;
   uint32_t nn_cap = 0;
 
   void release() {
     pts.release(); voxels.release(); centroids.release(); table.release(); gmeta.release(); meta.release();
-    nn_pts.release(); nn_table.release(); nn_meta.release();
+    nn_pts.release(); nn_table.release(); nn_meta.release(); nn_occ.release();
     has_ndt = has_nn = false;
     n = 0;
   }
@@ -52,7 +53,7 @@ struct CachedCloud {
   NnView nn_view() const {
     NnView v;
     v.meta = nn_meta.p; v.table = nn_table.p; v.table_mask = nn_cap - 1; v.table_shift = 32 - (int)__builtin_ctz(nn_cap);
-    v.pts = nn_pts.p; v.n = n;
+    v.pts = nn_pts.p; v.n = n; v.occ = nn_occ.p;
     return v;
   }
 };
@@ -71,10 +72,10 @@ inline cudaError_t cache_build_ndt(cudaStream_t st, NdtGrid& builder, CachedClou
 }
 
 inline cudaError_t cache_build_nn(cudaStream_t st, NnGrid& builder, CachedCloud& c) {
-  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta);
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta); std::swap(builder.occ, c.nn_occ);
   cudaError_t e = builder.build(st, c.pts.p, c.n);
   c.nn_cap = builder.table_cap;
-  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta);
+  std::swap(builder.pts, c.nn_pts); std::swap(builder.table, c.nn_table); std::swap(builder.sort.meta, c.nn_meta); std::swap(builder.occ, c.nn_occ);
   builder.built = false;
   if (e == cudaSuccess) c.has_nn = true;
   return e;

@@ -85,6 +85,7 @@ struct NdtShared {
   double gauss_d1, gauss_d2;
   double trig[6][2];  // sin, cos of: float-rounded angles (T) [0..2], double angles (tables) [3..5]
   double tot[kAccStride];
+  long long pf[6];  // developer cycle counters inside ndt_step: {totals -> state, line-search update, trial value, Newton end, 6x6 solve, Newton begin rest}
   double red[kAlignWarps][kAccStride];
 };
 
@@ -267,6 +268,8 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
   const double* t = s.tot;
+  long long tk = clock64();
+  auto lap = [&](int slot) { const long long now = clock64(); s.pf[slot] += now - tk; tk = now; };
   s.n_eval++;
   s.n_pass++;
   s.hits += t[28];
@@ -297,6 +300,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
     default:
       return;
   }
+  lap(0);
   if (go_loop_check) {
     // the evaluation at a_t just finished
     s.phi_t = -s.score;
@@ -318,6 +322,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
       s.step_iterations++;
     }
   }
+  lap(1);
   while (true) {
     if (go_loop_check) {
       go_loop_check = false;
@@ -330,6 +335,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
         s.phase = PH_MT_ITER;
         s.need_hessian = 1;
         s.new_pose = 1;
+        lap(2);
         return;
       }
       // computeHessian at x_t: taken from the last trial pass (see PH_MT_ITER above); it counts as an
@@ -344,12 +350,15 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
       s.nr_iterations++;
       if (s.converged) { s.phase = PH_DONE; return; }
       go_newton_begin = true;
+      lap(3);
     }
     if (go_newton_begin) {
       go_newton_begin = false;
       double neg_g[6], dp[6];
       for (int i = 0; i < 6; ++i) neg_g[i] = -s.g[i];
+      lap(5);
       solve6(s.H, neg_g, dp);
+      lap(4);
       double nrm = 0;
       for (int i = 0; i < 6; ++i) nrm += dp[i] * dp[i];
       nrm = sqrt(nrm);
@@ -389,6 +398,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
       s.phase = PH_MT_FIRST;
       s.need_hessian = 1;
       s.new_pose = 1;
+      lap(5);
       return;
     }
   }
@@ -603,7 +613,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   // the ticket; the other CTAs of the group read it from the mailbox after the group barrier.
   while (true) {
     int jb;
-    if (G == 1) {
+    if (jobs == nullptr) {
+      // one registration riding in the kernel parameters: no ticket, no mailbox, no barrier to fetch it
+      if (fetched) break;
+      jb = 0;
+      ++fetched;
+    } else if (G == 1) {
       if (tid == 0) s_job = (int)atomicAdd(queue, 1u);
       __syncthreads();
       jb = s_job;
@@ -673,6 +688,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         s.gauss_d2 = -2 * log((-log(c1 * exp(-0.5) + c2) - d3) / s.gauss_d1);
         for (int i = 0; i < 6; ++i) s.p[i] = job.p0[i];
         s.nr_iterations = 0; s.converged = 0; s.n_eval = 0; s.n_pass = 0; s.hits = 0.0;
+        for (int i = 0; i < 6; ++i) s.pf[i] = 0;
         s.score = 0.0;
         s.need_hessian = 1;
         s.phase = job.eval_only ? PH_EVAL_ONLY : PH_INIT;
@@ -813,8 +829,10 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += t4 - t3; prof[4] += t5 - t4; prof[5] += 1;
       if (s.phase == PH_DONE) break;
     }
-    if (job.prof && rank == 0 && tid == 0)
+    if (job.prof && rank == 0 && tid == 0) {
       for (int k = 0; k < 10; ++k) job.prof[k] = prof[k];
+      for (int k = 0; k < 6; ++k) job.prof[10 + k] = s.pf[k];
+    }
     // ---- result
     if (rank == 0 && tid == 0) {
       if (job.eval_only) {

@@ -24,8 +24,14 @@
 namespace b200 {
 
 constexpr int kNearRing = 1;   // rings walked by the thread-per-query phase
-constexpr int kFarRing = 8;    // rings walked by the warp-per-query phase before the brute-force pass (4 m)
-constexpr float kNnCell = 0.5f;
+#ifndef B200_NN_CELL
+#define B200_NN_CELL 0.5f
+#endif
+#ifndef B200_NN_FAR_RING
+#define B200_NN_FAR_RING 8
+#endif
+constexpr int kFarRing = B200_NN_FAR_RING;  // rings walked by the warp-per-query phase before the brute-force pass (4 m)
+constexpr float kNnCell = B200_NN_CELL;
 
 struct NnView {
   const SortMeta* meta;
@@ -34,7 +40,25 @@ struct NnView {
   int table_shift;
   const float4* pts;  // re-ordered by cell; w = original index (int bits)
   int n;
+  // occupancy bitmap over the cell lattice, bit index = cell key (x runs fastest, so one 32-bit word
+  // covers 32 consecutive cells of a row): word 0 is 1 when the bitmap is valid (the lattice fits
+  // kOccMaxCells), the bits start at word kOccHeader.  The far searches walk whole rows of a ring with
+  // two word loads and probe the hash only where a bit is set; nullptr = no bitmap.
+  const uint32_t* occ;
 };
+constexpr uint32_t kOccMaxCells = 32u << 20;  // 4 MB of bits: a 400 x 400 x 200 lattice of 0.5 m cells
+constexpr int kOccHeader = 4;                 // words in front of the bits (keeps them 16-byte aligned)
+constexpr size_t kOccWords = kOccMaxCells / 32 + kOccHeader + 4;
+
+__device__ __forceinline__ bool nn_occ_valid(const NnView& g) { return g.occ != nullptr && __ldg(g.occ) != 0u; }
+// bits [key0, key0 + nbits) of the bitmap, nbits <= 32 (the buffer is padded for the second word)
+__device__ __forceinline__ uint32_t nn_occ_bits(const NnView& g, uint32_t key0, int nbits) {
+  const uint32_t w = key0 >> 5, sh = key0 & 31u;
+  const uint32_t lo = __ldg(g.occ + kOccHeader + w), hi = __ldg(g.occ + kOccHeader + 1 + w);
+  const uint32_t v = __funnelshift_r(lo, hi, sh);
+  return nbits >= 32 ? v : (v & ((1u << nbits) - 1u));
+}
+__device__ __forceinline__ bool nn_occ_bit(const NnView& g, uint32_t key) { return (__ldg(g.occ + kOccHeader + (key >> 5)) >> (key & 31u)) & 1u; }
 
 // (first, end) of the cell's run, or first == end when the cell is empty
 __device__ __forceinline__ uint2 nn_lookup(const NnView& g, uint32_t key) {
@@ -58,11 +82,26 @@ __global__ void __launch_bounds__(256) k_nn_reorder(const float4* __restrict__ p
   out[i] = p;
 }
 
+// zero the words of the occupancy bitmap the lattice needs (its size is only known on the device)
+// and mark it valid; lattices above kOccMaxCells go without (the searches fall back to hash probes)
+__global__ void __launch_bounds__(256) k_nn_occ_clear(const SortMeta* __restrict__ meta, uint32_t* __restrict__ occ) {
+  const GridParams& gp = meta->grid;
+  const unsigned long long cells = (unsigned long long)gp.div_b[0] * (unsigned long long)gp.div_b[1] * (unsigned long long)gp.div_b[2];
+  const bool ok = gp.any && !gp.overflow && cells <= (unsigned long long)kOccMaxCells;
+  if (blockIdx.x == 0 && threadIdx.x == 0) occ[0] = ok ? 1u : 0u;
+  if (!ok) return;
+  const uint32_t words = (uint32_t)(cells / 32) + 3;
+  uint4* o4 = reinterpret_cast<uint4*>(occ + kOccHeader);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (words + 3) / 4; i += gridDim.x * blockDim.x) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(256) k_nn_insert(const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_key, const uint32_t* __restrict__ vox_start, uint4* __restrict__ table,
-                                                   uint32_t mask, int shift) {
+                                                   uint32_t mask, int shift, uint32_t* __restrict__ occ) {
   const int n_vox = (int)meta->n_vox;
+  const bool use_occ = occ != nullptr && occ[0] != 0u;
   for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_vox; slot += gridDim.x * blockDim.x) {
     const uint32_t key = vox_key[slot];
+    if (use_occ) atomicOr(occ + kOccHeader + (key >> 5), 1u << (key & 31u));
     uint32_t h = (key * 2654435761u) >> shift;
     while (true) {
       uint32_t old = atomicCAS(&table[h].x, kInvalidKey, key);
@@ -169,27 +208,59 @@ __device__ __forceinline__ void nn_warp_merge(float& best, int& best_idx) {
 // far phase, one warp (all 32 lanes call with the same query and the near phase's best): rings
 // kNearRing+1 .. max_ring.  Returns true when resolved; best / best_idx are warp-uniform on return.
 __device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int max_ring, int lane, float& best, int& best_idx) {
+  const bool use_occ = nn_occ_valid(g);  // warp-uniform
   for (int r = kNearRing + 1; r <= max_ring; ++r) {
     if (nn_settled(gp, q, r, best, max_d2)) return true;
-    // the shell of ring r: two z faces (side^2), two y faces (side x inner), two x faces (inner^2)
     const int side = 2 * r + 1, inner = 2 * r - 1;
-    const int nz = 2 * side * side, ny = 2 * side * inner, total = nz + ny + 2 * inner * inner;
-    for (int c = lane; c < total; c += 32) {
-      int dx, dy, dz;
-      if (c < nz) {
-        const int f = c / (side * side), rem = c - f * side * side;
-        dz = f ? r : -r; dx = rem % side - r; dy = rem / side - r;
-      } else if (c < nz + ny) {
-        const int cc = c - nz, f = cc / (side * inner), rem = cc - f * side * inner;
-        dy = f ? r : -r; dx = rem % side - r; dz = rem / side - (r - 1);
-      } else {
-        const int cc = c - nz - ny, f = cc / (inner * inner), rem = cc - f * inner * inner;
-        dx = f ? r : -r; dy = rem % inner - (r - 1); dz = rem / inner - (r - 1);
+    const int x0 = max(q.cx - r, gp.min_b[0]), x1 = min(q.cx + r, gp.max_b[0]);
+    if (use_occ && side <= 32) {
+      // the shell of ring r row by row: the (2r+1)^2 rows along x are dealt to the lanes; a row costs
+      // two word loads of the occupancy bitmap, and only occupied cells of the shell (every cell of a
+      // face row, the two end cells of an interior row) are probed and scanned
+      if (x0 <= x1) {
+        const int nb = x1 - x0 + 1;
+        uint32_t ends = 0u;
+        if (q.cx - r >= gp.min_b[0]) ends |= 1u;
+        if (q.cx + r <= gp.max_b[0]) ends |= 1u << (nb - 1);
+        const int xq = min(max(q.cx, gp.min_b[0]), gp.max_b[0]);
+        for (int row = lane; row < side * side; row += 32) {
+          const int dz = row / side - r, dy = row - (dz + r) * side - r;
+          const int iy = q.cy + dy, iz = q.cz + dz;
+          if (iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
+          if (nn_box_d2(gp, q, xq, iy, iz) > best) continue;  // no cell of this row can win
+          const bool face = dy == -r || dy == r || dz == -r || dz == r;
+          const uint32_t key0 = (uint32_t)((x0 - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+          uint32_t bits = nn_occ_bits(g, key0, nb);
+          if (!face) bits &= ends;
+          while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int ix = x0 + b;
+            if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+            nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
+          }
+        }
       }
-      const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
-      if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
-      if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
-      nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
+    } else {
+      // the shell of ring r: two z faces (side^2), two y faces (side x inner), two x faces (inner^2)
+      const int nz = 2 * side * side, ny = 2 * side * inner, total = nz + ny + 2 * inner * inner;
+      for (int c = lane; c < total; c += 32) {
+        int dx, dy, dz;
+        if (c < nz) {
+          const int f = c / (side * side), rem = c - f * side * side;
+          dz = f ? r : -r; dx = rem % side - r; dy = rem / side - r;
+        } else if (c < nz + ny) {
+          const int cc = c - nz, f = cc / (side * inner), rem = cc - f * side * inner;
+          dy = f ? r : -r; dx = rem % side - r; dz = rem / side - (r - 1);
+        } else {
+          const int cc = c - nz - ny, f = cc / (inner * inner), rem = cc - f * inner * inner;
+          dx = f ? r : -r; dy = rem % inner - (r - 1); dz = rem / inner - (r - 1);
+        }
+        const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
+        if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
+        if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+        nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
+      }
     }
     nn_warp_merge(best, best_idx);
   }
@@ -346,6 +417,7 @@ struct NnGrid {
   VoxelSort sort;
   DevBuf<float4> pts, queries;
   DevBuf<uint4> table;
+  DevBuf<uint32_t> occ;
   DevBuf<float> d2;
   DevBuf<int> idx, pending, pending2;
   DevBuf<unsigned int> n_pending;  // [0] after the near phase, [1] after the far phase
@@ -355,7 +427,7 @@ struct NnGrid {
   bool built = false;
 
   void release() {
-    sort.release(); pts.release(); queries.release(); table.release(); d2.release(); idx.release(); pending.release(); pending2.release(); n_pending.release(); T.release();
+    sort.release(); pts.release(); queries.release(); table.release(); occ.release(); d2.release(); idx.release(); pending.release(); pending2.release(); n_pending.release(); T.release();
   }
   NnView view() const {
     NnView v;
@@ -365,6 +437,7 @@ struct NnGrid {
     v.table_shift = 32 - (int)__builtin_ctz(table_cap);
     v.pts = pts.p;
     v.n = n;
+    v.occ = occ.p;
     return v;
   }
   static uint32_t capacity_for(int n_points) {
@@ -380,10 +453,15 @@ struct NnGrid {
     table_cap = capacity_for(n);
     if ((e = table.reserve(table_cap)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(table.p, 0xFF, (size_t)table_cap * sizeof(uint4), st)) != cudaSuccess) return e;
+    if (!occ.p) {
+      if ((e = occ.reserve(kOccWords)) != cudaSuccess) return e;
+      if ((e = cudaMemsetAsync(occ.p, 0, 16, st)) != cudaSuccess) return e;  // header: no bitmap until k_nn_occ_clear says so
+    }
     if (n > 0) {
-      launch_counter() += 2;
+      launch_counter() += 3;
+      k_nn_occ_clear<<<kNumSM, 256, 0, st>>>(sort.meta.p, occ.p);
       k_nn_reorder<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, sort.vals_a.p, sort.vals_b.p, sort.meta.p, pts.p);
-      k_nn_insert<<<kNumSM * 2, 256, 0, st>>>(sort.meta.p, sort.vox_key.p, sort.vox_start.p, table.p, table_cap - 1, 32 - (int)__builtin_ctz(table_cap));
+      k_nn_insert<<<kNumSM * 2, 256, 0, st>>>(sort.meta.p, sort.vox_key.p, sort.vox_start.p, table.p, table_cap - 1, 32 - (int)__builtin_ctz(table_cap), occ.p);
     }
     built = true;
     return cudaGetLastError();

@@ -138,13 +138,16 @@ static __device__ __noinline__ void svd_solve6(const double* A, const double* b,
 // two derivative passes and its latency is on the critical path of every Newton iteration.
 static __device__ __noinline__ void solve6(const double* A, const double* b, double* x) {
   double M[6][7];
-  double amax = 0.0;
+  double rmax[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { M[i][j] = A[6 * i + j]; amax = fmax(amax, fabs(M[i][j])); }
+    for (int j = 0; j < 6; ++j) M[i][j] = A[6 * i + j];
     M[i][6] = b[i];
+    // max |a_ij| as a tree (fmax is exact, so the order does not matter; one 36-long chain did)
+    rmax[i] = fmax(fmax(fmax(fabs(M[i][0]), fabs(M[i][1])), fmax(fabs(M[i][2]), fabs(M[i][3]))), fmax(fabs(M[i][4]), fabs(M[i][5])));
   }
+  const double amax = fmax(fmax(fmax(rmax[0], rmax[1]), fmax(rmax[2], rmax[3])), fmax(rmax[4], rmax[5]));
   bool ok = amax > 0.0 && amax == amax && amax < 1.7e308;
   double invs[6];
 #pragma unroll
@@ -167,7 +170,7 @@ static __device__ __noinline__ void solve6(const double* A, const double* b, dou
         M[i][j] = sw ? a : c;
       }
     }
-    const double inv = 1.0 / M[k][k];
+    const double inv = __drcp_rn(M[k][k]);  // correctly rounded reciprocal: the bits of 1.0 / x, without the general division's slow path
     invs[k] = inv;
 #pragma unroll
     for (int i = k + 1; i < 6; ++i) {

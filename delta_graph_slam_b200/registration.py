@@ -218,9 +218,10 @@ class Registration:
         return dict(launches_total=a.value, timed_aligns=b.value, align_kernel_ms=c.value)
 
     def profile(self):
-        v = np.zeros(10, np.int64)
+        v = np.zeros(16, np.int64)
         self._ck(_lib.load().b200reg_get_profile(self._h, v.ctypes.data))
-        return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage", "step_solve_mt", "step_trig", "step_tables"), v.tolist()))
+        return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage", "step_solve_mt", "step_trig", "step_tables",
+                         "st_totals", "st_interval", "st_trial", "st_newton_end", "st_solve", "st_newton_begin"), v.tolist()))
 
     def nn_stats(self):
         v = np.zeros(3, np.int64)

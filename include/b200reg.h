@@ -207,9 +207,11 @@ int b200reg_ndt_derivatives(b200reg_handle* h, const double p[6], double* score,
 int b200reg_set_timing(b200reg_handle* h, int on);
 int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long* timed_aligns, double* align_kernel_ms);
 
-/* developer counters of the last align: SM cycles spent by CTA 0 in {point pass, block reduce, group
- * barrier, partial sum, optimiser step}, the number of passes, and the grid staging cycles */
-int b200reg_get_profile(b200reg_handle* h, long long* out7);
+/* developer counters of the last align (16 values): SM cycles spent by CTA 0 in {point pass, block reduce,
+ * group barrier, partial sum, optimiser step}, the number of passes, the grid staging cycles, then the
+ * optimiser step split into {state machine, pose trig, transform + angle tables} and the state machine
+ * into {totals -> state, interval update, trial value, Newton end, 6x6 solve, Newton begin} */
+int b200reg_get_profile(b200reg_handle* h, long long* out16);
 
 /* A/B switch for tests (process-wide): 0 = the voxel key / sort / segmentation pipeline runs as one
  * cooperative kernel when the cloud fits one tile per SM (default), 1 = always the multi-kernel path */

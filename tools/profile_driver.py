@@ -15,7 +15,8 @@ clouds = [eng.DeviceCloud(d_raw[k].data_ptr(), counts[k], d_raw) for k in range(
 d_ds = torch.empty((rays, 4), dtype=torch.float32, device="cuda:0")
 ds_buf = eng.DeviceCloud(d_ds.data_ptr(), rays, d_ds)
 pre = eng.Prefilter(bench.PREFILTER_PARAMS, out=bench.DEVNULL)
-odo = eng.ScanMatchingOdometry(bench.ODOM_PARAMS, out=bench.DEVNULL)
+odo = eng.ScanMatchingOdometry(bench.GICP_ODOM_PARAMS if len(sys.argv) > 2 and sys.argv[2] == "gicp" else bench.ODOM_PARAMS, out=bench.DEVNULL)
 poses = bench.run_sequence(pre, odo, clouds, out_buf=ds_buf)
-odo.registration.getFitnessScore()
+if not (len(sys.argv) > 2 and sys.argv[2] == "gicp"):
+    odo.registration.getFitnessScore()
 print("frames", frames, "keyframes", odo.num_keyframes, "last pose t", poses[-1][:3, 3])
