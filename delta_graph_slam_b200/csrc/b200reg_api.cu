@@ -80,7 +80,8 @@ struct b200reg_handle {
   bool nn_src_stale = true;
   DevBuf<double> cov_src, cov_tgt, gicp_mahal;
   bool cov_src_ok = false, cov_tgt_ok = false;
-  DevBuf<int> gicp_corr;
+  DevBuf<int> gicp_corr, gicp_pending;
+  DevBuf<unsigned int> gicp_n_pending;
   DevBuf<GicpJob> gicp_jobs;
 
   // loop-closure batches: keyframe cloud cache + batch staging.  Target structures of different
@@ -246,7 +247,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
-  B200_ATTR(prefer_shared(k_gicp_covariances)); B200_ATTR(prefer_shared(k_gicp_align));
+  B200_ATTR(prefer_shared(k_gicp_knn)); B200_ATTR(prefer_shared(k_gicp_knn_brute)); B200_ATTR(prefer_shared(k_gicp_regularize)); B200_ATTR(prefer_shared(k_gicp_align));
   B200_ATTR(ndt_leaf_prefer_shared());
 #undef B200_ATTR
   if (device < 64) done.fetch_or(1ull << device);
@@ -405,9 +406,15 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
 cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const float4* pts, int n, double* covs) {
   if (n <= 0) return cudaSuccess;
   const int k = h->cfg.correspondence_randomness, reg = h->cfg.regularization;
+  cudaError_t e;
+  if ((e = h->gicp_pending.reserve((size_t)n)) != cudaSuccess) return e;
+  if ((e = h->gicp_n_pending.reserve(1)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(h->gicp_n_pending.p, 0, sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
   const int blocks = (n + 7) / 8;  // one warp per query, 8 warps per CTA
-  launch_counter() += 1;
-  k_gicp_covariances<<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, reg, covs);
+  launch_counter() += 3;
+  k_gicp_knn<<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p);
+  k_gicp_knn_brute<<<kNumSM * 4, 256, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p);
+  k_gicp_regularize<<<(n + 127) / 128, 128, 0, h->stream>>>(n, reg, covs);
   return cudaGetLastError();
 }
 
@@ -560,7 +567,7 @@ int b200reg_destroy(b200reg_handle* h) {
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
-  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_jobs.release();
+  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_pending.release(); h->gicp_n_pending.release(); h->gicp_jobs.release();
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
   for (auto& ln : h->lanes) {

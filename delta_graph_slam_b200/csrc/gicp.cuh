@@ -3,7 +3,7 @@
 // [REF src/hdl_graph_slam/registrations.cpp:27-36] (k = 20 neighbours, PLANE regularisation,
 // Levenberg-Marquardt, max correspondence distance 2.5 m / 2.0 m in the launch files).
 //
-//   k_gicp_covariances : calculate_covariances — per point the k nearest neighbours (exact, found
+//   k_gicp_knn / k_gicp_knn_brute / k_gicp_regularize : calculate_covariances — per point the k nearest neighbours (exact, found
 //                        on the cloud's own cell grid), their covariance in double, and the
 //                        regularised 3x3 (stored as 6 doubles)
 //   k_gicp_align       : LsqRegistration::computeTransformation — one persistent cooperative
@@ -32,7 +32,7 @@ namespace b200 {
 // the examined block can beat the k-th (or the block covers the lattice); a query still open after
 // kKnnMaxRing rings (an isolated point) restarts as a linear scan of the whole cloud.  Exact; ties
 // by lowest index, as the oracle's kd-tree.
-constexpr int kKnnMaxRing = 6;
+constexpr int kKnnMaxRing = 15;  // 7.5 m; the rings from 2 on are walked through the occupancy bitmap (32 cells of a row per word)
 
 // one compare-exchange step of a bitonic network over the lanes: partner = lane ^ j; in an ascending
 // block the lower lane of the pair keeps the smaller entry.  (d, i) pairs are totally ordered.
@@ -64,27 +64,151 @@ __device__ __forceinline__ void knn_merge32(float& td, int& ti, float cd, int ci
   for (int j = 16; j > 0; j >>= 1) bitonic_cmpex(td, ti, lane, j, true);
 }
 
-// offer the points [s, e) of the cell-ordered array to the list
-__device__ __forceinline__ void knn_offer_run(const NnView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, int km1, int lane, float& td, int& ti) {
-  for (uint32_t j0 = s; j0 < e; j0 += 32) {
-    const uint32_t j = j0 + lane;
-    float cd = 3.402823466e+38f;
-    int ci = kNoIndex;
-    if (j < e) {
-      const float4 p = __ldg(g.pts + j);
-      cd = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-      ci = __float_as_int(p.w);
+// The k-best list of one warp plus a staging row in shared memory.  A merge costs ~20 shuffle steps,
+// so candidates are FILTERED against the current k-th first (one ballot per 32 points) and the
+// survivors are packed into the staging row; the network runs only when 32 of them have gathered or
+// the caller needs the exact k-th (flush).  After the query's own cell has filled the list few points
+// of the neighbouring cells survive, so a query costs ~2 merges instead of one per occupied cell.
+struct KnnList {
+  float td;  // lane l: the l-th smallest squared distance so far
+  int ti;
+  float kd;  // the current k-th (warp-uniform); (+inf, kNoIndex) while the list is not full
+  int ki;
+  int ns;    // staged candidates (warp-uniform, < 32 between calls)
+  float* bd; // staging row of this warp, 64 entries
+  int* bi;
+};
+
+__device__ __forceinline__ void knn_init(KnnList& L, float* bd, int* bi) {
+  L.td = 3.402823466e+38f; L.ti = kNoIndex; L.kd = 3.402823466e+38f; L.ki = kNoIndex; L.ns = 0; L.bd = bd; L.bi = bi;
+}
+__device__ __forceinline__ void knn_merge_staged(KnnList& L, int km1, int lane) {
+  __syncwarp();
+  const float cd = lane < L.ns ? L.bd[lane] : 3.402823466e+38f;
+  const int ci = lane < L.ns ? L.bi[lane] : kNoIndex;
+  knn_merge32(L.td, L.ti, cd, ci, lane);
+  L.kd = __shfl_sync(0xffffffffu, L.td, km1);
+  L.ki = __shfl_sync(0xffffffffu, L.ti, km1);
+  const int rest = L.ns > 32 ? L.ns - 32 : 0;
+  float rd = 0.f;
+  int ri = 0;
+  if (lane < rest) { rd = L.bd[32 + lane]; ri = L.bi[32 + lane]; }
+  __syncwarp();
+  if (lane < rest) { L.bd[lane] = rd; L.bi[lane] = ri; }
+  L.ns = rest;
+  __syncwarp();
+}
+__device__ __forceinline__ void knn_flush(KnnList& L, int km1, int lane) {
+  if (L.ns > 0) knn_merge_staged(L, km1, lane);
+}
+// take one candidate per lane (valid = false: none): filter against the k-th, pack, merge when 32 gathered
+__device__ __forceinline__ void knn_take(KnnList& L, bool valid, float cd, int ci, int km1, int lane) {
+  const bool pass = valid && nn_better(cd, ci, L.kd, L.ki);
+  const unsigned mask = __ballot_sync(0xffffffffu, pass);
+  if (mask == 0u) return;
+  if (pass) {
+    const int slot = L.ns + __popc(mask & ((1u << lane) - 1u));
+    L.bd[slot] = cd;
+    L.bi[slot] = ci;
+  }
+  L.ns += __popc(mask);
+  if (L.ns >= 32) knn_merge_staged(L, km1, lane);
+}
+
+// offer the points [s, e) of the cell-ordered array (the brute-force slices): four loads in flight per lane
+__device__ __forceinline__ void knn_offer_range(const NnView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, int km1, int lane, KnnList& L) {
+  for (uint32_t j0 = s; j0 < e; j0 += 128) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t j = j0 + 32u * u + lane;
+      p[u] = j < e ? __ldg(g.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float kd = __shfl_sync(0xffffffffu, td, km1);
-    const int ki = __shfl_sync(0xffffffffu, ti, km1);
-    if (__ballot_sync(0xffffffffu, nn_better(cd, ci, kd, ki)) == 0u) continue;
-    knn_merge32(td, ti, cd, ci, lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t j = j0 + 32u * u + lane;
+      knn_take(L, j < e, l2_simple(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), km1, lane);
+    }
   }
 }
 
-// calculate_covariances (A.5).  covs[i] = {xx, xy, xz, yy, yz, zz} of the regularised covariance.
-__global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4* __restrict__ pts, int n, int k, int reg_method, double* __restrict__ covs) {
-  const int lane = threadIdx.x & 31;
+// offer the runs the lanes hold (run.x .. run.y, empty when equal), FLATTENED: the points of all runs
+// are numbered consecutively, batch b takes points 32 b .. 32 b + 31 whatever run they belong to (the
+// owner of a point is found by a 5-step search over the shuffled prefix sums), and the load of batch
+// b + 1 is issued before batch b is filtered — full batches and two loads in flight instead of one
+// short, dependent load per occupied cell.
+__device__ __forceinline__ void knn_offer_runs(const NnView& g, uint2 run, float qx, float qy, float qz, int km1, int lane, KnnList& L) {
+  const uint32_t len = run.y - run.x;
+  uint32_t incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0u) return;
+  const uint32_t first = run.x - (incl - len);  // point t of the flattened order owned by this lane sits at first + t
+  auto fetch = [&](uint32_t t0, float4& p) -> bool {
+    const uint32_t t = t0 + lane;
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, o + step - 1);
+      if (v <= t) o += step;
+    }
+    const uint32_t f = __shfl_sync(0xffffffffu, first, o & 31);
+    const bool ok = t < total;
+    p = ok ? __ldg(g.pts + (f + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return ok;
+  };
+  float4 p_cur, p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool ok_cur = fetch(0u, p_cur), ok_next = false;
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    if (t0 + 32 < total) ok_next = fetch(t0 + 32, p_next);
+    knn_take(L, ok_cur, l2_simple(qx, qy, qz, p_cur.x, p_cur.y, p_cur.z), __float_as_int(p_cur.w), km1, lane);
+    p_cur = p_next;
+    ok_cur = ok_next;
+    ok_next = false;
+  }
+}
+
+// neighbours as columns, minus the row-wise mean over the k REQUESTED columns, cov = N N^T / k
+// (calculate_covariances, A.5).  Lanes 0..5 return xx, xy, xz, yy, yz, zz in c.
+__device__ __forceinline__ double knn_raw_covariance(const float4* __restrict__ pts, int k, int lane, float td, int ti) {
+  (void)td;
+  const bool have = lane < k && ti != kNoIndex;
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (have) nb = __ldg(pts + ti);
+  const double kd = (double)k;
+  double m0 = have ? (double)nb.x : 0.0, m1 = have ? (double)nb.y : 0.0, m2 = have ? (double)nb.z : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  }
+  m0 /= kd; m1 /= kd; m2 /= kd;
+  const double v0 = have ? (double)nb.x - m0 : 0.0, v1 = have ? (double)nb.y - m1 : 0.0, v2 = have ? (double)nb.z - m2 : 0.0;
+  double c6[6] = {v0 * v0, v0 * v1, v0 * v2, v1 * v1, v1 * v2, v2 * v2};
+  double mine = 0.0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c6[a] += __shfl_xor_sync(0xffffffffu, c6[a], o);
+    c6[a] /= kd;
+    if (lane == a) mine = c6[a];
+  }
+  return mine;
+}
+
+// calculate_covariances, step 1: exact k nearest neighbours + raw covariance, one warp per point.
+// covs[i] = {xx, xy, xz, yy, yz, zz} (not yet regularised).  A point whose k-th neighbour is not settled
+// within kKnnMaxRing rings (an isolated return) goes to `pending` for the block-per-query scan.
+__global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __restrict__ pts, int n, int k, double* __restrict__ covs, int* __restrict__ pending,
+                                                  unsigned int* __restrict__ n_pending) {
+  __shared__ float s_bd[8][64];
+  __shared__ int s_bi[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // queries are taken in cell order: neighbouring warps touch neighbouring cells
   if (w >= n) return;
   const GridParams gp = g.meta->grid;
@@ -93,15 +217,51 @@ __global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4
   const float qx = qp.x, qy = qp.y, qz = qp.z;
   const NnQuery q = nn_make_query(gp, qx, qy, qz);
   const int km1 = k - 1;
-  float td = 3.402823466e+38f;
-  int ti = kNoIndex;
+  KnnList L;
+  knn_init(L, s_bd[warp], s_bi[warp]);
   bool open = true;
   const bool use_occ = nn_occ_valid(g);
   for (int r = 0; r <= kKnnMaxRing && open; ++r) {
-    const float kd = __shfl_sync(0xffffffffu, td, km1);
-    const int ki = __shfl_sync(0xffffffffu, ti, km1);
-    if (r >= 1 && nn_settled(gp, q, r, ki == kNoIndex ? 3.402823466e+38f : kd, 3.402823466e+38f)) { open = false; break; }
+    knn_flush(L, km1, lane);  // the settle test needs the exact k-th
+    if (r >= 1 && nn_settled(gp, q, r, L.ki == kNoIndex ? 3.402823466e+38f : L.kd, 3.402823466e+38f)) { open = false; break; }
     const int side = 2 * r + 1, inner = 2 * r - 1;
+    if (use_occ && r >= 2 && side <= 32) {
+      // outer rings row by row through the occupancy bitmap (see nn_query_far_warp): a lane takes a row
+      // of the shell, keeps the bits of its occupied shell cells, and the warp then consumes one cell
+      // per lane and round until no lane has a bit left
+      const int x0 = max(q.cx - r, gp.min_b[0]), x1 = min(q.cx + r, gp.max_b[0]);
+      if (x0 > x1) continue;
+      const int nb = x1 - x0 + 1;
+      uint32_t ends = 0u;
+      if (q.cx - r >= gp.min_b[0]) ends |= 1u;
+      if (q.cx + r <= gp.max_b[0]) ends |= 1u << (nb - 1);
+      const int xq = min(max(q.cx, gp.min_b[0]), gp.max_b[0]);
+      for (int row0 = 0; row0 < side * side; row0 += 32) {
+        const int row = row0 + lane;
+        uint32_t bits = 0u, key0 = 0u;
+        int iy = 0, iz = 0;
+        if (row < side * side) {
+          const int dz = row / side - r, dy = row - (dz + r) * side - r;
+          iy = q.cy + dy; iz = q.cz + dz;
+          const bool in = iy >= gp.min_b[1] && iy <= gp.max_b[1] && iz >= gp.min_b[2] && iz <= gp.max_b[2];
+          if (in && (L.ki == kNoIndex || nn_box_d2(gp, q, xq, iy, iz) <= L.kd)) {
+            key0 = (uint32_t)((x0 - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+            bits = nn_occ_bits(g, key0, nb);
+            if (!(dy == -r || dy == r || dz == -r || dz == r)) bits &= ends;
+          }
+        }
+        while (__any_sync(0xffffffffu, bits != 0u)) {
+          uint2 run = make_uint2(0u, 0u);
+          if (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            if (L.ki == kNoIndex || nn_box_d2(gp, q, x0 + b, iy, iz) <= L.kd) run = nn_lookup(g, key0 + (uint32_t)b * (uint32_t)gp.mul[0]);
+          }
+          knn_offer_runs(g, run, qx, qy, qz, km1, lane, L);
+        }
+      }
+      continue;
+    }
     const int nz = r == 0 ? 1 : 2 * side * side, ny = r == 0 ? 0 : 2 * side * inner, total = r == 0 ? 1 : nz + ny + 2 * inner * inner;
     for (int c0 = 0; c0 < total; c0 += 32) {
       const int c = c0 + lane;
@@ -122,56 +282,68 @@ __global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4
         }
         const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
         const bool in = ix >= gp.min_b[0] && ix <= gp.max_b[0] && iy >= gp.min_b[1] && iy <= gp.max_b[1] && iz >= gp.min_b[2] && iz <= gp.max_b[2];
-        if (in && (ki == kNoIndex || nn_box_d2(gp, q, ix, iy, iz) <= kd)) {
+        if (in && (L.ki == kNoIndex || nn_box_d2(gp, q, ix, iy, iz) <= L.kd)) {
           const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
           if (!use_occ || nn_occ_bit(g, key)) run = nn_lookup(g, key);  // most cells of a ring are empty: one bitmap bit instead of a hash walk
         }
       }
-      unsigned mask = __ballot_sync(0xffffffffu, run.y > run.x);
-      while (mask) {
-        const int L = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t s = __shfl_sync(0xffffffffu, run.x, L), e = __shfl_sync(0xffffffffu, run.y, L);
-        knn_offer_run(g, s, e, qx, qy, qz, km1, lane, td, ti);
-      }
+      knn_offer_runs(g, run, qx, qy, qz, km1, lane, L);
     }
   }
   if (open) {
-    const float kd = __shfl_sync(0xffffffffu, td, km1);
-    const int ki = __shfl_sync(0xffffffffu, ti, km1);
-    if (!nn_settled(gp, q, kKnnMaxRing + 1, ki == kNoIndex ? 3.402823466e+38f : kd, 3.402823466e+38f)) {
-      td = 3.402823466e+38f;  // an isolated point: start over as a linear scan of the whole cloud
-      ti = kNoIndex;
-      knn_offer_run(g, 0u, (uint32_t)g.n, qx, qy, qz, km1, lane, td, ti);
+    knn_flush(L, km1, lane);
+    if (!nn_settled(gp, q, kKnnMaxRing + 1, L.ki == kNoIndex ? 3.402823466e+38f : L.kd, 3.402823466e+38f)) {
+      if (lane == 0) pending[atomicAdd(n_pending, 1u)] = w;
+      return;
     }
   }
-  // neighbours as columns, minus the row-wise mean over the k REQUESTED columns, cov = N N^T / k
-  const bool have = lane < k && ti != kNoIndex;
-  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (have) nb = __ldg(pts + ti);
-  const double kd = (double)k;
-  double m0 = have ? (double)nb.x : 0.0, m1 = have ? (double)nb.y : 0.0, m2 = have ? (double)nb.z : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
-    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
-    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);
+  if (lane < 6) covs[(size_t)qi * 6 + lane] = c;
+}
+
+// step 1b: one CTA per isolated point: every warp scans its own eighth of the cloud with the same
+// filtered list, the eight lists are merged by warp 0
+__global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* __restrict__ pts, int k, double* __restrict__ covs, const int* __restrict__ pending,
+                                                        const unsigned int* __restrict__ n_pending) {
+  __shared__ float s_bd[8][64];
+  __shared__ int s_bi[8][64];
+  __shared__ float s_ld[8][32];
+  __shared__ int s_li[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int np = (int)*n_pending;
+  const int km1 = k - 1;
+  const uint32_t chunk = (((uint32_t)g.n + 7u) / 8u + 31u) & ~31u;
+  for (int e = blockIdx.x; e < np; e += gridDim.x) {
+    const int w = pending[e];
+    const float4 qp = __ldg(g.pts + w);
+    KnnList L;
+    knn_init(L, s_bd[warp], s_bi[warp]);
+    const uint32_t s0 = min((uint32_t)g.n, chunk * (uint32_t)warp), s1 = min((uint32_t)g.n, s0 + chunk);
+    knn_offer_range(g, s0, s1, qp.x, qp.y, qp.z, km1, lane, L);
+    knn_flush(L, km1, lane);
+    __syncthreads();  // the previous query's lists have been consumed
+    s_ld[warp][lane] = L.td;
+    s_li[warp][lane] = L.ti;
+    __syncthreads();
+    if (warp == 0) {
+      for (int o = 1; o < 8; ++o) knn_merge32(L.td, L.ti, s_ld[o][lane], s_li[o][lane], lane);
+      const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);
+      if (lane < 6) covs[(size_t)__float_as_int(qp.w) * 6 + lane] = c;
+    }
   }
-  m0 /= kd; m1 /= kd; m2 /= kd;
-  const double v0 = have ? (double)nb.x - m0 : 0.0, v1 = have ? (double)nb.y - m1 : 0.0, v2 = have ? (double)nb.z - m2 : 0.0;
-  double c6[6] = {v0 * v0, v0 * v1, v0 * v2, v1 * v1, v1 * v2, v2 * v2};
-#pragma unroll
-  for (int a = 0; a < 6; ++a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c6[a] += __shfl_xor_sync(0xffffffffu, c6[a], o);
-    c6[a] /= kd;
-  }
-  if (lane != 0) return;
+}
+
+// step 2: regularisation, one thread per point, in place (thirty-two eigen-decompositions per warp
+// instead of one lane of a warp each)
+__global__ void __launch_bounds__(128) k_gicp_regularize(int n, int reg_method, double* __restrict__ covs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* o = covs + (size_t)i * 6;
+  const double c6[6] = {o[0], o[1], o[2], o[3], o[4], o[5]};
   const double c[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
   double out[9];
   if (reg_method == B200REG_REG_NONE) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) out[a] = c[a];
+    return;
   } else if (reg_method == B200REG_REG_FROBENIUS) {
     const double lambda = 1e-3;
     double C[9], Ci[9];
@@ -209,7 +381,6 @@ __global__ void __launch_bounds__(256) k_gicp_covariances(NnView g, const float4
         for (int b = 0; b < 3; ++b) out[3 * a + b] += values[s] * V[3 * a + col] * V[3 * b + col];
     }
   }
-  double* o = covs + (size_t)qi * 6;
   o[0] = out[0]; o[1] = out[1]; o[2] = out[2]; o[3] = out[4]; o[4] = out[5]; o[5] = out[8];
 }
 
@@ -508,7 +679,8 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     // phase (rings 0-1) and finishes the point; the few queries left open are queued in shared memory
     // and, after a block barrier, dealt round-robin to the CTA's 16 warps for the cooperative far
     // search — so a warp that happened to draw several far points does not hold up the pass.
-    const int stride = G * kGicpThreads;
+    const int stride = G * kGicpWarps;  // 32-point groups per sweep of the whole grid
+    const int n_groups32 = (n_src + 31) >> 5;
     auto finish_point = [&](int i, const float4 p, float best, int best_idx) {
       int c = -1;
       if (best_idx != kNoIndex && (double)best < prm.corr_dist2) c = best_idx;
@@ -525,9 +697,13 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
       for (int k = 0; k < 6; ++k) pm[k] = M[k];
       gicp_residual<true>(s, p, __ldg(job.tgt_pts + c), M, acc);
     };
-    for (int b0 = rank * kGicpThreads; b0 < n_src; b0 += stride) {
-      const int i = b0 + tid;
-      const bool active = i < n_src;
+    // 32-point groups are dealt round-robin over the warps of all CTAs (like the NDT pass): source
+    // points without a correspondence come in spatial clumps, and their far searches would otherwise
+    // all land in a few CTAs while the rest of the grid waits at the group barrier
+    for (int q0 = 0; q0 < n_groups32; q0 += stride) {
+      const int qg = q0 + warp * G + rank;
+      const int i = (qg << 5) + lane;
+      const bool active = qg < n_groups32 && i < n_src;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) p = __ldg(job.src + i);
       if (phase == GP_LINEARIZE) {
