@@ -332,7 +332,7 @@ int wait_mail(b200reg_handle* h, volatile unsigned int* flag, unsigned int want)
 }
 
 template <int MODE>
-cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups, const NdtJob* single) {
+cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups, const NdtJob* single, int job_chunk) {
   NdtParams prm;
   prm.search = h->cfg.nn_search;
   prm.resolution = h->cfg.resolution;
@@ -346,16 +346,16 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
   unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
-  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&job_chunk, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
   return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 
-cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr) {
+cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr, int job_chunk = 1) {
   switch (h->cfg.nn_search) {
-    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups, single);
-    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups, single);
-    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups, single);
-    default: return launch_ndt<7>(h, n_jobs, G, n_groups, single);
+    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups, single, job_chunk);
+    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups, single, job_chunk);
+    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups, single, job_chunk);
+    default: return launch_ndt<7>(h, n_jobs, G, n_groups, single, job_chunk);
   }
 }
 
@@ -1103,7 +1103,9 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     if ((rc = ensure_barriers(h, (size_t)(n_groups + 1) * 32))) return rc;
     if ((rc = drain_events(h))) return rc;
     if ((rc = begin_timed_launch(h))) return rc;
-    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups));
+    // many more pairs than SMs: a ticket hands out four consecutive pairs (see k_ndt_align)
+    const int job_chunk = (G == 1 && n_jobs >= 8 * n_groups) ? 4 : 1;
+    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups, nullptr, job_chunk));
     launch_counter() += 1;
     if ((rc = end_timed_launch(h))) return rc;
   }

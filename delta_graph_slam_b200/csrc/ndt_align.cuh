@@ -101,14 +101,29 @@ struct NdtLookup {
   uint32_t s_table, s_voxels, s_centroids;  // shared-window byte addresses (staged grids)
 };
 
+// The hash is bucketised: two (key, record) entries share a 16-byte bucket, insertion fills entry 0,
+// then entry 1, then moves on to the next bucket.  A look-up is ONE 16-byte load and two compares for
+// all but the few keys whose bucket overflowed (a second entry left empty proves a miss), instead of
+// a data-dependent walk over 8-byte entries that diverged for every fourth look-up.
 template <bool STAGED>
-__device__ __forceinline__ uint2 lk_table(const NdtLookup& g, uint32_t h) {
+__device__ __forceinline__ uint4 lk_bucket(const NdtLookup& g, uint32_t b) {
   if (STAGED) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(g.s_table + h * 8u));
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(g.s_table + b * 16u));
     return v;
   }
-  return g.table[h];
+  return reinterpret_cast<const uint4*>(g.table)[b];
+}
+// record of `key` (flags included) or -1, starting from an already loaded first bucket
+template <bool STAGED>
+__device__ __forceinline__ int ndt_resolve(const NdtLookup& g, uint32_t key, uint32_t b, uint4 e) {
+  while (true) {
+    if (e.x == key) return (int)e.y;
+    if (e.z == key) return (int)e.w;
+    if (e.z == kInvalidKey) return -1;
+    b = (b + 1) & g.mask;
+    e = lk_bucket<STAGED>(g, b);
+  }
 }
 template <bool STAGED>
 __device__ __forceinline__ float4 lk_f4(const NdtLookup& g, uint32_t s_base, const float4* p_base, uint32_t index16) {
@@ -122,13 +137,8 @@ __device__ __forceinline__ float4 lk_f4(const NdtLookup& g, uint32_t s_base, con
 
 template <bool STAGED>
 __device__ __forceinline__ int ndt_lookup(const NdtLookup& g, uint32_t key) {
-  uint32_t h = ndt_hash(key, g.mask);
-  while (true) {
-    const uint2 e = lk_table<STAGED>(g, h);
-    if (e.x == key) return (int)e.y;
-    if (e.x == kInvalidKey) return -1;
-    h = (h + 1) & g.mask;
-  }
+  const uint32_t b = ndt_hash(key, g.mask);
+  return ndt_resolve<STAGED>(g, key, b, lk_bucket<STAGED>(g, b));
 }
 
 // ---- the pose -> transform / angle-derivative tables ---------------------------------------
@@ -430,7 +440,7 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
   int pre_slot[kBatchProbes ? NOFF : 1];
   if (kBatchProbes) {
     uint32_t pkey[NOFF], ph[NOFF];
-    uint2 pe[NOFF];
+    uint4 pe[NOFF];
     bool pin[NOFF];
 #pragma unroll
     for (int o = 0; o < NOFF; ++o) {
@@ -439,24 +449,14 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
       pin[o] = !(i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]);
       pkey[o] = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
       ph[o] = ndt_hash(pkey[o], grid.mask);
-      pe[o] = pin[o] ? lk_table<STAGED>(grid, ph[o]) : make_uint2(kInvalidKey, 0u);
+      pe[o] = pin[o] ? lk_bucket<STAGED>(grid, ph[o]) : make_uint4(kInvalidKey, 0u, kInvalidKey, 0u);
     }
 #pragma unroll
     for (int o = 0; o < NOFF; ++o) {
-      int sl = -1;
-      if (pin[o]) {
-        if (pe[o].x == pkey[o]) sl = (int)pe[o].y;
-        else if (pe[o].x != kInvalidKey) {  // collision: walk on from the next cell
-          uint32_t h = (ph[o] + 1) & grid.mask;
-          while (true) {
-            const uint2 e = lk_table<STAGED>(grid, h);
-            if (e.x == pkey[o]) { sl = (int)e.y; break; }
-            if (e.x == kInvalidKey) break;
-            h = (h + 1) & grid.mask;
-          }
-        }
-      }
-      pre_slot[o] = sl;
+      // both entries of the first bucket are compared without a branch; only an overflowed bucket walks on
+      int sl = pe[o].x == pkey[o] ? (int)pe[o].y : (pe[o].z == pkey[o] ? (int)pe[o].w : -1);
+      if (pin[o] && sl < 0 && pe[o].z != kInvalidKey) sl = ndt_resolve<STAGED>(grid, pkey[o], ph[o], pe[o]);
+      pre_slot[o] = pin[o] ? sl : -1;
     }
   }
 #pragma unroll
@@ -593,7 +593,7 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtParams prm, double* partials_all, unsigned int* barriers,
+__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, int job_chunk, NdtParams prm, double* partials_all, unsigned int* barriers,
                                                                 unsigned int* queue, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
   __shared__ int s_job;
@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   unsigned int epoch = 0;
   int parity = 0;
   unsigned int fetched = 0;
+  int chunk_left = 0, chunk_next = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
@@ -619,10 +620,17 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       jb = 0;
       ++fetched;
     } else if (G == 1) {
-      if (tid == 0) s_job = (int)atomicAdd(queue, 1u);
-      __syncthreads();
-      jb = s_job;
-      __syncthreads();
+      // a ticket is worth job_chunk consecutive jobs: the pairs of a loop batch arrive grouped by target,
+      // so the jobs of a chunk usually share their target and its grid is staged once for all of them
+      if (chunk_left == 0) {
+        if (tid == 0) s_job = (int)atomicAdd(queue, 1u);
+        __syncthreads();
+        chunk_next = s_job * job_chunk;
+        chunk_left = job_chunk;
+        __syncthreads();
+      }
+      jb = chunk_next++;
+      --chunk_left;
     } else {
       unsigned int* mailbox = barrier + 1 + (fetched & 1u);
       if (rank == 0 && tid == 0) {
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       const uint32_t n_rec = job.grid.gmeta->n_records, cap = job.grid.gmeta->table_cap;
       const size_t table_bytes = (size_t)cap * sizeof(uint2), vox_bytes = (size_t)n_rec * sizeof(NdtVoxel);
       const size_t cen_bytes = MODE == 0 ? (size_t)n_rec * sizeof(float4) : 0;
-      look.mask = cap - 1;
+      look.mask = cap / 2 - 1;  // buckets of two entries
       if (table_bytes + vox_bytes + cen_bytes <= (size_t)kStageBytes) {
         if (staged_table != (const void*)job.grid.table) {
           __syncthreads();
@@ -728,13 +736,19 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         // scoreboard was the top stall of the one-CTA-per-registration configuration)
         const int qstride = G * kAlignWarps;
         int q = warp * G + rank;
-        float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < n_groups32 && (q << 5) + lane < n_src) pt_next = __ldg(job.src + (q << 5) + lane);
+        // two groups ahead: with one SM per registration the 148 source clouds of a batch do not stay in
+        // L2, and one group of look-ahead did not cover an HBM round trip (ncu: long scoreboard on the
+        // first use of the point was the top stall of the batch configuration)
+        auto fetch = [&](int qq) -> float4 {
+          const int ii = (qq << 5) + lane;
+          return (qq < n_groups32 && ii < n_src) ? __ldg(job.src + ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 pt_n1 = fetch(q), pt_n2 = fetch(q + qstride);
         for (; q < n_groups32; q += qstride) {
           const int i = (q << 5) + lane;
-          const float4 pt = pt_next;
-          const int in = ((q + qstride) << 5) + lane;
-          if (q + qstride < n_groups32 && in < n_src) pt_next = __ldg(job.src + in);
+          const float4 pt = pt_n1;
+          pt_n1 = pt_n2;
+          pt_n2 = fetch(q + 2 * qstride);
           if (i < n_src) {
             if (grid_staged) ndt_point<MODE, true>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);
             else ndt_point<MODE, false>(s, look, gp, pt, d1h, d1l, gd2, res2, need_h, vals);

@@ -233,11 +233,14 @@ static __global__ void __launch_bounds__(1024) k_ndt_table(NdtLeafArgs a, const 
     float4* vdst = reinterpret_cast<float4*>(a.voxels + d);
     vdst[0] = v0; vdst[1] = v1; vdst[2] = v2;
     a.centroids[d] = c;
-    uint32_t h = ndt_hash(key, cap - 1);
+    // bucketised insert (see lk_bucket in ndt_align.cuh): entry 0 of the bucket, then entry 1, then the next bucket
+    uint32_t b = ndt_hash(key, cap / 2 - 1);
     while (true) {
-      const uint32_t old = atomicCAS(&a.table[h].x, kInvalidKey, key);
-      if (old == kInvalidKey) { a.table[h].y = rec; break; }
-      h = (h + 1) & (cap - 1);
+      uint32_t old = atomicCAS(&a.table[2 * b].x, kInvalidKey, key);
+      if (old == kInvalidKey) { a.table[2 * b].y = rec; break; }
+      old = atomicCAS(&a.table[2 * b + 1].x, kInvalidKey, key);
+      if (old == kInvalidKey) { a.table[2 * b + 1].y = rec; break; }
+      b = (b + 1) & (cap / 2 - 1);
     }
   }
 }
