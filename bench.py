@@ -60,6 +60,21 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(label):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (tools/ncu_traffic.py -> profiles/*_ncu_traffic.json); None when no capture is on file."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f).get(label)
+            if t:
+                return float(t["dram_bytes_per_launch"])
+        except Exception:
+            pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -388,7 +403,8 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
         "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
                 "wall_ms_per_step": 1e3 * wall_h / steps},
         "gpu_launches": int(launches_timed),
-        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                     "traffic": load_traffic("k_ndt_align_single" if is_ndt else "k_gicp_align"), "traffic_unit": "DRAM bytes per launch (ncu --set full capture of one registration of this workload)",
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms, "launches": int(n_al),
                      "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / steps),
                      "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
@@ -519,7 +535,7 @@ def bench_loop(ctx, steps, warmup):
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
         "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7> (one CTA per registration)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
+                     "traffic": None, "traffic_per_registration": load_traffic("k_ndt_align_batch_per_registration"), "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "checks": {"device_and_host_legs_bit_identical": legs_equal, "median_translation_error_m": float(np.median(err_t)), "pairs_within_5cm_of_ground_truth": float(np.mean(err_t < 0.05)),

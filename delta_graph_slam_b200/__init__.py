@@ -9,9 +9,10 @@ the C ABI in include/b200reg.h); this package is the thin host mirror used by te
 from . import _lib
 from ._lib import B200RegError, DIRECT1, DIRECT7, DIRECT26, KDTREE
 from . import loop_batch
+from .information_matrix import InformationMatrixCalculator
 from .loop_detector import KeyFrame, Loop, LoopDetector, transform2Dto3D
 from .odometry import FrontEnd, Prefilter, ScanMatchingOdometry
 from .registration import DBL_MAX, DeviceCloud, FastGICP, NormalDistributionsTransform, Registration, VoxelGrid, select_registration_method
 
-__all__ = ["KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "Registration", "VoxelGrid",
+__all__ = ["InformationMatrixCalculator", "KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "Registration", "VoxelGrid",
            "select_registration_method"]

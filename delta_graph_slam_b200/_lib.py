@@ -28,7 +28,7 @@ EXPORTS = [
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
     "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_end", "b200reg_set_sm_budget",
-    "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_get_batch_timing",
+    "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
     "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
 
@@ -117,6 +117,7 @@ def load():
     L.b200reg_cloud_clear.argtypes = [vp]
     L.b200reg_cloud_count.argtypes = [vp, szp]
     L.b200reg_align_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp]
+    L.b200reg_calc_fitness_batch.argtypes = [vp, vp, C.c_size_t, C.c_double, vp]
     L.b200reg_get_batch_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.b200reg_ndt_num_leaves.argtypes = [vp, szp]
     L.b200reg_ndt_get_leaves.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

@@ -1011,11 +1011,13 @@ int b200reg_cloud_count(b200reg_handle* h, size_t* out) {
   return B200REG_OK;
 }
 
-int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
+// do_align = 0: no registration, the pair's `guess` IS the transform the fitness is evaluated at
+// (b200reg_calc_fitness_batch); only the exact-NN product of the targets is needed then
+static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int do_align, int with_fitness, double fitness_max_range, b200reg_result* results) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || (n_pairs && (!pairs || !results))) return B200REG_E_INVALID;
   if (!n_pairs) return B200REG_OK;
-  if (h->cfg.method != B200REG_METHOD_NDT) { h->err = "align_batch: this handle's registration method has no batch path"; return B200REG_E_STATE; }
+  if (do_align && h->cfg.method != B200REG_METHOD_NDT) { h->err = "align_batch: this handle's registration method has no batch path"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
   const float res = (float)h->cfg.resolution;
@@ -1032,7 +1034,7 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     std::vector<CachedCloud*> todo;
     for (size_t i = 0; i < n_pairs; ++i) {
       CachedCloud& c = *tgt[i];
-      const bool need = !c.has_ndt || c.ndt_res != res || (with_fitness && !c.has_nn);
+      const bool need = (do_align && (!c.has_ndt || c.ndt_res != res)) || (with_fitness && !c.has_nn);
       if (need && std::find(todo.begin(), todo.end(), &c) == todo.end()) todo.push_back(&c);
     }
     if (!todo.empty()) {
@@ -1050,7 +1052,7 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
       for (size_t k = 0; k < todo.size(); ++k) {
         auto& ln = h->lanes[k % n_lanes];
         CachedCloud& c = *todo[k];
-        if (!c.has_ndt || c.ndt_res != res) B200_CUDA_TRY(cache_build_ndt(ln.st, ln.grid, c, res));
+        if (do_align && (!c.has_ndt || c.ndt_res != res)) B200_CUDA_TRY(cache_build_ndt(ln.st, ln.grid, c, res));
         if (with_fitness && !c.has_nn) B200_CUDA_TRY(cache_build_nn(ln.st, ln.nn, c));
       }
       for (int l = 0; l < n_lanes; ++l) {  // join
@@ -1093,7 +1095,7 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
   }
   B200_CUDA_TRY(cudaMemcpyAsync(h->batch_results.p, hr, n_pairs * sizeof(b200reg_result), cudaMemcpyHostToDevice, h->stream));
   h->batch_align_ms = h->batch_fitness_ms = 0.0;
-  if (n_jobs) {
+  if (n_jobs && do_align) {
     B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, hj, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
     // few pairs: several SMs cooperate on each; a full batch: one SM per registration, no grid-wide sync at all
     int G = h->num_sm / n_jobs;
@@ -1155,7 +1157,7 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
   memcpy(results, hr, n_pairs * sizeof(b200reg_result));
   if (!with_fitness)
     for (size_t i = 0; i < n_pairs; ++i) results[i].fitness = 1.7976931348623157e308;
-  if (h->timing && n_jobs) {
+  if (h->timing && n_jobs && do_align) {
     const double before = h->align_ms;
     if ((rc = drain_events(h))) return rc;
     h->batch_align_ms = h->align_ms - before;
@@ -1166,6 +1168,19 @@ int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_p
     }
   }
   if (evf0) { cudaEventDestroy(evf0); cudaEventDestroy(evf1); }
+  return B200REG_OK;
+}
+
+int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
+  return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, results);
+}
+
+int b200reg_calc_fitness_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, double max_range, double* out) {
+  if (!h || (n_pairs && (!pairs || !out))) return B200REG_E_INVALID;
+  std::vector<b200reg_result> res(n_pairs);
+  const int rc = batch_run(h, pairs, n_pairs, 0, 1, max_range, res.data());
+  if (rc) return rc;
+  for (size_t i = 0; i < n_pairs; ++i) out[i] = res[i].fitness;
   return B200REG_OK;
 }
 

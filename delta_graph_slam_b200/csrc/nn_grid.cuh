@@ -28,9 +28,9 @@ constexpr int kNearRing = 1;   // rings walked by the thread-per-query phase
 #define B200_NN_CELL 0.5f
 #endif
 #ifndef B200_NN_FAR_RING
-#define B200_NN_FAR_RING 8
+#define B200_NN_FAR_RING 15
 #endif
-constexpr int kFarRing = B200_NN_FAR_RING;  // rings walked by the warp-per-query phase before the brute-force pass (4 m)
+constexpr int kFarRing = B200_NN_FAR_RING;  // rings walked by the warp-per-query phase before the brute-force pass (7.5 m; rows of the occupancy bitmap, so a ring is cheap)
 constexpr float kNnCell = B200_NN_CELL;
 
 struct NnView {

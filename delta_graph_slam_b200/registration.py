@@ -204,6 +204,21 @@ class Registration:
             self._ck(_lib.load().b200reg_align_batch(self._h, arr.ctypes.data, len(arr), int(with_fitness), float(fitness_max_range), out.ctypes.data))
         return out
 
+    def calcFitnessBatch(self, pairs, max_range=DBL_MAX):
+        """calc_fitness_score(cloud1 = target_id, cloud2 = source_id, relpose) for every pair of cached
+        keyframes; pairs as in alignBatch with the relative pose in the `guess` slot.  Returns float64[n]."""
+        if isinstance(pairs, np.ndarray) and pairs.dtype == _lib.PAIR_DTYPE:
+            arr = np.ascontiguousarray(pairs)
+        else:
+            pairs = list(pairs)
+            arr = np.zeros(len(pairs), _lib.PAIR_DTYPE)
+            for i, (t, s, g) in enumerate(pairs):
+                arr[i] = (int(t), int(s), _lib.colmajor(np.eye(4) if g is None else g))
+        out = np.zeros(len(arr), np.float64)
+        if len(arr):
+            self._ck(_lib.load().b200reg_calc_fitness_batch(self._h, arr.ctypes.data, len(arr), float(max_range), out.ctypes.data))
+        return out
+
     def batchTiming(self):
         a, b = C.c_double(), C.c_double()
         self._ck(_lib.load().b200reg_get_batch_timing(self._h, C.byref(a), C.byref(b)))

@@ -187,6 +187,14 @@ int b200reg_cloud_drop(b200reg_handle* h, int64_t id);
 int b200reg_cloud_clear(b200reg_handle* h);
 int b200reg_cloud_count(b200reg_handle* h, size_t* out);
 int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results);
+/* InformationMatrixCalculator::calc_fitness_score for many keyframe pairs at once
+ * [REF src/hdl_graph_slam/information_matrix_calculator.cpp:53-108; called per odometry edge and per
+ * accepted loop, apps/delta_graph_slam_nodelet.cpp:572,820]: cloud1 = target_id (the exact-NN structure
+ * is built once and kept with the cached cloud, where the reference builds a fresh kd-tree per call),
+ * cloud2 = source_id, relpose = the pair's `guess` field (column-major float 4x4).  out[i] is the mean
+ * squared nearest-neighbour distance over the points with d2 <= max_range, DBL_MAX when there is none.
+ * No registration runs; works on a handle of any method. */
+int b200reg_calc_fitness_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, double max_range, double* out);
 /* with timing on: CUDA-event durations of the last batch's align kernel and fitness kernels */
 int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double* fitness_ms);
 

@@ -1,6 +1,6 @@
-for lib in libb200reg.so libb200reg_c70.so libb200reg_c100.so; do
+for lib in libb200reg.so libb200reg_r15.so; do
   B200REG_LIB=$PWD/delta_graph_slam_b200/$lib python bench.py --workload loop --loop-targets 64 --steps 2 --warmup 2 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('$lib', 'pairs/s %.0f'%d['value'], 'ms/step %.1f'%d['ms_per_step'], 'align %.1f'%d['roofline']['avg_launch_ms'], 'fitness %.1f'%d['roofline']['fitness_ms_per_step'], d['checks'])"
+print('$lib', 'pairs/s %.0f'%d['value'], 'ms/step %.1f'%d['ms_per_step'], 'align %.1f'%d['roofline']['avg_launch_ms'], 'fitness %.1f'%d['roofline']['fitness_ms_per_step'])"
 done
