@@ -31,6 +31,8 @@ struct HostMailbox {
   VgCounts vg;
   volatile unsigned int align_seq;
   volatile unsigned int vg_seq;
+  RorCounts ror;
+  volatile unsigned int ror_seq;
 };
 
 struct b200reg_handle {
@@ -52,6 +54,23 @@ struct b200reg_handle {
   DevBuf<VgCounts> vg_counts;
   DevBuf<unsigned int> vg_done;
   int vg_last_n = 0, vg_last_out = 0;
+  PointGate gate = kNoGate;  // distance_filter fused into the filter's key pipeline (b200reg_set_distance_filter)
+  // pcl::RadiusOutlierRemoval: its own NN structure and staging, so a VoxelGrid call of the next scan
+  // can be in flight on the same handle
+  NnGrid nn_ror;
+  DevBuf<float4> ror_in, ror_out;
+  PinnedBuf<float4> ror_pin_in, ror_pin_out;
+  DevBuf<unsigned char> ror_keep;
+  DevBuf<uint32_t> ror_block_count;
+  DevBuf<RorCounts> ror_counts;
+  DevBuf<unsigned int> ror_done;
+  unsigned int ror_seq = 0;
+  struct RorPending {
+    bool active = false;
+    float* host_out = nullptr;
+    size_t cap = 0;
+    bool zero_copy = false, device = false;
+  } ror_pending;
   // filter call in flight (b200reg_voxelgrid_filter_begin .. _end)
   struct VgPending {
     bool active = false;
@@ -98,6 +117,9 @@ struct b200reg_handle {
   cudaEvent_t ev_fork = nullptr;
   std::map<long long, CachedCloud> cache;
   DevBuf<b200reg_result> batch_results;
+  DevBuf<uint2> tq_runs;
+  DevBuf<unsigned int> tq_next;
+  PinnedBuf<uint2> pin_runs;
   DevBuf<FitJob> fit_jobs;
   DevBuf<float> batch_d2;
   DevBuf<uint2> batch_pending, batch_pending2;
@@ -243,7 +265,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1>)); B200_ATTR(prefer_shared(k_ndt_align<7>)); B200_ATTR(prefer_shared(k_ndt_align<27>)); B200_ATTR(prefer_shared(k_ndt_align<0>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -332,7 +354,7 @@ int wait_mail(b200reg_handle* h, volatile unsigned int* flag, unsigned int want)
 }
 
 template <int MODE>
-cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups, const NdtJob* single, int job_chunk) {
+cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_groups, const NdtJob* single, NdtTargetQueue tq) {
   NdtParams prm;
   prm.search = h->cfg.nn_search;
   prm.resolution = h->cfg.resolution;
@@ -346,16 +368,16 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   double* partials = h->partials.p;
   unsigned int* barriers = h->barriers.p;
   unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
-  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&job_chunk, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
+  void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&tq, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
   return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 
-cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr, int job_chunk = 1) {
+cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr, NdtTargetQueue tq = NdtTargetQueue{nullptr, nullptr, 0}) {
   switch (h->cfg.nn_search) {
-    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups, single, job_chunk);
-    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups, single, job_chunk);
-    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups, single, job_chunk);
-    default: return launch_ndt<7>(h, n_jobs, G, n_groups, single, job_chunk);
+    case B200REG_DIRECT1: return launch_ndt<1>(h, n_jobs, G, n_groups, single, tq);
+    case B200REG_DIRECT26: return launch_ndt<27>(h, n_jobs, G, n_groups, single, tq);
+    case B200REG_KDTREE: return launch_ndt<0>(h, n_jobs, G, n_groups, single, tq);
+    default: return launch_ndt<7>(h, n_jobs, G, n_groups, single, tq);
   }
 }
 
@@ -567,7 +589,8 @@ int b200reg_destroy(b200reg_handle* h) {
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
-  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->gicp_corr.release(); h->gicp_pending.release(); h->gicp_n_pending.release(); h->gicp_jobs.release();
+  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release();
+  h->gicp_corr.release(); h->gicp_pending.release(); h->gicp_n_pending.release(); h->gicp_jobs.release();
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
   for (auto& ln : h->lanes) {
@@ -577,7 +600,7 @@ int b200reg_destroy(b200reg_handle* h) {
     ln.nn.release();
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  h->batch_results.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
+  h->batch_results.release(); h->tq_runs.release(); h->tq_next.release(); h->pin_runs.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
   delete h;
   return B200REG_OK;
 }
@@ -812,7 +835,7 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_id.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_counts.reserve(1));
-  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true));
+  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   launch_counter() += 1 + (min_pts > 1 ? 1 : 0);
   // the overflow case publishes from k_vg_centroids even when a compaction pass follows
@@ -825,7 +848,11 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   }
   k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
                                                 min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1, host_out,
-                                                (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap));
+                                                (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->gate.on);
+  if (h->gate.on) {  // only acts in the "leaf size too small" case: the output is then the gated input
+    launch_counter() += 1;
+    k_gate_copy<<<1, 1024, 0, h->stream>>>(d_in, (int)n, h->gate, h->vg_sort.meta.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->vg_counts.p, hc, hf, seq);
+  }
   if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq);
   B200_CUDA_TRY(cudaGetLastError());
   h->vg_last_n = (int)n;
@@ -932,6 +959,123 @@ int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, siz
   int rc = b200reg_voxelgrid_filter_begin(h, xyzw, n, stride, leaf, min_pts, dense, out, cap);
   if (rc) return rc;
   return b200reg_voxelgrid_filter_end(h, n_out);
+}
+
+int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, double far_thresh) {
+  if (!h) return B200REG_E_INVALID;
+  h->gate.on = use ? 1 : 0;
+  h->gate.near_thresh = near_thresh;
+  h->gate.far_thresh = far_thresh;
+  return B200REG_OK;
+}
+
+// ---- RadiusOutlierRemoval ----------------------------------------------------------------------
+static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, double radius, int min_neighbors, float4* d_out, float4* host_out, size_t host_cap) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0));
+  const int blocks = n ? (int)((n + 255) / 256) : 1;
+  B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));
+  B200_CUDA_TRY(h->ror_block_count.reserve(blocks));
+  B200_CUDA_TRY(h->ror_counts.reserve(1));
+  if (!h->ror_done.p) {
+    B200_CUDA_TRY(h->ror_done.reserve(1));
+    B200_CUDA_TRY(cudaMemsetAsync(h->ror_done.p, 0, h->ror_done.cap * sizeof(unsigned int), h->stream));
+  }
+  const float r2 = (float)(radius * radius);
+  int rings = (int)ceil(radius / (double)kNnCell);
+  if (rings < 1) rings = 1;
+  RorCounts* hc = const_cast<RorCounts*>(&h->mail->ror);
+  unsigned int* hf = const_cast<unsigned int*>(&h->mail->ror_seq);
+  const unsigned int seq = ++h->ror_seq;
+  launch_counter() += 2;
+  k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
+  k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
+                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200REG_OK;
+}
+
+int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out) {
+  if (!h || !(radius > 0) || min_neighbors < 0 || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
+  if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = ror_run(h, (const float4*)d_xyzw, n, radius, min_neighbors, (float4*)d_out, nullptr, 0))) return rc;
+  h->ror_pending = b200reg_handle::RorPending();
+  h->ror_pending.active = true;
+  h->ror_pending.device = true;
+  return B200REG_OK;
+}
+
+int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !(radius > 0) || min_neighbors < 0 || (n && !xyzw)) return B200REG_E_INVALID;
+  if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
+  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(h->ror_in.reserve(n ? n : 1));
+  B200_CUDA_TRY(h->ror_out.reserve(n ? n : 1));
+  if (n) {
+    if (stride == 16 && is_pinned_host(xyzw)) {
+      B200_CUDA_TRY(cudaMemcpyAsync(h->ror_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      B200_CUDA_TRY(h->ror_pin_in.reserve(n));
+      const unsigned char* b = (const unsigned char*)xyzw;
+      for (size_t i = 0; i < n; ++i) {
+        const float* p = (const float*)(b + i * stride);
+        h->ror_pin_in.p[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 1.0f);
+      }
+      B200_CUDA_TRY(cudaMemcpyAsync(h->ror_in.p, h->ror_pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  const bool zero_copy = out && cap && is_pinned_host(out);
+  if ((rc = ror_run(h, h->ror_in.p, n, radius, min_neighbors, h->ror_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
+  h->ror_pending = b200reg_handle::RorPending();
+  h->ror_pending.active = true;
+  h->ror_pending.host_out = out;
+  h->ror_pending.cap = cap;
+  h->ror_pending.zero_copy = zero_copy;
+  return B200REG_OK;
+}
+
+int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  if (!h->ror_pending.active) { h->err = "no outlier-removal call in flight on this handle"; return B200REG_E_STATE; }
+  const b200reg_handle::RorPending pend = h->ror_pending;
+  h->ror_pending.active = false;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = wait_mail(h, &h->mail->ror_seq, h->ror_seq))) return rc;
+  const size_t m = h->mail->ror.n_out;
+  *n_out = m;
+  if (pend.device) return B200REG_OK;
+  if (m > pend.cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
+  if (!m || pend.zero_copy) return B200REG_OK;
+  if (!pend.host_out) return B200REG_E_INVALID;
+  B200_CUDA_TRY(h->ror_pin_out.reserve(m));
+  B200_CUDA_TRY(cudaMemcpyAsync(h->ror_pin_out.p, h->ror_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  memcpy(pend.host_out, h->ror_pin_out.p, m * 16);
+  return B200REG_OK;
+}
+
+int b200reg_radius_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_radius_outlier_removal_begin(h, xyzw, n, stride, radius, min_neighbors, out, cap);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_radius_outlier_removal_device_begin(h, d_xyzw, n, radius, min_neighbors, d_out);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
 }
 
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_vox, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow) {
@@ -1105,9 +1249,23 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
     if ((rc = ensure_barriers(h, (size_t)(n_groups + 1) * 32))) return rc;
     if ((rc = drain_events(h))) return rc;
     if ((rc = begin_timed_launch(h))) return rc;
-    // many more pairs than SMs: a ticket hands out four consecutive pairs (see k_ndt_align)
-    const int job_chunk = (G == 1 && n_jobs >= 8 * n_groups) ? 4 : 1;
-    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups, nullptr, job_chunk));
+    // more pairs than SMs: CTAs work through target runs and steal at the end (see NdtTargetQueue)
+    NdtTargetQueue tq{nullptr, nullptr, 0};
+    if (G == 1 && n_jobs > n_groups) {
+      std::vector<uint2> runs;
+      for (int j = 0; j < n_jobs; ++j) {
+        if (j > 0 && hj[j].grid.table == hj[j - 1].grid.table) runs.back().y += 1u;
+        else runs.push_back(make_uint2((unsigned)j, 1u));
+      }
+      B200_CUDA_TRY(h->pin_runs.reserve(runs.size()));
+      memcpy(h->pin_runs.p, runs.data(), runs.size() * sizeof(uint2));
+      B200_CUDA_TRY(h->tq_runs.reserve(runs.size()));
+      B200_CUDA_TRY(h->tq_next.reserve(runs.size()));
+      B200_CUDA_TRY(cudaMemcpyAsync(h->tq_runs.p, h->pin_runs.p, runs.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+      B200_CUDA_TRY(cudaMemsetAsync(h->tq_next.p, 0, runs.size() * sizeof(unsigned int), h->stream));
+      tq.runs = h->tq_runs.p; tq.next = h->tq_next.p; tq.n_runs = (int)runs.size();
+    }
+    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups, nullptr, tq));
     launch_counter() += 1;
     if ((rc = end_timed_launch(h))) return rc;
   }
@@ -1309,6 +1467,7 @@ int b200reg_set_sm_budget(b200reg_handle* h, int n_sm) {
   h->grid.sort.max_ctas = n_sm;
   h->nn.sort.max_ctas = n_sm;
   h->nn_src.sort.max_ctas = n_sm;
+  h->nn_ror.sort.max_ctas = n_sm;
   return B200REG_OK;
 }
 

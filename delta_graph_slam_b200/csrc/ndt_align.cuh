@@ -67,6 +67,13 @@ struct NdtJob {
   long long* prof;         // device, optional: SM cycles of CTA 0 per phase {pass, reduce, barrier, total, step, n, stage}
 };
 
+// Full loop batches: maximal runs of consecutive jobs that share a target, and one counter per run.
+struct NdtTargetQueue {
+  const uint2* runs;   // (first job, number of jobs); nullptr = plain tickets, one job each
+  unsigned int* next;  // per run: jobs handed out so far (zeroed by the host before the launch)
+  int n_runs;
+};
+
 struct NdtShared {
   // inputs of the current pass
   float T[12];
@@ -593,7 +600,7 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, int job_chunk, NdtParams prm, double* partials_all, unsigned int* barriers,
+__global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtTargetQueue tq, NdtParams prm, double* partials_all, unsigned int* barriers,
                                                                 unsigned int* queue, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
   __shared__ int s_job;
@@ -605,7 +612,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   unsigned int epoch = 0;
   int parity = 0;
   unsigned int fetched = 0;
-  int chunk_left = 0, chunk_next = 0;
+  int cur_run = -1;  // target run this CTA is working through (full batches, see NdtTargetQueue)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const void* staged_table = nullptr;  // which grid currently sits in shared memory
 
@@ -620,17 +627,39 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       jb = 0;
       ++fetched;
     } else if (G == 1) {
-      // a ticket is worth job_chunk consecutive jobs: the pairs of a loop batch arrive grouped by target,
-      // so the jobs of a chunk usually share their target and its grid is staged once for all of them
-      if (chunk_left == 0) {
-        if (tid == 0) s_job = (int)atomicAdd(queue, 1u);
-        __syncthreads();
-        chunk_next = s_job * job_chunk;
-        chunk_left = job_chunk;
-        __syncthreads();
+      // Full batches: the pairs arrive grouped by target.  A CTA works through the pairs of ONE target run
+      // (its 200 KB grid is staged once for all of them); runs are handed out from a ticket counter, pairs
+      // inside a run from the run's own counter, and a CTA that finds no run left STEALS pairs from runs
+      // still in progress — so the tail of the batch is one pair long, not one run long.
+      if (tid == 0) {
+        int got = n_jobs;
+        if (tq.runs == nullptr) {
+          got = (int)atomicAdd(queue, 1u);
+        } else {
+          while (true) {
+            if (cur_run >= 0) {
+              const uint2 rn = tq.runs[cur_run];
+              const unsigned int i = atomicAdd(tq.next + cur_run, 1u);
+              if (i < rn.y) { got = (int)(rn.x + i); break; }
+            }
+            const unsigned int t = atomicAdd(queue, 1u);
+            if (t < (unsigned)tq.n_runs) { cur_run = (int)t; continue; }
+            int found = -1;
+            for (int k = 0; k < tq.n_runs; ++k) {
+              const int g = (int)((blockIdx.x + (unsigned)k) % (unsigned)tq.n_runs);
+              unsigned int v;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tq.next + g) : "memory");
+              if (v < tq.runs[g].y) { found = g; break; }
+            }
+            if (found < 0) break;  // every pair of every run has been taken
+            cur_run = found;
+          }
+        }
+        s_job = got;
       }
-      jb = chunk_next++;
-      --chunk_left;
+      __syncthreads();
+      jb = s_job;
+      __syncthreads();
     } else {
       unsigned int* mailbox = barrier + 1 + (fetched & 1u);
       if (rank == 0 && tid == 0) {

@@ -413,6 +413,103 @@ __global__ void __launch_bounds__(256) k_fitness_partial(const float* __restrict
   }
 }
 
+// ---- pcl::RadiusOutlierRemoval [REF apps/prefiltering_nodelet.cpp:88-96,262-273] ----------------
+// keep[i] = 1 when more than min_neighbors points of the same cloud (the point itself included) lie
+// strictly inside the radius.  One thread per point in INPUT order over the cells the radius can
+// reach, pruned by box distance and the occupancy bitmap, stopping as soon as the count is reached.
+// block_count[b] = points kept by block b (for the order-preserving scatter).
+__global__ void __launch_bounds__(256) k_ror_flags(NnView g, const float4* __restrict__ pts, int n, float r2, int rings, int min_neighbors, unsigned char* __restrict__ keep,
+                                                   uint32_t* __restrict__ block_count) {
+  __shared__ uint32_t s_cnt[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int k = 0;
+  if (i < n) {
+    const float4 p = __ldg(pts + i);
+    const GridParams gp = g.meta->grid;
+    if (finite3(p.x, p.y, p.z) && gp.any && !gp.overflow) {
+      const bool use_occ = nn_occ_valid(g);
+      const NnQuery q = nn_make_query(gp, p.x, p.y, p.z);
+      int count = 0;
+      for (int dz = -rings; dz <= rings && count <= min_neighbors; ++dz)
+        for (int dy = -rings; dy <= rings && count <= min_neighbors; ++dy)
+          for (int dx = -rings; dx <= rings && count <= min_neighbors; ++dx) {
+            const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
+            if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
+            if (!(nn_box_d2(gp, q, ix, iy, iz) < r2)) continue;
+            const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+            if (use_occ && !nn_occ_bit(g, key)) continue;
+            const uint2 run = nn_lookup(g, key);
+            for (uint32_t j = run.x; j < run.y && count <= min_neighbors; ++j) {
+              const float4 t = __ldg(g.pts + j);
+              if (l2_simple(p.x, p.y, p.z, t.x, t.y, t.z) < r2) ++count;
+            }
+          }
+      k = count > min_neighbors ? 1 : 0;
+    }
+    keep[i] = (unsigned char)k;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) s_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int w = 0; w < 8; ++w) c += s_cnt[w];
+    block_count[blockIdx.x] = c;
+  }
+}
+
+struct RorCounts { uint32_t n_out; uint32_t pad; };
+// order-preserving scatter: every block sums the counts of the blocks before it (a few hundred words
+// out of L2), scans its own flags, writes; the last block to finish publishes the total
+__global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ pts, int n, const unsigned char* __restrict__ keep, const uint32_t* __restrict__ block_count,
+                                                     float4* __restrict__ out, float4* host_out, unsigned host_cap, RorCounts* __restrict__ counts, RorCounts* host_counts,
+                                                     unsigned int* host_flag, unsigned int host_seq, unsigned int* done_blocks) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t before = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) before += __ldcg(block_count + b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) s_part[warp] = before;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    s_base = t;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = i < n ? (int)keep[i] : 0;
+  const uint32_t bal = __ballot_sync(0xffffffffu, k);
+  __syncthreads();  // s_part is reused
+  if (lane == 0) s_part[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t off = s_base;
+  for (int w = 0; w < warp; ++w) off += s_part[w];
+  if (k) {
+    const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
+    const float4 p = __ldg(pts + i);
+    out[dst] = p;
+    if (host_out && dst < host_cap) host_out[dst] = p;
+  }
+  if (host_out) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(done_blocks, 1u) != gridDim.x - 1) return;
+  *done_blocks = 0u;
+  uint32_t total = 0;
+  for (int b = 0; b < (int)gridDim.x; ++b) total += __ldcg(block_count + b);
+  counts->n_out = total;
+  if (host_counts) {
+    host_counts->n_out = total;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
+  }
+}
+
 struct NnGrid {
   VoxelSort sort;
   DevBuf<float4> pts, queries;
@@ -445,10 +542,10 @@ struct NnGrid {
     while (cap < (uint32_t)(2 * n_points + 1)) cap <<= 1;
     return cap;
   }
-  cudaError_t build(cudaStream_t st, const float4* d_pts, int n_points) {
+  cudaError_t build(cudaStream_t st, const float4* d_pts, int n_points, int is_dense = 1) {
     cudaError_t e;
     n = n_points;
-    if ((e = sort.run(st, d_pts, n, 1, kNnCell, kNnCell, kNnCell, false)) != cudaSuccess) return e;
+    if ((e = sort.run(st, d_pts, n, is_dense, kNnCell, kNnCell, kNnCell, false)) != cudaSuccess) return e;
     if ((e = pts.reserve(n > 0 ? n : 1)) != cudaSuccess) return e;
     table_cap = capacity_for(n);
     if ((e = table.reserve(table_cap)) != cudaSuccess) return e;

@@ -27,6 +27,7 @@ constexpr int kCoopMaxItems = 32;
 struct CoopSortArgs {
   const float4* pts;
   int n, is_dense;
+  PointGate gate;
   float lx, ly, lz;
   SortMeta* meta;
   uint32_t *keys_a, *vals_a, *keys_b, *vals_b;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_voxel_sort_coop(CoopSortArg
     int any = 0;
     for (int i = blockIdx.x * kSortThreads + tid; i < n; i += gridDim.x * kSortThreads) {
       const float4 p = __ldg(a.pts + i);
-      if (!a.is_dense && !finite3(p.x, p.y, p.z)) continue;
+      if (!point_takes_part(a.gate, a.is_dense, p.x, p.y, p.z)) continue;
       mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
       mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
       any = 1;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_voxel_sort_coop(CoopSortArg
     v[r] = (uint32_t)i;
     if (i < n) {
       const float4 p = __ldg(a.pts + i);
-      k[r] = (a.is_dense || finite3(p.x, p.y, p.z)) ? voxel_key(g, p.x, p.y, p.z) : skip;
+      k[r] = point_takes_part(a.gate, a.is_dense, p.x, p.y, p.z) ? voxel_key(g, p.x, p.y, p.z) : skip;
       if (a.point_key) a.point_key[i] = (k[r] == skip) ? kInvalidKey : k[r];
     }
   }
@@ -359,7 +360,7 @@ inline bool coop_sort_items(int n, int num_sm, int* items_out) {
   return true;
 }
 
-inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err) {
+inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, PointGate gate, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err) {
   int items = 2;
   if (!coop_sort_items(n, vs.max_ctas, &items)) return false;
   const int tile = kSortThreads * items;
@@ -374,7 +375,7 @@ inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4*
     if ((e = cudaMemsetAsync(vs.coop_bar.p, 0, vs.coop_bar.cap * sizeof(unsigned int), st)) != cudaSuccess) { *err = e; return true; }
   }
   CoopSortArgs a;
-  a.pts = d_pts; a.n = n; a.is_dense = is_dense; a.lx = lx; a.ly = ly; a.lz = lz;
+  a.pts = d_pts; a.n = n; a.is_dense = is_dense; a.gate = gate; a.lx = lx; a.ly = ly; a.lz = lz;
   a.meta = vs.meta.p; a.keys_a = vs.keys_a.p; a.vals_a = vs.vals_a.p; a.keys_b = vs.keys_b.p; a.vals_b = vs.vals_b.p;
   a.hist = vs.hist.p; a.tile_heads = vs.tile_heads.p; a.vox_start = vs.vox_start.p; a.vox_key = vs.vox_key.p;
   a.point_key = keep_point_keys ? vs.point_key.p : nullptr;

@@ -25,6 +25,26 @@ struct SortMeta {     // device-resident, written by k_grid_keys / k_seg_scan
   uint32_t n_valid;   // points that received a voxel
 };
 
+// ---- which points take part ---------------------------------------------------
+// PrefilteringNodelet::distance_filter [REF apps/prefiltering_nodelet.cpp:275-291] fused into the key
+// pipeline: with the gate on a point takes part when near < |p| < far, |p| = Eigen's float norm()
+// (sqrtf((x*x + y*y) + z*z)) widened to double for the comparison with the double thresholds — the
+// copy_if pass and the cloud it materialises never exist.  NaN / inf fail both comparisons, which is
+// also what the finite test of the is_dense = false cloud the reference hands to VoxelGrid would drop.
+struct PointGate {
+  int on;
+  double near_thresh, far_thresh;
+};
+constexpr PointGate kNoGate = {0, 0.0, 0.0};
+__device__ __forceinline__ bool point_takes_part(const PointGate& gate, int is_dense, float x, float y, float z) {
+  if (gate.on) {
+    const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const double d = (double)__fsqrt_rn(sq);
+    return d > gate.near_thresh && d < gate.far_thresh;
+  }
+  return is_dense || finite3(x, y, z);
+}
+
 // ---- min / max -------------------------------------------------------------
 static __global__ void k_minmax_init(int* mm) {
   if (threadIdx.x < 3) mm[threadIdx.x] = 0x7FFFFFFF;
@@ -32,13 +52,13 @@ static __global__ void k_minmax_init(int* mm) {
   else if (threadIdx.x == 6) mm[6] = 0;
 }
 
-static __global__ void __launch_bounds__(256) k_minmax(const float4* __restrict__ pts, int n, int is_dense, int* mm) {
+static __global__ void __launch_bounds__(256) k_minmax(const float4* __restrict__ pts, int n, int is_dense, PointGate gate, int* mm) {
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
   float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
   int any = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = __ldg(pts + i);
-    if (!is_dense && !finite3(p.x, p.y, p.z)) continue;
+    if (!point_takes_part(gate, is_dense, p.x, p.y, p.z)) continue;
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
     any = 1;
@@ -113,7 +133,7 @@ __device__ __forceinline__ uint32_t voxel_key(const GridParams& g, float x, floa
 }
 
 // keys (A.1 step 4) + pass-0 digit histogram per tile
-static __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __restrict__ pts, int n, int is_dense, float lx, float ly, float lz, const int* __restrict__ mm,
+static __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4* __restrict__ pts, int n, int is_dense, PointGate gate, float lx, float ly, float lz, const int* __restrict__ mm,
                                                              SortMeta* meta, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ point_key) {
   __shared__ GridParams g;
   __shared__ uint32_t s_skip;
@@ -137,7 +157,7 @@ static __global__ void __launch_bounds__(kSortThreads) k_grid_keys(const float4*
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = __ldg(pts + i);
     uint32_t k = s_skip;
-    if (is_dense || finite3(p.x, p.y, p.z)) k = voxel_key(g, p.x, p.y, p.z);
+    if (point_takes_part(gate, is_dense, p.x, p.y, p.z)) k = voxel_key(g, p.x, p.y, p.z);
     keys[i] = k;
     vals[i] = (uint32_t)i;
     if (point_key) point_key[i] = (k == s_skip) ? kInvalidKey : k;
@@ -363,7 +383,7 @@ static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restr
 // ---- host driver -------------------------------------------------------------
 struct VoxelSort;
 // voxel_coop.cuh: the whole pipeline as one cooperative kernel; false = cloud too large, take the multi-kernel path
-bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err);
+bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, PointGate gate, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err);
 // 0 = cooperative single kernel when the cloud fits (default), 1 = always the multi-kernel path (A/B tests)
 inline int& sort_path_override() {
   static int v = 0;
@@ -385,7 +405,7 @@ struct VoxelSort {
 
   // enqueue: keys -> sort -> segmentation.  Afterwards (on the stream):
   //   meta->grid / n_vox / n_valid, sorted (key, point index) in A or B (sorted_in_b), vox_start[0..n_vox], vox_key[0..n_vox)
-  cudaError_t run(cudaStream_t st, const float4* d_pts, int n_points, int is_dense, float lx, float ly, float lz, bool keep_point_keys) {
+  cudaError_t run(cudaStream_t st, const float4* d_pts, int n_points, int is_dense, float lx, float ly, float lz, bool keep_point_keys, PointGate gate = kNoGate) {
     n = n_points;
     cudaError_t e;
     size_t nn = (size_t)(n > 0 ? n : 1);
@@ -400,7 +420,7 @@ struct VoxelSort {
     if (keep_point_keys && (e = point_key.reserve(nn)) != cudaSuccess) return e;
     if (sort_path_override() == 0) {
       cudaError_t ce = cudaSuccess;
-      if (launch_voxel_sort_coop(*this, st, d_pts, n, is_dense, lx, ly, lz, keep_point_keys, &ce)) return ce;
+      if (launch_voxel_sort_coop(*this, st, d_pts, n, is_dense, gate, lx, ly, lz, keep_point_keys, &ce)) return ce;
     }
     int items = 4;
     while (items < 32 && (n + kSortThreads * items - 1) / (kSortThreads * items) > 256) items *= 2;
@@ -417,8 +437,8 @@ struct VoxelSort {
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
     int mm_blocks = n > 0 ? (n + 1023) / 1024 : 1;
     if (mm_blocks > kNumSM * 2) mm_blocks = kNumSM * 2;
-    if (n > 0) k_minmax<<<mm_blocks, 256, 0, st>>>(d_pts, n, is_dense, mm.p);
-    k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
+    if (n > 0) k_minmax<<<mm_blocks, 256, 0, st>>>(d_pts, n, is_dense, gate, mm.p);
+    k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, gate, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
     if (n > 0) {
       for (int pass = 0; pass < 4; ++pass) {
         const uint32_t* ki = (pass & 1) ? keys_b.p : keys_a.p;

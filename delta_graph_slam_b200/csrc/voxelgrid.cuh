@@ -17,14 +17,17 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
                                                       const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_start, const uint32_t* __restrict__ vox_key,
                                                       unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id, uint32_t* __restrict__ out_count,
                                                       VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq,
-                                                      unsigned int* done_blocks, int publish_here, float4* host_out, unsigned host_cap) {
+                                                      unsigned int* done_blocks, int publish_here, float4* host_out, unsigned host_cap, int gated) {
   // host_out (optional): the caller's page-locked output cloud, mapped into the device address space.
   // The centroids are stored there as well (coalesced 16-byte stores over PCIe), so the host needs
   // no D2H copy after the count arrives — the stores are fenced before the flag below.
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool overflow = meta->grid.overflow != 0;  // "Leaf size is too small for the input dataset": output = *input_
   const int n_vox = (int)meta->n_vox;
-  if (overflow) {
+  if (overflow && gated) {
+    // "leaf size too small" with the distance gate on: the output is the GATED input in order, which
+    // k_gate_copy (one block, launched behind this kernel) compacts and publishes
+  } else if (overflow) {
     if (i < n) {
       const float4 p = pts[i];
       out[i] = p;
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
   __threadfence();
   if (atomicAdd(done_blocks, 1u) != gridDim.x - 1) return;
   *done_blocks = 0u;
-  if (!publish_here && !overflow) return;  // a compaction pass follows and publishes instead
+  if ((!publish_here && !overflow) || (overflow && gated)) return;  // a compaction pass follows and publishes instead
   const uint32_t n_out = overflow ? (uint32_t)n : (uint32_t)n_vox;
   counts->n_out = n_out;
   counts->overflow = overflow ? 1u : 0u;
@@ -101,6 +104,49 @@ __global__ void __launch_bounds__(1024) k_vg_compact(const SortMeta* __restrict_
     if (host_counts) {
       host_counts->n_out = s_base;
       host_counts->overflow = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
+    }
+  }
+}
+
+// Overflow case with the distance gate: output = the points that pass the gate, in input order (what
+// pcl::VoxelGrid does with the cloud distance_filter handed it).  One block; never on a hot path.
+__global__ void __launch_bounds__(1024) k_gate_copy(const float4* __restrict__ pts, int n, PointGate gate, const SortMeta* __restrict__ meta, float4* __restrict__ out,
+                                                    float4* host_out, unsigned host_cap, VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq) {
+  if (!meta->grid.overflow) return;  // the regular path published
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    float4 p = make_float4(0, 0, 0, 0);
+    int keep = 0;
+    if (i < n) { p = pts[i]; keep = point_takes_part(gate, 0, p.x, p.y, p.z); }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
+    if (keep) {
+      out[dst] = p;
+      if (host_out && dst < host_cap) host_out[dst] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_base = off + __popc(bal);
+    __syncthreads();
+  }
+  if (host_out) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counts->n_out = s_base;
+    counts->overflow = 1;
+    if (host_counts) {
+      host_counts->n_out = s_base;
+      host_counts->overflow = 1;
       __threadfence_system();
       *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
     }

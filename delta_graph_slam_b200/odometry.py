@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-from .registration import DeviceCloud, VoxelGrid, select_registration_method
+from .registration import DeviceCloud, RadiusOutlierRemoval, VoxelGrid, select_registration_method
 
 
 def quaternion_w(R):
@@ -31,13 +31,21 @@ def quaternion_w(R):
 
 
 class Prefilter:
-    """PrefilteringNodelet::downsample [REF apps/prefiltering_nodelet.cpp:55-75,249-260]:
-    downsample_method VOXELGRID (leaf = downsample_resolution) or NONE."""
+    """PrefilteringNodelet's 3-D chain [REF apps/prefiltering_nodelet.cpp:150-153]: distance_filter (:275-291)
+    -> downsample (:249-260, filter chosen :55-75) -> outlier_removal (:262-273, chosen :77-98), with the
+    reference's parameter names and defaults.  The distance filter is fused into the VoxelGrid call;
+    outlier_removal_method RADIUS runs on the engine, STATISTICAL stays on the reference's
+    pcl::StatisticalOutlierRemoval (NotImplementedError here).  NOTE the mirror's own default for
+    outlier_removal_method is NONE and for use_distance_filter False, so that a Prefilter built from
+    just the down-sampling parameters is the plain VoxelGrid the earlier tests and bench legs use; pass
+    the reference's values (launch/delta_graph_slam.launch:31-42) to get its chain."""
 
     def __init__(self, params=None, device=0, out=sys.stdout):
         p = dict(params or {})
         method = p.get("downsample_method", "VOXELGRID")
         res = p.get("downsample_resolution", 0.1)
+        if p.get("outlier_removal_method", "NONE") == "STATISTICAL":
+            raise NotImplementedError("outlier_removal_method=STATISTICAL stays on the reference's pcl::StatisticalOutlierRemoval; b200reg runs RADIUS")
         self.filter = None
         if method == "VOXELGRID":
             print(f"downsample: VOXELGRID {res:g}", file=out)
@@ -50,6 +58,31 @@ class Prefilter:
                 print(f"warning: unknown downsampling type ({method})", file=sys.stderr)
                 print("       : use passthrough filter", file=sys.stderr)
             print("downsample: NONE", file=out)
+        orm = p.get("outlier_removal_method", "NONE")
+        self.outlier_removal_filter = None
+        if orm == "RADIUS":
+            radius = p.get("radius_radius", 0.8)
+            min_neighbors = p.get("radius_min_neighbors", 2)
+            print(f"outlier_removal: RADIUS {radius:g} - {min_neighbors}", file=out)
+            # same handle (and stream) as the VoxelGrid: the stages of one scan run in order
+            self.outlier_removal_filter = RadiusOutlierRemoval(device=device, registration=self.filter._reg if self.filter is not None else None)
+            self.outlier_removal_filter.setRadiusSearch(radius)
+            self.outlier_removal_filter.setMinNeighborsInRadius(min_neighbors)
+        else:
+            print("outlier_removal: NONE", file=out)
+        self.use_distance_filter = bool(p.get("use_distance_filter", False))
+        self.distance_near_thresh = float(p.get("distance_near_thresh", 1.0))
+        self.distance_far_thresh = float(p.get("distance_far_thresh", 100.0))
+        if self.use_distance_filter:
+            if self.filter is None:
+                raise NotImplementedError("use_distance_filter without a VoxelGrid down-sampler is not on the B200 path (the gate is fused into the VoxelGrid keys)")
+            self.filter.setDistanceFilter(True, self.distance_near_thresh, self.distance_far_thresh)
+
+    def setSmBudget(self, n_sm):
+        if self.filter is not None:
+            self.filter.setSmBudget(n_sm)
+        elif self.outlier_removal_filter is not None:
+            self.outlier_removal_filter._reg.setSmBudget(n_sm)
 
     def downsample(self, cloud, out=None):
         if self.filter is None:
@@ -58,6 +91,15 @@ class Prefilter:
         self.filter.setInputCloud(cloud, is_dense=False)
         return self.filter.filter(out=out)
 
+    def outlier_removal(self, cloud, out=None):
+        if self.outlier_removal_filter is None:
+            return cloud
+        self.outlier_removal_filter.setInputCloud(cloud)
+        return self.outlier_removal_filter.filter(out=out)
+
+    def filter3d(self, cloud, out=None, out2=None):
+        """filtered3D of cloud_callback: distance_filter -> downsample -> outlier_removal."""
+        return self.outlier_removal(self.downsample(cloud, out=out), out=out2)
 
     def downsample_begin(self, cloud, out):
         """downsample() split in two: enqueue the filter of `cloud` into the caller-owned `out` ..."""
@@ -73,6 +115,13 @@ class Prefilter:
             return self._passthrough
         return self.filter.filter_end()
 
+    def outlier_removal_begin(self, cloud, out):
+        self.outlier_removal_filter.setInputCloud(cloud)
+        self.outlier_removal_filter.filter_begin(out)
+
+    def outlier_removal_end(self):
+        return self.outlier_removal_filter.filter_end()
+
 
 class FrontEnd:
     """prefiltering_nodelet -> /filtered_points -> scan_matching_odometry_nodelet as the pipeline it is in
@@ -87,12 +136,15 @@ class FrontEnd:
     rest, so both are resident together.  The poses are those of the sequential loop
     (`for cloud: matching(stamp, downsample(cloud))`) run with the same SM budgets."""
 
-    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148):
+    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148, ror_bufs=None):
         if len(out_bufs) < 3:
             raise ValueError("the pipelined front end needs three output clouds in rotation")
         self.prefilter, self.odometry, self.out_bufs = prefilter, odometry, list(out_bufs)
-        if prefilter.filter is not None and filter_sms:
-            prefilter.filter.setSmBudget(filter_sms)
+        self.ror_bufs = list(ror_bufs) if ror_bufs is not None else None
+        if prefilter.outlier_removal_filter is not None and (self.ror_bufs is None or len(self.ror_bufs) < 3):
+            raise ValueError("a prefilter with outlier removal needs three more output clouds (ror_bufs)")
+        if filter_sms:
+            prefilter.setSmBudget(filter_sms)
             odometry.registration.setSmBudget(total_sms - filter_sms)
 
     def run(self, clouds, stamps=None, on_frame=None):
@@ -101,14 +153,35 @@ class FrontEnd:
         n = len(clouds)
         if n == 0:
             return poses
+        stamp = (lambda k: 0.1 * k) if stamps is None else (lambda k: stamps[k])
+        if pre.outlier_removal_filter is None:
+            pre.downsample_begin(clouds[0], bufs[0])
+            for k in range(n):
+                filtered = pre.downsample_end()
+                if k + 1 < n:
+                    pre.downsample_begin(clouds[k + 1], bufs[(k + 1) % len(bufs)])
+                poses.append(odo.matching(stamp(k), filtered))
+                if on_frame is not None:
+                    on_frame(k, filtered)
+            return poses
+        # three stages (filter, outlier removal, matching), two scans ahead: while scan k is matched the
+        # outlier removal of scan k+1 and then the filter of scan k+2 run on the prefilter handle's stream
+        rb = self.ror_bufs
         pre.downsample_begin(clouds[0], bufs[0])
+        pre.outlier_removal_begin(pre.downsample_end(), rb[0])
+        if n > 1:
+            pre.downsample_begin(clouds[1], bufs[1 % len(bufs)])
+        cur = pre.outlier_removal_end()
         for k in range(n):
-            filtered = pre.downsample_end()
             if k + 1 < n:
-                pre.downsample_begin(clouds[k + 1], bufs[(k + 1) % len(bufs)])
-            poses.append(odo.matching(0.1 * k if stamps is None else stamps[k], filtered))
+                pre.outlier_removal_begin(pre.downsample_end(), rb[(k + 1) % len(rb)])
+                if k + 2 < n:
+                    pre.downsample_begin(clouds[k + 2], bufs[(k + 2) % len(bufs)])
+            poses.append(odo.matching(stamp(k), cur))
             if on_frame is not None:
-                on_frame(k, filtered)
+                on_frame(k, cur)
+            if k + 1 < n:
+                cur = pre.outlier_removal_end()
         return poses
 
 

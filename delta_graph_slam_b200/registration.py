@@ -299,6 +299,43 @@ class Registration:
             return DeviceCloud(out.ptr, n_out.value, out.owner)
         return out[: n_out.value]
 
+    def setDistanceFilter(self, use, near_thresh=1.0, far_thresh=100.0):
+        """distance_filter of the prefiltering nodelet fused into this handle's VoxelGrid calls (b200reg_set_distance_filter)."""
+        self._ck(_lib.load().b200reg_set_distance_filter(self._h, int(bool(use)), float(near_thresh), float(far_thresh)))
+
+    def radius_outlier_removal_begin(self, cloud, radius, min_neighbors, out):
+        """pcl::RadiusOutlierRemoval, first half (enqueue).  `cloud` / `out` both host arrays or both DeviceClouds."""
+        if isinstance(cloud, DeviceCloud):
+            if out.n < cloud.n:
+                raise ValueError("output buffer smaller than the input cloud")
+            self._ck(_lib.load().b200reg_radius_outlier_removal_device_begin(self._h, cloud.ptr, cloud.n, float(radius), int(min_neighbors), out.ptr))
+            self._ror_pending = (cloud, out)
+            return
+        c = _lib.as_cloud(cloud)
+        if out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
+        self._ck(_lib.load().b200reg_radius_outlier_removal_begin(self._h, c.ctypes.data if len(c) else None, len(c), 16, float(radius), int(min_neighbors), out.ctypes.data, len(out)))
+        self._ror_pending = (c, out)
+
+    def radius_outlier_removal_end(self):
+        _, out = self._ror_pending
+        self._ror_pending = None
+        n_out = C.c_size_t()
+        self._ck(_lib.load().b200reg_radius_outlier_removal_end(self._h, C.byref(n_out)))
+        if isinstance(out, DeviceCloud):
+            return DeviceCloud(out.ptr, n_out.value, out.owner)
+        return out[: n_out.value]
+
+    def radius_outlier_removal(self, cloud, radius, min_neighbors, out=None):
+        own = out is None
+        if own:
+            if isinstance(cloud, DeviceCloud):
+                raise ValueError("a device cloud needs a device output buffer")
+            out = np.empty((max(len(cloud), 1), 4), np.float32)
+        self.radius_outlier_removal_begin(cloud, radius, min_neighbors, out)
+        res = self.radius_outlier_removal_end()
+        return res.copy() if own else res
+
     def setSmBudget(self, n_sm):
         """At most n_sm CTAs (one per SM) for this handle's persistent kernels (b200reg_set_sm_budget)."""
         self._ck(_lib.load().b200reg_set_sm_budget(self._h, int(n_sm)))
@@ -396,6 +433,9 @@ class VoxelGrid:
             return self._reg.voxelgrid_filter_device(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
         return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense, out=out)
 
+    def setDistanceFilter(self, use, near_thresh=1.0, far_thresh=100.0):
+        self._reg.setDistanceFilter(use, near_thresh, far_thresh)
+
     def filter_begin(self, out):
         """filter() split in two for a pipelined front end: enqueue now, collect with filter_end()."""
         self._reg.voxelgrid_filter_begin(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
@@ -408,6 +448,35 @@ class VoxelGrid:
 
     def last_layout(self, n_voxels, n_points):
         return self._reg.voxelgrid_last_layout(n_voxels, n_points)
+
+
+class RadiusOutlierRemoval:
+    """pcl::RadiusOutlierRemoval<PointXYZ> as the prefiltering nodelet sets it up
+    [REF apps/prefiltering_nodelet.cpp:88-96,262-273]: setRadiusSearch + setMinNeighborsInRadius + filter."""
+
+    def __init__(self, device=0, registration=None):
+        self._reg = registration if registration is not None else Registration(device=device)
+        self.radius = 0.8
+        self.min_neighbors = 2
+        self._input = None
+
+    def setRadiusSearch(self, r):
+        self.radius = float(r)
+
+    def setMinNeighborsInRadius(self, n):
+        self.min_neighbors = int(n)
+
+    def setInputCloud(self, cloud):
+        self._input = cloud
+
+    def filter(self, out=None):
+        return self._reg.radius_outlier_removal(self._input, self.radius, self.min_neighbors, out=out)
+
+    def filter_begin(self, out):
+        self._reg.radius_outlier_removal_begin(self._input, self.radius, self.min_neighbors, out)
+
+    def filter_end(self):
+        return self._reg.radius_outlier_removal_end()
 
 
 def select_registration_method(params=None, device=0, out=sys.stdout):

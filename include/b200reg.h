@@ -163,6 +163,25 @@ int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out);
  * on the budget for the filter (bit-exact); NDT / GICP sums are taken in a budget-dependent order
  * (last-bit differences, as between OpenMP thread counts upstream). */
 int b200reg_set_sm_budget(b200reg_handle* h, int n_sm);
+/* The stages either side of VoxelGrid in PrefilteringNodelet::cloud_callback
+ * [REF apps/prefiltering_nodelet.cpp:150-153: distance_filter -> downsample -> outlier_removal].
+ *
+ * distance_filter [REF :275-291]: with the gate on, every VoxelGrid call on this handle keeps only the
+ * points with near < |p| < far (|p| in float, compared as double, as the reference does) — fused into
+ * the key pipeline, so the copy_if pass and its intermediate cloud never exist.  Defaults of the
+ * reference: use_distance_filter true, 1.0 / 100.0 [REF :100-102]; the launch files set 0.1 / 100.0. */
+int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, double far_thresh);
+/* pcl::RadiusOutlierRemoval (outlier_removal_method RADIUS) [REF :88-96,262-273]: a point stays when more
+ * than min_neighbors points of the cloud (itself included) lie strictly inside `radius`; order kept.
+ * Same calling conventions as the VoxelGrid filter: synchronous, device-resident, and begin / end halves
+ * (one call in flight per handle, independent of a VoxelGrid call in flight on the same handle).
+ * STATISTICAL outlier removal stays on the reference's pcl::StatisticalOutlierRemoval. */
+int b200reg_radius_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double radius, int min_neighbors, float* out_xyzw, size_t out_capacity,
+                                   size_t* n_out);
+int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out_xyzw, size_t* n_out);
+int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double radius, int min_neighbors, float* out_xyzw, size_t out_capacity);
+int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out_xyzw);
+int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out);
 /* introspection of the last filter call (parity tests): per output voxel linear index and point
  * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);

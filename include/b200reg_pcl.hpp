@@ -179,6 +179,9 @@ class VoxelGrid : public pcl::Filter<pcl::PointXYZ> {
   }
   void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
   void setMinimumPointsNumberPerVoxel(unsigned n) { min_points_ = n; }
+  // PrefilteringNodelet::distance_filter fused into this filter [REF apps/prefiltering_nodelet.cpp:100-102,275-291]
+  void setDistanceFilter(bool use, double near_thresh, double far_thresh) { b200reg_set_distance_filter(h_, use ? 1 : 0, near_thresh, far_thresh); }
+  b200reg_handle* handle() { return h_; }
 
  protected:
   void applyFilter(PointCloud& output) override {
@@ -202,6 +205,43 @@ class VoxelGrid : public pcl::Filter<pcl::PointXYZ> {
   b200reg_handle* h_ = nullptr;
   float leaf_[3] = {0.f, 0.f, 0.f};
   unsigned min_points_ = 0;
+};
+
+// Replaces pcl::RadiusOutlierRemoval<pcl::PointXYZ> behind pcl::Filter::Ptr (outlier_removal_method RADIUS)
+// [REF apps/prefiltering_nodelet.cpp:88-96,262-273]
+class RadiusOutlierRemoval : public pcl::Filter<pcl::PointXYZ> {
+ public:
+  using PointCloud = pcl::PointCloud<pcl::PointXYZ>;
+  explicit RadiusOutlierRemoval(int device = 0) : h_(detail::create(B200REG_METHOD_NONE, device)) { this->filter_name_ = "b200reg::RadiusOutlierRemoval"; }
+  ~RadiusOutlierRemoval() override {
+    if (h_) b200reg_destroy(h_);
+  }
+  void setRadiusSearch(double radius) { radius_ = radius; }
+  void setMinNeighborsInRadius(int n) { min_neighbors_ = n; }
+  b200reg_handle* handle() { return h_; }
+
+ protected:
+  void applyFilter(PointCloud& output) override {
+    const PointCloud& in = *this->input_;
+    output.header = in.header;
+    output.sensor_origin_ = in.sensor_origin_;
+    output.sensor_orientation_ = in.sensor_orientation_;
+    output.points.resize(in.points.size());
+    size_t n_out = 0;
+    int rc = b200reg_radius_outlier_removal(h_, detail::xyz(in), in.points.size(), sizeof(pcl::PointXYZ), radius_, min_neighbors_,
+                                            output.points.empty() ? nullptr : reinterpret_cast<float*>(output.points.data()), output.points.size(), &n_out);
+    if (rc != B200REG_OK) {
+      PCL_ERROR("[b200reg::RadiusOutlierRemoval] %s\n", b200reg_last_error(h_));
+      n_out = 0;
+    }
+    output.points.resize(n_out);
+    output.width = static_cast<uint32_t>(n_out);
+    output.height = 1;
+    output.is_dense = true;
+  }
+  b200reg_handle* h_ = nullptr;
+  double radius_ = 0.0;
+  int min_neighbors_ = 1;
 };
 
 }  // namespace b200reg

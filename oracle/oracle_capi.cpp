@@ -3,7 +3,9 @@
 // 4x4 transforms cross this boundary as 16 floats in Eigen's column-major order.
 #include <omp.h>
 
+#include <cmath>
 #include <cstring>
+#include <vector>
 #include <string>
 
 #include "../delta_graph_slam_b200/synth/synth_scene.h"
@@ -143,6 +145,49 @@ void orc_knn(const float* pts, long long n, const float* queries, long long m, i
     int found = t.knn(queries + 4 * i, k, idx + (size_t)k * i, d2 + (size_t)k * i);
     for (int j = found; j < k; ++j) { idx[(size_t)k * i + j] = -1; d2[(size_t)k * i + j] = 3.402823466e+38f; }
   }
+}
+
+// ---- the rest of the prefilter chain ----------------------
+// PrefilteringNodelet::distance_filter [REF apps/prefiltering_nodelet.cpp:275-291]: keep p when
+// near < |p| < far, |p| = Eigen's float norm() = sqrtf((x*x + y*y) + z*z) widened to double for
+// the comparison with the double thresholds; order kept; NaN / inf never pass.
+long long orc_distance_filter(const float* in, long long n, double near_thresh, double far_thresh, float* out) {
+  long long m = 0;
+  for (long long i = 0; i < n; ++i) {
+    const float x = in[4 * i], y = in[4 * i + 1], z = in[4 * i + 2];
+    const float sq = (x * x + y * y) + z * z;
+    const double d = (double)std::sqrt(sq);
+    if (d > near_thresh && d < far_thresh) {
+      std::memcpy(out + 4 * m, in + 4 * i, 16);
+      ++m;
+    }
+  }
+  return m;
+}
+
+// pcl::RadiusOutlierRemoval<PointXYZ>::applyFilterIndices [UPSTREAM-RECALLED, PCL 1.8-1.10] as set up at
+// [REF apps/prefiltering_nodelet.cpp:88-96]: k = radiusSearch(p, radius) counts the points of the SAME
+// cloud with d2 < radius^2 (the query itself included); the point is kept when k > min_neighbors;
+// non-finite points are dropped; order kept.
+long long orc_radius_outlier_removal(const float* in, long long n, double radius, int min_neighbors, float* out) {
+  KdTree t;
+  t.build(in, (size_t)n);
+  std::vector<unsigned char> keep((size_t)(n > 0 ? n : 1), 0);
+  const int k = min_neighbors + 1;
+  const float r2 = (float)(radius * radius);
+#pragma omp parallel for schedule(guided, 64)
+  for (long long i = 0; i < n; ++i) {
+    const float* q = in + 4 * i;
+    if (!std::isfinite(q[0]) || !std::isfinite(q[1]) || !std::isfinite(q[2])) continue;
+    std::vector<int> idx((size_t)k);
+    std::vector<float> d2((size_t)k);
+    const int found = t.knn(q, k, idx.data(), d2.data());
+    keep[(size_t)i] = (found >= k && d2[(size_t)k - 1] < r2) ? 1 : 0;  // at least k points inside the radius <=> count > min_neighbors
+  }
+  long long m = 0;
+  for (long long i = 0; i < n; ++i)
+    if (keep[(size_t)i]) { std::memcpy(out + 4 * m, in + 4 * i, 16); ++m; }
+  return m;
 }
 
 // ---- linear algebra known-answer hooks -------------------------------------

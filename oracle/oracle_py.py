@@ -57,6 +57,10 @@ def lib():
         L.orc_ndt_derivatives.restype = C.c_double
         L.orc_gicp_covariances.argtypes = [C.c_void_p, C.c_int, f64p]
         L.orc_knn.argtypes = [f32p, C.c_longlong, f32p, C.c_longlong, C.c_int, i32p, f32p]
+        L.orc_distance_filter.argtypes = [f32p, C.c_longlong, C.c_double, C.c_double, f32p]
+        L.orc_distance_filter.restype = C.c_longlong
+        L.orc_radius_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_double, C.c_int, f32p]
+        L.orc_radius_outlier_removal.restype = C.c_longlong
         L.orc_sym_eigen3.argtypes = [f64p, f64p, f64p]
         L.orc_inverse3.argtypes = [f64p, f64p]
         L.orc_svd_solve6.argtypes = [f64p, f64p, f64p]
@@ -103,6 +107,22 @@ def voxelgrid(cloud, leaf, min_points_per_voxel=0, is_dense=False):
     if ovf[0]:
         return dict(out=out[:m].copy(), voxel_id=vid[:0], count=cnt[:0], key=key[:n].copy(), min_b=grid[:3], div_b=grid[3:], overflow=True)
     return dict(out=out[:m].copy(), voxel_id=vid[:m].copy(), count=cnt[:m].copy(), key=key[:n].copy(), min_b=grid[:3].copy(), div_b=grid[3:].copy(), overflow=False)
+
+
+def distance_filter(cloud, near_thresh=1.0, far_thresh=100.0):
+    """PrefilteringNodelet::distance_filter [REF apps/prefiltering_nodelet.cpp:275-291]."""
+    cloud = _cloud(cloud)
+    out = np.empty((max(len(cloud), 1), 4), np.float32)
+    m = lib().orc_distance_filter(cloud if len(cloud) else np.zeros((1, 4), np.float32), len(cloud), float(near_thresh), float(far_thresh), out)
+    return out[:m].copy()
+
+
+def radius_outlier_removal(cloud, radius=0.8, min_neighbors=2):
+    """pcl::RadiusOutlierRemoval as configured at [REF apps/prefiltering_nodelet.cpp:88-96]."""
+    cloud = _cloud(cloud)
+    out = np.empty((max(len(cloud), 1), 4), np.float32)
+    m = lib().orc_radius_outlier_removal(cloud if len(cloud) else np.zeros((1, 4), np.float32), len(cloud), float(radius), int(min_neighbors), out)
+    return out[:m].copy()
 
 
 class Registration:

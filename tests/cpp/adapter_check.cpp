@@ -26,7 +26,13 @@ int main() {
     gicp->setCorrespondenceRandomness(20);
     auto vg = std::make_shared<b200reg::VoxelGrid>();
     vg->setLeafSize(0.1f, 0.1f, 0.1f);
+    vg->setDistanceFilter(true, 0.1, 100.0);
     downsample_filter = vg;
+    auto rad = std::make_shared<b200reg::RadiusOutlierRemoval>();
+    rad->setRadiusSearch(0.5);
+    rad->setMinNeighborsInRadius(2);
+    pcl::Filter<PointT>::Ptr outlier_removal_filter = rad;
+    (void)outlier_removal_filter;
   } catch (const std::exception& e) {
     std::printf("no engine: %s\n", e.what());
     return 3;

@@ -1,0 +1,158 @@
+"""The stages either side of VoxelGrid in PrefilteringNodelet::cloud_callback
+[REF apps/prefiltering_nodelet.cpp:150-153 chain; :275-291 distance_filter; :88-96,262-273 RadiusOutlierRemoval]."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import bits_equal
+
+DEVNULL = open(os.devnull, "w")
+# the reference's launch file: launch/delta_graph_slam.launch:31-42
+LAUNCH = dict(downsample_method="VOXELGRID", downsample_resolution=0.1, use_distance_filter=True, distance_near_thresh=0.1, distance_far_thresh=100.0,
+              outlier_removal_method="RADIUS", radius_radius=0.5, radius_min_neighbors=2)
+
+
+def np_distance_filter(c, near, far):
+    sq = (c[:, 0] * c[:, 0] + c[:, 1] * c[:, 1]).astype(np.float32) + c[:, 2] * c[:, 2]
+    d = np.sqrt(sq.astype(np.float32)).astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        return c[(d > near) & (d < far)]
+
+
+def np_radius_outlier_removal(c, radius, min_neighbors):
+    p = c[:, :3].astype(np.float32)
+    keep = np.zeros(len(c), bool)
+    r2 = np.float32(radius * radius)
+    for i in range(len(c)):
+        d = p - p[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
+        keep[i] = np.count_nonzero(d2 < r2) > min_neighbors
+    return c[keep]
+
+
+def cloud_with_outliers(oracle, rng):
+    raw = oracle.synth_scan(oracle.synth_traj(2), noise_seed=1002)[::5].copy()
+    far = np.ones((40, 4), np.float32)
+    far[:, :3] = rng.uniform(-150, 150, (40, 3)).astype(np.float32)
+    bad = np.ones((3, 4), np.float32)
+    bad[0, 0], bad[1, 1], bad[2, 2] = np.nan, np.inf, -np.inf
+    return np.concatenate([raw[:100], far[:20], bad, raw[100:], far[20:]]).astype(np.float32)
+
+
+def test_oracle_distance_filter_and_outlier_removal_follow_their_definitions(oracle):
+    rng = np.random.default_rng(3)
+    c = cloud_with_outliers(oracle, rng)
+    for near, far in ((1.0, 100.0), (0.1, 100.0), (5.0, 20.0)):
+        assert bits_equal(oracle.distance_filter(c, near, far), np_distance_filter(c, near, far))
+    small = oracle.voxelgrid(oracle.distance_filter(c, 1.0, 60.0), 0.4)["out"][:3000]
+    for radius, mn in ((0.5, 2), (0.8, 2), (1.3, 5)):
+        assert bits_equal(oracle.radius_outlier_removal(small, radius, mn), np_radius_outlier_removal(small, radius, mn))
+    assert len(oracle.radius_outlier_removal(np.zeros((0, 4), np.float32), 0.5, 2)) == 0
+
+
+def test_prefilter_mirror_reads_the_reference_parameters(capsys):
+    import delta_graph_slam_b200.odometry as odo
+    with pytest.raises(NotImplementedError):
+        odo.Prefilter(dict(outlier_removal_method="STATISTICAL"), out=DEVNULL)  # refused before any engine handle is created
+
+
+@pytest.mark.gpu
+def test_fused_distance_filter_matches_filter_then_voxelgrid(oracle):
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(4)
+    c = cloud_with_outliers(oracle, rng)
+    for near, far in ((1.0, 100.0), (0.1, 100.0), (5.0, 20.0)):
+        want = oracle.voxelgrid(oracle.distance_filter(c, near, far), 0.1, is_dense=False)["out"]
+        vg = eng.VoxelGrid()
+        vg.setLeafSize(0.1, 0.1, 0.1)
+        vg.setDistanceFilter(True, near, far)
+        vg.setInputCloud(c, is_dense=False)
+        assert bits_equal(vg.filter(), want)
+    # gate that lets nothing through -> empty cloud; gate off again -> plain VoxelGrid
+    vg.setDistanceFilter(True, 500.0, 600.0)
+    assert len(vg.filter()) == 0
+    vg.setDistanceFilter(False)
+    assert bits_equal(vg.filter(), oracle.voxelgrid(c, 0.1, is_dense=False)["out"])
+
+
+@pytest.mark.gpu
+def test_leaf_too_small_with_the_gate_returns_the_gated_input(oracle):
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(5)
+    c = cloud_with_outliers(oracle, rng)
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(1e-4, 1e-4, 1e-4)  # extents / leaf overflow int32: PCL warns and copies its input
+    vg.setDistanceFilter(True, 1.0, 100.0)
+    vg.setInputCloud(c, is_dense=False)
+    gated = oracle.distance_filter(c, 1.0, 100.0)
+    ref = oracle.voxelgrid(gated, 1e-4, is_dense=False)
+    assert ref["overflow"] and bits_equal(ref["out"], gated)
+    assert bits_equal(vg.filter(), gated)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius,min_neighbors", [(0.5, 2), (0.8, 2), (1.3, 5)])
+def test_radius_outlier_removal_matches_the_oracle(oracle, radius, min_neighbors):
+    import torch
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(6)
+    c = oracle.voxelgrid(oracle.distance_filter(cloud_with_outliers(oracle, rng), 0.1, 100.0), 0.1)["out"]
+    c = np.concatenate([c, np.array([[np.nan, 0, 0, 1]], np.float32)])  # non-finite points are dropped
+    want = oracle.radius_outlier_removal(c, radius, min_neighbors)
+    ror = eng.RadiusOutlierRemoval()
+    ror.setRadiusSearch(radius)
+    ror.setMinNeighborsInRadius(min_neighbors)
+    ror.setInputCloud(c)
+    assert bits_equal(ror.filter(), want)
+    # device-resident and page-locked (zero-copy) outputs
+    d_in = torch.from_numpy(c).cuda()
+    d_out = torch.zeros_like(d_in)
+    ror.setInputCloud(eng.DeviceCloud(d_in.data_ptr(), len(c), d_in))
+    got = ror.filter(out=eng.DeviceCloud(d_out.data_ptr(), len(c), d_out))
+    assert got.n == len(want) and bits_equal(d_out[: got.n].cpu().numpy(), want)
+    h_out = torch.zeros((len(c), 4), dtype=torch.float32, pin_memory=True)
+    ror.setInputCloud(c)
+    ror.filter_begin(h_out.numpy())
+    assert bits_equal(ror.filter_end(), want) and not h_out.numpy()[len(want):].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_launch_file_chain_and_three_stage_front_end(oracle, where):
+    import torch
+    import delta_graph_slam_b200 as eng
+    from test_gpu_frontend import ODOM
+    clouds = [oracle.synth_scan(oracle.synth_traj(k), noise_seed=1000 + k) for k in range(5)]
+    want = [oracle.radius_outlier_removal(oracle.voxelgrid(oracle.distance_filter(c, 0.1, 100.0), 0.1, is_dense=False)["out"], 0.5, 2) for c in clouds]
+    cap = max(len(c) for c in clouds)
+    if where == "device":
+        d_in = [torch.from_numpy(c).cuda() for c in clouds]
+        inputs = [eng.DeviceCloud(t.data_ptr(), len(t), t) for t in d_in]
+        d_a, d_b = torch.empty((3, cap, 4), dtype=torch.float32, device="cuda"), torch.empty((3, cap, 4), dtype=torch.float32, device="cuda")
+        bufs = [eng.DeviceCloud(d_a[j].data_ptr(), cap, d_a) for j in range(3)]
+        rbufs = [eng.DeviceCloud(d_b[j].data_ptr(), cap, d_b) for j in range(3)]
+        to_np = lambda f: torch.empty((f.n, 4), dtype=torch.float32).copy_(d_b.view(-1, 4)[(f.ptr - d_b.data_ptr()) // 16:(f.ptr - d_b.data_ptr()) // 16 + f.n]).numpy()
+    else:
+        inputs = clouds
+        h_a = torch.empty((3, cap, 4), dtype=torch.float32, pin_memory=True).numpy()
+        h_b = torch.empty((3, cap, 4), dtype=torch.float32, pin_memory=True).numpy()
+        bufs, rbufs = [h_a[j] for j in range(3)], [h_b[j] for j in range(3)]
+        to_np = lambda f: np.array(f)
+    pre = eng.Prefilter(LAUNCH, out=DEVNULL)
+    for k, c in enumerate(inputs):
+        f = pre.filter3d(c, out=bufs[k % 3], out2=rbufs[k % 3])
+        assert bits_equal(to_np(f), want[k]), k
+
+    def make():
+        p, o = eng.Prefilter(LAUNCH, out=DEVNULL), eng.ScanMatchingOdometry(ODOM, out=DEVNULL)
+        p.setSmBudget(40)
+        o.registration.setSmBudget(108)
+        return p, o
+    p1, o1 = make()
+    seq = [o1.matching(0.1 * k, p1.filter3d(c, out=bufs[k % 3], out2=rbufs[k % 3])) for k, c in enumerate(inputs)]
+    p2, o2 = make()
+    seen = []
+    got = eng.FrontEnd(p2, o2, bufs, filter_sms=40, ror_bufs=rbufs).run(inputs, on_frame=lambda k, f: seen.append(to_np(f).copy()))
+    assert all(np.array_equal(a, b) for a, b in zip(got, seq))
+    assert all(bits_equal(a, b) for a, b in zip(seen, want))
