@@ -170,8 +170,13 @@ long long orc_distance_filter(const float* in, long long n, double near_thresh, 
 // cloud with d2 < radius^2 (the query itself included); the point is kept when k > min_neighbors;
 // non-finite points are dropped; order kept.
 long long orc_radius_outlier_removal(const float* in, long long n, double radius, int min_neighbors, float* out) {
+  // pcl::KdTreeFLANN::setInputCloud leaves non-finite points out of the tree
+  std::vector<float> finite;
+  finite.reserve((size_t)n * 4);
+  for (long long i = 0; i < n; ++i)
+    if (std::isfinite(in[4 * i]) && std::isfinite(in[4 * i + 1]) && std::isfinite(in[4 * i + 2])) finite.insert(finite.end(), in + 4 * i, in + 4 * i + 4);
   KdTree t;
-  t.build(in, (size_t)n);
+  t.build(finite.data(), finite.size() / 4);
   std::vector<unsigned char> keep((size_t)(n > 0 ? n : 1), 0);
   const int k = min_neighbors + 1;
   const float r2 = (float)(radius * radius);

@@ -25,9 +25,10 @@ def np_radius_outlier_removal(c, radius, min_neighbors):
     keep = np.zeros(len(c), bool)
     r2 = np.float32(radius * radius)
     for i in range(len(c)):
-        d = p - p[i]
-        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
-        keep[i] = np.count_nonzero(d2 < r2) > min_neighbors
+        with np.errstate(invalid="ignore"):
+            d = p - p[i]
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
+            keep[i] = np.count_nonzero(d2 < r2) > min_neighbors
     return c[keep]
 
 
@@ -46,6 +47,7 @@ def test_oracle_distance_filter_and_outlier_removal_follow_their_definitions(ora
     for near, far in ((1.0, 100.0), (0.1, 100.0), (5.0, 20.0)):
         assert bits_equal(oracle.distance_filter(c, near, far), np_distance_filter(c, near, far))
     small = oracle.voxelgrid(oracle.distance_filter(c, 1.0, 60.0), 0.4)["out"][:3000]
+    small = np.concatenate([small[:500], np.array([[np.nan, 0, 0, 1], [0, np.inf, 0, 1]], np.float32), small[500:]])  # never kept, never counted
     for radius, mn in ((0.5, 2), (0.8, 2), (1.3, 5)):
         assert bits_equal(oracle.radius_outlier_removal(small, radius, mn), np_radius_outlier_removal(small, radius, mn))
     assert len(oracle.radius_outlier_removal(np.zeros((0, 4), np.float32), 0.5, 2)) == 0
