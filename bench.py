@@ -418,14 +418,18 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     return out
 
 
-def bench_loop(ctx, steps, warmup):
-    """BASELINE.json configs[3]: the loop-candidate batch, whole targets sharded over the ranks."""
+def bench_loop(ctx, steps, warmup, dense=False):
+    """BASELINE.json configs[3]: the loop-candidate batch, whole targets sharded over the ranks.
+    dense=True: configs[4], the 128-beam 1M-point stress scans with NDT DIRECT1 on a smaller batch."""
     import delta_graph_slam_b200 as eng
     from delta_graph_slam_b200 import loop_batch, synth
     from delta_graph_slam_b200.synth.loop_scenario import loop_scenario
     torch, args, dev, rank, world = ctx.torch, ctx.args, ctx.dev, ctx.rank, ctx.world
 
-    sc = loop_scenario(synth.traj_kitti_like, n_targets=args.loop_targets, n_candidates=args.loop_candidates)
+    n_targets, n_candidates = (args.dense_targets, args.dense_candidates) if dense else (args.loop_targets, args.loop_candidates)
+    sensor = synth.DENSE128 if dense else synth.HDL64
+    loop_params = dict(LOOP_PARAMS, reg_nn_search_method="DIRECT1") if dense else LOOP_PARAMS
+    sc = loop_scenario(synth.traj_kitti_like, n_targets=n_targets, n_candidates=n_candidates)
     pairs = loop_batch.make_pairs([(t, c, g) for t, c, g, _ in sc["pairs"]])
     n_pairs = len(pairs)
     shards = loop_batch.shard_by_target(pairs["target_id"], world)
@@ -434,19 +438,29 @@ def bench_loop(ctx, steps, warmup):
     my_targets = sorted(set(mine["target_id"].tolist()))
 
     # ---- this rank's keyframe clouds: ray-cast and down-sampled (0.1 m) on the device, packed in one buffer
-    rays = synth.num_rays(synth.HDL64)
+    rays = synth.num_rays(sensor)
     vg = eng.VoxelGrid(device=dev)
     vg.setLeafSize(0.1, 0.1, 0.1)
     d_raw = torch.empty((rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
     d_tmp = torch.empty((rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
     specs = [(cid, P, ns) for cid, P, ns in sc["targets"] + sc["candidates"] if cid in need]
-    cap = 70000
+    cap = 400000 if dense else 70000
+    vg_ms, raw_n = [], []
     d_kf = torch.empty((len(specs), cap, 4), dtype=torch.float32, device=f"cuda:{dev}")
     kf_n, slot_of = [], {}
     for s, (cid, P, ns) in enumerate(specs):
-        n = synth.scan_to_device(d_raw.data_ptr(), P, synth.HDL64, scene_seed=1, noise_seed=ns, device=dev)
+        n = synth.scan_to_device(d_raw.data_ptr(), P, sensor, scene_seed=1, noise_seed=ns, device=dev)
         vg.setInputCloud(eng.DeviceCloud(d_raw.data_ptr(), n, d_raw), is_dense=False)
         f = vg.filter(out=eng.DeviceCloud(d_tmp.data_ptr(), rays, d_tmp))
+        if dense and s >= 2:  # VoxelGrid of the 1 M-point scans, CUDA events on the filter's stream
+            st = torch.cuda.ExternalStream(vg._reg.stream(), device=f"cuda:{dev}")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            f = vg.filter(out=eng.DeviceCloud(d_tmp.data_ptr(), rays, d_tmp))
+            e1.record(st)
+            e1.synchronize()
+            vg_ms.append(e0.elapsed_time(e1))
+            raw_n.append(n)
         if f.n > cap:
             raise RuntimeError(f"down-sampled keyframe has {f.n} points, more than the bench buffer holds")
         d_kf[s, : f.n].copy_(d_tmp[: f.n])  # the filter call returned after its stream drained
@@ -461,7 +475,7 @@ def bench_loop(ctx, steps, warmup):
     h_np = h_kf.numpy()
     host_cloud = {cid: h_np[s, : kf_n[s]] for cid, s in slot_of.items()}
 
-    reg = eng.select_registration_method(LOOP_PARAMS, device=dev, out=DEVNULL)
+    reg = eng.select_registration_method(loop_params, device=dev, out=DEVNULL)
     reg.setTiming(True)
     gdev = f"cuda:{dev}"
 
@@ -494,7 +508,7 @@ def bench_loop(ctx, steps, warmup):
     achieved = alg_bytes / (align_ms * 1e-3) / 1e9 if align_ms > 0 else 0.0
 
     # ---- host-buffer leg (e2e): every keyframe cloud of the share uploaded from pinned host memory each step
-    reg_h = eng.select_registration_method(LOOP_PARAMS, device=dev, out=DEVNULL)
+    reg_h = eng.select_registration_method(loop_params, device=dev, out=DEVNULL)
     h2d = sum(host_cloud[cid].nbytes for cid in need) + mine.nbytes
 
     def step_host(i):
@@ -515,7 +529,7 @@ def bench_loop(ctx, steps, warmup):
     err_t = np.array(err_t)
 
     cpu = None
-    if rank == 0 and world == 1 and args.loop_cpu_pairs > 0:
+    if rank == 0 and world == 1 and args.loop_cpu_pairs > 0 and not dense:
         from oracle import oracle_py as oracle
         k = min(args.loop_cpu_pairs, args.loop_candidates)
         sub = pairs[:k]
@@ -527,20 +541,26 @@ def bench_loop(ctx, steps, warmup):
     out = {
         "metric": "loop pairs/sec (NDT + fitness)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec_d / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
-        "config": {"workload": f"LoopDetector batch: {args.loop_targets} new keyframes x {args.loop_candidates} candidates = {n_pairs} NDT DIRECT7 + getFitnessScore pairs (BASELINE configs[3])",
-                   "points_per_keyframe": int(np.mean(kf_n)), "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
+        "config": {"workload": (f"dense-scan stress: 128-beam 1M-ray scans, VoxelGrid 0.1 m + {n_targets} x {n_candidates} = {n_pairs} NDT DIRECT1 + getFitnessScore pairs (BASELINE configs[4])" if dense else
+                                f"LoopDetector batch: {n_targets} new keyframes x {n_candidates} candidates = {n_pairs} NDT DIRECT7 + getFitnessScore pairs (BASELINE configs[3])"),
+                   "points_per_keyframe": int(np.mean(kf_n)), "registration": f"NDT_OMP-equivalent {'DIRECT1' if dense else 'DIRECT7'} res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
                    "sharding": "whole targets per rank, one all-gather of 104-byte result records", "pairs_this_rank": int(len(mine)),
                    "l2": f"{len(specs)} distinct keyframe clouds ({sum(kf_n) * 16 / 1e9:.2f} GB) per rank: inputs larger than L2",
                    "passes_per_registration": float(np.mean(res["passes"])), "reference_evaluations_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
         "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
-        "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7> (one CTA per registration)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+        "roofline": {"bound": "hbm", "kernel": f"k_ndt_align<{1 if dense else 7}> ({'one CTA per registration' if len(mine) >= 148 else str(148 // max(len(mine), 1)) + ' CTAs per registration'})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                      "traffic": None, "traffic_per_registration": load_traffic("k_ndt_align_batch_per_registration"), "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "checks": {"device_and_host_legs_bit_identical": legs_equal, "median_translation_error_m": float(np.median(err_t)), "pairs_within_5cm_of_ground_truth": float(np.mean(err_t < 0.05)),
                    "wall_ms_per_step": 1e3 * wall_d / steps},
     }
+    if dense and vg_ms:
+        # VoxelGrid(N -> M): 16 N + 16 M algorithmic bytes
+        ms, nr = float(np.median(vg_ms)), float(np.mean(raw_n))
+        out["voxelgrid"] = {"raw_points": int(nr), "filtered_points": int(np.mean(kf_n)), "ms_per_scan": ms, "scans_per_s": 1e3 / ms,
+                            "achieved_gbs": (16 * nr + 16 * float(np.mean(kf_n))) / (ms * 1e-3) / 1e9, "peak_gbs": peak}
     del d_kf, h_kf
     torch.cuda.empty_cache()
     return out
@@ -561,6 +581,9 @@ def main():
     ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
     ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-scan stress leg (BASELINE configs[4]) of the default run")
+    ap.add_argument("--dense-targets", type=int, default=8)
+    ap.add_argument("--dense-candidates", type=int, default=8)
     ap.add_argument("--filter-sms", type=int, default=40, help="SMs given to the prefilter handle's persistent kernel in the pipelined front end (the registration takes the rest)")
     ap.add_argument("--gicp-frames", type=int, default=300, help="frames of the sequence the FAST_GICP leg runs per step")
     args = ap.parse_args()
@@ -586,6 +609,9 @@ def main():
         if not args.no_loop:
             lb = bench_loop(ctx, max(1, min(args.steps, 2)), 3)
             out["loop_batch"] = {k: lb[k] for k in keys}
+        if not args.no_dense:
+            db = bench_loop(ctx, 1, 3, dense=True)
+            out["dense_stress"] = {k: db[k] for k in keys + ("voxelgrid",) if k in db}
         if not args.no_gicp:
             gb = bench_odometry(ctx, GICP_ODOM_PARAMS, frames=min(args.frames, args.gicp_frames), steps=max(1, min(args.steps, 2)), warmup=3, label="FAST_GICP", cpu_frames=min(args.cpu_frames, 12))
             out["gicp_odometry"] = {k: gb[k] for k in keys}
