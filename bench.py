@@ -307,6 +307,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     # The filter handle's persistent kernel is given args.filter_sms SMs, the registration the rest.
     def new_front_end(bufs):
         pre, odo = new_pipeline()
+        odo.prepare_promotion = bool(args.filter_sms) and args.prepare
         return eng.FrontEnd(pre, odo, bufs, filter_sms=args.filter_sms), pre, odo
 
     # ---- device-resident leg (value) + roofline of the align kernel
@@ -376,7 +377,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     pre_s, odo_s = new_pipeline()
     if pre_s.filter is not None and args.filter_sms:
         pre_s.filter.setSmBudget(args.filter_sms)
-        odo_s.registration.setSmBudget(148 - args.filter_sms)
+        odo_s.registration.setSmBudget(148 - args.filter_sms)  # no prepared promotions here: they must not change a pose
     poses_seq = run_sequence(pre_s, odo_s, dev_clouds[:nchk], out_buf=ds_buf)
     pipeline_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_seq))
     P0 = synth.traj_kitti_like(5000 * rank)
@@ -398,7 +399,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                    "frames_per_step": F, "points_per_scan": int(np.mean(counts)),
                    "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64" if is_ndt else "FAST_GICP-equivalent k 20, max corr 2.5 m, eps 0.01, max_iter 64, LM, PLANE",
                    "l2": f"each step streams {F} distinct scans ({F * rays * 16 / 1e9:.1f} GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
-                   "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms} SMs, registration {148 - args.filter_sms} SMs" if args.filter_sms else "sequential: filter, then match",
+                   "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms - (16 if args.prepare else 0)} SMs, registration {148 - args.filter_sms} SMs{', 16 SMs for the NDT grid of a predicted next keyframe built during its own registration' if args.prepare else ''}" if args.filter_sms else "sequential: filter, then match",
                    "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
         "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
                 "wall_ms_per_step": 1e3 * wall_h / steps},
@@ -581,6 +582,7 @@ def main():
     ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
     ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
+    ap.add_argument("--prepare", action="store_true", help="build a predicted next keyframe's target structures during its own registration (b200reg_prepare_promotion; measured: no net gain, off by default)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-scan stress leg (BASELINE configs[4]) of the default run")
     ap.add_argument("--dense-targets", type=int, default=8)
     ap.add_argument("--dense-candidates", type=int, default=8)

@@ -23,7 +23,7 @@ EXPORTS = [
     "b200reg_default_config", "b200reg_create", "b200reg_destroy", "b200reg_last_error", "b200reg_version",
     "b200reg_set_resolution", "b200reg_set_nn_search", "b200reg_set_transformation_epsilon", "b200reg_set_maximum_iterations",
     "b200reg_set_max_correspondence_distance", "b200reg_set_correspondence_randomness", "b200reg_set_gicp_options", "b200reg_gicp_get_covariances",
-    "b200reg_set_target", "b200reg_set_source", "b200reg_set_target_device", "b200reg_set_source_device", "b200reg_promote_source_to_target",
+    "b200reg_set_target", "b200reg_set_source", "b200reg_set_target_device", "b200reg_set_source_device", "b200reg_promote_source_to_target", "b200reg_prepare_promotion", "b200reg_set_side_budget",
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
@@ -97,6 +97,8 @@ def load():
     L.b200reg_set_target_device.argtypes = [vp, vp, C.c_size_t]
     L.b200reg_set_source_device.argtypes = [vp, vp, C.c_size_t]
     L.b200reg_promote_source_to_target.argtypes = [vp]
+    L.b200reg_prepare_promotion.argtypes = [vp]
+    L.b200reg_set_side_budget.argtypes = [vp, C.c_int]
     L.b200reg_align.argtypes = [vp, vp, vp]
     L.b200reg_has_converged.argtypes = [vp, C.POINTER(C.c_int)]
     L.b200reg_get_final_transformation.argtypes = [vp, vp]

@@ -89,6 +89,19 @@ struct b200reg_handle {
   DevBuf<unsigned int> barriers;
   PinnedBuf<unsigned char> pin_small;  // results / jobs staging
 
+  // Keyframe promotion prepared ahead (b200reg_prepare_promotion): the NDT grid of the CURRENT SOURCE is
+  // built on a side stream while the registration of that source runs, so that promoting it to target
+  // (the keyframe switch of the odometry) does not put a grid build in front of the next registration
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_src_ready = nullptr, ev_side_done = nullptr;
+  NdtGrid grid_spec;
+  bool spec_valid = false;      // grid_spec holds the grid of (spec_ptr, spec_n) at spec_res
+  bool spec_in_flight = false;  // the side stream may still be reading the source buffer
+  const float4* spec_ptr = nullptr;
+  int spec_n = 0;
+  float spec_res = 0.f;
+  int spec_sms = 16;            // CTAs of the side build's cooperative sort
+
   // exact-NN structure on the target (fitness, inlier fraction, GICP)
   NnGrid nn;
   bool nn_stale = true;
@@ -600,6 +613,10 @@ int b200reg_destroy(b200reg_handle* h) {
     ln.nn.release();
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_src_ready) cudaEventDestroy(h->ev_src_ready);
+  if (h->ev_side_done) cudaEventDestroy(h->ev_side_done);
+  h->grid_spec.release();
   h->batch_results.release(); h->tq_runs.release(); h->tq_next.release(); h->pin_runs.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
   delete h;
   return B200REG_OK;
@@ -652,10 +669,23 @@ int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   return B200REG_OK;
 }
 
+// the source buffer is about to change: a prepared promotion no longer applies, and a side build that
+// may still be reading the buffer has to finish first (stream order, no host wait)
+static int retire_spec(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (h->spec_in_flight) {
+    B200_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_side_done, 0));
+    h->spec_in_flight = false;
+  }
+  h->spec_valid = false;
+  return B200REG_OK;
+}
+
 int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t stride) {
   if (!h || (n && !xyzw)) return B200REG_E_INVALID;
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = retire_spec(h))) return rc;
   if ((rc = upload_cloud(h, xyzw, n, stride, h->src))) return rc;
   h->n_src = (int)n;
   h->have_src = true;
@@ -686,6 +716,7 @@ int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n) 
   if (!h || (n && !d_xyzw)) return B200REG_E_INVALID;
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = retire_spec(h))) return rc;
   B200_CUDA_TRY(h->src.reserve(n ? n : 1));
   if (n) B200_CUDA_TRY(cudaMemcpyAsync(h->src.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
   h->n_src = (int)n;
@@ -714,7 +745,47 @@ int b200reg_promote_source_to_target(b200reg_handle* h) {
   std::swap(h->cov_tgt, h->cov_src);
   h->cov_tgt_ok = h->cov_src_ok;
   h->cov_src_ok = false;
-  if (h->cfg.method == B200REG_METHOD_NDT) return ensure_ndt_grid(h);
+  if (h->cfg.method == B200REG_METHOD_NDT) {
+    if (h->spec_valid && h->spec_ptr == h->tgt.p && h->spec_n == h->n_tgt && h->spec_res == (float)h->cfg.resolution) {
+      // the grid of this cloud was built ahead on the side stream: take it (same kernels, same bits)
+      auto set_error = [&](const std::string& s) { h->err = s; };
+      B200_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_side_done, 0));
+      std::swap(h->grid, h->grid_spec);
+      h->grid_stale = false;
+      h->spec_valid = false;
+      h->spec_in_flight = false;
+      return B200REG_OK;
+    }
+    if ((rc = retire_spec(h))) return rc;
+    return ensure_ndt_grid(h);
+  }
+  return B200REG_OK;
+}
+
+int b200reg_prepare_promotion(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  if (h->cfg.method != B200REG_METHOD_NDT) return B200REG_OK;  // FAST_GICP keeps the source's structures on promotion anyway
+  if (!h->have_src || h->n_src == 0) { h->err = "no source to prepare"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->spec_valid && h->spec_ptr == h->src.p && h->spec_n == h->n_src && h->spec_res == (float)h->cfg.resolution) return B200REG_OK;
+  if (!h->side) {
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_src_ready, cudaEventDisableTiming));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_side_done, cudaEventDisableTiming));
+  }
+  // the side stream starts after the source cloud has arrived (set_source's copy is on the main stream)
+  B200_CUDA_TRY(cudaEventRecord(h->ev_src_ready, h->stream));
+  B200_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_src_ready, 0));
+  h->grid_spec.sort.max_ctas = h->spec_sms;
+  B200_CUDA_TRY(h->grid_spec.build(h->side, h->src.p, h->n_src, (float)h->cfg.resolution));
+  B200_CUDA_TRY(cudaEventRecord(h->ev_side_done, h->side));
+  h->spec_valid = true;
+  h->spec_in_flight = true;
+  h->spec_ptr = h->src.p;
+  h->spec_n = h->n_src;
+  h->spec_res = (float)h->cfg.resolution;
   return B200REG_OK;
 }
 
@@ -1468,6 +1539,12 @@ int b200reg_set_sm_budget(b200reg_handle* h, int n_sm) {
   h->nn.sort.max_ctas = n_sm;
   h->nn_src.sort.max_ctas = n_sm;
   h->nn_ror.sort.max_ctas = n_sm;
+  return B200REG_OK;
+}
+
+int b200reg_set_side_budget(b200reg_handle* h, int n_sm) {
+  if (!h || n_sm < 1) return B200REG_E_INVALID;
+  h->spec_sms = n_sm > h->dev_sm ? h->dev_sm : n_sm;
   return B200REG_OK;
 }
 

@@ -136,7 +136,7 @@ class FrontEnd:
     rest, so both are resident together.  The poses are those of the sequential loop
     (`for cloud: matching(stamp, downsample(cloud))`) run with the same SM budgets."""
 
-    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148, ror_bufs=None):
+    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148, ror_bufs=None, side_sms=16):
         if len(out_bufs) < 3:
             raise ValueError("the pipelined front end needs three output clouds in rotation")
         self.prefilter, self.odometry, self.out_bufs = prefilter, odometry, list(out_bufs)
@@ -144,8 +144,13 @@ class FrontEnd:
         if prefilter.outlier_removal_filter is not None and (self.ror_bufs is None or len(self.ror_bufs) < 3):
             raise ValueError("a prefilter with outlier removal needs three more output clouds (ror_bufs)")
         if filter_sms:
-            prefilter.setSmBudget(filter_sms)
+            # persistent kernels that may be resident together: registration, filter (+ outlier removal's
+            # sort, same stream) and, with prepared promotions, the side build of the next target
+            side = side_sms if getattr(odometry, "prepare_promotion", False) and hasattr(odometry.registration, "setSideBudget") else 0
+            prefilter.setSmBudget(filter_sms - side)
             odometry.registration.setSmBudget(total_sms - filter_sms)
+            if side:
+                odometry.registration.setSideBudget(side)
 
     def run(self, clouds, stamps=None, on_frame=None):
         pre, odo, bufs = self.prefilter, self.odometry, self.out_bufs
@@ -220,6 +225,12 @@ class ScanMatchingOdometry:
         self.prev_time = None
         self.num_keyframes = 0
         self.last_converged = True
+        # scheduling hint for the engine (not part of the reference's logic, never changes a result): when the
+        # motion since the keyframe says this scan will probably become the next keyframe, the registration
+        # is asked to build the scan's target structures while it is being aligned (preparePromotion)
+        self.prepare_promotion = bool(p.get("prepare_promotion", False))
+        self._last_step = 0.0
+        self.promotions_prepared = 0
 
     def downsample(self, cloud):
         if self.downsample_filter is None:
@@ -248,6 +259,10 @@ class ScanMatchingOdometry:
         filtered = self.downsample(cloud)
         reg.setInputSource(filtered)
         guess = self.prev_trans if msf_delta is None else (self.prev_trans @ np.asarray(msf_delta, np.float32))
+        dist_before = float(np.linalg.norm(self.prev_trans[:3, 3]))
+        if self.prepare_promotion and hasattr(reg, "preparePromotion") and dist_before + self._last_step > 0.95 * self.keyframe_delta_trans:
+            reg.preparePromotion()
+            self.promotions_prepared += 1
         reg.align(guess)
         self.last_converged = reg.hasConverged()
         if not self.last_converged:
@@ -266,6 +281,7 @@ class ScanMatchingOdometry:
         self.prev_time = stamp
         self.prev_trans = trans
         delta_trans = float(np.linalg.norm(trans[:3, 3]))
+        self._last_step = max(delta_trans - dist_before, 0.0)
         delta_angle = float(np.arccos(np.clip(quaternion_w(trans[:3, :3]), -1.0, 1.0)))
         delta_time = stamp - self.keyframe_stamp
         if delta_trans > self.keyframe_delta_trans or delta_angle > self.keyframe_delta_angle or delta_time > self.keyframe_delta_time:

@@ -118,6 +118,13 @@ class Registration:
         self._n_src = 0
         self._src_ref = None
 
+    def preparePromotion(self):
+        """Scheduling hint before align: the source will probably become the target (b200reg_prepare_promotion)."""
+        self._ck(_lib.load().b200reg_prepare_promotion(self._h))
+
+    def setSideBudget(self, n_sm):
+        self._ck(_lib.load().b200reg_set_side_budget(self._h, int(n_sm)))
+
     # ---- run
     def align(self, guess=None, want_aligned=False):
         """registration->align(*aligned, guess).  Returns the aligned cloud when asked for."""

@@ -114,6 +114,17 @@ int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n);
  * without leaving the device (same result as b200reg_set_target on the same cloud). */
 int b200reg_promote_source_to_target(b200reg_handle* h);
 
+/* Hint: the current source will probably be promoted to target after its registration (the odometry's
+ * keyframe switch, decided from the result of the align that is about to run).  The NDT grid of the
+ * source is then built on a side stream WHILE that align runs, and b200reg_promote_source_to_target
+ * takes it instead of building in front of the next registration.  Purely a scheduling hint: results
+ * are bit-identical with or without it, a hint that does not come true only costs idle-SM time.
+ * b200reg_set_side_budget: CTAs of the side build's persistent sort kernel (default 16) — together with
+ * the budgets of b200reg_set_sm_budget the persistent kernels that may be resident at once must not
+ * exceed the SM count. */
+int b200reg_prepare_promotion(b200reg_handle* h);
+int b200reg_set_side_budget(b200reg_handle* h, int n_sm);
+
 /* pcl::Registration::align(output, guess) [REF apps/scan_matching_odometry_nodelet.cpp:218;
  * include/hdl_graph_slam/loop_detector.hpp:145].  guess == NULL means identity.
  * aligned_xyzw (optional, host, n_source * 16 bytes) receives the transformed source. */

@@ -145,3 +145,35 @@ def test_pipelined_front_end_equals_the_plain_loop(scans, where):
     got = fe.run(inputs)
     assert len(got) == len(seq) and all(np.array_equal(a, b) for a, b in zip(got, seq))
     assert odo2.num_keyframes == odo.num_keyframes
+
+
+def test_prepared_promotion_changes_no_pose(scans):
+    """b200reg_prepare_promotion: the next keyframe's NDT grid built on a side stream during its own
+    registration; wrong guesses (prepared, not promoted) and unprepared promotions included."""
+    import delta_graph_slam_b200 as eng
+    O, _ = scans
+    clouds = [O.voxelgrid(O.synth_scan(O.synth_traj(k), noise_seed=1000 + k), 0.1)["out"] for k in range(9)]
+
+    def run(prepare, hint_always=False):
+        odo = eng.ScanMatchingOdometry(dict(ODOM, prepare_promotion=prepare), out=DEVNULL)
+        odo.registration.setSmBudget(108)
+        odo.registration.setSideBudget(16)
+        poses = []
+        for k, c in enumerate(clouds):
+            if hint_always and k > 0:
+                odo._last_step = 10.0  # force a hint on every frame: most of them will not come true
+            poses.append(odo.matching(0.1 * k, c))
+        return poses, odo
+    base, o0 = run(False)
+    got, o1 = run(True)
+    forced, o2 = run(True, hint_always=True)
+    assert o0.num_keyframes >= 3 and o1.num_keyframes == o0.num_keyframes == o2.num_keyframes
+    assert 0 < o1.promotions_prepared < len(clouds) and o2.promotions_prepared == len(clouds) - 1
+    assert all(np.array_equal(a, b) for a, b in zip(base, got))
+    assert all(np.array_equal(a, b) for a, b in zip(base, forced))
+    # the hint is a state error without a source, and a no-op on a FAST_GICP handle
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP"), out=DEVNULL)
+    with pytest.raises(eng.B200RegError) as e:
+        ndt.preparePromotion()
+    assert e.value.code == eng._lib.E_STATE
+    eng.select_registration_method(dict(registration_method="FAST_GICP"), out=DEVNULL).preparePromotion()
