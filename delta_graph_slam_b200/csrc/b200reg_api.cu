@@ -501,6 +501,8 @@ int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
   job->cov_tgt = h->cov_tgt.p;
   const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   memcpy(job->guess, guess_colmajor ? guess_colmajor : I, 64);
+  B200_CUDA_TRY(h->prof.reserve(16));
+  job->prof = h->prof.p;
   job->corr = h->gicp_corr.p;
   job->mahal = h->gicp_mahal.p;
   job->result = h->d_result.p;

@@ -415,6 +415,7 @@ struct GicpJob {
   b200reg_result* result_host;  // mapped host copy + completion flag (see NdtJob)
   unsigned int* done_flag;
   unsigned int done_seq;
+  long long* prof;         // optional developer counters of CTA 0: cycles in {near phase, far queue, error pass, block reduce, group barrier, row sum, step}, linearize passes, error passes, far queries of CTA 0
 };
 
 struct GicpShared {
@@ -670,8 +671,11 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     s.phase = (prm.max_iterations > 0 && n_src > 0) ? GP_LINEARIZE : GP_DONE;
   }
   __syncthreads();
+  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   while (s.phase != GP_DONE) {
     const int phase = s.phase;
+    const long long tp0 = clock64();
+    long long tp_near = tp0;
     double acc[kGicpAcc];
 #pragma unroll
     for (int k = 0; k < kGicpAcc; ++k) acc[k] = 0.0;
@@ -721,6 +725,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         if (lane == 0) s_wq[warp] = __popc(open);
         if (active && ok) finish_point(i, p, best, best_idx);
         __syncthreads();
+        tp_near = clock64();
         int qbase = 0, nq = 0;
 #pragma unroll
         for (int w = 0; w < kGicpWarps; ++w) {
@@ -728,6 +733,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
           if (w < warp) qbase += c;
           nq += c;
         }
+        pf[9] += nq;
         if (active && !ok) {
           const int slot = qbase + __popc(open & ((1u << lane) - 1u));
           s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i));
@@ -741,10 +747,16 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
           int fi = __float_as_int(qb.y);
           const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, q.x, q.y, q.z), prm.search_d2, prm.far_ring, lane, fb, fi);
           if (!done) nn_query_brute_warp(job.tgt, q.x, q.y, q.z, lane, fb, fi);
-          if (lane == 0) {
-            const int qi = __float_as_int(q.w);
-            finish_point(qi, __ldg(job.src + qi), fb, fi);
-          }
+          if (lane == 0) s_qb[e] = make_float2(fb, __int_as_float(fi));
+        }
+        __syncthreads();
+        // the far queries are FINISHED thread-per-query (Mahalanobis matrix, residual) once all searches are
+        // done — not by lane 0 of each searching warp, which serialised ~400 FP64 operations per query
+        if (tid < nq) {
+          const float4 q = s_q[tid];
+          const float2 qb = s_qb[tid];
+          const int qi = __float_as_int(q.w);
+          finish_point(qi, __ldg(job.src + qi), qb.x, __float_as_int(qb.y));
         }
         __syncthreads();  // the queue is reused by the next slice
       } else {
@@ -758,6 +770,8 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         }
       }
     }
+    const long long tp1 = clock64();
+    if (phase == GP_LINEARIZE) { pf[0] += tp_near - tp0; pf[1] += tp1 - tp_near; pf[7] += 1; } else { pf[2] += tp1 - tp0; pf[8] += 1; }
     // ---- reduce: warp shuffles -> shared memory -> one partial row per CTA -> group
 #pragma unroll
     for (int k = 0; k < kGicpAcc; ++k) {
@@ -774,9 +788,12 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
       if (G == 1) s.tot[tid] = v;
       else partials[((size_t)parity * G + rank) * kGicpStride + tid] = v;
     }
+    const long long tp2 = clock64();
+    long long tp3 = tp2;
     if (G > 1) {
       epoch += (unsigned)G;
       gicp_group_barrier(barrier, epoch);
+      tp3 = clock64();
       const double* base = partials + (size_t)parity * G * kGicpStride + lane;
       double v = 0.0;
       if (lane < kGicpAcc)
@@ -793,9 +810,14 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     }
     parity ^= 1;
     __syncthreads();
+    const long long tp4 = clock64();
     if (tid == 0) gicp_step(s, prm);
     __syncthreads();
+    const long long tp5 = clock64();
+    pf[3] += tp2 - tp1; pf[4] += tp3 - tp2; pf[5] += tp4 - tp3; pf[6] += tp5 - tp4;
   }
+  if (job.prof && rank == 0 && tid == 0)
+    for (int k = 0; k < 10; ++k) job.prof[k] = pf[k];
   if (rank == 0 && tid == 0) {
     b200reg_result r;
     for (int c = 0; c < 3; ++c) {
