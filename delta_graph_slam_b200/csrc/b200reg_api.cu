@@ -282,7 +282,10 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
-  B200_ATTR(prefer_shared(k_gicp_knn)); B200_ATTR(prefer_shared(k_gicp_knn_brute)); B200_ATTR(prefer_shared(k_gicp_regularize)); B200_ATTR(prefer_shared(k_gicp_align));
+  B200_ATTR(prefer_shared(k_gicp_knn)); B200_ATTR(prefer_shared(k_gicp_knn_brute)); B200_ATTR(prefer_shared(k_gicp_regularize));
+  // k_gicp_align needs 17.5 KB of shared memory and keeps its 29 double accumulators + 3x3 temporaries in a
+  // 1.4 KB per-thread stack frame (128-register cap at 512 threads): it wants the L1, not the carve-out
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
   B200_ATTR(ndt_leaf_prefer_shared());
 #undef B200_ATTR
   if (device < 64) done.fetch_or(1ull << device);

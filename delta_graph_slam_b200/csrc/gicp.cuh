@@ -671,9 +671,10 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     s.phase = (prm.max_iterations > 0 && n_src > 0) ? GP_LINEARIZE : GP_DONE;
   }
   __syncthreads();
-  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pf[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   while (s.phase != GP_DONE) {
     const int phase = s.phase;
+    const bool seed_from_corr = s.n_lin > 0;  // job.corr holds the correspondences of this align's previous linearize pass
     const long long tp0 = clock64();
     long long tp_near = tp0;
     double acc[kGicpAcc];
@@ -717,8 +718,20 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         const float qz = affine_row(s.Tf[8], s.Tf[9], s.Tf[10], s.Tf[11], p.x, p.y, p.z);
         float best = 3.402823466e+38f;
         int best_idx = kNoIndex;
-        bool ok = true;
-        if (active && grid_ok) ok = nn_query_near(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
+        int st = kNnDone;
+        // from the second linearize pass on, last pass's correspondence seeds the search: it is a real
+        // target point, so the answer is the same exact nearest neighbour, but nearly every neighbour cell
+        // is pruned at once and a point that used to need a far search is settled after a ring or two
+        if (active && grid_ok && seed_from_corr) {
+          const int cp = job.corr[i];
+          if (cp >= 0) {
+            const float4 tp = __ldg(job.tgt_pts + cp);
+            best = l2_simple(qx, qy, qz, tp.x, tp.y, tp.z);
+            best_idx = cp;
+          }
+        }
+        if (active && grid_ok) st = nn_query_near<4, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
+        const bool ok = st == kNnDone;
         // queue slots in thread order (ballot compaction): the far points are always dealt to the same
         // warps, so the summation order — and with it the result — is reproducible bit for bit
         const unsigned open = __ballot_sync(0xffffffffu, active && !ok);
@@ -736,29 +749,35 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         pf[9] += nq;
         if (active && !ok) {
           const int slot = qbase + __popc(open & ((1u << lane) - 1u));
-          s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i));
+          s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i | (st == kNnBail ? (int)kBailFlag : 0)));
           s_qb[slot] = make_float2(best, __int_as_float(best_idx));
         }
         __syncthreads();
+        const long long tq0 = clock64();
         for (int e = warp; e < nq; e += kGicpWarps) {
           const float4 q = s_q[e];
           const float2 qb = s_qb[e];
           float fb = qb.x;
           int fi = __float_as_int(qb.y);
-          const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, q.x, q.y, q.z), prm.search_d2, prm.far_ring, lane, fb, fi);
+          const long long tf0 = clock64();
+          const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, q.x, q.y, q.z), prm.search_d2, prm.far_ring, lane, fb, fi, (__float_as_int(q.w) & (int)kBailFlag) != 0);
+          const long long tf1 = clock64();
           if (!done) nn_query_brute_warp(job.tgt, q.x, q.y, q.z, lane, fb, fi);
+          pf[10] += done ? 0 : 1; pf[11] += tf1 - tf0; pf[12] += clock64() - tf1;
           if (lane == 0) s_qb[e] = make_float2(fb, __int_as_float(fi));
         }
         __syncthreads();
+        const long long tq1 = clock64();
         // the far queries are FINISHED thread-per-query (Mahalanobis matrix, residual) once all searches are
         // done — not by lane 0 of each searching warp, which serialised ~400 FP64 operations per query
         if (tid < nq) {
           const float4 q = s_q[tid];
           const float2 qb = s_qb[tid];
-          const int qi = __float_as_int(q.w);
+          const int qi = __float_as_int(q.w) & (int)~kBailFlag;
           finish_point(qi, __ldg(job.src + qi), qb.x, __float_as_int(qb.y));
         }
         __syncthreads();  // the queue is reused by the next slice
+        pf[13] += tq0 - tp_near; pf[14] += tq1 - tq0; pf[15] += clock64() - tq1;
       } else {
         const int c = active ? job.corr[i] : -1;
         if (c >= 0) {
@@ -817,7 +836,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     pf[3] += tp2 - tp1; pf[4] += tp3 - tp2; pf[5] += tp4 - tp3; pf[6] += tp5 - tp4;
   }
   if (job.prof && rank == 0 && tid == 0)
-    for (int k = 0; k < 10; ++k) job.prof[k] = pf[k];
+    for (int k = 0; k < 16; ++k) job.prof[k] = pf[k];
   if (rank == 0 && tid == 0) {
     b200reg_result r;
     for (int c = 0; c < 3; ++c) {

@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restric
   fit_transform(T, __ldg(job.src + i), qx, qy, qz);
   float best = 3.402823466e+38f;
   int best_idx = kNoIndex;
-  bool ok = true;
-  if (job.view.n > 0 && gp.any && !gp.overflow) ok = nn_query_near(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  int st = kNnDone;
+  if (job.view.n > 0 && gp.any && !gp.overflow) st = nn_query_near(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
   d2_out[job.d2_offset + i] = best_idx != kNoIndex ? best : kNoNeighbour;
-  if (!ok) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i);
+  if (st != kNnDone) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i | (st == kNnBail ? kBailFlag : 0u));
 }
 
 // far phase: one warp per pending (job, point); still-open queries move to pending2
@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(256) k_nn_far_batch(const FitJob* __restrict__
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int np = (int)*n_pending;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < np; w += warps) {
-    const uint2 pe = pending[w];
+    uint2 pe = pending[w];
+    const bool bailed = (pe.y & kBailFlag) != 0u;
+    pe.y &= ~kBailFlag;
     const FitJob& job = jobs[pe.x];
     const GridParams gp = job.view.meta->grid;
     float qx, qy, qz;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256) k_nn_far_batch(const FitJob* __restrict__
     const float prev = d2_out[job.d2_offset + pe.y];
     float best = prev == kNoNeighbour ? 3.402823466e+38f : prev;
     int best_idx = prev == kNoNeighbour ? kNoIndex : 0;  // the index itself is not needed for the score
-    const bool ok = nn_query_far_warp(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, kFarRing, lane, best, best_idx);
+    const bool ok = nn_query_far_warp(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, kFarRing, lane, best, best_idx, bailed);
     __syncwarp();
     if (lane == 0) {
       d2_out[job.d2_offset + pe.y] = best_idx != kNoIndex ? best : kNoNeighbour;

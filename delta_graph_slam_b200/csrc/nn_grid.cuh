@@ -157,29 +157,68 @@ __device__ __forceinline__ float nn_box_d2(const GridParams& gp, const NnQuery& 
 
 __device__ __forceinline__ bool nn_better(float d, int idx, float best, int best_idx) { return d < best || (d == best && idx < best_idx); }
 
-// scan one cell; best_idx = INT_MAX-style sentinel 0x7FFFFFFF while nothing was found
-__device__ __forceinline__ void nn_scan_cell(const NnView& g, const GridParams& gp, const NnQuery& q, int ix, int iy, int iz, float& best, int& best_idx) {
+// scan one cell; best_idx = INT_MAX-style sentinel 0x7FFFFFFF while nothing was found.  DEPTH loads are
+// in flight at a time: a thread-per-query scan is a chain of L2 round trips.  The fitness kernels keep
+// DEPTH = 4 (measured: with 8 the 16 extra registers cost them a resident CTA per SM and the batched
+// fitness went from 16.7 to 22.0 ms per 1024 pairs; in the GICP align kernel 8 was slower as well, 374 vs 318 us).
+template <int DEPTH = 4>
+__device__ __forceinline__ uint32_t nn_scan_cell(const NnView& g, const GridParams& gp, const NnQuery& q, int ix, int iy, int iz, float& best, int& best_idx) {
   const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
   const uint2 run = nn_lookup(g, key);
-  // (eight loads in flight instead of four were measured: the 16 extra registers cost the thread-per-query
-  // kernels a resident CTA per SM and the batched fitness went from 16.7 to 22.0 ms per 1024 pairs)
+  if (DEPTH == 4) {
 #pragma unroll 4
-  for (uint32_t j = run.x; j < run.y; ++j) {
-    const float4 p = __ldg(g.pts + j);
-    const float d = l2_simple(q.qx, q.qy, q.qz, p.x, p.y, p.z);
-    const int idx = __float_as_int(p.w);
-    if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+    for (uint32_t j = run.x; j < run.y; ++j) {
+      const float4 p = __ldg(g.pts + j);
+      const float d = l2_simple(q.qx, q.qy, q.qz, p.x, p.y, p.z);
+      const int idx = __float_as_int(p.w);
+      if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+    }
+  } else {
+    for (uint32_t j = run.x; j < run.y; j += DEPTH) {
+      float4 p[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; ++u) p[u] = j + u < run.y ? __ldg(g.pts + j + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < DEPTH; ++u) {
+        if (j + u < run.y) {
+          const float d = l2_simple(q.qx, q.qy, q.qz, p[u].x, p[u].y, p[u].z);
+          const int idx = __float_as_int(p[u].w);
+          if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+        }
+      }
+    }
   }
+  return run.y - run.x;
 }
 
 constexpr int kNoIndex = 0x7FFFFFFF;
 
-// near phase, one thread: rings 0..kNearRing.  Returns true when the query is resolved.
-__device__ __forceinline__ bool nn_query_near(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, float& best, int& best_idx) {
-  best = 3.402823466e+38f;
-  best_idx = kNoIndex;
+// near phase, one thread: rings 0..kNearRing.
+//   kNnDone : resolved
+//   kNnOpen : rings 0..kNearRing done, something farther out can still win -> far phase from ring kNearRing + 1
+//   kNnBail : (only with -DB200_NN_NEAR_BUDGET=n) the thread has scanned more than n points without
+//             settling -> the far phase takes the query over from ring 0, 32 lanes to a cell.  Built to test
+//             whether single slow threads inside dense clumps hold their CTA at the block barrier;
+//             measured with n = 128: exact (full GPU suite green) but no faster — batched fitness 18.9 vs
+//             16.8 ms per 1024 pairs, GICP align 0.324 vs 0.289 ms — so the default is off.
+// SEEDED: best / best_idx arrive holding a real point of the cloud (e.g. last iteration's correspondence),
+// which only tightens the pruning — the result is the same exact nearest neighbour.
+constexpr int kNnDone = 0, kNnOpen = 1, kNnBail = 2;
+#ifndef B200_NN_NEAR_BUDGET
+#define B200_NN_NEAR_BUDGET 0
+#endif
+constexpr uint32_t kNearBudget = B200_NN_NEAR_BUDGET;
+constexpr uint32_t kBailFlag = 1u << 30;  // carried in the point index of a pending / queue entry
+
+template <int DEPTH = 4, bool SEEDED = false>
+__device__ __forceinline__ int nn_query_near(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, float& best, int& best_idx) {
+  if (!SEEDED) {
+    best = 3.402823466e+38f;
+    best_idx = kNoIndex;
+  }
+  uint32_t scanned = 0;
   for (int r = 0; r <= kNearRing; ++r) {
-    if (r >= 1 && nn_settled(gp, q, r, best, max_d2)) return true;
+    if (r >= 1 && nn_settled(gp, q, r, best, max_d2)) return kNnDone;
     const int z0 = max(q.cz - r, gp.min_b[2]), z1 = min(q.cz + r, gp.max_b[2]);
     const int y0 = max(q.cy - r, gp.min_b[1]), y1 = min(q.cy + r, gp.max_b[1]);
     for (int iz = z0; iz <= z1; ++iz) {
@@ -189,13 +228,14 @@ __device__ __forceinline__ bool nn_query_near(const NnView& g, const GridParams&
         const int xstep = face ? 1 : (r == 0 ? 1 : 2 * r);
         for (int ix = q.cx - r; ix <= q.cx + r; ix += xstep) {
           if (ix < gp.min_b[0] || ix > gp.max_b[0]) continue;
-          if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
-          nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
+          if (nn_box_d2(gp, q, ix, iy, iz) > fminf(best, max_d2)) continue;  // beyond the range of interest: nothing in there can count
+          if (kNearBudget != 0u && scanned > kNearBudget) return kNnBail;
+          scanned += nn_scan_cell<DEPTH>(g, gp, q, ix, iy, iz, best, best_idx);
         }
       }
     }
   }
-  return nn_settled(gp, q, kNearRing + 1, best, max_d2);
+  return nn_settled(gp, q, kNearRing + 1, best, max_d2) ? kNnDone : kNnOpen;
 }
 
 __device__ __forceinline__ void nn_warp_merge(float& best, int& best_idx) {
@@ -207,10 +247,77 @@ __device__ __forceinline__ void nn_warp_merge(float& best, int& best_idx) {
   }
 }
 
+// one warp scans the runs its lanes hold (empty when run.x == run.y) for ONE query, flattened: the
+// points of all runs are numbered consecutively and batch b takes points 32 b .. 32 b + 31 whatever
+// run they belong to; the load of the next batch is issued before the current one is compared
+__device__ __forceinline__ void nn_scan_runs_warp(const NnView& g, uint2 run, const NnQuery& q, int lane, float& best, int& best_idx) {
+  const uint32_t len = run.y - run.x;
+  uint32_t incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0u) return;
+  const uint32_t first = run.x - (incl - len);
+  auto fetch = [&](uint32_t t0, float4& p) -> bool {
+    const uint32_t t = t0 + lane;
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, o + step - 1);
+      if (v <= t) o += step;
+    }
+    const uint32_t f = __shfl_sync(0xffffffffu, first, o & 31);
+    const bool ok = t < total;
+    p = ok ? __ldg(g.pts + (f + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return ok;
+  };
+  float4 p_cur, p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool ok_cur = fetch(0u, p_cur), ok_next = false;
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    if (t0 + 32 < total) ok_next = fetch(t0 + 32, p_next);
+    if (ok_cur) {
+      const float d = l2_simple(q.qx, q.qy, q.qz, p_cur.x, p_cur.y, p_cur.z);
+      const int idx = __float_as_int(p_cur.w);
+      if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+    }
+    p_cur = p_next;
+    ok_cur = ok_next;
+    ok_next = false;
+  }
+}
+
+// rings 0 and 1 for one query by a whole warp (a query the near phase gave up on): the query's own cell
+// is scanned 32 points at a time, then the 26 neighbours are pruned against that result and what
+// survives is scanned flattened
+__device__ __forceinline__ void nn_rings01_warp(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int lane, float& best, int& best_idx) {
+  const bool use_occ = nn_occ_valid(g);
+  auto cell_run = [&](int ix, int iy, int iz) -> uint2 {
+    if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) return make_uint2(0u, 0u);
+    if (nn_box_d2(gp, q, ix, iy, iz) > fminf(best, max_d2)) return make_uint2(0u, 0u);
+    const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+    if (use_occ && !nn_occ_bit(g, key)) return make_uint2(0u, 0u);
+    return nn_lookup(g, key);
+  };
+  uint2 run = make_uint2(0u, 0u);
+  if (lane == 0) run = cell_run(q.cx, q.cy, q.cz);
+  nn_scan_runs_warp(g, run, q, lane, best, best_idx);
+  nn_warp_merge(best, best_idx);
+  run = make_uint2(0u, 0u);
+  if (lane < 27 && lane != 13) run = cell_run(q.cx + lane % 3 - 1, q.cy + (lane / 3) % 3 - 1, q.cz + lane / 9 - 1);
+  nn_scan_runs_warp(g, run, q, lane, best, best_idx);
+  nn_warp_merge(best, best_idx);
+}
+
 // far phase, one warp (all 32 lanes call with the same query and the near phase's best): rings
-// kNearRing+1 .. max_ring.  Returns true when resolved; best / best_idx are warp-uniform on return.
-__device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int max_ring, int lane, float& best, int& best_idx) {
+// kNearRing+1 .. max_ring, preceded by rings 0..kNearRing when the near phase bailed out (from_ring0).
+// Returns true when resolved; best / best_idx are warp-uniform on return.
+__device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int max_ring, int lane, float& best, int& best_idx,
+                                                  bool from_ring0 = false) {
   const bool use_occ = nn_occ_valid(g);  // warp-uniform
+  if (from_ring0) nn_rings01_warp(g, gp, q, max_d2, lane, best, best_idx);
   for (int r = kNearRing + 1; r <= max_ring; ++r) {
     if (nn_settled(gp, q, r, best, max_d2)) return true;
     const int side = 2 * r + 1, inner = 2 * r - 1;
@@ -229,7 +336,7 @@ __device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridPar
           const int dz = row / side - r, dy = row - (dz + r) * side - r;
           const int iy = q.cy + dy, iz = q.cz + dz;
           if (iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
-          if (nn_box_d2(gp, q, xq, iy, iz) > best) continue;  // no cell of this row can win
+          if (nn_box_d2(gp, q, xq, iy, iz) > fminf(best, max_d2)) continue;  // no cell of this row can win or lies in range
           const bool face = dy == -r || dy == r || dz == -r || dz == r;
           const uint32_t key0 = (uint32_t)((x0 - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
           uint32_t bits = nn_occ_bits(g, key0, nb);
@@ -238,7 +345,7 @@ __device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridPar
             const int b = __ffs(bits) - 1;
             bits &= bits - 1u;
             const int ix = x0 + b;
-            if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+            if (nn_box_d2(gp, q, ix, iy, iz) > fminf(best, max_d2)) continue;
             nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
           }
         }
@@ -260,7 +367,7 @@ __device__ __forceinline__ bool nn_query_far_warp(const NnView& g, const GridPar
         }
         const int ix = q.cx + dx, iy = q.cy + dy, iz = q.cz + dz;
         if (ix < gp.min_b[0] || ix > gp.max_b[0] || iy < gp.min_b[1] || iy > gp.max_b[1] || iz < gp.min_b[2] || iz > gp.max_b[2]) continue;
-        if (nn_box_d2(gp, q, ix, iy, iz) > best) continue;
+        if (nn_box_d2(gp, q, ix, iy, iz) > fminf(best, max_d2)) continue;
         nn_scan_cell(g, gp, q, ix, iy, iz, best, best_idx);
       }
     }
@@ -314,11 +421,11 @@ __global__ void __launch_bounds__(256) k_nn_search(NnView g, const float4* __res
   q_out[i] = make_float4(qx, qy, qz, 1.f);
   float best = 3.402823466e+38f;
   int best_idx = kNoIndex;
-  bool ok = true;
-  if (g.n > 0 && gp.any && !gp.overflow) ok = nn_query_near(g, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  int st = kNnDone;
+  if (g.n > 0 && gp.any && !gp.overflow) st = nn_query_near(g, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
   d2_out[i] = best;
   idx_out[i] = best_idx == kNoIndex ? -1 : best_idx;
-  if (!ok) pending[atomicAdd(n_pending, 1u)] = i;
+  if (st != kNnDone) pending[atomicAdd(n_pending, 1u)] = i | (st == kNnBail ? (int)kBailFlag : 0);
 }
 
 // far: one warp per pending query; what is still open afterwards moves to pending2
@@ -329,11 +436,12 @@ __global__ void __launch_bounds__(256) k_nn_far(NnView g, const float4* __restri
   const int np = (int)*n_pending;
   const GridParams gp = g.meta->grid;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < np; w += warps) {
-    const int i = pending[w];
+    const int pe = pending[w];
+    const int i = pe & (int)~kBailFlag;
     const float4 q = queries[i];
     float best = d2_out[i];
     int best_idx = idx_out[i] < 0 ? kNoIndex : idx_out[i];
-    const bool ok = nn_query_far_warp(g, gp, nn_make_query(gp, q.x, q.y, q.z), max_d2, kFarRing, lane, best, best_idx);
+    const bool ok = nn_query_far_warp(g, gp, nn_make_query(gp, q.x, q.y, q.z), max_d2, kFarRing, lane, best, best_idx, (pe & (int)kBailFlag) != 0);
     __syncwarp();
     if (lane == 0) {
       d2_out[i] = best;

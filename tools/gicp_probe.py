@@ -15,7 +15,7 @@ for _ in range(3):
     t = time.perf_counter(); g.align(None); dt = time.perf_counter() - t
 v = np.zeros(16, np.int64)
 d._lib.check(g._h, d._lib.load().b200reg_get_profile(g._h, v.ctypes.data))
-names = ("near", "far_queue", "error_pass", "block_reduce", "group_barrier", "row_sum", "step", "n_linearize", "n_error", "far_queries_cta0")
+names = ("near", "far_queue", "error_pass", "block_reduce", "group_barrier", "row_sum", "step", "n_linearize", "n_error", "far_queries_cta0", "warp0_brute_calls", "warp0_far_cycles", "warp0_brute_cycles", "fq_queue_fill", "fq_search", "fq_finish")
 print("align (with covariances of the source) %.1f us" % (dt * 1e6), g.getResult()["iterations"], "iterations")
-print({n: int(x) for n, x in zip(names, v[:10])})
+print({n: int(x) for n, x in zip(names, v[:16])})
 print({n: round(float(x) / 1965.0, 1) for n, x in zip(names[:7], v[:7])}, "us total")
