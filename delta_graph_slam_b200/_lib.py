@@ -31,7 +31,7 @@ EXPORTS = [
     "b200reg_radius_outlier_removal", "b200reg_radius_outlier_removal_device", "b200reg_radius_outlier_removal_begin", "b200reg_radius_outlier_removal_device_begin",
     "b200reg_radius_outlier_removal_end",
     "b200reg_cloud_put", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
-    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
+    "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
 
 
@@ -133,6 +133,7 @@ def load():
     L.b200reg_ndt_get_leaves.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, C.POINTER(C.c_double), vp, vp]
     L.b200reg_get_profile.argtypes = [vp, vp]
+    L.b200reg_set_profile.argtypes = [vp, C.c_int]
     L.b200reg_get_nn_stats.argtypes = [vp, vp]
     L.b200reg_set_sort_path.argtypes = [C.c_int]
     L.b200reg_set_timing.argtypes = [vp, C.c_int]

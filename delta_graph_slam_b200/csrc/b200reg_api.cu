@@ -152,6 +152,7 @@ struct b200reg_handle {
   // launch, resolved lazily (when a pair is reused or the counters are read) so that timing never
   // puts an event synchronisation on the critical path of a call
   bool timing = false;
+  bool profile = false;  // developer cycle counters (b200reg_set_profile): the PROF instantiation of the align kernels
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // aliases of the pair of the launch in flight
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   std::vector<int> ev_pending;
@@ -271,11 +272,16 @@ cudaError_t init_kernel_attributes(int device) {
   if (device < 64 && (done.load() >> device) & 1ull) return cudaSuccess;
   cudaError_t e;
 #define B200_ATTR(expr) if ((e = (expr)) != cudaSuccess) return e
-  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
-  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
-  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
-  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
-  B200_ATTR(prefer_shared(k_ndt_align<1>)); B200_ATTR(prefer_shared(k_ndt_align<7>)); B200_ATTR(prefer_shared(k_ndt_align<27>)); B200_ATTR(prefer_shared(k_ndt_align<0>));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<27, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<27, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_ndt_align<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes));
+  B200_ATTR(prefer_shared(k_ndt_align<1, false>)); B200_ATTR(prefer_shared(k_ndt_align<7, false>)); B200_ATTR(prefer_shared(k_ndt_align<27, false>)); B200_ATTR(prefer_shared(k_ndt_align<0, false>));
+  B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
   B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
@@ -285,7 +291,8 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_gicp_knn)); B200_ATTR(prefer_shared(k_gicp_knn_brute)); B200_ATTR(prefer_shared(k_gicp_regularize));
   // k_gicp_align needs 17.5 KB of shared memory and keeps its 29 double accumulators + 3x3 temporaries in a
   // 1.4 KB per-thread stack frame (128-register cap at 512 threads): it wants the L1, not the carve-out
-  B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
+  B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
   B200_ATTR(ndt_leaf_prefer_shared());
 #undef B200_ATTR
   if (device < 64) done.fetch_or(1ull << device);
@@ -385,7 +392,8 @@ cudaError_t launch_ndt(b200reg_handle* h, int n_jobs, int ctas_per_group, int n_
   unsigned int* barriers = h->barriers.p;
   unsigned int* queue = h->barriers.p + (size_t)n_groups * 32;  // the job ticket counter sits behind the groups' barrier lines
   void* args[] = {(void*)&jobs, (void*)&n_jobs, (void*)&ctas_per_group, (void*)&tq, (void*)&prm, (void*)&partials, (void*)&barriers, (void*)&queue, (void*)&sj};
-  return cudaLaunchCooperativeKernel((const void*)k_ndt_align<MODE>, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
+  const void* fn = (h->profile && single) ? (const void*)k_ndt_align<MODE, true> : (const void*)k_ndt_align<MODE, false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(ctas_per_group * n_groups), dim3(kAlignThreads), args, kStageBytes, h->stream);
 }
 
 cudaError_t launch_ndt_mode(b200reg_handle* h, int n_jobs, int G, int n_groups, const NdtJob* single = nullptr, NdtTargetQueue tq = NdtTargetQueue{nullptr, nullptr, 0}) {
@@ -526,7 +534,7 @@ int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
   unsigned int* barrier = h->barriers.p;
   void* args[] = {(void*)job, (void*)&g, (void*)&prm, (void*)&partials, (void*)&barrier};
   if ((rc = begin_timed_launch(h))) return rc;
-  B200_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_gicp_align, dim3(G), dim3(kGicpThreads), args, 0, h->stream));
+  B200_CUDA_TRY(cudaLaunchCooperativeKernel(h->profile ? (const void*)k_gicp_align<true> : (const void*)k_gicp_align<false>, dim3(G), dim3(kGicpThreads), args, 0, h->stream));
   launch_counter() += 1;
   if ((rc = end_timed_launch(h))) return rc;
   return B200REG_OK;
@@ -1524,10 +1532,16 @@ int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long
   return B200REG_OK;
 }
 
+int b200reg_set_profile(b200reg_handle* h, int on) {
+  if (!h) return B200REG_E_INVALID;
+  h->profile = on != 0;
+  return B200REG_OK;
+}
+
 int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || !out6) return B200REG_E_INVALID;
-  if (!h->prof.p) return B200REG_E_STATE;
+  if (!h->prof.p || !h->profile) { h->err = "no profile: b200reg_set_profile(h, 1) before the align"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));

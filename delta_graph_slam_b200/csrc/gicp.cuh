@@ -646,6 +646,7 @@ __device__ __forceinline__ void gicp_group_barrier(unsigned int* counter, unsign
   __syncthreads();
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_constant__ GicpJob job, int G, GicpParams prm, double* partials, unsigned int* barrier) {
   __shared__ GicpShared s;
   __shared__ float4 s_q[kGicpThreads];   // far-query queue of the current slice: transformed point, w = source index
@@ -671,11 +672,11 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     s.phase = (prm.max_iterations > 0 && n_src > 0) ? GP_LINEARIZE : GP_DONE;
   }
   __syncthreads();
-  long long pf[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pf[PROF ? 16 : 1] = {0};
   while (s.phase != GP_DONE) {
     const int phase = s.phase;
     const bool seed_from_corr = s.n_lin > 0;  // job.corr holds the correspondences of this align's previous linearize pass
-    const long long tp0 = clock64();
+    const long long tp0 = PROF ? clock64() : 0;
     long long tp_near = tp0;
     double acc[kGicpAcc];
 #pragma unroll
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         if (lane == 0) s_wq[warp] = __popc(open);
         if (active && ok) finish_point(i, p, best, best_idx);
         __syncthreads();
-        tp_near = clock64();
+        if (PROF) tp_near = clock64();
         int qbase = 0, nq = 0;
 #pragma unroll
         for (int w = 0; w < kGicpWarps; ++w) {
@@ -746,28 +747,28 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
           if (w < warp) qbase += c;
           nq += c;
         }
-        pf[9] += nq;
+        if (PROF) pf[9] += nq;
         if (active && !ok) {
           const int slot = qbase + __popc(open & ((1u << lane) - 1u));
           s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i | (st == kNnBail ? (int)kBailFlag : 0)));
           s_qb[slot] = make_float2(best, __int_as_float(best_idx));
         }
         __syncthreads();
-        const long long tq0 = clock64();
+        const long long tq0 = PROF ? clock64() : 0;
         for (int e = warp; e < nq; e += kGicpWarps) {
           const float4 q = s_q[e];
           const float2 qb = s_qb[e];
           float fb = qb.x;
           int fi = __float_as_int(qb.y);
-          const long long tf0 = clock64();
+          const long long tf0 = PROF ? clock64() : 0;
           const bool done = nn_query_far_warp(job.tgt, gp, nn_make_query(gp, q.x, q.y, q.z), prm.search_d2, prm.far_ring, lane, fb, fi, (__float_as_int(q.w) & (int)kBailFlag) != 0);
-          const long long tf1 = clock64();
+          const long long tf1 = PROF ? clock64() : 0;
           if (!done) nn_query_brute_warp(job.tgt, q.x, q.y, q.z, lane, fb, fi);
-          pf[10] += done ? 0 : 1; pf[11] += tf1 - tf0; pf[12] += clock64() - tf1;
+          if (PROF) { pf[10] += done ? 0 : 1; pf[11] += tf1 - tf0; pf[12] += clock64() - tf1; }
           if (lane == 0) s_qb[e] = make_float2(fb, __int_as_float(fi));
         }
         __syncthreads();
-        const long long tq1 = clock64();
+        const long long tq1 = PROF ? clock64() : 0;
         // the far queries are FINISHED thread-per-query (Mahalanobis matrix, residual) once all searches are
         // done — not by lane 0 of each searching warp, which serialised ~400 FP64 operations per query
         if (tid < nq) {
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
           finish_point(qi, __ldg(job.src + qi), qb.x, __float_as_int(qb.y));
         }
         __syncthreads();  // the queue is reused by the next slice
-        pf[13] += tq0 - tp_near; pf[14] += tq1 - tq0; pf[15] += clock64() - tq1;
+        if (PROF) { pf[13] += tq0 - tp_near; pf[14] += tq1 - tq0; pf[15] += clock64() - tq1; }
       } else {
         const int c = active ? job.corr[i] : -1;
         if (c >= 0) {
@@ -789,8 +790,10 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
         }
       }
     }
-    const long long tp1 = clock64();
-    if (phase == GP_LINEARIZE) { pf[0] += tp_near - tp0; pf[1] += tp1 - tp_near; pf[7] += 1; } else { pf[2] += tp1 - tp0; pf[8] += 1; }
+    const long long tp1 = PROF ? clock64() : 0;
+    if (PROF) {
+      if (phase == GP_LINEARIZE) { pf[0] += tp_near - tp0; pf[1] += tp1 - tp_near; pf[7] += 1; } else { pf[2] += tp1 - tp0; pf[8] += 1; }
+    }
     // ---- reduce: warp shuffles -> shared memory -> one partial row per CTA -> group
 #pragma unroll
     for (int k = 0; k < kGicpAcc; ++k) {
@@ -807,12 +810,12 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
       if (G == 1) s.tot[tid] = v;
       else partials[((size_t)parity * G + rank) * kGicpStride + tid] = v;
     }
-    const long long tp2 = clock64();
+    const long long tp2 = PROF ? clock64() : 0;
     long long tp3 = tp2;
     if (G > 1) {
       epoch += (unsigned)G;
       gicp_group_barrier(barrier, epoch);
-      tp3 = clock64();
+      if (PROF) tp3 = clock64();
       const double* base = partials + (size_t)parity * G * kGicpStride + lane;
       double v = 0.0;
       if (lane < kGicpAcc)
@@ -829,13 +832,15 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     }
     parity ^= 1;
     __syncthreads();
-    const long long tp4 = clock64();
+    const long long tp4 = PROF ? clock64() : 0;
     if (tid == 0) gicp_step(s, prm);
     __syncthreads();
-    const long long tp5 = clock64();
-    pf[3] += tp2 - tp1; pf[4] += tp3 - tp2; pf[5] += tp4 - tp3; pf[6] += tp5 - tp4;
+    if (PROF) {
+      const long long tp5 = clock64();
+      pf[3] += tp2 - tp1; pf[4] += tp3 - tp2; pf[5] += tp4 - tp3; pf[6] += tp5 - tp4;
+    }
   }
-  if (job.prof && rank == 0 && tid == 0)
+  if (PROF && job.prof && rank == 0 && tid == 0)
     for (int k = 0; k < 16; ++k) job.prof[k] = pf[k];
   if (rank == 0 && tid == 0) {
     b200reg_result r;

@@ -281,12 +281,15 @@ __host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (
 // ---- the optimiser state machine; one lane, after every derivative pass ----------------------
 // Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the next pass
 // must be evaluated at s.x_t (the caller then rebuilds T and the angle tables).
+template <bool PROF>
 static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm) {
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
   const double* t = s.tot;
-  long long tk = clock64();
-  auto lap = [&](int slot) { const long long now = clock64(); s.pf[slot] += now - tk; tk = now; };
+  long long tk = PROF ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (PROF) { const long long now = clock64(); s.pf[slot] += now - tk; tk = now; }
+  };
   s.n_eval++;
   s.n_pass++;
   s.hits += t[28];
@@ -599,7 +602,11 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
   __syncthreads();
 }
 
-template <int MODE>
+// PROF: developer cycle counters (b200reg_set_profile).  A template parameter, not a run-time switch: the
+// counters and time stamps of the profiled build cost every thread a dozen registers, which the 128-register
+// kernel pays for in spills — ncu showed 4.7 M local-memory sectors per registration (more than the
+// algorithmic traffic) coming from the counters alone when they were always on.
+template <int MODE, bool PROF>
 __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtTargetQueue tq, NdtParams prm, double* partials_all, unsigned int* barriers,
                                                                 unsigned int* queue, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
@@ -677,8 +684,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
     const NdtJob& job = jobs ? jobs[jb] : single;  // one registration: the job rides in the kernel parameters
     const GridParams gp = job.grid.meta->grid;
     const int n_src = job.n_src;
-    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long ts0 = clock64();
+    long long prof[PROF ? 10 : 1] = {0};
+    const long long ts0 = PROF ? clock64() : 0;
     // ---- stage the target grid in shared memory when it fits
     NdtLookup look;
     bool grid_staged = false;
@@ -740,12 +747,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       }
     }
     __syncthreads();
-    prof[6] = clock64() - ts0;
+    if (PROF) prof[6] = clock64() - ts0;
     const int n_groups32 = (n_src + 31) >> 5;
     const float res2 = __fmul_rn((float)prm.resolution, (float)prm.resolution);
     while (true) {
       // ---- pass
-      const long long t0 = clock64();
+      const long long t0 = PROF ? clock64() : 0;
       constexpr int need_h = 1;  // every pass evaluates the Hessian (see ndt_step, PH_MT_ITER)
       const float d1h = (float)s.gauss_d1, d1l = (float)(s.gauss_d1 - (double)d1h);
       const float gd2 = (float)s.gauss_d2;
@@ -795,7 +802,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
           accd += (double)vals[0];
         }
       }
-      const long long t1 = clock64();
+      const long long t1 = PROF ? clock64() : 0;
       // ---- block reduce: warp totals -> shared memory -> one partial row per CTA
       s.red[warp][lane] = accd;
       __syncthreads();
@@ -809,12 +816,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       // ---- group sync + redundant fixed-order reduction of the G partials.  (Tagging every row with
       // its own arrival flag instead of one counter barrier was measured: 2368 polling lanes cost more
       // than 148 spinners on one line — 288 us vs 223 us per registration.)
-      const long long t2 = clock64();
+      const long long t2 = PROF ? clock64() : 0;
       long long t3 = t2;
       if (G > 1) {
         epoch += (unsigned)G;
         group_barrier(barrier, epoch);
-        t3 = clock64();
+        if (PROF) t3 = clock64();
         // warp w sums rows w, w+16, ... (each row one coalesced 256-byte read), then the 16 row
         // groups are combined through shared memory; fixed order -> every CTA gets the same bits
         const double* base = partials + (size_t)parity * G * kAccStride + lane;
@@ -840,7 +847,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       }
       parity ^= 1;
       __syncthreads();
-      const long long t4 = clock64();
+      const long long t4 = PROF ? clock64() : 0;
       // ---- optimiser step (warp 0 of every CTA, identical inputs -> identical state)
       if (tid < 32) {
         if (tid == 0) {
@@ -851,28 +858,30 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
             s.phase = PH_DONE;
             s.new_pose = 0;
           } else {
-            ndt_step(s, prm);
+            ndt_step<PROF>(s, prm);
           }
         }
-        const long long tb = clock64();
+        const long long tb = PROF ? clock64() : 0;
         __syncwarp();
         if (s.new_pose) {
           pose_trig_warp(s, s.x_t, lane);
-          const long long tc = clock64();
+          const long long tc = PROF ? clock64() : 0;
           if (tid == 0) {
             pose_to_T(s.x_t, s.trig, s.T);
             angle_tables(s.trig, s.j_ang, s.h_ang);
-            prof[8] += tc - tb; prof[9] += clock64() - tc;
+            if (PROF) { prof[8] += tc - tb; prof[9] += clock64() - tc; }
           }
         }
-        if (tid == 0) prof[7] += tb - t4;
+        if (PROF && tid == 0) prof[7] += tb - t4;
       }
       __syncthreads();
-      const long long t5 = clock64();
-      prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += t4 - t3; prof[4] += t5 - t4; prof[5] += 1;
+      if (PROF) {
+        const long long t5 = clock64();
+        prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += t4 - t3; prof[4] += t5 - t4; prof[5] += 1;
+      }
       if (s.phase == PH_DONE) break;
     }
-    if (job.prof && rank == 0 && tid == 0) {
+    if (PROF && job.prof && rank == 0 && tid == 0) {
       for (int k = 0; k < 10; ++k) job.prof[k] = prof[k];
       for (int k = 0; k < 6; ++k) job.prof[10 + k] = s.pf[k];
     }

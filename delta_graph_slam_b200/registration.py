@@ -239,6 +239,10 @@ class Registration:
         self._ck(_lib.load().b200reg_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(launches_total=a.value, timed_aligns=b.value, align_kernel_ms=c.value)
 
+    def setProfile(self, on=True):
+        """Developer cycle counters of the align kernels (a separate kernel instantiation; off by default)."""
+        self._ck(_lib.load().b200reg_set_profile(self._h, int(on)))
+
     def profile(self):
         v = np.zeros(16, np.int64)
         self._ck(_lib.load().b200reg_get_profile(self._h, v.ctypes.data))

@@ -250,6 +250,9 @@ int b200reg_get_counters(b200reg_handle* h, long long* launches_total, long long
  * optimiser step split into {state machine, pose trig, transform + angle tables} and the state machine
  * into {totals -> state, interval update, trial value, Newton end, 6x6 solve, Newton begin} */
 int b200reg_get_profile(b200reg_handle* h, long long* out16);
+/* the counters are compiled into a separate instantiation of the align kernels (they cost registers the
+ * production kernel does not have to spare): off by default, single registrations only */
+int b200reg_set_profile(b200reg_handle* h, int on);
 
 /* A/B switch for tests (process-wide): 0 = the voxel key / sort / segmentation pipeline runs as one
  * cooperative kernel when the cloud fits one tile per SM (default), 1 = always the multi-kernel path */

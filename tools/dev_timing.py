@@ -24,6 +24,7 @@ for search in ("DIRECT7", "DIRECT1", "KDTREE"):
     ndt = d.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method=search), out=open(os.devnull, "w"))
     print(search, "set_target", t(lambda: ndt.setInputTarget(v0)))
     ndt.setInputSource(v1)
+    ndt.setProfile(True)
     print(search, "set_source", t(lambda: ndt.setInputSource(v1)))
     print(search, "align(identity)", t(lambda: ndt.align(None)), ndt.getResult()["iterations"], "iters", ndt.getResult()["evaluations"], "evals", ndt.getResult()["hits"], "hits")
     print(search, "profile(cycles)", ndt.profile())

@@ -9,6 +9,7 @@ P0, P1 = O.synth_traj(0), O.synth_traj(1)
 v0 = O.voxelgrid(O.synth_scan(P0, noise_seed=1000), 0.1)["out"]
 v1 = O.voxelgrid(O.synth_scan(P1, noise_seed=1001), 0.1)["out"]
 g = d.select_registration_method(bench.GICP_ODOM_PARAMS, out=bench.DEVNULL)
+g.setProfile(True)
 g.setInputTarget(v0); g.setInputSource(v1)
 for _ in range(3):
     g.setInputSource(v1)
