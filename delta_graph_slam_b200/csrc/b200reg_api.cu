@@ -187,7 +187,7 @@ bool is_pinned_host(const void* p) {
 }
 
 // host cloud (any stride) -> device float4 buffer on the handle's stream
-int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, DevBuf<float4>& dst) {
+int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, DevBuf<float4>& dst, bool defer_pinned = false) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) {
     h->err = "stride_bytes must be a multiple of 4 and at least 12";
@@ -198,7 +198,9 @@ int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_b
   if (stride_bytes == 16 && is_pinned_host(xyzw)) {
     // page-locked caller memory (cudaHostAlloc / cudaHostRegister): DMA straight from it
     B200_CUDA_TRY(cudaMemcpyAsync(dst.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer after the call returns
+    // the caller may reuse its buffer after the call returns — except for keyframe clouds put into the cache
+    // (defer_pinned): those are immutable in the reference and are read by DMA until the next batch call
+    if (!defer_pinned) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200REG_OK;
   }
   B200_CUDA_TRY(h->pin_in.reserve(n));
@@ -1194,7 +1196,7 @@ int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n
   int rc = set_device(h);
   if (rc) return rc;
   CachedCloud& c = h->cache[(long long)id];
-  if ((rc = upload_cloud(h, xyzw, n, stride, c.pts))) return rc;
+  if ((rc = upload_cloud(h, xyzw, n, stride, c.pts, /*defer_pinned=*/true))) return rc;
   c.n = (int)n;
   c.has_ndt = c.has_nn = false;
   return B200REG_OK;
@@ -1230,6 +1232,15 @@ int b200reg_cloud_clear(b200reg_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
+  return B200REG_OK;
+}
+
+int b200reg_cloud_sync(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return B200REG_OK;
 }
 

@@ -185,6 +185,10 @@ class Registration:
         c = _lib.as_cloud(cloud)
         self._ck(_lib.load().b200reg_cloud_put(self._h, int(cloud_id), c.ctypes.data if len(c) else None, len(c), 16))
 
+    def cloudSync(self):
+        """Wait until every cloud put so far has left the caller's (page-locked) memory."""
+        self._ck(_lib.load().b200reg_cloud_sync(self._h))
+
     def cloudDrop(self, cloud_id):
         self._ck(_lib.load().b200reg_cloud_drop(self._h, int(cloud_id)))
 

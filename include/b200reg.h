@@ -211,7 +211,12 @@ typedef struct b200reg_pair {
   int64_t source_id; /* candidate     (setInputSource) */
   float guess[16];   /* column-major initial guess (transform2Dto3D of the 2-D relative pose, :139-143) */
 } b200reg_pair;
+/* b200reg_cloud_put: a PAGE-LOCKED keyframe cloud is read by DMA after the call has returned — keep it
+ * unchanged until the next b200reg_align_batch / b200reg_calc_fitness_batch / b200reg_cloud_sync returns
+ * (keyframe clouds are immutable for the whole run in the reference [REF include/hdl_graph_slam/keyframe.hpp:25-59]);
+ * a pageable cloud is staged inside the call and may be reused at once. */
 int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n, size_t stride_bytes);
+int b200reg_cloud_sync(b200reg_handle* h);
 int b200reg_cloud_put_device(b200reg_handle* h, int64_t id, const float* d_xyzw, size_t n);
 int b200reg_cloud_drop(b200reg_handle* h, int64_t id);
 int b200reg_cloud_clear(b200reg_handle* h);

@@ -13,10 +13,19 @@ python tools/profile_driver.py 8 gicp > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_gicp.csv python tools/profile_driver.py 8 gicp > /dev/null 2>&1
 python tools/profile_batch.py > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_nn\|k_fitness\|k_ndt -c 300 --csv --log-file gpurun_out/launches_batch.csv python tools/profile_batch.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ndt_align -s 3 -c 1 -f -o gpurun_out/prof_align python tools/profile_driver.py 8 > gpurun_out/ncu_full1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_voxel_sort_coop -s 4 -c 1 -f -o gpurun_out/prof_sort python tools/profile_driver.py 8 > gpurun_out/ncu_full2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ndt_align -s 1 -c 1 -f -o gpurun_out/prof_align_batch python tools/profile_batch.py > gpurun_out/ncu_full3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gicp_align -s 2 -c 1 -f -o gpurun_out/prof_gicp_align python tools/profile_driver.py 6 gicp > gpurun_out/ncu_full4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gicp_knn$ -s 2 -c 1 -f -o gpurun_out/prof_gicp_knn python tools/profile_driver.py 6 gicp > gpurun_out/ncu_full5.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_nn_search_batch -s 1 -c 1 -f -o gpurun_out/prof_nn_batch python tools/profile_batch.py > gpurun_out/ncu_full6.log 2>&1
+cap() {  # cap <name> <kernel regex> <skip> <driver...>: one --set full capture, summarised on the box (the reports are too big to bring back)
+  local name=$1 k=$2 skip=$3; shift 3
+  ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c 1 -f -o gpurun_out/prof_$name "$@" > gpurun_out/ncu_full_$name.log 2>&1
+  python tools/ncu_summary.py gpurun_out/prof_$name.ncu-rep > gpurun_out/ncu_full_$name.txt 2>/dev/null
+  ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv --print-source cuda,sass > /tmp/src_$name.csv 2>/dev/null
+  python tools/ncu_lines.py /tmp/src_$name.csv 40 > gpurun_out/ncu_lines_$name.txt 2>/dev/null
+}
+cap k_ndt_align k_ndt_align 3 python tools/profile_driver.py 8
+cap k_voxel_sort_coop k_voxel_sort_coop 4 python tools/profile_driver.py 8
+cap k_ndt_align_batch k_ndt_align 1 python tools/profile_batch.py
+cap k_gicp_align k_gicp_align 2 python tools/profile_driver.py 6 gicp
+cap k_gicp_knn 'k_gicp_knn$' 2 python tools/profile_driver.py 6 gicp
+cap k_nn_search_batch k_nn_search_batch 1 python tools/profile_batch.py
+python tools/ncu_traffic.py gpurun_out/ncu_traffic.json k_ndt_align_single=gpurun_out/prof_k_ndt_align.ncu-rep k_ndt_align_batch_per_registration=gpurun_out/prof_k_ndt_align_batch.ncu-rep/160 k_gicp_align=gpurun_out/prof_k_gicp_align.ncu-rep k_voxel_sort_coop=gpurun_out/prof_k_voxel_sort_coop.ncu-rep > /dev/null 2>&1
+rm -f gpurun_out/prof_k_voxel_sort_coop.ncu-rep gpurun_out/prof_k_gicp_knn.ncu-rep gpurun_out/prof_k_nn_search_batch.ncu-rep gpurun_out/prof_k_gicp_align.ncu-rep gpurun_out/prof_k_ndt_align_batch.ncu-rep
 echo done
