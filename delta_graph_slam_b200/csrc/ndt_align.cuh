@@ -81,6 +81,8 @@ struct NdtShared {
   float h_ang[15][3];
   int need_hessian;
   int phase;
+  int solve_req;       // the state machine stopped in front of the 6x6 solve: warp 0 solves H dp = -g together
+  double neg_g[6], dp[6];
   int new_pose;  // the step asked for an evaluation at a new x_t (T / tables must be rebuilt)
   // optimiser state (identical in every CTA of the group)
   double p[6], x_t[6], dir[6];
@@ -281,8 +283,10 @@ __host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (
 // ---- the optimiser state machine; one lane, after every derivative pass ----------------------
 // Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the next pass
 // must be evaluated at s.x_t (the caller then rebuilds T and the angle tables).
+// resume = false: a derivative pass has just finished.  resume = true: the solve the previous call asked for
+// (s.solve_req) is in s.dp.  The routine runs on one lane; the solve in between runs on the whole warp.
 template <bool PROF>
-static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm) {
+static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, bool resume) {
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
   const double* t = s.tot;
@@ -290,11 +294,17 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
   auto lap = [&](int slot) {
     if (PROF) { const long long now = clock64(); s.pf[slot] += now - tk; tk = now; }
   };
+  bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
+  bool have_dp = false;
+  s.solve_req = 0;
+  if (resume) {
+    go_newton_begin = true;
+    have_dp = true;
+  } else {
   s.n_eval++;
   s.n_pass++;
   s.hits += t[28];
   s.new_pose = 0;
-  bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
   switch (s.phase) {
     case PH_INIT:
     case PH_MT_FIRST:
@@ -319,6 +329,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
       break;
     default:
       return;
+  }
   }
   lap(0);
   if (go_loop_check) {
@@ -374,11 +385,15 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm)
     }
     if (go_newton_begin) {
       go_newton_begin = false;
-      double neg_g[6], dp[6];
-      for (int i = 0; i < 6; ++i) neg_g[i] = -s.g[i];
-      lap(5);
-      solve6(s.H, neg_g, dp);
-      lap(4);
+      if (!have_dp) {  // hand the solve to the warp (warp_solve6 in the caller), come back with resume = true
+        for (int i = 0; i < 6; ++i) s.neg_g[i] = -s.g[i];
+        s.solve_req = 1;
+        lap(5);
+        return;
+      }
+      have_dp = false;
+      double dp[6];
+      for (int i = 0; i < 6; ++i) dp[i] = s.dp[i];
       double nrm = 0;
       for (int i = 0; i < 6; ++i) nrm += dp[i] * dp[i];
       nrm = sqrt(nrm);
@@ -735,6 +750,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         for (int i = 0; i < 6; ++i) s.pf[i] = 0;
         s.score = 0.0;
         s.need_hessian = 1;
+        s.solve_req = 0;
         s.phase = job.eval_only ? PH_EVAL_ONLY : PH_INIT;
       }
       __syncwarp();
@@ -858,8 +874,25 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
             s.phase = PH_DONE;
             s.new_pose = 0;
           } else {
-            ndt_step<PROF>(s, prm);
+            ndt_step<PROF>(s, prm, false);
           }
+        }
+        __syncwarp();
+        while (s.solve_req) {  // warp-uniform: the state machine is waiting for H dp = -g
+          const long long ts_a = PROF ? clock64() : 0;
+          double dpv[6];
+          const bool solved = warp_solve6(s.H, s.neg_g, dpv, lane);
+          if (tid == 0) {
+            if (solved) {
+#pragma unroll
+              for (int i = 0; i < 6; ++i) s.dp[i] = dpv[i];
+            } else {
+              svd_solve6(s.H, s.neg_g, s.dp);  // rank-deficient or NaN input: JacobiSVD's minimum-norm answer (see solve6)
+            }
+            if (PROF) s.pf[4] += clock64() - ts_a;
+            ndt_step<PROF>(s, prm, true);
+          }
+          __syncwarp();
         }
         const long long tb = PROF ? clock64() : 0;
         __syncwarp();

@@ -195,4 +195,70 @@ static __device__ __noinline__ void solve6(const double* A, const double* b, dou
   for (int i = 0; i < 6; ++i) x[i] = xs[i];
 }
 
+// The same elimination by a whole warp: lane i (i < 6) holds row i of [A | b] in registers, the pivot
+// search is a three-step butterfly, the row exchange and the pivot-row broadcast are shuffles.  Every
+// element goes through the same operations in the same order as in solve6 (f = m_ik * inv,
+// m_ij -= f * m_kj; back substitution with ascending j), so the bits are those of the serial routine —
+// which kept its 6x7 tableau in a stack frame (the caller's 128 registers are taken) and spent ~4.5 k
+// cycles per solve on one lane while the rest of the CTA waited.  Returns false when a pivot collapses
+// (the caller then runs svd_solve6 on one lane, as solve6 does).  All 32 lanes must call; x[0..5] is
+// valid in every lane on return.
+__device__ __forceinline__ bool warp_solve6(const double* A, const double* b, double x[6], int lane) {
+  const int row = lane < 6 ? lane : 0;
+  double r[7];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r[j] = A[6 * row + j];
+  r[6] = b[row];
+  double amax = fmax(fmax(fmax(fabs(r[0]), fabs(r[1])), fmax(fabs(r[2]), fabs(r[3]))), fmax(fabs(r[4]), fabs(r[5])));
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));  // lanes 6, 7 hold copies of row 0
+  amax = __shfl_sync(0xffffffffu, amax, 0);
+  bool ok = amax > 0.0 && amax == amax && amax < 1.7e308;
+  double invs[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    // first row at or below k with the largest |m_ik| (solve6: strict > in ascending i)
+    double best = (lane >= k && lane < 6) ? fabs(r[k]) : -1.0;
+    int piv = lane;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    best = __shfl_sync(0xffffffffu, best, 0);
+    piv = __shfl_sync(0xffffffffu, piv, 0);
+    // NaN entries: fabs(NaN) never wins a comparison, as in solve6 (v > best is false) — best stays the
+    // value of the first candidate, and the test below rejects NaN pivots the same way
+    if (!(best > 1e-11 * amax)) ok = false;
+    double pr[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j < k) continue;
+      const double from_piv = __shfl_sync(0xffffffffu, r[j], piv);
+      const double from_k = __shfl_sync(0xffffffffu, r[j], k);
+      pr[j] = from_piv;                    // the pivot row after the exchange
+      if (lane == k) r[j] = from_piv;
+      else if (lane == piv) r[j] = from_k;
+    }
+    const double inv = __drcp_rn(pr[k]);
+    invs[k] = inv;
+    if (lane > k && lane < 6) {
+      const double f = r[k] * inv;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j > k) r[j] -= f * pr[j];
+    }
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double sacc = r[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j > i) sacc -= r[j] * x[j];
+    x[i] = __shfl_sync(0xffffffffu, sacc * invs[i], i);
+  }
+  return ok;
+}
+
 }  // namespace b200
