@@ -283,6 +283,21 @@ __host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (
 // ---- the optimiser state machine; one lane, after every derivative pass ----------------------
 // Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the next pass
 // must be evaluated at s.x_t (the caller then rebuilds T and the angle tables).
+// totals of the pass -> score, gradient, full symmetric Hessian of the optimiser state: 43 copies, one
+// or two per lane of warp 0 instead of a serial loop on the lane that runs the state machine
+__device__ __forceinline__ void ndt_take_totals(NdtShared& s, int lane) {
+  const double* t = s.tot;
+  if (lane == 0) s.score = t[0];
+  if (lane < 6) s.g[lane] = t[1 + lane];
+#pragma unroll
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e - 6 * i;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    s.H[e] = t[hidx(a, b)];
+  }
+  __syncwarp();
+}
+
 // resume = false: a derivative pass has just finished.  resume = true: the solve the previous call asked for
 // (s.solve_req) is in s.dp.  The routine runs on one lane; the solve in between runs on the whole warp.
 template <bool PROF>
@@ -308,10 +323,7 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm,
   switch (s.phase) {
     case PH_INIT:
     case PH_MT_FIRST:
-      s.score = t[0];
-      for (int i = 0; i < 6; ++i) s.g[i] = t[1 + i];
-      for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = t[hidx(i, j)];
+      // score, gradient and Hessian were copied out of the totals by the whole warp (ndt_take_totals)
       if (s.phase == PH_INIT) go_newton_begin = true;
       else go_loop_check = true;
       break;
@@ -321,10 +333,6 @@ static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm,
       // was just evaluated.  Here that Hessian is already in the totals of the last trial pass (same
       // transform, same tables, same arithmetic as a pass of its own), so the extra pass never runs;
       // the Hessian of a trial that is not the last one is simply overwritten by the next.
-      s.score = t[0];
-      for (int i = 0; i < 6; ++i) s.g[i] = t[1 + i];
-      for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) s.H[6 * i + j] = s.H[6 * j + i] = t[hidx(i, j)];
       go_loop_check = true;
       break;
     default:
@@ -873,9 +881,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
             s.hits += s.tot[28];
             s.phase = PH_DONE;
             s.new_pose = 0;
-          } else {
-            ndt_step<PROF>(s, prm, false);
           }
+        }
+        __syncwarp();
+        if (s.phase != PH_EVAL_ONLY && s.phase != PH_DONE) {  // warp-uniform (PH_EVAL_ONLY became PH_DONE just above)
+          ndt_take_totals(s, lane);
+          if (tid == 0) ndt_step<PROF>(s, prm, false);
         }
         __syncwarp();
         while (s.solve_req) {  // warp-uniform: the state machine is waiting for H dp = -g
