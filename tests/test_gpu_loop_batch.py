@@ -178,3 +178,26 @@ def test_loop_detector_batch_equals_reference_serial_loop(eng, oracle, scenario)
         if la is not None:
             assert la.key2.id == lb.key2.id
     assert total_diverged <= 1
+
+
+def test_page_locked_keyframes_are_read_after_the_put_returns(eng, scenario):
+    """b200reg_cloud_put of a page-locked cloud does not wait for the DMA (keyframe clouds are immutable in the
+    reference); the batch call, or b200reg_cloud_sync, is where the caller's memory is released."""
+    import torch
+    base = new_engine(eng, scenario).alignBatch(scenario["pairs"])
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7"), out=io.StringIO())
+    keep = {}
+    for k, v in scenario["clouds"].items():
+        keep[k] = torch.empty((max(len(v), 1), 4), dtype=torch.float32, pin_memory=True)
+        keep[k].numpy()[: len(v)] = v
+        ndt.cloudPut(k, keep[k].numpy()[: len(v)])
+    res = ndt.alignBatch(scenario["pairs"])
+    assert np.array_equal(res.view(np.uint8), base.view(np.uint8))
+    # after cloudSync the page-locked buffers may be scribbled over without changing anything
+    for k, v in scenario["clouds"].items():
+        ndt.cloudPut(k, keep[k].numpy()[: len(v)])
+    ndt.cloudSync()
+    for t in keep.values():
+        t.zero_()
+    res2 = ndt.alignBatch(scenario["pairs"])
+    assert np.array_equal(res2.view(np.uint8), base.view(np.uint8))
