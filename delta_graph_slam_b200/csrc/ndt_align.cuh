@@ -633,6 +633,7 @@ template <int MODE, bool PROF>
 __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __restrict__ jobs, int n_jobs, int ctas_per_group, NdtTargetQueue tq, NdtParams prm, double* partials_all, unsigned int* barriers,
                                                                 unsigned int* queue, const __grid_constant__ NdtJob single) {
   __shared__ NdtShared s;
+  __shared__ GridParams s_gp;
   __shared__ int s_job;
   extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
   const int G = ctas_per_group;
@@ -705,7 +706,13 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
     }
     if (jb >= n_jobs) break;
     const NdtJob& job = jobs ? jobs[jb] : single;  // one registration: the job rides in the kernel parameters
-    const GridParams gp = job.grid.meta->grid;
+    // the lattice of the target (20 words) is read by every thread for every point: it lives in shared
+    // memory, not in 20 registers per thread of a kernel that is already spilling (ncu: the first use of
+    // gp.leaf was the top long-scoreboard stall of the batch configuration — a reload from local / global)
+    __syncthreads();
+    if (tid < (int)(sizeof(GridParams) / 4)) reinterpret_cast<uint32_t*>(&s_gp)[tid] = reinterpret_cast<const uint32_t*>(&job.grid.meta->grid)[tid];
+    __syncthreads();
+    const GridParams& gp = s_gp;
     const int n_src = job.n_src;
     long long prof[PROF ? 10 : 1] = {0};
     const long long ts0 = PROF ? clock64() : 0;
