@@ -107,10 +107,13 @@ __global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restric
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x * blockDim.x >= job.n_src) return;
   __shared__ float T[16];
+  __shared__ GridParams s_gp;  // the target's cell lattice, shared by the CTA instead of 20 registers per thread
   if (threadIdx.x < 16) T[threadIdx.x] = results[job.result].transformation[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + (int)(sizeof(GridParams) / 4))
+    reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(&job.view.meta->grid)[threadIdx.x - 32];
   __syncthreads();
   if (i >= job.n_src) return;
-  const GridParams gp = job.view.meta->grid;
+  const GridParams& gp = s_gp;
   float qx, qy, qz;
   fit_transform(T, __ldg(job.src + i), qx, qy, qz);
   float best = 3.402823466e+38f;
