@@ -209,9 +209,12 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
   __shared__ float s_bd[8][64];
   __shared__ int s_bi[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ GridParams s_gp;  // the cloud's cell lattice, shared by the CTA instead of 20 registers per thread
+  if (threadIdx.x < (int)(sizeof(GridParams) / 4)) reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&g.meta->grid)[threadIdx.x];
+  __syncthreads();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // queries are taken in cell order: neighbouring warps touch neighbouring cells
   if (w >= n) return;
-  const GridParams gp = g.meta->grid;
+  const GridParams& gp = s_gp;
   const float4 qp = __ldg(g.pts + w);
   const int qi = __float_as_int(qp.w);
   const float qx = qp.x, qy = qp.y, qz = qp.z;

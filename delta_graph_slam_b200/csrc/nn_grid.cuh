@@ -406,11 +406,14 @@ __global__ void __launch_bounds__(256) k_nn_search(NnView g, const float4* __res
                                                    float* __restrict__ d2_out, int* __restrict__ idx_out, float4* __restrict__ q_out, int* __restrict__ pending,
                                                    unsigned int* __restrict__ n_pending) {
   __shared__ float T[16];
+  __shared__ GridParams s_gp;  // the target's cell lattice, shared by the CTA instead of 20 registers per thread
   if (threadIdx.x < 16) T[threadIdx.x] = use_T ? T16[threadIdx.x] : ((threadIdx.x % 5 == 0) ? 1.f : 0.f);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + (int)(sizeof(GridParams) / 4))
+    reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(&g.meta->grid)[threadIdx.x - 32];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_src) return;
-  const GridParams gp = g.meta->grid;
+  const GridParams& gp = s_gp;
   const float4 p = __ldg(src + i);
   float qx = p.x, qy = p.y, qz = p.z;
   if (use_T) {
