@@ -18,6 +18,12 @@
 #include "ndt_grid.cuh"
 #include "nn_grid.cuh"
 
+#ifndef B200_FIT_DEPTH
+#define B200_FIT_DEPTH 4
+#endif
+#ifndef B200_FIT_MINB
+#define B200_FIT_MINB 1
+#endif
 namespace b200 {
 
 struct CachedCloud {
@@ -101,7 +107,7 @@ __device__ __forceinline__ void fit_transform(const float* T, const float4 p, fl
 // near phase: blockIdx.y = job, blockIdx.x = 256-point slice of its source.  Transform by the pair's
 // final transformation (float, pcl::transformPoint order) and search rings 0..1; unresolved queries
 // go to `pending` with their best-so-far in d2_out.
-__global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, float max_d2, float* __restrict__ d2_out,
+__global__ void __launch_bounds__(256, B200_FIT_MINB) k_nn_search_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, float max_d2, float* __restrict__ d2_out,
                                                          uint2* __restrict__ pending, unsigned int* __restrict__ n_pending) {
   const FitJob& job = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(256) k_nn_search_batch(const FitJob* __restric
   float best = 3.402823466e+38f;
   int best_idx = kNoIndex;
   int st = kNnDone;
-  if (job.view.n > 0 && gp.any && !gp.overflow) st = nn_query_near(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  if (job.view.n > 0 && gp.any && !gp.overflow) st = nn_query_near<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
   d2_out[job.d2_offset + i] = best_idx != kNoIndex ? best : kNoNeighbour;
   if (st != kNnDone) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i | (st == kNnBail ? kBailFlag : 0u));
 }
