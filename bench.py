@@ -550,7 +550,7 @@ def bench_loop(ctx, steps, warmup, dense=False):
                    "passes_per_registration": float(np.mean(res["passes"])), "reference_evaluations_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
         "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
-        "roofline": {"bound": "hbm", "kernel": f"k_ndt_align<{1 if dense else 7}> ({'one CTA per registration' if len(mine) >= 148 else str(148 // max(len(mine), 1)) + ' CTAs per registration'})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+        "roofline": {"bound": "hbm", "kernel": f"k_ndt_align<{1 if dense else 7}> ({'1, 2 or 4 CTAs per registration, whichever fills the last round of the batch best' if len(mine) >= 148 else str(148 // max(len(mine), 1)) + ' CTAs per registration'})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                      "traffic": None, "traffic_per_registration": load_traffic("k_ndt_align_batch_per_registration"), "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),

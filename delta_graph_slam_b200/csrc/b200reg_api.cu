@@ -1338,7 +1338,19 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
     B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, hj, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
     // few pairs: several SMs cooperate on each; a full batch: one SM per registration, no grid-wide sync at all
     int G = h->num_sm / n_jobs;
-    if (G < 1) G = 1;
+    if (G < 1) {
+      // more pairs than SMs: the batch runs in rounds of num_sm / G registrations, and the last round is
+      // rarely full — 512 pairs on 148 SMs are 3.46 rounds of one-CTA registrations, i.e. 4.  Two or
+      // four CTAs per registration halve / quarter a registration's time and waste less of the last round
+      // (512 pairs: 7 rounds of half-length registrations = 3.5).  A group pays a barrier per pass (~1 %).
+      double best_cost = 0.0;
+      for (int g = 1; g <= 4; ++g) {
+        const int groups = h->num_sm / g;
+        const int rounds = (n_jobs + groups - 1) / groups;
+        const double cost = (double)rounds * (1.0 / g) * (g > 1 ? 1.02 : 1.0);
+        if (g == 1 || cost < best_cost * 0.97) { best_cost = cost; G = g; }
+      }
+    }
     const int n_groups = h->num_sm / G;
     B200_CUDA_TRY(h->partials.reserve((size_t)n_groups * 2 * G * kAccStride));
     if ((rc = ensure_barriers(h, (size_t)(n_groups + 1) * 32))) return rc;
