@@ -37,11 +37,14 @@ constexpr int kKnnMaxRing = 15;  // 7.5 m; the rings from 2 on are walked throug
 // one compare-exchange step of a bitonic network over the lanes: partner = lane ^ j; in an ascending
 // block the lower lane of the pair keeps the smaller entry.  (d, i) pairs are totally ordered.
 __device__ __forceinline__ void bitonic_cmpex(float& d, int& i, int lane, int j, bool up) {
-  const float od = __shfl_xor_sync(0xffffffffu, d, j);
-  const int oi = __shfl_xor_sync(0xffffffffu, i, j);
+  // (d, i) as ONE 64-bit key: squared distances are >= +0, so their float bits order like the values, and
+  // indices are non-negative — the lexicographic (d, then lowest index) order of nn_better is a single
+  // unsigned compare.  The networks were half of the k-NN kernel's instructions with the two-field compare.
+  const unsigned long long me = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
+  const unsigned long long other = __shfl_xor_sync(0xffffffffu, me, j);
   const bool keep_min = ((lane & j) == 0) == up;
-  const bool take = keep_min ? nn_better(od, oi, d, i) : nn_better(d, i, od, oi);
-  if (take) { d = od; i = oi; }
+  const bool take = keep_min ? (other < me) : (me < other);
+  if (take) { d = __uint_as_float((unsigned)(other >> 32)); i = (int)(unsigned)(other & 0xffffffffull); }
 }
 
 // ascending bitonic sort of one (d, i) per lane
