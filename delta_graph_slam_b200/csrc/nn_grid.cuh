@@ -166,13 +166,19 @@ __device__ __forceinline__ uint32_t nn_scan_cell(const NnView& g, const GridPara
   const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
   const uint2 run = nn_lookup(g, key);
   if (DEPTH == 4) {
+    // (d, index) as one 64-bit key: squared distances are >= +0, so their float bits order like the values,
+    // and indices are non-negative — nn_better's "smaller d, then lower index" is an unsigned 64-bit minimum
+    // (a NaN distance has the largest bits and never wins, as it never wins nn_better)
+    unsigned long long bk = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(unsigned)best_idx;
 #pragma unroll 4
     for (uint32_t j = run.x; j < run.y; ++j) {
       const float4 p = __ldg(g.pts + j);
       const float d = l2_simple(q.qx, q.qy, q.qz, p.x, p.y, p.z);
-      const int idx = __float_as_int(p.w);
-      if (nn_better(d, idx, best, best_idx)) { best = d; best_idx = idx; }
+      const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)__float_as_uint(p.w);
+      bk = k < bk ? k : bk;
     }
+    best = __uint_as_float((unsigned)(bk >> 32));
+    best_idx = (int)(unsigned)(bk & 0xffffffffull);
   } else {
     for (uint32_t j = run.x; j < run.y; j += DEPTH) {
       float4 p[DEPTH];
