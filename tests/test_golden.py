@@ -31,6 +31,16 @@ def test_oracle_voxelgrid_golden(oracle):
     assert np.array_equal(r2["out"].view(np.uint32), g["out_min2"].view(np.uint32)) and np.array_equal(r2["count"], g["count_min2"])
 
 
+def test_oracle_prefilter_golden(oracle):
+    g = load("prefilter.npz")
+    gated = oracle.distance_filter(g["pts"], *[float(x) for x in g["near_far"]])
+    assert len(gated) == int(g["n_gated"])
+    ds = oracle.voxelgrid(gated, float(g["leaf"]), is_dense=False)["out"]
+    assert np.array_equal(ds.view(np.uint32), g["ds"].view(np.uint32))
+    kept = oracle.radius_outlier_removal(ds, float(g["radius_min"][0]), int(g["radius_min"][1]))
+    assert np.array_equal(kept.view(np.uint32), g["kept"].view(np.uint32))
+
+
 @pytest.mark.parametrize("name,code", [("direct7", 2), ("direct1", 3), ("kdtree", 0)])
 def test_oracle_ndt_golden(oracle, name, code):
     g = load("ndt.npz")
@@ -78,6 +88,19 @@ def test_engine_voxelgrid_golden():
     vg.setMinimumPointsNumberPerVoxel(2)
     vg.setInputCloud(g["pts"], is_dense=False)
     assert np.array_equal(vg.filter().view(np.uint32), g["out_min2"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_engine_prefilter_golden():
+    import delta_graph_slam_b200 as eng
+    g = load("prefilter.npz")
+    pre = eng.Prefilter(dict(downsample_method="VOXELGRID", downsample_resolution=float(g["leaf"]), use_distance_filter=True, distance_near_thresh=float(g["near_far"][0]),
+                             distance_far_thresh=float(g["near_far"][1]), outlier_removal_method="RADIUS", radius_radius=float(g["radius_min"][0]),
+                             radius_min_neighbors=int(g["radius_min"][1])), out=open(os.devnull, "w"))
+    ds = pre.downsample(g["pts"])
+    assert np.array_equal(np.asarray(ds).view(np.uint32), g["ds"].view(np.uint32))
+    kept = pre.outlier_removal(ds)
+    assert np.array_equal(np.asarray(kept).view(np.uint32), g["kept"].view(np.uint32))
 
 
 @pytest.mark.gpu

@@ -31,6 +31,23 @@ def voxelgrid_case():
                         min_b=r["min_b"], div_b=r["div_b"], out_min2=r2["out"], count_min2=r2["count"])
 
 
+def prefilter_case():
+    """distance_filter -> VoxelGrid -> RadiusOutlierRemoval with the reference launch file's parameters
+    [REF launch/delta_graph_slam.launch:31-42] on a quarter of a synthetic scan plus stray / non-finite points."""
+    rng = np.random.default_rng(77)
+    raw = O.synth_scan(O.synth_traj(4), noise_seed=1004)[::4].copy()
+    stray = np.ones((60, 4), np.float32)
+    stray[:, :3] = rng.uniform(-160, 160, (60, 3)).astype(np.float32)
+    bad = np.ones((3, 4), np.float32)
+    bad[0, 0], bad[1, 1], bad[2, 2] = np.nan, np.inf, -np.inf
+    pts = np.concatenate([raw[:500], stray[:30], bad, raw[500:], stray[30:]]).astype(np.float32)
+    gated = O.distance_filter(pts, 0.1, 100.0)
+    ds = O.voxelgrid(gated, 0.1, is_dense=False)["out"]
+    kept = O.radius_outlier_removal(ds, 0.5, 2)
+    np.savez_compressed(os.path.join(OUT, "prefilter.npz"), pts=pts, near_far=np.array([0.1, 100.0]), leaf=np.float32(0.1), radius_min=np.array([0.5, 2.0]),
+                        n_gated=np.int64(len(gated)), ds=ds, kept=kept)
+
+
 def clouds():
     P0, P1 = O.synth_traj(0), O.synth_traj(1)
     s0 = O.synth_scan(P0, noise_seed=1000)[::4]
@@ -82,6 +99,7 @@ def gicp_case(tgt, src):
 def main():
     os.makedirs(OUT, exist_ok=True)
     voxelgrid_case()
+    prefilter_case()
     tgt, src, gt = clouds()
     ndt_case(tgt, src)
     gicp_case(tgt, src)
