@@ -12,7 +12,7 @@ from . import loop_batch
 from .information_matrix import InformationMatrixCalculator
 from .loop_detector import KeyFrame, Loop, LoopDetector, transform2Dto3D
 from .odometry import FrontEnd, Prefilter, ScanMatchingOdometry
-from .registration import DBL_MAX, DeviceCloud, FastGICP, NormalDistributionsTransform, RadiusOutlierRemoval, Registration, VoxelGrid, select_registration_method
+from .registration import DBL_MAX, DeviceCloud, FastGICP, NormalDistributionsTransform, RadiusOutlierRemoval, Registration, StatisticalOutlierRemoval, VoxelGrid, select_registration_method
 
-__all__ = ["InformationMatrixCalculator", "KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "RadiusOutlierRemoval", "Registration", "VoxelGrid",
+__all__ = ["InformationMatrixCalculator", "KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "RadiusOutlierRemoval", "Registration", "StatisticalOutlierRemoval", "VoxelGrid",
            "select_registration_method"]

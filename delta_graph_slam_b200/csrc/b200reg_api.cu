@@ -19,6 +19,7 @@
 #include "loop_batch.cuh"
 #include "ndt_align.cuh"
 #include "nn_grid.cuh"
+#include "sor.cuh"
 #include "voxel_coop.cuh"
 #include "voxelgrid.cuh"
 
@@ -64,6 +65,10 @@ struct b200reg_handle {
   DevBuf<uint32_t> ror_block_count;
   DevBuf<RorCounts> ror_counts;
   DevBuf<unsigned int> ror_done;
+  DevBuf<float> sor_dist;       // pcl::StatisticalOutlierRemoval: mean neighbour distance per point
+  DevBuf<SorStats> sor_stats;
+  DevBuf<int> sor_pending;
+  DevBuf<unsigned int> sor_n_pending;
   unsigned int ror_seq = 0;
   struct RorPending {
     bool active = false;
@@ -290,7 +295,8 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
-  B200_ATTR(prefer_shared(k_gicp_knn)); B200_ATTR(prefer_shared(k_gicp_knn_brute)); B200_ATTR(prefer_shared(k_gicp_regularize));
+  B200_ATTR(prefer_shared(k_gicp_knn<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn<kKnnMeanDistance>));
+  B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnMeanDistance>)); B200_ATTR(prefer_shared(k_sor_threshold)); B200_ATTR(prefer_shared(k_sor_flags)); B200_ATTR(prefer_shared(k_gicp_regularize));
   // k_gicp_align needs 17.5 KB of shared memory and keeps its 29 double accumulators + 3x3 temporaries in a
   // 1.4 KB per-thread stack frame (128-register cap at 512 threads): it wants the L1, not the carve-out
   B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
@@ -460,8 +466,8 @@ cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const f
   if ((e = cudaMemsetAsync(h->gicp_n_pending.p, 0, sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
   const int blocks = (n + 7) / 8;  // one warp per query, 8 warps per CTA
   launch_counter() += 3;
-  k_gicp_knn<<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p);
-  k_gicp_knn_brute<<<kNumSM * 4, 256, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p);
+  k_gicp_knn<kKnnCovariance><<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
+  k_gicp_knn_brute<kKnnCovariance><<<kNumSM * 4, 256, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
   k_gicp_regularize<<<(n + 127) / 128, 128, 0, h->stream>>>(n, reg, covs);
   return cudaGetLastError();
 }
@@ -617,7 +623,7 @@ int b200reg_destroy(b200reg_handle* h) {
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
   h->nn.release(); h->fit_partials.release();
-  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release();
+  h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release(); h->sor_dist.release(); h->sor_stats.release(); h->sor_pending.release(); h->sor_n_pending.release();
   h->gicp_corr.release(); h->gicp_pending.release(); h->gicp_n_pending.release(); h->gicp_jobs.release();
   for (auto& kv : h->cache) kv.second.release();
   h->cache.clear();
@@ -1056,8 +1062,20 @@ int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, 
 }
 
 // ---- RadiusOutlierRemoval ----------------------------------------------------------------------
-static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, double radius, int min_neighbors, float4* d_out, float4* host_out, size_t host_cap) {
+// which outlier filter a call runs: pcl::RadiusOutlierRemoval or pcl::StatisticalOutlierRemoval
+struct OutlierSpec {
+  bool statistical = false;
+  double radius = 0.0;
+  int min_neighbors = 0;
+  int mean_k = 0;
+  double stddev_mul = 0.0;
+  bool valid() const { return statistical ? (mean_k >= 1 && mean_k <= 31 && stddev_mul == stddev_mul) : (radius > 0 && min_neighbors >= 0); }
+};
+
+static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const OutlierSpec& spec, float4* d_out, float4* host_out, size_t host_cap) {
   auto set_error = [&](const std::string& s) { h->err = s; };
+  const double radius = spec.radius;
+  const int min_neighbors = spec.min_neighbors;
   B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));
@@ -1073,29 +1091,64 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, double radiu
   RorCounts* hc = const_cast<RorCounts*>(&h->mail->ror);
   unsigned int* hf = const_cast<unsigned int*>(&h->mail->ror_seq);
   const unsigned int seq = ++h->ror_seq;
-  launch_counter() += 2;
-  k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
+  if (spec.statistical) {
+    // the k-NN kernels write one float per finite point; everything else stays at the "not counted" mark (< 0)
+    B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
+    B200_CUDA_TRY(h->sor_stats.reserve(1));
+    B200_CUDA_TRY(h->sor_pending.reserve(n ? n : 1));
+    B200_CUDA_TRY(h->sor_n_pending.reserve(1));
+    B200_CUDA_TRY(cudaMemsetAsync(h->sor_dist.p, 0xBF, (n ? n : 1) * sizeof(float), h->stream));
+    B200_CUDA_TRY(cudaMemsetAsync(h->sor_n_pending.p, 0, sizeof(unsigned int), h->stream));
+    launch_counter() += 5;
+    if (n) {
+      k_gicp_knn<kKnnMeanDistance><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+      k_gicp_knn_brute<kKnnMeanDistance><<<kNumSM * 4, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+    }
+    k_sor_threshold<<<1, 1024, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.stddev_mul, h->sor_stats.p);
+    k_sor_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, h->sor_stats.p, h->ror_keep.p, h->ror_block_count.p);
+  } else {
+    launch_counter() += 2;
+    k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
+  }
   k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
                                                h->ror_counts.p, hc, hf, seq, h->ror_done.p);
   B200_CUDA_TRY(cudaGetLastError());
   return B200REG_OK;
 }
 
-int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out) {
-  if (!h || !(radius > 0) || min_neighbors < 0 || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
+static int outlier_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const OutlierSpec& spec, float* d_out) {
+  if (!h || !spec.valid() || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
   if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
-  if ((rc = ror_run(h, (const float4*)d_xyzw, n, radius, min_neighbors, (float4*)d_out, nullptr, 0))) return rc;
+  if ((rc = ror_run(h, (const float4*)d_xyzw, n, spec, (float4*)d_out, nullptr, 0))) return rc;
   h->ror_pending = b200reg_handle::RorPending();
   h->ror_pending.active = true;
   h->ror_pending.device = true;
   return B200REG_OK;
 }
 
-int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap) {
+static OutlierSpec radius_spec(double radius, int min_neighbors) {
+  OutlierSpec s;
+  s.radius = radius; s.min_neighbors = min_neighbors;
+  return s;
+}
+static OutlierSpec statistical_spec(int mean_k, double stddev_mul) {
+  OutlierSpec s;
+  s.statistical = true; s.mean_k = mean_k; s.stddev_mul = stddev_mul;
+  return s;
+}
+int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out) {
+  return outlier_device_begin(h, d_xyzw, n, radius_spec(radius, min_neighbors), d_out);
+}
+int b200reg_statistical_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out) {
+  if (h && (mean_k < 1 || mean_k > 31)) { h->err = "statistical_mean_k must lie in 1..31 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
+  return outlier_device_begin(h, d_xyzw, n, statistical_spec(mean_k, stddev_mul), d_out);
+}
+
+static int outlier_host_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const OutlierSpec& spec, float* out, size_t cap) {
   auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !(radius > 0) || min_neighbors < 0 || (n && !xyzw)) return B200REG_E_INVALID;
+  if (!h || !spec.valid() || (n && !xyzw)) return B200REG_E_INVALID;
   if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
   if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
   int rc = set_device(h);
@@ -1116,13 +1169,21 @@ int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, s
     }
   }
   const bool zero_copy = out && cap && is_pinned_host(out);
-  if ((rc = ror_run(h, h->ror_in.p, n, radius, min_neighbors, h->ror_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
+  if ((rc = ror_run(h, h->ror_in.p, n, spec, h->ror_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
   h->ror_pending = b200reg_handle::RorPending();
   h->ror_pending.active = true;
   h->ror_pending.host_out = out;
   h->ror_pending.cap = cap;
   h->ror_pending.zero_copy = zero_copy;
   return B200REG_OK;
+}
+
+int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap) {
+  return outlier_host_begin(h, xyzw, n, stride, radius_spec(radius, min_neighbors), out, cap);
+}
+int b200reg_statistical_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, int mean_k, double stddev_mul, float* out, size_t cap) {
+  if (h && (mean_k < 1 || mean_k > 31)) { h->err = "statistical_mean_k must lie in 1..31 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
+  return outlier_host_begin(h, xyzw, n, stride, statistical_spec(mean_k, stddev_mul), out, cap);
 }
 
 int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out) {
@@ -1162,6 +1223,47 @@ int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw
   int rc = b200reg_radius_outlier_removal_device_begin(h, d_xyzw, n, radius, min_neighbors, d_out);
   if (rc) return rc;
   return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+int b200reg_statistical_outlier_removal_end(b200reg_handle* h, size_t* n_out) { return b200reg_radius_outlier_removal_end(h, n_out); }
+
+int b200reg_statistical_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, int mean_k, double stddev_mul, float* out, size_t cap, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_statistical_outlier_removal_begin(h, xyzw, n, stride, mean_k, stddev_mul, out, cap);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+int b200reg_statistical_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_statistical_outlier_removal_device_begin(h, d_xyzw, n, mean_k, stddev_mul, d_out);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+// mean / stddev / cut of the last statistical call (after its _end), its count of points with a full
+// neighbour list and whether the index-order summation had to run; dist (optional, n floats): the per-point
+// mean neighbour distances, 0 for the points upstream leaves uncounted
+int b200reg_statistical_last_stats(b200reg_handle* h, double stats3[3], unsigned long long* valid, int* exact_pass, float* dist, size_t n) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  if (!h->sor_stats.p) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  SorStats st;
+  B200_CUDA_TRY(cudaMemcpyAsync(&st, h->sor_stats.p, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  if (dist && n) {
+    if (n > h->sor_dist.cap) return B200REG_E_INVALID;
+    B200_CUDA_TRY(cudaMemcpyAsync(dist, h->sor_dist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (dist) for (size_t i = 0; i < n; ++i) if (dist[i] < 0.f) dist[i] = 0.f;
+  if (stats3) { stats3[0] = st.mean; stats3[1] = st.stddev; stats3[2] = st.threshold; }
+  if (valid) *valid = st.valid;
+  if (exact_pass) *exact_pass = (int)st.exact_pass;
+  return B200REG_OK;
 }
 
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_vox, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow) {

@@ -204,11 +204,28 @@ __device__ __forceinline__ double knn_raw_covariance(const float4* __restrict__ 
   return mine;
 }
 
+// pcl::StatisticalOutlierRemoval's per-point figure [REF apps/prefiltering_nodelet.cpp:77-87]: the list holds the
+// k = mean_k + 1 nearest of the cloud itself (entry 0 is the point, or a duplicate of it, at distance 0);
+// distance = float( (sqrtf(d2_1) + ... + sqrtf(d2_mean_k)) [double, nearest first] / mean_k ).  A list that
+// never filled (fewer than k finite points in the cloud) leaves the point uncounted: -1.
+__device__ __forceinline__ float knn_mean_distance(int k, int lane, float td, int ti) {
+  const bool full = __shfl_sync(0xffffffffu, ti, k - 1) != kNoIndex;
+  const float s = __fsqrt_rn(lane < k ? td : 0.f);
+  double sum = 0.0;
+  for (int j = 1; j < k; ++j) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, s, j));
+  return full ? (float)__ddiv_rn(sum, (double)(k - 1)) : -1.0f;
+}
+
+// The two k-NN kernels serve two callers; kKnnCovariance is FAST_GICP's, kKnnMeanDistance the statistical
+// outlier filter's (same search, `n` taken from the grid's own count of finite points, a float per point out).
+constexpr int kKnnCovariance = 0, kKnnMeanDistance = 1;
+
 // calculate_covariances, step 1: exact k nearest neighbours + raw covariance, one warp per point.
 // covs[i] = {xx, xy, xz, yy, yz, zz} (not yet regularised).  A point whose k-th neighbour is not settled
 // within kKnnMaxRing rings (an isolated return) goes to `pending` for the block-per-query scan.
+template <int TAIL>
 __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __restrict__ pts, int n, int k, double* __restrict__ covs, int* __restrict__ pending,
-                                                  unsigned int* __restrict__ n_pending) {
+                                                  unsigned int* __restrict__ n_pending, float* __restrict__ mean_dist) {
   __shared__ float s_bd[8][64];
   __shared__ int s_bi[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,6 +233,7 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
   if (threadIdx.x < (int)(sizeof(GridParams) / 4)) reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&g.meta->grid)[threadIdx.x];
   __syncthreads();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // queries are taken in cell order: neighbouring warps touch neighbouring cells
+  if (TAIL == kKnnMeanDistance) n = min(n, (int)g.meta->n_valid);  // non-finite points never entered the grid
   if (w >= n) return;
   const GridParams& gp = s_gp;
   const float4 qp = __ldg(g.pts + w);
@@ -303,14 +321,20 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
       return;
     }
   }
+  if (TAIL == kKnnMeanDistance) {
+    const float d = knn_mean_distance(k, lane, L.td, L.ti);
+    if (lane == 0) mean_dist[qi] = d;
+    return;
+  }
   const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);
   if (lane < 6) covs[(size_t)qi * 6 + lane] = c;
 }
 
 // step 1b: one CTA per isolated point: every warp scans its own eighth of the cloud with the same
 // filtered list, the eight lists are merged by warp 0
+template <int TAIL>
 __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* __restrict__ pts, int k, double* __restrict__ covs, const int* __restrict__ pending,
-                                                        const unsigned int* __restrict__ n_pending) {
+                                                        const unsigned int* __restrict__ n_pending, float* __restrict__ mean_dist) {
   __shared__ float s_bd[8][64];
   __shared__ int s_bi[8][64];
   __shared__ float s_ld[8][32];
@@ -318,13 +342,14 @@ __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int np = (int)*n_pending;
   const int km1 = k - 1;
-  const uint32_t chunk = (((uint32_t)g.n + 7u) / 8u + 31u) & ~31u;
+  const uint32_t gn = TAIL == kKnnMeanDistance ? min((uint32_t)g.n, g.meta->n_valid) : (uint32_t)g.n;
+  const uint32_t chunk = ((gn + 7u) / 8u + 31u) & ~31u;
   for (int e = blockIdx.x; e < np; e += gridDim.x) {
     const int w = pending[e];
     const float4 qp = __ldg(g.pts + w);
     KnnList L;
     knn_init(L, s_bd[warp], s_bi[warp]);
-    const uint32_t s0 = min((uint32_t)g.n, chunk * (uint32_t)warp), s1 = min((uint32_t)g.n, s0 + chunk);
+    const uint32_t s0 = min(gn, chunk * (uint32_t)warp), s1 = min(gn, s0 + chunk);
     knn_offer_range(g, s0, s1, qp.x, qp.y, qp.z, km1, lane, L);
     knn_flush(L, km1, lane);
     __syncthreads();  // the previous query's lists have been consumed
@@ -333,6 +358,11 @@ __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* 
     __syncthreads();
     if (warp == 0) {
       for (int o = 1; o < 8; ++o) knn_merge32(L.td, L.ti, s_ld[o][lane], s_li[o][lane], lane);
+      if (TAIL == kKnnMeanDistance) {
+        const float d = knn_mean_distance(k, lane, L.td, L.ti);
+        if (lane == 0) mean_dist[__float_as_int(qp.w)] = d;
+        continue;
+      }
       const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);
       if (lane < 6) covs[(size_t)__float_as_int(qp.w) * 6 + lane] = c;
     }

@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-from .registration import DeviceCloud, RadiusOutlierRemoval, VoxelGrid, select_registration_method
+from .registration import DeviceCloud, RadiusOutlierRemoval, StatisticalOutlierRemoval, VoxelGrid, select_registration_method
 
 
 def quaternion_w(R):
@@ -34,8 +34,7 @@ class Prefilter:
     """PrefilteringNodelet's 3-D chain [REF apps/prefiltering_nodelet.cpp:150-153]: distance_filter (:275-291)
     -> downsample (:249-260, filter chosen :55-75) -> outlier_removal (:262-273, chosen :77-98), with the
     reference's parameter names and defaults.  The distance filter is fused into the VoxelGrid call;
-    outlier_removal_method RADIUS runs on the engine, STATISTICAL stays on the reference's
-    pcl::StatisticalOutlierRemoval (NotImplementedError here).  NOTE the mirror's own default for
+    outlier_removal_method RADIUS and STATISTICAL both run on the engine.  NOTE the mirror's own default for
     outlier_removal_method is NONE and for use_distance_filter False, so that a Prefilter built from
     just the down-sampling parameters is the plain VoxelGrid the earlier tests and bench legs use; pass
     the reference's values (launch/delta_graph_slam.launch:31-42) to get its chain."""
@@ -44,8 +43,6 @@ class Prefilter:
         p = dict(params or {})
         method = p.get("downsample_method", "VOXELGRID")
         res = p.get("downsample_resolution", 0.1)
-        if p.get("outlier_removal_method", "NONE") == "STATISTICAL":
-            raise NotImplementedError("outlier_removal_method=STATISTICAL stays on the reference's pcl::StatisticalOutlierRemoval; b200reg runs RADIUS")
         self.filter = None
         if method == "VOXELGRID":
             print(f"downsample: VOXELGRID {res:g}", file=out)
@@ -60,7 +57,14 @@ class Prefilter:
             print("downsample: NONE", file=out)
         orm = p.get("outlier_removal_method", "NONE")
         self.outlier_removal_filter = None
-        if orm == "RADIUS":
+        if orm == "STATISTICAL":
+            mean_k = p.get("statistical_mean_k", 20)
+            stddev_mul_thresh = p.get("statistical_stddev", 1.0)
+            print(f"outlier_removal: STATISTICAL {mean_k} - {stddev_mul_thresh:g}", file=out)
+            self.outlier_removal_filter = StatisticalOutlierRemoval(device=device, registration=self.filter._reg if self.filter is not None else None)
+            self.outlier_removal_filter.setMeanK(mean_k)
+            self.outlier_removal_filter.setStddevMulThresh(stddev_mul_thresh)
+        elif orm == "RADIUS":
             radius = p.get("radius_radius", 0.8)
             min_neighbors = p.get("radius_min_neighbors", 2)
             print(f"outlier_removal: RADIUS {radius:g} - {min_neighbors}", file=out)

@@ -351,6 +351,42 @@ class Registration:
         res = self.radius_outlier_removal_end()
         return res.copy() if own else res
 
+    def statistical_outlier_removal_begin(self, cloud, mean_k, stddev_mul, out):
+        """pcl::StatisticalOutlierRemoval, first half (enqueue).  `cloud` / `out` both host arrays or both DeviceClouds."""
+        if isinstance(cloud, DeviceCloud):
+            if out.n < cloud.n:
+                raise ValueError("output buffer smaller than the input cloud")
+            self._ck(_lib.load().b200reg_statistical_outlier_removal_device_begin(self._h, cloud.ptr, cloud.n, int(mean_k), float(stddev_mul), out.ptr))
+            self._ror_pending = (cloud, out)
+            return
+        c = _lib.as_cloud(cloud)
+        if out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
+        self._ck(_lib.load().b200reg_statistical_outlier_removal_begin(self._h, c.ctypes.data if len(c) else None, len(c), 16, int(mean_k), float(stddev_mul), out.ctypes.data, len(out)))
+        self._ror_pending = (c, out)
+
+    def statistical_outlier_removal_end(self):
+        return self.radius_outlier_removal_end()  # one in-flight slot and one _end for both outlier filters
+
+    def statistical_outlier_removal(self, cloud, mean_k, stddev_mul, out=None):
+        own = out is None
+        if own:
+            if isinstance(cloud, DeviceCloud):
+                raise ValueError("a device cloud needs a device output buffer")
+            out = np.empty((max(len(cloud), 1), 4), np.float32)
+        self.statistical_outlier_removal_begin(cloud, mean_k, stddev_mul, out)
+        res = self.statistical_outlier_removal_end()
+        return res.copy() if own else res
+
+    def statistical_last_stats(self, n_points=0):
+        """{mean, stddev, threshold, valid, exact_pass[, distances]} of the last statistical call (b200reg_statistical_last_stats)."""
+        st = np.zeros(3, np.float64)
+        valid = C.c_ulonglong()
+        exact = C.c_int()
+        dist = np.zeros(max(n_points, 1), np.float32)
+        self._ck(_lib.load().b200reg_statistical_last_stats(self._h, st.ctypes.data, C.addressof(valid), C.addressof(exact), dist.ctypes.data if n_points else None, n_points))
+        return dict(mean=st[0], stddev=st[1], threshold=st[2], valid=valid.value, exact_pass=bool(exact.value), distances=dist[:n_points])
+
     def setSmBudget(self, n_sm):
         """At most n_sm CTAs (one per SM) for this handle's persistent kernels (b200reg_set_sm_budget)."""
         self._ck(_lib.load().b200reg_set_sm_budget(self._h, int(n_sm)))
@@ -492,6 +528,38 @@ class RadiusOutlierRemoval:
 
     def filter_end(self):
         return self._reg.radius_outlier_removal_end()
+
+
+class StatisticalOutlierRemoval:
+    """pcl::StatisticalOutlierRemoval<PointXYZ> as the prefiltering nodelet sets it up (its default outlier filter)
+    [REF apps/prefiltering_nodelet.cpp:77-87,262-273]: setMeanK + setStddevMulThresh + filter."""
+
+    def __init__(self, device=0, registration=None):
+        self._reg = registration if registration is not None else Registration(device=device)
+        self.mean_k = 1          # pcl's own defaults; the nodelet sets 20 / 1.0
+        self.stddev_mul = 0.0
+        self._input = None
+
+    def setMeanK(self, k):
+        self.mean_k = int(k)
+
+    def setStddevMulThresh(self, m):
+        self.stddev_mul = float(m)
+
+    def setInputCloud(self, cloud):
+        self._input = cloud
+
+    def filter(self, out=None):
+        return self._reg.statistical_outlier_removal(self._input, self.mean_k, self.stddev_mul, out=out)
+
+    def filter_begin(self, out):
+        self._reg.statistical_outlier_removal_begin(self._input, self.mean_k, self.stddev_mul, out)
+
+    def filter_end(self):
+        return self._reg.statistical_outlier_removal_end()
+
+    def last_stats(self, n_points=0):
+        return self._reg.statistical_last_stats(n_points)
 
 
 def select_registration_method(params=None, device=0, out=sys.stdout):

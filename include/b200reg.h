@@ -186,13 +186,29 @@ int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, 
  * than min_neighbors points of the cloud (itself included) lie strictly inside `radius`; order kept.
  * Same calling conventions as the VoxelGrid filter: synchronous, device-resident, and begin / end halves
  * (one call in flight per handle, independent of a VoxelGrid call in flight on the same handle).
- * STATISTICAL outlier removal stays on the reference's pcl::StatisticalOutlierRemoval. */
+ * Either outlier filter (this one or the statistical one below) shares the one in-flight slot. */
 int b200reg_radius_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double radius, int min_neighbors, float* out_xyzw, size_t out_capacity,
                                    size_t* n_out);
 int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out_xyzw, size_t* n_out);
 int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double radius, int min_neighbors, float* out_xyzw, size_t out_capacity);
 int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out_xyzw);
 int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out);
+/* pcl::StatisticalOutlierRemoval (outlier_removal_method STATISTICAL, the nodelet's DEFAULT) [REF :77-87,262-273]:
+ * per point the mean distance to its mean_k nearest neighbours (statistical_mean_k, default 20; 1..31 here),
+ * over the cloud the mean and the sample standard deviation of those figures, and a point is dropped when
+ * its figure exceeds mean + stddev_mul * stddev (statistical_stddev, default 1.0); order kept.  Non-finite
+ * points and clouds of fewer than mean_k + 1 finite points behave as upstream (figure 0, not counted, kept).
+ * Bit-exact against the CPU filter including its index-order double sums (csrc/sor.cuh).  Same calling
+ * conventions as the radius filter; _end is the same call as b200reg_radius_outlier_removal_end. */
+int b200reg_statistical_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, float* out_xyzw, size_t out_capacity,
+                                        size_t* n_out);
+int b200reg_statistical_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out_xyzw, size_t* n_out);
+int b200reg_statistical_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, float* out_xyzw, size_t out_capacity);
+int b200reg_statistical_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out_xyzw);
+int b200reg_statistical_outlier_removal_end(b200reg_handle* h, size_t* n_out);
+/* introspection of the last statistical call, after its _end (parity tests): {mean, stddev, cut}, the number of
+ * counted points, whether the index-order summation pass ran, and (dist != NULL) the n per-point figures. */
+int b200reg_statistical_last_stats(b200reg_handle* h, double stats3[3], unsigned long long* valid, int* exact_pass, float* dist, size_t n);
 /* introspection of the last filter call (parity tests): per output voxel linear index and point
  * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);

@@ -244,4 +244,43 @@ class RadiusOutlierRemoval : public pcl::Filter<pcl::PointXYZ> {
   int min_neighbors_ = 1;
 };
 
+// Replaces pcl::StatisticalOutlierRemoval<pcl::PointXYZ> behind pcl::Filter::Ptr (outlier_removal_method STATISTICAL,
+// the nodelet's default) [REF apps/prefiltering_nodelet.cpp:77-87,262-273]
+class StatisticalOutlierRemoval : public pcl::Filter<pcl::PointXYZ> {
+ public:
+  using PointCloud = pcl::PointCloud<pcl::PointXYZ>;
+  explicit StatisticalOutlierRemoval(int device = 0) : h_(detail::create(B200REG_METHOD_NONE, device)) { this->filter_name_ = "b200reg::StatisticalOutlierRemoval"; }
+  ~StatisticalOutlierRemoval() override {
+    if (h_) b200reg_destroy(h_);
+  }
+  void setMeanK(int k) { mean_k_ = k; }
+  int getMeanK() const { return mean_k_; }
+  void setStddevMulThresh(double m) { std_mul_ = m; }
+  double getStddevMulThresh() const { return std_mul_; }
+  b200reg_handle* handle() { return h_; }
+
+ protected:
+  void applyFilter(PointCloud& output) override {
+    const PointCloud& in = *this->input_;
+    output.header = in.header;
+    output.sensor_origin_ = in.sensor_origin_;
+    output.sensor_orientation_ = in.sensor_orientation_;
+    output.points.resize(in.points.size());
+    size_t n_out = 0;
+    int rc = b200reg_statistical_outlier_removal(h_, detail::xyz(in), in.points.size(), sizeof(pcl::PointXYZ), mean_k_, std_mul_,
+                                                 output.points.empty() ? nullptr : reinterpret_cast<float*>(output.points.data()), output.points.size(), &n_out);
+    if (rc != B200REG_OK) {
+      PCL_ERROR("[b200reg::StatisticalOutlierRemoval] %s\n", b200reg_last_error(h_));
+      n_out = 0;
+    }
+    output.points.resize(n_out);
+    output.width = static_cast<uint32_t>(n_out);
+    output.height = 1;
+    output.is_dense = in.is_dense;  // non-finite input points are kept, as upstream
+  }
+  b200reg_handle* h_ = nullptr;
+  int mean_k_ = 1;       // pcl's defaults; the nodelet sets 20 / 1.0
+  double std_mul_ = 0.0;
+};
+
 }  // namespace b200reg

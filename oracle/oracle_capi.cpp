@@ -195,6 +195,60 @@ long long orc_radius_outlier_removal(const float* in, long long n, double radius
   return m;
 }
 
+// pcl::StatisticalOutlierRemoval<PointXYZ>::applyFilterIndices as configured at
+// [REF apps/prefiltering_nodelet.cpp:77-87] (mean_k 20, stddev multiplier 1.0, keep inliers):
+//   per point: k = mean_k + 1 nearest neighbours on a tree of the finite points (the first one is the
+//   point itself), distance_i = float( sum_{j=1..mean_k} sqrtf(d2_j) [double sum] / mean_k );
+//   a non-finite point, or one whose search returns fewer than k, keeps distance 0 and is not counted;
+//   sum / sq_sum (float product, double sums, INDEX order), mean = sum / valid,
+//   variance = (sq_sum - sum * sum / valid) / (valid - 1), threshold = mean + mul * sqrt(variance);
+//   a point is removed when distance > threshold (so the uncounted points, at 0, stay).
+// stats3 (optional) receives {mean, stddev, threshold}; dist (optional) the per-point distances.
+long long orc_statistical_outlier_removal(const float* in, long long n, int mean_k, double stddev_mul, float* out, double* stats3, float* dist) {
+  std::vector<float> finite;
+  finite.reserve((size_t)n * 4);
+  for (long long i = 0; i < n; ++i)
+    if (std::isfinite(in[4 * i]) && std::isfinite(in[4 * i + 1]) && std::isfinite(in[4 * i + 2])) finite.insert(finite.end(), in + 4 * i, in + 4 * i + 4);
+  KdTree t;
+  t.build(finite.data(), finite.size() / 4);
+  const int k = mean_k + 1;
+  std::vector<float> distances((size_t)(n > 0 ? n : 1), 0.0f);
+  std::vector<unsigned char> valid((size_t)(n > 0 ? n : 1), 0);
+#pragma omp parallel for schedule(guided, 64)
+  for (long long i = 0; i < n; ++i) {
+    const float* q = in + 4 * i;
+    if (!std::isfinite(q[0]) || !std::isfinite(q[1]) || !std::isfinite(q[2])) continue;
+    std::vector<int> idx((size_t)k);
+    std::vector<float> d2((size_t)k);
+    if (t.knn(q, k, idx.data(), d2.data()) != k) continue;
+    double dist_sum = 0.0;
+    for (int j = 1; j < k; ++j) dist_sum += std::sqrt(d2[(size_t)j]);  // float sqrt, double sum
+    distances[(size_t)i] = static_cast<float>(dist_sum / mean_k);
+    valid[(size_t)i] = 1;
+  }
+  long long valid_distances = 0;
+  double sum = 0, sq_sum = 0;
+  for (long long i = 0; i < n; ++i) {
+    valid_distances += valid[(size_t)i];
+    const float d = distances[(size_t)i];
+    sum += d;
+    sq_sum += d * d;  // float product
+  }
+  const double mean = sum / static_cast<double>(valid_distances);
+  const double variance = (sq_sum - sum * sum / static_cast<double>(valid_distances)) / (static_cast<double>(valid_distances) - 1);
+  const double stddev = std::sqrt(variance);
+  const double threshold = mean + stddev_mul * stddev;
+  if (stats3) { stats3[0] = mean; stats3[1] = stddev; stats3[2] = threshold; }
+  if (dist) std::memcpy(dist, distances.data(), (size_t)n * sizeof(float));
+  long long m = 0;
+  for (long long i = 0; i < n; ++i) {
+    if (distances[(size_t)i] > threshold) continue;
+    std::memcpy(out + 4 * m, in + 4 * i, 16);
+    ++m;
+  }
+  return m;
+}
+
 // ---- linear algebra known-answer hooks -------------------------------------
 void orc_sym_eigen3(const double* a9, double* evals3, double* evecs9) {
   M3 a, v;

@@ -61,6 +61,8 @@ def lib():
         L.orc_distance_filter.restype = C.c_longlong
         L.orc_radius_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_double, C.c_int, f32p]
         L.orc_radius_outlier_removal.restype = C.c_longlong
+        L.orc_statistical_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_int, C.c_double, f32p, f64p, f32p]
+        L.orc_statistical_outlier_removal.restype = C.c_longlong
         L.orc_sym_eigen3.argtypes = [f64p, f64p, f64p]
         L.orc_inverse3.argtypes = [f64p, f64p]
         L.orc_svd_solve6.argtypes = [f64p, f64p, f64p]
@@ -122,6 +124,20 @@ def radius_outlier_removal(cloud, radius=0.8, min_neighbors=2):
     cloud = _cloud(cloud)
     out = np.empty((max(len(cloud), 1), 4), np.float32)
     m = lib().orc_radius_outlier_removal(cloud if len(cloud) else np.zeros((1, 4), np.float32), len(cloud), float(radius), int(min_neighbors), out)
+    return out[:m].copy()
+
+
+def statistical_outlier_removal(cloud, mean_k=20, stddev_mul=1.0, details=False):
+    """pcl::StatisticalOutlierRemoval as configured at [REF apps/prefiltering_nodelet.cpp:77-87] (the nodelet's default
+    outlier_removal_method).  details=True also returns {mean, stddev, threshold} and the per-point mean distances."""
+    cloud = _cloud(cloud)
+    n = len(cloud)
+    out = np.empty((max(n, 1), 4), np.float32)
+    stats = np.zeros(3, np.float64)
+    dist = np.zeros(max(n, 1), np.float32)
+    m = lib().orc_statistical_outlier_removal(cloud if n else np.zeros((1, 4), np.float32), n, int(mean_k), float(stddev_mul), out, stats, dist)
+    if details:
+        return out[:m].copy(), dict(mean=stats[0], stddev=stats[1], threshold=stats[2], distances=dist[:n].copy())
     return out[:m].copy()
 
 

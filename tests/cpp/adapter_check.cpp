@@ -32,6 +32,10 @@ int main() {
     rad->setRadiusSearch(0.5);
     rad->setMinNeighborsInRadius(2);
     pcl::Filter<PointT>::Ptr outlier_removal_filter = rad;
+    auto sor = std::make_shared<b200reg::StatisticalOutlierRemoval>();
+    sor->setMeanK(20);
+    sor->setStddevMulThresh(1.0);
+    outlier_removal_filter = sor;
     (void)outlier_removal_filter;
   } catch (const std::exception& e) {
     std::printf("no engine: %s\n", e.what());

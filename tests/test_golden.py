@@ -39,6 +39,9 @@ def test_oracle_prefilter_golden(oracle):
     assert np.array_equal(ds.view(np.uint32), g["ds"].view(np.uint32))
     kept = oracle.radius_outlier_removal(ds, float(g["radius_min"][0]), int(g["radius_min"][1]))
     assert np.array_equal(kept.view(np.uint32), g["kept"].view(np.uint32))
+    kept, det = oracle.statistical_outlier_removal(ds, int(g["meank_mul"][0]), float(g["meank_mul"][1]), details=True)
+    assert np.array_equal(kept.view(np.uint32), g["kept_stat"].view(np.uint32)) and np.array_equal(det["distances"].view(np.uint32), g["stat_dist"].view(np.uint32))
+    assert np.array_equal(np.array([det["mean"], det["stddev"], det["threshold"]]), g["stat"])
 
 
 @pytest.mark.parametrize("name,code", [("direct7", 2), ("direct1", 3), ("kdtree", 0)])
@@ -101,6 +104,13 @@ def test_engine_prefilter_golden():
     assert np.array_equal(np.asarray(ds).view(np.uint32), g["ds"].view(np.uint32))
     kept = pre.outlier_removal(ds)
     assert np.array_equal(np.asarray(kept).view(np.uint32), g["kept"].view(np.uint32))
+    sor = eng.StatisticalOutlierRemoval()
+    sor.setMeanK(int(g["meank_mul"][0]))
+    sor.setStddevMulThresh(float(g["meank_mul"][1]))
+    sor.setInputCloud(g["ds"])
+    assert np.array_equal(sor.filter().view(np.uint32), g["kept_stat"].view(np.uint32))
+    st = sor.last_stats(len(g["ds"]))
+    assert np.array_equal(st["distances"].view(np.uint32), g["stat_dist"].view(np.uint32)) and abs(st["threshold"] - g["stat"][2]) <= 1e-11 * g["stat"][2]
 
 
 @pytest.mark.gpu

@@ -1,5 +1,5 @@
 """The stages either side of VoxelGrid in PrefilteringNodelet::cloud_callback
-[REF apps/prefiltering_nodelet.cpp:150-153 chain; :275-291 distance_filter; :88-96,262-273 RadiusOutlierRemoval]."""
+[REF apps/prefiltering_nodelet.cpp:150-153 chain; :275-291 distance_filter; :88-96,262-273 RadiusOutlierRemoval; :77-87 StatisticalOutlierRemoval]."""
 import os
 
 import numpy as np
@@ -53,10 +53,63 @@ def test_oracle_distance_filter_and_outlier_removal_follow_their_definitions(ora
     assert len(oracle.radius_outlier_removal(np.zeros((0, 4), np.float32), 0.5, 2)) == 0
 
 
-def test_prefilter_mirror_reads_the_reference_parameters(capsys):
-    import delta_graph_slam_b200.odometry as odo
-    with pytest.raises(NotImplementedError):
-        odo.Prefilter(dict(outlier_removal_method="STATISTICAL"), out=DEVNULL)  # refused before any engine handle is created
+def np_statistical_outlier_removal(c, mean_k, stddev_mul):
+    """pcl::StatisticalOutlierRemoval::applyFilterIndices written out with brute-force neighbour searches."""
+    p = c[:, :3].astype(np.float32)
+    finite = np.isfinite(p).all(axis=1)
+    tree = p[finite]
+    dist = np.zeros(len(c), np.float32)
+    valid = 0
+    for i in range(len(c)):
+        if not finite[i] or len(tree) < mean_k + 1:
+            continue
+        d = tree - p[i]
+        d2 = np.sort((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2])[: mean_k + 1]
+        acc = 0.0
+        for v in np.sqrt(d2[1:]).astype(np.float32):
+            acc += float(v)
+        dist[i] = np.float32(acc / mean_k)
+        valid += 1
+    s = sq = 0.0
+    for v in dist:
+        s += float(v)
+        sq += float(np.float32(v * v))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = np.float64(s) / np.float64(valid)
+        var = (np.float64(sq) - np.float64(s) * np.float64(s) / np.float64(valid)) / (np.float64(valid) - 1.0)
+        thr = mean + stddev_mul * np.sqrt(var)
+        return c[~(dist.astype(np.float64) > thr)], dist, thr
+
+
+def small_cloud(oracle, rng, n=1500):
+    c = oracle.voxelgrid(oracle.distance_filter(cloud_with_outliers(oracle, rng), 1.0, 60.0), 0.4)["out"][:n]
+    return np.concatenate([c[:500], np.array([[np.nan, 0, 0, 1], [0, np.inf, 0, 1]], np.float32), c[500:]])
+
+
+def line_cloud(n=64):
+    """Equally spaced points: every mean neighbour distance is the same float, the variance is exactly 0."""
+    c = np.ones((n, 4), np.float32)
+    c[:, 0] = np.arange(n, dtype=np.float32) * np.float32(0.5)
+    c[:, 1:3] = 0
+    return c
+
+
+def test_oracle_statistical_outlier_removal_follows_its_definition(oracle):
+    c = small_cloud(oracle, np.random.default_rng(8))
+    for mean_k, mul in ((20, 1.0), (10, 0.5), (31, 2.0), (1, 0.0)):
+        got, det = oracle.statistical_outlier_removal(c, mean_k, mul, details=True)
+        want, dist, thr = np_statistical_outlier_removal(c, mean_k, mul)
+        assert bits_equal(det["distances"], dist) and det["threshold"] == thr
+        assert bits_equal(got, want) and 0 < len(got) < len(c)
+        assert np.isnan(got[:, :3]).any() and np.isinf(got[:, :3]).any()  # uncounted points stand at distance 0 and stay (upstream behaviour)
+    # fewer finite points than mean_k + 1: no search succeeds, the cut is NaN, everything stays
+    tiny = c[495:507]
+    got, det = oracle.statistical_outlier_removal(tiny, 20, 1.0, details=True)
+    assert bits_equal(got, tiny) and np.isnan(det["threshold"]) and not det["distances"].any()
+    assert len(oracle.statistical_outlier_removal(np.zeros((0, 4), np.float32), 20, 1.0)) == 0
+    # equally spaced points with one neighbour each: all distances equal, variance exactly 0, nothing removed
+    got, det = oracle.statistical_outlier_removal(line_cloud(), 1, 1.0, details=True)
+    assert len(got) == 64 and det["stddev"] == 0.0 and det["threshold"] == 0.5
 
 
 @pytest.mark.gpu
@@ -117,6 +170,110 @@ def test_radius_outlier_removal_matches_the_oracle(oracle, radius, min_neighbors
     ror.setInputCloud(c)
     ror.filter_begin(h_out.numpy())
     assert bits_equal(ror.filter_end(), want) and not h_out.numpy()[len(want):].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mean_k,mul", [(20, 1.0), (10, 0.5), (31, 2.0), (1, 0.0)])
+def test_statistical_outlier_removal_matches_the_oracle(oracle, mean_k, mul):
+    import torch
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(9)
+    c = oracle.voxelgrid(oracle.distance_filter(cloud_with_outliers(oracle, rng), 0.1, 100.0), 0.1)["out"]
+    c = np.concatenate([c[:1000], np.array([[np.nan, 0, 0, 1], [0, -np.inf, 0, 1]], np.float32), c[1000:]])  # uncounted, kept (upstream behaviour)
+    want, det = oracle.statistical_outlier_removal(c, mean_k, mul, details=True)
+    sor = eng.StatisticalOutlierRemoval()
+    sor.setMeanK(mean_k)
+    sor.setStddevMulThresh(mul)
+    sor.setInputCloud(c)
+    assert bits_equal(sor.filter(), want) and 0 < len(want) < len(c)
+    st = sor.last_stats(len(c))
+    assert bits_equal(st["distances"], det["distances"]) and st["valid"] == len(c) - 2
+    # the index-order sums are only taken when a distance sits within rounding of the cut; the tree sums agree to ~n * 2^-53
+    for key in ("mean", "stddev", "threshold"):
+        assert st[key] == det[key] if st["exact_pass"] else abs(st[key] - det[key]) <= 1e-11 * abs(det[key]), key
+    # device-resident and page-locked (zero-copy) outputs
+    d_in = torch.from_numpy(c).cuda()
+    d_out = torch.zeros_like(d_in)
+    sor.setInputCloud(eng.DeviceCloud(d_in.data_ptr(), len(c), d_in))
+    got = sor.filter(out=eng.DeviceCloud(d_out.data_ptr(), len(c), d_out))
+    assert got.n == len(want) and bits_equal(d_out[: got.n].cpu().numpy(), want)
+    h_out = torch.zeros((len(c), 4), dtype=torch.float32, pin_memory=True)
+    sor.setInputCloud(c)
+    sor.filter_begin(h_out.numpy())
+    assert bits_equal(sor.filter_end(), want) and not h_out.numpy()[len(want):].any()
+
+
+@pytest.mark.gpu
+def test_statistical_outlier_removal_edge_cases(oracle):
+    import delta_graph_slam_b200 as eng
+    sor = eng.StatisticalOutlierRemoval()
+    sor.setMeanK(20)
+    sor.setStddevMulThresh(1.0)
+    # fewer finite points than mean_k + 1: nothing is counted, the cut is NaN, everything stays — non-finite points too
+    tiny = small_cloud(oracle, np.random.default_rng(8))[495:507]
+    sor.setInputCloud(tiny)
+    assert bits_equal(sor.filter(), tiny) and bits_equal(oracle.statistical_outlier_removal(tiny, 20, 1.0), tiny)
+    st = sor.last_stats(len(tiny))
+    assert st["valid"] == 0 and np.isnan(st["threshold"]) and not st["distances"].any()
+    sor.setInputCloud(np.zeros((0, 4), np.float32))
+    assert len(sor.filter()) == 0
+    # isolated points (their 21st neighbour is beyond the ring search: block-per-query scan) among a dense patch
+    rng = np.random.default_rng(10)
+    dense = np.ones((4000, 4), np.float32)
+    dense[:, :3] = rng.normal(0, 1.5, (4000, 3)).astype(np.float32)
+    lonely = np.ones((25, 4), np.float32)
+    lonely[:, :3] = rng.uniform(-150, 150, (25, 3)).astype(np.float32)
+    c = np.concatenate([dense[:2000], lonely, dense[2000:]])
+    want, det = oracle.statistical_outlier_removal(c, 20, 1.0, details=True)
+    sor.setInputCloud(c)
+    assert bits_equal(sor.filter(), want)
+    assert bits_equal(sor.last_stats(len(c))["distances"], det["distances"])
+    # exactly zero variance: no rounding bound exists, the index-order pass decides (and agrees to the bit)
+    sor.setMeanK(1)
+    line = line_cloud()
+    sor.setInputCloud(line)
+    want, det = oracle.statistical_outlier_removal(line, 1, 1.0, details=True)
+    assert bits_equal(sor.filter(), want) and len(want) == 64
+    st = sor.last_stats(64)
+    assert st["exact_pass"] and (st["mean"], st["stddev"], st["threshold"]) == (det["mean"], det["stddev"], det["threshold"])
+    # mean_k beyond the warp-wide neighbour list is refused loudly
+    sor.setMeanK(32)
+    with pytest.raises(eng.B200RegError):
+        sor.filter()
+
+
+@pytest.mark.gpu
+def test_nodelet_default_chain_statistical(oracle, capsys):
+    """The nodelet's own defaults [REF apps/prefiltering_nodelet.cpp:77-80]: STATISTICAL 20 - 1, through filter3d and the three-stage front end."""
+    import torch
+    import delta_graph_slam_b200 as eng
+    from test_gpu_frontend import ODOM
+    import sys
+    params = dict(LAUNCH, outlier_removal_method="STATISTICAL")
+    eng.Prefilter(params, out=sys.stdout)
+    assert "outlier_removal: STATISTICAL 20 - 1" in capsys.readouterr().out
+    clouds = [oracle.synth_scan(oracle.synth_traj(k), noise_seed=1000 + k) for k in range(4)]
+    want = [oracle.statistical_outlier_removal(oracle.voxelgrid(oracle.distance_filter(c, 0.1, 100.0), 0.1, is_dense=False)["out"], 20, 1.0) for c in clouds]
+    cap = max(len(c) for c in clouds)
+    h_a = torch.empty((3, cap, 4), dtype=torch.float32, pin_memory=True).numpy()
+    h_b = torch.empty((3, cap, 4), dtype=torch.float32, pin_memory=True).numpy()
+    bufs, rbufs = [h_a[j] for j in range(3)], [h_b[j] for j in range(3)]
+    pre = eng.Prefilter(params, out=DEVNULL)
+    for k, c in enumerate(clouds):
+        assert bits_equal(np.array(pre.filter3d(c, out=bufs[k % 3], out2=rbufs[k % 3])), want[k]), k
+
+    def make():
+        p, o = eng.Prefilter(params, out=DEVNULL), eng.ScanMatchingOdometry(ODOM, out=DEVNULL)
+        p.setSmBudget(40)
+        o.registration.setSmBudget(108)
+        return p, o
+    p1, o1 = make()
+    seq = [o1.matching(0.1 * k, p1.filter3d(c, out=bufs[k % 3], out2=rbufs[k % 3])) for k, c in enumerate(clouds)]
+    p2, o2 = make()
+    seen = []
+    got = eng.FrontEnd(p2, o2, bufs, filter_sms=40, ror_bufs=rbufs).run(clouds, on_frame=lambda k, f: seen.append(np.array(f).copy()))
+    assert all(np.array_equal(a, b) for a, b in zip(got, seq))
+    assert all(bits_equal(a, b) for a, b in zip(seen, want))
 
 
 @pytest.mark.gpu

@@ -44,8 +44,11 @@ def prefilter_case():
     gated = O.distance_filter(pts, 0.1, 100.0)
     ds = O.voxelgrid(gated, 0.1, is_dense=False)["out"]
     kept = O.radius_outlier_removal(ds, 0.5, 2)
+    # the nodelet's own default outlier filter: STATISTICAL 20 - 1.0 [REF apps/prefiltering_nodelet.cpp:77-80]
+    kept_stat, det = O.statistical_outlier_removal(ds, 20, 1.0, details=True)
     np.savez_compressed(os.path.join(OUT, "prefilter.npz"), pts=pts, near_far=np.array([0.1, 100.0]), leaf=np.float32(0.1), radius_min=np.array([0.5, 2.0]),
-                        n_gated=np.int64(len(gated)), ds=ds, kept=kept)
+                        n_gated=np.int64(len(gated)), ds=ds, kept=kept, meank_mul=np.array([20.0, 1.0]), kept_stat=kept_stat,
+                        stat=np.array([det["mean"], det["stddev"], det["threshold"]]), stat_dist=det["distances"])
 
 
 def clouds():
