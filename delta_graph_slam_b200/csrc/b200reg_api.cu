@@ -1111,7 +1111,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
     k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
   }
   k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
-                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p);
+                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, h->nn_ror.sort.meta.p);
   B200_CUDA_TRY(cudaGetLastError());
   return B200REG_OK;
 }
@@ -1196,6 +1196,10 @@ int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out) {
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = wait_mail(h, &h->mail->ror_seq, h->ror_seq))) return rc;
+  if (h->mail->ror.overflow) {
+    h->err = "outlier removal: the cloud spans more than 2^31 cells of the 0.5 m search lattice (gate it with the distance filter first); no result";
+    return B200REG_E_INVALID;
+  }
   const size_t m = h->mail->ror.n_out;
   *n_out = m;
   if (pend.device) return B200REG_OK;

@@ -578,12 +578,12 @@ __global__ void __launch_bounds__(256) k_ror_flags(NnView g, const float4* __res
   }
 }
 
-struct RorCounts { uint32_t n_out; uint32_t pad; };
+struct RorCounts { uint32_t n_out; uint32_t overflow; };  // overflow: the cloud spans more 0.5 m cells than the lattice can index (no result)
 // order-preserving scatter: every block sums the counts of the blocks before it (a few hundred words
 // out of L2), scans its own flags, writes; the last block to finish publishes the total
 __global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ pts, int n, const unsigned char* __restrict__ keep, const uint32_t* __restrict__ block_count,
                                                      float4* __restrict__ out, float4* host_out, unsigned host_cap, RorCounts* __restrict__ counts, RorCounts* host_counts,
-                                                     unsigned int* host_flag, unsigned int host_seq, unsigned int* done_blocks) {
+                                                     unsigned int* host_flag, unsigned int host_seq, unsigned int* done_blocks, const SortMeta* __restrict__ meta) {
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -621,9 +621,12 @@ __global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ 
   *done_blocks = 0u;
   uint32_t total = 0;
   for (int b = 0; b < (int)gridDim.x; ++b) total += __ldcg(block_count + b);
+  const uint32_t overflow = meta->grid.overflow ? 1u : 0u;
   counts->n_out = total;
+  counts->overflow = overflow;
   if (host_counts) {
     host_counts->n_out = total;
+    host_counts->overflow = overflow;
     __threadfence_system();
     *reinterpret_cast<volatile unsigned int*>(host_flag) = host_seq;
   }

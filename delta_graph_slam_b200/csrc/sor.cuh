@@ -42,10 +42,23 @@ __global__ void __launch_bounds__(1024) k_sor_threshold(const float* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sum = 0.0, sq = 0.0;
   unsigned long long cnt = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = __ldg(dist + i);
+  // one CTA, so the loads have to overlap inside each thread: 16-byte loads, four of them in flight
+  const int n4 = n >> 2;
+  const float4* __restrict__ dist4 = reinterpret_cast<const float4*>(dist);
+  auto take = [&](float d) {
     if (d >= 0.f) { sum += (double)d; sq += (double)__fmul_rn(d, d); ++cnt; }
+  };
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < n4 ? __ldg(dist4 + i) : make_float4(-1.f, -1.f, -1.f, -1.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { take(v[u].x); take(v[u].y); take(v[u].z); take(v[u].w); }
   }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) take(__ldg(dist + i));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -77,10 +90,24 @@ __global__ void __launch_bounds__(1024) k_sor_threshold(const float* __restrict_
   const double cut = s_cut, band = s_band;
   unsigned int amb = 0;
   if (band > 0.0) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float d = fmaxf(__ldg(dist + i), 0.f);
-      if (fabs((double)d - cut) <= band) ++amb;
+    // the distances are floats: the band test runs on the two floats that bracket it (one compare each, the
+    // double subtraction only decides for values that land exactly on a bracket)
+    const float lo = __double2float_rd(cut - band), hi = __double2float_ru(cut + band);
+    auto check = [&](float d) {
+      d = fmaxf(d, 0.f);
+      if (d >= lo && d <= hi && fabs((double)d - cut) <= band) ++amb;
+    };
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < n4 ? __ldg(dist4 + i) : make_float4(-1.f, -1.f, -1.f, -1.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { check(v[u].x); check(v[u].y); check(v[u].z); check(v[u].w); }
     }
+    for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) check(__ldg(dist + i));
     if (amb) atomicAdd(&s_amb, amb);
   }
   __syncthreads();

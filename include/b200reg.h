@@ -186,7 +186,9 @@ int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, 
  * than min_neighbors points of the cloud (itself included) lie strictly inside `radius`; order kept.
  * Same calling conventions as the VoxelGrid filter: synchronous, device-resident, and begin / end halves
  * (one call in flight per handle, independent of a VoxelGrid call in flight on the same handle).
- * Either outlier filter (this one or the statistical one below) shares the one in-flight slot. */
+ * Either outlier filter (this one or the statistical one below) shares the one in-flight slot.  Both search on a
+ * 0.5 m lattice over the cloud's bounding box: a cloud spanning more than 2^31 such cells (about 645 m cubed; the
+ * reference's distance filter caps scans at 200 m) is refused by _end with B200REG_E_INVALID, never filtered wrongly. */
 int b200reg_radius_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double radius, int min_neighbors, float* out_xyzw, size_t out_capacity,
                                    size_t* n_out);
 int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out_xyzw, size_t* n_out);

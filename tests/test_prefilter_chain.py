@@ -240,6 +240,18 @@ def test_statistical_outlier_removal_edge_cases(oracle):
     sor.setMeanK(32)
     with pytest.raises(eng.B200RegError):
         sor.filter()
+    # a cloud too wide for the 0.5 m search lattice (> 2^31 cells) is refused by both filters, not filtered wrongly
+    wide = np.concatenate([dense[:100], np.array([[1000, 1000, 1000, 1]], np.float32)])
+    sor.setMeanK(20)
+    sor.setInputCloud(wide)
+    with pytest.raises(eng.B200RegError, match="lattice"):
+        sor.filter()
+    ror = eng.RadiusOutlierRemoval(registration=sor._reg)
+    ror.setInputCloud(wide)
+    with pytest.raises(eng.B200RegError, match="lattice"):
+        ror.filter()
+    sor.setInputCloud(c)  # and the handle carries on
+    assert bits_equal(sor.filter(), oracle.statistical_outlier_removal(c, 20, 1.0))
 
 
 @pytest.mark.gpu

@@ -14,7 +14,7 @@ import delta_graph_slam_b200 as eng  # noqa: E402
 from oracle import oracle_py as O  # noqa: E402  (checker only)
 
 
-def med(fn, reps=50, warm=5):
+def med(fn, reps=int(os.environ.get("SOR_PROBE_REPS", "50")), warm=2):
     for _ in range(warm):
         fn()
     t = []
