@@ -32,6 +32,7 @@ EXPORTS = [
     "b200reg_radius_outlier_removal_end",
     "b200reg_statistical_outlier_removal", "b200reg_statistical_outlier_removal_device", "b200reg_statistical_outlier_removal_begin", "b200reg_statistical_outlier_removal_device_begin",
     "b200reg_statistical_outlier_removal_end", "b200reg_statistical_last_stats",
+    "b200reg_flat_filter", "b200reg_flat_filter_device", "b200reg_flat_filter_begin", "b200reg_flat_filter_device_begin", "b200reg_flat_filter_end", "b200reg_flat_filter_last_nz",
     "b200reg_cloud_put", "b200reg_cloud_sync", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
     "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_profile", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
@@ -128,6 +129,12 @@ def load():
     L.b200reg_statistical_outlier_removal_device_begin.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp]
     L.b200reg_statistical_outlier_removal_end.argtypes = [vp, szp]
     L.b200reg_statistical_last_stats.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
+    L.b200reg_flat_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_int, C.c_double, vp, C.c_size_t, szp]
+    L.b200reg_flat_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_double, C.c_int, C.c_double, vp, szp]
+    L.b200reg_flat_filter_begin.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_int, C.c_double, vp, C.c_size_t]
+    L.b200reg_flat_filter_device_begin.argtypes = [vp, vp, C.c_size_t, C.c_double, C.c_int, C.c_double, vp]
+    L.b200reg_flat_filter_end.argtypes = [vp, szp]
+    L.b200reg_flat_filter_last_nz.argtypes = [vp, vp, C.c_size_t]
     L.b200reg_voxelgrid_last_layout.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.POINTER(C.c_int)]
     L.b200reg_cloud_put.argtypes = [vp, C.c_int64, vp, C.c_size_t, C.c_size_t]
     L.b200reg_cloud_put_device.argtypes = [vp, C.c_int64, vp, C.c_size_t]

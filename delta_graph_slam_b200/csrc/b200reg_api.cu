@@ -296,7 +296,8 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
   B200_ATTR(prefer_shared(k_gicp_knn<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn<kKnnMeanDistance>));
-  B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnMeanDistance>)); B200_ATTR(prefer_shared(k_sor_threshold)); B200_ATTR(prefer_shared(k_sor_flags)); B200_ATTR(prefer_shared(k_gicp_regularize));
+  B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnMeanDistance>)); B200_ATTR(prefer_shared(k_sor_threshold)); B200_ATTR(prefer_shared(k_sor_flags));
+  B200_ATTR(prefer_shared(k_gicp_knn<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_nz_flags)); B200_ATTR(prefer_shared(k_gicp_regularize));
   // k_gicp_align needs 17.5 KB of shared memory and keeps its 29 double accumulators + 3x3 temporaries in a
   // 1.4 KB per-thread stack frame (128-register cap at 512 threads): it wants the L1, not the carve-out
   B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
@@ -1069,14 +1070,24 @@ struct OutlierSpec {
   int min_neighbors = 0;
   int mean_k = 0;
   double stddev_mul = 0.0;
-  bool valid() const { return statistical ? (mean_k >= 1 && mean_k <= 31 && stddev_mul == stddev_mul) : (radius > 0 && min_neighbors >= 0); }
+  // filtered2D of the prefilter nodelet: height gate -> normal test -> flatten (b200reg_flat_filter)
+  bool flat = false;
+  double lidar_z = 0.0;
+  int normal_k = 0;
+  float normal_thresh = 0.f;
+  bool valid() const {
+    if (flat) return normal_k >= 1 && normal_k <= 32 && lidar_z == lidar_z && normal_thresh == normal_thresh;
+    return statistical ? (mean_k >= 1 && mean_k <= 31 && stddev_mul == stddev_mul) : (radius > 0 && min_neighbors >= 0);
+  }
 };
 
 static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const OutlierSpec& spec, float4* d_out, float4* host_out, size_t host_cap) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   const double radius = spec.radius;
   const int min_neighbors = spec.min_neighbors;
-  B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0));
+  PointGate gate = kNoGate;
+  if (spec.flat) { gate.on = 2; gate.near_thresh = spec.lidar_z; }  // height_filtering as a gate of the lattice build: no intermediate cloud
+  B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0, gate));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));
   B200_CUDA_TRY(h->ror_block_count.reserve(blocks));
@@ -1091,7 +1102,20 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
   RorCounts* hc = const_cast<RorCounts*>(&h->mail->ror);
   unsigned int* hf = const_cast<unsigned int*>(&h->mail->ror_seq);
   const unsigned int seq = ++h->ror_seq;
-  if (spec.statistical) {
+  if (spec.flat) {
+    // |n_z| per point that passed the height gate; NaN (never kept) everywhere else
+    B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
+    B200_CUDA_TRY(h->sor_pending.reserve(n ? n : 1));
+    B200_CUDA_TRY(h->sor_n_pending.reserve(1));
+    B200_CUDA_TRY(cudaMemsetAsync(h->sor_dist.p, 0xFF, (n ? n : 1) * sizeof(float), h->stream));
+    B200_CUDA_TRY(cudaMemsetAsync(h->sor_n_pending.p, 0, sizeof(unsigned int), h->stream));
+    launch_counter() += 4;
+    if (n) {
+      k_gicp_knn<kKnnNormalNz><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+      k_gicp_knn_brute<kKnnNormalNz><<<kNumSM * 4, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+    }
+    k_nz_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.normal_thresh, h->ror_keep.p, h->ror_block_count.p);
+  } else if (spec.statistical) {
     // the k-NN kernels write one float per finite point; everything else stays at the "not counted" mark (< 0)
     B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
     B200_CUDA_TRY(h->sor_stats.reserve(1));
@@ -1111,7 +1135,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
     k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
   }
   k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
-                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, h->nn_ror.sort.meta.p);
+                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, h->nn_ror.sort.meta.p, spec.flat ? 1 : 0);
   B200_CUDA_TRY(cudaGetLastError());
   return B200REG_OK;
 }
@@ -1245,6 +1269,53 @@ int b200reg_statistical_outlier_removal_device(b200reg_handle* h, const float* d
   int rc = b200reg_statistical_outlier_removal_device_begin(h, d_xyzw, n, mean_k, stddev_mul, d_out);
   if (rc) return rc;
   return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+// ---- filtered2D: height_filtering -> normal_filtering -> flatten ----------------------------------
+static OutlierSpec flat_spec(double lidar_z, int k, double thresh) {
+  OutlierSpec s;
+  s.flat = true; s.lidar_z = lidar_z; s.normal_k = k; s.normal_thresh = (float)thresh;
+  return s;
+}
+static int flat_check(b200reg_handle* h, int k) {
+  if (h && (k < 1 || k > 32)) { h->err = "normal_k must lie in 1..32 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
+  return B200REG_OK;
+}
+int b200reg_flat_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double lidar_z, int normal_k, double normal_thresh, float* out, size_t cap) {
+  int rc = flat_check(h, normal_k);
+  if (rc) return rc;
+  return outlier_host_begin(h, xyzw, n, stride, flat_spec(lidar_z, normal_k, normal_thresh), out, cap);
+}
+int b200reg_flat_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out) {
+  int rc = flat_check(h, normal_k);
+  if (rc) return rc;
+  return outlier_device_begin(h, d_xyzw, n, flat_spec(lidar_z, normal_k, normal_thresh), d_out);
+}
+int b200reg_flat_filter_end(b200reg_handle* h, size_t* n_out) { return b200reg_radius_outlier_removal_end(h, n_out); }
+int b200reg_flat_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double lidar_z, int normal_k, double normal_thresh, float* out, size_t cap, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_flat_filter_begin(h, xyzw, n, stride, lidar_z, normal_k, normal_thresh, out, cap);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+int b200reg_flat_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = b200reg_flat_filter_device_begin(h, d_xyzw, n, lidar_z, normal_k, normal_thresh, d_out);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+// |n_z| per input point of the last flat-filter call (NaN: below the height gate, or no normal)
+int b200reg_flat_filter_last_nz(b200reg_handle* h, float* nz, size_t n) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !nz) return B200REG_E_INVALID;
+  if (!h->sor_dist.p || n > h->sor_dist.cap) return B200REG_E_STATE;
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(cudaMemcpyAsync(nz, h->sor_dist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return B200REG_OK;
 }
 
 // mean / stddev / cut of the last statistical call (after its _end), its count of points with a full

@@ -218,9 +218,102 @@ __device__ __forceinline__ float knn_mean_distance(int k, int lane, float td, in
   return full ? (float)__ddiv_rn(sum, (double)(k - 1)) : -1.0f;
 }
 
+// pcl::NormalEstimation's per-point normal, reduced to what PrefilteringNodelet::normal_filtering keeps of it
+// [REF apps/prefiltering_nodelet.cpp:222-251]: |n_z| of the normalised normal of the k nearest neighbours (the point
+// included).  PCL 1.8-1.10 [UPSTREAM-RECALLED, mirrored operation by operation, no contraction]:
+// computeMeanAndCovarianceMatrix = nine FLOAT accumulators in neighbour order, / count, cov = E[ab] - E[a]E[b];
+// pcl::eigen33 = scale by the largest |entry|, closed-form roots (atan2 / cos / sin: computed in double and rounded,
+// the correctly rounded float), eigenvector of the smallest root = the longest cross product of two rows of A - root I.
+// flipNormalTowardsViewpoint only changes the sign.  Fewer than three neighbours: no normal (NaN), as upstream.
+__device__ __forceinline__ void pcl_roots2(float b, float c, float* r) {
+  r[0] = 0.0f;
+  float d = __fsub_rn(__fmul_rn(b, b), __fmul_rn(4.0f, c));
+  if (d < 0.0f) d = 0.0f;
+  const float sd = __fsqrt_rn(d);
+  r[2] = __fmul_rn(0.5f, __fadd_rn(b, sd));
+  r[1] = __fmul_rn(0.5f, __fsub_rn(b, sd));
+}
+__device__ __forceinline__ float knn_normal_abs_nz(const float4* __restrict__ pts, int k, int lane, float td, int ti) {
+  (void)td;
+  const bool have = lane < k && ti != kNoIndex;
+  const int cnt = __popc(__ballot_sync(0xffffffffu, have));  // the list is packed: entries 0 .. cnt-1
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (have) nb = __ldg(pts + ti);
+  if (cnt < 3) return __int_as_float(0x7fc00000);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  for (int j = 0; j < cnt; ++j) {
+    const float x = __shfl_sync(0xffffffffu, nb.x, j), y = __shfl_sync(0xffffffffu, nb.y, j), z = __shfl_sync(0xffffffffu, nb.z, j);
+    a0 = __fadd_rn(a0, __fmul_rn(x, x)); a1 = __fadd_rn(a1, __fmul_rn(x, y)); a2 = __fadd_rn(a2, __fmul_rn(x, z));
+    a3 = __fadd_rn(a3, __fmul_rn(y, y)); a4 = __fadd_rn(a4, __fmul_rn(y, z)); a5 = __fadd_rn(a5, __fmul_rn(z, z));
+    a6 = __fadd_rn(a6, x); a7 = __fadd_rn(a7, y); a8 = __fadd_rn(a8, z);
+  }
+  const float fc = (float)cnt;
+  a0 = __fdiv_rn(a0, fc); a1 = __fdiv_rn(a1, fc); a2 = __fdiv_rn(a2, fc); a3 = __fdiv_rn(a3, fc); a4 = __fdiv_rn(a4, fc);
+  a5 = __fdiv_rn(a5, fc); a6 = __fdiv_rn(a6, fc); a7 = __fdiv_rn(a7, fc); a8 = __fdiv_rn(a8, fc);
+  float c00 = __fsub_rn(a0, __fmul_rn(a6, a6)), c01 = __fsub_rn(a1, __fmul_rn(a6, a7)), c02 = __fsub_rn(a2, __fmul_rn(a6, a8));
+  float c11 = __fsub_rn(a3, __fmul_rn(a7, a7)), c12 = __fsub_rn(a4, __fmul_rn(a7, a8)), c22 = __fsub_rn(a5, __fmul_rn(a8, a8));
+  float scale = fmaxf(fmaxf(fmaxf(fabsf(c00), fabsf(c01)), fmaxf(fabsf(c02), fabsf(c11))), fmaxf(fabsf(c12), fabsf(c22)));
+  if (!(scale == scale)) return __int_as_float(0x7fc00000);
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float m00 = __fdiv_rn(c00, scale), m01 = __fdiv_rn(c01, scale), m02 = __fdiv_rn(c02, scale), m11 = __fdiv_rn(c11, scale), m12 = __fdiv_rn(c12, scale), m22 = __fdiv_rn(c22, scale);
+  // computeRoots
+  float r[3];
+  {
+    const float t1 = __fmul_rn(__fmul_rn(m00, m11), m22), t2 = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, m01), m02), m12), t3 = __fmul_rn(__fmul_rn(m00, m12), m12);
+    const float t4 = __fmul_rn(__fmul_rn(m11, m02), m02), t5 = __fmul_rn(__fmul_rn(m22, m01), m01);
+    const float c0 = __fsub_rn(__fsub_rn(__fsub_rn(__fadd_rn(t1, t2), t3), t4), t5);
+    const float c1 = __fsub_rn(__fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(m00, m11), __fmul_rn(m01, m01)), __fmul_rn(m00, m22)), __fmul_rn(m02, m02)), __fmul_rn(m11, m22)), __fmul_rn(m12, m12));
+    const float c2 = __fadd_rn(__fadd_rn(m00, m11), m22);
+    if (fabsf(c0) < 1.1920929e-07f) {
+      pcl_roots2(c2, c1, r);
+    } else {
+      const float s_inv3 = 0.333333343f, s_sqrt3 = 1.73205078f;  // 1.0f / 3.0f, sqrtf(3.0f)
+      const float c2_over_3 = __fmul_rn(c2, s_inv3);
+      float a_over_3 = __fmul_rn(__fsub_rn(c1, __fmul_rn(c2, c2_over_3)), s_inv3);
+      if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+      const float half_b = __fmul_rn(0.5f, __fadd_rn(c0, __fmul_rn(c2_over_3, __fsub_rn(__fmul_rn(__fmul_rn(2.0f, c2_over_3), c2_over_3), c1))));
+      float q = __fadd_rn(__fmul_rn(half_b, half_b), __fmul_rn(__fmul_rn(a_over_3, a_over_3), a_over_3));
+      if (q > 0.0f) q = 0.0f;
+      const float rho = __fsqrt_rn(-a_over_3);
+      const float theta = __fmul_rn((float)atan2((double)__fsqrt_rn(-q), (double)half_b), s_inv3);
+      const float cos_theta = (float)cos((double)theta), sin_theta = (float)sin((double)theta);
+      r[0] = __fadd_rn(c2_over_3, __fmul_rn(__fmul_rn(2.0f, rho), cos_theta));
+      r[1] = __fsub_rn(c2_over_3, __fmul_rn(rho, __fadd_rn(cos_theta, __fmul_rn(s_sqrt3, sin_theta))));
+      r[2] = __fsub_rn(c2_over_3, __fmul_rn(rho, __fsub_rn(cos_theta, __fmul_rn(s_sqrt3, sin_theta))));
+      float t;
+      if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+      if (r[1] >= r[2]) {
+        t = r[1]; r[1] = r[2]; r[2] = t;
+        if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+      }
+      if (r[0] <= 0.0f) pcl_roots2(c2, c1, r);
+    }
+  }
+  m00 = __fsub_rn(m00, r[0]); m11 = __fsub_rn(m11, r[0]); m22 = __fsub_rn(m22, r[0]);
+  // rows: (m00 m01 m02) (m01 m11 m12) (m02 m12 m22)
+#define B200_CROSS(ax, ay, az, bx, by, bz, ox, oy, oz) \
+  const float ox = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by)), oy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz)), oz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+  B200_CROSS(m00, m01, m02, m01, m11, m12, u0, u1, u2)
+  B200_CROSS(m00, m01, m02, m02, m12, m22, v0, v1, v2)
+  B200_CROSS(m01, m11, m12, m02, m12, m22, w0, w1, w2)
+#undef B200_CROSS
+  const float l1 = __fadd_rn(__fadd_rn(__fmul_rn(u0, u0), __fmul_rn(u1, u1)), __fmul_rn(u2, u2));
+  const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2));
+  const float l3 = __fadd_rn(__fadd_rn(__fmul_rn(w0, w0), __fmul_rn(w1, w1)), __fmul_rn(w2, w2));
+  float e0 = w0, e1 = w1, e2 = w2, l = l3;
+  if (l1 >= l2 && l1 >= l3) { e0 = u0; e1 = u1; e2 = u2; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { e0 = v0; e1 = v1; e2 = v2; l = l2; }
+  const float sl = __fsqrt_rn(l);
+  e0 = __fdiv_rn(e0, sl); e1 = __fdiv_rn(e1, sl); e2 = __fdiv_rn(e2, sl);
+  const float z2 = __fadd_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), __fmul_rn(e2, e2));  // Eigen normalized()
+  const float nz = z2 > 0.0f ? __fdiv_rn(e2, __fsqrt_rn(z2)) : e2;
+  return fabsf(nz);
+}
+
 // The two k-NN kernels serve two callers; kKnnCovariance is FAST_GICP's, kKnnMeanDistance the statistical
 // outlier filter's (same search, `n` taken from the grid's own count of finite points, a float per point out).
-constexpr int kKnnCovariance = 0, kKnnMeanDistance = 1;
+// kKnnNormalNz the flat-cloud normal filter's (|n_z| per point into the same float array).
+constexpr int kKnnCovariance = 0, kKnnMeanDistance = 1, kKnnNormalNz = 2;
 
 // calculate_covariances, step 1: exact k nearest neighbours + raw covariance, one warp per point.
 // covs[i] = {xx, xy, xz, yy, yz, zz} (not yet regularised).  A point whose k-th neighbour is not settled
@@ -235,7 +328,7 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
   if (threadIdx.x < (int)(sizeof(GridParams) / 4)) reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&g.meta->grid)[threadIdx.x];
   __syncthreads();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // queries are taken in cell order: neighbouring warps touch neighbouring cells
-  if (TAIL == kKnnMeanDistance) n = min(n, (int)g.meta->n_valid);  // non-finite points never entered the grid
+  if (TAIL != kKnnCovariance) n = min(n, (int)g.meta->n_valid);  // non-finite points never entered the grid
   if (w >= n) return;
   const GridParams& gp = s_gp;
   const float4 qp = __ldg(g.pts + w);
@@ -328,6 +421,11 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
     if (lane == 0) mean_dist[qi] = d;
     return;
   }
+  if (TAIL == kKnnNormalNz) {
+    const float a = knn_normal_abs_nz(pts, k, lane, L.td, L.ti);
+    if (lane == 0) mean_dist[qi] = a;
+    return;
+  }
   const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);
   if (lane < 6) covs[(size_t)qi * 6 + lane] = c;
 }
@@ -344,7 +442,7 @@ __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int np = (int)*n_pending;
   const int km1 = k - 1;
-  const uint32_t gn = TAIL == kKnnMeanDistance ? min((uint32_t)g.n, g.meta->n_valid) : (uint32_t)g.n;
+  const uint32_t gn = TAIL != kKnnCovariance ? min((uint32_t)g.n, g.meta->n_valid) : (uint32_t)g.n;
   const uint32_t chunk = ((gn + 7u) / 8u + 31u) & ~31u;
   for (int e = blockIdx.x; e < np; e += gridDim.x) {
     const int w = pending[e];
@@ -363,6 +461,11 @@ __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* 
       if (TAIL == kKnnMeanDistance) {
         const float d = knn_mean_distance(k, lane, L.td, L.ti);
         if (lane == 0) mean_dist[__float_as_int(qp.w)] = d;
+        continue;
+      }
+      if (TAIL == kKnnNormalNz) {
+        const float a = knn_normal_abs_nz(pts, k, lane, L.td, L.ti);
+        if (lane == 0) mean_dist[__float_as_int(qp.w)] = a;
         continue;
       }
       const double c = knn_raw_covariance(pts, k, lane, L.td, L.ti);

@@ -583,7 +583,7 @@ struct RorCounts { uint32_t n_out; uint32_t overflow; };  // overflow: the cloud
 // out of L2), scans its own flags, writes; the last block to finish publishes the total
 __global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ pts, int n, const unsigned char* __restrict__ keep, const uint32_t* __restrict__ block_count,
                                                      float4* __restrict__ out, float4* host_out, unsigned host_cap, RorCounts* __restrict__ counts, RorCounts* host_counts,
-                                                     unsigned int* host_flag, unsigned int host_seq, unsigned int* done_blocks, const SortMeta* __restrict__ meta) {
+                                                     unsigned int* host_flag, unsigned int host_seq, unsigned int* done_blocks, const SortMeta* __restrict__ meta, int flatten) {
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -609,7 +609,8 @@ __global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ 
   for (int w = 0; w < warp; ++w) off += s_part[w];
   if (k) {
     const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
-    const float4 p = __ldg(pts + i);
+    float4 p = __ldg(pts + i);
+    if (flatten) p.z = 0.f;  // PrefilteringNodelet::flatten [REF apps/prefiltering_nodelet.cpp:166-183]
     out[dst] = p;
     if (host_out && dst < host_cap) host_out[dst] = p;
   }
@@ -664,10 +665,10 @@ struct NnGrid {
     while (cap < (uint32_t)(2 * n_points + 1)) cap <<= 1;
     return cap;
   }
-  cudaError_t build(cudaStream_t st, const float4* d_pts, int n_points, int is_dense = 1) {
+  cudaError_t build(cudaStream_t st, const float4* d_pts, int n_points, int is_dense = 1, PointGate gate = kNoGate) {
     cudaError_t e;
     n = n_points;
-    if ((e = sort.run(st, d_pts, n, is_dense, kNnCell, kNnCell, kNnCell, false)) != cudaSuccess) return e;
+    if ((e = sort.run(st, d_pts, n, is_dense, kNnCell, kNnCell, kNnCell, false, gate)) != cudaSuccess) return e;
     if ((e = pts.reserve(n > 0 ? n : 1)) != cudaSuccess) return e;
     table_cap = capacity_for(n);
     if ((e = table.reserve(table_cap)) != cudaSuccess) return e;

@@ -145,4 +145,25 @@ __global__ void __launch_bounds__(256) k_sor_flags(const float* __restrict__ dis
   }
 }
 
+// PrefilteringNodelet::normal_filtering's test [REF apps/prefiltering_nodelet.cpp:243-246]: keep when |n_z| < thresh
+// (nz[i] = NaN for the points the height gate dropped and the points without a normal: never kept)
+__global__ void __launch_bounds__(256) k_nz_flags(const float* __restrict__ nz, int n, float thresh, unsigned char* __restrict__ keep, uint32_t* __restrict__ block_count) {
+  __shared__ uint32_t s_cnt[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int k = 0;
+  if (i < n) {
+    k = __ldg(nz + i) < thresh ? 1 : 0;
+    keep[i] = (unsigned char)k;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) s_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int w = 0; w < 8; ++w) c += s_cnt[w];
+    block_count[blockIdx.x] = c;
+  }
+}
+
 }  // namespace b200

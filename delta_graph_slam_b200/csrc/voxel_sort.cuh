@@ -38,6 +38,9 @@ struct PointGate {
 constexpr PointGate kNoGate = {0, 0.0, 0.0};
 __device__ __forceinline__ bool point_takes_part(const PointGate& gate, int is_dense, float x, float y, float z) {
   if (gate.on) {
+    // on == 2: PrefilteringNodelet::height_filtering [REF apps/prefiltering_nodelet.cpp:198-214] as a gate — the point
+    // takes part when z > near_thresh (float widened to double, as the reference compares) and it is finite
+    if (gate.on == 2) return finite3(x, y, z) && (double)z > gate.near_thresh;
     const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
     const double d = (double)__fsqrt_rn(sq);
     return d > gate.near_thresh && d < gate.far_thresh;

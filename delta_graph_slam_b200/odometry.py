@@ -101,6 +101,14 @@ class Prefilter:
         self.outlier_removal_filter.setInputCloud(cloud)
         return self.outlier_removal_filter.filter(out=out)
 
+    def filter2d(self, filtered3d, lidar_z, out=None):
+        """filtered2D of cloud_callback [REF apps/prefiltering_nodelet.cpp:155-158]: height_filtering (z > lidar z) ->
+        normal_filtering (k = 10, |n_z| < 0.2) -> flatten, one engine call on the prefilter's handle."""
+        reg = self.filter._reg if self.filter is not None else (self.outlier_removal_filter._reg if self.outlier_removal_filter is not None else None)
+        if reg is None:
+            raise NotImplementedError("filter2d needs an engine handle: configure a VoxelGrid down-sampler or an outlier filter")
+        return reg.flat_filter(filtered3d, lidar_z, out=out)
+
     def filter3d(self, cloud, out=None, out2=None):
         """filtered3D of cloud_callback: distance_filter -> downsample -> outlier_removal."""
         return self.outlier_removal(self.downsample(cloud, out=out), out=out2)

@@ -378,6 +378,38 @@ class Registration:
         res = self.statistical_outlier_removal_end()
         return res.copy() if own else res
 
+    def flat_filter_begin(self, cloud, lidar_z, out, normal_k=10, normal_thresh=0.2):
+        """height_filtering -> normal_filtering -> flatten of the prefilter nodelet in one call (b200reg_flat_filter), first half."""
+        if isinstance(cloud, DeviceCloud):
+            if out.n < cloud.n:
+                raise ValueError("output buffer smaller than the input cloud")
+            self._ck(_lib.load().b200reg_flat_filter_device_begin(self._h, cloud.ptr, cloud.n, float(lidar_z), int(normal_k), float(normal_thresh), out.ptr))
+            self._ror_pending = (cloud, out)
+            return
+        c = _lib.as_cloud(cloud)
+        if out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
+        self._ck(_lib.load().b200reg_flat_filter_begin(self._h, c.ctypes.data if len(c) else None, len(c), 16, float(lidar_z), int(normal_k), float(normal_thresh), out.ctypes.data, len(out)))
+        self._ror_pending = (c, out)
+
+    def flat_filter_end(self):
+        return self.radius_outlier_removal_end()
+
+    def flat_filter(self, cloud, lidar_z, out=None, normal_k=10, normal_thresh=0.2):
+        own = out is None
+        if own:
+            if isinstance(cloud, DeviceCloud):
+                raise ValueError("a device cloud needs a device output buffer")
+            out = np.empty((max(len(cloud), 1), 4), np.float32)
+        self.flat_filter_begin(cloud, lidar_z, out, normal_k, normal_thresh)
+        res = self.flat_filter_end()
+        return res.copy() if own else res
+
+    def flat_filter_last_nz(self, n_points):
+        nz = np.zeros(max(n_points, 1), np.float32)
+        self._ck(_lib.load().b200reg_flat_filter_last_nz(self._h, nz.ctypes.data, n_points))
+        return nz[:n_points]
+
     def statistical_last_stats(self, n_points=0):
         """{mean, stddev, threshold, valid, exact_pass[, distances]} of the last statistical call (b200reg_statistical_last_stats)."""
         st = np.zeros(3, np.float64)

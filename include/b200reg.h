@@ -211,6 +211,25 @@ int b200reg_statistical_outlier_removal_end(b200reg_handle* h, size_t* n_out);
 /* introspection of the last statistical call, after its _end (parity tests): {mean, stddev, cut}, the number of
  * counted points, whether the index-order summation pass ran, and (dist != NULL) the n per-point figures. */
 int b200reg_statistical_last_stats(b200reg_handle* h, double stats3[3], unsigned long long* valid, int* exact_pass, float* dist, size_t n);
+/* filtered2D of PrefilteringNodelet::cloud_callback [REF apps/prefiltering_nodelet.cpp:155-158], one call:
+ *   height_filtering (:198-214)  keep z > lidar_z (the lidar's z in base_link, :143)
+ *   normal_filtering (:222-251)  pcl::NormalEstimation with setKSearch(normal_k = 10) on what is left, keep
+ *                                |normalised n_z| < normal_thresh (0.2): the vertical structures
+ *   flatten (:166-183)           z := 0
+ * Order kept.  The height test gates the search-lattice build (no intermediate cloud), the normal is the third
+ * tail of the warp-per-query k-NN kernel, the flatten happens in the order-preserving scatter.  The normal mirrors
+ * PCL 1.8-1.10's float arithmetic operation by operation; its three libm calls (atan2f, cosf, sinf) are taken
+ * correctly rounded (as glibc >= 2.41 returns them).  Against an older libm the last bit of a root can differ, and a
+ * near-degenerate neighbourhood amplifies it: upstream's normals are not bit-reproducible across hosts either.
+ * Same calling conventions and in-flight slot as the outlier filters; _end is b200reg_radius_outlier_removal_end. */
+int b200reg_flat_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double lidar_z, int normal_k, double normal_thresh, float* out_xyzw, size_t out_capacity,
+                        size_t* n_out);
+int b200reg_flat_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out_xyzw, size_t* n_out);
+int b200reg_flat_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double lidar_z, int normal_k, double normal_thresh, float* out_xyzw, size_t out_capacity);
+int b200reg_flat_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out_xyzw);
+int b200reg_flat_filter_end(b200reg_handle* h, size_t* n_out);
+/* |n_z| per input point of the last flat-filter call, after its _end (NaN: below the height gate, or no normal) */
+int b200reg_flat_filter_last_nz(b200reg_handle* h, float* nz, size_t n);
 /* introspection of the last filter call (parity tests): per output voxel linear index and point
  * count, per input point key (0xFFFFFFFF = skipped), min_b[3] + div_b[3].  Any pointer may be NULL. */
 int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_voxels, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow);

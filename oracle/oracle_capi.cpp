@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 #include <string>
 
@@ -247,6 +248,151 @@ long long orc_statistical_outlier_removal(const float* in, long long n, int mean
     ++m;
   }
   return m;
+}
+
+// ---- filtered2D of PrefilteringNodelet::cloud_callback [REF apps/prefiltering_nodelet.cpp:155-158] -----------------
+// height_filtering (:198-214, z > lidar z) -> normal_filtering (:222-251: pcl::NormalEstimation, k = 10, keep
+// |normalized n_z| < 0.2) -> flatten (:166-183, z := 0).  pcl::NormalEstimation restated from PCL 1.8-1.10
+// [UPSTREAM-RECALLED]: computeMeanAndCovarianceMatrix (single pass, nine FLOAT accumulators in neighbour order),
+// solvePlaneParameters -> pcl::eigen33 (matrix scaled by its largest |entry|, closed-form roots, eigenvector of the
+// smallest root as the longest cross product of two rows).  flipNormalTowardsViewpoint only changes the sign, which
+// |n_z| does not see.
+static void pcl_compute_roots2(float b, float c, float roots[3]) {
+  roots[0] = 0.0f;
+  float d = b * b - 4.0f * c;
+  if (d < 0.0f) d = 0.0f;
+  const float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+static void pcl_compute_roots(const float m[3][3], float roots[3]) {
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] - m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] - m[1][2] * m[1][2];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+    pcl_compute_roots2(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = 1.0f / 3.0f;
+  const float s_sqrt3 = std::sqrt(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  const float rho = std::sqrt(-a_over_3);
+  // atan2f / cosf / sinf taken CORRECTLY ROUNDED (double evaluation, rounded once; what glibc >= 2.41's CORE-MATH
+  // routines return).  Older libms differ in the last bit (glibc 2.39's atan2f in 16 % of calls, measured here), and a
+  // near-degenerate neighbourhood amplifies that bit: upstream's own normals are not bit-reproducible across hosts.
+  const float theta = static_cast<float>(std::atan2(static_cast<double>(std::sqrt(-q)), static_cast<double>(half_b))) * s_inv3;
+  const float cos_theta = static_cast<float>(std::cos(static_cast<double>(theta)));
+  const float sin_theta = static_cast<float>(std::sin(static_cast<double>(theta)));
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    std::swap(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0.0f) pcl_compute_roots2(c2, c1, roots);
+}
+// normal of the neighbourhood idx[0..cnt) (finite points); false = NaN normal upstream
+static bool pcl_point_normal(const float* pts, const int* idx, int cnt, float n[3]) {
+  if (cnt < 3) return false;
+  float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < cnt; ++j) {
+    const float* p = pts + 4 * (size_t)idx[j];
+    accu[0] += p[0] * p[0];
+    accu[1] += p[0] * p[1];
+    accu[2] += p[0] * p[2];
+    accu[3] += p[1] * p[1];
+    accu[4] += p[1] * p[2];
+    accu[5] += p[2] * p[2];
+    accu[6] += p[0];
+    accu[7] += p[1];
+    accu[8] += p[2];
+  }
+  for (float& a : accu) a /= static_cast<float>(cnt);
+  float c[3][3];
+  c[0][0] = accu[0] - accu[6] * accu[6];
+  c[0][1] = accu[1] - accu[6] * accu[7];
+  c[0][2] = accu[2] - accu[6] * accu[8];
+  c[1][1] = accu[3] - accu[7] * accu[7];
+  c[1][2] = accu[4] - accu[7] * accu[8];
+  c[2][2] = accu[5] - accu[8] * accu[8];
+  c[1][0] = c[0][1]; c[2][0] = c[0][2]; c[2][1] = c[1][2];
+  float scale = 0.0f;
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) scale = std::max(scale, std::fabs(c[r][k]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float m[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) m[r][k] = c[r][k] / scale;
+  float roots[3];
+  pcl_compute_roots(m, roots);
+  for (int r = 0; r < 3; ++r) m[r][r] -= roots[0];
+  auto cross = [](const float* a, const float* b, float* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  float v1[3], v2[3], v3[3];
+  cross(m[0], m[1], v1);
+  cross(m[0], m[2], v2);
+  cross(m[1], m[2], v3);
+  auto sq = [](const float* v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; };
+  const float l1 = sq(v1), l2 = sq(v2), l3 = sq(v3);
+  const float* v = v3;
+  float l = l3;
+  if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; }
+  const float s = std::sqrt(l);
+  for (int a = 0; a < 3; ++a) n[a] = v[a] / s;
+  return true;
+}
+
+// out: kept points with z = 0; nz_out (optional, n floats): |normalized n_z| per INPUT point, NaN where the point
+// fell to the height filter or has no normal (tests use it to tell decisions that sit on the threshold)
+long long orc_flat_filter(const float* in, long long n, double lidar_z, int k, float thresh, float* out, float* nz_out) {
+  std::vector<float> high;   // height_filtering output (is_dense = false: non-finite points may remain)
+  std::vector<long long> src;
+  for (long long i = 0; i < n; ++i)
+    if (in[4 * i + 2] > lidar_z) { high.insert(high.end(), in + 4 * i, in + 4 * i + 4); src.push_back(i); }
+  const long long m = (long long)src.size();
+  if (nz_out) for (long long i = 0; i < n; ++i) nz_out[i] = std::numeric_limits<float>::quiet_NaN();
+  // the search tree holds the finite points; indices map back into `high`
+  std::vector<float> finite;
+  std::vector<int> fidx;
+  for (long long i = 0; i < m; ++i)
+    if (std::isfinite(high[4 * i]) && std::isfinite(high[4 * i + 1]) && std::isfinite(high[4 * i + 2])) { finite.insert(finite.end(), high.begin() + 4 * i, high.begin() + 4 * i + 4); fidx.push_back((int)i); }
+  KdTree t;
+  t.build(finite.data(), finite.size() / 4);
+  std::vector<unsigned char> keep((size_t)(m > 0 ? m : 1), 0);
+#pragma omp parallel for schedule(guided, 64)
+  for (long long i = 0; i < m; ++i) {
+    const float* q = high.data() + 4 * i;
+    if (!std::isfinite(q[0]) || !std::isfinite(q[1]) || !std::isfinite(q[2])) continue;
+    std::vector<int> idx((size_t)k);
+    std::vector<float> d2((size_t)k);
+    const int found = t.knn(q, k, idx.data(), d2.data());
+    float nrm[3];
+    if (found == 0 || !pcl_point_normal(finite.data(), idx.data(), found, nrm)) continue;
+    const float z2 = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];  // Eigen normalized(): v / sqrt(squaredNorm) when > 0
+    const float nz = z2 > 0.0f ? nrm[2] / std::sqrt(z2) : nrm[2];
+    const float a = std::fabs(nz);
+    if (nz_out) nz_out[src[(size_t)i]] = a;
+    keep[(size_t)i] = a < thresh ? 1 : 0;
+  }
+  long long o = 0;
+  for (long long i = 0; i < m; ++i)
+    if (keep[(size_t)i]) {
+      std::memcpy(out + 4 * o, high.data() + 4 * i, 16);
+      out[4 * o + 2] = 0.0f;
+      ++o;
+    }
+  return o;
 }
 
 // ---- linear algebra known-answer hooks -------------------------------------

@@ -63,6 +63,8 @@ def lib():
         L.orc_radius_outlier_removal.restype = C.c_longlong
         L.orc_statistical_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_int, C.c_double, f32p, f64p, f32p]
         L.orc_statistical_outlier_removal.restype = C.c_longlong
+        L.orc_flat_filter.argtypes = [f32p, C.c_longlong, C.c_double, C.c_int, C.c_float, f32p, f32p]
+        L.orc_flat_filter.restype = C.c_longlong
         L.orc_sym_eigen3.argtypes = [f64p, f64p, f64p]
         L.orc_inverse3.argtypes = [f64p, f64p]
         L.orc_svd_solve6.argtypes = [f64p, f64p, f64p]
@@ -138,6 +140,19 @@ def statistical_outlier_removal(cloud, mean_k=20, stddev_mul=1.0, details=False)
     m = lib().orc_statistical_outlier_removal(cloud if n else np.zeros((1, 4), np.float32), n, int(mean_k), float(stddev_mul), out, stats, dist)
     if details:
         return out[:m].copy(), dict(mean=stats[0], stddev=stats[1], threshold=stats[2], distances=dist[:n].copy())
+    return out[:m].copy()
+
+
+def flat_filter(cloud, lidar_z, k=10, thresh=0.2, details=False):
+    """filtered2D of the prefiltering nodelet [REF apps/prefiltering_nodelet.cpp:155-158]: height_filtering (z > lidar z) ->
+    normal_filtering (pcl::NormalEstimation k = 10, |n_z| < 0.2) -> flatten (z := 0).  details=True also returns |n_z| per input point."""
+    cloud = _cloud(cloud)
+    n = len(cloud)
+    out = np.empty((max(n, 1), 4), np.float32)
+    nz = np.zeros(max(n, 1), np.float32)
+    m = lib().orc_flat_filter(cloud if n else np.zeros((1, 4), np.float32), n, float(lidar_z), int(k), float(thresh), out, nz)
+    if details:
+        return out[:m].copy(), nz[:n].copy()
     return out[:m].copy()
 
 
