@@ -283,4 +283,43 @@ class StatisticalOutlierRemoval : public pcl::Filter<pcl::PointXYZ> {
   double std_mul_ = 0.0;
 };
 
+// filtered2D of PrefilteringNodelet::cloud_callback behind pcl::Filter::Ptr: height_filtering -> normal_filtering ->
+// flatten [REF apps/prefiltering_nodelet.cpp:155-158, 166-251] in one engine call (b200reg_flat_filter)
+class FlatFilter : public pcl::Filter<pcl::PointXYZ> {
+ public:
+  using PointCloud = pcl::PointCloud<pcl::PointXYZ>;
+  explicit FlatFilter(int device = 0) : h_(detail::create(B200REG_METHOD_NONE, device)) { this->filter_name_ = "b200reg::FlatFilter"; }
+  ~FlatFilter() override {
+    if (h_) b200reg_destroy(h_);
+  }
+  void setLidarHeight(double lidar_z) { lidar_z_ = lidar_z; }       // lidar_position.z() (:143)
+  void setKSearch(int k) { k_ = k; }                                 // ne.setKSearch(10) (:231)
+  void setNormalThreshold(double t) { thresh_ = t; }                 // normal_filter_thresh = 0.2f (:241)
+  b200reg_handle* handle() { return h_; }
+
+ protected:
+  void applyFilter(PointCloud& output) override {
+    const PointCloud& in = *this->input_;
+    output.header = in.header;
+    output.sensor_origin_ = in.sensor_origin_;
+    output.sensor_orientation_ = in.sensor_orientation_;
+    output.points.resize(in.points.size());
+    size_t n_out = 0;
+    int rc = b200reg_flat_filter(h_, detail::xyz(in), in.points.size(), sizeof(pcl::PointXYZ), lidar_z_, k_, thresh_,
+                                 output.points.empty() ? nullptr : reinterpret_cast<float*>(output.points.data()), output.points.size(), &n_out);
+    if (rc != B200REG_OK) {
+      PCL_ERROR("[b200reg::FlatFilter] %s\n", b200reg_last_error(h_));
+      n_out = 0;
+    }
+    output.points.resize(n_out);
+    output.width = static_cast<uint32_t>(n_out);
+    output.height = 1;
+    output.is_dense = false;  // as flatten() leaves it (:178)
+  }
+  b200reg_handle* h_ = nullptr;
+  double lidar_z_ = 0.0;
+  int k_ = 10;
+  double thresh_ = 0.2;
+};
+
 }  // namespace b200reg

@@ -37,6 +37,12 @@ int main() {
     sor->setStddevMulThresh(1.0);
     outlier_removal_filter = sor;
     (void)outlier_removal_filter;
+    auto flat = std::make_shared<b200reg::FlatFilter>();
+    flat->setLidarHeight(0.0);
+    flat->setKSearch(10);
+    flat->setNormalThreshold(0.2);
+    pcl::Filter<PointT>::Ptr flat_filter = flat;
+    (void)flat_filter;
   } catch (const std::exception& e) {
     std::printf("no engine: %s\n", e.what());
     return 3;
