@@ -5,6 +5,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <algorithm>
+#include <array>
 #include <limits>
 #include <vector>
 #include <string>
@@ -393,6 +395,94 @@ long long orc_flat_filter(const float* in, long long n, double lidar_z, int k, f
       ++o;
     }
   return o;
+}
+
+// ---- MapCloudGenerator::generate [REF src/hdl_graph_slam/map_cloud_generator.cpp:13-49] (the other half) ----
+// Every keyframe cloud transformed by its pose (Matrix4f * Vector4f, w = 1, accumulated column by column without
+// contraction), concatenated; resolution <= 0 returns that cloud, otherwise the occupied voxel centres of a
+// pcl::octree::OctreePointCloud(resolution) in the order getOccupiedVoxelCenters walks them.  PCL 1.8-1.10
+// [UPSTREAM-RECALLED]: points are added in order, non-finite ones skipped; the FIRST point centres a box of one
+// resolution which getKeyBitSize widens to depth 1 (two cells per axis); a later point outside [min, max) re-roots the
+// tree one level up, moving min down by the old side length on every axis where the point did not violate the UPPER
+// bound, until it fits; a key is (unsigned)((p - min) / resolution) with the min of the moment (earlier keys gain the
+// top bit of each such move); the walk is depth-first with child index = x-bit << 2 | y-bit << 1 | z-bit, i.e. ascending
+// Morton order (x most significant); a centre is float((key + 0.5f) * resolution + min).
+// GPU counterpart: not built yet; this restatement and its property tests come first.
+long long orc_map_cloud(const float* clouds, const long long* offsets, long long n_keyframes, const float* poses_colmajor, double resolution, float* out, double* min3_depth) {
+  const long long n = offsets[n_keyframes];
+  std::vector<float> world((size_t)(n > 0 ? n : 1) * 4);
+  for (long long kf = 0; kf < n_keyframes; ++kf) {
+    const float* T = poses_colmajor + 16 * kf;
+    for (long long i = offsets[kf]; i < offsets[kf + 1]; ++i) {
+      const float* p = clouds + 4 * i;
+      float* d = world.data() + 4 * i;
+      for (int r = 0; r < 4; ++r) d[r] = ((T[r] * p[0] + T[4 + r] * p[1]) + T[8 + r] * p[2]) + T[12 + r] * 1.0f;
+    }
+  }
+  if (!(resolution > 0.0)) {
+    std::memcpy(out, world.data(), (size_t)n * 16);
+    return n;
+  }
+  const float min_value = std::numeric_limits<float>::epsilon();
+  double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  bool defined = false;
+  unsigned depth = 0;
+  unsigned long long shift[3] = {0, 0, 0};  // cells the origin has moved down since the first point
+  struct Entry { unsigned long long k[3]; unsigned long long at[3]; };
+  std::vector<Entry> entries;
+  for (long long i = 0; i < n; ++i) {
+    const float* p = world.data() + 4 * i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    while (true) {  // adoptBoundingBoxToPoint
+      bool lo[3], up[3], any = false;
+      for (int a = 0; a < 3; ++a) { lo[a] = p[a] < mn[a]; up[a] = p[a] >= mx[a]; any = any || lo[a] || up[a]; }
+      if (!any && defined) break;
+      if (defined) {
+        double side = static_cast<double>(1ull << depth) * resolution;
+        for (int a = 0; a < 3; ++a)
+          if (!up[a]) { mn[a] -= side; shift[a] += 1ull << depth; }
+        ++depth;
+        side = static_cast<double>(1ull << depth) * resolution - min_value;
+        for (int a = 0; a < 3; ++a) mx[a] = mn[a] + side;
+      } else {
+        for (int a = 0; a < 3; ++a) { mn[a] = p[a] - resolution / 2; mx[a] = p[a] + resolution / 2; }
+        // getKeyBitSize on the empty tree
+        unsigned max_key = 2;
+        for (int a = 0; a < 3; ++a) max_key = std::max(max_key, static_cast<unsigned>(std::ceil((mx[a] - mn[a] - min_value) / resolution)));
+        depth = static_cast<unsigned>(std::ceil(std::log2(static_cast<double>(max_key)) - min_value));
+        const double side = static_cast<double>(1ull << depth) * resolution;
+        for (int a = 0; a < 3; ++a) {
+          const double over = (side - (mx[a] - mn[a])) / 2.0;
+          if (over > min_value) { mn[a] -= over; mx[a] += over; }
+        }
+        defined = true;
+      }
+    }
+    Entry e;
+    for (int a = 0; a < 3; ++a) { e.k[a] = static_cast<unsigned>((p[a] - mn[a]) / resolution); e.at[a] = shift[a]; }
+    entries.push_back(e);
+  }
+  if (min3_depth) { min3_depth[0] = mn[0]; min3_depth[1] = mn[1]; min3_depth[2] = mn[2]; min3_depth[3] = depth; }
+  // final keys, Morton codes (x most significant per level), unique in ascending order
+  std::vector<std::array<unsigned long long, 3>> keys(entries.size());
+  std::vector<std::pair<unsigned __int128, size_t>> order(entries.size());
+  for (size_t j = 0; j < entries.size(); ++j) {
+    unsigned __int128 code = 0;
+    for (int a = 0; a < 3; ++a) keys[j][a] = entries[j].k[a] + (shift[a] - entries[j].at[a]);
+    for (int b = (int)depth - 1; b >= 0; --b)
+      for (int a = 0; a < 3; ++a) code = (code << 1) | ((keys[j][a] >> b) & 1ull);
+    order[j] = {code, j};
+  }
+  std::sort(order.begin(), order.end());
+  long long m = 0;
+  for (size_t j = 0; j < order.size(); ++j) {
+    if (j && order[j].first == order[j - 1].first) continue;
+    const auto& k = keys[order[j].second];
+    for (int a = 0; a < 3; ++a) out[4 * m + a] = static_cast<float>((static_cast<double>(k[a]) + 0.5f) * resolution + mn[a]);
+    out[4 * m + 3] = 1.0f;
+    ++m;
+  }
+  return m;
 }
 
 // ---- linear algebra known-answer hooks -------------------------------------

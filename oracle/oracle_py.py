@@ -65,6 +65,8 @@ def lib():
         L.orc_statistical_outlier_removal.restype = C.c_longlong
         L.orc_flat_filter.argtypes = [f32p, C.c_longlong, C.c_double, C.c_int, C.c_float, f32p, f32p]
         L.orc_flat_filter.restype = C.c_longlong
+        L.orc_map_cloud.argtypes = [f32p, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), C.c_longlong, f32p, C.c_double, f32p, f64p]
+        L.orc_map_cloud.restype = C.c_longlong
         L.orc_sym_eigen3.argtypes = [f64p, f64p, f64p]
         L.orc_inverse3.argtypes = [f64p, f64p]
         L.orc_svd_solve6.argtypes = [f64p, f64p, f64p]
@@ -153,6 +155,22 @@ def flat_filter(cloud, lidar_z, k=10, thresh=0.2, details=False):
     m = lib().orc_flat_filter(cloud if n else np.zeros((1, 4), np.float32), n, float(lidar_z), int(k), float(thresh), out, nz)
     if details:
         return out[:m].copy(), nz[:n].copy()
+    return out[:m].copy()
+
+
+def map_cloud(clouds, poses, resolution, details=False):
+    """MapCloudGenerator::generate [REF src/hdl_graph_slam/map_cloud_generator.cpp:13-49]: keyframe clouds transformed by their
+    4x4 float poses, concatenated, and (resolution > 0) reduced to pcl's occupied octree voxel centres in its own order."""
+    clouds = [_cloud(c) for c in clouds]
+    offsets = np.zeros(len(clouds) + 1, np.int64)
+    offsets[1:] = np.cumsum([len(c) for c in clouds])
+    cat = np.concatenate(clouds) if clouds and offsets[-1] else np.zeros((1, 4), np.float32)
+    T = np.ascontiguousarray(np.stack([np.asarray(p, np.float32).T.reshape(16) for p in poses]) if len(poses) else np.zeros((1, 16), np.float32), np.float32)  # column-major
+    out = np.empty((max(int(offsets[-1]), 1), 4), np.float32)
+    info = np.zeros(4, np.float64)
+    m = lib().orc_map_cloud(np.ascontiguousarray(cat), offsets, len(clouds), T, float(resolution), out, info)
+    if details:
+        return out[:m].copy(), dict(min=info[:3].copy(), depth=int(info[3]))
     return out[:m].copy()
 
 
