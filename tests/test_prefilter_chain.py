@@ -112,6 +112,42 @@ def test_oracle_statistical_outlier_removal_follows_its_definition(oracle):
     assert len(got) == 64 and det["stddev"] == 0.0 and det["threshold"] == 0.5
 
 
+def test_prefilter_mirror_reads_the_reference_parameters(monkeypatch):
+    """initialize_params [REF apps/prefiltering_nodelet.cpp:55-102] on recorders instead of engine handles: parameter names,
+    the nodelet's defaults for the chosen methods, and its console lines."""
+    import io
+    import delta_graph_slam_b200.odometry as odo
+    calls = []
+
+    class Rec:
+        def __init__(self, name):
+            self._name = name
+            self._reg = object()
+
+        def __getattr__(self, attr):
+            return lambda *a, **k: calls.append((self._name, attr) + a)
+
+    monkeypatch.setattr(odo, "VoxelGrid", lambda device=0: Rec("vg"))
+    monkeypatch.setattr(odo, "StatisticalOutlierRemoval", lambda device=0, registration=None: Rec("sor"))
+    monkeypatch.setattr(odo, "RadiusOutlierRemoval", lambda device=0, registration=None: Rec("ror"))
+    out = io.StringIO()
+    odo.Prefilter(dict(outlier_removal_method="STATISTICAL", use_distance_filter=True), out=out)
+    assert out.getvalue().splitlines() == ["downsample: VOXELGRID 0.1", "outlier_removal: STATISTICAL 20 - 1"]
+    assert calls == [("vg", "setLeafSize", 0.1, 0.1, 0.1), ("sor", "setMeanK", 20), ("sor", "setStddevMulThresh", 1.0), ("vg", "setDistanceFilter", True, 1.0, 100.0)]
+    calls.clear()
+    out = io.StringIO()
+    odo.Prefilter(dict(LAUNCH, statistical_mean_k=30), out=out)  # the launch file: RADIUS 0.5 - 2, gate 0.1 .. 100
+    assert out.getvalue().splitlines() == ["downsample: VOXELGRID 0.1", "outlier_removal: RADIUS 0.5 - 2"]
+    assert calls == [("vg", "setLeafSize", 0.1, 0.1, 0.1), ("ror", "setRadiusSearch", 0.5), ("ror", "setMinNeighborsInRadius", 2), ("vg", "setDistanceFilter", True, 0.1, 100.0)]
+    calls.clear()
+    out = io.StringIO()
+    odo.Prefilter(dict(downsample_method="VOXELGRID", downsample_resolution=0.25, outlier_removal_method="STATISTICAL", statistical_mean_k=12, statistical_stddev=2.5), out=out)
+    assert out.getvalue().splitlines() == ["downsample: VOXELGRID 0.25", "outlier_removal: STATISTICAL 12 - 2.5"]
+    assert ("sor", "setMeanK", 12) in calls and ("sor", "setStddevMulThresh", 2.5) in calls
+    with pytest.raises(NotImplementedError):
+        odo.Prefilter(dict(downsample_method="APPROX_VOXELGRID"), out=io.StringIO())
+
+
 @pytest.mark.gpu
 def test_fused_distance_filter_matches_filter_then_voxelgrid(oracle):
     import delta_graph_slam_b200 as eng
