@@ -42,7 +42,11 @@ ODOM_PARAMS = dict(  # launch/delta_graph_slam.launch:50-69 (NDT_OMP instead of 
     keyframe_delta_trans=1.0, keyframe_delta_angle=1.0, keyframe_delta_time=10000.0, downsample_method="NONE",
     registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64,
 )
-PREFILTER_PARAMS = dict(downsample_method="VOXELGRID", downsample_resolution=0.1)
+# prefiltering nodelet as launch/delta_graph_slam.launch:31-36 sets it: distance gate 0.1 .. 100 m, VoxelGrid 0.1 m; the
+# outlier filter (RADIUS in the launch file, STATISTICAL by default) is switched off for the headline — BASELINE
+# configs[1] names down-sampling + NDT — and measured in tools/prefilter_probe.py
+PREFILTER_PARAMS = dict(downsample_method="VOXELGRID", downsample_resolution=0.1, distance_near_thresh=0.1, distance_far_thresh=100.0, outlier_removal_method="NONE")
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal CUDA-core FMA rate at the maximum SM clock (no measured figure in MEASURED_PEAKS.json)
 GICP_ODOM_PARAMS = dict(  # BASELINE configs[2]: FAST_GICP with the factory's code defaults [REF src/hdl_graph_slam/registrations.cpp:27-36]
     keyframe_delta_trans=1.0, keyframe_delta_angle=1.0, keyframe_delta_time=10000.0, downsample_method="NONE",
     registration_method="FAST_GICP", reg_transformation_epsilon=0.01, reg_maximum_iterations=64, reg_max_correspondence_distance=2.5, reg_correspondence_randomness=20,
@@ -50,6 +54,33 @@ GICP_ODOM_PARAMS = dict(  # BASELINE configs[2]: FAST_GICP with the factory's co
 LOOP_PARAMS = dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64)
 DEVNULL = open(os.devnull, "w")
 DBL_MAX = float(np.finfo(np.float64).max)
+
+
+def odometry_config(frames, is_ndt, stride=1):
+    """The workload description shared by both arms (`--impl b200` and `--impl reference` print the same dict)."""
+    label = "NDT" if is_ndt else "FAST_GICP"
+    return {"workload": f"scan_matching_odometry: {frames} consecutive synthetic KITTI-like HDL-64 scans (street_v1 scene, {0.5 * stride:g} m/frame at 10 Hz; SURVEY cfg 2 names 1.0 m/frame, see odometry_1m_per_frame), "
+                        f"distance gate 0.1-100 m + VoxelGrid 0.1 m + {label} keyframe odometry (BASELINE configs[{1 if is_ndt else 2}])",
+            "frames_per_sequence": frames, "metres_per_frame": 0.5 * stride, "keyframe_delta": "1.0 m / 1.0 rad / 10000 s (launch/delta_graph_slam.launch:50-52)",
+            "registration": "NDT_OMP DIRECT7 res 1.0 eps 0.01 max_iter 64" if is_ndt else "FAST_GICP k 20, max corr 2.5 m, eps 0.01, max_iter 64, LM, PLANE",
+            "l2": f"a pass over the sequence streams {frames} distinct raw scans ({frames * 133312 * 16 / 1e9:.1f} GB): inputs larger than L2",
+            "multi_gpu": "independent sequence per GPU (replicas only)"}
+
+
+def loop_config(n_targets, n_candidates, dense):
+    n_pairs = n_targets * n_candidates
+    return {"workload": (f"dense-scan stress: 128-beam 1M-ray scans, VoxelGrid 0.1 m + {n_targets} x {n_candidates} = {n_pairs} NDT DIRECT1 + getFitnessScore pairs (BASELINE configs[4])" if dense else
+                         f"LoopDetector batch: {n_targets} new keyframes x {n_candidates} candidates = {n_pairs} NDT DIRECT7 + getFitnessScore pairs (BASELINE configs[3])"),
+            "pairs_per_batch": n_pairs, "registration": f"NDT_OMP {'DIRECT1' if dense else 'DIRECT7'} res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
+            "sharding": "whole targets per rank, one all-gather of 104-byte result records"}
+
+
+def host_threads():
+    """Host cores this process may use — NOT what OMP_NUM_THREADS says: torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def load_peaks():
@@ -124,11 +155,14 @@ def run_sequence(pre, odo, clouds, out_buf=None):
 
 
 class OraclePrefilter:
+    """distance_filter -> pcl::VoxelGrid of the prefiltering nodelet, CPU oracle [REF apps/prefiltering_nodelet.cpp:150-151]."""
+
     def __init__(self, oracle):
         self.oracle = oracle
 
     def downsample(self, cloud):
-        return self.oracle.voxelgrid(cloud, PREFILTER_PARAMS["downsample_resolution"], is_dense=False)["out"]
+        gated = self.oracle.distance_filter(cloud, PREFILTER_PARAMS["distance_near_thresh"], PREFILTER_PARAMS["distance_far_thresh"])
+        return self.oracle.voxelgrid(gated, PREFILTER_PARAMS["downsample_resolution"], is_dense=False)["out"]
 
 
 def oracle_odometry(oracle, threads=0, params=None):
@@ -143,18 +177,45 @@ def oracle_odometry(oracle, threads=0, params=None):
     return OraclePrefilter(oracle), ScanMatchingOdometry(params, registration=reg, out=DEVNULL)
 
 
+def run_sequence_two_nodelets(pre, odo, clouds, stats=None):
+    """The CPU arm as the reference runs it: the prefiltering nodelet and the scan-matching nodelet are two nodelets of
+    one multi-threaded manager joined by a topic, so scan k+1 is filtered (one thread: pcl::VoxelGrid is serial) while
+    scan k is matched (OpenMP on all cores).  The oracle's C calls release the GIL."""
+    from concurrent.futures import ThreadPoolExecutor
+    poses = []
+    if not clouds:
+        return poses
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(pre.downsample, clouds[0])
+        for k in range(len(clouds)):
+            filtered = nxt.result()
+            if k + 1 < len(clouds):
+                nxt = pool.submit(pre.downsample, clouds[k + 1])
+            was_first = odo.keyframe is None
+            poses.append(odo.matching(0.1 * k, filtered))
+            if stats is not None and not was_first:
+                info = odo.registration.info()
+                stats["evaluations"] += int(info[1])
+                stats["iterations"] += odo.registration.getFinalNumIteration()
+                stats["registrations"] += 1
+    return poses
+
+
 def time_oracle_odometry(host_clouds, frames, params=None):
     from oracle import oracle_py as oracle
+    oracle.lib().orc_set_num_threads(host_threads())
     pre, odo = oracle_odometry(oracle, params=params)
+    stats = dict(evaluations=0, iterations=0, registrations=0)
     t0 = time.perf_counter()
-    run_sequence(pre, odo, host_clouds[:frames])
+    poses = run_sequence_two_nodelets(pre, odo, host_clouds[:frames], stats)
     dt = time.perf_counter() - t0
-    return (frames - 1) / dt, oracle.lib().orc_max_threads(), dt
+    return (frames - 1) / dt, oracle.lib().orc_max_threads(), dt, poses, stats
 
 
-def oracle_loop_pairs(oracle, clouds, pairs):
+def oracle_loop_pairs(oracle, clouds, pairs, results=None):
     """The reference's serial candidate loop on the CPU: setInputTarget once per target, then per
-    candidate setInputSource + align + getFitnessScore.  Returns seconds."""
+    candidate setInputSource + align + getFitnessScore.  Returns seconds; `results` (a list) receives
+    (transform, fitness, converged, iterations, evaluations) per pair."""
     reg = oracle.Registration(oracle.NDT, resolution=LOOP_PARAMS["reg_resolution"], nn_search=oracle.DIRECT7, trans_eps=LOOP_PARAMS["reg_transformation_epsilon"],
                               max_iter=LOOP_PARAMS["reg_maximum_iterations"])
     t0 = time.perf_counter()
@@ -165,8 +226,35 @@ def oracle_loop_pairs(oracle, clouds, pairs):
             last = int(p["target_id"])
         reg.setInputSource(clouds[int(p["source_id"])])
         reg.align(np.array(p["guess"], np.float32).reshape(4, 4).T)
-        reg.getFitnessScore(DBL_MAX)
+        fit = reg.getFitnessScore(DBL_MAX)
+        if results is not None:
+            results.append((reg.getFinalTransformation(), fit, reg.hasConverged(), reg.getFinalNumIteration(), int(reg.info()[1])))
     return time.perf_counter() - t0
+
+
+def loop_parity_vs_oracle(pairs_sub, engine_records, oracle_results, fitness_at_oracle_transform=None):
+    """Engine result records against the oracle's serial loop on the same pairs.  A pair whose iteration / evaluation counts
+    differ has left the oracle's optimisation path (every pass is evaluated at a float32-rounded transform, so a last-bit
+    difference can flip a rounding and grow); those are counted, not hidden."""
+    out = dict(pairs=len(pairs_sub), max_dt=0.0, max_dr=0.0, max_rel_fitness=0.0, max_rel_fitness_own_transform=0.0, path_diverged=0, outside_tolerance=0, converged_mismatch=0, max_dt_diverged=0.0)
+    for i, (rec, (T, fit, conv, iters, evals)) in enumerate(zip(engine_records, oracle_results)):
+        Te = np.array(rec["transformation"], np.float32).reshape(4, 4).T
+        dt, dr = transform_deltas(Te, T)
+        rel_own = abs(float(rec["fitness"]) - fit) / abs(fit) if fit else 0.0
+        # the fitness bar applies at the same transform (the engine's getFitnessScore evaluated at the oracle's result)
+        rel = abs(float(fitness_at_oracle_transform[i]) - fit) / abs(fit) if (fitness_at_oracle_transform is not None and fit) else rel_own
+        out["max_rel_fitness_own_transform"] = max(out["max_rel_fitness_own_transform"], rel_own)
+        same_path = int(rec["iterations"]) == iters and int(rec["evaluations"]) == evals
+        out["converged_mismatch"] += int(bool(rec["converged"]) != bool(conv))
+        if not same_path:
+            out["path_diverged"] += 1
+            out["max_dt_diverged"] = max(out["max_dt_diverged"], dt)
+        if dt >= 1e-4 or dr >= 1e-4 or rel >= 1e-5:
+            out["outside_tolerance"] += 1
+        if same_path:
+            out["max_dt"], out["max_dr"], out["max_rel_fitness"] = max(out["max_dt"], dt), max(out["max_dr"], dr), max(out["max_rel_fitness"], rel)
+    out["note"] = "max_* over the pairs on the oracle's path; tolerance 1e-4 m / 1e-4 rad / 1e-5 relative fitness"
+    return out
 
 
 def reference_arm(args, rank, emit=print):
@@ -175,7 +263,9 @@ def reference_arm(args, rank, emit=print):
     if rank != 0:
         return 0
     from oracle import oracle_py as oracle
+    oracle.lib().orc_set_num_threads(host_threads())  # all host cores, whatever OMP_NUM_THREADS torchrun handed down
     cores = oracle.lib().orc_max_threads()
+    extra = {}
     if args.workload == "loop":
         from delta_graph_slam_b200.loop_batch import make_pairs
         from delta_graph_slam_b200.synth.loop_scenario import loop_scenario
@@ -187,33 +277,41 @@ def reference_arm(args, rank, emit=print):
         dt = sum(oracle_loop_pairs(oracle, clouds, pairs) for _ in range(args.steps))
         value = args.steps * len(pairs) / dt
         metric, unit = "loop pairs/sec (NDT + fitness)", "pairs/s"
-        sample = f"{len(pairs)} candidate pairs of one new keyframe per step (setInputTarget once, then align + getFitnessScore per candidate), oracle restatement of ndt_omp + pcl::Registration"
-        cfg = {"workload": "LoopDetector batch: NDT DIRECT7 + getFitnessScore candidate pairs (BASELINE configs[3])", "pairs_per_step": len(pairs)}
+        sample = f"{len(pairs)} candidate pairs of one new keyframe per step (setInputTarget once, then align + getFitnessScore per candidate), oracle restatement of ndt_omp + pcl::Registration, OpenMP on {cores} threads"
+        cfg = loop_config(args.loop_targets, args.loop_candidates, dense=False)
     else:
-        n = args.ref_frames
-        clouds = [oracle.synth_scan(oracle.synth_traj(k), noise_seed=1000 + k) for k in range(n)]
+        # a window from the middle of the sequence (the sequence itself is the b200 arm's: same scene, seeds, poses)
+        n, start = args.ref_frames, args.ref_start
+        clouds = [oracle.synth_scan(oracle.synth_traj(start + k), noise_seed=1000 + start + k) for k in range(n)]
         pre, _ = oracle_odometry(oracle)
+        stats = dict(evaluations=0, iterations=0, registrations=0)
 
-        def one_step():
+        def one_step(st=None):
             _, odo = oracle_odometry(oracle)
-            run_sequence(pre, odo, clouds)
+            run_sequence_two_nodelets(pre, odo, clouds, st)
+            return odo.num_keyframes
         for _ in range(args.warmup):
             one_step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            one_step()
+            keyframes = one_step(stats)
         dt = time.perf_counter() - t0
         value = args.steps * (n - 1) / dt
         metric, unit = "scan registrations/sec (NDT keyframe odometry)", "registrations/s"
-        sample = f"first {n} frames of the sequence per step (VoxelGrid 0.1 + NDT DIRECT7 keyframe odometry), oracle restatement of pcl::VoxelGrid + ndt_omp"
-        cfg = {"workload": "scan_matching_odometry: synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + NDT DIRECT7 keyframe odometry (BASELINE configs[1])", "frames_per_step": n,
-               "registration": "NDT_OMP DIRECT7 res 1.0 eps 0.01 max_iter 64"}
-    emit(json.dumps({
+        sample = (f"frames {start}..{start + n - 1} of the same {args.frames}-frame sequence per step ({n - 1} registrations, {keyframes} keyframes; the window's first scan becomes the keyframe, "
+                  f"so its first registration starts from an identity guess exactly like every registration that follows a keyframe switch): distance gate + pcl::VoxelGrid 0.1 m on one thread "
+                  f"overlapped with ndt_omp DIRECT7 keyframe odometry on {cores} OpenMP threads (the reference's two nodelets), oracle restatement")
+        cfg = odometry_config(args.frames, True)
+        extra = {"stats": {"evaluations_per_registration": stats["evaluations"] / max(stats["registrations"], 1), "iterations_per_registration": stats["iterations"] / max(stats["registrations"], 1),
+                           "keyframes_per_window": keyframes, "note": "the CPU runs one pass over the source per evaluation (computeDerivatives / computeHessian)"}}
+    line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak" if args.workload == "odometry" else "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    line.update(extra)
+    emit(json.dumps(line))
     return 0
 
 
@@ -269,7 +367,57 @@ class Ctx:
         return sec, wall, stats
 
 
-def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, label="NDT", cpu_frames=None):
+def transform_deltas(Ta, Tb):
+    """(max |dt| in metres, rotation angle in radians) between two 4x4 transforms (skew part: resolves angles far below float32 trace noise)."""
+    Ta, Tb = np.asarray(Ta, np.float64), np.asarray(Tb, np.float64)
+    R = Ta[:3, :3].T @ Tb[:3, :3]
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2.0
+    return float(np.max(np.abs(Ta[:3, 3] - Tb[:3, 3]))), float(np.arctan2(np.linalg.norm(w), (np.trace(R) - 1.0) / 2.0))
+
+
+def odometry_parity_vs_oracle(eng, host_clouds, frames, odom_params, dev, filter_sms):
+    """The engine against the CPU oracle on the first `frames` scans of the bench sequence, frame by frame through the same
+    host state machine: frame-to-keyframe transform, accumulated pose, iteration / evaluation counts, getFitnessScore.
+    Untimed; the same comparison at full length is tests/test_gpu_odometry_sequence.py."""
+    from oracle import oracle_py as oracle
+    pre_o, odo_o = oracle_odometry(oracle, params=odom_params)
+    pre_e = eng.Prefilter(PREFILTER_PARAMS, device=dev, out=DEVNULL)
+    odo_e = eng.ScanMatchingOdometry(odom_params, device=dev, out=DEVNULL)
+    if filter_sms:
+        pre_e.setSmBudget(filter_sms)
+        odo_e.registration.setSmBudget(148 - filter_sms)
+    out = dict(frames=frames, max_dt=0.0, max_dr=0.0, max_dt_odom=0.0, max_dr_odom=0.0, max_rel_fitness=0.0, max_rel_fitness_own_transform=0.0, path_diverged=0, voxelgrid_mismatches=0, keyframes_equal=True,
+               tolerance="1e-4 m / 1e-4 rad; fitness 1e-5 relative at the same (the oracle's) final transform — at each side's own final transform a 3e-5 m difference already moves the mean squared NN distance by ~1e-4 relative (north_star bars)")
+    for k in range(frames):
+        fo, fe = pre_o.downsample(host_clouds[k]), pre_e.downsample(host_clouds[k])
+        if fo.shape != fe.shape or not np.array_equal(np.asarray(fo).view(np.uint32), np.asarray(fe).view(np.uint32)):
+            out["voxelgrid_mismatches"] += 1
+        first = odo_o.keyframe is None
+        po, pe = odo_o.matching(0.1 * k, fo), odo_e.matching(0.1 * k, fe)
+        if first:
+            continue
+        ro, re_ = odo_o.registration, odo_e.registration.getResult()
+        if odom_params["registration_method"] == "NDT_OMP":
+            if re_["iterations"] != ro.getFinalNumIteration() or re_["evaluations"] != int(ro.info()[1]):
+                out["path_diverged"] += 1
+        elif re_["iterations"] != ro.getFinalNumIteration():
+            out["path_diverged"] += 1
+        dt, dr = transform_deltas(re_["transformation"], ro.getFinalTransformation())
+        dto, dro = transform_deltas(pe, po)
+        f_o, f_e = ro.getFitnessScore(), odo_e.registration.getFitnessScore()
+        f_same = odo_e.registration.calcFitnessScore(ro.getFinalTransformation())
+        out["max_dt"], out["max_dr"] = max(out["max_dt"], dt), max(out["max_dr"], dr)
+        out["max_dt_odom"], out["max_dr_odom"] = max(out["max_dt_odom"], dto), max(out["max_dr_odom"], dro)
+        out["max_rel_fitness"] = max(out["max_rel_fitness"], abs(f_same - f_o) / abs(f_o))
+        out["max_rel_fitness_own_transform"] = max(out["max_rel_fitness_own_transform"], abs(f_e - f_o) / abs(f_o))
+    out["keyframes_equal"] = bool(odo_o.num_keyframes == odo_e.num_keyframes)
+    out["keyframes"] = int(odo_e.num_keyframes)
+    out["within_tolerance"] = bool(out["max_dt"] < 1e-4 and out["max_dr"] < 1e-4 and out["max_dt_odom"] < 1e-4 and out["max_dr_odom"] < 1e-4 and out["max_rel_fitness"] < 1e-5 and
+                                   out["voxelgrid_mismatches"] == 0 and out["keyframes_equal"])
+    return out
+
+
+def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, label="NDT", cpu_frames=None, stride=1, pageable_leg=True):
     import delta_graph_slam_b200 as eng
     from delta_graph_slam_b200 import synth
     torch, args, dev, rank, world = ctx.torch, ctx.args, ctx.dev, ctx.rank, ctx.world
@@ -285,8 +433,8 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     d_raw = torch.empty((F, rays, 4), dtype=torch.float32, device=f"cuda:{dev}")
     counts = []
     for k in range(F):
-        P = synth.traj_kitti_like(k + 5000 * rank)
-        counts.append(synth.scan_to_device(d_raw[k].data_ptr(), P, synth.HDL64, scene_seed=1, noise_seed=1000 + k + 5000 * rank, device=dev))
+        P = synth.traj_kitti_like(stride * k + 5000 * rank)
+        counts.append(synth.scan_to_device(d_raw[k].data_ptr(), P, synth.HDL64, scene_seed=1, noise_seed=1000 + stride * k + 5000 * rank, device=dev))
     h_raw = torch.empty((F, rays, 4), dtype=torch.float32, pin_memory=True)
     h_raw.copy_(d_raw)
     torch.cuda.synchronize()
@@ -305,9 +453,10 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     # The front end runs as the reference runs it: prefiltering and scan matching are two nodelets
     # joined by a topic, so the filter of scan k+1 is in flight while scan k is matched (eng.FrontEnd).
     # The filter handle's persistent kernel is given args.filter_sms SMs, the registration the rest.
-    def new_front_end(bufs):
+    def new_front_end(bufs, aligned_out=None):
         pre, odo = new_pipeline()
         odo.prepare_promotion = bool(args.filter_sms) and args.prepare
+        odo.aligned_out = aligned_out
         return eng.FrontEnd(pre, odo, bufs, filter_sms=args.filter_sms), pre, odo
 
     # ---- device-resident leg (value) + roofline of the align kernel
@@ -316,7 +465,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
 
     def step_device(i):
         odo_d.keyframe = None  # restart the sequence; engine buffers stay allocated
-        acc = dict(alg_bytes=0, evals=0, hits=0)
+        acc = dict(alg_bytes=0, evals=0, hits=0, ref_evals=0, points=0)
 
         def on_frame(k, filtered):
             if k > 0:
@@ -327,9 +476,12 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                 # (GICP outer iteration) — approximated with hits = linearize correspondences
                 acc["alg_bytes"] += (16 * filtered.n * r["passes"] + 48 * r["hits"]) if is_ndt else (16 * filtered.n * r["passes"] + 160 * r["hits"])
                 acc["evals"] += r["passes"]
+                acc["ref_evals"] += r["evaluations"]
                 acc["hits"] += r["hits"]
+                acc["points"] += filtered.n * r["passes"]
         fe_d.run(dev_clouds, on_frame=on_frame)
-        return dict(alg_bytes=acc["alg_bytes"], evals=acc["evals"], hits=acc["hits"], keyframes=odo_d.num_keyframes)
+        acc["keyframes"] = odo_d.num_keyframes
+        return acc
 
     sampler = ClockSampler(dev)
     with sampler:
@@ -345,26 +497,51 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
     peak, peak_kind = load_peaks()
     launches_timed = (c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)
+    passes_per_reg = st_d[-1]["evals"] / regs_per_step
+    # FP32 view: ~30 flops per point per pass + ~400 per (point, voxel) hit for a Hessian pass that
+    # exploits the sparsity of the point Jacobian / Hessian (upstream's dense 4x6 / 24x6 form is ~1100)
+    flops_per_launch = (30.0 * st_d[-1]["points"] + 400.0 * st_d[-1]["hits"]) / regs_per_step
+    fp32_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
 
-    # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out
-    # caller-owned output clouds of the filter (pcl::Filter::filter(output)), page-locked; three in
-    # rotation because the odometry keeps the keyframe's cloud while the next scans are filtered
-    h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
-    fe_h, pre_h, odo_h = new_front_end([h_out[j] for j in range(3)])
+    # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out.
+    # Caller-owned output clouds of the filter (pcl::Filter::filter(output)), three in rotation because the odometry
+    # keeps the keyframe's cloud while the next scans are filtered, and the `aligned` cloud that
+    # registration->align(*aligned, guess) always fills [REF apps/scan_matching_odometry_nodelet.cpp:217-218]
+    def make_host_leg(pinned):
+        if pinned:
+            h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
+            h_al = torch.empty((rays, 4), dtype=torch.float32, pin_memory=True).numpy()
+            inputs = host_clouds
+        else:
+            h_out = np.empty((3, rays, 4), np.float32)
+            h_al = np.empty((rays, 4), np.float32)
+            inputs = [np.array(c) for c in host_clouds]  # pageable copies of the raw scans (what a pcl::PointCloud holds)
+        fe_h, pre_h, odo_h = new_front_end([h_out[j] for j in range(3)], aligned_out=h_al)
 
-    def step_host(i):
-        odo_h.keyframe = None
-        acc = dict(h2d=0, d2h=0)
+        def step_host(i):
+            odo_h.keyframe = None
+            acc = dict(h2d=0, d2h=0)
 
-        def on_frame(k, filtered):
-            # raw scan up, filtered cloud down (the /filtered_points message), filtered cloud up again
-            # (setInputSource of the odometry nodelet), result record down
-            acc["h2d"] += host_clouds[k].nbytes + filtered.nbytes
-            acc["d2h"] += filtered.nbytes + 128
-        fe_h.run(host_clouds, on_frame=on_frame)
-        return acc
+            def on_frame(k, filtered):
+                # raw scan up, filtered cloud down (the /filtered_points message), filtered cloud up again
+                # (setInputSource of the odometry nodelet), aligned cloud + result record down
+                acc["h2d"] += inputs[k].nbytes + filtered.nbytes
+                acc["d2h"] += filtered.nbytes + (filtered.nbytes + 128 if k > 0 else 0)
+            fe_h.run(inputs, on_frame=on_frame)
+            return acc
+        return step_host, odo_h, h_out
+    step_host, odo_h, h_out = make_host_leg(True)
     sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), steps, warmup)
     e2e_value = world * steps * regs_per_step / sec_h
+    e2e_pageable = None
+    if pageable_leg:
+        step_pg, odo_pg, _ = make_host_leg(False)
+        sec_p, wall_p, st_p = ctx.timed(step_pg, odo_pg.registration.stream(), max(1, min(steps, 5)), 2)
+        # wall clock, not stream time: with pageable buffers the library's staging memcpys run on the host between stream operations
+        e2e_pageable = {"value": world * max(1, min(steps, 5)) * regs_per_step / wall_p, "unit": "registrations/s", "ms_per_step": 1e3 * wall_p / max(1, min(steps, 5)),
+                        "h2d_bytes_per_step": st_p[-1]["h2d"], "d2h_bytes_per_step": st_p[-1]["d2h"],
+                        "note": "same calls with PAGEABLE caller clouds in and out (raw scan, filtered cloud, aligned cloud): the library stages through its own pinned buffers; wall clock"}
+        del step_pg, odo_pg
 
     # ---- parity of the two legs (same inputs -> same poses) and odometry sanity vs ground truth
     nchk = min(50, F)
@@ -381,38 +558,48 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     poses_seq = run_sequence(pre_s, odo_s, dev_clouds[:nchk], out_buf=ds_buf)
     pipeline_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_seq))
     P0 = synth.traj_kitti_like(5000 * rank)
-    gt = np.linalg.inv(P0) @ synth.traj_kitti_like(nchk - 1 + 5000 * rank)
+    gt = np.linalg.inv(P0) @ synth.traj_kitti_like(stride * (nchk - 1) + 5000 * rank)
     drift = float(np.linalg.norm(poses_dev[nchk - 1][:3, 3] - gt[:3, 3]))
 
-    # ---- CPU baseline (rank 0, N = 1): the oracle on the first frames of the same sequence
-    cpu = None
+    # ---- CPU baseline (rank 0, N = 1): the oracle on the first frames of the same sequence, and the engine checked against it
+    cpu, parity = None, None
     if rank == 0 and world == 1 and cpu_frames > 1:
-        v, cores, dt = time_oracle_odometry(host_clouds, min(cpu_frames, F), odom_params)
+        nf = min(cpu_frames, F)
+        v, cores, dt, poses_cpu, cpu_stats = time_oracle_odometry(host_clouds, nf, odom_params)
         cpu = {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
-               "sample": f"first {min(cpu_frames, F)} frames of the same sequence ({dt:.1f} s): oracle restatement of pcl::VoxelGrid 0.1 m + {'ndt_omp DIRECT7' if is_ndt else 'fast_gicp'} keyframe odometry, OpenMP on all host cores"}
+               "sample": f"first {nf} frames of the same sequence ({dt:.1f} s): oracle restatement of distance gate + pcl::VoxelGrid 0.1 m (one thread) overlapped with {'ndt_omp DIRECT7' if is_ndt else 'fast_gicp'} keyframe odometry (OpenMP on all host cores), as the reference's two nodelets",
+               "evaluations_per_registration": cpu_stats["evaluations"] / max(cpu_stats["registrations"], 1)}
+        parity = odometry_parity_vs_oracle(eng, host_clouds, nf, odom_params, dev, args.filter_sms)
+        # the pipelined device leg's poses against the oracle's timed run (same frames)
+        worst = [transform_deltas(a, b) for a, b in zip(poses_dev[:nf], poses_cpu[:nf])]
+        parity["pipelined_leg_max_dt_odom"], parity["pipelined_leg_max_dr_odom"] = max(w[0] for w in worst), max(w[1] for w in worst)
 
+    cfg = odometry_config(F, is_ndt, stride)
     out = {
         "metric": f"scan registrations/sec ({label} keyframe odometry)", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * sec_d / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 per hit, f64 sums" if is_ndt else "f64 (f32 points and NN search)",
-        "data": "synthetic",
-        "config": {"workload": f"scan_matching_odometry: {F} consecutive synthetic KITTI-like HDL-64 scans, VoxelGrid 0.1 m + {label} keyframe odometry (BASELINE configs[{1 if is_ndt else 2}])",
-                   "frames_per_step": F, "points_per_scan": int(np.mean(counts)),
-                   "registration": "NDT_OMP-equivalent DIRECT7 res 1.0 eps 0.01 max_iter 64" if is_ndt else "FAST_GICP-equivalent k 20, max corr 2.5 m, eps 0.01, max_iter 64, LM, PLANE",
-                   "l2": f"each step streams {F} distinct scans ({F * rays * 16 / 1e9:.1f} GB) through the engine: inputs larger than L2", "multi_gpu": "independent sequence per GPU (replicas only)",
-                   "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms - (16 if args.prepare else 0)} SMs, registration {148 - args.filter_sms} SMs{', 16 SMs for the NDT grid of a predicted next keyframe built during its own registration' if args.prepare else ''}" if args.filter_sms else "sequential: filter, then match",
-                   "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": st_d[-1]["evals"] / regs_per_step},
+        "data": "synthetic", "config": cfg,
+        "stats": {"points_per_scan": int(np.mean(counts)), "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": passes_per_reg,
+                  "evaluations_per_registration": st_d[-1]["ref_evals"] / regs_per_step,
+                  "note": "evaluations = computeDerivatives + computeHessian calls of the reference's algorithm; passes = sweeps over the source the device ran (a closing computeHessian rides in the last trial pass)",
+                  "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms - (16 if args.prepare else 0)} SMs, registration {148 - args.filter_sms} SMs{', 16 SMs for the NDT grid of a predicted next keyframe built during its own registration' if args.prepare else ''}" if args.filter_sms else "sequential: filter, then match"},
         "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
-                "wall_ms_per_step": 1e3 * wall_h / steps},
+                "wall_ms_per_step": 1e3 * wall_h / steps, "note": "page-locked caller clouds; per frame raw scan H2D, filtered cloud D2H + H2D, aligned cloud + result D2H"},
+        "e2e_pageable": e2e_pageable,
         "gpu_launches": int(launches_timed),
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                      "traffic": load_traffic("k_ndt_align_single" if is_ndt else "k_gicp_align"), "traffic_unit": "DRAM bytes per launch (ncu --set full capture of one registration of this workload)",
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms, "launches": int(n_al),
                      "share_of_step": align_ms / max(n_al, 1) * regs_per_step / (1e3 * sec_d / steps),
                      "note": "working set (source cloud + staged voxel grid) is L2/SMEM resident, so DRAM traffic is far below the algorithmic bytes; the kernel is latency / issue bound, see DESIGN.md"},
+        "roofline_fp32": {"bound": "fp32 CUDA cores", "achieved": fp32_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fp32_tflops / FP32_PEAK_TFLOPS, "peak_kind": "nominal: 148 SM x 128 lanes x 2 x 1.965 GHz",
+                          "algorithmic_flops_per_launch": flops_per_launch, "definition": "30 flops per point per pass + 400 per (point, voxel) hit (SURVEY.md 8d, sparsity-exploiting Hessian pass)"} if is_ndt else None,
+        "latency_model": {"passes_per_registration": passes_per_reg, "us_per_pass": 1e3 * avg_launch_ms / max(passes_per_reg, 1e-9), "us_per_registration": 1e3 * avg_launch_ms,
+                          "note": "a registration is a chain of dependent passes (each: point sweep, reduction across the SMs, optimiser step); the per-pass latency, not bandwidth, sets the kernel time — per-phase split in profiles/"},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "pipelined_equals_sequential_first_frames": bool(pipeline_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
-                   "wall_ms_per_step": 1e3 * wall_d / steps},
+                   "wall_ms_per_step": 1e3 * wall_d / steps, "parity_vs_oracle": parity},
     }
     del d_raw, h_raw
     torch.cuda.empty_cache()
@@ -529,33 +716,49 @@ def bench_loop(ctx, steps, warmup, dense=False):
         err_t.append(float(np.max(np.abs(T[:3, 3] - rel[:3, 3]))))
     err_t = np.array(err_t)
 
-    cpu = None
-    if rank == 0 and world == 1 and args.loop_cpu_pairs > 0 and not dense:
+    cpu, parity = None, None
+    if rank == 0 and args.loop_cpu_pairs > 0 and not dense:
         from oracle import oracle_py as oracle
-        k = min(args.loop_cpu_pairs, args.loop_candidates)
-        sub = pairs[:k]
-        clouds = {int(c): np.array(host_cloud[int(c)]) for c in set(sub["target_id"].tolist()) | set(sub["source_id"].tolist())}
-        dt = oracle_loop_pairs(oracle, clouds, sub)
-        cpu = {"value": k / dt, "unit": "pairs/s", "cores": oracle.lib().orc_max_threads(), "kind": "port",
-               "sample": f"first {k} pairs of the same batch ({dt:.1f} s): setInputTarget once, then align + getFitnessScore per candidate; oracle restatement of ndt_omp + pcl::Registration, OpenMP on all host cores"}
+        oracle.lib().orc_set_num_threads(host_threads())
+        if world == 1:
+            k = min(args.loop_cpu_pairs, args.loop_candidates)
+            sub = pairs[:k]
+            clouds = {int(c): np.array(host_cloud[int(c)]) for c in set(sub["target_id"].tolist()) | set(sub["source_id"].tolist())}
+            got = []
+            dt = oracle_loop_pairs(oracle, clouds, sub, got)
+            cpu = {"value": k / dt, "unit": "pairs/s", "cores": oracle.lib().orc_max_threads(), "kind": "port",
+                   "sample": f"first {k} pairs of the same batch ({dt:.1f} s): setInputTarget once, then align + getFitnessScore per candidate; oracle restatement of ndt_omp + pcl::Registration, OpenMP on all host cores"}
+        # a sample of this rank's pairs against the oracle: up to 8 targets spread over the share, up to 8 candidates each
+        if args.loop_parity_pairs > 0:
+            tids = my_targets[:: max(1, len(my_targets) // 8)][:8]
+            per_t = max(1, args.loop_parity_pairs // max(len(tids), 1))
+            idx = [i for t in tids for i in np.nonzero(mine["target_id"] == t)[0][:per_t].tolist()]
+            sub = mine[idx]
+            clouds = {int(c): np.array(host_cloud[int(c)]) for c in set(sub["target_id"].tolist()) | set(sub["source_id"].tolist())}
+            want = []
+            oracle_loop_pairs(oracle, clouds, sub, want)
+            at_oracle = reg.calcFitnessBatch([(int(p["target_id"]), int(p["source_id"]), w[0]) for p, w in zip(sub, want)], max_range=DBL_MAX)
+            parity = loop_parity_vs_oracle(sub, local[idx], want, at_oracle)
 
+    cfg = loop_config(n_targets, n_candidates, dense)
+    step_ms = 1e3 * sec_d / steps
     out = {
-        "metric": "loop pairs/sec (NDT + fitness)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec_d / steps,
+        "metric": "loop pairs/sec (NDT + fitness)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 per hit, f64 sums", "data": "synthetic",
-        "config": {"workload": (f"dense-scan stress: 128-beam 1M-ray scans, VoxelGrid 0.1 m + {n_targets} x {n_candidates} = {n_pairs} NDT DIRECT1 + getFitnessScore pairs (BASELINE configs[4])" if dense else
-                                f"LoopDetector batch: {n_targets} new keyframes x {n_candidates} candidates = {n_pairs} NDT DIRECT7 + getFitnessScore pairs (BASELINE configs[3])"),
-                   "points_per_keyframe": int(np.mean(kf_n)), "registration": f"NDT_OMP-equivalent {'DIRECT1' if dense else 'DIRECT7'} res 1.0 eps 0.01 max_iter 64, fitness max_range DBL_MAX",
-                   "sharding": "whole targets per rank, one all-gather of 104-byte result records", "pairs_this_rank": int(len(mine)),
-                   "l2": f"{len(specs)} distinct keyframe clouds ({sum(kf_n) * 16 / 1e9:.2f} GB) per rank: inputs larger than L2",
-                   "passes_per_registration": float(np.mean(res["passes"])), "reference_evaluations_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"]))},
+        "config": cfg,
+        "stats": {"points_per_keyframe": int(np.mean(kf_n)), "pairs_this_rank": int(len(mine)),
+                  "l2": f"{len(specs)} distinct keyframe clouds ({sum(kf_n) * 16 / 1e9:.2f} GB) per rank: inputs larger than L2",
+                  "passes_per_registration": float(np.mean(res["passes"])), "reference_evaluations_per_registration": float(np.mean(res["evaluations"])), "converged_fraction": float(np.mean(res["converged"])),
+                  "align_ms": align_ms, "fitness_ms": fit_ms, "other_ms": step_ms - align_ms - fit_ms,
+                  "other_is": "target builds (NDT grid + exact-NN structure per new keyframe), job upload, result download, all-gather"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(local.nbytes), "ms_per_step": 1e3 * sec_h / steps},
         "gpu_launches": int((c1["launches_total"] - c0["launches_total"]) * steps // (steps + warmup)),
         "roofline": {"bound": "hbm", "kernel": f"k_ndt_align<{1 if dense else 7}> ({'1, 2 or 4 CTAs per registration, whichever fills the last round of the batch best' if len(mine) >= 148 else str(148 // max(len(mine), 1)) + ' CTAs per registration'})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                     "traffic": None, "traffic_per_registration": load_traffic("k_ndt_align_batch_per_registration"), "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / (1e3 * sec_d / steps), "fitness_ms_per_step": fit_ms},
+                     "traffic": None, "traffic_per_registration": load_traffic("k_ndt_align_batch_per_registration"), "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": align_ms, "share_of_step": align_ms / step_ms, "fitness_ms_per_step": fit_ms},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "checks": {"device_and_host_legs_bit_identical": legs_equal, "median_translation_error_m": float(np.median(err_t)), "pairs_within_5cm_of_ground_truth": float(np.mean(err_t < 0.05)),
-                   "wall_ms_per_step": 1e3 * wall_d / steps},
+                   "wall_ms_per_step": 1e3 * wall_d / steps, "parity_vs_oracle": parity},
     }
     if dense and vg_ms:
         # VoxelGrid(N -> M): 16 N + 16 M algorithmic bytes
@@ -576,13 +779,16 @@ def main():
     ap.add_argument("--workload", default="odometry", choices=["odometry", "loop"], help="headline line: odometry (configs[1]) or the loop-candidate batch (configs[3])")
     ap.add_argument("--frames", type=int, default=1000, help="scans per sequence (one odometry step = one pass over the sequence)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the sequence the CPU baseline runs")
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the --impl reference arm")
+    ap.add_argument("--ref-frames", type=int, default=24, help="frames per step of the --impl reference arm")
+    ap.add_argument("--ref-start", type=int, default=400, help="first frame of the reference arm's window into the sequence")
     ap.add_argument("--loop-targets", type=int, default=256, help="new keyframes of the loop batch (x candidates = pairs)")
     ap.add_argument("--loop-candidates", type=int, default=16)
     ap.add_argument("--loop-cpu-pairs", type=int, default=8, help="pairs of the batch the CPU baseline registers")
+    ap.add_argument("--loop-parity-pairs", type=int, default=64, help="pairs of rank 0's share re-registered by the CPU oracle and compared with the engine's records (0 = skip)")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
     ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
     ap.add_argument("--prepare", action="store_true", help="build a predicted next keyframe's target structures during its own registration (b200reg_prepare_promotion; measured: no net gain, off by default)")
+    ap.add_argument("--no-1m", action="store_true", help="skip the 1.0 m/frame variant of the odometry sequence (SURVEY cfg 2's spacing: every frame a keyframe switch)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-scan stress leg (BASELINE configs[4]) of the default run")
     ap.add_argument("--dense-targets", type=int, default=8)
     ap.add_argument("--dense-candidates", type=int, default=8)
@@ -603,20 +809,50 @@ def main():
         return reference_arm(args, rank, emit)
 
     ctx = Ctx(args)
+
+    def brief(d):
+        """The few numbers of a leg a reader needs first; the JSON line ends with these (the driver keeps the line's tail)."""
+        b = {"value": round(d["value"], 1), "e2e": round(d["e2e"]["value"], 1), "unit": d["unit"], "ms_per_step": round(d["ms_per_step"], 3), "n_gpus": d["n_gpus"],
+             "frac": round(d["roofline"]["frac"], 4)}
+        st = d.get("stats", {})
+        for k in ("align_ms", "fitness_ms", "other_ms"):
+            if k in st:
+                b[k] = round(st[k], 3)
+        par = d.get("checks", {}).get("parity_vs_oracle")
+        if par:
+            b["parity"] = {k: (float(f"{v:.3g}") if isinstance(v, float) else v) for k, v in par.items() if k in ("max_dt", "max_dr", "max_rel_fitness", "path_diverged", "outside_tolerance", "pairs", "frames", "within_tolerance")}
+        if d.get("cpu_baseline"):
+            b["cpu"] = round(d["cpu_baseline"]["value"], 2)
+        if "voxelgrid" in d:
+            b["voxelgrid_ms_per_1M_scan"] = round(d["voxelgrid"]["ms_per_scan"], 4)
+            b["voxelgrid_frac"] = round(d["voxelgrid"]["achieved_gbs"] / d["voxelgrid"]["peak_gbs"], 4)
+        return b
     if args.workload == "loop":
         out = bench_loop(ctx, args.steps, args.warmup)
+        out["summary"] = {"loop_batch": brief(out)}
     else:
         out = bench_odometry(ctx)
-        keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "checks")
+        keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "stats", "e2e", "e2e_pageable", "gpu_launches", "roofline", "cpu_baseline", "checks")
+        summary = {"odometry": brief(out)}
         if not args.no_loop:
             lb = bench_loop(ctx, max(1, min(args.steps, 2)), 3)
-            out["loop_batch"] = {k: lb[k] for k in keys}
+            out["loop_batch"] = {k: lb[k] for k in keys if k in lb}
+            summary["loop_batch"] = brief(lb)
         if not args.no_dense:
             db = bench_loop(ctx, 1, 3, dense=True)
             out["dense_stress"] = {k: db[k] for k in keys + ("voxelgrid",) if k in db}
+            summary["dense_stress"] = brief(db)
         if not args.no_gicp:
-            gb = bench_odometry(ctx, GICP_ODOM_PARAMS, frames=min(args.frames, args.gicp_frames), steps=max(1, min(args.steps, 2)), warmup=3, label="FAST_GICP", cpu_frames=min(args.cpu_frames, 12))
-            out["gicp_odometry"] = {k: gb[k] for k in keys}
+            gb = bench_odometry(ctx, GICP_ODOM_PARAMS, frames=min(args.frames, args.gicp_frames), steps=max(1, min(args.steps, 2)), warmup=3, label="FAST_GICP", cpu_frames=min(args.cpu_frames, 12), pageable_leg=False)
+            out["gicp_odometry"] = {k: gb[k] for k in keys if k in gb}
+            summary["gicp_odometry"] = brief(gb)
+        if not args.no_1m:
+            ob = bench_odometry(ctx, frames=min(args.frames, 300), steps=max(1, min(args.steps, 2)), warmup=3, cpu_frames=min(args.cpu_frames, 10), stride=2, pageable_leg=False)
+            out["odometry_1m_per_frame"] = {k: ob[k] for k in keys if k in ob}
+            out["odometry_1m_per_frame"]["note"] = ("SURVEY cfg 2's spacing. With keyframe_delta_trans = 1.0 m a frame 0.999 m from its keyframe is not promoted, the next one then starts a full NDT voxel (1 m) from its guess "
+                                                    "and the reference's algorithm itself loses track (see checks.position_error_m_after_frames_checked; the CPU oracle follows the same wrong path, checks.parity_vs_oracle): throughput only")
+            summary["odometry_1m_per_frame"] = brief(ob)
+        out["summary"] = summary  # LAST key of the line
     if ctx.rank == 0:
         emit(json.dumps(out))
     if ctx.dist is not None:

@@ -27,7 +27,7 @@ EXPORTS = [
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
-    "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_end", "b200reg_set_sm_budget", "b200reg_set_distance_filter",
+    "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_end", "b200reg_set_sm_budget", "b200reg_set_distance_filter", "b200reg_distance_filter", "b200reg_distance_filter_device",
     "b200reg_radius_outlier_removal", "b200reg_radius_outlier_removal_device", "b200reg_radius_outlier_removal_begin", "b200reg_radius_outlier_removal_device_begin",
     "b200reg_radius_outlier_removal_end",
     "b200reg_statistical_outlier_removal", "b200reg_statistical_outlier_removal_device", "b200reg_statistical_outlier_removal_begin", "b200reg_statistical_outlier_removal_device_begin",
@@ -118,6 +118,8 @@ def load():
     L.b200reg_voxelgrid_filter_end.argtypes = [vp, szp]
     L.b200reg_set_sm_budget.argtypes = [vp, C.c_int]
     L.b200reg_set_distance_filter.argtypes = [vp, C.c_int, C.c_double, C.c_double]
+    L.b200reg_distance_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, vp, C.c_size_t, szp]
+    L.b200reg_distance_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_double, C.c_double, vp, szp]
     L.b200reg_radius_outlier_removal.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_int, vp, C.c_size_t, szp]
     L.b200reg_radius_outlier_removal_device.argtypes = [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, szp]
     L.b200reg_radius_outlier_removal_begin.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_int, vp, C.c_size_t]

@@ -48,6 +48,7 @@ struct b200reg_handle {
   PinnedBuf<float4> pin_in, pin_out;
   int n_src = 0, n_tgt = 0;
   bool have_src = false, have_tgt = false;
+  bool src_is_tgt = false;  // the source was promoted to target and no new source has been set: pcl's input_ still is that cloud
 
   // VoxelGrid filter
   VoxelSort vg_sort;
@@ -267,6 +268,22 @@ int ensure_nn_grid(b200reg_handle* h) {
   return B200REG_OK;
 }
 
+// After b200reg_promote_source_to_target the cloud lives in the target buffer only.  pcl::Registration would
+// still hold it as input_ as well (the reference never aligns in that state: the next matching() sets a new
+// source first), so a call that needs the source re-creates it from the target on demand.
+int materialize_source(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (h->have_src || !h->src_is_tgt || !h->have_tgt) return B200REG_OK;
+  B200_CUDA_TRY(h->src.reserve(h->n_tgt ? h->n_tgt : 1));
+  B200_CUDA_TRY(cudaMemcpyAsync(h->src.p, h->tgt.p, (size_t)h->n_tgt * 16, cudaMemcpyDeviceToDevice, h->stream));
+  h->n_src = h->n_tgt;
+  h->have_src = true;
+  h->src_is_tgt = false;
+  h->nn_src_stale = true;
+  h->cov_src_ok = false;
+  return B200REG_OK;
+}
+
 // Kernel attributes, once per device: the align kernels opt in to 192 KB of dynamic shared memory
 // (the staged target grid), and EVERY kernel of the library asks for the maximum shared-memory
 // carve-out, so that consecutive kernels of a frame never make the SMs re-partition L1 / shared
@@ -297,7 +314,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
   B200_ATTR(prefer_shared(k_gicp_knn<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnCovariance>)); B200_ATTR(prefer_shared(k_gicp_knn<kKnnMeanDistance>));
   B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnMeanDistance>)); B200_ATTR(prefer_shared(k_sor_threshold)); B200_ATTR(prefer_shared(k_sor_flags));
-  B200_ATTR(prefer_shared(k_gicp_knn<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_nz_flags)); B200_ATTR(prefer_shared(k_gicp_regularize));
+  B200_ATTR(prefer_shared(k_gicp_knn<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_gicp_knn_brute<kKnnNormalNz>)); B200_ATTR(prefer_shared(k_nz_flags)); B200_ATTR(prefer_shared(k_gate_flags)); B200_ATTR(prefer_shared(k_gicp_regularize));
   // k_gicp_align needs 17.5 KB of shared memory and keeps its 29 double accumulators + 3x3 temporaries in a
   // 1.4 KB per-thread stack frame (128-register cap at 512 threads): it wants the L1, not the carve-out
   B200_ATTR(cudaFuncSetAttribute((const void*)k_gicp_align<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
@@ -681,6 +698,7 @@ int b200reg_set_target(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   if (!n || !xyzw) { h->err = "Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = materialize_source(h))) return rc;  // the promoted cloud is still pcl's input_
   if ((rc = upload_cloud(h, xyzw, n, stride, h->tgt))) return rc;
   h->n_tgt = (int)n;
   h->have_tgt = true;
@@ -711,6 +729,7 @@ int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   if ((rc = upload_cloud(h, xyzw, n, stride, h->src))) return rc;
   h->n_src = (int)n;
   h->have_src = true;
+  h->src_is_tgt = false;
   h->nn_src_stale = true;
   h->cov_src_ok = false;
   return B200REG_OK;
@@ -722,6 +741,7 @@ int b200reg_set_target_device(b200reg_handle* h, const float* d_xyzw, size_t n) 
   if (!n || !d_xyzw) { h->err = "Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = materialize_source(h))) return rc;
   B200_CUDA_TRY(h->tgt.reserve(n));
   B200_CUDA_TRY(cudaMemcpyAsync(h->tgt.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
   h->n_tgt = (int)n;
@@ -743,6 +763,7 @@ int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n) 
   if (n) B200_CUDA_TRY(cudaMemcpyAsync(h->src.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
   h->n_src = (int)n;
   h->have_src = true;
+  h->src_is_tgt = false;
   h->nn_src_stale = true;
   h->cov_src_ok = false;
   return B200REG_OK;
@@ -758,6 +779,7 @@ int b200reg_promote_source_to_target(b200reg_handle* h) {
   h->n_tgt = h->n_src;
   h->have_tgt = true;
   h->have_src = false;
+  h->src_is_tgt = true;
   h->n_src = 0;
   h->grid_stale = true;
   // GICP: the cloud keeps its NN structure and covariances when it changes role (same cloud, same values)
@@ -816,9 +838,10 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
   if (!h) return B200REG_E_INVALID;
   h->have_result = false;
   if (!h->have_tgt) { h->err = "No input target dataset was given!"; return B200REG_E_STATE; }
-  if (!h->have_src || h->n_src == 0) { h->err = "No input source dataset was given!"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = materialize_source(h))) return rc;
+  if (!h->have_src || h->n_src == 0) { h->err = "No input source dataset was given!"; return B200REG_E_STATE; }
   if (h->cfg.method == B200REG_METHOD_NDT) {
     if ((rc = run_ndt_single(h, guess, nullptr))) return rc;
   } else if (h->cfg.method == B200REG_METHOD_GICP) {
@@ -827,16 +850,21 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
     h->err = "align: registration method not available on this handle";
     return B200REG_E_STATE;
   }
+  bool aligned_direct = false;
   if (aligned_xyzw) {
+    // pcl::Registration::align fills `output` with the transformed source [REF apps/scan_matching_odometry_nodelet.cpp:217-218]:
+    // one kernel behind the registration, then DMA straight into a page-locked caller cloud, or through the
+    // handle's pinned staging buffer into a pageable one
     B200_CUDA_TRY(h->aligned.reserve(h->n_src));
-    B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
+    aligned_direct = is_pinned_host(aligned_xyzw);
+    if (!aligned_direct) B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
     launch_counter() += 1;
     k_transform_cloud<<<(h->n_src + 255) / 256, 256, 0, h->stream>>>(h->src.p, h->n_src, h->d_result.p, h->aligned.p);
-    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(aligned_direct ? (void*)aligned_xyzw : (void*)h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  if (aligned_xyzw) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
-  if (aligned_xyzw) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  if (aligned_xyzw && !aligned_direct) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
   return B200REG_OK;
 }
 
@@ -875,6 +903,7 @@ int b200reg_get_fitness_score(b200reg_handle* h, double max_range, double* out) 
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || !out) return B200REG_E_INVALID;
   *out = 1.7976931348623157e308;
+  if (h->src_is_tgt && set_device(h) == B200REG_OK) materialize_source(h);
   if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;  // DBL_MAX, as upstream with no correspondences
   int rc = set_device(h);
   if (rc) return rc;
@@ -893,6 +922,7 @@ int b200reg_calc_fitness_score(b200reg_handle* h, const float* relpose16, double
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || !out || !relpose16) return B200REG_E_INVALID;
   *out = 1.7976931348623157e308;
+  if (h->src_is_tgt && set_device(h) == B200REG_OK) materialize_source(h);
   if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;
   int rc = set_device(h);
   if (rc) return rc;
@@ -908,6 +938,7 @@ int b200reg_get_inlier_fraction(b200reg_handle* h, double max_dist, double* out)
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h || !out) return B200REG_E_INVALID;
   *out = 0.0;
+  if (h->src_is_tgt && set_device(h) == B200REG_OK) materialize_source(h);
   if (!h->have_tgt || !h->have_src || h->n_src == 0) return B200REG_OK;
   int rc = set_device(h);
   if (rc) return rc;
@@ -1075,7 +1106,11 @@ struct OutlierSpec {
   double lidar_z = 0.0;
   int normal_k = 0;
   float normal_thresh = 0.f;
+  // distance_filter on its own (down-sampling NONE) [REF apps/prefiltering_nodelet.cpp:275-291]
+  bool gate_only = false;
+  double near_thresh = 0.0, far_thresh = 0.0;
   bool valid() const {
+    if (gate_only) return near_thresh == near_thresh && far_thresh == far_thresh;
     if (flat) return normal_k >= 1 && normal_k <= 32 && lidar_z == lidar_z && normal_thresh == normal_thresh;
     return statistical ? (mean_k >= 1 && mean_k <= 31 && stddev_mul == stddev_mul) : (radius > 0 && min_neighbors >= 0);
   }
@@ -1087,7 +1122,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
   const int min_neighbors = spec.min_neighbors;
   PointGate gate = kNoGate;
   if (spec.flat) { gate.on = 2; gate.near_thresh = spec.lidar_z; }  // height_filtering as a gate of the lattice build: no intermediate cloud
-  B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0, gate));
+  if (!spec.gate_only) B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0, gate));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));
   B200_CUDA_TRY(h->ror_block_count.reserve(blocks));
@@ -1102,7 +1137,11 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
   RorCounts* hc = const_cast<RorCounts*>(&h->mail->ror);
   unsigned int* hf = const_cast<unsigned int*>(&h->mail->ror_seq);
   const unsigned int seq = ++h->ror_seq;
-  if (spec.flat) {
+  if (spec.gate_only) {
+    PointGate dg = {1, spec.near_thresh, spec.far_thresh};
+    launch_counter() += 2;
+    k_gate_flags<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, dg, h->ror_keep.p, h->ror_block_count.p);
+  } else if (spec.flat) {
     // |n_z| per point that passed the height gate; NaN (never kept) everywhere else
     B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
     B200_CUDA_TRY(h->sor_pending.reserve(n ? n : 1));
@@ -1135,7 +1174,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
     k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
   }
   k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
-                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, h->nn_ror.sort.meta.p, spec.flat ? 1 : 0);
+                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, spec.gate_only ? nullptr : h->nn_ror.sort.meta.p, spec.flat ? 1 : 0);
   B200_CUDA_TRY(cudaGetLastError());
   return B200REG_OK;
 }
@@ -1267,6 +1306,27 @@ int b200reg_statistical_outlier_removal_device(b200reg_handle* h, const float* d
   if (!n_out) return B200REG_E_INVALID;
   *n_out = 0;
   int rc = b200reg_statistical_outlier_removal_device_begin(h, d_xyzw, n, mean_k, stddev_mul, d_out);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+
+// ---- distance_filter on its own (the prefilter nodelet with downsample_method NONE) ------------------
+static OutlierSpec gate_spec(double near_thresh, double far_thresh) {
+  OutlierSpec s;
+  s.gate_only = true; s.near_thresh = near_thresh; s.far_thresh = far_thresh;
+  return s;
+}
+int b200reg_distance_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double near_thresh, double far_thresh, float* out, size_t cap, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = outlier_host_begin(h, xyzw, n, stride, gate_spec(near_thresh, far_thresh), out, cap);
+  if (rc) return rc;
+  return b200reg_radius_outlier_removal_end(h, n_out);
+}
+int b200reg_distance_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double near_thresh, double far_thresh, float* d_out, size_t* n_out) {
+  if (!n_out) return B200REG_E_INVALID;
+  *n_out = 0;
+  int rc = outlier_device_begin(h, d_xyzw, n, gate_spec(near_thresh, far_thresh), d_out);
   if (rc) return rc;
   return b200reg_radius_outlier_removal_end(h, n_out);
 }

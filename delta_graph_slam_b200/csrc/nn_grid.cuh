@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) k_ror_scatter(const float4* __restrict__ 
   *done_blocks = 0u;
   uint32_t total = 0;
   for (int b = 0; b < (int)gridDim.x; ++b) total += __ldcg(block_count + b);
-  const uint32_t overflow = meta->grid.overflow ? 1u : 0u;
+  const uint32_t overflow = (meta && meta->grid.overflow) ? 1u : 0u;  // meta == nullptr: no search lattice behind this call (distance filter)
   counts->n_out = total;
   counts->overflow = overflow;
   if (host_counts) {

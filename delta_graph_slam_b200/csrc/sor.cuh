@@ -166,4 +166,26 @@ __global__ void __launch_bounds__(256) k_nz_flags(const float* __restrict__ nz, 
   }
 }
 
+// PrefilteringNodelet::distance_filter on its own [REF apps/prefiltering_nodelet.cpp:275-291] (down-sampling NONE: there is
+// no VoxelGrid key pass to fuse the gate into): keep when near < |p| < far, order kept by k_ror_scatter
+__global__ void __launch_bounds__(256) k_gate_flags(const float4* __restrict__ pts, int n, PointGate gate, unsigned char* __restrict__ keep, uint32_t* __restrict__ block_count) {
+  __shared__ uint32_t s_cnt[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int k = 0;
+  if (i < n) {
+    const float4 p = __ldg(pts + i);
+    k = point_takes_part(gate, 0, p.x, p.y, p.z) ? 1 : 0;
+    keep[i] = (unsigned char)k;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) s_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int w = 0; w < 8; ++w) c += s_cnt[w];
+    block_count[blockIdx.x] = c;
+  }
+}
+
 }  // namespace b200

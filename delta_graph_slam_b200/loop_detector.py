@@ -15,6 +15,9 @@ import sys
 
 import numpy as np
 
+from collections import OrderedDict
+
+from . import _lib
 from .registration import DBL_MAX, select_registration_method
 
 
@@ -82,7 +85,10 @@ class LoopDetector:
         self.registration = registration if registration is not None else select_registration_method(p, device=device, out=out)
         self.last_edge_accum_distance = 0.0
         self.out = out
-        self._cached = set()
+        # keyframe clouds resident on the device, least recently used first; beyond `b200_max_cached_keyframes`
+        # (the mirror's own key; ~0.8 MB per HDL-64 keyframe, 4 MB once it has served as a target) the oldest are dropped
+        self.max_cached_keyframes = int(p.get("b200_max_cached_keyframes", 16384))
+        self._cached = OrderedDict()
 
     def get_distance_thresh(self):
         return self.distance_thresh
@@ -111,18 +117,37 @@ class LoopDetector:
 
     # ---- the registrations
     def _ensure_cached(self, kf):
-        if kf.id not in self._cached:
-            self.registration.cloudPut(kf.id, kf.cloud)
-            self._cached.add(kf.id)
+        if kf.id in self._cached:
+            self._cached.move_to_end(kf.id)
+            return
+        self.registration.cloudPut(kf.id, kf.cloud)
+        self._cached[kf.id] = True
+
+    def _evict(self, keep):
+        """Drop least-recently-used keyframes above the cap (never one of the batch about to run)."""
+        while len(self._cached) > self.max_cached_keyframes:
+            victim = next((k for k in self._cached if k not in keep), None)
+            if victim is None:
+                return
+            del self._cached[victim]
+            self.registration.cloudDrop(victim)
+
+    def batch_capable(self):
+        """The engine's batch path registers NDT pairs (b200reg_align_batch); any other registration object — FAST_GICP,
+        the launch file's choice [REF launch/delta_graph_slam.launch:95], or a plain pcl::Registration surface — is
+        driven through the reference's own serial loop."""
+        reg = self.registration
+        return hasattr(reg, "alignBatch") and getattr(reg, "method", _lib.METHOD_NDT) in getattr(reg, "batch_methods", (_lib.METHOD_NDT,))
 
     def register_candidates(self, candidates, new_keyframe):
         """(converged[], scores[], transforms[]) of every candidate against the new keyframe."""
         reg = self.registration
         guesses = [candidate_guess(new_keyframe, c) for c in candidates]
-        if hasattr(reg, "alignBatch"):
+        if self.batch_capable():
             self._ensure_cached(new_keyframe)
             for c in candidates:
                 self._ensure_cached(c)
+            self._evict({new_keyframe.id} | {c.id for c in candidates})
             res = reg.alignBatch([(new_keyframe.id, c.id, g) for c, g in zip(candidates, guesses)], with_fitness=True, fitness_max_range=self.fitness_score_max_range)
             return ([bool(r["converged"]) for r in res], [float(r["fitness"]) for r in res],
                     [np.array(r["transformation"], np.float32).reshape(4, 4).T.copy() for r in res])

@@ -33,21 +33,24 @@ def quaternion_w(R):
 class Prefilter:
     """PrefilteringNodelet's 3-D chain [REF apps/prefiltering_nodelet.cpp:150-153]: distance_filter (:275-291)
     -> downsample (:249-260, filter chosen :55-75) -> outlier_removal (:262-273, chosen :77-98), with the
-    reference's parameter names and defaults.  The distance filter is fused into the VoxelGrid call;
-    outlier_removal_method RADIUS and STATISTICAL both run on the engine.  NOTE the mirror's own default for
-    outlier_removal_method is NONE and for use_distance_filter False, so that a Prefilter built from
-    just the down-sampling parameters is the plain VoxelGrid the earlier tests and bench legs use; pass
-    the reference's values (launch/delta_graph_slam.launch:31-42) to get its chain."""
+    reference's parameter names AND defaults: down-sampling VOXELGRID 0.1, outlier removal STATISTICAL 20 / 1.0,
+    distance gate 1.0 .. 100.0.  The gate runs on EVERY scan: the reference reads `use_distance_filter` (:100) and
+    never tests it (cloud_callback calls distance_filter unconditionally, :150), so the parameter is accepted and
+    ignored here as well.  The one opt-out is the mirror's own key `b200_skip_distance_filter` (not a reference
+    parameter; for callers whose input has already been gated).  With a VoxelGrid the gate is fused into the filter's
+    key pass; without one (downsample_method NONE) it is a call of its own (b200reg_distance_filter)."""
 
     def __init__(self, params=None, device=0, out=sys.stdout):
         p = dict(params or {})
         method = p.get("downsample_method", "VOXELGRID")
         res = p.get("downsample_resolution", 0.1)
         self.filter = None
+        self._reg = None
         if method == "VOXELGRID":
             print(f"downsample: VOXELGRID {res:g}", file=out)
             self.filter = VoxelGrid(device=device)
             self.filter.setLeafSize(res, res, res)
+            self._reg = self.filter._reg
         elif method == "APPROX_VOXELGRID":
             raise NotImplementedError("APPROX_VOXELGRID stays on the reference's pcl::ApproximateVoxelGrid (not on the B200 path)")
         else:
@@ -55,13 +58,13 @@ class Prefilter:
                 print(f"warning: unknown downsampling type ({method})", file=sys.stderr)
                 print("       : use passthrough filter", file=sys.stderr)
             print("downsample: NONE", file=out)
-        orm = p.get("outlier_removal_method", "NONE")
+        orm = p.get("outlier_removal_method", "STATISTICAL")
         self.outlier_removal_filter = None
         if orm == "STATISTICAL":
             mean_k = p.get("statistical_mean_k", 20)
             stddev_mul_thresh = p.get("statistical_stddev", 1.0)
             print(f"outlier_removal: STATISTICAL {mean_k} - {stddev_mul_thresh:g}", file=out)
-            self.outlier_removal_filter = StatisticalOutlierRemoval(device=device, registration=self.filter._reg if self.filter is not None else None)
+            self.outlier_removal_filter = StatisticalOutlierRemoval(device=device, registration=self._reg)
             self.outlier_removal_filter.setMeanK(mean_k)
             self.outlier_removal_filter.setStddevMulThresh(stddev_mul_thresh)
         elif orm == "RADIUS":
@@ -69,24 +72,35 @@ class Prefilter:
             min_neighbors = p.get("radius_min_neighbors", 2)
             print(f"outlier_removal: RADIUS {radius:g} - {min_neighbors}", file=out)
             # same handle (and stream) as the VoxelGrid: the stages of one scan run in order
-            self.outlier_removal_filter = RadiusOutlierRemoval(device=device, registration=self.filter._reg if self.filter is not None else None)
+            self.outlier_removal_filter = RadiusOutlierRemoval(device=device, registration=self._reg)
             self.outlier_removal_filter.setRadiusSearch(radius)
             self.outlier_removal_filter.setMinNeighborsInRadius(min_neighbors)
         else:
             print("outlier_removal: NONE", file=out)
-        self.use_distance_filter = bool(p.get("use_distance_filter", False))
+        if self._reg is None and self.outlier_removal_filter is not None:
+            self._reg = self.outlier_removal_filter._reg
+        self.use_distance_filter = bool(p.get("use_distance_filter", True))  # read and never tested, as upstream
         self.distance_near_thresh = float(p.get("distance_near_thresh", 1.0))
         self.distance_far_thresh = float(p.get("distance_far_thresh", 100.0))
-        if self.use_distance_filter:
-            if self.filter is None:
-                raise NotImplementedError("use_distance_filter without a VoxelGrid down-sampler is not on the B200 path (the gate is fused into the VoxelGrid keys)")
-            self.filter.setDistanceFilter(True, self.distance_near_thresh, self.distance_far_thresh)
+        self.distance_filter_on = not bool(p.get("b200_skip_distance_filter", False))
+        if self.distance_filter_on:
+            if self.filter is not None:
+                self.filter.setDistanceFilter(True, self.distance_near_thresh, self.distance_far_thresh)
+            elif self._reg is None:
+                from .registration import Registration
+                self._reg = Registration(device=device)  # a filter-only handle for the stand-alone gate
 
     def setSmBudget(self, n_sm):
         if self.filter is not None:
             self.filter.setSmBudget(n_sm)
         elif self.outlier_removal_filter is not None:
             self.outlier_removal_filter._reg.setSmBudget(n_sm)
+
+    def distance_filter(self, cloud, out=None):
+        """distance_filter as a stage of its own; with a VoxelGrid it is part of downsample() instead."""
+        if not self.distance_filter_on or self.filter is not None:
+            return cloud
+        return self._reg.distance_filter(cloud, self.distance_near_thresh, self.distance_far_thresh, out=out)
 
     def downsample(self, cloud, out=None):
         if self.filter is None:
@@ -104,19 +118,20 @@ class Prefilter:
     def filter2d(self, filtered3d, lidar_z, out=None):
         """filtered2D of cloud_callback [REF apps/prefiltering_nodelet.cpp:155-158]: height_filtering (z > lidar z) ->
         normal_filtering (k = 10, |n_z| < 0.2) -> flatten, one engine call on the prefilter's handle."""
-        reg = self.filter._reg if self.filter is not None else (self.outlier_removal_filter._reg if self.outlier_removal_filter is not None else None)
-        if reg is None:
-            raise NotImplementedError("filter2d needs an engine handle: configure a VoxelGrid down-sampler or an outlier filter")
-        return reg.flat_filter(filtered3d, lidar_z, out=out)
+        if self._reg is None:
+            from .registration import Registration
+            self._reg = Registration(device=0)
+        return self._reg.flat_filter(filtered3d, lidar_z, out=out)
 
-    def filter3d(self, cloud, out=None, out2=None):
-        """filtered3D of cloud_callback: distance_filter -> downsample -> outlier_removal."""
-        return self.outlier_removal(self.downsample(cloud, out=out), out=out2)
+    def filter3d(self, cloud, out=None, out2=None, out0=None):
+        """filtered3D of cloud_callback: distance_filter -> downsample -> outlier_removal (`out0`: output of the
+        stand-alone gate when there is no VoxelGrid)."""
+        return self.outlier_removal(self.downsample(self.distance_filter(cloud, out=out0), out=out), out=out2)
 
     def downsample_begin(self, cloud, out):
         """downsample() split in two: enqueue the filter of `cloud` into the caller-owned `out` ..."""
         if self.filter is None:
-            self._passthrough = cloud
+            self._passthrough = self.distance_filter(cloud, out=out if self.distance_filter_on else None)
             return
         self.filter.setInputCloud(cloud, is_dense=False)
         self.filter.filter_begin(out)
@@ -205,8 +220,13 @@ class FrontEnd:
 class ScanMatchingOdometry:
     """matching(stamp, cloud) -> odom (4x4 float32), state as in the nodelet."""
 
-    def __init__(self, params=None, device=0, out=sys.stdout, registration=None, downsample_filter=None):
+    def __init__(self, params=None, device=0, out=sys.stdout, registration=None, downsample_filter=None, downsample_bufs=None):
+        """`downsample_bufs`: for device-resident input with a VoxelGrid down-sampler, at least three caller-owned
+        DeviceClouds used in rotation as the filter's outputs (the keyframe's cloud stays referenced while the next
+        scans are filtered); host input needs none."""
         p = dict(params or {})
+        self.downsample_bufs = list(downsample_bufs) if downsample_bufs is not None else None
+        self._ds_next = 0
         self.keyframe_delta_trans = p.get("keyframe_delta_trans", 0.25)
         self.keyframe_delta_angle = p.get("keyframe_delta_angle", 0.15)
         self.keyframe_delta_time = p.get("keyframe_delta_time", 1.0)
@@ -243,6 +263,11 @@ class ScanMatchingOdometry:
         self.prepare_promotion = bool(p.get("prepare_promotion", False))
         self._last_step = 0.0
         self.promotions_prepared = 0
+        # pcl::Registration::align(*aligned, guess) [REF apps/scan_matching_odometry_nodelet.cpp:217-218] always fills the
+        # aligned cloud.  The mirror asks the engine for it when the caller provides the cloud to fill (`aligned_out`, an
+        # (M, 4) float32 array) — the bench's end-to-end legs do; parity tests that only read the transform leave it out.
+        self.aligned_out = None
+        self.aligned = None
 
     def downsample(self, cloud):
         if self.downsample_filter is None:
@@ -254,6 +279,12 @@ class ScanMatchingOdometry:
                 return DeviceCloud(cloud.ptr, cloud.n, cloud.owner)
             return np.asarray(cloud, dtype=np.float32).view()
         self.downsample_filter.setInputCloud(cloud, is_dense=True)
+        if isinstance(cloud, DeviceCloud):
+            if not self.downsample_bufs or len(self.downsample_bufs) < 3:
+                raise ValueError("ScanMatchingOdometry: device-resident scans with downsample_method VOXELGRID need downsample_bufs=[three DeviceClouds] (or downsample_method NONE)")
+            buf = self.downsample_bufs[self._ds_next % len(self.downsample_bufs)]
+            self._ds_next += 1
+            return self.downsample_filter.filter(out=buf)
         return self.downsample_filter.filter()
 
     def matching(self, stamp, cloud, msf_delta=None):
@@ -275,7 +306,10 @@ class ScanMatchingOdometry:
         if self.prepare_promotion and hasattr(reg, "preparePromotion") and dist_before + self._last_step > 0.95 * self.keyframe_delta_trans:
             reg.preparePromotion()
             self.promotions_prepared += 1
-        reg.align(guess)
+        if self.aligned_out is not None:
+            self.aligned = reg.align(guess, aligned_out=self.aligned_out)
+        else:
+            reg.align(guess)
         self.last_converged = reg.hasConverged()
         if not self.last_converged:
             # "scan matching has not converged!! ignore this frame": state untouched
@@ -298,7 +332,12 @@ class ScanMatchingOdometry:
         delta_time = stamp - self.keyframe_stamp
         if delta_trans > self.keyframe_delta_trans or delta_angle > self.keyframe_delta_angle or delta_time > self.keyframe_delta_time:
             self.keyframe = filtered
-            reg.setInputTarget(self.keyframe)  # the cloud just used as source: promoted on the device
+            # keyframe = filtered; registration->setInputTarget(keyframe): the cloud just aligned as the source.  The
+            # engine changes its role on the device; any other registration object gets the plain call.
+            if hasattr(reg, "promoteSourceToTarget"):
+                reg.promoteSourceToTarget()
+            else:
+                reg.setInputTarget(self.keyframe)
             self.keyframe_pose = odom
             self.keyframe_stamp = stamp
             self.prev_time = stamp

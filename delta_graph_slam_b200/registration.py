@@ -2,7 +2,7 @@
 
 `select_registration_method(params)` follows [REF src/hdl_graph_slam/registrations.cpp:22-124]:
 same parameter names (`registration_method`, `reg_*`), same defaults, same banners, same
-fall-back-to-NDT warning for unknown strings.  The objects it returns expose the
+warning for unknown strings (which, like plain "NDT", select the reference's single-thread pcl NDT: not replaced, raises).  The objects it returns expose the
 pcl::Registration calls the reference makes (SURVEY.md §8b): setInputTarget, setInputSource,
 align, hasConverged, getFinalTransformation, getFitnessScore — backed by the CUDA engine only.
 """
@@ -50,7 +50,6 @@ class Registration:
             self._h = None
             raise B200RegError(rc, "b200reg_create failed (no usable sm_100 CUDA device?)")
         self._n_src = 0
-        self._src_ref = None
         self.device = device
 
     def close(self):
@@ -79,31 +78,24 @@ class Registration:
 
     # ---- data
     def setInputTarget(self, cloud):
+        """pcl::Registration::setInputTarget: the cloud is copied to the device at the call (host arrays may be
+        reused afterwards).  A caller that wants the source it has just aligned to become the target without
+        another upload says so explicitly with promoteSourceToTarget()."""
         if isinstance(cloud, DeviceCloud):
-            if self._src_ref is not None and cloud is self._src_ref:
-                return self.promoteSourceToTarget()
             return self.setInputTargetDevice(cloud.ptr, cloud.n)
         c = _lib.as_cloud(cloud)
         if len(c) == 0:  # PCL_ERROR + return: the previous target stays
             print("[b200reg::setInputTarget] Invalid or empty point cloud dataset given!", file=sys.stderr)
-            return
-        if self._src_ref is not None and cloud is self._src_ref:
-            # keyframe = filtered; setInputTarget(keyframe) [REF apps/scan_matching_odometry_nodelet.cpp:253-254]
-            self._ck(_lib.load().b200reg_promote_source_to_target(self._h))
-            self._src_ref = None
-            self._n_src = 0
             return
         self._ck(_lib.load().b200reg_set_target(self._h, c.ctypes.data, len(c), 16))
 
     def setInputSource(self, cloud):
         if isinstance(cloud, DeviceCloud):
             self.setInputSourceDevice(cloud.ptr, cloud.n)
-            self._src_ref = cloud
             return
         c = _lib.as_cloud(cloud)
         self._ck(_lib.load().b200reg_set_source(self._h, c.ctypes.data if len(c) else None, len(c), 16))
         self._n_src = len(c)
-        self._src_ref = cloud
 
     def setInputTargetDevice(self, ptr, n):
         self._ck(_lib.load().b200reg_set_target_device(self._h, ptr, n))
@@ -111,12 +103,11 @@ class Registration:
     def setInputSourceDevice(self, ptr, n):
         self._ck(_lib.load().b200reg_set_source_device(self._h, ptr, n))
         self._n_src = n
-        self._src_ref = None
 
     def promoteSourceToTarget(self):
+        """keyframe = filtered; registration->setInputTarget(keyframe) [REF apps/scan_matching_odometry_nodelet.cpp:253-254]
+        for the cloud that is the current source: it changes role on the device (b200reg_promote_source_to_target)."""
         self._ck(_lib.load().b200reg_promote_source_to_target(self._h))
-        self._n_src = 0
-        self._src_ref = None
 
     def preparePromotion(self):
         """Scheduling hint before align: the source will probably become the target (b200reg_prepare_promotion)."""
@@ -126,11 +117,19 @@ class Registration:
         self._ck(_lib.load().b200reg_set_side_budget(self._h, int(n_sm)))
 
     # ---- run
-    def align(self, guess=None, want_aligned=False):
-        """registration->align(*aligned, guess).  Returns the aligned cloud when asked for."""
+    def align(self, guess=None, want_aligned=False, aligned_out=None):
+        """registration->align(*aligned, guess).  Returns the aligned cloud when asked for: a fresh array
+        (want_aligned) or the first n_source rows of the caller's `aligned_out` ((M, 4) float32, M >= n_source;
+        page-locked memory is written by DMA without staging)."""
         g = _lib.colmajor(np.eye(4) if guess is None else guess)
-        out = np.zeros((self._n_src, 4), np.float32) if want_aligned else None
-        rc = _lib.load().b200reg_align(self._h, g.ctypes.data, out.ctypes.data if want_aligned and self._n_src else None)
+        out = None
+        if aligned_out is not None:
+            if aligned_out.dtype != np.float32 or aligned_out.ndim != 2 or aligned_out.shape[1] != 4 or not aligned_out.flags.c_contiguous or len(aligned_out) < self._n_src:
+                raise ValueError("aligned_out must be a C-contiguous (M, 4) float32 array with M >= the source size")
+            out = aligned_out[: self._n_src]
+        elif want_aligned:
+            out = np.zeros((self._n_src, 4), np.float32)
+        rc = _lib.load().b200reg_align(self._h, g.ctypes.data, out.ctypes.data if out is not None and self._n_src else None)
         if rc == _lib.E_STATE:  # PCL logs and returns with converged_ == false
             print(f"[b200reg::align] {_lib.load().b200reg_last_error(self._h).decode()}", file=sys.stderr)
             return out
@@ -317,6 +316,23 @@ class Registration:
     def setDistanceFilter(self, use, near_thresh=1.0, far_thresh=100.0):
         """distance_filter of the prefiltering nodelet fused into this handle's VoxelGrid calls (b200reg_set_distance_filter)."""
         self._ck(_lib.load().b200reg_set_distance_filter(self._h, int(bool(use)), float(near_thresh), float(far_thresh)))
+
+    def distance_filter(self, cloud, near_thresh=1.0, far_thresh=100.0, out=None):
+        """PrefilteringNodelet::distance_filter as a call of its own (b200reg_distance_filter): for a prefilter without a VoxelGrid."""
+        n_out = C.c_size_t()
+        if isinstance(cloud, DeviceCloud):
+            if out is None or out.n < cloud.n:
+                raise ValueError("a device cloud needs a device output buffer at least as large as the input")
+            self._ck(_lib.load().b200reg_distance_filter_device(self._h, cloud.ptr, cloud.n, float(near_thresh), float(far_thresh), out.ptr, C.byref(n_out)))
+            return DeviceCloud(out.ptr, n_out.value, out.owner)
+        c = _lib.as_cloud(cloud)
+        own = out is None
+        if own:
+            out = np.empty((max(len(c), 1), 4), np.float32)
+        elif out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags.c_contiguous or len(out) < len(c):
+            raise ValueError("out must be a C-contiguous (M, 4) float32 array with M >= len(cloud)")
+        self._ck(_lib.load().b200reg_distance_filter(self._h, c.ctypes.data if len(c) else None, len(c), 16, float(near_thresh), float(far_thresh), out.ctypes.data, len(out), C.byref(n_out)))
+        return out[: n_out.value].copy() if own else out[: n_out.value]
 
     def radius_outlier_removal_begin(self, cloud, radius, min_neighbors, out):
         """pcl::RadiusOutlierRemoval, first half (enqueue).  `cloud` / `out` both host arrays or both DeviceClouds."""
@@ -513,6 +529,8 @@ class VoxelGrid:
 
     def filter(self, out=None):
         if isinstance(self._input, DeviceCloud):
+            if not isinstance(out, DeviceCloud):
+                raise ValueError("VoxelGrid.filter: a device-resident input needs a caller-owned DeviceCloud output (out=...) with room for len(input) points")
             return self._reg.voxelgrid_filter_device(self._input, self._leaf, out, self.min_points_per_voxel, self.is_dense)
         return self._reg.voxelgrid_filter(self._input, self._leaf, self.min_points_per_voxel, self.is_dense, out=out)
 
@@ -616,8 +634,11 @@ def select_registration_method(params=None, device=0, out=sys.stdout):
         print(f"warning: unknown registration type({registration_method})", file=sys.stderr)
         print("       : use NDT", file=sys.stderr)
     ndt_resolution = p.get("reg_resolution", 0.5)
-    if "OMP" not in registration_method and "NDT" in registration_method:
-        raise NotImplementedError("registration_method=NDT (single-thread pcl::NormalDistributionsTransform) stays on the reference's CPU implementation")
+    if "OMP" not in registration_method:
+        # "NDT" and every unknown string end in the reference's single-thread pcl::NormalDistributionsTransform branch
+        # [REF src/hdl_graph_slam/registrations.cpp:88-99], which is not on the path this engine replaces
+        raise NotImplementedError(f"registration_method={registration_method} selects the reference's single-thread pcl::NormalDistributionsTransform, which stays on its CPU implementation; "
+                                  "b200reg replaces NDT_OMP and FAST_GICP")
     num_threads = p.get("reg_num_threads", 0)
     nn_search_method = p.get("reg_nn_search_method", "DIRECT7")
     print(f"registration: NDT_OMP {nn_search_method} {ndt_resolution:g} ({num_threads} threads)", file=out)

@@ -111,7 +111,8 @@ int b200reg_set_target_device(b200reg_handle* h, const float* d_xyzw, size_t n);
 int b200reg_set_source_device(b200reg_handle* h, const float* d_xyzw, size_t n);
 /* keyframe = filtered; registration->setInputTarget(keyframe)
  * [REF apps/scan_matching_odometry_nodelet.cpp:253-254]: the current source becomes the target
- * without leaving the device (same result as b200reg_set_target on the same cloud). */
+ * without leaving the device (same result as b200reg_set_target on the same cloud).  As in PCL the cloud also stays
+ * the input source until b200reg_set_source replaces it (an align before that registers the cloud against itself). */
 int b200reg_promote_source_to_target(b200reg_handle* h);
 
 /* Hint: the current source will probably be promoted to target after its registration (the odometry's
@@ -182,6 +183,12 @@ int b200reg_set_sm_budget(b200reg_handle* h, int n_sm);
  * the key pipeline, so the copy_if pass and its intermediate cloud never exist.  Defaults of the
  * reference: use_distance_filter true, 1.0 / 100.0 [REF :100-102]; the launch files set 0.1 / 100.0. */
 int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, double far_thresh);
+/* distance_filter as a call of its own [REF :150, :275-291] for a prefilter WITHOUT a VoxelGrid down-sampler
+ * (downsample_method NONE [REF :70-75]: there is no key pass to fuse the gate into).  The reference applies the gate
+ * to every scan whatever `use_distance_filter` says (it reads the flag [REF :100] and never tests it).  Order kept;
+ * same conventions as the outlier filters (synchronous; host or device-resident; shares their in-flight slot). */
+int b200reg_distance_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, float* out_xyzw, size_t out_capacity, size_t* n_out);
+int b200reg_distance_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double near_thresh, double far_thresh, float* d_out_xyzw, size_t* n_out);
 /* pcl::RadiusOutlierRemoval (outlier_removal_method RADIUS) [REF :88-96,262-273]: a point stays when more
  * than min_neighbors points of the cloud (itself included) lie strictly inside `radius`; order kept.
  * Same calling conventions as the VoxelGrid filter: synchronous, device-resident, and begin / end halves

@@ -126,6 +126,7 @@ class NDT : public Registration {
   const VoxelGridCovariance& cells() const { return target_cells_; }
   // exposed for known-answer tests: score / gradient / Hessian of the source at pose p
   double derivativesAt(const double p[6], double g[6], double H[36], bool compute_hessian);
+  void hessianAt(const double p[6], double H[36]);
   long n_eval = 0;  // derivative passes in the last align (roofline accounting)
   long n_hits = 0;  // (point, voxel) pairs visited in the last align
 

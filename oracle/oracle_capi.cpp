@@ -39,6 +39,8 @@ void to_colmajor(const M4f& m, float* c) {
 extern "C" {
 
 int orc_max_threads() { return omp_get_max_threads(); }
+// explicit thread count for every OpenMP region of the oracle (overrides an inherited OMP_NUM_THREADS: torchrun exports 1)
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 long long orc_voxelgrid(const float* in, long long n, float lx, float ly, float lz, unsigned min_pts, int is_dense, float* out, unsigned* voxel_id, unsigned* count, unsigned* key, int* grid6, int* overflow) {
   VoxelGridResult r = voxelgrid_filter((const Pt*)in, (size_t)n, lx, ly, lz, min_pts, is_dense != 0);
@@ -131,6 +133,8 @@ void orc_ndt_get_leaves(void* hv, unsigned long long* idx, int* npts, double* me
 double orc_ndt_derivatives(void* hv, const double* p6, double* g6, double* H36, int compute_hessian) {
   return ((Handle*)hv)->ndt.derivativesAt(p6, g6, H36, compute_hessian != 0);
 }
+
+void orc_ndt_hessian(void* hv, const double* p6, double* H36) { ((Handle*)hv)->ndt.hessianAt(p6, H36); }
 
 // ---- GICP introspection ----------------------------------------------------
 void orc_gicp_covariances(void* hv, int which, double* out9) {

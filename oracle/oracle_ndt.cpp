@@ -439,4 +439,17 @@ double NDT::derivativesAt(const double p[6], double g[6], double H[36], bool com
   return s;
 }
 
+// computeHessian at an arbitrary pose (the double-precision sweep that closes a line search upstream,
+// A.4 "if step_iterations: computeHessian(H, trans_cloud, x_t)")
+void NDT::hessianAt(const double p[6], double H[36]) {
+  initGauss();
+  M4f T = m4f_from_xyz_euler(p);
+  Cloud tc;
+  transform_cloud(input_, tc, T);
+  computeAngleDerivatives(p);
+  M6 Hm;
+  computeHessian(Hm, tc, p);
+  for (int k = 0; k < 36; ++k) H[k] = Hm.m[k];
+}
+
 }  // namespace orc

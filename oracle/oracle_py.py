@@ -33,6 +33,8 @@ def lib():
         L = C.CDLL(build())
         f32p, f64p, i32p, u32p, u64p = (np.ctypeslib.ndpointer(dtype=t, flags="C_CONTIGUOUS") for t in (np.float32, np.float64, np.int32, np.uint32, np.uint64))
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_voxelgrid.restype = C.c_longlong
         L.orc_voxelgrid.argtypes = [f32p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_uint, C.c_int, f32p, u32p, u32p, u32p, i32p, i32p]
         L.orc_reg_create.restype = C.c_void_p
@@ -55,6 +57,8 @@ def lib():
         L.orc_ndt_get_leaves.argtypes = [C.c_void_p, u64p, i32p, f64p, f64p, f64p, f32p]
         L.orc_ndt_derivatives.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_int]
         L.orc_ndt_derivatives.restype = C.c_double
+        L.orc_ndt_hessian.argtypes = [C.c_void_p, f64p, f64p]
+        L.orc_ndt_hessian.restype = None
         L.orc_gicp_covariances.argtypes = [C.c_void_p, C.c_int, f64p]
         L.orc_knn.argtypes = [f32p, C.c_longlong, f32p, C.c_longlong, C.c_int, i32p, f32p]
         L.orc_distance_filter.argtypes = [f32p, C.c_longlong, C.c_double, C.c_double, f32p]
@@ -258,6 +262,12 @@ class Registration:
         H = np.zeros(36)
         s = lib().orc_ndt_derivatives(self._h, np.ascontiguousarray(p, np.float64), g, H, int(compute_hessian))
         return s, g, H.reshape(6, 6)
+
+    def ndt_hessian(self, p):
+        """pclomp computeHessian (double arithmetic, serial) at pose p: what closes a More-Thuente line search upstream."""
+        H = np.zeros(36)
+        lib().orc_ndt_hessian(self._h, np.ascontiguousarray(p, np.float64), H)
+        return H.reshape(6, 6)
 
     def gicp_covariances(self, which, n):
         out = np.zeros((max(n, 1), 9))

@@ -149,12 +149,13 @@ def test_factory_parameter_handling_mirrors_the_reference(monkeypatch):
     assert out.getvalue() == "registration: FAST_GICP\n"
     assert calls == [("ctor", "FastGICP"), ("setNumThreads", 0), ("setTransformationEpsilon", 0.01), ("setMaximumIterations", 64), ("setMaxCorrespondenceDistance", 2.0),
                      ("setCorrespondenceRandomness", 20)]
-    # unknown strings: the reference warns "use NDT" and takes its NDT branch (:88-91); the mirror
-    # prints the same warning and hands out the engine's NDT
+    # unknown strings: the reference warns "use NDT" (:88-91) and, the string holding no "OMP", hands out the
+    # single-thread pcl NDT (:94-99) — not a method this engine replaces: same warning, then the same refusal as "NDT".
+    # An unknown string that does hold "OMP" reaches the NDT_OMP branch (:100-119) and gets the engine.
     calls.clear()
-    R.select_registration_method(dict(registration_method="SOMETHING"), out=io.StringIO())
+    R.select_registration_method(dict(registration_method="MY_OMP_THING"), out=io.StringIO())
     assert calls[0] == ("ctor", "NormalDistributionsTransform")
-    for m in ("FAST_VGICP", "ICP", "GICP", "GICP_OMP", "NDT"):
+    for m in ("FAST_VGICP", "ICP", "GICP", "GICP_OMP", "NDT", "SOMETHING"):
         with pytest.raises(NotImplementedError):
             R.select_registration_method(dict(registration_method=m), out=io.StringIO())
 

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 DEVNULL = open(os.devnull, "w")
 ODOM = dict(keyframe_delta_trans=1.0, keyframe_delta_angle=1.0, keyframe_delta_time=10000.0, downsample_method="NONE", registration_method="NDT_OMP", reg_resolution=1.0,
             reg_nn_search_method="DIRECT7", reg_transformation_epsilon=0.01, reg_maximum_iterations=64)
-PRE = dict(downsample_method="VOXELGRID", downsample_resolution=0.1)
+# a plain VoxelGrid: the nodelet's outlier filter and distance gate have tests of their own (test_prefilter_chain.py)
+PRE = dict(downsample_method="VOXELGRID", downsample_resolution=0.1, outlier_removal_method="NONE", b200_skip_distance_filter=True)
 
 
 @pytest.fixture(scope="module")
@@ -177,3 +178,30 @@ def test_prepared_promotion_changes_no_pose(scans):
         ndt.preparePromotion()
     assert e.value.code == eng._lib.E_STATE
     eng.select_registration_method(dict(registration_method="FAST_GICP"), out=DEVNULL).preparePromotion()
+
+
+def test_odometry_downsamples_device_scans_with_its_own_voxelgrid(scans):
+    """downsample_method VOXELGRID in the odometry nodelet [REF apps/scan_matching_odometry_nodelet.cpp:85-89,155-165]
+    on device-resident scans: the filter's outputs rotate through caller-owned device buffers; without them the
+    mirror says so instead of crashing."""
+    import torch
+    import delta_graph_slam_b200 as eng
+    _, clouds = scans
+    params = dict(ODOM, downsample_method="VOXELGRID", downsample_resolution=0.2)
+    host = eng.ScanMatchingOdometry(params, out=DEVNULL)
+    want = [host.matching(0.1 * k, c) for k, c in enumerate(clouds[:4])]
+    cap = max(len(c) for c in clouds)
+    d_in = [torch.from_numpy(c).cuda() for c in clouds[:4]]
+    d_out = torch.empty((3, cap, 4), dtype=torch.float32, device="cuda")
+    bufs = [eng.DeviceCloud(d_out[j].data_ptr(), cap, d_out) for j in range(3)]
+    dev = eng.ScanMatchingOdometry(params, out=DEVNULL, downsample_bufs=bufs)
+    got = [dev.matching(0.1 * k, eng.DeviceCloud(t.data_ptr(), len(t), t)) for k, t in enumerate(d_in)]
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    bare = eng.ScanMatchingOdometry(params, out=DEVNULL)
+    with pytest.raises(ValueError):
+        bare.matching(0.0, eng.DeviceCloud(d_in[0].data_ptr(), len(d_in[0]), d_in[0]))
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.2, 0.2, 0.2)
+    vg.setInputCloud(eng.DeviceCloud(d_in[0].data_ptr(), len(d_in[0]), d_in[0]))
+    with pytest.raises(ValueError):
+        vg.filter()

@@ -107,7 +107,7 @@ def test_gicp_keyframe_promotion_keeps_structures(eng, scans):
     a.setInputTarget(k0)
     a.setInputSource(k1)
     a.align(None)
-    a.setInputTarget(k1)      # promoted on the device (same array object as the source)
+    a.promoteSourceToTarget()  # keyframe = filtered; setInputTarget(keyframe), on the device
     a.setInputSource(k2)
     a.align(None)
     b.setInputTarget(k1.copy())

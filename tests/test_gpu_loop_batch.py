@@ -180,6 +180,34 @@ def test_loop_detector_batch_equals_reference_serial_loop(eng, oracle, scenario)
     assert total_diverged <= 1
 
 
+def test_loop_detector_with_fast_gicp_runs_the_serial_loop(eng, oracle, scenario):
+    """registration_method FAST_GICP is what the launch file gives the loop detector [REF launch/delta_graph_slam.launch:95]:
+    no batch path for it, so LoopDetector drives the handle through the reference's own sequence (setInputTarget once,
+    then setInputSource / align / getFitnessScore per candidate) and must agree with the oracle's FAST_GICP doing the same."""
+    from delta_graph_slam_b200.loop_detector import KeyFrame, LoopDetector, isometry2d
+    clouds, pairs = scenario["clouds"], scenario["pairs"]
+    params = dict(distance_thresh=35.0, accum_distance_thresh=8.0, min_edge_interval=1.0, fitness_score_thresh=0.5, registration_method="FAST_GICP")
+    ref_reg = oracle.Registration(oracle.GICP, trans_eps=0.01, max_iter=64, max_corr_dist=2.5, k_corr=20)
+    ld_ref = LoopDetector(params, registration=ref_reg, out=io.StringIO())
+    ld_gpu = LoopDetector(params, out=io.StringIO())
+    assert not ld_gpu.batch_capable() and ld_gpu.registration.cloudCount() == 0
+    new_est = isometry2d(3.0, -1.0, 0.2)
+    new = KeyFrame(0, clouds[0], new_est, accum_distance=100.0)
+    old = []
+    for p in pairs[pairs["target_id"] == 0]:
+        g = np.array(p["guess"], np.float64).reshape(4, 4).T
+        g2 = np.array([[g[0, 0], g[0, 1], g[0, 3]], [g[1, 0], g[1, 1], g[1, 3]], [0, 0, 1.0]])
+        old.append(KeyFrame(int(p["source_id"]), clouds[int(p["source_id"])], new_est @ g2, accum_distance=1.0))
+    c0, s0, T0 = ld_ref.register_candidates(old, new)
+    c1, s1, T1 = ld_gpu.register_candidates(old, new)
+    assert c0 == c1 and ld_gpu.registration.cloudCount() == 0
+    for a, b, Ta, Tb in zip(s0, s1, T0, T1):
+        assert np.max(np.abs(Ta[:3, 3] - Tb[:3, 3])) < TOL_T and rot_angle(Ta[:3, :3], Tb[:3, :3]) < TOL_R
+        assert abs(a - b) <= TOL_FIT * abs(a)
+    la, lb = ld_ref.matching(old, new), ld_gpu.matching(old, new)
+    assert (la is None) == (lb is None) and (la is None or la.key2.id == lb.key2.id)
+
+
 def test_page_locked_keyframes_are_read_after_the_put_returns(eng, scenario):
     """b200reg_cloud_put of a page-locked cloud does not wait for the DMA (keyframe clouds are immutable in the
     reference); the batch call, or b200reg_cloud_sync, is where the caller's memory is released."""

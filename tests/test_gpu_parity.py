@@ -159,6 +159,46 @@ def test_ndt_align_parity(eng, oracle, scans, search):
         assert abs(f1 - f0) <= TOL_FIT * f0
 
 
+def test_closing_hessian_of_a_line_search_float_per_hit_against_upstream_double(eng, oracle, scans):
+    """Upstream closes a More-Thuente search that took extra trials with computeHessian — a serial, all-double sweep
+    (oracle_ndt.cpp NDT::computeHessian, A.4) — where every other Hessian comes from computeDerivatives' float per-hit
+    algebra.  The engine takes the float per-hit Hessian its last trial pass accumulated anyway (csrc/ndt_align.cuh).
+    This quantifies that substitution at the level where it could matter: the Hessian itself and the Newton step it
+    yields, and then checks registrations whose line searches DID iterate against the oracle (which runs the double sweep)."""
+    ref = oracle.Registration(oracle.NDT, resolution=1.0, nn_search=oracle.DIRECT7, trans_eps=0.01, max_iter=64)
+    ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0, reg_nn_search_method="DIRECT7"))
+    for r in (ref, ndt):
+        r.setInputTarget(scans["ds0"])
+        r.setInputSource(scans["ds1"])
+    worst_h, worst_step = 0.0, 0.0
+    for p in ([0, 0, 0, 0, 0, 0], [0.4, -0.1, 0.03, 0.01, -0.02, 0.05], [0.5, 0.0, 0.0, 0.0, 0.0, 0.003], [0.9, 0.05, 0.0, 3.13, 3.12, -3.1], [0.2, 0.3, -0.05, -0.03, 0.02, -0.08]):
+        p = np.array(p, np.float64)
+        _, g, H_engine = ndt.ndt_derivatives(p)       # float per-hit, double sums: what the engine's trial pass holds
+        H_double = ref.ndt_hessian(p)                  # upstream's closing sweep
+        rel = np.max(np.abs(H_engine - H_double)) / np.max(np.abs(H_double))
+        step_e, step_d = np.linalg.solve(H_engine, -g), np.linalg.solve(H_double, -g)
+        # upstream normalises delta_p and walks at most step_size = 0.1 along it: the pose change of the next iteration
+        walk = lambda d: d / np.linalg.norm(d) * min(np.linalg.norm(d), 0.1)
+        worst_h, worst_step = max(worst_h, rel), max(worst_step, float(np.max(np.abs(walk(step_e) - walk(step_d)))))
+    print(f"closing Hessian: float-per-hit vs double sweep, max relative entry difference {worst_h:.2e}, max difference of the next Newton step {worst_step:.2e} (m | rad)")
+    assert worst_h < 2e-6 and worst_step < 1e-6  # two orders below the 1e-4 parity bar
+    # registrations whose line search took more than one trial (evaluations > passes: a closing sweep was folded away)
+    folded = 0
+    for k, (tx, ty, yaw) in enumerate([(0.0, 0.0, 0.0), (0.7, 0.05, 0.01), (1.6, -0.3, 0.03), (-0.4, 0.5, -0.05), (2.2, 0.0, 0.0), (1.0, 0.8, 0.08), (0.3, -0.9, -0.1)]):
+        guess = np.eye(4, dtype=np.float32)
+        guess[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+        guess[:3, 3] = [tx, ty, 0.0]
+        ref.align(guess)
+        ndt.align(guess)
+        res, info = ndt.getResult(), ref.info()
+        assert res["iterations"] == ref.getFinalNumIteration() and res["evaluations"] == int(info[1]), f"guess {k}: same path"
+        T0, T1 = ref.getFinalTransformation(), ndt.getFinalTransformation()
+        if res["evaluations"] > res["passes"]:
+            folded += 1
+            assert np.max(np.abs(T1[:3, 3] - T0[:3, 3])) < TOL_T and rot_angle(T0[:3, :3], T1[:3, :3]) < TOL_R, f"guess {k}"
+    assert folded >= 2, "the guesses must exercise line searches with extra trials"
+
+
 def test_ndt_recovers_ground_truth(eng, scans):
     ndt = eng.select_registration_method(dict(registration_method="NDT_OMP", reg_resolution=1.0))
     ndt.setInputTarget(scans["ds0"])
@@ -208,7 +248,8 @@ def test_fitness_exact_nn(eng, oracle, scans):
 
 
 def test_odometry_keyframe_promotion(eng, oracle, scans):
-    """setInputTarget(keyframe = last source) must equal uploading the same cloud again."""
+    """promoteSourceToTarget (keyframe = last source; setInputTarget(keyframe)) must equal uploading the same cloud again,
+    and as in PCL the cloud stays the input source until a new one is set."""
     a = eng.NormalDistributionsTransform()
     b = eng.NormalDistributionsTransform()
     for r in (a, b):
@@ -216,11 +257,30 @@ def test_odometry_keyframe_promotion(eng, oracle, scans):
         r.setInputTarget(scans["ds0"])
     src = scans["ds1"]
     a.setInputSource(src)
-    a.setInputTarget(src)          # promoted on the device
+    a.promoteSourceToTarget()      # changes role on the device
     b.setInputTarget(src.copy())   # uploaded
     La, Lb = a.ndt_leaves(), b.ndt_leaves()
     assert np.array_equal(La["idx"], Lb["idx"]) and np.array_equal(La["n"], Lb["n"])
     assert np.array_equal(La["icov"], Lb["icov"])
+    # pcl still holds the promoted cloud as input_: an align now registers it against itself
+    b.setInputSource(src)
+    for r in (a, b):
+        r.align(None)
+    assert a.hasConverged() and np.array_equal(a.getFinalTransformation(), b.getFinalTransformation())
+    assert a.getFitnessScore() == b.getFitnessScore() and a.getFitnessScore() < 1e-9
+    # refilling the caller's buffer in place after setInputSource must not leak into a later setInputTarget of that array
+    c = eng.NormalDistributionsTransform()
+    c.setResolution(1.0)
+    buf = scans["ds0"].copy()
+    c.setInputTarget(scans["ds0"])
+    c.setInputSource(buf)
+    buf[: len(scans["ds1"])] = scans["ds1"][: len(buf)]
+    c.setInputTarget(buf)          # the CURRENT contents are uploaded (no identity shortcut)
+    d = eng.NormalDistributionsTransform()
+    d.setResolution(1.0)
+    d.setInputTarget(buf.copy())
+    Lc, Ld = c.ndt_leaves(), d.ndt_leaves()
+    assert np.array_equal(Lc["idx"], Ld["idx"]) and np.array_equal(Lc["icov"], Ld["icov"])
 
 
 def test_cooperative_and_multi_kernel_sort_paths_agree(eng, oracle, scans):

@@ -96,6 +96,51 @@ def test_loop_detector_on_plain_registration_surface(oracle, scenario):
     assert serial.detect(old, [KeyFrame(1, clouds[1], isometry2d(0.6, 0, 0), 52.0)]) == []
 
 
+def test_batch_path_is_ndt_only_and_the_keyframe_cache_is_bounded(oracle, scenario):
+    """A registration object whose batch call cannot take its method (FAST_GICP, the launch file's loop-detector
+    method [REF launch/delta_graph_slam.launch:95]) runs the reference's serial loop; cached keyframes beyond the cap
+    are dropped least-recently-used first, never one of the running batch."""
+    from delta_graph_slam_b200 import _lib
+    clouds, pairs = scenario
+    log = []
+
+    class GicpLike(OracleBatchEngine):
+        method = _lib.METHOD_GICP
+
+        def alignBatch(self, *a, **k):
+            raise AssertionError("the batch path must not be taken for a FAST_GICP handle")
+
+        def __getattr__(self, name):  # the pcl::Registration surface, served by the oracle's NDT object
+            return getattr(self.reg, name)
+
+    old = [KeyFrame(int(p["source_id"]), clouds[int(p["source_id"])], isometry2d(0.4 * k, 0.0, 0.0), 1.0) for k, p in enumerate(pairs[:3])]
+    new = KeyFrame(0, clouds[0], isometry2d(0.5, 0.0, 0.0), 50.0)
+    params = dict(distance_thresh=5.0, accum_distance_thresh=8.0, min_edge_interval=5.0, fitness_score_thresh=10.0)
+    serial = LoopDetector(params, registration=oracle.Registration(oracle.NDT, resolution=1.0, nn_search=2, trans_eps=0.01, max_iter=64), out=io.StringIO())
+    gicp_like = LoopDetector(params, registration=GicpLike(oracle), out=io.StringIO())
+    assert not gicp_like.batch_capable()
+    la, lb = serial.detect(old, [new]), gicp_like.detect(old, [new])
+    assert len(la) == len(lb) == 1 and la[0].key2.id == lb[0].key2.id and la[0].score == lb[0].score
+
+    class Counting(OracleBatchEngine):
+        def cloudPut(self, cid, cloud):
+            log.append(("put", int(cid)))
+            super().cloudPut(cid, cloud)
+
+        def cloudDrop(self, cid):
+            log.append(("drop", int(cid)))
+            del self.clouds[int(cid)]
+
+    ld = LoopDetector(dict(params, b200_max_cached_keyframes=3), registration=Counting(oracle), out=io.StringIO())
+    ld.register_candidates(old[:2], new)              # 3 clouds cached: at the cap
+    assert [e for e in log if e[0] == "drop"] == []
+    ld.register_candidates(old[2:3], new)             # one more: the least recently used candidate goes
+    assert [e for e in log if e[0] == "drop"] == [("drop", old[0].id)]
+    assert set(ld._cached) == {new.id, old[1].id, old[2].id} and set(ld.registration.clouds) == set(ld._cached)
+    ld.register_candidates(old[:3], new)              # a batch larger than the cap keeps all of its own clouds
+    assert set(ld._cached) == {new.id, old[0].id, old[1].id, old[2].id}
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

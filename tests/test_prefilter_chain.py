@@ -146,6 +146,26 @@ def test_prefilter_mirror_reads_the_reference_parameters(monkeypatch):
     assert ("sor", "setMeanK", 12) in calls and ("sor", "setStddevMulThresh", 2.5) in calls
     with pytest.raises(NotImplementedError):
         odo.Prefilter(dict(downsample_method="APPROX_VOXELGRID"), out=io.StringIO())
+    # no parameters at all: the nodelet's own defaults [REF apps/prefiltering_nodelet.cpp:56-57,77-80,100-102]
+    calls.clear()
+    out = io.StringIO()
+    pre = odo.Prefilter({}, out=out)
+    assert out.getvalue().splitlines() == ["downsample: VOXELGRID 0.1", "outlier_removal: STATISTICAL 20 - 1"]
+    assert calls == [("vg", "setLeafSize", 0.1, 0.1, 0.1), ("sor", "setMeanK", 20), ("sor", "setStddevMulThresh", 1.0), ("vg", "setDistanceFilter", True, 1.0, 100.0)]
+    # use_distance_filter = false changes nothing: the reference reads the flag (:100) and gates every scan anyway (:150)
+    calls.clear()
+    odo.Prefilter(dict(use_distance_filter=False, outlier_removal_method="NONE"), out=io.StringIO())
+    assert calls == [("vg", "setLeafSize", 0.1, 0.1, 0.1), ("vg", "setDistanceFilter", True, 1.0, 100.0)]
+    # the mirror's own opt-out
+    calls.clear()
+    pre = odo.Prefilter(dict(b200_skip_distance_filter=True, outlier_removal_method="NONE"), out=io.StringIO())
+    assert calls == [("vg", "setLeafSize", 0.1, 0.1, 0.1)] and not pre.distance_filter_on
+    # downsample NONE: the gate becomes a call of its own on the outlier filter's handle
+    calls.clear()
+    out = io.StringIO()
+    pre = odo.Prefilter(dict(downsample_method="NONE", outlier_removal_method="RADIUS"), out=out)
+    assert out.getvalue().splitlines() == ["downsample: NONE", "outlier_removal: RADIUS 0.8 - 2"]
+    assert pre.filter is None and pre.distance_filter_on and pre._reg is pre.outlier_removal_filter._reg
 
 
 @pytest.mark.gpu
@@ -288,6 +308,37 @@ def test_statistical_outlier_removal_edge_cases(oracle):
         ror.filter()
     sor.setInputCloud(c)  # and the handle carries on
     assert bits_equal(sor.filter(), oracle.statistical_outlier_removal(c, 20, 1.0))
+
+
+@pytest.mark.gpu
+def test_distance_filter_alone_and_the_chain_without_a_voxelgrid(oracle):
+    """downsample_method NONE [REF apps/prefiltering_nodelet.cpp:70-75]: distance_filter is a call of its own
+    (b200reg_distance_filter), host and device-resident, bit-exact and order-preserving; then the nodelet's default
+    STATISTICAL filter on the gated cloud."""
+    import torch
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(5)
+    c = cloud_with_outliers(oracle, rng)
+    reg = eng.Registration()
+    for near, far in ((1.0, 100.0), (0.1, 100.0), (5.0, 20.0), (200.0, 300.0)):
+        want = oracle.distance_filter(c, near, far)
+        assert bits_equal(reg.distance_filter(c, near, far), want)
+        t = torch.from_numpy(c).cuda()
+        o = torch.empty_like(t)
+        f = reg.distance_filter(eng.DeviceCloud(t.data_ptr(), len(t), t), near, far, out=eng.DeviceCloud(o.data_ptr(), len(o), o))
+        assert f.n == len(want) and bits_equal(o[: f.n].cpu().numpy(), want)
+    assert len(reg.distance_filter(np.zeros((0, 4), np.float32))) == 0
+    pinned = torch.empty((len(c), 4), dtype=torch.float32, pin_memory=True).numpy()
+    assert bits_equal(np.array(reg.distance_filter(c, 1.0, 100.0, out=pinned)), oracle.distance_filter(c, 1.0, 100.0))
+    small = c[::3].copy()
+    pre = eng.Prefilter(dict(downsample_method="NONE"), out=DEVNULL)  # defaults: gate 1 .. 100, STATISTICAL 20 - 1
+    assert bits_equal(pre.filter3d(small), oracle.statistical_outlier_removal(oracle.distance_filter(small, 1.0, 100.0), 20, 1.0))
+    pre = eng.Prefilter(dict(downsample_method="NONE", outlier_removal_method="NONE", distance_near_thresh=5.0, distance_far_thresh=20.0), out=DEVNULL)
+    assert bits_equal(pre.filter3d(small), oracle.distance_filter(small, 5.0, 20.0))
+    # the reference's defaults end to end: gate fused into the VoxelGrid, then STATISTICAL
+    pre = eng.Prefilter({}, out=DEVNULL)
+    want = oracle.statistical_outlier_removal(oracle.voxelgrid(oracle.distance_filter(c, 1.0, 100.0), 0.1, is_dense=False)["out"], 20, 1.0)
+    assert bits_equal(pre.filter3d(c), want)
 
 
 @pytest.mark.gpu
