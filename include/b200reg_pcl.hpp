@@ -22,10 +22,13 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <pcl/registration/registration.h>
+#include <pcl/search/kdtree.h>
 
 #include <cfloat>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "b200reg.h"
 
@@ -49,6 +52,57 @@ inline b200reg_handle* create(int method, int device) {
 inline const float* xyz(const pcl::PointCloud<pcl::PointXYZ>& c) { return c.points.empty() ? nullptr : reinterpret_cast<const float*>(c.points.data()); }
 }  // namespace detail
 
+// The search object the adapters install with setSearchMethodTarget(tree, /*force_no_recompute=*/true).
+//
+// pcl::Registration::align() -> initCompute() rebuilds a FLANN kd-tree over the target every time the target changed
+//  — 10-20 ms of single-thread CPU work per keyframe switch [REF apps/scan_matching_odometry_nodelet.cpp:180,254]
+// and per loop-closure target [REF include/hdl_graph_slam/loop_detector.hpp:124] that the engine never uses (its own exact-NN
+// structure lives on the GPU).  With force_no_recompute PCL leaves the tree alone, and this subclass only REMEMBERS the
+// target.  The real tree is built on first use, so the base class's non-virtual getFitnessScore() and a caller that takes
+// getSearchMethodTarget() [REF apps/scan_matching_odometry_nodelet.cpp:327] still get exact answers — they pay for the tree
+// only if they ask for it.
+class LazyKdTree : public pcl::search::KdTree<pcl::PointXYZ> {
+ public:
+  using Base = pcl::search::KdTree<pcl::PointXYZ>;
+  using Ptr = pcl::shared_ptr<LazyKdTree>;
+  using PointCloudConstPtr = Base::PointCloudConstPtr;
+  using IndicesConstPtr = Base::IndicesConstPtr;
+
+  void setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& indices = IndicesConstPtr()) override {
+    std::lock_guard<std::mutex> lock(mutex_);
+    pending_ = cloud;
+    pending_indices_ = indices;
+    dirty_ = true;
+  }
+  PointCloudConstPtr getInputCloud() const override {
+    std::lock_guard<std::mutex> lock(mutex_);
+    return dirty_ ? pending_ : Base::getInputCloud();
+  }
+  int nearestKSearch(const pcl::PointXYZ& point, int k, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const override {
+    ensure_built();
+    return Base::nearestKSearch(point, k, k_indices, k_sqr_distances);
+  }
+  int radiusSearch(const pcl::PointXYZ& point, double radius, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances, unsigned int max_nn = 0) const override {
+    ensure_built();
+    return Base::radiusSearch(point, radius, k_indices, k_sqr_distances, max_nn);
+  }
+  int builds() const { return builds_; }  // how many real trees were built (adapter check)
+
+ private:
+  void ensure_built() const {
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!dirty_) return;
+    if (pending_) const_cast<LazyKdTree*>(this)->Base::setInputCloud(pending_, pending_indices_);
+    dirty_ = false;
+    ++builds_;
+  }
+  mutable std::mutex mutex_;
+  PointCloudConstPtr pending_;
+  IndicesConstPtr pending_indices_;
+  mutable bool dirty_ = false;
+  mutable int builds_ = 0;
+};
+
 // Common part of the two registration adapters.
 class RegistrationBase : public pcl::Registration<pcl::PointXYZ, pcl::PointXYZ, float> {
  public:
@@ -67,8 +121,9 @@ class RegistrationBase : public pcl::Registration<pcl::PointXYZ, pcl::PointXYZ, 
   void setNumThreads(int n) { num_threads_ = n; }  // reg_num_threads: the CUDA grid replaces OpenMP
 
   void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
-    Base::setInputTarget(cloud);  // keeps target_ / target_cloud_updated_ so the base getFitnessScore still works
+    Base::setInputTarget(cloud);  // keeps target_ so the base getFitnessScore / getSearchMethodTarget still work
     if (!cloud || cloud->points.empty()) return;  // PCL_ERROR + return upstream; previous target stays
+    lazy_tree_->setInputCloud(cloud);  // remembered, not built (initCompute no longer touches the tree)
     if (b200reg_set_target(h_, detail::xyz(*cloud), cloud->points.size(), sizeof(pcl::PointXYZ)) != B200REG_OK) PCL_ERROR("[b200reg::setInputTarget] %s\n", b200reg_last_error(h_));
   }
   void setInputSource(const PointCloudSourceConstPtr& cloud) override {
@@ -91,9 +146,13 @@ class RegistrationBase : public pcl::Registration<pcl::PointXYZ, pcl::PointXYZ, 
   }
   int getFinalNumIteration() const { return this->nr_iterations_; }
   b200reg_handle* handle() { return h_; }
+  const LazyKdTree& lazyTree() const { return *lazy_tree_; }
 
  protected:
-  RegistrationBase(int method, int device) : h_(detail::create(method, device)) {}
+  RegistrationBase(int method, int device) : h_(detail::create(method, device)), lazy_tree_(new LazyKdTree) {
+    // no FLANN build inside align(): see LazyKdTree
+    this->setSearchMethodTarget(lazy_tree_, /*force_no_recompute=*/true);
+  }
 
   void push_common() {
     b200reg_set_transformation_epsilon(h_, this->transformation_epsilon_);
@@ -125,6 +184,7 @@ class RegistrationBase : public pcl::Registration<pcl::PointXYZ, pcl::PointXYZ, 
   virtual void push_params() = 0;
 
   b200reg_handle* h_ = nullptr;
+  LazyKdTree::Ptr lazy_tree_;
   b200reg_result last_{};
   int num_threads_ = 0;
 };
