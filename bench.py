@@ -393,9 +393,11 @@ def odometry_parity_vs_oracle(eng, host_clouds, frames, odom_params, dev, filter
         if fo.shape != fe.shape or not np.array_equal(np.asarray(fo).view(np.uint32), np.asarray(fe).view(np.uint32)):
             out["voxelgrid_mismatches"] += 1
         first = odo_o.keyframe is None
+        kf_o, kf_e = odo_o.num_keyframes, odo_e.num_keyframes
         po, pe = odo_o.matching(0.1 * k, fo), odo_e.matching(0.1 * k, fe)
         if first:
             continue
+        switched = odo_o.num_keyframes > kf_o or odo_e.num_keyframes > kf_e
         ro, re_ = odo_o.registration, odo_e.registration.getResult()
         if odom_params["registration_method"] == "NDT_OMP":
             if re_["iterations"] != ro.getFinalNumIteration() or re_["evaluations"] != int(ro.info()[1]):
@@ -404,16 +406,20 @@ def odometry_parity_vs_oracle(eng, host_clouds, frames, odom_params, dev, filter
             out["path_diverged"] += 1
         dt, dr = transform_deltas(re_["transformation"], ro.getFinalTransformation())
         dto, dro = transform_deltas(pe, po)
-        f_o, f_e = ro.getFitnessScore(), odo_e.registration.getFitnessScore()
-        f_same = odo_e.registration.calcFitnessScore(ro.getFinalTransformation())
         out["max_dt"], out["max_dr"] = max(out["max_dt"], dt), max(out["max_dr"], dr)
         out["max_dt_odom"], out["max_dr_odom"] = max(out["max_dt_odom"], dto), max(out["max_dr_odom"], dro)
-        out["max_rel_fitness"] = max(out["max_rel_fitness"], abs(f_same - f_o) / abs(f_o))
-        out["max_rel_fitness_own_transform"] = max(out["max_rel_fitness_own_transform"], abs(f_e - f_o) / abs(f_o))
+        out["frames_outside_1e-4"] = out.get("frames_outside_1e-4", 0) + int(dt >= 1e-4 or dr >= 1e-4)
+        if not switched:  # after a keyframe switch the registration objects hold the NEW target: no status figure for that frame
+            f_o, f_e = ro.getFitnessScore(), odo_e.registration.getFitnessScore()
+            f_same = odo_e.registration.calcFitnessScore(ro.getFinalTransformation())
+            out["max_rel_fitness"] = max(out["max_rel_fitness"], abs(f_same - f_o) / abs(f_o))
+            out["max_rel_fitness_own_transform"] = max(out["max_rel_fitness_own_transform"], abs(f_e - f_o) / abs(f_o))
     out["keyframes_equal"] = bool(odo_o.num_keyframes == odo_e.num_keyframes)
     out["keyframes"] = int(odo_e.num_keyframes)
     out["within_tolerance"] = bool(out["max_dt"] < 1e-4 and out["max_dr"] < 1e-4 and out["max_dt_odom"] < 1e-4 and out["max_dr_odom"] < 1e-4 and out["max_rel_fitness"] < 1e-5 and
                                    out["voxelgrid_mismatches"] == 0 and out["keyframes_equal"])
+    out["note"] = ("free-running comparison; frames on which the reference algorithm itself is not reproducible to 1e-4 m under a 3-ulp change of its initial guess "
+                   "(measured per frame in tests/test_gpu_odometry_sequence.py) may exceed the bar on either side")
     return out
 
 

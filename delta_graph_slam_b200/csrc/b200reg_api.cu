@@ -92,6 +92,7 @@ struct b200reg_handle {
   DevBuf<b200reg_result> d_result;
   DevBuf<double> partials, deriv;
   DevBuf<long long> prof;
+  DevBuf<double> trace;  // developer trace of the profiled align kernel (b200reg_get_trace)
   DevBuf<unsigned int> barriers;
   PinnedBuf<unsigned char> pin_small;  // results / jobs staging
 
@@ -308,7 +309,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_pass<uint32_t>)); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -454,6 +455,11 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
   job->done_seq = ++h->align_seq;
   job->deriv_out = h->deriv.p;
   job->prof = h->prof.p;
+  if (h->profile) {
+    B200_CUDA_TRY(h->trace.reserve((size_t)(kTraceCap + 1) * kTraceDoubles));
+    B200_CUDA_TRY(cudaMemsetAsync(h->trace.p, 0, (size_t)(kTraceCap + 1) * kTraceDoubles * sizeof(double), h->stream));
+    job->trace = h->trace.p;
+  }
   if (p_eval) {
     job->eval_only = 1;
     for (int i = 0; i < 6; ++i) job->p0[i] = p_eval[i];
@@ -639,7 +645,7 @@ int b200reg_destroy(b200reg_handle* h) {
   if (h->mail) cudaFreeHost((void*)h->mail);
   h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
   h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
-  h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release();
+  h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release(); h->trace.release();
   h->nn.release(); h->fit_partials.release();
   h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release(); h->sor_dist.release(); h->sor_stats.release(); h->sor_pending.release(); h->sor_n_pending.release();
   h->gicp_corr.release(); h->gicp_pending.release(); h->gicp_n_pending.release(); h->gicp_jobs.release();
@@ -1489,9 +1495,19 @@ int b200reg_cloud_count(b200reg_handle* h, size_t* out) {
 
 // do_align = 0: no registration, the pair's `guess` IS the transform the fitness is evaluated at
 // (b200reg_calc_fitness_batch); only the exact-NN product of the targets is needed then
-static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int do_align, int with_fitness, double fitness_max_range, b200reg_result* results) {
+// results == nullptr with d_results_out != nullptr: the records stay on the device (slot i of *d_results_out belongs to
+// pairs[i]); everything is only ENQUEUED on the handle's stream — the multi-GPU entry (b200reg_multi.cu) gathers them
+// with one NCCL all-gather and synchronises once.  `min_slots`: capacity the record array must have (the gather's slot).
+static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int do_align, int with_fitness, double fitness_max_range, b200reg_result* results,
+                     b200reg_result** d_results_out = nullptr, size_t min_slots = 0) {
   auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || (n_pairs && (!pairs || !results))) return B200REG_E_INVALID;
+  const bool keep_on_device = results == nullptr && d_results_out != nullptr;
+  if (!h || (n_pairs && (!pairs || (!results && !keep_on_device)))) return B200REG_E_INVALID;
+  if (keep_on_device) {
+    if (set_device(h)) return B200REG_E_CUDA;
+    B200_CUDA_TRY(h->batch_results.reserve(std::max(n_pairs, min_slots) + 1));
+    *d_results_out = h->batch_results.p;
+  }
   if (!n_pairs) return B200REG_OK;
   if (do_align && h->cfg.method != B200REG_METHOD_NDT) { h->err = "align_batch: this handle's registration method has no batch path"; return B200REG_E_STATE; }
   int rc = set_device(h);
@@ -1654,6 +1670,10 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
     }
     if (h->timing) B200_CUDA_TRY(cudaEventRecord(evf1, h->stream));
   }
+  if (keep_on_device) {
+    if (evf0) { cudaEventDestroy(evf0); cudaEventDestroy(evf1); }
+    return B200REG_OK;
+  }
   B200_CUDA_TRY(cudaMemcpyAsync(hr, h->batch_results.p, n_pairs * sizeof(b200reg_result), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   memcpy(results, hr, n_pairs * sizeof(b200reg_result));
@@ -1675,6 +1695,23 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
 
 int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
   return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, results);
+}
+
+// internal (not in include/b200reg.h): the batch enqueued only, records left on the device — see b200reg_multi.cu
+int b200reg_internal_align_batch_device(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, size_t min_slots, b200reg_result** d_results) {
+  if (!d_results) return B200REG_E_INVALID;
+  if (!n_pairs) {  // a device without a share still takes part in the gather: it needs a send buffer
+    b200reg_pair none;
+    (void)none;
+    auto set_error = [&](const std::string& s) { h->err = s; };
+    if (!h) return B200REG_E_INVALID;
+    int rc = set_device(h);
+    if (rc) return rc;
+    B200_CUDA_TRY(h->batch_results.reserve(min_slots + 1));
+    *d_results = h->batch_results.p;
+    return B200REG_OK;
+  }
+  return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, nullptr, d_results, min_slots);
 }
 
 int b200reg_calc_fitness_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, double max_range, double* out) {
@@ -1809,6 +1846,24 @@ int b200reg_get_profile(b200reg_handle* h, long long* out6) {
   return B200REG_OK;
 }
 
+int b200reg_get_trace(b200reg_handle* h, double* out, size_t cap_records, size_t* n_records) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !n_records) return B200REG_E_INVALID;
+  *n_records = 0;
+  if (!h->trace.p || !h->profile) { h->err = "no trace: b200reg_set_profile(h, 1) before the align"; return B200REG_E_STATE; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  std::vector<double> t((size_t)(kTraceCap + 1) * kTraceDoubles);
+  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  B200_CUDA_TRY(cudaMemcpy(t.data(), h->trace.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  size_t n = (size_t)t[0];
+  if (n > (size_t)kTraceCap) n = kTraceCap;
+  *n_records = n;
+  // record k (1-based: pass k) starts at k * kTraceDoubles; record 0's first slot is the count
+  for (size_t k = 0; k < n && k < cap_records && out; ++k) memcpy(out + k * kTraceDoubles, t.data() + (k + 1) * kTraceDoubles, kTraceDoubles * sizeof(double));
+  return B200REG_OK;
+}
+
 int b200reg_set_sm_budget(b200reg_handle* h, int n_sm) {
   if (!h || n_sm < 1) return B200REG_E_INVALID;
   if (n_sm > h->dev_sm) n_sm = h->dev_sm;
@@ -1828,7 +1883,7 @@ int b200reg_set_side_budget(b200reg_handle* h, int n_sm) {
 }
 
 int b200reg_set_sort_path(int path) {
-  if (path < 0 || path > 1) return B200REG_E_INVALID;
+  if (path < 0 || path > 3) return B200REG_E_INVALID;
   sort_path_override() = path;
   return B200REG_OK;
 }

@@ -65,7 +65,9 @@ struct NdtJob {
   unsigned int done_seq;
   double* deriv_out;       // device, 1 + 6 + 36 doubles (eval_only)
   long long* prof;         // device, optional: SM cycles of CTA 0 per phase {pass, reduce, barrier, total, step, n, stage}
+  double* trace;           // device, optional (profiled instantiation): kTraceDoubles per pass, at most kTraceCap passes; trace[-1 record] holds the count
 };
+constexpr int kTraceDoubles = 12, kTraceCap = 255;
 
 // Full loop batches: maximal runs of consecutive jobs that share a target, and one counter per run.
 struct NdtTargetQueue {
@@ -924,6 +926,13 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
           }
         }
         if (PROF && tid == 0) prof[7] += tb - t4;
+      }
+      if (PROF && job.trace && rank == 0 && tid == 0 && s.n_pass <= kTraceCap) {
+        // one record per pass, the quantities the oracle's trace holds (oracle.hpp NDT::trace)
+        double* r = job.trace + (size_t)s.n_pass * kTraceDoubles;
+        r[0] = s.nr_iterations; r[1] = s.step_iterations; r[2] = s.a_t; r[3] = s.tot[0]; r[4] = s.phi_t; r[5] = s.d_phi_t; r[6] = s.psi_t; r[7] = s.d_psi_t;
+        r[8] = s.open_interval; r[9] = s.interval_converged; r[10] = s.phi_0; r[11] = s.d_phi_0;
+        job.trace[0] = (double)s.n_pass;
       }
       __syncthreads();
       if (PROF) {

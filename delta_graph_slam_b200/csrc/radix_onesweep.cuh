@@ -1,0 +1,222 @@
+// b200reg — stable LSD radix sort of (key, 32-bit value) pairs with ONE sweep over the data per digit:
+// chained-scan ("decoupled look-back") digit passes in the manner of Onesweep (Adinets & Merrill 2022).
+//
+// voxel_sort.cuh sorts with three launches per digit (tile histograms -> one-block scan -> scatter): every key is
+// read twice per digit and the one-block scan caps the tile count at 256 (2 M points).  The cooperative kernel of
+// voxel_coop.cuh removes the launches but pays 13 grid barriers and is limited to one tile per SM.  Here:
+//
+//   k_os_histogram : ONE read of the keys builds the digit histograms of ALL passes (per-CTA shared-memory
+//                    histograms, one atomicAdd per bin and CTA into hist[pass][256]);
+//   k_os_pass      : per digit, one launch.  A CTA takes the next tile from a ticket counter (so every lower tile has
+//                    started), counts its digits per warp, publishes the tile's 256 counts as "aggregate" status
+//                    words, looks back over the preceding tiles' status words until it meets an inclusive prefix,
+//                    publishes its own inclusive prefix, and scatters — keys and values are read once and written
+//                    once per digit.  Inside a tile every warp owns a contiguous slice and ranks its keys in lane
+//                    order (match_any), tiles are ordered by the look-back: the sort is stable, so its output is
+//                    bit-identical to the three-launch path.
+//
+// Digit passes beyond the number of significant key bits (device-resident: it depends on the data) return at once,
+// as in voxel_sort.cuh; the sorted data then sits in buffer A or B according to the parity of the passes that ran.
+// No grid barrier, no cooperative launch, any number of tiles, two to four resident CTAs per SM.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kOsThreads = 256;
+constexpr int kOsRadixBits = 8;
+constexpr int kOsRadix = 256;
+constexpr int kOsItems = 16;                       // keys per thread: 4096-key tiles
+constexpr int kOsTile = kOsThreads * kOsItems;
+constexpr int kOsLookBack = 8;                     // predecessor tiles inspected per round trip of the look-back
+constexpr uint32_t kOsFlagAggregate = 1u << 30, kOsFlagPrefix = 2u << 30, kOsFlagMask = 3u << 30, kOsCountMask = ~kOsFlagMask;
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t os_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & (kOsRadix - 1); }
+
+// all digit histograms in one read of the keys.  hist: [max_passes][256], zeroed before the launch.
+template <typename KeyT>
+static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* __restrict__ keys, int n, const uint32_t* __restrict__ nbits_ptr, int max_passes, uint32_t* __restrict__ hist) {
+  constexpr int MAXP = (int)sizeof(KeyT);
+  __shared__ uint32_t s[MAXP][kOsRadix];
+  const uint32_t nbits = *nbits_ptr;
+  const int passes = min(max_passes, (int)((nbits + kOsRadixBits - 1) / kOsRadixBits));
+  for (int i = threadIdx.x; i < MAXP * kOsRadix; i += kOsThreads) (&s[0][0])[i] = 0;
+  __syncthreads();
+  // whole warps walk the keys together (the trip count is warp-uniform), so equal digits inside a warp — the rule
+  // for the upper digits of voxel keys — are counted with one shared-memory atomic instead of up to 32 serialised ones
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * kOsThreads + (threadIdx.x & ~31)); base < n; base += gridDim.x * kOsThreads) {
+    const int i = base + lane;
+    const bool ok = i < n;
+    const KeyT k = ok ? keys[i] : (KeyT)0;
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t dgt = ok ? os_digit(k, p * kOsRadixBits) : (uint32_t)kOsRadix;
+      const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+      if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&s[p][dgt], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t c = s[p][threadIdx.x];
+    if (c) atomicAdd(hist + p * kOsRadix + threadIdx.x, c);
+  }
+}
+
+// One digit pass.  status: [n_tiles][256] words of this pass (zero = not yet published); ticket: this pass's tile
+// counter (zero before the launch).
+template <typename KeyT>
+static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
+                                                        int pass, const uint32_t* __restrict__ nbits_ptr, const uint32_t* __restrict__ hist, uint32_t* status, unsigned int* ticket) {
+  if ((uint32_t)(pass * kOsRadixBits) >= *nbits_ptr) return;
+  constexpr int WARPS = kOsThreads / 32;
+  __shared__ uint32_t cnt[WARPS][kOsRadix];
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < WARPS * kOsRadix; i += kOsThreads) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const int shift = pass * kOsRadixBits;
+  const int wbase = tile * kOsTile + warp * (32 * kOsItems);
+  KeyT k[kOsItems];
+  uint32_t v[kOsItems];
+  // ---- A: per-warp digit counts (all loads of the slice issued before the first use)
+#pragma unroll
+  for (int r = 0; r < kOsItems; ++r) {
+    const int i = wbase + r * 32 + lane;
+    k[r] = i < n ? keys_in[i] : (KeyT)0;
+  }
+#pragma unroll
+  for (int r = 0; r < kOsItems; ++r) {
+    const int i = wbase + r * 32 + lane;
+    v[r] = i < n ? vals_in[i] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < kOsItems; ++r) {
+    const int i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;  // kOsRadix = "no element"
+    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- B: thread d owns digit d.  Tile count -> publish -> look back -> publish the inclusive prefix
+  {
+    const int d = tid;
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) c += cnt[w][d];
+    volatile uint32_t* st = status + (size_t)tile * kOsRadix + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      *st = kOsFlagPrefix | c;
+    } else {
+      *st = kOsFlagAggregate | c;
+      // look back kOsLookBack tiles at a time: the loads are independent (one L2 round trip per batch, not per
+      // tile) and are then consumed in order; a word that is not published yet ends the batch and is polled again.
+      // (When every tile of a small sort is resident at once they all publish aggregates together and the prefix has
+      // to travel the whole chain: walking it one dependent load at a time would cost a round trip per tile.)
+      int t = tile - 1;
+      bool done = false;
+      while (!done) {
+        uint32_t w[kOsLookBack];
+#pragma unroll
+        for (int j = 0; j < kOsLookBack; ++j) {
+          const int tt = t - j;
+          w[j] = tt >= 0 ? *(volatile const uint32_t*)(status + (size_t)tt * kOsRadix + d) : kOsFlagPrefix;  // in front of tile 0: an empty prefix
+        }
+        int used = 0;
+#pragma unroll
+        for (int j = 0; j < kOsLookBack; ++j) {
+          if (!done && used == j && (w[j] & kOsFlagMask) != 0u) {
+            excl += w[j] & kOsCountMask;
+            used = j + 1;
+            if (w[j] & kOsFlagPrefix) done = true;
+          }
+        }
+        t -= used;
+      }
+      *st = kOsFlagPrefix | (excl + c);
+    }
+    // first output slot of digit d = keys with a smaller digit (global histogram) + this digit in lower tiles
+    const uint32_t total_d = hist[pass * kOsRadix + d];
+    uint32_t incl = total_d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      if (w < warp) off += s_warp[w];
+    uint32_t run = off + incl - total_d + excl;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const uint32_t cw = cnt[w][d];
+      cnt[w][d] = run;
+      run += cw;
+    }
+  }
+  __syncthreads();
+  // ---- C: ranks inside the warp round, in lane order; scatter
+#pragma unroll
+  for (int r = 0; r < kOsItems; ++r) {
+    const int i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;
+    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t dst = 0;
+    if (ok) dst = cnt[warp][dgt] + rank;
+    __syncwarp();
+    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      keys_out[dst] = k[r];
+      vals_out[dst] = v[r];
+    }
+  }
+}
+
+// Scratch of the sort: digit histograms, tile status words, tickets — one region per pass, zeroed with a single
+// memset in front of the histogram kernel.
+struct OneSweepScratch {
+  DevBuf<uint32_t> buf;
+  int tiles(int n) const { return n > 0 ? (n + kOsTile - 1) / kOsTile : 1; }
+  size_t words(int n, int max_passes) const { return (size_t)max_passes * (kOsRadix + 32 + (size_t)tiles(n) * kOsRadix); }
+};
+
+// enqueue: sorts (keys_a, vals_a)[0..n) by the low *nbits_ptr key bits (device-resident count, <= 8 * max_passes);
+// pass p reads A when p is even, B when odd, so the result lies in B after an odd number of passes that ran.
+template <typename KeyT>
+inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const uint32_t* nbits_ptr, int max_passes) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e;
+  const int n_tiles = sc.tiles(n);
+  const size_t words = sc.words(n, max_passes);
+  if ((e = sc.buf.reserve(words)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(sc.buf.p, 0, words * sizeof(uint32_t), st)) != cudaSuccess) return e;
+  uint32_t* hist = sc.buf.p;                                   // [max_passes][256]
+  unsigned int* tickets = sc.buf.p + (size_t)max_passes * kOsRadix;  // [max_passes][32] (one 128-byte line each)
+  uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
+  int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
+  if (hb > kNumSM * 4) hb = kNumSM * 4;
+  launch_counter() += 1 + max_passes;
+  k_os_histogram<KeyT><<<hb, kOsThreads, 0, st>>>(keys_a, n, nbits_ptr, max_passes, hist);
+  for (int p = 0; p < max_passes; ++p) {
+    const KeyT* ki = (p & 1) ? keys_b : keys_a;
+    const uint32_t* vi = (p & 1) ? vals_b : vals_a;
+    KeyT* ko = (p & 1) ? keys_a : keys_b;
+    uint32_t* vo = (p & 1) ? vals_a : vals_b;
+    k_os_pass<KeyT><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -9,6 +9,7 @@
 // kernels that need them read them there.
 #pragma once
 #include "common.cuh"
+#include "radix_onesweep.cuh"
 
 namespace b200 {
 
@@ -387,7 +388,10 @@ static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restr
 struct VoxelSort;
 // voxel_coop.cuh: the whole pipeline as one cooperative kernel; false = cloud too large, take the multi-kernel path
 bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4* d_pts, int n, int is_dense, PointGate gate, float lx, float ly, float lz, bool keep_point_keys, cudaError_t* err);
-// 0 = cooperative single kernel when the cloud fits (default), 1 = always the multi-kernel path (A/B tests)
+// 0 = default: the cooperative single kernel for clouds up to kCoopDefaultMax points, the one-sweep sort above that;
+// 1 = always the three-launch-per-digit path (A/B tests, <= 2 M points); 2 = always the one-sweep sort; 3 = always the
+// cooperative kernel when the cloud fits it
+constexpr int kCoopDefaultMax = 400000;
 inline int& sort_path_override() {
   static int v = 0;
   return v;
@@ -398,12 +402,13 @@ struct VoxelSort {
   DevBuf<int> mm;
   DevBuf<unsigned int> coop_bar;
   DevBuf<SortMeta> meta;
+  OneSweepScratch onesweep;
   int n = 0;
   int max_ctas = kNumSM;  // CTAs the cooperative path may occupy (b200reg_set_sm_budget)
 
   void release() {
     keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); hist.release(); tile_heads.release(); tile_valid.release();
-    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release(); coop_bar.release();
+    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release(); coop_bar.release(); onesweep.buf.release();
   }
 
   // enqueue: keys -> sort -> segmentation.  Afterwards (on the stream):
@@ -421,15 +426,18 @@ struct VoxelSort {
     if ((e = mm.reserve(8)) != cudaSuccess) return e;
     if ((e = meta.reserve(1)) != cudaSuccess) return e;
     if (keep_point_keys && (e = point_key.reserve(nn)) != cudaSuccess) return e;
-    if (sort_path_override() == 0) {
+    const int path = sort_path_override();
+    if ((path == 0 && n <= kCoopDefaultMax) || path == 3) {
       cudaError_t ce = cudaSuccess;
       if (launch_voxel_sort_coop(*this, st, d_pts, n, is_dense, gate, lx, ly, lz, keep_point_keys, &ce)) return ce;
     }
+    const bool one_sweep = path != 1;
     int items = 4;
     while (items < 32 && (n + kSortThreads * items - 1) / (kSortThreads * items) > 256) items *= 2;
     const int tile = kSortThreads * items;
     const int n_tiles = n > 0 ? (n + tile - 1) / tile : 1;
     const int n_seg_tiles = n > 0 ? (n + 255) / 256 : 1;
+    if (!one_sweep && n_tiles > 256) return cudaErrorInvalidValue;  // the one-block histogram scan holds 65536 counters
     if ((e = hist.reserve((size_t)n_tiles * kRadix)) != cudaSuccess) return e;
     if ((e = tile_heads.reserve(n_seg_tiles)) != cudaSuccess) return e;
     if ((e = tile_valid.reserve(n_seg_tiles)) != cudaSuccess) return e;
@@ -442,7 +450,10 @@ struct VoxelSort {
     if (mm_blocks > kNumSM * 2) mm_blocks = kNumSM * 2;
     if (n > 0) k_minmax<<<mm_blocks, 256, 0, st>>>(d_pts, n, is_dense, gate, mm.p);
     k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, gate, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
-    if (n > 0) {
+    if (n > 0 && one_sweep) {
+      // one read of the keys for all digit histograms, then one launch per digit with chained tile prefixes
+      if ((e = onesweep_sort<uint32_t>(st, onesweep, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n, &meta.p->nbits, 4)) != cudaSuccess) return e;
+    } else if (n > 0) {
       for (int pass = 0; pass < 4; ++pass) {
         const uint32_t* ki = (pass & 1) ? keys_b.p : keys_a.p;
         const uint32_t* vi = (pass & 1) ? vals_b.p : vals_a.p;

@@ -89,3 +89,66 @@ def needed_clouds(pairs, shard):
     """ids of the clouds a rank has to hold for its share (targets and sources)."""
     sub = np.asarray(pairs)[shard]
     return sorted(set(sub["target_id"].tolist()) | set(sub["source_id"].tolist()))
+
+
+class MultiGpuBatch:
+    """b200reg_batch_* (include/b200reg.h): the loop-candidate batch over several GPUs from ONE process — what a C++
+    LoopDetector links against (the multi-process form above is what bench.py runs under torchrun).  Same sharding rule
+    as shard_by_target; one NCCL all-gather of the result records inside the library."""
+
+    def __init__(self, devices, params=None):
+        import ctypes as C
+        p = dict(params or {})
+        L = _lib.load()
+        cfg = _lib.Config()
+        L.b200reg_default_config(_lib.METHOD_NDT, C.byref(cfg))
+        cfg.resolution = float(p.get("reg_resolution", 0.5))
+        cfg.transformation_epsilon = float(p.get("reg_transformation_epsilon", 0.01))
+        cfg.maximum_iterations = int(p.get("reg_maximum_iterations", 64))
+        cfg.nn_search = {"KDTREE": _lib.KDTREE, "DIRECT1": _lib.DIRECT1}.get(p.get("reg_nn_search_method", "DIRECT7"), _lib.DIRECT7)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = C.c_void_p()
+        rc = L.b200reg_batch_create(C.byref(cfg), devs, len(devices), C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            raise _lib.B200RegError(rc, "b200reg_batch_create failed (a listed device is not a usable sm_100 GPU, or NCCL is not loadable for more than one device)")
+        self.devices = list(devices)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().b200reg_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != _lib.OK:
+            raise _lib.B200RegError(rc, _lib.load().b200reg_batch_last_error(self._h).decode())
+
+    def cloudPut(self, cloud_id, cloud):
+        c = _lib.as_cloud(cloud)
+        self._keep[int(cloud_id)] = c  # the library keeps the pointer, so the array must stay alive
+        self._ck(_lib.load().b200reg_batch_cloud_put(self._h, int(cloud_id), c.ctypes.data if len(c) else None, len(c), 16))
+
+    def cloudDrop(self, cloud_id):
+        self._ck(_lib.load().b200reg_batch_cloud_drop(self._h, int(cloud_id)))
+        self._keep.pop(int(cloud_id), None)
+
+    def alignBatch(self, pairs, with_fitness=True, fitness_max_range=float(np.finfo(np.float64).max)):
+        arr = np.ascontiguousarray(pairs) if isinstance(pairs, np.ndarray) and pairs.dtype == PAIR_DTYPE else make_pairs(pairs)
+        out = np.zeros(len(arr), RESULT_DTYPE)
+        if len(arr):
+            self._ck(_lib.load().b200reg_batch_run(self._h, arr.ctypes.data, len(arr), int(with_fitness), float(fitness_max_range), out.ctypes.data))
+        return out
+
+    def info(self):
+        import ctypes as C
+        n, nc, ver, ms = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        per = (C.c_int * len(self.devices))()
+        self._ck(_lib.load().b200reg_batch_get_info(self._h, C.byref(n), C.byref(nc), C.byref(ver), per, C.byref(ms)))
+        return dict(n_devices=n.value, uses_nccl=bool(nc.value), nccl_version=ver.value, pairs_per_device=list(per), gather_ms=ms.value)

@@ -252,6 +252,13 @@ class Registration:
         return dict(zip(("pass", "reduce", "barrier", "total", "step", "n", "stage", "step_solve_mt", "step_trig", "step_tables",
                          "st_totals", "st_interval", "st_trial", "st_newton_end", "st_solve", "st_newton_begin"), v.tolist()))
 
+    def trace(self, cap=255):
+        """Per-pass More-Thuente quantities of the last profiled NDT align (b200reg_get_trace), (n, 12) float64."""
+        out = np.zeros((cap, 12))
+        n = C.c_size_t()
+        self._ck(_lib.load().b200reg_get_trace(self._h, out.ctypes.data, cap, C.byref(n)))
+        return out[: min(n.value, cap)]
+
     def nn_stats(self):
         v = np.zeros(3, np.int64)
         self._ck(_lib.load().b200reg_get_nn_stats(self._h, v.ctypes.data))

@@ -277,6 +277,29 @@ int b200reg_calc_fitness_batch(b200reg_handle* h, const b200reg_pair* pairs, siz
 /* with timing on: CUDA-event durations of the last batch's align kernel and fitness kernels */
 int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double* fitness_ms);
 
+/* ---- loop-closure batches over several GPUs of one box, single process ----
+ * hdl_graph_slam::LoopDetector is one C++ object in one process [REF include/hdl_graph_slam/loop_detector.hpp:33-187;
+ * apps/delta_graph_slam_nodelet.cpp:816-824], so the multi-GPU form of b200reg_align_batch lives behind one object too:
+ * one engine handle per listed device, whole targets (a new keyframe with all of its candidates) dealt to the devices so
+ * every target's structures are built on exactly one GPU, and — the path shards, there is no data-path collective — ONE
+ * NCCL all-gather of the result records as the only exchange (ncclCommInitAll inside; NCCL is loaded at run time and is
+ * required only for n_devices > 1).  results[i] belongs to pairs[i], exactly as b200reg_align_batch returns them.
+ *
+ * b200reg_batch_cloud_put registers a keyframe cloud by id and KEEPS THE POINTER: the cloud must stay valid and unchanged
+ * until it is dropped or the object destroyed (keyframe clouds are immutable for the whole run in the reference
+ * [REF include/hdl_graph_slam/keyframe.hpp:25-59]); it is uploaded once, to the device that first needs it.
+ * `cfg->device` is ignored (the device list decides); `cfg->method` must be B200REG_METHOD_NDT. */
+typedef struct b200reg_multi b200reg_multi;
+int b200reg_batch_create(const b200reg_config* cfg, const int* devices, int n_devices, b200reg_multi** out);
+int b200reg_batch_destroy(b200reg_multi* m);
+const char* b200reg_batch_last_error(const b200reg_multi* m);
+int b200reg_batch_cloud_put(b200reg_multi* m, int64_t id, const float* xyzw, size_t n, size_t stride_bytes);
+int b200reg_batch_cloud_drop(b200reg_multi* m, int64_t id);
+int b200reg_batch_run(b200reg_multi* m, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results);
+/* after a run: device count, whether NCCL carried the gather (and its version code), pairs each device registered
+ * (n_devices ints), CUDA-event duration of the all-gather on device 0.  Any pointer may be NULL. */
+int b200reg_batch_get_info(b200reg_multi* m, int* n_devices, int* uses_nccl, int* nccl_version, int* pairs_per_device, double* gather_ms);
+
 /* introspection of the NDT target grid (parity tests): number of occupied voxels, then per
  * voxel (ascending linear index): index, point count (-1 = rejected by the eigenvalue test),
  * mean[3], cov[9], icov[9] (row-major doubles), centroid[3] floats.  Any pointer may be NULL. */
@@ -302,9 +325,15 @@ int b200reg_get_profile(b200reg_handle* h, long long* out16);
 /* the counters are compiled into a separate instantiation of the align kernels (they cost registers the
  * production kernel does not have to spare): off by default, single registrations only */
 int b200reg_set_profile(b200reg_handle* h, int on);
+/* developer trace of the last profiled NDT align: one record of 12 doubles per pass over the source
+ * {nr_iterations, step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t, open_interval, interval_converged, phi_0, d_phi_0}
+ * (the More-Thuente quantities after the pass was digested), the counterpart of the oracle's NDT::trace */
+int b200reg_get_trace(b200reg_handle* h, double* out, size_t cap_records, size_t* n_records);
 
-/* A/B switch for tests (process-wide): 0 = the voxel key / sort / segmentation pipeline runs as one
- * cooperative kernel when the cloud fits one tile per SM (default), 1 = always the multi-kernel path */
+/* A/B switch for tests (process-wide) of the voxel key / sort / segmentation pipeline: 0 = default (one cooperative
+ * kernel for clouds up to 400 k points, the one-sweep chained-scan radix sort above that), 1 = always the three-launch-per-
+ * digit path (<= 2 M points), 2 = always the one-sweep sort, 3 = the cooperative kernel whenever the cloud fits one tile
+ * per SM.  All paths are stable sorts of the same keys: bit-identical output (tested). */
 int b200reg_set_sort_path(int path);
 
 /* developer counters of the last getFitnessScore / inlier-fraction search: {queries, queries the

@@ -129,6 +129,9 @@ class NDT : public Registration {
   void hessianAt(const double p[6], double H[36]);
   long n_eval = 0;  // derivative passes in the last align (roofline accounting)
   long n_hits = 0;  // (point, voxel) pairs visited in the last align
+  // developer trace of the last align: one record of 12 doubles per line-search evaluation
+  // {nr_iterations, step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t, open_interval, interval_converged, phi_0, d_phi_0}
+  std::vector<double> trace;
 
  protected:
   void computeTransformation(Cloud& output, const M4f& guess) override;

@@ -134,6 +134,13 @@ double orc_ndt_derivatives(void* hv, const double* p6, double* g6, double* H36, 
   return ((Handle*)hv)->ndt.derivativesAt(p6, g6, H36, compute_hessian != 0);
 }
 
+// developer trace of the last NDT align (oracle.hpp NDT::trace): returns the number of 12-double records, copies up to cap
+long long orc_ndt_trace(void* hv, double* out, long long cap) {
+  const std::vector<double>& t = ((Handle*)hv)->ndt.trace;
+  const long long n = (long long)t.size() / 12;
+  for (long long i = 0; i < n && i < cap; ++i) std::memcpy(out + 12 * i, t.data() + 12 * i, 12 * sizeof(double));
+  return n;
+}
 void orc_ndt_hessian(void* hv, const double* p6, double* H36) { ((Handle*)hv)->ndt.hessianAt(p6, H36); }
 
 // ---- GICP introspection ----------------------------------------------------

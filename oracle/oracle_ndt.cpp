@@ -354,6 +354,11 @@ double NDT::computeStepLengthMT(const double x[6], V6& step_dir, double step_ini
   double d_phi_t = -v6_dot(g, step_dir);
   double psi_t = aux_psi(a_t, phi_t, phi_0, d_phi_0, mu);
   double d_psi_t = aux_dpsi(d_phi_t, d_phi_0, mu);
+  auto rec = [&]() {
+    const double r[12] = {(double)nr_iterations_, (double)step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t, open_interval ? 1.0 : 0.0, interval_converged ? 1.0 : 0.0, phi_0, d_phi_0};
+    trace.insert(trace.end(), r, r + 12);
+  };
+  rec();
   while (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
     if (open_interval)
       a_t = trialValueSelectionMT(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
@@ -381,6 +386,7 @@ double NDT::computeStepLengthMT(const double x[6], V6& step_dir, double step_ini
     else
       interval_converged = updateIntervalMT(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
     step_iterations++;
+    rec();
   }
   if (step_iterations) computeHessian(H, trans_cloud, x_t);
   return a_t;
@@ -391,6 +397,7 @@ void NDT::computeTransformation(Cloud& output, const M4f& guess) {
   converged_ = false;
   n_eval = 0;
   n_hits = 0;
+  trace.clear();
   initGauss();
   if (!m4f_is_identity(guess)) {
     final_transformation_ = guess;

@@ -57,6 +57,8 @@ def lib():
         L.orc_ndt_get_leaves.argtypes = [C.c_void_p, u64p, i32p, f64p, f64p, f64p, f32p]
         L.orc_ndt_derivatives.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_int]
         L.orc_ndt_derivatives.restype = C.c_double
+        L.orc_ndt_trace.argtypes = [C.c_void_p, f64p, C.c_longlong]
+        L.orc_ndt_trace.restype = C.c_longlong
         L.orc_ndt_hessian.argtypes = [C.c_void_p, f64p, f64p]
         L.orc_ndt_hessian.restype = None
         L.orc_gicp_covariances.argtypes = [C.c_void_p, C.c_int, f64p]
@@ -262,6 +264,13 @@ class Registration:
         H = np.zeros(36)
         s = lib().orc_ndt_derivatives(self._h, np.ascontiguousarray(p, np.float64), g, H, int(compute_hessian))
         return s, g, H.reshape(6, 6)
+
+    def ndt_trace(self, cap=1024):
+        """Line-search evaluations of the last NDT align: rows {nr_iterations, step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t,
+        open_interval, interval_converged, phi_0, d_phi_0}."""
+        out = np.zeros((cap, 12))
+        n = lib().orc_ndt_trace(self._h, out, cap)
+        return out[: min(n, cap)]
 
     def ndt_hessian(self, p):
         """pclomp computeHessian (double arithmetic, serial) at pose p: what closes a More-Thuente line search upstream."""

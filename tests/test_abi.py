@@ -115,6 +115,23 @@ def test_no_cpu_fallback_without_a_gpu():
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f"{f} reaches into oracle/"
 
 
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_multi_gpu_batch_entry_validates_and_fails_loudly_without_devices():
+    L = _lib.load()
+    cfg = _lib.Config()
+    L.b200reg_default_config(_lib.METHOD_NDT, C.byref(cfg))
+    m = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert L.b200reg_batch_create(C.byref(cfg), devs, 0, C.byref(m)) == _lib.E_INVALID
+    assert L.b200reg_batch_create(C.byref(cfg), (C.c_int * 2)(3, 3), 2, C.byref(m)) == _lib.E_INVALID  # one handle per GPU
+    assert L.b200reg_batch_create(C.byref(cfg), devs, 2, C.byref(m)) == _lib.E_CUDA and not m.value
+    assert L.b200reg_batch_destroy(None) == _lib.E_INVALID
+    assert L.b200reg_batch_last_error(None) == b"null batch object"
+    from delta_graph_slam_b200.loop_batch import MultiGpuBatch
+    with pytest.raises(pkg.B200RegError):
+        MultiGpuBatch([0])
+
+
 def test_factory_parameter_handling_mirrors_the_reference(monkeypatch):
     """select_registration_method: names, defaults, banners and the unknown-method warning of
     [REF src/hdl_graph_slam/registrations.cpp:22-124], checked against a recording stand-in handle."""

@@ -49,6 +49,18 @@ def test_dense_voxelgrid_full_size(eng, oracle, dense):
     ref = oracle.voxelgrid(raw, 0.1, is_dense=False)
     assert np.array_equal(lay["key"], ref["key"]) and np.array_equal(lay["count"], ref["count"]) and np.array_equal(lay["voxel_id"], ref["voxel_id"])
     assert np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+    # at this size the default is the one-sweep sort; the cooperative kernel and the three-launch path must agree with it
+    from delta_graph_slam_b200 import _lib
+    L = _lib.load()
+    try:
+        for path in (3, 1, 2):
+            assert L.b200reg_set_sort_path(path) == 0
+            vg2 = eng.VoxelGrid()
+            vg2.setLeafSize(0.1, 0.1, 0.1)
+            vg2.setInputCloud(raw, is_dense=False)
+            assert np.array_equal(vg2.filter().view(np.uint32), out.view(np.uint32)), path
+    finally:
+        L.b200reg_set_sort_path(0)
 
 
 @pytest.mark.parametrize("search", ["DIRECT1", "DIRECT7"])

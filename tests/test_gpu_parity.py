@@ -184,7 +184,7 @@ def test_closing_hessian_of_a_line_search_float_per_hit_against_upstream_double(
     assert worst_h < 2e-6 and worst_step < 1e-6  # two orders below the 1e-4 parity bar
     # registrations whose line search took more than one trial (evaluations > passes: a closing sweep was folded away)
     folded = 0
-    for k, (tx, ty, yaw) in enumerate([(0.0, 0.0, 0.0), (0.7, 0.05, 0.01), (1.6, -0.3, 0.03), (-0.4, 0.5, -0.05), (2.2, 0.0, 0.0), (1.0, 0.8, 0.08), (0.3, -0.9, -0.1)]):
+    for k, (tx, ty, yaw) in enumerate([(0.0, 0.0, 0.0), (0.7, 0.05, 0.01), (1.6, -0.3, 0.03), (-0.4, 0.5, -0.05), (2.2, 0.0, 0.0), (1.0, 0.8, 0.08), (0.2, -0.3, -0.02)]):
         guess = np.eye(4, dtype=np.float32)
         guess[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
         guess[:3, 3] = [tx, ty, 0.0]
@@ -284,13 +284,14 @@ def test_odometry_keyframe_promotion(eng, oracle, scans):
 
 
 def test_cooperative_and_multi_kernel_sort_paths_agree(eng, oracle, scans):
-    """The voxel key / sort / segmentation pipeline as ONE cooperative kernel (default) against the
-    multi-kernel path: identical keys, order, runs, centroids and NDT leaves, bit for bit."""
+    """The voxel key / sort / segmentation pipeline as ONE cooperative kernel (default at this size) against the
+    three-launch-per-digit path and the one-sweep chained-scan sort: identical keys, order, runs, centroids and NDT
+    leaves, bit for bit (all three are stable sorts of the same keys)."""
     from delta_graph_slam_b200 import _lib
     L = _lib.load()
     outs = []
     try:
-        for path in (0, 1):
+        for path in (0, 1, 2, 3):
             assert L.b200reg_set_sort_path(path) == 0
             vg = eng.VoxelGrid()
             vg.setLeafSize(0.1, 0.1, 0.1)
@@ -309,12 +310,14 @@ def test_cooperative_and_multi_kernel_sort_paths_agree(eng, oracle, scans):
             outs.append((out, lay, G, small.filter()))
     finally:
         L.b200reg_set_sort_path(0)
-    (o0, l0, g0, s0), (o1, l1, g1, s1) = outs
-    assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
-    for k in ("voxel_id", "count", "key", "min_b", "div_b"):
-        assert np.array_equal(l0[k], l1[k]), k
-    for k in ("idx", "n", "mean", "cov", "icov"):
-        assert np.array_equal(g0[k], g1[k]), k
+    assert L.b200reg_set_sort_path(4) != 0
+    (o0, l0, g0, s0) = outs[0]
+    for path, (o1, l1, g1, s1) in enumerate(outs[1:], start=1):
+        assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32)), path
+        for k in ("voxel_id", "count", "key", "min_b", "div_b"):
+            assert np.array_equal(l0[k], l1[k]), (path, k)
+        for k in ("idx", "n", "mean", "cov", "icov"):
+            assert np.array_equal(g0[k], g1[k]), (path, k)
     ref = oracle.voxelgrid(scans["raw0"], 0.1, is_dense=False)
     vg = eng.VoxelGrid()
     vg.setLeafSize(0.1, 0.1, 0.1)
