@@ -67,7 +67,7 @@ struct NdtJob {
   long long* prof;         // device, optional: SM cycles of CTA 0 per phase {pass, reduce, barrier, total, step, n, stage}
   double* trace;           // device, optional (profiled instantiation): kTraceDoubles per pass, at most kTraceCap passes; trace[-1 record] holds the count
 };
-constexpr int kTraceDoubles = 12, kTraceCap = 255;
+constexpr int kTraceDoubles = 13, kTraceCap = 255;
 
 // Full loop batches: maximal runs of consecutive jobs that share a target, and one counter per run.
 struct NdtTargetQueue {
@@ -83,7 +83,6 @@ struct NdtShared {
   float h_ang[15][3];
   int need_hessian;
   int phase;
-  int solve_req;       // the state machine stopped in front of the 6x6 solve: warp 0 solves H dp = -g together
   double neg_g[6], dp[6];
   int new_pose;  // the step asked for an evaluation at a new x_t (T / tables must be rebuilt)
   // optimiser state (identical in every CTA of the group)
@@ -96,6 +95,7 @@ struct NdtShared {
   double gauss_d1, gauss_d2;
   double trig[6][2];  // sin, cos of: float-rounded angles (T) [0..2], double angles (tables) [3..5]
   double tot[kAccStride];
+  int solve_path;  // developer trace: how the last H dp = -g was solved (0 none, 1 block closed form, 2 pivoted elimination, 3 SVD)
   long long pf[6];  // developer cycle counters inside ndt_step: {totals -> state, line-search update, trial value, Newton end, 6x6 solve, Newton begin rest}
   double red[kAlignWarps][kAccStride];
 };
@@ -285,168 +285,192 @@ __host__ __device__ constexpr int hidx(int i, int j) { return 7 + i * 6 - (i * (
 // ---- the optimiser state machine; one lane, after every derivative pass ----------------------
 // Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the next pass
 // must be evaluated at s.x_t (the caller then rebuilds T and the angle tables).
-// totals of the pass -> score, gradient, full symmetric Hessian of the optimiser state: 43 copies, one
-// or two per lane of warp 0 instead of a serial loop on the lane that runs the state machine
-__device__ __forceinline__ void ndt_take_totals(NdtShared& s, int lane) {
-  const double* t = s.tot;
-  if (lane == 0) s.score = t[0];
-  if (lane < 6) s.g[lane] = t[1 + lane];
-#pragma unroll
-  for (int e = lane; e < 36; e += 32) {
-    const int i = e / 6, j = e - 6 * i;
-    const int a = i < j ? i : j, b = i < j ? j : i;
-    s.H[e] = t[hidx(a, b)];
-  }
-  __syncwarp();
+// The optimiser step, run by ALL 32 lanes of warp 0 after every derivative pass.
+//
+// The state machine of computeTransformation / computeStepLengthMT (A.4) used to run on one lane with its state in
+// shared memory: ~8.7 k cycles of dependent shared-memory loads, stores and double-precision operations per pass
+// (4.4 us of a 12.4 us pass) while 107 SMs x 16 warps waited at the next barrier.  Here the state is loaded into
+// registers once, every lane executes the (warp-uniform) scalar control flow redundantly, the 6-vectors p, dir, g, x_t live
+// one component per lane (lane i < 6; dot products are three-step butterflies), the Hessian one ROW per lane — which is the
+// layout the warp-level elimination wants, so the 6x6 solve starts without touching memory — and the state goes back to
+// shared memory once at the end.  Leaves the next phase in s.phase (PH_DONE when finished) and sets s.new_pose when the
+// next pass must be evaluated at s.x_t.
+__device__ __forceinline__ double warp_dot6(double a, double b, int lane) {
+  double v = lane < 6 ? a * b : 0.0;
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return __shfl_sync(0xffffffffu, v, 0);  // one value for the whole warp (lanes 8.. hold other butterflies)
 }
 
-// resume = false: a derivative pass has just finished.  resume = true: the solve the previous call asked for
-// (s.solve_req) is in s.dp.  The routine runs on one lane; the solve in between runs on the whole warp.
+#ifndef B200_STEP_ATTR
+#define B200_STEP_ATTR __forceinline__
+#endif
 template <bool PROF>
-static __device__ __noinline__ void ndt_step(NdtShared& s, const NdtParams& prm, bool resume) {
+static __device__ B200_STEP_ATTR void ndt_step_warp(NdtShared& s, const NdtParams& prm, int lane) {
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = prm.step_size, step_min = prm.trans_eps / 2;
-  const double* t = s.tot;
   long long tk = PROF ? clock64() : 0;
   auto lap = [&](int slot) {
-    if (PROF) { const long long now = clock64(); s.pf[slot] += now - tk; tk = now; }
+    if (PROF) { const long long now = clock64(); if (lane == 0) s.pf[slot] += now - tk; tk = now; }
   };
-  bool go_newton_begin = false, go_loop_check = false, go_newton_end = false;
-  bool have_dp = false;
-  s.solve_req = 0;
-  if (resume) {
-    go_newton_begin = true;
-    have_dp = true;
-  } else {
-  s.n_eval++;
-  s.n_pass++;
-  s.hits += t[28];
-  s.new_pose = 0;
-  switch (s.phase) {
-    case PH_INIT:
-    case PH_MT_FIRST:
-      // score, gradient and Hessian were copied out of the totals by the whole warp (ndt_take_totals)
-      if (s.phase == PH_INIT) go_newton_begin = true;
-      else go_loop_check = true;
-      break;
-    case PH_MT_ITER:
-      // A trial pass evaluates the Hessian as well: upstream ends the line search with
-      // computeHessian(x_t) at the LAST trial point — a whole extra pass over the cloud at the pose that
-      // was just evaluated.  Here that Hessian is already in the totals of the last trial pass (same
-      // transform, same tables, same arithmetic as a pass of its own), so the extra pass never runs;
-      // the Hessian of a trial that is not the last one is simply overwritten by the next.
-      go_loop_check = true;
-      break;
-    default:
-      return;
-  }
-  }
+  const int li = lane < 6 ? lane : 0;
+  // ---- state -> registers (independent shared-memory loads, all in flight together)
+  const double* t = s.tot;
+  const double score = t[0];
+  const double g_i = lane < 6 ? t[1 + li] : 0.0;
+  const double hits_pass = t[28];
+  double p_i = s.p[li], dir_i = s.dir[li], x_t_i = 0.0;
+  double phi_0 = s.phi_0, d_phi_0 = s.d_phi_0, a_l = s.a_l, f_l = s.f_l, g_l = s.g_l, a_u = s.a_u, f_u = s.f_u, g_u = s.g_u, a_t = s.a_t;
+  int phase = s.phase, step_iterations = s.step_iterations, open_interval = s.open_interval, interval_converged = s.interval_converged;
+  int nr_iterations = s.nr_iterations, converged = s.converged, n_eval = s.n_eval + 1;
+  double phi_t = 0.0, d_phi_t = 0.0, psi_t = 0.0, d_psi_t = 0.0;
+  int new_pose = 0;
+  bool go_newton_begin = phase == PH_INIT, go_loop_check = phase != PH_INIT, go_newton_end = false;
   lap(0);
   if (go_loop_check) {
-    // the evaluation at a_t just finished
-    s.phi_t = -s.score;
-    double gd = 0;
-    for (int i = 0; i < 6; ++i) gd += s.g[i] * s.dir[i];
-    s.d_phi_t = -gd;
-    s.psi_t = mt_psi(s.a_t, s.phi_t, s.phi_0, s.d_phi_0, mu);
-    s.d_psi_t = mt_dpsi(s.d_phi_t, s.d_phi_0, mu);
-    if (s.phase == PH_MT_ITER) {
-      if (s.open_interval && (s.psi_t <= 0 && s.d_psi_t >= 0)) {
-        s.open_interval = 0;
-        s.f_l = s.f_l + s.phi_0 - mu * s.d_phi_0 * s.a_l;
-        s.g_l = s.g_l + mu * s.d_phi_0;
-        s.f_u = s.f_u + s.phi_0 - mu * s.d_phi_0 * s.a_u;
-        s.g_u = s.g_u + mu * s.d_phi_0;
+    // the evaluation at a_t just finished.  A trial pass (PH_MT_ITER) evaluated the Hessian as well: upstream ends the
+    // line search with computeHessian(x_t) at the LAST trial point — a whole extra pass over the cloud at the pose that
+    // was just evaluated.  Here that Hessian is already in the totals of the last trial pass (same transform, same
+    // tables, same arithmetic as a pass of its own), so the extra pass never runs.
+    phi_t = -score;
+    d_phi_t = -warp_dot6(g_i, dir_i, lane);
+    psi_t = mt_psi(a_t, phi_t, phi_0, d_phi_0, mu);
+    d_psi_t = mt_dpsi(d_phi_t, d_phi_0, mu);
+    if (phase == PH_MT_ITER) {
+      if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+        open_interval = 0;
+        f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
+        g_l = g_l + mu * d_phi_0;
+        f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
+        g_u = g_u + mu * d_phi_0;
       }
-      if (s.open_interval) s.interval_converged = mt_update_interval(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.psi_t, s.d_psi_t);
-      else s.interval_converged = mt_update_interval(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.phi_t, s.d_phi_t);
-      s.step_iterations++;
+      if (open_interval) interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+      else interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+      step_iterations++;
     }
   }
   lap(1);
-  while (true) {
+  while (true) {  // warp-uniform: every lane holds the same scalars
     if (go_loop_check) {
       go_loop_check = false;
-      if (!s.interval_converged && s.step_iterations < 10 && !(s.psi_t <= 0 && s.d_phi_t <= -nu * s.d_phi_0)) {
-        if (s.open_interval) s.a_t = mt_trial_value(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.psi_t, s.d_psi_t);
-        else s.a_t = mt_trial_value(s.a_l, s.f_l, s.g_l, s.a_u, s.f_u, s.g_u, s.a_t, s.phi_t, s.d_phi_t);
-        s.a_t = fmin(s.a_t, step_max);
-        s.a_t = fmax(s.a_t, step_min);
-        for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
-        s.phase = PH_MT_ITER;
-        s.need_hessian = 1;
-        s.new_pose = 1;
+      if (!interval_converged && step_iterations < 10 && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
+        if (open_interval) a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+        else a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+        a_t = fmin(a_t, step_max);
+        a_t = fmax(a_t, step_min);
+        x_t_i = p_i + dir_i * a_t;
+        phase = PH_MT_ITER;
+        new_pose = 1;
         lap(2);
-        return;
+        break;
       }
-      // computeHessian at x_t: taken from the last trial pass (see PH_MT_ITER above); it counts as an
-      // evaluation of the reference's algorithm, not as a pass of ours
-      if (s.step_iterations) s.n_eval++;
+      // computeHessian at x_t: taken from the last trial pass; it counts as an evaluation of the reference's
+      // algorithm, not as a pass of ours
+      if (step_iterations) n_eval++;
       go_newton_end = true;
     }
     if (go_newton_end) {
       go_newton_end = false;
-      for (int i = 0; i < 6; ++i) s.p[i] += s.dir[i] * s.a_t;
-      if (s.nr_iterations > prm.max_iterations || (s.nr_iterations && (fabs(s.a_t) < prm.trans_eps))) s.converged = 1;
-      s.nr_iterations++;
-      if (s.converged) { s.phase = PH_DONE; return; }
+      p_i += dir_i * a_t;
+      if (nr_iterations > prm.max_iterations || (nr_iterations && (fabs(a_t) < prm.trans_eps))) converged = 1;
+      nr_iterations++;
+      if (converged) { phase = PH_DONE; break; }
       go_newton_begin = true;
       lap(3);
     }
     if (go_newton_begin) {
       go_newton_begin = false;
-      if (!have_dp) {  // hand the solve to the warp (warp_solve6 in the caller), come back with resume = true
-        for (int i = 0; i < 6; ++i) s.neg_g[i] = -s.g[i];
-        s.solve_req = 1;
-        lap(5);
-        return;
+      // H dp = -g.  Fast path: every lane solves the system by 3x3 blocks in closed form from the totals (broadcast
+      // shared-memory loads, no exchange between lanes) and verifies the residual; if that refuses (degenerate or strongly
+      // indefinite Hessian) the pivoted elimination runs on the warp, and if a pivot collapses there too, JacobiSVD's
+      // minimum-norm answer on one lane (see small_solve.cuh).
+      double dp_i = 0.0;
+      {
+        double x[6];
+        bool solved = solve6_schur(t + 7, t + 1, x);
+        int path = 1;
+        if (!solved) {  // warp-uniform: every lane computed the same bits
+          path = 2;
+          double r[7];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const int a = li < j ? li : j, b = li < j ? j : li;
+            r[j] = lane < 6 ? t[7 + a * 6 - (a * (a - 1)) / 2 + (b - a)] : 0.0;
+          }
+          r[6] = -g_i;
+          solved = warp_solve6_rows(r, x, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dp_i = lane == j ? x[j] : dp_i;
+        if (!solved) {
+          path = 3;
+          if (lane < 6) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const int a = li < j ? li : j, b = li < j ? j : li;
+              s.H[6 * lane + j] = t[7 + a * 6 - (a * (a - 1)) / 2 + (b - a)];
+            }
+            s.neg_g[lane] = -g_i;
+          }
+          __syncwarp();
+          if (lane == 0) svd_solve6(s.H, s.neg_g, s.dp);
+          __syncwarp();
+          dp_i = lane < 6 ? s.dp[li] : 0.0;
+        }
+        if (PROF && lane == 0) s.solve_path = path;
       }
-      have_dp = false;
-      double dp[6];
-      for (int i = 0; i < 6; ++i) dp[i] = s.dp[i];
-      double nrm = 0;
-      for (int i = 0; i < 6; ++i) nrm += dp[i] * dp[i];
-      nrm = sqrt(nrm);
+      lap(4);
+      const double nrm = sqrt(warp_dot6(dp_i, dp_i, lane));
       if (nrm == 0 || nrm != nrm) {
-        s.converged = (nrm == nrm) ? 1 : 0;
-        s.phase = PH_DONE;
-        return;
+        converged = (nrm == nrm) ? 1 : 0;
+        phase = PH_DONE;
+        break;
       }
       const double inv_nrm = 1.0 / nrm;
-      for (int i = 0; i < 6; ++i) s.dir[i] = dp[i] * inv_nrm;
+      dir_i = dp_i * inv_nrm;
       // computeStepLengthMT prologue
-      s.phi_0 = -s.score;
-      double gd = 0;
-      for (int i = 0; i < 6; ++i) gd += s.g[i] * s.dir[i];
-      s.d_phi_0 = -gd;
-      if (s.d_phi_0 >= 0) {
-        if (s.d_phi_0 == 0) {  // returns 0 without evaluating anything
-          s.a_t = 0;
+      phi_0 = -score;
+      d_phi_0 = -warp_dot6(g_i, dir_i, lane);
+      if (d_phi_0 >= 0) {
+        if (d_phi_0 == 0) {  // returns 0 without evaluating anything
+          a_t = 0;
           go_newton_end = true;
           continue;
         }
-        s.d_phi_0 *= -1;
-        for (int i = 0; i < 6; ++i) s.dir[i] *= -1;
+        d_phi_0 *= -1;
+        dir_i *= -1;
       }
-      s.step_iterations = 0;
-      s.a_l = 0; s.a_u = 0;
-      s.f_l = mt_psi(s.a_l, s.phi_0, s.phi_0, s.d_phi_0, mu);
-      s.g_l = mt_dpsi(s.d_phi_0, s.d_phi_0, mu);
-      s.f_u = mt_psi(s.a_u, s.phi_0, s.phi_0, s.d_phi_0, mu);
-      s.g_u = mt_dpsi(s.d_phi_0, s.d_phi_0, mu);
-      s.interval_converged = (step_max - step_min) < 0;
-      s.open_interval = 1;
-      s.a_t = nrm;
-      s.a_t = fmin(s.a_t, step_max);
-      s.a_t = fmax(s.a_t, step_min);
-      for (int i = 0; i < 6; ++i) s.x_t[i] = s.p[i] + s.dir[i] * s.a_t;
-      s.phase = PH_MT_FIRST;
-      s.need_hessian = 1;
-      s.new_pose = 1;
+      step_iterations = 0;
+      a_l = 0; a_u = 0;
+      f_l = mt_psi(a_l, phi_0, phi_0, d_phi_0, mu);
+      g_l = mt_dpsi(d_phi_0, d_phi_0, mu);
+      f_u = mt_psi(a_u, phi_0, phi_0, d_phi_0, mu);
+      g_u = mt_dpsi(d_phi_0, d_phi_0, mu);
+      interval_converged = (step_max - step_min) < 0;
+      open_interval = 1;
+      a_t = nrm;
+      a_t = fmin(a_t, step_max);
+      a_t = fmax(a_t, step_min);
+      x_t_i = p_i + dir_i * a_t;
+      phase = PH_MT_FIRST;
+      new_pose = 1;
       lap(5);
-      return;
+      break;
     }
   }
+  // ---- registers -> state
+  if (lane < 6) { s.p[lane] = p_i; s.dir[lane] = dir_i; s.x_t[lane] = x_t_i; }
+  if (lane == 0) {
+    s.score = score;
+    s.phi_0 = phi_0; s.d_phi_0 = d_phi_0; s.a_l = a_l; s.f_l = f_l; s.g_l = g_l; s.a_u = a_u; s.f_u = f_u; s.g_u = g_u; s.a_t = a_t;
+    s.phase = phase; s.step_iterations = step_iterations; s.open_interval = open_interval; s.interval_converged = interval_converged;
+    s.nr_iterations = nr_iterations; s.converged = converged; s.n_eval = n_eval; s.n_pass = s.n_pass + 1; s.hits += hits_pass;
+    s.new_pose = new_pose;
+    s.need_hessian = 1;
+    if (PROF) { s.phi_t = phi_t; s.d_phi_t = d_phi_t; s.psi_t = psi_t; s.d_psi_t = d_psi_t; }
+  }
+  __syncwarp();
 }
 
 // ---- one source point ------------------------------------------------------------------------
@@ -767,7 +791,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         for (int i = 0; i < 6; ++i) s.pf[i] = 0;
         s.score = 0.0;
         s.need_hessian = 1;
-        s.solve_req = 0;
+        s.solve_path = 0;
         s.phase = job.eval_only ? PH_EVAL_ONLY : PH_INIT;
       }
       __syncwarp();
@@ -893,27 +917,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
           }
         }
         __syncwarp();
-        if (s.phase != PH_EVAL_ONLY && s.phase != PH_DONE) {  // warp-uniform (PH_EVAL_ONLY became PH_DONE just above)
-          ndt_take_totals(s, lane);
-          if (tid == 0) ndt_step<PROF>(s, prm, false);
-        }
-        __syncwarp();
-        while (s.solve_req) {  // warp-uniform: the state machine is waiting for H dp = -g
-          const long long ts_a = PROF ? clock64() : 0;
-          double dpv[6];
-          const bool solved = warp_solve6(s.H, s.neg_g, dpv, lane);
-          if (tid == 0) {
-            if (solved) {
-#pragma unroll
-              for (int i = 0; i < 6; ++i) s.dp[i] = dpv[i];
-            } else {
-              svd_solve6(s.H, s.neg_g, s.dp);  // rank-deficient or NaN input: JacobiSVD's minimum-norm answer (see solve6)
-            }
-            if (PROF) s.pf[4] += clock64() - ts_a;
-            ndt_step<PROF>(s, prm, true);
-          }
-          __syncwarp();
-        }
+        if (s.phase != PH_EVAL_ONLY && s.phase != PH_DONE) ndt_step_warp<PROF>(s, prm, lane);  // warp-uniform (PH_EVAL_ONLY became PH_DONE just above)
         const long long tb = PROF ? clock64() : 0;
         __syncwarp();
         if (s.new_pose) {
@@ -931,7 +935,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
         // one record per pass, the quantities the oracle's trace holds (oracle.hpp NDT::trace)
         double* r = job.trace + (size_t)s.n_pass * kTraceDoubles;
         r[0] = s.nr_iterations; r[1] = s.step_iterations; r[2] = s.a_t; r[3] = s.tot[0]; r[4] = s.phi_t; r[5] = s.d_phi_t; r[6] = s.psi_t; r[7] = s.d_psi_t;
-        r[8] = s.open_interval; r[9] = s.interval_converged; r[10] = s.phi_0; r[11] = s.d_phi_0;
+        r[8] = s.open_interval; r[9] = s.interval_converged; r[10] = s.phi_0; r[11] = s.d_phi_0; r[12] = s.solve_path;
+        s.solve_path = 0;
         job.trace[0] = (double)s.n_pass;
       }
       __syncthreads();

@@ -253,8 +253,8 @@ class Registration:
                          "st_totals", "st_interval", "st_trial", "st_newton_end", "st_solve", "st_newton_begin"), v.tolist()))
 
     def trace(self, cap=255):
-        """Per-pass More-Thuente quantities of the last profiled NDT align (b200reg_get_trace), (n, 12) float64."""
-        out = np.zeros((cap, 12))
+        """Per-pass More-Thuente quantities of the last profiled NDT align (b200reg_get_trace), (n, 13) float64."""
+        out = np.zeros((cap, 13))
         n = C.c_size_t()
         self._ck(_lib.load().b200reg_get_trace(self._h, out.ctypes.data, cap, C.byref(n)))
         return out[: min(n.value, cap)]

@@ -325,8 +325,9 @@ int b200reg_get_profile(b200reg_handle* h, long long* out16);
 /* the counters are compiled into a separate instantiation of the align kernels (they cost registers the
  * production kernel does not have to spare): off by default, single registrations only */
 int b200reg_set_profile(b200reg_handle* h, int on);
-/* developer trace of the last profiled NDT align: one record of 12 doubles per pass over the source
- * {nr_iterations, step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t, open_interval, interval_converged, phi_0, d_phi_0}
+/* developer trace of the last profiled NDT align: one record of 13 doubles per pass over the source
+ * {nr_iterations, step_iterations, a_t, score, phi_t, d_phi_t, psi_t, d_psi_t, open_interval, interval_converged, phi_0, d_phi_0,
+ *  solve_path: how H dp = -g was solved after this pass — 0 no solve, 1 closed-form 3x3 blocks, 2 pivoted elimination, 3 SVD}
  * (the More-Thuente quantities after the pass was digested), the counterpart of the oracle's NDT::trace */
 int b200reg_get_trace(b200reg_handle* h, double* out, size_t cap_records, size_t* n_records);
 

@@ -42,4 +42,4 @@ for k in range(max(len(to), len(te))):
     if a is not None:
         print("   oracle", " ".join(f"{v:.10g}" for v in a))
     if b is not None:
-        print("   engine", " ".join(f"{v:.10g}" for v in b))
+        print("   engine", " ".join(f"{v:.10g}" for v in b[:12]), "solve_path", int(b[12]))
