@@ -461,39 +461,37 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     # The filter handle's persistent kernel is given args.filter_sms SMs, the registration the rest.
     def new_front_end(bufs, aligned_out=None):
         pre, odo = new_pipeline()
-        odo.prepare_promotion = bool(args.filter_sms) and args.prepare
         odo.aligned_out = aligned_out
         return eng.FrontEnd(pre, odo, bufs, filter_sms=args.filter_sms), pre, odo
 
-    # ---- device-resident leg (value) + roofline of the align kernel
-    fe_d, pre_d, odo_d = new_front_end(ds_bufs)
-    odo_d.registration.setTiming(True)
+    # ---- device-resident leg (value) + roofline of the align kernel.  The two nodelets run as host C++ above the
+    # engine (b200reg_frontend_*, csrc/b200reg_odometry.cu) — the reference's nodelets are compiled C++ too; the Python
+    # mirror of the same state machine (eng.FrontEnd) is the one the oracle parity tests drive and is checked against it below.
+    native_params = {**odom_params, **PREFILTER_PARAMS}
+    fe_d = eng.NativeFrontEnd(native_params, device=dev, filter_sms=args.filter_sms, prepare_promotion=args.prepare if is_ndt else 0)
+    fe_d.set_timing(True)
+    last_dev = {}
 
     def step_device(i):
-        odo_d.keyframe = None  # restart the sequence; engine buffers stay allocated
-        acc = dict(alg_bytes=0, evals=0, hits=0, ref_evals=0, points=0)
-
-        def on_frame(k, filtered):
-            if k > 0:
-                r = odo_d.registration.getResult()
-                # NDT pass: 16 B per source point + 48 B per (point, voxel) hit.  GICP: a linearize pass reads the
-                # point, its covariance, the correspondence's point and covariance and writes the Mahalanobis
-                # matrix (16 + 48 + 16 + 48 + 48 B per correspondence); an error pass re-reads 16 + 16 + 48 B
-                # (GICP outer iteration) — approximated with hits = linearize correspondences
-                acc["alg_bytes"] += (16 * filtered.n * r["passes"] + 48 * r["hits"]) if is_ndt else (16 * filtered.n * r["passes"] + 160 * r["hits"])
-                acc["evals"] += r["passes"]
-                acc["ref_evals"] += r["evaluations"]
-                acc["hits"] += r["hits"]
-                acc["points"] += filtered.n * r["passes"]
-        fe_d.run(dev_clouds, on_frame=on_frame)
-        acc["keyframes"] = odo_d.num_keyframes
-        return acc
+        poses, res, nf = fe_d.run_device(dev_clouds)
+        last_dev["poses"] = poses
+        r, n = res[1:], nf[1:].astype(np.int64)
+        passes, hits = r["passes"].astype(np.int64), r["hits"].astype(np.int64)
+        # NDT pass: 16 B per source point + 48 B per (point, voxel) hit.  GICP: a linearize pass reads the
+        # point, its covariance, the correspondence's point and covariance and writes the Mahalanobis
+        # matrix (16 + 48 + 16 + 48 + 48 B per correspondence); an error pass re-reads 16 + 16 + 48 B
+        # (GICP outer iteration) — approximated with hits = linearize correspondences
+        alg = int(np.sum(16 * n * passes + (48 if is_ndt else 160) * hits))
+        return dict(alg_bytes=alg, evals=int(passes.sum()), ref_evals=int(r["evaluations"].sum()), hits=int(hits.sum()), points=int(np.sum(n * passes)), keyframes=fe_d.num_keyframes())
 
     sampler = ClockSampler(dev)
     with sampler:
-        c0 = odo_d.registration.counters()
-        sec_d, wall_d, st_d = ctx.timed(step_device, odo_d.registration.stream(), steps, warmup)
-        c1 = odo_d.registration.counters()
+        c0 = fe_d.counters()
+        sec_d, wall_d, st_d = ctx.timed(step_device, fe_d.stream(), steps, warmup)
+        c1 = fe_d.counters()
+    fe_d.timing()
+    step_device(0)
+    host_phases = fe_d.timing()  # host wall clock per frame by phase over one more (untimed) pass
     regs_per_step = F - 1
     value = world * steps * regs_per_step / sec_d
     n_al = c1["timed_aligns"]  # the counters also saw the warm-up steps: per-launch averages over everything the library timed
@@ -509,10 +507,11 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     flops_per_launch = (30.0 * st_d[-1]["points"] + 400.0 * st_d[-1]["hits"]) / regs_per_step
     fp32_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
 
-    # ---- host-buffer leg (e2e): the calls the reference's nodelets make, host clouds in and out.
-    # Caller-owned output clouds of the filter (pcl::Filter::filter(output)), three in rotation because the odometry
-    # keeps the keyframe's cloud while the next scans are filtered, and the `aligned` cloud that
-    # registration->align(*aligned, guess) always fills [REF apps/scan_matching_odometry_nodelet.cpp:217-218]
+    # ---- host-buffer leg (e2e): the calls the reference's two nodelets make, host clouds in and out — raw scan up,
+    # filtered cloud down into the caller's cloud (the /filtered_points message; three in rotation because the message of
+    # scan k is still referenced while scans k+1 and k+2 are filtered), filtered cloud up again (setInputSource of the
+    # odometry nodelet), the `aligned` cloud that registration->align(*aligned, guess) always fills
+    # [REF apps/scan_matching_odometry_nodelet.cpp:217-218] and the result down
     def make_host_leg(pinned):
         if pinned:
             h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
@@ -522,47 +521,48 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
             h_out = np.empty((3, rays, 4), np.float32)
             h_al = np.empty((rays, 4), np.float32)
             inputs = [np.array(c) for c in host_clouds]  # pageable copies of the raw scans (what a pcl::PointCloud holds)
-        fe_h, pre_h, odo_h = new_front_end([h_out[j] for j in range(3)], aligned_out=h_al)
+        fe_h = eng.NativeFrontEnd(native_params, device=dev, filter_sms=args.filter_sms, prepare_promotion=args.prepare if is_ndt else 0)
+        raw_bytes = int(sum(c.nbytes for c in inputs))
 
         def step_host(i):
-            odo_h.keyframe = None
-            acc = dict(h2d=0, d2h=0)
-
-            def on_frame(k, filtered):
-                # raw scan up, filtered cloud down (the /filtered_points message), filtered cloud up again
-                # (setInputSource of the odometry nodelet), aligned cloud + result record down
-                acc["h2d"] += inputs[k].nbytes + filtered.nbytes
-                acc["d2h"] += filtered.nbytes + (filtered.nbytes + 128 if k > 0 else 0)
-            fe_h.run(inputs, on_frame=on_frame)
-            return acc
-        return step_host, odo_h, h_out
-    step_host, odo_h, h_out = make_host_leg(True)
-    sec_h, wall_h, st_h = ctx.timed(step_host, odo_h.registration.stream(), steps, warmup)
+            poses = fe_h.run_host(inputs, filtered_bufs=[h_out[j] for j in range(3)], aligned_out=h_al)
+            last_dev["poses_host_pinned" if pinned else "poses_host_pageable"] = poses
+            return None
+        return step_host, fe_h, h_out, raw_bytes
+    step_host, fe_h, h_out, raw_bytes = make_host_leg(True)
+    sec_h, wall_h, _ = ctx.timed(step_host, fe_h.stream(), steps, warmup)
     e2e_value = world * steps * regs_per_step / sec_h
+    # bytes moved per step, from the clouds copied: filtered sizes are those of the device leg (same scans, same filter)
+    _, _, nf_all = fe_d.run_device(dev_clouds, want_results=False)
+    filt_bytes = int(nf_all.astype(np.int64).sum()) * 16
+    filt_bytes_matched = int(nf_all[1:].astype(np.int64).sum()) * 16
+    h2d_step = raw_bytes + filt_bytes                       # raw scans + filtered clouds uploaded again
+    d2h_step = filt_bytes + filt_bytes_matched + 128 * regs_per_step  # filtered clouds + aligned clouds + result records
     e2e_pageable = None
     if pageable_leg:
-        step_pg, odo_pg, _ = make_host_leg(False)
-        sec_p, wall_p, st_p = ctx.timed(step_pg, odo_pg.registration.stream(), max(1, min(steps, 5)), 2)
+        step_pg, fe_pg, _, _ = make_host_leg(False)
+        ps = max(1, min(steps, 5))
+        sec_p, wall_p, _ = ctx.timed(step_pg, fe_pg.stream(), ps, 2)
         # wall clock, not stream time: with pageable buffers the library's staging memcpys run on the host between stream operations
-        e2e_pageable = {"value": world * max(1, min(steps, 5)) * regs_per_step / wall_p, "unit": "registrations/s", "ms_per_step": 1e3 * wall_p / max(1, min(steps, 5)),
-                        "h2d_bytes_per_step": st_p[-1]["h2d"], "d2h_bytes_per_step": st_p[-1]["d2h"],
+        e2e_pageable = {"value": world * ps * regs_per_step / wall_p, "unit": "registrations/s", "ms_per_step": 1e3 * wall_p / ps, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                         "note": "same calls with PAGEABLE caller clouds in and out (raw scan, filtered cloud, aligned cloud): the library stages through its own pinned buffers; wall clock"}
-        del step_pg, odo_pg
+        del step_pg, fe_pg
 
-    # ---- parity of the two legs (same inputs -> same poses) and odometry sanity vs ground truth
+    # ---- the legs against each other and against the Python mirror of the state machine; odometry sanity vs ground truth
     nchk = min(50, F)
+    poses_dev = [last_dev["poses"][k] for k in range(nchk)]
+    legs_equal = bool(np.array_equal(last_dev["poses"], last_dev["poses_host_pinned"]))
+    # the Python mirror (eng.FrontEnd over Prefilter + ScanMatchingOdometry: what the oracle parity tests drive), pipelined
+    # and as the plain loop (filter, then match, one scan at a time), on the same SM budgets
     fe_c, _, _ = new_front_end(ds_bufs)
-    poses_dev = fe_c.run(dev_clouds[:nchk])
-    fe_c2, _, _ = new_front_end([h_out[j] for j in range(3)])
-    poses_host = fe_c2.run(host_clouds[:nchk])
-    legs_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_host))
-    # the pipelined front end against the plain loop (filter, then match, one scan at a time) on the same SM budgets
+    poses_py = fe_c.run(dev_clouds[:nchk])
     pre_s, odo_s = new_pipeline()
     if pre_s.filter is not None and args.filter_sms:
         pre_s.filter.setSmBudget(args.filter_sms)
-        odo_s.registration.setSmBudget(148 - args.filter_sms)  # no prepared promotions here: they must not change a pose
+        odo_s.registration.setSmBudget(148 - args.filter_sms)
     poses_seq = run_sequence(pre_s, odo_s, dev_clouds[:nchk], out_buf=ds_buf)
-    pipeline_equal = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_seq))
+    pipeline_equal = all(np.array_equal(a, b) for a, b in zip(poses_py, poses_seq))
+    mirror_dev = max(max(transform_deltas(a, b)) for a, b in zip(poses_dev, poses_py))  # float 4x4 products in another order: ~1e-7
     P0 = synth.traj_kitti_like(5000 * rank)
     gt = np.linalg.inv(P0) @ synth.traj_kitti_like(stride * (nchk - 1) + 5000 * rank)
     drift = float(np.linalg.norm(poses_dev[nchk - 1][:3, 3] - gt[:3, 3]))
@@ -588,9 +588,11 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
         "stats": {"points_per_scan": int(np.mean(counts)), "keyframes_per_step": st_d[-1]["keyframes"], "passes_per_registration": passes_per_reg,
                   "evaluations_per_registration": st_d[-1]["ref_evals"] / regs_per_step,
                   "note": "evaluations = computeDerivatives + computeHessian calls of the reference's algorithm; passes = sweeps over the source the device ran (a closing computeHessian rides in the last trial pass)",
-                  "front_end": f"pipelined as the reference's two nodelets: filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms - (16 if args.prepare else 0)} SMs, registration {148 - args.filter_sms} SMs{', 16 SMs for the NDT grid of a predicted next keyframe built during its own registration' if args.prepare else ''}" if args.filter_sms else "sequential: filter, then match"},
-        "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": st_h[-1]["h2d"], "d2h_bytes_per_step": st_h[-1]["d2h"], "ms_per_step": 1e3 * sec_h / steps,
-                "wall_ms_per_step": 1e3 * wall_h / steps, "note": "page-locked caller clouds; per frame raw scan H2D, filtered cloud D2H + H2D, aligned cloud + result D2H"},
+                  "host_us_per_frame": {k: round(v, 2) if isinstance(v, float) else v for k, v in host_phases.items()},
+                  "front_end": (f"the two nodelets as host C++ above the engine (b200reg_frontend_*): filter of scan k+1 in flight while scan k is matched; filter handle {args.filter_sms - (16 if (args.prepare and is_ndt) else 0)} SMs, registration {148 - args.filter_sms} SMs" + (", 16 SMs for the side build of every scan's NDT target grid during its own registration (prepared keyframe promotion)" if (args.prepare and is_ndt) else "")
+                                if args.filter_sms else "the two nodelets as host C++ above the engine, no SM split")},
+        "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * sec_h / steps,
+                "wall_ms_per_step": 1e3 * wall_h / steps, "note": "page-locked caller clouds; per frame raw scan H2D, filtered cloud D2H + H2D (the two nodelets' message), aligned cloud + result D2H"},
         "e2e_pageable": e2e_pageable,
         "gpu_launches": int(launches_timed),
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
@@ -604,7 +606,8 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                           "note": "a registration is a chain of dependent passes (each: point sweep, reduction across the SMs, optimiser step); the per-pass latency, not bandwidth, sets the kernel time — per-phase split in profiles/"},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
-        "checks": {"device_and_host_legs_bit_identical_first_frames": bool(legs_equal), "pipelined_equals_sequential_first_frames": bool(pipeline_equal), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
+        "checks": {"device_and_host_legs_bit_identical": bool(legs_equal), "python_mirror_pipelined_equals_sequential_first_frames": bool(pipeline_equal),
+                   "native_front_end_vs_python_mirror_max_pose_delta": float(mirror_dev), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
                    "wall_ms_per_step": 1e3 * wall_d / steps, "parity_vs_oracle": parity},
     }
     del d_raw, h_raw
@@ -793,7 +796,7 @@ def main():
     ap.add_argument("--loop-parity-pairs", type=int, default=64, help="pairs of rank 0's share re-registered by the CPU oracle and compared with the engine's records (0 = skip)")
     ap.add_argument("--no-loop", action="store_true", help="skip the loop-batch leg of the default (odometry) run")
     ap.add_argument("--no-gicp", action="store_true", help="skip the FAST_GICP odometry leg (BASELINE configs[2]) of the default run")
-    ap.add_argument("--prepare", action="store_true", help="build a predicted next keyframe's target structures during its own registration (b200reg_prepare_promotion; measured: no net gain, off by default)")
+    ap.add_argument("--prepare", type=int, default=2, help="prepared keyframe promotions in the native front end: 0 off, 1 when the motion so far predicts a switch, 2 every scan (a scan's NDT target grid is built on a side stream with 16 of the filter's SMs while the scan is registered; scheduling only, poses unchanged; measured 196 -> 190 -> 188 us per frame)")
     ap.add_argument("--no-1m", action="store_true", help="skip the 1.0 m/frame variant of the odometry sequence (SURVEY cfg 2's spacing: every frame a keyframe switch)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-scan stress leg (BASELINE configs[4]) of the default run")
     ap.add_argument("--dense-targets", type=int, default=8)

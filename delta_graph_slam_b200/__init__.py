@@ -11,8 +11,8 @@ from ._lib import B200RegError, DIRECT1, DIRECT7, DIRECT26, KDTREE
 from . import loop_batch
 from .information_matrix import InformationMatrixCalculator
 from .loop_detector import KeyFrame, Loop, LoopDetector, transform2Dto3D
-from .odometry import FrontEnd, Prefilter, ScanMatchingOdometry
+from .odometry import FrontEnd, NativeFrontEnd, Prefilter, ScanMatchingOdometry
 from .registration import DBL_MAX, DeviceCloud, FastGICP, NormalDistributionsTransform, RadiusOutlierRemoval, Registration, StatisticalOutlierRemoval, VoxelGrid, select_registration_method
 
-__all__ = ["InformationMatrixCalculator", "KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "RadiusOutlierRemoval", "Registration", "StatisticalOutlierRemoval", "VoxelGrid",
+__all__ = ["InformationMatrixCalculator", "KeyFrame", "Loop", "LoopDetector", "loop_batch", "transform2Dto3D", "B200RegError", "DIRECT1", "DIRECT7", "DIRECT26", "KDTREE", "DBL_MAX", "DeviceCloud", "FrontEnd", "NativeFrontEnd", "Prefilter", "ScanMatchingOdometry", "FastGICP", "NormalDistributionsTransform", "RadiusOutlierRemoval", "Registration", "StatisticalOutlierRemoval", "VoxelGrid",
            "select_registration_method"]

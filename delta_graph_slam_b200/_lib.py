@@ -27,7 +27,11 @@ EXPORTS = [
     "b200reg_align", "b200reg_has_converged", "b200reg_get_final_transformation", "b200reg_get_num_iterations",
     "b200reg_get_transformation_probability", "b200reg_get_result", "b200reg_get_fitness_score", "b200reg_calc_fitness_score", "b200reg_get_inlier_fraction",
     "b200reg_voxelgrid_filter", "b200reg_voxelgrid_filter_device", "b200reg_voxelgrid_last_layout",
-    "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_end", "b200reg_set_sm_budget", "b200reg_set_distance_filter", "b200reg_distance_filter", "b200reg_distance_filter_device",
+    "b200reg_voxelgrid_filter_begin", "b200reg_voxelgrid_filter_device_begin", "b200reg_voxelgrid_filter_host_to_device_begin", "b200reg_voxelgrid_filter_end",
+    "b200reg_odometry_default_config", "b200reg_odometry_create", "b200reg_odometry_destroy", "b200reg_odometry_last_error", "b200reg_odometry_reset", "b200reg_odometry_matching",
+    "b200reg_odometry_matching_device", "b200reg_odometry_get_state",
+    "b200reg_frontend_default_config", "b200reg_frontend_create", "b200reg_frontend_destroy", "b200reg_frontend_last_error", "b200reg_frontend_reset", "b200reg_frontend_registration",
+    "b200reg_frontend_filter", "b200reg_frontend_odometry", "b200reg_frontend_begin", "b200reg_frontend_begin_device", "b200reg_frontend_step", "b200reg_frontend_step_device", "b200reg_frontend_run_device", "b200reg_frontend_get_timing", "b200reg_set_sm_budget", "b200reg_set_distance_filter", "b200reg_distance_filter", "b200reg_distance_filter_device",
     "b200reg_radius_outlier_removal", "b200reg_radius_outlier_removal_device", "b200reg_radius_outlier_removal_begin", "b200reg_radius_outlier_removal_device_begin",
     "b200reg_radius_outlier_removal_end",
     "b200reg_statistical_outlier_removal", "b200reg_statistical_outlier_removal_device", "b200reg_statistical_outlier_removal_begin", "b200reg_statistical_outlier_removal_device_begin",
@@ -46,6 +50,16 @@ class Config(C.Structure):
         ("outlier_ratio", C.c_double), ("max_correspondence_distance", C.c_double), ("correspondence_randomness", C.c_int),
         ("rotation_epsilon", C.c_double), ("regularization", C.c_int), ("lsq_optimizer", C.c_int), ("num_threads", C.c_int),
     ]
+
+
+class OdometryConfig(C.Structure):
+    _fields_ = [("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double), ("transform_thresholding", C.c_int),
+                ("max_acceptable_trans", C.c_double), ("max_acceptable_angle", C.c_double)]
+
+
+class FrontEndConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("registration", Config), ("odometry", OdometryConfig), ("downsample_resolution", C.c_double), ("use_distance_filter", C.c_int),
+                ("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("filter_sms", C.c_int), ("prepare_promotion", C.c_int), ("side_sms", C.c_int)]
 
 
 class Result(C.Structure):
@@ -116,7 +130,34 @@ def load():
     L.b200reg_voxelgrid_filter_device.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp, szp]
     L.b200reg_voxelgrid_filter_begin.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp, C.c_size_t]
     L.b200reg_voxelgrid_filter_device_begin.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp]
+    L.b200reg_voxelgrid_filter_host_to_device_begin.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_float), C.c_uint, C.c_int, vp]
     L.b200reg_voxelgrid_filter_end.argtypes = [vp, szp]
+    L.b200reg_odometry_default_config.argtypes = [C.POINTER(OdometryConfig)]
+    L.b200reg_odometry_default_config.restype = None
+    L.b200reg_odometry_create.argtypes = [vp, C.POINTER(OdometryConfig), C.POINTER(vp)]
+    L.b200reg_odometry_destroy.argtypes = [vp]
+    L.b200reg_odometry_last_error.argtypes = [vp]
+    L.b200reg_odometry_last_error.restype = C.c_char_p
+    L.b200reg_odometry_reset.argtypes = [vp]
+    L.b200reg_odometry_matching.argtypes = [vp, C.c_double, vp, C.c_size_t, C.c_size_t, vp, vp, vp]
+    L.b200reg_odometry_matching_device.argtypes = [vp, C.c_double, vp, C.c_size_t, vp, vp]
+    L.b200reg_odometry_get_state.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, C.POINTER(Result)]
+    L.b200reg_frontend_default_config.argtypes = [C.POINTER(FrontEndConfig)]
+    L.b200reg_frontend_default_config.restype = None
+    L.b200reg_frontend_create.argtypes = [C.POINTER(FrontEndConfig), C.POINTER(vp)]
+    L.b200reg_frontend_destroy.argtypes = [vp]
+    L.b200reg_frontend_last_error.argtypes = [vp]
+    L.b200reg_frontend_last_error.restype = C.c_char_p
+    L.b200reg_frontend_reset.argtypes = [vp]
+    for name in ("b200reg_frontend_registration", "b200reg_frontend_filter", "b200reg_frontend_odometry"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.b200reg_frontend_begin.argtypes = [vp, C.c_double, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t]
+    L.b200reg_frontend_begin_device.argtypes = [vp, C.c_double, vp, C.c_size_t]
+    L.b200reg_frontend_step.argtypes = [vp, C.c_double, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, szp, vp, vp]
+    L.b200reg_frontend_step_device.argtypes = [vp, C.c_double, vp, C.c_size_t, szp, vp]
+    L.b200reg_frontend_get_timing.argtypes = [vp, vp]
+    L.b200reg_frontend_run_device.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, C.POINTER(C.c_int)]
     L.b200reg_set_sm_budget.argtypes = [vp, C.c_int]
     L.b200reg_set_distance_filter.argtypes = [vp, C.c_int, C.c_double, C.c_double]
     L.b200reg_distance_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, vp, C.c_size_t, szp]

@@ -104,6 +104,7 @@ struct b200reg_handle {
   NdtGrid grid_spec;
   bool spec_valid = false;      // grid_spec holds the grid of (spec_ptr, spec_n) at spec_res
   bool spec_in_flight = false;  // the side stream may still be reading the source buffer
+  bool prepare_pending = false; // a hint was given: the side build is launched by the next align, behind its own kernel
   const float4* spec_ptr = nullptr;
   int spec_n = 0;
   float spec_res = 0.f;
@@ -724,6 +725,7 @@ static int retire_spec(b200reg_handle* h) {
     h->spec_in_flight = false;
   }
   h->spec_valid = false;
+  h->prepare_pending = false;
   return B200REG_OK;
 }
 
@@ -812,6 +814,23 @@ int b200reg_promote_source_to_target(b200reg_handle* h) {
   return B200REG_OK;
 }
 
+// The side build itself: enqueued on the side stream behind ev_src_ready (recorded when the hint was given, i.e. after
+// the source cloud's copy and BEFORE the align kernel was launched on the main stream).
+static int launch_side_build(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  h->prepare_pending = false;
+  B200_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_src_ready, 0));
+  h->grid_spec.sort.max_ctas = h->spec_sms;
+  B200_CUDA_TRY(h->grid_spec.build(h->side, h->src.p, h->n_src, (float)h->cfg.resolution));
+  B200_CUDA_TRY(cudaEventRecord(h->ev_side_done, h->side));
+  h->spec_valid = true;
+  h->spec_in_flight = true;
+  h->spec_ptr = h->src.p;
+  h->spec_n = h->n_src;
+  h->spec_res = (float)h->cfg.resolution;
+  return B200REG_OK;
+}
+
 int b200reg_prepare_promotion(b200reg_handle* h) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h) return B200REG_E_INVALID;
@@ -825,17 +844,12 @@ int b200reg_prepare_promotion(b200reg_handle* h) {
     B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_src_ready, cudaEventDisableTiming));
     B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_side_done, cudaEventDisableTiming));
   }
-  // the side stream starts after the source cloud has arrived (set_source's copy is on the main stream)
+  // the side stream starts after the source cloud has arrived (set_source's copy is on the main stream).  The four
+  // launches of the build are issued by the NEXT b200reg_align right after its own kernel is on its way, so the host time
+  // they cost runs under the registration instead of in front of it; without an align in between, the promotion builds
+  // the grid as usual.
   B200_CUDA_TRY(cudaEventRecord(h->ev_src_ready, h->stream));
-  B200_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_src_ready, 0));
-  h->grid_spec.sort.max_ctas = h->spec_sms;
-  B200_CUDA_TRY(h->grid_spec.build(h->side, h->src.p, h->n_src, (float)h->cfg.resolution));
-  B200_CUDA_TRY(cudaEventRecord(h->ev_side_done, h->side));
-  h->spec_valid = true;
-  h->spec_in_flight = true;
-  h->spec_ptr = h->src.p;
-  h->spec_n = h->n_src;
-  h->spec_res = (float)h->cfg.resolution;
+  h->prepare_pending = true;
   return B200REG_OK;
 }
 
@@ -856,6 +870,7 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
     h->err = "align: registration method not available on this handle";
     return B200REG_E_STATE;
   }
+  if (h->prepare_pending && (rc = launch_side_build(h))) return rc;  // under the registration that has just been launched
   bool aligned_direct = false;
   if (aligned_xyzw) {
     // pcl::Registration::align fills `output` with the transformed source [REF apps/scan_matching_odometry_nodelet.cpp:217-218]:
@@ -1043,6 +1058,40 @@ int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t 
   h->vg_pending.host_out = out;
   h->vg_pending.cap = cap;
   h->vg_pending.zero_copy = zero_copy;
+  return B200REG_OK;
+}
+
+// host scan in, filtered cloud left on the device (a fused front end hands it to the registration without a round trip
+// through host memory)
+int b200reg_voxelgrid_filter_host_to_device_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* d_out) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h || !leaf || (n && (!xyzw || !d_out))) return B200REG_E_INVALID;
+  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
+  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
+  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
+  int rc = set_device(h);
+  if (rc) return rc;
+  B200_CUDA_TRY(h->stage_in.reserve(n ? n : 1));
+  if (n) {
+    if (stride == 16 && is_pinned_host(xyzw)) {
+      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      B200_CUDA_TRY(h->pin_in.reserve(n));
+      if (stride == 16) {
+        memcpy(h->pin_in.p, xyzw, n * 16);
+      } else {
+        const unsigned char* b = (const unsigned char*)xyzw;
+        for (size_t i = 0; i < n; ++i) {
+          const float* p = (const float*)(b + i * stride);
+          h->pin_in.p[i] = make_float4(p[0], p[1], p[2], 1.0f);
+        }
+      }
+      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, h->pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  if ((rc = vg_run(h, h->stage_in.p, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
+  h->vg_pending = b200reg_handle::VgPending();
+  h->vg_pending.active = true;
   return B200REG_OK;
 }
 

@@ -344,3 +344,143 @@ class ScanMatchingOdometry:
             self.prev_trans = np.eye(4, dtype=np.float32)
             self.num_keyframes += 1
         return odom
+
+
+class NativeFrontEnd:
+    """b200reg_frontend_* (include/b200reg.h, csrc/b200reg_odometry.cu): the prefiltering nodelet and the scan-matching
+    nodelet as host C++ above the engine — the same state machine as Prefilter + ScanMatchingOdometry + FrontEnd in this
+    module, without an interpreter between the kernels (the reference's nodelets are compiled C++).  `params` takes the
+    two nodelets' parameter names (this module's classes document them)."""
+
+    def __init__(self, params=None, device=0, filter_sms=40, prepare_promotion=0, side_sms=16):
+        import ctypes as C
+        from . import _lib
+        p = dict(params or {})
+        L = _lib.load()
+        cfg = _lib.FrontEndConfig()
+        L.b200reg_frontend_default_config(C.byref(cfg))
+        cfg.device = device
+        method = p.get("registration_method", "NDT_OMP")
+        if method == "FAST_GICP":
+            L.b200reg_default_config(_lib.METHOD_GICP, C.byref(cfg.registration))
+            cfg.registration.max_correspondence_distance = float(p.get("reg_max_correspondence_distance", 2.5))
+            cfg.registration.correspondence_randomness = int(p.get("reg_correspondence_randomness", 20))
+        elif "NDT" in method and "OMP" in method:
+            L.b200reg_default_config(_lib.METHOD_NDT, C.byref(cfg.registration))
+            cfg.registration.resolution = float(p.get("reg_resolution", 0.5))
+            cfg.registration.nn_search = {"KDTREE": _lib.KDTREE, "DIRECT1": _lib.DIRECT1}.get(p.get("reg_nn_search_method", "DIRECT7"), _lib.DIRECT7)
+        else:
+            raise NotImplementedError(f"registration_method={method}: the engine replaces NDT_OMP and FAST_GICP")
+        cfg.registration.transformation_epsilon = float(p.get("reg_transformation_epsilon", 0.01))
+        cfg.registration.maximum_iterations = int(p.get("reg_maximum_iterations", 64))
+        cfg.odometry.keyframe_delta_trans = float(p.get("keyframe_delta_trans", 0.25))
+        cfg.odometry.keyframe_delta_angle = float(p.get("keyframe_delta_angle", 0.15))
+        cfg.odometry.keyframe_delta_time = float(p.get("keyframe_delta_time", 1.0))
+        cfg.odometry.transform_thresholding = int(bool(p.get("transform_thresholding", False)))
+        cfg.odometry.max_acceptable_trans = float(p.get("max_acceptable_trans", 1.0))
+        cfg.odometry.max_acceptable_angle = float(p.get("max_acceptable_angle", 1.0))
+        if p.get("downsample_method", "VOXELGRID") != "VOXELGRID":
+            raise NotImplementedError("the native front end runs the prefilter's VoxelGrid (downsample_method VOXELGRID)")
+        cfg.downsample_resolution = float(p.get("downsample_resolution", 0.1))
+        cfg.use_distance_filter = 0 if p.get("b200_skip_distance_filter", False) else 1
+        cfg.distance_near_thresh = float(p.get("distance_near_thresh", 1.0))
+        cfg.distance_far_thresh = float(p.get("distance_far_thresh", 100.0))
+        cfg.filter_sms = int(filter_sms)
+        cfg.prepare_promotion = int(prepare_promotion)
+        cfg.side_sms = int(side_sms)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        rc = L.b200reg_frontend_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            raise _lib.B200RegError(rc, "b200reg_frontend_create failed (no usable sm_100 CUDA device?)")
+        self._L, self._C = L, C
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200reg_frontend_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            from . import _lib
+            raise _lib.B200RegError(rc, self._L.b200reg_frontend_last_error(self._h).decode())
+
+    def registration_handle(self):
+        return self._L.b200reg_frontend_registration(self._h)
+
+    def stream(self):
+        p = self._C.c_void_p()
+        self._L.b200reg_get_stream(self.registration_handle(), self._C.byref(p))
+        return p.value
+
+    def set_timing(self, on=True):
+        self._L.b200reg_set_timing(self.registration_handle(), int(on))
+
+    def counters(self):
+        C = self._C
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_double()
+        self._L.b200reg_get_counters(self.registration_handle(), C.byref(a), C.byref(b), C.byref(c))
+        return dict(launches_total=a.value, timed_aligns=b.value, align_kernel_ms=c.value)
+
+    def num_keyframes(self):
+        n = self._C.c_int()
+        self._L.b200reg_odometry_get_state(self._L.b200reg_frontend_odometry(self._h), self._C.byref(n), None, None, None, None, None)
+        return n.value
+
+    def timing(self):
+        """Host wall clock per phase since the last call (b200reg_frontend_get_timing), microseconds per step."""
+        v = np.zeros(9)
+        self._ck(self._L.b200reg_frontend_get_timing(self._h, v.ctypes.data))
+        n = max(v[0], 1.0)
+        return dict(steps=int(v[0]), filter_wait_us=v[1] / n, begin_next_us=v[2] / n, set_source_us=v[3] / n, align_us=v[4] / n, promote_us_per_step=v[5] / n,
+                    promote_us_each=v[5] / max(v[6], 1.0), promotions=int(v[6]), step_us=v[7] / n, hints=int(v[8]))
+
+    def run_device(self, clouds, want_results=True):
+        """A whole sequence of DeviceClouds: (poses (F, 4, 4) float32, result records or None, filtered sizes)."""
+        from . import _lib
+        C = self._C
+        F = len(clouds)
+        ptrs = (C.c_void_p * F)(*[c.ptr for c in clouds])
+        ns = (C.c_size_t * F)(*[c.n for c in clouds])
+        odom = np.zeros((F, 16), np.float32)
+        res = np.zeros(F, _lib.RESULT_DTYPE) if want_results else None
+        nf = np.zeros(F, np.uint64)
+        kf = C.c_int()
+        self._ck(self._L.b200reg_frontend_run_device(self._h, ptrs, ns, None, F, odom.ctypes.data, res.ctypes.data if want_results else None, nf.ctypes.data, C.byref(kf)))
+        return odom.reshape(F, 4, 4).transpose(0, 2, 1).copy(), res, nf
+
+    def run_host(self, clouds, filtered_bufs=None, aligned_out=None, stamps=None):
+        """Host scans one by one through begin / step.  filtered_bufs: three (M, 4) float32 host clouds in rotation
+        (the two-nodelet form: filtered cloud to the host, uploaded again for the registration) or None (fused)."""
+        C = self._C
+        F = len(clouds)
+        poses = np.zeros((F, 16), np.float32)
+        nf = C.c_size_t()
+        stamp = (lambda k: 0.1 * k) if stamps is None else (lambda k: stamps[k])
+
+        def fb(k):
+            if filtered_bufs is None:
+                return None, 0
+            b = filtered_bufs[k % len(filtered_bufs)]
+            return b.ctypes.data, len(b)
+        if F == 0:
+            return poses.reshape(0, 4, 4)
+        c0 = clouds[0]
+        p0, cap0 = fb(0)
+        self._ck(self._L.b200reg_frontend_begin(self._h, stamp(0), c0.ctypes.data, len(c0), 16, p0, cap0))
+        al = aligned_out.ctypes.data if aligned_out is not None else None
+        for k in range(F):
+            if k + 1 < F:
+                c1 = clouds[k + 1]
+                p1, cap1 = fb(k + 1)
+                self._ck(self._L.b200reg_frontend_step(self._h, stamp(k + 1), c1.ctypes.data, len(c1), 16, p1, cap1, C.byref(nf), al, poses[k].ctypes.data))
+            else:
+                self._ck(self._L.b200reg_frontend_step(self._h, 0.0, None, 0, 16, None, 0, C.byref(nf), al, poses[k].ctypes.data))
+        return poses.reshape(F, 4, 4).transpose(0, 2, 1).copy()

@@ -167,6 +167,10 @@ int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t 
                                    int input_is_dense, float* out_xyzw, size_t out_capacity);
 int b200reg_voxelgrid_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_points_per_voxel, int input_is_dense,
                                           float* d_out_xyzw);
+/* host scan in, filtered cloud left on the device at d_out_xyzw (room for n points): what a front end that keeps
+ * the prefilter and the registration in one process uses to hand the cloud over without a round trip through host memory */
+int b200reg_voxelgrid_filter_host_to_device_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_bytes, const float leaf[3], unsigned min_points_per_voxel, int input_is_dense,
+                                                  float* d_out_xyzw);
 int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out);
 /* Share of the GPU a handle's persistent (cooperative) kernels occupy: at most n_sm CTAs, one per SM.
  * Default: every SM.  A front end that overlaps the filter of scan k+1 with the registration of
@@ -299,6 +303,75 @@ int b200reg_batch_run(b200reg_multi* m, const b200reg_pair* pairs, size_t n_pair
 /* after a run: device count, whether NCCL carried the gather (and its version code), pairs each device registered
  * (n_devices ints), CUDA-event duration of the all-gather on device 0.  Any pointer may be NULL. */
 int b200reg_batch_get_info(b200reg_multi* m, int* n_devices, int* uses_nccl, int* nccl_version, int* pairs_per_device, double* gather_ms);
+
+/* ---- the host side of the two front-end nodelets, in C++ above the calls of this header (csrc/b200reg_odometry.cu) ----
+ * ScanMatchingOdometryNodelet::matching [REF apps/scan_matching_odometry_nodelet.cpp:173-270] as an object: the frame-to-
+ * keyframe state machine (first scan -> keyframe; guess = prev_trans * delta; not converged / jump gate -> frame ignored;
+ * keyframe switch on keyframe_delta_trans / _angle / _time, the aligned source promoted to target on the device) around
+ * a registration handle the caller owns.  odom16 receives keyframe_pose * trans, column-major.  Parameters and defaults
+ * are the nodelet's [REF :73-80]. */
+typedef struct b200reg_odometry_config {
+  double keyframe_delta_trans, keyframe_delta_angle, keyframe_delta_time; /* 0.25 m, 0.15 rad, 1.0 s */
+  int transform_thresholding;                                             /* false */
+  double max_acceptable_trans, max_acceptable_angle;                      /* 1.0 m, 1.0 rad */
+} b200reg_odometry_config;
+typedef struct b200reg_odometry b200reg_odometry;
+void b200reg_odometry_default_config(b200reg_odometry_config* out);
+int b200reg_odometry_create(b200reg_handle* registration, const b200reg_odometry_config* cfg, b200reg_odometry** out);
+int b200reg_odometry_destroy(b200reg_odometry* o);
+const char* b200reg_odometry_last_error(const b200reg_odometry* o);
+int b200reg_odometry_reset(b200reg_odometry* o); /* forget the keyframe: the next scan starts a new sequence */
+/* matching(stamp, cloud).  guess_delta16 (may be NULL = identity): the msf / robot-odometry delta multiplied onto prev_trans
+ * [REF :190-214]; aligned_xyzw (may be NULL): the `aligned` cloud of registration->align(*aligned, guess) [REF :217-218]. */
+int b200reg_odometry_matching(b200reg_odometry* o, double stamp, const float* xyzw, size_t n, size_t stride_bytes, const float* guess_delta16, float* aligned_xyzw, float* odom16);
+int b200reg_odometry_matching_device(b200reg_odometry* o, double stamp, const float* d_xyzw, size_t n, const float* guess_delta16, float* odom16);
+/* keyframes so far, whether the last scan converged / switched the keyframe, keyframe_pose, prev_trans, the last registration record; any pointer may be NULL */
+int b200reg_odometry_get_state(b200reg_odometry* o, int* num_keyframes, int* last_converged, int* last_switched, float* keyframe_pose16, float* prev_trans16, b200reg_result* last_result);
+
+/* prefiltering_nodelet -> /filtered_points -> scan_matching_odometry_nodelet as the pipeline it is in the reference
+ * [REF launch/delta_graph_slam.launch:26,46; apps/prefiltering_nodelet.cpp:48,51,150-151; apps/scan_matching_odometry_nodelet.cpp:53]:
+ * the distance gate + VoxelGrid of scan k+1 run on their own handle, stream and share of the SMs while scan k is matched.
+ * _begin enqueues the prefilter of a scan; _step collects it, enqueues the prefilter of the NEXT scan (next_xyzw == NULL:
+ * none) and matches the collected one.  Where a scan's filtered cloud goes is chosen at ITS begin:
+ *   filtered_out != NULL  the reference's two nodelets: the filtered cloud lands in the caller's host cloud (the
+ *                         /filtered_points message; a page-locked cloud is written by the filter kernel itself) and the
+ *                         odometry side uploads it again, as setInputSource of a separate nodelet would;
+ *   filtered_out == NULL  fused: the filtered cloud stays on the device and reaches the registration by a device copy.
+ * Device-resident scans (_begin_device / _step_device / _run_device) always take the fused form. */
+typedef struct b200reg_frontend_config {
+  int device;
+  b200reg_config registration;      /* the odometry nodelet's registration object (method, reg_* parameters) */
+  b200reg_odometry_config odometry;
+  double downsample_resolution;     /* prefilter VoxelGrid leaf, 0.1 [REF apps/prefiltering_nodelet.cpp:56-57] */
+  int use_distance_filter;          /* 1: the gate runs on every scan, as the reference's cloud_callback does [REF :150] */
+  double distance_near_thresh, distance_far_thresh; /* 1.0 / 100.0 [REF :101-102] */
+  int filter_sms;                   /* SMs of the prefilter handle's persistent kernel (the registration takes the rest); 0 = no split */
+  int prepare_promotion;            /* scheduling only, results unchanged: 0 off; 1 build a scan's target structures on a side stream during
+                                       its own registration when the motion so far says it will become the keyframe; 2 for every scan */
+  int side_sms;                     /* SMs (out of filter_sms) of that side build's persistent sort kernel, 16 */
+} b200reg_frontend_config;
+typedef struct b200reg_frontend b200reg_frontend;
+void b200reg_frontend_default_config(b200reg_frontend_config* out);
+int b200reg_frontend_create(const b200reg_frontend_config* cfg, b200reg_frontend** out);
+int b200reg_frontend_destroy(b200reg_frontend* fe);
+const char* b200reg_frontend_last_error(const b200reg_frontend* fe);
+int b200reg_frontend_reset(b200reg_frontend* fe);
+b200reg_handle* b200reg_frontend_registration(b200reg_frontend* fe); /* borrowed: timing hooks, getFitnessScore, ... */
+b200reg_handle* b200reg_frontend_filter(b200reg_frontend* fe);
+b200reg_odometry* b200reg_frontend_odometry(b200reg_frontend* fe);
+int b200reg_frontend_begin(b200reg_frontend* fe, double stamp, const float* xyzw, size_t n, size_t stride_bytes, float* filtered_out, size_t filtered_capacity);
+int b200reg_frontend_begin_device(b200reg_frontend* fe, double stamp, const float* d_xyzw, size_t n);
+int b200reg_frontend_step(b200reg_frontend* fe, double next_stamp, const float* next_xyzw, size_t next_n, size_t next_stride_bytes, float* next_filtered_out, size_t next_filtered_capacity,
+                          size_t* n_filtered, float* aligned_out, float* odom16);
+int b200reg_frontend_step_device(b200reg_frontend* fe, double next_stamp, const float* next_d_xyzw, size_t next_n, size_t* n_filtered, float* odom16);
+/* a whole sequence of device-resident scans: odom16_out = frames x 16 floats; results (optional) the registration record of
+ * every frame (zeros for frame 0); n_filtered (optional) the filtered cloud sizes; stamps == NULL: 0.1 s apart */
+/* host wall clock per phase since the previous call, microseconds summed over the steps: out9 = {steps, wait for the
+ * filter in flight, begin of the next filter, set source, align launch -> result, keyframe promotions, number of promotions,
+ * whole steps, promotion hints given}; the counters restart */
+int b200reg_frontend_get_timing(b200reg_frontend* fe, double* out9);
+int b200reg_frontend_run_device(b200reg_frontend* fe, const float* const* d_scans, const size_t* n_points, const double* stamps, size_t frames, float* odom16_out, b200reg_result* results,
+                                size_t* n_filtered, int* keyframes_out);
 
 /* introspection of the NDT target grid (parity tests): number of occupied voxels, then per
  * voxel (ascending linear index): index, point count (-1 = rejected by the eigenvalue test),
