@@ -38,6 +38,7 @@ EXPORTS = [
     "b200reg_statistical_outlier_removal_end", "b200reg_statistical_last_stats",
     "b200reg_flat_filter", "b200reg_flat_filter_device", "b200reg_flat_filter_begin", "b200reg_flat_filter_device_begin", "b200reg_flat_filter_end", "b200reg_flat_filter_last_nz",
     "b200reg_cloud_put", "b200reg_cloud_sync", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
+    "b200reg_map_cloud", "b200reg_map_cloud_cached",
     "b200reg_batch_create", "b200reg_batch_destroy", "b200reg_batch_last_error", "b200reg_batch_cloud_put", "b200reg_batch_cloud_drop", "b200reg_batch_run", "b200reg_batch_get_info",
     "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_profile", "b200reg_get_trace", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
 ]
@@ -189,6 +190,8 @@ def load():
     L.b200reg_align_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_double, vp]
     L.b200reg_calc_fitness_batch.argtypes = [vp, vp, C.c_size_t, C.c_double, vp]
     L.b200reg_get_batch_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.b200reg_map_cloud.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_double, vp, C.c_size_t, szp, vp]
+    L.b200reg_map_cloud_cached.argtypes = [vp, vp, vp, C.c_size_t, C.c_double, vp, C.c_size_t, szp, vp]
     L.b200reg_batch_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.b200reg_batch_destroy.argtypes = [vp]
     L.b200reg_batch_last_error.argtypes = [vp]

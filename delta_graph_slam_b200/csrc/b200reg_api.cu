@@ -17,6 +17,7 @@
 
 #include "gicp.cuh"
 #include "loop_batch.cuh"
+#include "map_cloud.cuh"
 #include "ndt_align.cuh"
 #include "nn_grid.cuh"
 #include "sor.cuh"
@@ -148,6 +149,14 @@ struct b200reg_handle {
   PinnedBuf<unsigned char> pin_batch;
   double batch_align_ms = 0.0;  // last batch: duration of the align kernel (timing on)
   double batch_fitness_ms = 0.0;
+
+  // MapCloudGenerator::generate (map_cloud.cuh)
+  DevBuf<float4> map_src, map_world, map_out;
+  DevBuf<MapKeyframe> map_kf;
+  DevBuf<MapEvents> map_events;
+  DevBuf<unsigned long long> map_codes_a, map_codes_b, map_scalar;
+  DevBuf<uint32_t> map_tile_heads;
+  OneSweepScratch map_sort;
 
   HostMailbox* mail = nullptr;  // cudaHostAllocMapped
   unsigned int align_seq = 0, vg_seq = 0;
@@ -310,7 +319,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_pass<uint32_t>)); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared(k_os_pass<unsigned long long>)); B200_ATTR(prefer_shared(k_os_pass<uint32_t>)); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -588,6 +597,37 @@ int fetch_result(b200reg_handle* h, bool synced = false) {
   return B200REG_OK;
 }
 
+// Morton codes of the map cloud: digits that hold code bits, then ONE pass over the top digit (zero for every valid code,
+// 0xFF for the all-ones code of a non-finite point), so invalid codes end up behind the valid ones without sorting the
+// empty digits in between.  The one-sweep sort takes "bits to sort" from device memory; here each launch names its digit.
+cudaError_t map_sort_codes(b200reg_handle* h, int n, int code_passes) {
+  cudaError_t e;
+  OneSweepScratch& sc = h->map_sort;
+  const int max_passes = 8;
+  const int n_tiles = sc.tiles(n);
+  const size_t words = sc.words(n, max_passes);
+  if ((e = sc.buf.reserve(words)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(sc.buf.p, 0, words * sizeof(uint32_t), h->stream)) != cudaSuccess) return e;
+  uint32_t* hist = sc.buf.p;
+  unsigned int* tickets = sc.buf.p + (size_t)max_passes * kOsRadix;
+  uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
+  const uint32_t* d_nbits = reinterpret_cast<const uint32_t*>(h->map_scalar.p + 1);  // holds 64: every digit "significant"
+  int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
+  if (hb > kNumSM * 4) hb = kNumSM * 4;
+  launch_counter() += 2 + code_passes;
+  k_os_histogram<unsigned long long><<<hb, kOsThreads, 0, h->stream>>>(h->map_codes_a.p, n, d_nbits, max_passes, hist);
+  unsigned long long* a = h->map_codes_a.p;
+  unsigned long long* b = h->map_codes_b.p;
+  int launch = 0;
+  for (int p = 0; p < code_passes + 1; ++p) {
+    const int digit = p < code_passes ? p : 7;
+    k_os_pass<unsigned long long><<<n_tiles, kOsThreads, 0, h->stream>>>((launch & 1) ? b : a, nullptr, (launch & 1) ? a : b, nullptr, n, digit, d_nbits, hist,
+                                                                          status + (size_t)digit * n_tiles * kOsRadix, tickets + digit * 32);
+    ++launch;
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -664,6 +704,7 @@ int b200reg_destroy(b200reg_handle* h) {
   if (h->ev_side_done) cudaEventDestroy(h->ev_side_done);
   h->grid_spec.release();
   h->batch_results.release(); h->tq_runs.release(); h->tq_next.release(); h->pin_runs.release(); h->fit_jobs.release(); h->batch_d2.release(); h->batch_pending.release(); h->batch_pending2.release(); h->batch_n_pending.release(); h->pin_batch.release();
+  h->map_src.release(); h->map_world.release(); h->map_out.release(); h->map_kf.release(); h->map_events.release(); h->map_codes_a.release(); h->map_codes_b.release(); h->map_scalar.release(); h->map_tile_heads.release(); h->map_sort.buf.release();
   delete h;
   return B200REG_OK;
 }
@@ -1778,6 +1819,8 @@ int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double*
   if (fitness_ms) *fitness_ms = h->batch_fitness_ms;
   return B200REG_OK;
 }
+
+#include "b200reg_api_map.inl"
 
 // ---- GICP introspection ----------------------------------------------------------------------
 int b200reg_gicp_get_covariances(b200reg_handle* h, int which, double* out9, size_t n_points) {

@@ -91,7 +91,7 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
 #pragma unroll
   for (int r = 0; r < kOsItems; ++r) {
     const int i = wbase + r * 32 + lane;
-    v[r] = i < n ? vals_in[i] : 0u;
+    v[r] = (vals_in != nullptr && i < n) ? vals_in[i] : 0u;  // vals_in == nullptr: a keys-only sort
   }
 #pragma unroll
   for (int r = 0; r < kOsItems; ++r) {
@@ -179,7 +179,7 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
     __syncwarp();
     if (ok) {
       keys_out[dst] = k[r];
-      vals_out[dst] = v[r];
+      if (vals_out != nullptr) vals_out[dst] = v[r];
     }
   }
 }
@@ -192,7 +192,7 @@ struct OneSweepScratch {
   size_t words(int n, int max_passes) const { return (size_t)max_passes * (kOsRadix + 32 + (size_t)tiles(n) * kOsRadix); }
 };
 
-// enqueue: sorts (keys_a, vals_a)[0..n) by the low *nbits_ptr key bits (device-resident count, <= 8 * max_passes);
+// enqueue: sorts (keys_a, vals_a)[0..n) — vals_a == nullptr: the keys alone — by the low *nbits_ptr key bits (device-resident count, <= 8 * max_passes);
 // pass p reads A when p is even, B when odd, so the result lies in B after an odd number of passes that ran.
 template <typename KeyT>
 inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const uint32_t* nbits_ptr, int max_passes) {
@@ -211,9 +211,9 @@ inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* key
   k_os_histogram<KeyT><<<hb, kOsThreads, 0, st>>>(keys_a, n, nbits_ptr, max_passes, hist);
   for (int p = 0; p < max_passes; ++p) {
     const KeyT* ki = (p & 1) ? keys_b : keys_a;
-    const uint32_t* vi = (p & 1) ? vals_b : vals_a;
+    const uint32_t* vi = vals_a ? ((p & 1) ? vals_b : vals_a) : nullptr;
     KeyT* ko = (p & 1) ? keys_a : keys_b;
-    uint32_t* vo = (p & 1) ? vals_a : vals_b;
+    uint32_t* vo = vals_a ? ((p & 1) ? vals_a : vals_b) : nullptr;
     k_os_pass<KeyT><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32);
   }
   return cudaGetLastError();

@@ -304,6 +304,20 @@ int b200reg_batch_run(b200reg_multi* m, const b200reg_pair* pairs, size_t n_pair
  * (n_devices ints), CUDA-event duration of the all-gather on device 0.  Any pointer may be NULL. */
 int b200reg_batch_get_info(b200reg_multi* m, int* n_devices, int* uses_nccl, int* nccl_version, int* pairs_per_device, double* gather_ms);
 
+/* ---- MapCloudGenerator::generate [REF src/hdl_graph_slam/map_cloud_generator.cpp:13-49] ----
+ * Every keyframe cloud transformed by its pose (poses16: n_keyframes column-major float 4x4, keyframe->pose.matrix().cast<float>())
+ * and concatenated in keyframe order; with resolution > 0 reduced to the occupied voxel centres of a
+ * pcl::octree::OctreePointCloud(resolution) over that cloud, in getOccupiedVoxelCenters' depth-first order (bit-identical:
+ * the octree's bounding box grows with the points in insertion order, and the device path reproduces that growth); with
+ * resolution <= 0 the unfiltered concatenation comes back [REF :33-34].  out needs room for every input point in the
+ * worst case; B200REG_E_CAPACITY reports the needed count in *n_out.  min3_depth (optional, 4 doubles): origin of the final
+ * octree box and its depth.  No keyframes is B200REG_E_INVALID (the reference warns and returns nullptr).
+ * _cached takes the keyframe clouds from the handle's keyframe cache (b200reg_cloud_put) instead of host pointers. */
+int b200reg_map_cloud(b200reg_handle* h, const float* const* clouds, const size_t* n_points, const float* poses16, size_t n_keyframes, double resolution, float* out_xyzw, size_t out_capacity,
+                      size_t* n_out, double* min3_depth);
+int b200reg_map_cloud_cached(b200reg_handle* h, const int64_t* ids, const float* poses16, size_t n_keyframes, double resolution, float* out_xyzw, size_t out_capacity, size_t* n_out,
+                             double* min3_depth);
+
 /* ---- the host side of the two front-end nodelets, in C++ above the calls of this header (csrc/b200reg_odometry.cu) ----
  * ScanMatchingOdometryNodelet::matching [REF apps/scan_matching_odometry_nodelet.cpp:173-270] as an object: the frame-to-
  * keyframe state machine (first scan -> keyframe; guess = prev_trans * delta; not converged / jump gate -> frame ignored;
