@@ -501,7 +501,7 @@ cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const f
   const int blocks = (n + 7) / 8;  // one warp per query, 8 warps per CTA
   launch_counter() += 3;
   k_gicp_knn<kKnnCovariance><<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
-  k_gicp_knn_brute<kKnnCovariance><<<kNumSM * 4, 256, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
+  k_gicp_knn_brute<kKnnCovariance><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
   k_gicp_regularize<<<(n + 127) / 128, 128, 0, h->stream>>>(n, reg, covs);
   return cudaGetLastError();
 }
@@ -1247,7 +1247,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
     launch_counter() += 4;
     if (n) {
       k_gicp_knn<kKnnNormalNz><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-      k_gicp_knn_brute<kKnnNormalNz><<<kNumSM * 4, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+      k_gicp_knn_brute<kKnnNormalNz><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
     }
     k_nz_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.normal_thresh, h->ror_keep.p, h->ror_block_count.p);
   } else if (spec.statistical) {
@@ -1261,7 +1261,7 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
     launch_counter() += 5;
     if (n) {
       k_gicp_knn<kKnnMeanDistance><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-      k_gicp_knn_brute<kKnnMeanDistance><<<kNumSM * 4, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
+      k_gicp_knn_brute<kKnnMeanDistance><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
     }
     k_sor_threshold<<<1, 1024, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.stddev_mul, h->sor_stats.p);
     k_sor_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, h->sor_stats.p, h->ror_keep.p, h->ror_block_count.p);

@@ -430,20 +430,25 @@ __global__ void __launch_bounds__(256) k_gicp_knn(NnView g, const float4* __rest
   if (lane < 6) covs[(size_t)qi * 6 + lane] = c;
 }
 
-// step 1b: one CTA per isolated point: every warp scans its own eighth of the cloud with the same
-// filtered list, the eight lists are merged by warp 0
+// step 1b: one CTA per isolated point: every one of its sixteen warps scans its own sixteenth of the cloud with the same
+// filtered list, then the sixteen lists are merged pairwise in four rounds (a tree: warps 0, 2, 4, .. take their right
+// neighbour's list, then 0, 4, 8, .. and so on).  Round 1 of this kernel ran eight warps and let warp 0 merge the other
+// seven lists one after the other: one query per CTA is pure latency (ncu: long_scoreboard 39 %, 12 % warps active), so
+// halving the scan per warp and turning seven serial merges into four rounds is worth ~2x on the ~100 isolated returns of
+// a scan (65-85 us of a 0.41 ms statistical filter call, and the same for FAST_GICP's covariances and the flat filter).
+constexpr int kBruteWarps = 16;
 template <int TAIL>
-__global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* __restrict__ pts, int k, double* __restrict__ covs, const int* __restrict__ pending,
-                                                        const unsigned int* __restrict__ n_pending, float* __restrict__ mean_dist) {
-  __shared__ float s_bd[8][64];
-  __shared__ int s_bi[8][64];
-  __shared__ float s_ld[8][32];
-  __shared__ int s_li[8][32];
+__global__ void __launch_bounds__(kBruteWarps * 32) k_gicp_knn_brute(NnView g, const float4* __restrict__ pts, int k, double* __restrict__ covs, const int* __restrict__ pending,
+                                                                     const unsigned int* __restrict__ n_pending, float* __restrict__ mean_dist) {
+  __shared__ float s_bd[kBruteWarps][64];
+  __shared__ int s_bi[kBruteWarps][64];
+  __shared__ float s_ld[kBruteWarps][32];
+  __shared__ int s_li[kBruteWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int np = (int)*n_pending;
   const int km1 = k - 1;
   const uint32_t gn = TAIL != kKnnCovariance ? min((uint32_t)g.n, g.meta->n_valid) : (uint32_t)g.n;
-  const uint32_t chunk = ((gn + 7u) / 8u + 31u) & ~31u;
+  const uint32_t chunk = ((gn + (uint32_t)kBruteWarps - 1u) / (uint32_t)kBruteWarps + 31u) & ~31u;
   for (int e = blockIdx.x; e < np; e += gridDim.x) {
     const int w = pending[e];
     const float4 qp = __ldg(g.pts + w);
@@ -453,11 +458,17 @@ __global__ void __launch_bounds__(256) k_gicp_knn_brute(NnView g, const float4* 
     knn_offer_range(g, s0, s1, qp.x, qp.y, qp.z, km1, lane, L);
     knn_flush(L, km1, lane);
     __syncthreads();  // the previous query's lists have been consumed
-    s_ld[warp][lane] = L.td;
-    s_li[warp][lane] = L.ti;
-    __syncthreads();
+    // pairwise merge tree; the k smallest of a union do not depend on the order of the merges (ties by index)
+    for (int stride = 1; stride < kBruteWarps; stride <<= 1) {
+      if ((warp & (2 * stride - 1)) == stride) {  // a right-hand list of this round: publish it
+        s_ld[warp][lane] = L.td;
+        s_li[warp][lane] = L.ti;
+      }
+      __syncthreads();
+      if ((warp & (2 * stride - 1)) == 0) knn_merge32(L.td, L.ti, s_ld[warp + stride][lane], s_li[warp + stride][lane], lane);
+      __syncthreads();
+    }
     if (warp == 0) {
-      for (int o = 1; o < 8; ++o) knn_merge32(L.td, L.ti, s_ld[o][lane], s_li[o][lane], lane);
       if (TAIL == kKnnMeanDistance) {
         const float d = knn_mean_distance(k, lane, L.td, L.ti);
         if (lane == 0) mean_dist[__float_as_int(qp.w)] = d;

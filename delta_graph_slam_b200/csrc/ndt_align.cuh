@@ -506,12 +506,20 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
     uint32_t pkey[NOFF], ph[NOFF];
     uint4 pe[NOFF];
     bool pin[NOFF];
+    // the seven keys are the centre key +- one stride, and a neighbour is inside the lattice when its own axis
+    // coordinate is (the other two are the centre's): one key and nine range tests instead of seven of each
+    const int r0 = c0 - gp.min_b[0], r1 = c1 - gp.min_b[1], r2 = c2 - gp.min_b[2];
+    const uint32_t kc = (uint32_t)(r0 * gp.mul[0] + r1 * gp.mul[1] + r2 * gp.mul[2]);
+    const int e0 = gp.max_b[0] - gp.min_b[0], e1 = gp.max_b[1] - gp.min_b[1], e2 = gp.max_b[2] - gp.min_b[2];
+    const bool x_c = r0 >= 0 && r0 <= e0, y_c = r1 >= 0 && r1 <= e1, z_c = r2 >= 0 && r2 <= e2;
 #pragma unroll
     for (int o = 0; o < NOFF; ++o) {
       const int dx = NOFF == 1 ? 0 : (o == 1 ? 1 : o == 2 ? -1 : 0), dy = NOFF == 1 ? 0 : (o == 3 ? 1 : o == 4 ? -1 : 0), dz = NOFF == 1 ? 0 : (o == 5 ? 1 : o == 6 ? -1 : 0);
-      const int i0 = c0 + dx, i1 = c1 + dy, i2 = c2 + dz;
-      pin[o] = !(i0 < gp.min_b[0] || i0 > gp.max_b[0] || i1 < gp.min_b[1] || i1 > gp.max_b[1] || i2 < gp.min_b[2] || i2 > gp.max_b[2]);
-      pkey[o] = (uint32_t)((i0 - gp.min_b[0]) * gp.mul[0] + (i1 - gp.min_b[1]) * gp.mul[1] + (i2 - gp.min_b[2]) * gp.mul[2]);
+      const bool x_ok = dx == 0 ? x_c : (r0 + dx >= 0 && r0 + dx <= e0);
+      const bool y_ok = dy == 0 ? y_c : (r1 + dy >= 0 && r1 + dy <= e1);
+      const bool z_ok = dz == 0 ? z_c : (r2 + dz >= 0 && r2 + dz <= e2);
+      pin[o] = x_ok && y_ok && z_ok;
+      pkey[o] = kc + (uint32_t)(dx * gp.mul[0] + dy * gp.mul[1] + dz * gp.mul[2]);
       ph[o] = ndt_hash(pkey[o], grid.mask);
       pe[o] = pin[o] ? lk_bucket<STAGED>(grid, ph[o]) : make_uint4(kInvalidKey, 0u, kInvalidKey, 0u);
     }
@@ -573,19 +581,18 @@ __device__ __forceinline__ void ndt_point(const NdtShared& s, const NdtLookup& g
     float e = __fmul_rn(gauss_d2, ex);
     const bool ok = valid && !(e > 1.f || e < 0.f || e != e);  // upstream returns 0 for such a hit (score included)
     if (!kBatchProbes && !ok) continue;
-    const float nscore = __fsub_rn(score, sinc);
     // e = float(e * d1)
     const float t2 = __fmul_rn(d1h, e);
     e = __fadd_rn(t2, fmaf(d1l, e, fmaf(d1h, e, -t2)));
-    const float n0 = fmaf(e, cq0, v0), n1 = fmaf(e, cq1, v1), n2 = fmaf(e, cq2, v2);
-    score = ok ? nscore : score;
-    v0 = ok ? n0 : v0; v1 = ok ? n1 : v1; v2 = ok ? n2 : v2;
+    // a hit that does not count contributes with weight zero: two selects instead of one per accumulator (the voxel
+    // record read for it is record 0, a real voxel, so every product below is finite and x + 0 * y == x)
+    const float em = ok ? e : 0.f;
+    score = __fsub_rn(score, ok ? sinc : 0.f);
+    v0 = fmaf(em, cq0, v0); v1 = fmaf(em, cq1, v1); v2 = fmaf(em, cq2, v2);
     if (need_hessian) {
-      const float ed = __fmul_rn(e, gauss_d2);
-      const float h00 = m00 + (e * C00 - ed * cq0 * cq0), h01 = m01 + (e * C01 - ed * cq0 * cq1), h02 = m02 + (e * C02 - ed * cq0 * cq2);
-      const float h11 = m11 + (e * C11 - ed * cq1 * cq1), h12 = m12 + (e * C12 - ed * cq1 * cq2), h22 = m22 + (e * C22 - ed * cq2 * cq2);
-      m00 = ok ? h00 : m00; m01 = ok ? h01 : m01; m02 = ok ? h02 : m02;
-      m11 = ok ? h11 : m11; m12 = ok ? h12 : m12; m22 = ok ? h22 : m22;
+      const float ed = __fmul_rn(em, gauss_d2);
+      m00 = m00 + (em * C00 - ed * cq0 * cq0); m01 = m01 + (em * C01 - ed * cq0 * cq1); m02 = m02 + (em * C02 - ed * cq0 * cq2);
+      m11 = m11 + (em * C11 - ed * cq1 * cq1); m12 = m12 + (em * C12 - ed * cq1 * cq2); m22 = m22 + (em * C22 - ed * cq2 * cq2);
     }
   }
   if (!hits) return;
@@ -641,6 +648,33 @@ __device__ __forceinline__ void warp_transpose_reduce32(float v[32], int lane) {
   }
 }
 
+// ---- bulk asynchronous copy global -> shared (the TMA engine's 1-D form, cp.async.bulk; SASS: UBLKCP) ---------------
+// One elected thread posts the expected byte count on an mbarrier and issues the copies; the copy engine moves the data
+// without passing through registers and completes the transaction count on the barrier, on whose phase every thread waits.
+// Sizes and addresses are multiples of 16 bytes (cudaMalloc'd arrays, 16-byte records).
+#ifndef B200_STAGE_TMA
+#define B200_STAGE_TMA 1
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+               "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+
 // group barrier: monotonically increasing counter, one arrival per CTA per use
 __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int target) {
   __syncthreads();
@@ -666,6 +700,10 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
   __shared__ NdtShared s;
   __shared__ GridParams s_gp;
   __shared__ int s_job;
+  __shared__ __align__(8) uint64_t s_stage_bar;  // mbarrier of the grid staging copies
+  uint32_t stage_parity = 0;
+  if (B200_STAGE_TMA && threadIdx.x == 0) mbar_init(&s_stage_bar, 1);
+  __syncthreads();
   extern __shared__ __align__(16) unsigned char stage[];  // kStageBytes
   const int G = ctas_per_group;
   const int group = blockIdx.x / G, rank = blockIdx.x % G;
@@ -758,6 +796,19 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
       if (table_bytes + vox_bytes + cen_bytes <= (size_t)kStageBytes) {
         if (staged_table != (const void*)job.grid.table) {
           __syncthreads();
+#if B200_STAGE_TMA
+          // three bulk copies (hash table, 48-byte voxel records, centroids for KDTREE) posted by one thread: ~200 KB per SM
+          // without an instruction per 16 bytes; everybody waits on the barrier's phase
+          if (tid == 0) {
+            mbar_expect_tx(&s_stage_bar, (uint32_t)(table_bytes + vox_bytes + cen_bytes));
+            // a single bulk copy moves at most 2^20 - 16 bytes here; the pieces are far below that
+            bulk_g2s(stage, job.grid.table, (uint32_t)table_bytes, &s_stage_bar);
+            if (vox_bytes) bulk_g2s(stage + table_bytes, job.grid.voxels, (uint32_t)vox_bytes, &s_stage_bar);
+            if (cen_bytes) bulk_g2s(stage + table_bytes + vox_bytes, job.grid.centroids, (uint32_t)cen_bytes, &s_stage_bar);
+          }
+          mbar_wait(&s_stage_bar, stage_parity);
+          stage_parity ^= 1u;
+#else
           const uint4* src_t = reinterpret_cast<const uint4*>(job.grid.table);
           uint4* dst = reinterpret_cast<uint4*>(stage);
           const int n_t = (int)(table_bytes / 16), n_v = (int)(vox_bytes / 16), n_c = (int)(cen_bytes / 16);
@@ -766,6 +817,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_ndt_align(const NdtJob* __
           for (int i = tid; i < n_v; i += kAlignThreads) dst[n_t + i] = __ldg(src_v + i);
           const uint4* src_c = reinterpret_cast<const uint4*>(job.grid.centroids);
           for (int i = tid; i < n_c; i += kAlignThreads) dst[n_t + n_v + i] = __ldg(src_c + i);
+#endif
           staged_table = (const void*)job.grid.table;
         }
         look.table = reinterpret_cast<const uint2*>(stage);
