@@ -54,6 +54,7 @@ struct b200reg_handle {
   // VoxelGrid filter
   VoxelSort vg_sort;
   DevBuf<uint32_t> vg_id, vg_count;
+  DevBuf<float4> vg_sorted;  // the scan's points in sorted (voxel, input) order: k_vg_gather -> k_vg_centroids
   DevBuf<VgCounts> vg_counts;
   DevBuf<unsigned int> vg_done;
   int vg_last_n = 0, vg_last_out = 0;
@@ -319,7 +320,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared(k_os_pass<unsigned long long>)); B200_ATTR(prefer_shared(k_os_pass<uint32_t>)); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared((k_os_pass<unsigned long long, 8>))); B200_ATTR(prefer_shared((k_os_pass<uint32_t, 16>))); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_gather)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -604,8 +605,9 @@ cudaError_t map_sort_codes(b200reg_handle* h, int n, int code_passes) {
   cudaError_t e;
   OneSweepScratch& sc = h->map_sort;
   const int max_passes = 8;
-  const int n_tiles = sc.tiles(n);
-  const size_t words = sc.words(n, max_passes);
+  constexpr int ITEMS = os_items<unsigned long long>();
+  const int n_tiles = sc.tiles(n, ITEMS);
+  const size_t words = sc.words(n, max_passes, ITEMS);
   if ((e = sc.buf.reserve(words)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(sc.buf.p, 0, words * sizeof(uint32_t), h->stream)) != cudaSuccess) return e;
   uint32_t* hist = sc.buf.p;
@@ -613,7 +615,7 @@ cudaError_t map_sort_codes(b200reg_handle* h, int n, int code_passes) {
   uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
   const uint32_t* d_nbits = reinterpret_cast<const uint32_t*>(h->map_scalar.p + 1);  // holds 64: every digit "significant"
   int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
-  if (hb > kNumSM * 4) hb = kNumSM * 4;
+  if (hb > kNumSM * 2) hb = kNumSM * 2;
   launch_counter() += 2 + code_passes;
   k_os_histogram<unsigned long long><<<hb, kOsThreads, 0, h->stream>>>(h->map_codes_a.p, n, d_nbits, max_passes, hist);
   unsigned long long* a = h->map_codes_a.p;
@@ -621,7 +623,7 @@ cudaError_t map_sort_codes(b200reg_handle* h, int n, int code_passes) {
   int launch = 0;
   for (int p = 0; p < code_passes + 1; ++p) {
     const int digit = p < code_passes ? p : 7;
-    k_os_pass<unsigned long long><<<n_tiles, kOsThreads, 0, h->stream>>>((launch & 1) ? b : a, nullptr, (launch & 1) ? a : b, nullptr, n, digit, d_nbits, hist,
+    k_os_pass<unsigned long long, ITEMS><<<n_tiles, kOsThreads, 0, h->stream>>>((launch & 1) ? b : a, nullptr, (launch & 1) ? a : b, nullptr, n, digit, d_nbits, hist,
                                                                           status + (size_t)digit * n_tiles * kOsRadix, tickets + digit * 32);
     ++launch;
   }
@@ -685,7 +687,7 @@ int b200reg_destroy(b200reg_handle* h) {
   for (auto& pr : h->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (h->mail) cudaFreeHost((void*)h->mail);
   h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
-  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_counts.release(); h->vg_done.release();
+  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_sorted.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release(); h->trace.release();
   h->nn.release(); h->fit_partials.release();
   h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release(); h->sor_dist.release(); h->sor_stats.release(); h->sor_pending.release(); h->sor_n_pending.release();
@@ -1023,7 +1025,9 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_counts.reserve(1));
   B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
-  launch_counter() += 1 + (min_pts > 1 ? 1 : 0);
+  B200_CUDA_TRY(h->vg_sorted.reserve(n ? n : 1));
+  launch_counter() += 2 + (min_pts > 1 ? 1 : 0);
+  k_vg_gather<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sorted.p);
   // the overflow case publishes from k_vg_centroids even when a compaction pass follows
   VgCounts* hc = const_cast<VgCounts*>(&h->mail->vg);
   unsigned int* hf = const_cast<unsigned int*>(&h->mail->vg_seq);
@@ -1032,7 +1036,7 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
     B200_CUDA_TRY(h->vg_done.reserve(1));
     B200_CUDA_TRY(cudaMemsetAsync(h->vg_done.p, 0, h->vg_done.cap * sizeof(unsigned int), h->stream));
   }
-  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
+  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sorted.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
                                                 min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1, host_out,
                                                 (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->gate.on);
   if (h->gate.on) {  // only acts in the "leaf size too small" case: the output is then the gated input

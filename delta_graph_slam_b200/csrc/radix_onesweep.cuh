@@ -26,15 +26,15 @@ namespace b200 {
 constexpr int kOsThreads = 256;
 constexpr int kOsRadixBits = 8;
 constexpr int kOsRadix = 256;
-constexpr int kOsItems = 16;                       // keys per thread: 4096-key tiles
-constexpr int kOsTile = kOsThreads * kOsItems;
 constexpr int kOsLookBack = 8;                     // predecessor tiles inspected per round trip of the look-back
 constexpr uint32_t kOsFlagAggregate = 1u << 30, kOsFlagPrefix = 2u << 30, kOsFlagMask = 3u << 30, kOsCountMask = ~kOsFlagMask;
 
 template <typename KeyT>
 __device__ __forceinline__ uint32_t os_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & (kOsRadix - 1); }
 
-// all digit histograms in one read of the keys.  hist: [max_passes][256], zeroed before the launch.
+// all digit histograms in one read of the keys.  hist: [max_passes][256], zeroed before the launch.  Two CTAs per SM at
+// most (every CTA ends with up to 256 global atomics per digit: a grid of hundreds of small CTAs spent more time on those
+// than on the keys), four keys per thread in flight.
 template <typename KeyT>
 static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* __restrict__ keys, int n, const uint32_t* __restrict__ nbits_ptr, int max_passes, uint32_t* __restrict__ hist) {
   constexpr int MAXP = (int)sizeof(KeyT);
@@ -46,14 +46,23 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* 
   // whole warps walk the keys together (the trip count is warp-uniform), so equal digits inside a warp — the rule
   // for the upper digits of voxel keys — are counted with one shared-memory atomic instead of up to 32 serialised ones
   const int lane = threadIdx.x & 31;
-  for (int base = (blockIdx.x * kOsThreads + (threadIdx.x & ~31)); base < n; base += gridDim.x * kOsThreads) {
-    const int i = base + lane;
-    const bool ok = i < n;
-    const KeyT k = ok ? keys[i] : (KeyT)0;
+  constexpr int U = 4;
+  for (int base = (blockIdx.x * kOsThreads + (threadIdx.x & ~31)) * U; base < n; base += gridDim.x * kOsThreads * U) {
+    KeyT k[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * 32 + lane;
+      ok[u] = i < n;
+      k[u] = ok[u] ? keys[i] : (KeyT)0;
+    }
     for (int p = 0; p < passes; ++p) {
-      const uint32_t dgt = ok ? os_digit(k, p * kOsRadixBits) : (uint32_t)kOsRadix;
-      const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-      if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&s[p][dgt], (uint32_t)__popc(peers));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t dgt = ok[u] ? os_digit(k[u], p * kOsRadixBits) : (uint32_t)kOsRadix;
+        const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+        if (ok[u] && (__ffs(peers) - 1) == lane) atomicAdd(&s[p][dgt], (uint32_t)__popc(peers));
+      }
     }
   }
   __syncthreads();
@@ -64,13 +73,19 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* 
 }
 
 // One digit pass.  status: [n_tiles][256] words of this pass (zero = not yet published); ticket: this pass's tile
-// counter (zero before the launch).
-template <typename KeyT>
+// counter (zero before the launch).  ITEMS keys per thread (16 for 32-bit keys, 8 for 64-bit ones: the tile is staged in
+// shared memory).
+template <typename KeyT, int ITEMS>
 static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
                                                         int pass, const uint32_t* __restrict__ nbits_ptr, const uint32_t* __restrict__ hist, uint32_t* status, unsigned int* ticket) {
   if ((uint32_t)(pass * kOsRadixBits) >= *nbits_ptr) return;
   constexpr int WARPS = kOsThreads / 32;
-  __shared__ uint32_t cnt[WARPS][kOsRadix];
+  constexpr int TILE = kOsThreads * ITEMS;
+  __shared__ uint32_t cnt[WARPS][kOsRadix];   // per-warp digit counts, then per-warp LOCAL bases (position inside the staged tile)
+  __shared__ uint32_t s_tstart[kOsRadix];     // first position of digit d inside the staged tile
+  __shared__ uint32_t s_gbase[kOsRadix];      // first output slot of this tile's digit-d run
+  __shared__ KeyT s_keys[TILE];
+  __shared__ uint32_t s_vals[TILE];
   __shared__ uint32_t s_warp[8];
   __shared__ unsigned int s_tile;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -79,22 +94,25 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
   __syncthreads();
   const int tile = (int)s_tile;
   const int shift = pass * kOsRadixBits;
-  const int wbase = tile * kOsTile + warp * (32 * kOsItems);
-  KeyT k[kOsItems];
-  uint32_t v[kOsItems];
+  const int tbase = tile * TILE;
+  const int wbase = tbase + warp * (32 * ITEMS);
+  const int tile_n = min(TILE, n - tbase);
+  const bool has_vals = vals_in != nullptr;  // nullptr: a keys-only sort
+  KeyT k[ITEMS];
+  uint32_t v[ITEMS];
   // ---- A: per-warp digit counts (all loads of the slice issued before the first use)
 #pragma unroll
-  for (int r = 0; r < kOsItems; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
     k[r] = i < n ? keys_in[i] : (KeyT)0;
   }
 #pragma unroll
-  for (int r = 0; r < kOsItems; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
-    v[r] = (vals_in != nullptr && i < n) ? vals_in[i] : 0u;  // vals_in == nullptr: a keys-only sort
+    v[r] = (has_vals && i < n) ? vals_in[i] : 0u;
   }
 #pragma unroll
-  for (int r = 0; r < kOsItems; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
     const bool ok = i < n;
     const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;  // kOsRadix = "no element"
@@ -141,21 +159,27 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
       }
       *st = kOsFlagPrefix | (excl + c);
     }
-    // first output slot of digit d = keys with a smaller digit (global histogram) + this digit in lower tiles
+    // two exclusive scans over the digits: the global histogram (keys with a smaller digit anywhere) and this tile's
+    // own counts (where the digit's run starts inside the staged tile)
     const uint32_t total_d = hist[pass * kOsRadix + d];
-    uint32_t incl = total_d;
+    uint32_t incl_g = total_d, incl_t = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const uint32_t tg = __shfl_up_sync(0xffffffffu, incl_g, o);
+      const uint32_t tt = __shfl_up_sync(0xffffffffu, incl_t, o);
+      if (lane >= o) { incl_g += tg; incl_t += tt; }
     }
-    if (lane == 31) s_warp[warp] = incl;
+    __shared__ uint32_t s_warp_t[8];
+    if (lane == 31) { s_warp[warp] = incl_g; s_warp_t[warp] = incl_t; }
     __syncthreads();
-    uint32_t off = 0;
+    uint32_t off_g = 0, off_t = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w)
-      if (w < warp) off += s_warp[w];
-    uint32_t run = off + incl - total_d + excl;
+      if (w < warp) { off_g += s_warp[w]; off_t += s_warp_t[w]; }
+    const uint32_t tstart = off_t + incl_t - c;
+    s_tstart[d] = tstart;
+    s_gbase[d] = off_g + incl_g - total_d + excl;
+    uint32_t run = tstart;
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
       const uint32_t cw = cnt[w][d];
@@ -164,23 +188,35 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
     }
   }
   __syncthreads();
-  // ---- C: ranks inside the warp round, in lane order; scatter
+  // ---- C: rank of every key inside the tile (warp slices in order, rounds in order, lanes in order: stable), staged in
+  // shared memory in digit order ...
 #pragma unroll
-  for (int r = 0; r < kOsItems; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
     const bool ok = i < n;
     const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;
     const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t dst = 0;
-    if (ok) dst = cnt[warp][dgt] + rank;
+    uint32_t lpos = 0;
+    if (ok) lpos = cnt[warp][dgt] + rank;
     __syncwarp();
     if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
     __syncwarp();
     if (ok) {
-      keys_out[dst] = k[r];
-      if (vals_out != nullptr) vals_out[dst] = v[r];
+      s_keys[lpos] = k[r];
+      s_vals[lpos] = v[r];
     }
+  }
+  __syncthreads();
+  // ... and written out from there: consecutive threads hold consecutive positions of the staged tile, i.e. (mostly) the
+  // same digit and therefore consecutive output slots — the scatter of a 256-way partition as runs of coalesced stores
+  // instead of 32 different sectors per store instruction
+  for (int p = tid; p < tile_n; p += kOsThreads) {
+    const KeyT key = s_keys[p];
+    const uint32_t d = os_digit(key, shift);
+    const uint32_t dst = s_gbase[d] + ((uint32_t)p - s_tstart[d]);
+    keys_out[dst] = key;
+    if (has_vals) vals_out[dst] = s_vals[p];
   }
 }
 
@@ -188,9 +224,11 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
 // memset in front of the histogram kernel.
 struct OneSweepScratch {
   DevBuf<uint32_t> buf;
-  int tiles(int n) const { return n > 0 ? (n + kOsTile - 1) / kOsTile : 1; }
-  size_t words(int n, int max_passes) const { return (size_t)max_passes * (kOsRadix + 32 + (size_t)tiles(n) * kOsRadix); }
+  static int tiles(int n, int items) { return n > 0 ? (n + kOsThreads * items - 1) / (kOsThreads * items) : 1; }
+  static size_t words(int n, int max_passes, int items) { return (size_t)max_passes * (kOsRadix + 32 + (size_t)tiles(n, items) * kOsRadix); }
 };
+template <typename KeyT>
+constexpr int os_items() { return sizeof(KeyT) == 8 ? 8 : 16; }
 
 // enqueue: sorts (keys_a, vals_a)[0..n) — vals_a == nullptr: the keys alone — by the low *nbits_ptr key bits (device-resident count, <= 8 * max_passes);
 // pass p reads A when p is even, B when odd, so the result lies in B after an odd number of passes that ran.
@@ -198,15 +236,16 @@ template <typename KeyT>
 inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const uint32_t* nbits_ptr, int max_passes) {
   if (n <= 0) return cudaSuccess;
   cudaError_t e;
-  const int n_tiles = sc.tiles(n);
-  const size_t words = sc.words(n, max_passes);
+  constexpr int ITEMS = os_items<KeyT>();
+  const int n_tiles = sc.tiles(n, ITEMS);
+  const size_t words = sc.words(n, max_passes, ITEMS);
   if ((e = sc.buf.reserve(words)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(sc.buf.p, 0, words * sizeof(uint32_t), st)) != cudaSuccess) return e;
   uint32_t* hist = sc.buf.p;                                   // [max_passes][256]
   unsigned int* tickets = sc.buf.p + (size_t)max_passes * kOsRadix;  // [max_passes][32] (one 128-byte line each)
   uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
   int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
-  if (hb > kNumSM * 4) hb = kNumSM * 4;
+  if (hb > kNumSM * 2) hb = kNumSM * 2;
   launch_counter() += 1 + max_passes;
   k_os_histogram<KeyT><<<hb, kOsThreads, 0, st>>>(keys_a, n, nbits_ptr, max_passes, hist);
   for (int p = 0; p < max_passes; ++p) {
@@ -214,7 +253,7 @@ inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* key
     const uint32_t* vi = vals_a ? ((p & 1) ? vals_b : vals_a) : nullptr;
     KeyT* ko = (p & 1) ? keys_a : keys_b;
     uint32_t* vo = vals_a ? ((p & 1) ? vals_a : vals_b) : nullptr;
-    k_os_pass<KeyT><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32);
+    k_os_pass<KeyT, ITEMS><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32);
   }
   return cudaGetLastError();
 }

@@ -9,3 +9,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 1
   > "gpurun_out/bench_loop_n$N.json" 2> "gpurun_out/bench_loop_n$N.err"
 echo "bench loop N=$N rc=$?"
 tail -c 900 "gpurun_out/bench_loop_n$N.json"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$N" --steps 2 --warmup 3 \
+  > "gpurun_out/bench_n$N.json" 2> "gpurun_out/bench_n$N.err"
+echo "bench default N=$N rc=$?"
+tail -c 1500 "gpurun_out/bench_n$N.json"

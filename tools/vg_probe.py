@@ -45,3 +45,6 @@ for name, sensor in (("dense128", synth.DENSE128), ("hdl64", synth.HDL64)):
                                          gbs=(16 * n + 16 * f.n) / (1e-3 * float(np.median(ms))) / 1e9)
     L.b200reg_set_sort_path(0)
 print(json.dumps(out, indent=1))
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/vg_probe.json", "w") as fh:
+    json.dump(out, fh, indent=1)
