@@ -320,7 +320,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared((k_os_pass<unsigned long long, 8>))); B200_ATTR(prefer_shared((k_os_pass<uint32_t, 16>))); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_gather)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared((k_os_pass<unsigned long long, 8>))); B200_ATTR(prefer_shared((k_os_pass<uint32_t, 8>))); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_gather)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -615,16 +615,16 @@ cudaError_t map_sort_codes(b200reg_handle* h, int n, int code_passes) {
   uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
   const uint32_t* d_nbits = reinterpret_cast<const uint32_t*>(h->map_scalar.p + 1);  // holds 64: every digit "significant"
   int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
-  if (hb > kNumSM * 2) hb = kNumSM * 2;
+  if (hb > kNumSM * 4) hb = kNumSM * 4;
   launch_counter() += 2 + code_passes;
-  k_os_histogram<unsigned long long><<<hb, kOsThreads, 0, h->stream>>>(h->map_codes_a.p, n, d_nbits, max_passes, hist);
+  k_os_histogram<unsigned long long><<<hb, kOsThreads, 0, h->stream>>>(h->map_codes_a.p, n, d_nbits, max_passes, hist, kNoGather);
   unsigned long long* a = h->map_codes_a.p;
   unsigned long long* b = h->map_codes_b.p;
   int launch = 0;
   for (int p = 0; p < code_passes + 1; ++p) {
     const int digit = p < code_passes ? p : 7;
     k_os_pass<unsigned long long, ITEMS><<<n_tiles, kOsThreads, 0, h->stream>>>((launch & 1) ? b : a, nullptr, (launch & 1) ? a : b, nullptr, n, digit, d_nbits, hist,
-                                                                          status + (size_t)digit * n_tiles * kOsRadix, tickets + digit * 32);
+                                                                          status + (size_t)digit * n_tiles * kOsRadix, tickets + digit * 32, kNoGather);
     ++launch;
   }
   return cudaGetLastError();
@@ -1023,11 +1023,12 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_id.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_counts.reserve(1));
-  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate));
-  const int blocks = n ? (int)((n + 255) / 256) : 1;
   B200_CUDA_TRY(h->vg_sorted.reserve(n ? n : 1));
-  launch_counter() += 2 + (min_pts > 1 ? 1 : 0);
-  k_vg_gather<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sorted.p);
+  bool gathered = false;  // the one-sweep sort's last pass writes the points in sorted order itself
+  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate, h->vg_sorted.p, &gathered));
+  const int blocks = n ? (int)((n + 255) / 256) : 1;
+  launch_counter() += (gathered ? 1 : 2) + (min_pts > 1 ? 1 : 0);
+  if (!gathered) k_vg_gather<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sorted.p);
   // the overflow case publishes from k_vg_centroids even when a compaction pass follows
   VgCounts* hc = const_cast<VgCounts*>(&h->mail->vg);
   unsigned int* hf = const_cast<unsigned int*>(&h->mail->vg_seq);
@@ -1036,7 +1037,7 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
     B200_CUDA_TRY(h->vg_done.reserve(1));
     B200_CUDA_TRY(cudaMemsetAsync(h->vg_done.p, 0, h->vg_done.cap * sizeof(unsigned int), h->stream));
   }
-  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sorted.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
+  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sorted.p, h->vg_sort.seg_first.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
                                                 min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1, host_out,
                                                 (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->gate.on);
   if (h->gate.on) {  // only acts in the "leaf size too small" case: the output is then the gated input

@@ -19,6 +19,7 @@
 // NCCL is loaded at run time (dlopen "libnccl.so.2"): the library has no link-time dependency on it, single-GPU
 // users never touch it, and inside a process that already carries a NCCL (PyTorch) the same copy is used.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <string.h>
 
 #include <algorithm>
@@ -52,9 +53,13 @@ struct Nccl {
   ncclResult_t (*GetVersion)(int*) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
+    // B200REG_NCCL_LIB names the library explicitly.  Otherwise the soname: a process that already holds an NCCL
+    // (a host that imported torch first gets torch's bundled copy) hands that one back, so there is one NCCL per process.
+    // RTLD_LOCAL: a library loaded here must not satisfy somebody else's later symbol look-ups.
+    if (const char* path = getenv("B200REG_NCCL_LIB")) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (lib) break;
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!lib) { err = std::string("NCCL is not loadable (dlopen libnccl.so.2): ") + dlerror(); return false; }
 #define B200_SYM(field, sym)                                                       \

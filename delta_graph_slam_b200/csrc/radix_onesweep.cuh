@@ -12,7 +12,7 @@
 //                    words, looks back over the preceding tiles' status words until it meets an inclusive prefix,
 //                    publishes its own inclusive prefix, and scatters — keys and values are read once and written
 //                    once per digit.  Inside a tile every warp owns a contiguous slice and ranks its keys in lane
-//                    order (match_any), tiles are ordered by the look-back: the sort is stable, so its output is
+//                    order (ballots over the digit bits), tiles are ordered by the look-back: the sort is stable, so its output is
 //                    bit-identical to the three-launch path.
 //
 // Digit passes beyond the number of significant key bits (device-resident: it depends on the data) return at once,
@@ -32,53 +32,94 @@ constexpr uint32_t kOsFlagAggregate = 1u << 30, kOsFlagPrefix = 2u << 30, kOsFla
 template <typename KeyT>
 __device__ __forceinline__ uint32_t os_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & (kOsRadix - 1); }
 
-// all digit histograms in one read of the keys.  hist: [max_passes][256], zeroed before the launch.  Two CTAs per SM at
-// most (every CTA ends with up to 256 global atomics per digit: a grid of hundreds of small CTAs spent more time on those
-// than on the keys), four keys per thread in flight.
+// Lanes holding the same digit.  match.any costs a round per distinct value in the warp (the 32 different low digits of
+// neighbouring voxel keys are its worst case), so both kernels issue the matches of several keys back to back in front
+// of the code that consumes them and run enough warps per SM to cover the rest.  (Nine ballots over the digit bits
+// instead — fixed latency, three times the instructions — measured 18 us slower per 1 M-point sort in the digit passes
+// and the same in the histogram; profiles/r02_voxelgrid_1m.md.)
+__device__ __forceinline__ uint32_t os_match(uint32_t dgt) { return __match_any_sync(0xffffffffu, dgt); }
+
+// Optional tail of the LAST digit pass that runs: the records the sorted values index are gathered into sorted order
+// while the tile's values are still in shared memory (the VoxelGrid centroid pass then reads consecutive records and
+// no separate gather launch exists).  With a gather attached pass 0 always runs (a key range of one value has no
+// significant bits: the pass is then a stable copy) unless *disabled.
+struct OsGather {
+  const float4* src;    // records indexed by the sorted values
+  float4* dst;          // dst[j] = src[vals_sorted[j]]; nullptr = plain sort
+  const int* disabled;  // device flag: nothing to sort (keys and values were never written)
+};
+constexpr OsGather kNoGather = {nullptr, nullptr, nullptr};
+
+// all digit histograms in one read of the keys.  hist: [max_passes][256], zeroed before the launch.  Four keys per thread
+// in flight.  The kernel is bound by the chain match -> counter update -> __syncwarp of every warp, not by its atomics
+// (taking out the shared or the global ones changed nothing; 148 CTAs took 28 us on a 1 M-key sort, 296 took 20, 592
+// took 19): up to four CTAs per SM.
 template <typename KeyT>
-static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* __restrict__ keys, int n, const uint32_t* __restrict__ nbits_ptr, int max_passes, uint32_t* __restrict__ hist) {
+static __global__ void __launch_bounds__(kOsThreads) k_os_histogram(const KeyT* __restrict__ keys, int n, const uint32_t* __restrict__ nbits_ptr, int max_passes, uint32_t* __restrict__ hist,
+                                                             OsGather gather) {
   constexpr int MAXP = (int)sizeof(KeyT);
-  __shared__ uint32_t s[MAXP][kOsRadix];
+  constexpr int WARPS = kOsThreads / 32;
+  // counters private to a warp: plain read-modify-write by the lane elected per distinct digit
+  __shared__ uint32_t s[MAXP > 4 ? 4 : MAXP][WARPS][kOsRadix];
+  constexpr int PASSES_PER_SWEEP = MAXP > 4 ? 4 : MAXP;  // 64-bit keys: two sweeps over the keys (32 KB of counters each)
   const uint32_t nbits = *nbits_ptr;
-  const int passes = min(max_passes, (int)((nbits + kOsRadixBits - 1) / kOsRadixBits));
-  for (int i = threadIdx.x; i < MAXP * kOsRadix; i += kOsThreads) (&s[0][0])[i] = 0;
-  __syncthreads();
-  // whole warps walk the keys together (the trip count is warp-uniform), so equal digits inside a warp — the rule
-  // for the upper digits of voxel keys — are counted with one shared-memory atomic instead of up to 32 serialised ones
-  const int lane = threadIdx.x & 31;
+  if (gather.dst && *gather.disabled) return;
+  int passes = min(max_passes, (int)((nbits + kOsRadixBits - 1) / kOsRadixBits));
+  if (gather.dst && passes < 1) passes = 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int U = 4;
-  for (int base = (blockIdx.x * kOsThreads + (threadIdx.x & ~31)) * U; base < n; base += gridDim.x * kOsThreads * U) {
-    KeyT k[U];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * 32 + lane;
-      ok[u] = i < n;
-      k[u] = ok[u] ? keys[i] : (KeyT)0;
-    }
-    for (int p = 0; p < passes; ++p) {
+  for (int p0 = 0; p0 < passes; p0 += PASSES_PER_SWEEP) {
+    const int np = min(PASSES_PER_SWEEP, passes - p0);
+    for (int i = threadIdx.x; i < PASSES_PER_SWEEP * WARPS * kOsRadix; i += kOsThreads) (&s[0][0][0])[i] = 0;
+    __syncthreads();
+    // whole warps walk the keys together (the trip count is warp-uniform)
+    for (int base = (blockIdx.x * kOsThreads + (threadIdx.x & ~31)) * U; base < n; base += gridDim.x * kOsThreads * U) {
+      KeyT k[U];
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t dgt = ok[u] ? os_digit(k[u], p * kOsRadixBits) : (uint32_t)kOsRadix;
-        const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-        if (ok[u] && (__ffs(peers) - 1) == lane) atomicAdd(&s[p][dgt], (uint32_t)__popc(peers));
+        const int i = base + u * 32 + lane;
+        ok[u] = i < n;
+        k[u] = ok[u] ? keys[i] : (KeyT)0;
+      }
+      // the digits of one key go to the counters of different passes: their read-modify-writes are independent and
+      // overlap; the next key's (another lane may be elected for the same counter) wait behind one __syncwarp
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int p = 0; p < PASSES_PER_SWEEP; ++p) {
+          if (p < np) {
+            const uint32_t dgt = ok[u] ? os_digit(k[u], (p0 + p) * kOsRadixBits) : (uint32_t)kOsRadix;
+            const uint32_t peers = os_match(dgt);
+            if (ok[u] && (__ffs(peers) - 1) == lane) s[p][warp][dgt] += __popc(peers);  // one lane per digit: no two lanes share a counter
+          }
+        }
+        __syncwarp();
       }
     }
-  }
-  __syncthreads();
-  for (int p = 0; p < passes; ++p) {
-    const uint32_t c = s[p][threadIdx.x];
-    if (c) atomicAdd(hist + p * kOsRadix + threadIdx.x, c);
+    __syncthreads();
+    for (int p = 0; p < np; ++p) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) c += s[p][w][threadIdx.x];
+      if (c) atomicAdd(hist + (p0 + p) * kOsRadix + threadIdx.x, c);
+    }
+    __syncthreads();
   }
 }
 
 // One digit pass.  status: [n_tiles][256] words of this pass (zero = not yet published); ticket: this pass's tile
-// counter (zero before the launch).  ITEMS keys per thread (16 for 32-bit keys, 8 for 64-bit ones: the tile is staged in
-// shared memory).
+// counter (zero before the launch).  ITEMS keys per thread; the tile is staged in shared memory.
 template <typename KeyT, int ITEMS>
 static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
-                                                        int pass, const uint32_t* __restrict__ nbits_ptr, const uint32_t* __restrict__ hist, uint32_t* status, unsigned int* ticket) {
-  if ((uint32_t)(pass * kOsRadixBits) >= *nbits_ptr) return;
+                                                        int pass, const uint32_t* __restrict__ nbits_ptr, const uint32_t* __restrict__ hist, uint32_t* status, unsigned int* ticket, OsGather gather) {
+  const uint32_t nbits = *nbits_ptr;
+  if (gather.dst) {
+    if (*gather.disabled || (pass > 0 && (uint32_t)(pass * kOsRadixBits) >= nbits)) return;
+  } else if ((uint32_t)(pass * kOsRadixBits) >= nbits) {
+    return;
+  }
+  const bool do_gather = gather.dst != nullptr && (uint32_t)((pass + 1) * kOsRadixBits) >= nbits;  // the last pass that runs
   constexpr int WARPS = kOsThreads / 32;
   constexpr int TILE = kOsThreads * ITEMS;
   __shared__ uint32_t cnt[WARPS][kOsRadix];   // per-warp digit counts, then per-warp LOCAL bases (position inside the staged tile)
@@ -86,7 +127,7 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
   __shared__ uint32_t s_gbase[kOsRadix];      // first output slot of this tile's digit-d run
   __shared__ KeyT s_keys[TILE];
   __shared__ uint32_t s_vals[TILE];
-  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_warp[8], s_warp_t[8];
   __shared__ unsigned int s_tile;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -100,7 +141,9 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
   const bool has_vals = vals_in != nullptr;  // nullptr: a keys-only sort
   KeyT k[ITEMS];
   uint32_t v[ITEMS];
-  // ---- A: per-warp digit counts (all loads of the slice issued before the first use)
+  uint32_t wrank[(ITEMS + 1) / 2];  // rank of every key among its warp slice's keys of the same digit, two per register
+  // ---- A: per-warp digit counts and, on the way, every key's rank inside (warp slice, digit): round after round the
+  // slice's running count of the digit plus the lower lanes holding it in this round (all loads issued first)
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
@@ -111,14 +154,29 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
     const int i = wbase + r * 32 + lane;
     v[r] = (has_vals && i < n) ? vals_in[i] : 0u;
   }
+  // (the votes of all rounds first — they do not depend on each other — then the chain through the counters)
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int i = wbase + r * 32 + lane;
+    const uint32_t dgt = i < n ? os_digit(k[r], shift) : (uint32_t)kOsRadix;  // kOsRadix = "no element"
+    const uint32_t peers = os_match(dgt);
+    // lower lanes with the digit (5 bits), lanes with the digit (6 bits), elected lane (1 bit)
+    const uint32_t info = __popc(peers & ((1u << lane) - 1u)) | (__popc(peers) << 5) | (((__ffs(peers) - 1) == lane ? 1u : 0u) << 11);
+    if (r & 1) wrank[r >> 1] |= info << 16;
+    else wrank[r >> 1] = info;
+  }
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
     const bool ok = i < n;
-    const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;  // kOsRadix = "no element"
-    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
+    const uint32_t dgt = os_digit(k[r], shift);
+    const uint32_t info = (wrank[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+    const uint32_t prior = ok ? cnt[warp][dgt] : 0u;
     __syncwarp();
+    if (ok && (info >> 11)) cnt[warp][dgt] = prior + ((info >> 5) & 63u);
+    __syncwarp();
+    const uint32_t wr = prior + (info & 31u);
+    wrank[r >> 1] = (wrank[r >> 1] & ~(0xffffu << ((r & 1) * 16))) | (wr << ((r & 1) * 16));
   }
   __syncthreads();
   // ---- B: thread d owns digit d.  Tile count -> publish -> look back -> publish the inclusive prefix
@@ -169,7 +227,6 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
       const uint32_t tt = __shfl_up_sync(0xffffffffu, incl_t, o);
       if (lane >= o) { incl_g += tg; incl_t += tt; }
     }
-    __shared__ uint32_t s_warp_t[8];
     if (lane == 31) { s_warp[warp] = incl_g; s_warp_t[warp] = incl_t; }
     __syncthreads();
     uint32_t off_g = 0, off_t = 0;
@@ -188,21 +245,13 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
     }
   }
   __syncthreads();
-  // ---- C: rank of every key inside the tile (warp slices in order, rounds in order, lanes in order: stable), staged in
-  // shared memory in digit order ...
+  // ---- C: position of every key inside the tile = start of (digit, warp slice) + the rank from A (warp slices in
+  // order, rounds in order, lanes in order: stable); the tile is staged in shared memory in that order ...
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const int i = wbase + r * 32 + lane;
-    const bool ok = i < n;
-    const uint32_t dgt = ok ? os_digit(k[r], shift) : (uint32_t)kOsRadix;
-    const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t lpos = 0;
-    if (ok) lpos = cnt[warp][dgt] + rank;
-    __syncwarp();
-    if (ok && (__ffs(peers) - 1) == lane) cnt[warp][dgt] += __popc(peers);
-    __syncwarp();
-    if (ok) {
+    if (i < n) {
+      const uint32_t lpos = cnt[warp][os_digit(k[r], shift)] + ((wrank[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
       s_keys[lpos] = k[r];
       s_vals[lpos] = v[r];
     }
@@ -211,12 +260,20 @@ static __global__ void __launch_bounds__(kOsThreads) k_os_pass(const KeyT* __res
   // ... and written out from there: consecutive threads hold consecutive positions of the staged tile, i.e. (mostly) the
   // same digit and therefore consecutive output slots — the scatter of a 256-way partition as runs of coalesced stores
   // instead of 32 different sectors per store instruction
-  for (int p = tid; p < tile_n; p += kOsThreads) {
-    const KeyT key = s_keys[p];
-    const uint32_t d = os_digit(key, shift);
-    const uint32_t dst = s_gbase[d] + ((uint32_t)p - s_tstart[d]);
-    keys_out[dst] = key;
-    if (has_vals) vals_out[dst] = s_vals[p];
+#pragma unroll 4
+  for (int r = 0; r < ITEMS; ++r) {
+    const int p = r * kOsThreads + tid;
+    if (p < tile_n) {
+      const KeyT key = s_keys[p];
+      const uint32_t d = os_digit(key, shift);
+      const uint32_t dst = s_gbase[d] + ((uint32_t)p - s_tstart[d]);
+      keys_out[dst] = key;
+      if (has_vals) {
+        const uint32_t val = s_vals[p];
+        vals_out[dst] = val;
+        if (do_gather) gather.dst[dst] = __ldg(gather.src + val);
+      }
+    }
   }
 }
 
@@ -228,12 +285,13 @@ struct OneSweepScratch {
   static size_t words(int n, int max_passes, int items) { return (size_t)max_passes * (kOsRadix + 32 + (size_t)tiles(n, items) * kOsRadix); }
 };
 template <typename KeyT>
-constexpr int os_items() { return sizeof(KeyT) == 8 ? 8 : 16; }
+constexpr int os_items() { return 8; }  // 2048-key tiles: three to four CTAs per SM, more warps to cover each other's latencies than 4096-key tiles
 
 // enqueue: sorts (keys_a, vals_a)[0..n) — vals_a == nullptr: the keys alone — by the low *nbits_ptr key bits (device-resident count, <= 8 * max_passes);
 // pass p reads A when p is even, B when odd, so the result lies in B after an odd number of passes that ran.
 template <typename KeyT>
-inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const uint32_t* nbits_ptr, int max_passes) {
+inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const uint32_t* nbits_ptr, int max_passes,
+                                 OsGather gather = kNoGather) {
   if (n <= 0) return cudaSuccess;
   cudaError_t e;
   constexpr int ITEMS = os_items<KeyT>();
@@ -245,15 +303,15 @@ inline cudaError_t onesweep_sort(cudaStream_t st, OneSweepScratch& sc, KeyT* key
   unsigned int* tickets = sc.buf.p + (size_t)max_passes * kOsRadix;  // [max_passes][32] (one 128-byte line each)
   uint32_t* status = sc.buf.p + (size_t)max_passes * (kOsRadix + 32);
   int hb = (n + kOsThreads * 8 - 1) / (kOsThreads * 8);
-  if (hb > kNumSM * 2) hb = kNumSM * 2;
+  if (hb > kNumSM * 4) hb = kNumSM * 4;
   launch_counter() += 1 + max_passes;
-  k_os_histogram<KeyT><<<hb, kOsThreads, 0, st>>>(keys_a, n, nbits_ptr, max_passes, hist);
+  k_os_histogram<KeyT><<<hb, kOsThreads, 0, st>>>(keys_a, n, nbits_ptr, max_passes, hist, gather);
   for (int p = 0; p < max_passes; ++p) {
     const KeyT* ki = (p & 1) ? keys_b : keys_a;
     const uint32_t* vi = vals_a ? ((p & 1) ? vals_b : vals_a) : nullptr;
     KeyT* ko = (p & 1) ? keys_a : keys_b;
     uint32_t* vo = vals_a ? ((p & 1) ? vals_a : vals_b) : nullptr;
-    k_os_pass<KeyT, ITEMS><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32);
+    k_os_pass<KeyT, ITEMS><<<n_tiles, kOsThreads, 0, st>>>(ki, vi, ko, vo, n, p, nbits_ptr, hist, status + (size_t)p * n_tiles * kOsRadix, tickets + p * 32, gather);
   }
   return cudaGetLastError();
 }

@@ -33,6 +33,7 @@ struct CoopSortArgs {
   uint32_t *keys_a, *vals_a, *keys_b, *vals_b;
   uint32_t* hist;        // [n_tiles][256], tile-major
   uint32_t* tile_heads;  // [n_tiles][2]: run heads, valid points
+  uint32_t* seg_first;   // [n / kSegFirstTile + 1]
   uint32_t *vox_start, *vox_key, *point_key;
   int* slots;            // [gridDim][8]: min xyz, max xyz (ordered ints), any
   unsigned int* barrier; // zeroed by the host before the launch
@@ -334,6 +335,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_voxel_sort_coop(CoopSortArg
       const uint32_t is_head = (hflag >> r) & 1u;
       uint32_t row_total = 0;
       const uint32_t excl = block_excl_scan256(is_head, s_warp, &row_total);
+      // row r of the tile starts at a multiple of 256 sorted positions: the runs in front of it are k_vg_centroids' split
+      if (tid == 0 && tile * TILE + r * kSortThreads < n) a.seg_first[(tile * TILE + r * kSortThreads) / kSegFirstTile] = running;
       if (is_head) {
         const uint32_t slot = running + excl;
         a.vox_start[slot] = (uint32_t)(tile * TILE + r * kSortThreads + tid);
@@ -377,7 +380,7 @@ inline bool launch_voxel_sort_coop(VoxelSort& vs, cudaStream_t st, const float4*
   CoopSortArgs a;
   a.pts = d_pts; a.n = n; a.is_dense = is_dense; a.gate = gate; a.lx = lx; a.ly = ly; a.lz = lz;
   a.meta = vs.meta.p; a.keys_a = vs.keys_a.p; a.vals_a = vs.vals_a.p; a.keys_b = vs.keys_b.p; a.vals_b = vs.vals_b.p;
-  a.hist = vs.hist.p; a.tile_heads = vs.tile_heads.p; a.vox_start = vs.vox_start.p; a.vox_key = vs.vox_key.p;
+  a.hist = vs.hist.p; a.tile_heads = vs.tile_heads.p; a.vox_start = vs.vox_start.p; a.vox_key = vs.vox_key.p; a.seg_first = vs.seg_first.p;
   a.point_key = keep_point_keys ? vs.point_key.p : nullptr;
   a.slots = vs.mm.p; a.barrier = vs.coop_bar.p;
   void* args[] = {(void*)&a};

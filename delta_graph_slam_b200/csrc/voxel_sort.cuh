@@ -301,22 +301,57 @@ static __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint
 // sorted buffers live in A when an even number of passes ran, else in B
 __device__ __forceinline__ bool sorted_in_b(const SortMeta* meta) { return (((meta->nbits + kRadixBits - 1) / kRadixBits) & 1u) != 0; }
 
+// Segmentation tiles: kSegItems consecutive sorted positions per thread.  The second kernel adds up the head counts of
+// all earlier tiles per block — with 256-position tiles that was 3641 x 3641 / 2 loads on a 1 M-point scan and a third of
+// the kernel's stall samples (profiles/r02_ncu_voxelgrid_1m.txt); 2048-position tiles make it 455 x 455 / 2.
+constexpr int kSegFirstTile = 256;  // seg_first[t] = runs that start in front of sorted position t * kSegFirstTile (k_vg_centroids' work split)
+constexpr int kSegItems = 8;
+constexpr int kSegTile = 256 * kSegItems;
+
+// keys of this thread's kSegItems positions (kInvalid beyond n) and the key in front of the first one
+__device__ __forceinline__ void seg_load(const uint32_t* __restrict__ keys, int n, int first, uint32_t skip, uint32_t (&k)[kSegItems], uint32_t& prev, bool& has_prev) {
+  if (first + kSegItems <= n) {
+    const uint4 a = *reinterpret_cast<const uint4*>(keys + first), b = *reinterpret_cast<const uint4*>(keys + first + 4);
+    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+  } else {
+#pragma unroll
+    for (int r = 0; r < kSegItems; ++r) k[r] = first + r < n ? keys[first + r] : skip;
+  }
+  has_prev = first > 0 && first < n;
+  prev = has_prev ? keys[first - 1] : 0u;
+}
+
 // heads per tile
 static __global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, const SortMeta* __restrict__ meta,
                                                    uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_valid) {
   if (meta->grid.overflow) return;
   const uint32_t* keys = sorted_in_b(meta) ? keys_b : keys_a;
   const uint32_t skip = meta->skip_key;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int first = (blockIdx.x * 256 + threadIdx.x) * kSegItems;
+  uint32_t k[kSegItems], prev;
+  bool has_prev;
+  seg_load(keys, n, first, skip, k, prev, has_prev);
   int head = 0, valid = 0;
-  if (i < n) {
-    uint32_t k = keys[i];
-    valid = k != skip;
-    head = valid && (i == 0 || keys[i - 1] != k);
+#pragma unroll
+  for (int r = 0; r < kSegItems; ++r) {
+    const bool in = first + r < n, val = in && k[r] != skip;
+    const bool differs = r == 0 ? (!has_prev || prev != k[0]) : (k[r - 1] != k[r]);
+    valid += val;
+    head += val && differs;
   }
-  int h = __syncthreads_count(head);
-  int v = __syncthreads_count(valid);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int s_h[8], s_v[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    head += __shfl_xor_sync(0xffffffffu, head, o);
+    valid += __shfl_xor_sync(0xffffffffu, valid, o);
+  }
+  if (lane == 0) { s_h[warp] = head; s_v[warp] = valid; }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    int h = 0, v = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { h += s_h[w]; v += s_v[w]; }
     tile_heads[blockIdx.x] = (uint32_t)h;
     tile_valid[blockIdx.x] = (uint32_t)v;
   }
@@ -326,19 +361,26 @@ static __global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __rest
 // head in the sorted order; vox_start[n_vox] = n_valid closes the last run
 static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, int n, SortMeta* meta,
                                                   const uint32_t* __restrict__ tile_heads, const uint32_t* __restrict__ tile_valid, int n_tiles,
-                                                  uint32_t* __restrict__ vox_start, uint32_t* __restrict__ vox_key) {
+                                                  uint32_t* __restrict__ vox_start, uint32_t* __restrict__ vox_key, uint32_t* __restrict__ seg_first) {
   if (meta->grid.overflow) return;
   const uint32_t* keys = sorted_in_b(meta) ? keys_b : keys_a;
   const uint32_t skip = meta->skip_key;
   __shared__ uint32_t s_red[8];
   __shared__ uint32_t s_base, s_tot, s_valid;
-  // base = heads in all earlier tiles (block-wide strided sum; n_tiles is a few hundred)
+  // this thread's positions first: the loads overlap the sums over the tiles below
+  const int first = (blockIdx.x * 256 + threadIdx.x) * kSegItems;
+  uint32_t k[kSegItems], prev;
+  bool has_prev;
+  seg_load(keys, n, first, skip, k, prev, has_prev);
+  // base = heads in all earlier tiles (block-wide strided sum); block 0 also needs the totals
+  const bool totals = blockIdx.x == 0;
+  const int t_end = totals ? n_tiles : (int)blockIdx.x;
   uint32_t part = 0, tot = 0, val = 0;
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
-    uint32_t h = tile_heads[t];
+  for (int t = threadIdx.x; t < t_end; t += blockDim.x) {
+    const uint32_t h = tile_heads[t];
     if (t < (int)blockIdx.x) part += h;
     tot += h;
-    val += tile_valid[t];
+    if (totals) val += tile_valid[t];
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto block_sum = [&](uint32_t x) {
@@ -352,32 +394,43 @@ static __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restr
     for (int w = 0; w < 8; ++w) r += s_red[w];
     return r;
   };
-  uint32_t b = block_sum(part), T = block_sum(tot), V = block_sum(val);
+  uint32_t b = block_sum(part);
+  uint32_t T = 0, V = 0;
+  if (totals) { T = block_sum(tot); V = block_sum(val); }  // block-uniform branch
   if (threadIdx.x == 0) { s_base = b; s_tot = T; s_valid = V; }
-  __syncthreads();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int head = 0;
-  uint32_t k = 0;
-  if (i < n) {
-    k = keys[i];
-    head = (k != skip) && (i == 0 || keys[i - 1] != k);
+  uint32_t heads = 0;  // bit r: position first + r opens a run
+#pragma unroll
+  for (int r = 0; r < kSegItems; ++r) {
+    const bool val_r = first + r < n && k[r] != skip;
+    const bool differs = r == 0 ? (!has_prev || prev != k[0]) : (k[r - 1] != k[r]);
+    if (val_r && differs) heads |= 1u << r;
   }
-  // in-block exclusive scan of the head flags
-  uint32_t bal = __ballot_sync(0xffffffffu, head);
-  uint32_t wpre = __popc(bal & ((1u << lane) - 1u));
+  // in-block exclusive scan of the per-thread head counts
+  const uint32_t mine = __popc(heads);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
   __syncthreads();
-  if (lane == 0) s_red[warp] = __popc(bal);
+  if (lane == 31) s_red[warp] = incl;
   __syncthreads();
   uint32_t woff = 0;
 #pragma unroll
   for (int w = 0; w < 8; ++w)
     if (w < warp) woff += s_red[w];
-  if (head) {
-    uint32_t slot = s_base + woff + wpre;
-    vox_start[slot] = (uint32_t)i;
-    vox_key[slot] = k;
+  uint32_t slot = s_base + woff + incl - mine;
+  if (first < n && first % kSegFirstTile == 0) seg_first[first / kSegFirstTile] = slot;
+#pragma unroll
+  for (int r = 0; r < kSegItems; ++r) {
+    if (heads & (1u << r)) {
+      vox_start[slot] = (uint32_t)(first + r);
+      vox_key[slot] = k[r];
+      ++slot;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (totals && threadIdx.x == 0) {
     meta->n_vox = s_tot;
     meta->n_valid = s_valid;
     vox_start[s_tot] = s_valid;
@@ -398,7 +451,7 @@ inline int& sort_path_override() {
 }
 
 struct VoxelSort {
-  DevBuf<uint32_t> keys_a, keys_b, vals_a, vals_b, hist, tile_heads, tile_valid, vox_start, vox_key, point_key;
+  DevBuf<uint32_t> keys_a, keys_b, vals_a, vals_b, hist, tile_heads, tile_valid, vox_start, vox_key, point_key, seg_first;
   DevBuf<int> mm;
   DevBuf<unsigned int> coop_bar;
   DevBuf<SortMeta> meta;
@@ -408,12 +461,16 @@ struct VoxelSort {
 
   void release() {
     keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); hist.release(); tile_heads.release(); tile_valid.release();
-    vox_start.release(); vox_key.release(); point_key.release(); mm.release(); meta.release(); coop_bar.release(); onesweep.buf.release();
+    vox_start.release(); vox_key.release(); point_key.release(); seg_first.release(); mm.release(); meta.release(); coop_bar.release(); onesweep.buf.release();
   }
 
   // enqueue: keys -> sort -> segmentation.  Afterwards (on the stream):
   //   meta->grid / n_vox / n_valid, sorted (key, point index) in A or B (sorted_in_b), vox_start[0..n_vox], vox_key[0..n_vox)
-  cudaError_t run(cudaStream_t st, const float4* d_pts, int n_points, int is_dense, float lx, float ly, float lz, bool keep_point_keys, PointGate gate = kNoGate) {
+  // gather_dst (optional): the points in sorted order, written by the one-sweep sort's last pass; *gathered tells the
+  // caller whether that happened (the other sort paths leave it to a k_vg_gather launch)
+  cudaError_t run(cudaStream_t st, const float4* d_pts, int n_points, int is_dense, float lx, float ly, float lz, bool keep_point_keys, PointGate gate = kNoGate,
+                  float4* gather_dst = nullptr, bool* gathered = nullptr) {
+    if (gathered) *gathered = false;
     n = n_points;
     cudaError_t e;
     size_t nn = (size_t)(n > 0 ? n : 1);
@@ -423,6 +480,7 @@ struct VoxelSort {
     if ((e = vals_b.reserve(nn)) != cudaSuccess) return e;
     if ((e = vox_start.reserve(nn + 1)) != cudaSuccess) return e;
     if ((e = vox_key.reserve(nn)) != cudaSuccess) return e;
+    if ((e = seg_first.reserve(nn / kSegFirstTile + 2)) != cudaSuccess) return e;
     if ((e = mm.reserve(8)) != cudaSuccess) return e;
     if ((e = meta.reserve(1)) != cudaSuccess) return e;
     if (keep_point_keys && (e = point_key.reserve(nn)) != cudaSuccess) return e;
@@ -436,7 +494,7 @@ struct VoxelSort {
     while (items < 32 && (n + kSortThreads * items - 1) / (kSortThreads * items) > 256) items *= 2;
     const int tile = kSortThreads * items;
     const int n_tiles = n > 0 ? (n + tile - 1) / tile : 1;
-    const int n_seg_tiles = n > 0 ? (n + 255) / 256 : 1;
+    const int n_seg_tiles = n > 0 ? (n + kSegTile - 1) / kSegTile : 1;
     if (!one_sweep && n_tiles > 256) return cudaErrorInvalidValue;  // the one-block histogram scan holds 65536 counters
     if ((e = hist.reserve((size_t)n_tiles * kRadix)) != cudaSuccess) return e;
     if ((e = tile_heads.reserve(n_seg_tiles)) != cudaSuccess) return e;
@@ -452,7 +510,9 @@ struct VoxelSort {
     k_grid_keys<<<blocks, kSortThreads, 0, st>>>(d_pts, n, is_dense, gate, lx, ly, lz, mm.p, meta.p, keys_a.p, vals_a.p, keep_point_keys ? point_key.p : nullptr);
     if (n > 0 && one_sweep) {
       // one read of the keys for all digit histograms, then one launch per digit with chained tile prefixes
-      if ((e = onesweep_sort<uint32_t>(st, onesweep, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n, &meta.p->nbits, 4)) != cudaSuccess) return e;
+      const OsGather g = {d_pts, gather_dst, &meta.p->grid.overflow};
+      if ((e = onesweep_sort<uint32_t>(st, onesweep, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n, &meta.p->nbits, 4, gather_dst ? g : kNoGather)) != cudaSuccess) return e;
+      if (gathered && gather_dst) *gathered = true;
     } else if (n > 0) {
       for (int pass = 0; pass < 4; ++pass) {
         const uint32_t* ki = (pass & 1) ? keys_b.p : keys_a.p;
@@ -475,7 +535,7 @@ struct VoxelSort {
       }
     }
     k_seg_count<<<n_seg_tiles, 256, 0, st>>>(keys_a.p, keys_b.p, n, meta.p, tile_heads.p, tile_valid.p);
-    k_seg_scan<<<n_seg_tiles, 256, 0, st>>>(keys_a.p, keys_b.p, n, meta.p, tile_heads.p, tile_valid.p, n_seg_tiles, vox_start.p, vox_key.p);
+    k_seg_scan<<<n_seg_tiles, 256, 0, st>>>(keys_a.p, keys_b.p, n, meta.p, tile_heads.p, tile_valid.p, n_seg_tiles, vox_start.p, vox_key.p, seg_first.p);
     return cudaGetLastError();
   }
 };

@@ -16,6 +16,8 @@ struct VgCounts {  // device-resident summary of the last filter call
 // populated — the densest voxel of a scan (tens of points at 0.1 m next to the sensor) set the kernel's duration
 // (63 us of a 190 us filter call on a 1 M-point scan, 26 of 81 us on an HDL-64 scan: the largest single kernel of the filter).
 // Here every gather is its own thread; the centroid pass then reads consecutive 16-byte records.
+constexpr int kVgChunk = kSegFirstTile;  // sorted positions per warp of k_vg_centroids (and records it stages in shared memory at a time)
+
 __global__ void __launch_bounds__(256) k_vg_gather(const float4* __restrict__ pts, int n, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
                                                    const SortMeta* __restrict__ meta, float4* __restrict__ sorted_pts) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(256) k_vg_gather(const float4* __restrict__ pt
 // sort's in-voxel order), divided by float(count) — A.1 step 7.  sorted_pts (optional): the points already gathered
 // into sorted order by k_vg_gather.
 __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__ pts, int n, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
-                                                      const float4* __restrict__ sorted_pts,
+                                                      const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ seg_first,
                                                       const SortMeta* __restrict__ meta, const uint32_t* __restrict__ vox_start, const uint32_t* __restrict__ vox_key,
                                                       unsigned min_points, float4* __restrict__ out, uint32_t* __restrict__ out_id, uint32_t* __restrict__ out_count,
                                                       VgCounts* __restrict__ counts, VgCounts* host_counts, unsigned int* host_flag, unsigned int host_seq,
@@ -48,35 +50,79 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const float4* __restrict__
       out[i] = p;
       if (host_out && (unsigned)i < host_cap) host_out[i] = p;
     }
-  } else if (i < n_vox) {
+  } else {
+    // One warp per kVgChunk sorted positions: it owns the runs that START there (seg_first = number of runs in front of
+    // the tile, from the segmentation) and follows the last one past the tile's end.  A warp's work is bounded by the
+    // tile plus one run, however the points crowd into the voxels next to the sensor — one thread per voxel walking its
+    // run through global memory made the densest voxel the kernel's duration (63 us of a 190 us call on a 1 M-point scan).
+    // The tile's records are loaded (eight coalesced 16-byte loads per lane) without waiting for the run table; every
+    // lane then adds up its runs from shared memory — one serial float sum per voxel in input order, so the bits stay.
     const uint32_t* vals = sorted_in_b(meta) ? vals_b : vals_a;
-    const uint32_t s = vox_start[i], e = vox_start[i + 1];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    if (sorted_pts) {
-      // consecutive records; four loads in flight in front of the (serial, input-order) float sums
-      uint32_t j = s;
-      for (; j + 4 <= e; j += 4) {
-        const float4 p0 = __ldg(sorted_pts + j), p1 = __ldg(sorted_pts + j + 1), p2 = __ldg(sorted_pts + j + 2), p3 = __ldg(sorted_pts + j + 3);
-        ax = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ax, p0.x), p1.x), p2.x), p3.x);
-        ay = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ay, p0.y), p1.y), p2.y), p3.y);
-        az = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(az, p0.z), p1.z), p2.z), p3.z);
-      }
-      for (; j < e; ++j) {
-        const float4 p = __ldg(sorted_pts + j);
-        ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
-      }
-    } else {
-      for (uint32_t j = s; j < e; ++j) {
-        const float4 p = __ldg(pts + vals[j]);
-        ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = (uint32_t)i >> 5, p0 = tile * (uint32_t)kVgChunk, n_valid = meta->n_valid;
+    if (p0 < n_valid) {  // warp-uniform
+      __shared__ float s_x[8][kVgChunk], s_y[8][kVgChunk], s_z[8][kVgChunk];
+      auto stage = [&](uint32_t c0) {  // records [c0, c0 + kVgChunk) -> shared memory
+        float4 p[kVgChunk / 32];
+#pragma unroll
+        for (int u = 0; u < kVgChunk / 32; ++u) {
+          const uint32_t j = c0 + u * 32 + lane;
+          if (sorted_pts) p[u] = j < n_valid ? __ldg(sorted_pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          else p[u] = j < n_valid ? __ldg(pts + vals[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kVgChunk / 32; ++u) {
+          s_x[warp][u * 32 + lane] = p[u].x;
+          s_y[warp][u * 32 + lane] = p[u].y;
+          s_z[warp][u * 32 + lane] = p[u].z;
+        }
+        __syncwarp();
+      };
+      const uint32_t v0 = seg_first[tile];
+      const uint32_t v1 = p0 + (uint32_t)kVgChunk < (uint32_t)n ? seg_first[tile + 1] : (uint32_t)n_vox;
+      uint32_t s = 0, e = 0;
+      if (v0 + lane < v1) { s = vox_start[v0 + lane]; e = vox_start[v0 + lane + 1]; }
+      stage(p0);
+      const uint32_t tile_end = p0 + (uint32_t)kVgChunk;
+      for (uint32_t vb = v0; vb < v1; vb += 32) {
+        const uint32_t v = vb + lane;
+        const bool mine = v < v1;
+        uint32_t s_next = 0, e_next = 0;  // the next batch's run bounds travel while this batch is summed
+        if (v + 32 < v1) { s_next = vox_start[v + 32]; e_next = vox_start[v + 33]; }
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const uint32_t hi = min(e, tile_end);
+        for (uint32_t j = s; j < hi; ++j) {
+          ax = __fadd_rn(ax, s_x[warp][j - p0]);
+          ay = __fadd_rn(ay, s_y[warp][j - p0]);
+          az = __fadd_rn(az, s_z[warp][j - p0]);
+        }
+        // the tile's last run may go on past its end (only the last lane of the last batch): the warp streams the rest
+        const uint32_t tail = __reduce_max_sync(0xffffffffu, mine ? e : 0u);
+        if (tail > tile_end) {  // warp-uniform
+          __syncwarp();
+          for (uint32_t c0 = tile_end; c0 < tail; c0 += kVgChunk) {
+            stage(c0);
+            const uint32_t lo = max(max(s, c0), tile_end), h2 = min(e, c0 + (uint32_t)kVgChunk);
+            for (uint32_t j = lo; j < h2; ++j) {
+              ax = __fadd_rn(ax, s_x[warp][j - c0]);
+              ay = __fadd_rn(ay, s_y[warp][j - c0]);
+              az = __fadd_rn(az, s_z[warp][j - c0]);
+            }
+            __syncwarp();
+          }
+        }
+        if (mine) {
+          const float cnt = (float)(e - s);
+          const float4 c = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
+          out[v] = c;
+          if (host_out && v < host_cap) host_out[v] = c;
+          if (out_id) out_id[v] = vox_key[v];
+          if (out_count) out_count[v] = e - s;
+        }
+        s = s_next;
+        e = e_next;
       }
     }
-    const float cnt = (float)(e - s);
-    const float4 c = make_float4(__fdiv_rn(ax, cnt), __fdiv_rn(ay, cnt), __fdiv_rn(az, cnt), 1.0f);
-    out[i] = c;
-    if (host_out && (unsigned)i < host_cap) host_out[i] = c;
-    if (out_id) out_id[i] = vox_key[i];
-    if (out_count) out_count[i] = e - s;
   }
   // The point count goes to the device summary and, for the caller waiting on the host, straight into
   // mapped page-locked memory followed by a sequence flag.  The LAST block to finish publishes it:

@@ -98,6 +98,10 @@ class MultiGpuBatch:
 
     def __init__(self, devices, params=None):
         import ctypes as C
+        # one NCCL per process: torch (device plumbing of this package) links its bundled libnccl.so.2; imported first,
+        # the library's dlopen("libnccl.so.2") gets that same object.  The other order would put the system NCCL under
+        # torch's soname and a later `import torch` would fail on its missing symbols.
+        import torch  # noqa: F401
         p = dict(params or {})
         L = _lib.load()
         cfg = _lib.Config()

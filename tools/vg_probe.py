@@ -14,14 +14,18 @@ from delta_graph_slam_b200 import _lib, synth  # noqa: E402
 
 L = _lib.load()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+paths = [int(c) for c in sys.argv[2]] if len(sys.argv) > 2 else [0, 3, 2, 1]     # e.g. "2": the onesweep path only
+sensors = sys.argv[3].split(",") if len(sys.argv) > 3 else ["dense128", "hdl64"]
 out = {}
 for name, sensor in (("dense128", synth.DENSE128), ("hdl64", synth.HDL64)):
+    if name not in sensors:
+        continue
     rays = synth.num_rays(sensor)
     d_raw = torch.empty((rays, 4), dtype=torch.float32, device="cuda:0")
     d_out = torch.empty((rays, 4), dtype=torch.float32, device="cuda:0")
     n = synth.scan_to_device(d_raw.data_ptr(), synth.traj_kitti_like(3), sensor, scene_seed=1, noise_seed=77, device=0)
     ref = None
-    for path in (0, 3, 2, 1):
+    for path in paths:
         L.b200reg_set_sort_path(path)
         vg = eng.VoxelGrid()
         vg.setLeafSize(0.1, 0.1, 0.1)
