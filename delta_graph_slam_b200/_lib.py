@@ -31,7 +31,7 @@ EXPORTS = [
     "b200reg_odometry_default_config", "b200reg_odometry_create", "b200reg_odometry_destroy", "b200reg_odometry_last_error", "b200reg_odometry_reset", "b200reg_odometry_matching",
     "b200reg_odometry_matching_device", "b200reg_odometry_get_state",
     "b200reg_frontend_default_config", "b200reg_frontend_create", "b200reg_frontend_destroy", "b200reg_frontend_last_error", "b200reg_frontend_reset", "b200reg_frontend_registration",
-    "b200reg_frontend_filter", "b200reg_frontend_odometry", "b200reg_frontend_begin", "b200reg_frontend_begin_device", "b200reg_frontend_step", "b200reg_frontend_step_device", "b200reg_frontend_run_device", "b200reg_frontend_get_timing", "b200reg_set_sm_budget", "b200reg_set_distance_filter", "b200reg_distance_filter", "b200reg_distance_filter_device",
+    "b200reg_frontend_filter", "b200reg_frontend_odometry", "b200reg_frontend_begin", "b200reg_frontend_begin_device", "b200reg_frontend_step", "b200reg_frontend_step_device", "b200reg_frontend_run_device", "b200reg_frontend_get_timing", "b200reg_set_sm_budget", "b200reg_set_distance_filter", "b200reg_set_input_transform", "b200reg_distance_filter", "b200reg_distance_filter_device",
     "b200reg_radius_outlier_removal", "b200reg_radius_outlier_removal_device", "b200reg_radius_outlier_removal_begin", "b200reg_radius_outlier_removal_device_begin",
     "b200reg_radius_outlier_removal_end",
     "b200reg_statistical_outlier_removal", "b200reg_statistical_outlier_removal_device", "b200reg_statistical_outlier_removal_begin", "b200reg_statistical_outlier_removal_device_begin",
@@ -161,6 +161,7 @@ def load():
     L.b200reg_frontend_run_device.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, C.POINTER(C.c_int)]
     L.b200reg_set_sm_budget.argtypes = [vp, C.c_int]
     L.b200reg_set_distance_filter.argtypes = [vp, C.c_int, C.c_double, C.c_double]
+    L.b200reg_set_input_transform.argtypes = [vp, C.POINTER(C.c_double)]
     L.b200reg_distance_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, vp, C.c_size_t, szp]
     L.b200reg_distance_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_double, C.c_double, vp, szp]
     L.b200reg_radius_outlier_removal.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_int, vp, C.c_size_t, szp]

@@ -37,6 +37,8 @@ struct HostMailbox {
   volatile unsigned int ror_seq;
 };
 
+struct InputXf { double m[12]; };  // rows 0..2 of the base_link matrix, row-major (k_input_transform)
+
 struct b200reg_handle {
   b200reg_config cfg;
   cudaStream_t stream = nullptr;
@@ -55,6 +57,9 @@ struct b200reg_handle {
   VoxelSort vg_sort;
   DevBuf<uint32_t> vg_id, vg_count;
   DevBuf<float4> vg_sorted;  // the scan's points in sorted (voxel, input) order: k_vg_gather -> k_vg_centroids
+  DevBuf<float4> in_xf_buf;  // the scan in the base_link frame (b200reg_set_input_transform)
+  bool in_xf_on = false;
+  InputXf in_xf{};
   DevBuf<VgCounts> vg_counts;
   DevBuf<unsigned int> vg_done;
   int vg_last_n = 0, vg_last_out = 0;
@@ -255,6 +260,25 @@ void euler_xyz_from_colmajor(const float* T, float out[3]) {
   out[0] = -r0; out[1] = -r1; out[2] = -r2;
 }
 
+// pcl::transformPointCloud(in, out, Matrix4d) as PrefilteringNodelet::cloud_callback calls it for the base_link frame
+// [REF apps/prefiltering_nodelet.cpp:137-147]: per point, in double, left to right
+//   out.x = float(m00 * x + m01 * y + m02 * z + m03)   (pcl/common/impl/transforms.hpp, Scalar = double)
+// and w = 1; a cloud that is not dense keeps its non-finite points as they are.  m: rows 0..2 of the matrix, row-major.
+__global__ void __launch_bounds__(256) k_input_transform(const float4* __restrict__ in, int n, InputXf xf, int is_dense, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  float4 q = p;
+  if (is_dense || finite3(p.x, p.y, p.z)) {
+    const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+    q.x = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xf.m[0], x), __dmul_rn(xf.m[1], y)), __dmul_rn(xf.m[2], z)), xf.m[3]);
+    q.y = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xf.m[4], x), __dmul_rn(xf.m[5], y)), __dmul_rn(xf.m[6], z)), xf.m[7]);
+    q.z = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xf.m[8], x), __dmul_rn(xf.m[9], y)), __dmul_rn(xf.m[10], z)), xf.m[11]);
+    q.w = 1.0f;
+  }
+  out[i] = q;
+}
+
 __global__ void k_transform_cloud(const float4* __restrict__ in, int n, const b200reg_result* __restrict__ res, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -320,7 +344,7 @@ cudaError_t init_kernel_attributes(int device) {
   B200_ATTR(prefer_shared(k_ndt_align<1, true>)); B200_ATTR(prefer_shared(k_ndt_align<7, true>)); B200_ATTR(prefer_shared(k_ndt_align<27, true>)); B200_ATTR(prefer_shared(k_ndt_align<0, true>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<2>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<4>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<8>));
   B200_ATTR(prefer_shared(k_voxel_sort_coop<16>)); B200_ATTR(prefer_shared(k_voxel_sort_coop<32>));
-  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared((k_os_pass<unsigned long long, 8>))); B200_ATTR(prefer_shared((k_os_pass<uint32_t, 8>))); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_gather)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud));
+  B200_ATTR(prefer_shared(k_os_histogram<uint32_t>)); B200_ATTR(prefer_shared(k_os_histogram<unsigned long long>)); B200_ATTR(prefer_shared((k_os_pass<unsigned long long, 8>))); B200_ATTR(prefer_shared((k_os_pass<uint32_t, 8>))); B200_ATTR(prefer_shared(k_vg_centroids)); B200_ATTR(prefer_shared(k_vg_gather)); B200_ATTR(prefer_shared(k_vg_compact)); B200_ATTR(prefer_shared(k_gate_copy)); B200_ATTR(prefer_shared(k_ror_flags)); B200_ATTR(prefer_shared(k_ror_scatter)); B200_ATTR(prefer_shared(k_nn_occ_clear)); B200_ATTR(prefer_shared(k_transform_cloud)); B200_ATTR(prefer_shared(k_input_transform));
   B200_ATTR(prefer_shared(k_nn_reorder)); B200_ATTR(prefer_shared(k_nn_insert)); B200_ATTR(prefer_shared(k_nn_search)); B200_ATTR(prefer_shared(k_nn_far));
   B200_ATTR(prefer_shared(k_nn_bruteforce)); B200_ATTR(prefer_shared(k_fitness_partial));
   B200_ATTR(prefer_shared(k_nn_search_batch)); B200_ATTR(prefer_shared(k_nn_far_batch)); B200_ATTR(prefer_shared(k_nn_bruteforce_batch)); B200_ATTR(prefer_shared(k_fitness_batch));
@@ -687,7 +711,7 @@ int b200reg_destroy(b200reg_handle* h) {
   for (auto& pr : h->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (h->mail) cudaFreeHost((void*)h->mail);
   h->src.release(); h->tgt.release(); h->stage_in.release(); h->stage_out.release(); h->aligned.release();
-  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_sorted.release(); h->vg_counts.release(); h->vg_done.release();
+  h->pin_in.release(); h->pin_out.release(); h->vg_sort.release(); h->vg_id.release(); h->vg_count.release(); h->vg_sorted.release(); h->in_xf_buf.release(); h->vg_counts.release(); h->vg_done.release();
   h->grid.release(); h->jobs.release(); h->d_result.release(); h->partials.release(); h->deriv.release(); h->barriers.release(); h->pin_small.release(); h->prof.release(); h->trace.release();
   h->nn.release(); h->fit_partials.release();
   h->nn_src.release(); h->cov_src.release(); h->cov_tgt.release(); h->gicp_mahal.release(); h->nn_ror.release(); h->ror_in.release(); h->ror_out.release(); h->ror_pin_in.release(); h->ror_pin_out.release(); h->ror_keep.release(); h->ror_block_count.release(); h->ror_counts.release(); h->ror_done.release(); h->sor_dist.release(); h->sor_stats.release(); h->sor_pending.release(); h->sor_n_pending.release();
@@ -1024,6 +1048,12 @@ static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float l
   B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
   B200_CUDA_TRY(h->vg_counts.reserve(1));
   B200_CUDA_TRY(h->vg_sorted.reserve(n ? n : 1));
+  if (h->in_xf_on && n) {  // base_link frame first, as cloud_callback does [REF apps/prefiltering_nodelet.cpp:123-148]
+    B200_CUDA_TRY(h->in_xf_buf.reserve(n));
+    launch_counter() += 1;
+    k_input_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_in, (int)n, h->in_xf, dense, h->in_xf_buf.p);
+    d_in = h->in_xf_buf.p;
+  }
   bool gathered = false;  // the one-sweep sort's last pass writes the points in sorted order itself
   B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate, h->vg_sorted.p, &gathered));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
@@ -1194,6 +1224,15 @@ int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, 
   return B200REG_OK;
 }
 
+int b200reg_set_input_transform(b200reg_handle* h, const double* matrix4x4_colmajor) {
+  if (!h) return B200REG_E_INVALID;
+  h->in_xf_on = matrix4x4_colmajor != nullptr;
+  if (matrix4x4_colmajor)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) h->in_xf.m[4 * r + c] = matrix4x4_colmajor[4 * c + r];
+  return B200REG_OK;
+}
+
 // ---- RadiusOutlierRemoval ----------------------------------------------------------------------
 // which outlier filter a call runs: pcl::RadiusOutlierRemoval or pcl::StatisticalOutlierRemoval
 struct OutlierSpec {
@@ -1223,6 +1262,12 @@ static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const Outlie
   const int min_neighbors = spec.min_neighbors;
   PointGate gate = kNoGate;
   if (spec.flat) { gate.on = 2; gate.near_thresh = spec.lidar_z; }  // height_filtering as a gate of the lattice build: no intermediate cloud
+  if (spec.gate_only && h->in_xf_on && n) {  // distance_filter is the first stage of a prefilter without a down-sampler: base_link frame first
+    B200_CUDA_TRY(h->in_xf_buf.reserve(n));
+    launch_counter() += 1;
+    k_input_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_in, (int)n, h->in_xf, /*is_dense=*/0, h->in_xf_buf.p);
+    d_in = h->in_xf_buf.p;
+  }
   if (!spec.gate_only) B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0, gate));
   const int blocks = n ? (int)((n + 255) / 256) : 1;
   B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));

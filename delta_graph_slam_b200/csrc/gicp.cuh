@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(128) k_gicp_regularize(int n, int reg_method, 
 // ---- the alignment kernel -------------------------------------------------------------------------
 constexpr int kGicpThreads = 512;
 constexpr int kGicpWarps = kGicpThreads / 32;
+constexpr int kGicpQueryLanes = 4;  // lanes that share one source point's near search in a linearize pass
 constexpr int kGicpAcc = 29;  // H upper triangle [21], b [6], sum of errors, correspondences
 constexpr int kGicpStride = 32;
 
@@ -838,7 +839,6 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     // and, after a block barrier, dealt round-robin to the CTA's 16 warps for the cooperative far
     // search — so a warp that happened to draw several far points does not hold up the pass.
     const int stride = G * kGicpWarps;  // 32-point groups per sweep of the whole grid
-    const int n_groups32 = (n_src + 31) >> 5;
     auto finish_point = [&](int i, const float4 p, float best, int best_idx) {
       int c = -1;
       if (best_idx != kNoIndex && (double)best < prm.corr_dist2) c = best_idx;
@@ -858,10 +858,16 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     // 32-point groups are dealt round-robin over the warps of all CTAs (like the NDT pass): source
     // points without a correspondence come in spatial clumps, and their far searches would otherwise
     // all land in a few CTAs while the rest of the grid waits at the group barrier
-    for (int q0 = 0; q0 < n_groups32; q0 += stride) {
+    // linearize: kGicpQueryLanes lanes share a query in the near phase (nn_query_near_group), so a warp takes 32 /
+    // kGicpQueryLanes points; the error passes keep a point per lane.  Either way every point is visited once.
+    const int per_warp = phase == GP_LINEARIZE ? 32 / kGicpQueryLanes : 32;
+    const int n_groups = (n_src + per_warp - 1) / per_warp;
+    const int sub = lane % kGicpQueryLanes;
+    const bool leader = phase != GP_LINEARIZE || sub == 0;
+    for (int q0 = 0; q0 < n_groups; q0 += stride) {
       const int qg = q0 + warp * G + rank;
-      const int i = (qg << 5) + lane;
-      const bool active = qg < n_groups32 && i < n_src;
+      const int i = qg * per_warp + (phase == GP_LINEARIZE ? lane / kGicpQueryLanes : lane);
+      const bool active = qg < n_groups && i < n_src;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) p = __ldg(job.src + i);
       if (phase == GP_LINEARIZE) {
@@ -883,13 +889,13 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
             best_idx = cp;
           }
         }
-        if (active && grid_ok) st = nn_query_near<4, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
+        st = nn_query_near_group<kGicpQueryLanes, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, sub, active && grid_ok, best, best_idx);
         const bool ok = st == kNnDone;
         // queue slots in thread order (ballot compaction): the far points are always dealt to the same
         // warps, so the summation order — and with it the result — is reproducible bit for bit
-        const unsigned open = __ballot_sync(0xffffffffu, active && !ok);
+        const unsigned open = __ballot_sync(0xffffffffu, active && !ok && leader);
         if (lane == 0) s_wq[warp] = __popc(open);
-        if (active && ok) finish_point(i, p, best, best_idx);
+        if (active && ok && leader) finish_point(i, p, best, best_idx);
         __syncthreads();
         if (PROF) tp_near = clock64();
         int qbase = 0, nq = 0;
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
           nq += c;
         }
         if (PROF) pf[9] += nq;
-        if (active && !ok) {
+        if (active && !ok && leader) {
           const int slot = qbase + __popc(open & ((1u << lane) - 1u));
           s_q[slot] = make_float4(qx, qy, qz, __int_as_float(i | (st == kNnBail ? (int)kBailFlag : 0)));
           s_qb[slot] = make_float2(best, __int_as_float(best_idx));

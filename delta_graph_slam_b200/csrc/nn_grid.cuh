@@ -244,6 +244,64 @@ __device__ __forceinline__ int nn_query_near(const NnView& g, const GridParams& 
   return nn_settled(gp, q, kNearRing + 1, best, max_d2) ? kNnDone : kNnOpen;
 }
 
+// The near phase for ONE query by a group of LANES adjacent lanes (2, 4 or 8; all 32 lanes of the warp call it, `sub` =
+// lane % LANES, `active` false for a group without a query).  A thread-per-query walk of rings 0..1 is a chain of
+// dependent L2 round trips — hash slot, then the cell's points, cell after cell — and a pass of k_gicp_align over a
+// 15 k-point scan gives each thread of the grid at most ONE query: the pass lasted as long as that chain while four
+// fifths of the warps had nothing to do.  Here the group scans the query's own cell LANES points at a time and deals the
+// 26 neighbours over its lanes; candidates are compared as (distance bits, index) keys, whose minimum does not depend on
+// the order of the scan, so the result is nn_query_near's exact neighbour (same tie rule).  Group-uniform on return.
+template <int LANES, bool SEEDED = false>
+__device__ __forceinline__ int nn_query_near_group(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, int sub, bool active, float& best, int& best_idx) {
+  static_assert(kNearRing == 1, "rings 0 and 1 are written out");
+  if (!SEEDED) {
+    best = 3.402823466e+38f;
+    best_idx = kNoIndex;
+  }
+  unsigned long long bk = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(unsigned)best_idx;
+  auto merge = [&]() {
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, bk, o);
+      bk = other < bk ? other : bk;
+    }
+    best = __uint_as_float((unsigned)(bk >> 32));
+    best_idx = (int)(unsigned)(bk & 0xffffffffull);
+  };
+  auto inside = [&](int ix, int iy, int iz) { return ix >= gp.min_b[0] && ix <= gp.max_b[0] && iy >= gp.min_b[1] && iy <= gp.max_b[1] && iz >= gp.min_b[2] && iz <= gp.max_b[2]; };
+  auto offer = [&](uint32_t j) {
+    const float4 p = __ldg(g.pts + j);
+    const float d = l2_simple(q.qx, q.qy, q.qz, p.x, p.y, p.z);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)__float_as_uint(p.w);
+    bk = k < bk ? k : bk;
+  };
+  // ring 0: the query's own cell, LANES points at a time
+  if (active && inside(q.cx, q.cy, q.cz) && !(nn_box_d2(gp, q, q.cx, q.cy, q.cz) > fminf(best, max_d2))) {
+    const uint32_t key = (uint32_t)((q.cx - gp.min_b[0]) * gp.mul[0] + (q.cy - gp.min_b[1]) * gp.mul[1] + (q.cz - gp.min_b[2]) * gp.mul[2]);
+    const uint2 run = nn_lookup(g, key);
+#pragma unroll 2
+    for (uint32_t j = run.x + (uint32_t)sub; j < run.y; j += LANES) offer(j);
+  }
+  merge();
+  const bool done = !active || nn_settled(gp, q, 1, best, max_d2);
+  // ring 1: the 26 neighbours dealt over the lanes, each pruned against what the lane knows so far
+  if (!done) {
+    for (int c = sub; c < 27; c += LANES) {
+      if (c == 13) continue;
+      const int ix = q.cx + c % 3 - 1, iy = q.cy + (c / 3) % 3 - 1, iz = q.cz + c / 9 - 1;
+      if (!inside(ix, iy, iz)) continue;
+      if (nn_box_d2(gp, q, ix, iy, iz) > fminf(__uint_as_float((unsigned)(bk >> 32)), max_d2)) continue;
+      const uint32_t key = (uint32_t)((ix - gp.min_b[0]) * gp.mul[0] + (iy - gp.min_b[1]) * gp.mul[1] + (iz - gp.min_b[2]) * gp.mul[2]);
+      const uint2 run = nn_lookup(g, key);
+#pragma unroll 4
+      for (uint32_t j = run.x; j < run.y; ++j) offer(j);
+    }
+  }
+  merge();
+  if (done) return kNnDone;
+  return nn_settled(gp, q, kNearRing + 1, best, max_d2) ? kNnDone : kNnOpen;
+}
+
 __device__ __forceinline__ void nn_warp_merge(float& best, int& best_idx) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -90,6 +90,28 @@ class Prefilter:
                 from .registration import Registration
                 self._reg = Registration(device=device)  # a filter-only handle for the stand-alone gate
 
+    def setBaseLinkTransform(self, transform):
+        """The base_link step of cloud_callback [REF apps/prefiltering_nodelet.cpp:123-148].  `transform`: the 4x4
+        sensor -> base_link transform the nodelet looks up from tf when `base_link_frame` is set (None: parameter empty,
+        the reference's default — scans stay in the sensor frame).  As upstream the x / y translation is zeroed ("lidar
+        scans should be centered in base_link"), the remaining translation is the lidar position handed to the height
+        filter, and the cloud is transformed with the Matrix4d (double arithmetic, one rounding to float) in front of
+        distance_filter — on the device, by the handle of the chain's first stage.  Returns the lidar position."""
+        first = self.filter._reg if self.filter is not None else (self._reg if self.distance_filter_on else None)
+        if transform is None:
+            if first is not None:
+                first.setInputTransform(None)
+            self.lidar_position = np.zeros(3)
+            return self.lidar_position
+        if first is None:
+            raise ValueError("base_link transform: this chain has neither a VoxelGrid nor the distance gate to attach it to (b200_skip_distance_filter with downsample_method NONE)")
+        m = np.array(transform, np.float64).reshape(4, 4)
+        m[0, 3] = 0.0
+        m[1, 3] = 0.0
+        self.lidar_position = m[:3, 3].copy()
+        first.setInputTransform(m)
+        return self.lidar_position
+
     def setSmBudget(self, n_sm):
         if self.filter is not None:
             self.filter.setSmBudget(n_sm)

@@ -324,6 +324,15 @@ class Registration:
         """distance_filter of the prefiltering nodelet fused into this handle's VoxelGrid calls (b200reg_set_distance_filter)."""
         self._ck(_lib.load().b200reg_set_distance_filter(self._h, int(bool(use)), float(near_thresh), float(far_thresh)))
 
+    def setInputTransform(self, matrix4x4):
+        """pcl::transformPointCloud(src, transformed, Matrix4d) in front of this handle's VoxelGrid / distance_filter calls
+        (b200reg_set_input_transform) [REF apps/prefiltering_nodelet.cpp:137-147]; None switches it off."""
+        if matrix4x4 is None:
+            self._ck(_lib.load().b200reg_set_input_transform(self._h, None))
+            return
+        m = np.ascontiguousarray(np.asarray(matrix4x4, np.float64).reshape(4, 4).T)  # column-major, as Eigen stores it
+        self._ck(_lib.load().b200reg_set_input_transform(self._h, m.ctypes.data_as(C.POINTER(C.c_double))))
+
     def distance_filter(self, cloud, near_thresh=1.0, far_thresh=100.0, out=None):
         """PrefilteringNodelet::distance_filter as a call of its own (b200reg_distance_filter): for a prefilter without a VoxelGrid."""
         n_out = C.c_size_t()

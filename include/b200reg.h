@@ -187,6 +187,15 @@ int b200reg_set_sm_budget(b200reg_handle* h, int n_sm);
  * the key pipeline, so the copy_if pass and its intermediate cloud never exist.  Defaults of the
  * reference: use_distance_filter true, 1.0 / 100.0 [REF :100-102]; the launch files set 0.1 / 100.0. */
 int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, double far_thresh);
+/* The base_link step in front of those stages [REF apps/prefiltering_nodelet.cpp:123-148]: when `base_link_frame` is set
+ * the nodelet looks the sensor -> base_link transform up, zeroes its x / y translation and runs
+ * pcl::transformPointCloud(*src_cloud, *transformed, transform_isometry.matrix()) — a Matrix4d, so PCL computes every
+ * coordinate in double, left to right (m00*x + m01*y + m02*z + m03), and rounds to float once; w = 1; non-finite points
+ * of a non-dense cloud stay as they are.  With a matrix set (16 doubles, column-major as Eigen stores it; the caller
+ * zeroes the translation as the nodelet does) every VoxelGrid call — and b200reg_distance_filter, the first stage of a
+ * prefilter without a down-sampler — on this handle starts with that transform, on the device, in front of the gate.
+ * NULL switches it off (the reference's default: base_link_frame empty [REF :50]). */
+int b200reg_set_input_transform(b200reg_handle* h, const double* matrix4x4_colmajor);
 /* distance_filter as a call of its own [REF :150, :275-291] for a prefilter WITHOUT a VoxelGrid down-sampler
  * (downsample_method NONE [REF :70-75]: there is no key pass to fuse the gate into).  The reference applies the gate
  * to every scan whatever `use_distance_filter` says (it reads the flag [REF :100] and never tests it).  Order kept;

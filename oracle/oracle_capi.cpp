@@ -179,6 +179,26 @@ long long orc_distance_filter(const float* in, long long n, double near_thresh, 
   return m;
 }
 
+// The base_link step in front of it [REF apps/prefiltering_nodelet.cpp:123-148]:
+//   pcl::transformPointCloud(*src_cloud, *transformed, transform_isometry.matrix())
+// with transform_isometry an Eigen::Isometry3d, i.e. pcl::transformPointCloud<PointT, double> [UPSTREAM-RECALLED,
+// pcl/common/impl/transforms.hpp, PCL 1.8-1.12]: the output starts as a copy of the input; per point (all of them when
+// is_dense, the finite ones otherwise) each coordinate is
+//   static_cast<float>(m(r,0) * x + m(r,1) * y + m(r,2) * z + m(r,3))
+// evaluated in double, left to right (1.8: written out on coeffRefs; 1.10+: detail::Transformer<double>::se3, the same
+// expression), and w = 1.  m: 16 doubles, column-major (Eigen's storage).
+void orc_transform_cloud_d(const float* in, long long n, const double* m, int is_dense, float* out) {
+  for (long long i = 0; i < n; ++i) {
+    const float* p = in + 4 * i;
+    float* q = out + 4 * i;
+    std::memcpy(q, p, 16);
+    if (!is_dense && !(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    const double x = p[0], y = p[1], z = p[2];
+    for (int r = 0; r < 3; ++r) q[r] = static_cast<float>(m[r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r]);
+    q[3] = 1.0f;
+  }
+}
+
 // pcl::RadiusOutlierRemoval<PointXYZ>::applyFilterIndices [UPSTREAM-RECALLED, PCL 1.8-1.10] as set up at
 // [REF apps/prefiltering_nodelet.cpp:88-96]: k = radiusSearch(p, radius) counts the points of the SAME
 // cloud with d2 < radius^2 (the query itself included); the point is kept when k > min_neighbors;

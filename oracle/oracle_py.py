@@ -65,6 +65,8 @@ def lib():
         L.orc_knn.argtypes = [f32p, C.c_longlong, f32p, C.c_longlong, C.c_int, i32p, f32p]
         L.orc_distance_filter.argtypes = [f32p, C.c_longlong, C.c_double, C.c_double, f32p]
         L.orc_distance_filter.restype = C.c_longlong
+        L.orc_transform_cloud_d.argtypes = [f32p, C.c_longlong, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int, f32p]
+        L.orc_transform_cloud_d.restype = None
         L.orc_radius_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_double, C.c_int, f32p]
         L.orc_radius_outlier_removal.restype = C.c_longlong
         L.orc_statistical_outlier_removal.argtypes = [f32p, C.c_longlong, C.c_int, C.c_double, f32p, f64p, f32p]
@@ -127,6 +129,16 @@ def distance_filter(cloud, near_thresh=1.0, far_thresh=100.0):
     out = np.empty((max(len(cloud), 1), 4), np.float32)
     m = lib().orc_distance_filter(cloud if len(cloud) else np.zeros((1, 4), np.float32), len(cloud), float(near_thresh), float(far_thresh), out)
     return out[:m].copy()
+
+
+def transform_cloud_d(cloud, matrix4x4, is_dense=False):
+    """pcl::transformPointCloud(cloud, out, Matrix4d) as the prefilter's base_link step calls it
+    [REF apps/prefiltering_nodelet.cpp:137-147]."""
+    cloud = _cloud(cloud)
+    out = np.empty((max(len(cloud), 1), 4), np.float32)
+    m = np.ascontiguousarray(np.asarray(matrix4x4, np.float64).reshape(4, 4).T).reshape(-1)  # column-major
+    lib().orc_transform_cloud_d(cloud if len(cloud) else np.zeros((1, 4), np.float32), len(cloud), m, int(is_dense), out)
+    return out[: len(cloud)].copy()
 
 
 def radius_outlier_removal(cloud, radius=0.8, min_neighbors=2):

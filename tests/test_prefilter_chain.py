@@ -168,6 +168,77 @@ def test_prefilter_mirror_reads_the_reference_parameters(monkeypatch):
     assert pre.filter is None and pre.distance_filter_on and pre._reg is pre.outlier_removal_filter._reg
 
 
+def base_link_transform(rng):
+    """a sensor -> base_link transform as tf would hand it over: tilted, yawed, mounted 1.9 m up and off-centre"""
+    a, b, c = 0.03, -0.02, 0.7
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    m = np.eye(4)
+    m[:3, :3] = rz @ ry @ rx
+    m[:3, 3] = [0.8, -0.15, 1.9]
+    return m
+
+
+def test_oracle_base_link_transform_is_the_double_expression_rounded_once(oracle):
+    """pcl::transformPointCloud<PointT, double> [REF apps/prefiltering_nodelet.cpp:137-147]: per coordinate
+    m(r,0) x + m(r,1) y + m(r,2) z + m(r,3) in double, left to right, then one rounding to float; w = 1; the
+    non-finite points of a non-dense cloud stay untouched."""
+    rng = np.random.default_rng(12)
+    c = cloud_with_outliers(oracle, rng)
+    c[:, 3] = 7.0  # whatever the sensor driver left in the padding
+    m = base_link_transform(rng)
+    got = oracle.transform_cloud_d(c, m, is_dense=False)
+    fin = np.isfinite(c[:, :3]).all(axis=1)
+    x, y, z = (c[fin, k].astype(np.float64) for k in range(3))
+    for r in range(3):
+        want = (((m[r, 0] * x) + (m[r, 1] * y)) + (m[r, 2] * z)) + m[r, 3]
+        assert np.array_equal(got[fin, r], want.astype(np.float32))
+    assert np.all(got[fin, 3] == 1.0)
+    assert bits_equal(got[~fin], c[~fin]) and (~fin).sum() == 3
+
+
+@pytest.mark.gpu
+def test_base_link_transform_in_front_of_the_chain_matches_the_oracle(oracle):
+    """cloud_callback with base_link_frame set [REF apps/prefiltering_nodelet.cpp:123-153]: transform (x / y translation
+    zeroed) -> distance_filter -> VoxelGrid -> outlier removal, every stage bit-exact; lidar_position is what the height
+    filter gets; None returns to the sensor frame."""
+    import delta_graph_slam_b200 as eng
+    rng = np.random.default_rng(13)
+    c = cloud_with_outliers(oracle, rng)
+    m = base_link_transform(rng)
+    m0 = m.copy()
+    m0[0, 3] = m0[1, 3] = 0.0
+    moved = oracle.transform_cloud_d(c, m0, is_dense=False)
+    assert not bits_equal(moved, c)
+    # launch-file chain
+    pre = eng.Prefilter(LAUNCH, out=DEVNULL)
+    lidar = pre.setBaseLinkTransform(m)
+    assert np.array_equal(lidar, [0.0, 0.0, 1.9])
+    want = oracle.radius_outlier_removal(oracle.voxelgrid(oracle.distance_filter(moved, 0.1, 100.0), 0.1, is_dense=False)["out"], 0.5, 2)
+    assert bits_equal(pre.filter3d(c), want)
+    # the same from a device-resident scan
+    import torch
+    t = torch.from_numpy(c).cuda()
+    bufs = [torch.empty_like(t) for _ in range(2)]
+    f = pre.filter3d(eng.DeviceCloud(t.data_ptr(), len(t), t), out=eng.DeviceCloud(bufs[0].data_ptr(), len(t), bufs[0]), out2=eng.DeviceCloud(bufs[1].data_ptr(), len(t), bufs[1]))
+    assert f.n == len(want) and bits_equal(bufs[1][: f.n].cpu().numpy(), want)
+    # a chain without a down-sampler: the stand-alone gate is the first stage and takes the transform
+    pre2 = eng.Prefilter(dict(downsample_method="NONE", outlier_removal_method="NONE", distance_near_thresh=5.0, distance_far_thresh=20.0), out=DEVNULL)
+    pre2.setBaseLinkTransform(m)
+    assert bits_equal(pre2.filter3d(c), oracle.distance_filter(moved, 5.0, 20.0))
+    # the VoxelGrid alone (no gate), and off again
+    vg = eng.VoxelGrid()
+    vg.setLeafSize(0.1, 0.1, 0.1)
+    vg._reg.setInputTransform(m0)
+    vg.setInputCloud(c, is_dense=False)
+    assert bits_equal(vg.filter(), oracle.voxelgrid(moved, 0.1, is_dense=False)["out"])
+    vg._reg.setInputTransform(None)
+    assert bits_equal(vg.filter(), oracle.voxelgrid(c, 0.1, is_dense=False)["out"])
+    pre.setBaseLinkTransform(None)
+    assert bits_equal(pre.filter3d(c), oracle.radius_outlier_removal(oracle.voxelgrid(oracle.distance_filter(c, 0.1, 100.0), 0.1, is_dense=False)["out"], 0.5, 2))
+
+
 @pytest.mark.gpu
 def test_fused_distance_filter_matches_filter_then_voxelgrid(oracle):
     import delta_graph_slam_b200 as eng
