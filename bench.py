@@ -512,7 +512,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     # scan k is still referenced while scans k+1 and k+2 are filtered), filtered cloud up again (setInputSource of the
     # odometry nodelet), the `aligned` cloud that registration->align(*aligned, guess) always fills
     # [REF apps/scan_matching_odometry_nodelet.cpp:217-218] and the result down
-    def make_host_leg(pinned):
+    def make_host_leg(pinned, fused=False):
         if pinned:
             h_out = torch.empty((3, rays, 4), dtype=torch.float32, pin_memory=True).numpy()
             h_al = torch.empty((rays, 4), dtype=torch.float32, pin_memory=True).numpy()
@@ -525,8 +525,8 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
         raw_bytes = int(sum(c.nbytes for c in inputs))
 
         def step_host(i):
-            poses = fe_h.run_host(inputs, filtered_bufs=[h_out[j] for j in range(3)], aligned_out=h_al)
-            last_dev["poses_host_pinned" if pinned else "poses_host_pageable"] = poses
+            poses = fe_h.run_host(inputs, filtered_bufs=None if fused else [h_out[j] for j in range(3)], aligned_out=h_al)
+            last_dev["poses_host_fused" if fused else ("poses_host_pinned" if pinned else "poses_host_pageable")] = poses
             return None
         return step_host, fe_h, h_out, raw_bytes
     step_host, fe_h, h_out, raw_bytes = make_host_leg(True)
@@ -538,6 +538,17 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     filt_bytes_matched = int(nf_all[1:].astype(np.int64).sum()) * 16
     h2d_step = raw_bytes + filt_bytes                       # raw scans + filtered clouds uploaded again
     d2h_step = filt_bytes + filt_bytes_matched + 128 * regs_per_step  # filtered clouds + aligned clouds + result records
+    # the two nodelets merged into one object: the filtered cloud never leaves the device, so per frame
+    # only the raw scan goes up and the aligned cloud + result come down
+    e2e_fused = None
+    if pageable_leg:
+        step_fu, fe_fu, _, _ = make_host_leg(True, fused=True)
+        fs = max(1, min(steps, 5))
+        sec_f, wall_f, _ = ctx.timed(step_fu, fe_fu.stream(), fs, 2)
+        e2e_fused = {"value": world * fs * regs_per_step / sec_f, "unit": "registrations/s", "ms_per_step": 1e3 * sec_f / fs, "h2d_bytes_per_step": raw_bytes,
+                     "d2h_bytes_per_step": filt_bytes_matched + 128 * regs_per_step, "poses_equal_two_nodelet_leg": bool(np.array_equal(last_dev["poses_host_fused"], last_dev["poses_host_pinned"])),
+                     "note": "page-locked caller clouds through b200reg_frontend_begin / _step with no filtered-cloud buffer: the one-object front end of INTEGRATION.md 5d; raw scan H2D, aligned cloud + result D2H"}
+        del step_fu, fe_fu
     e2e_pageable = None
     if pageable_leg:
         step_pg, fe_pg, _, _ = make_host_leg(False)
@@ -594,6 +605,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
         "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * sec_h / steps,
                 "wall_ms_per_step": 1e3 * wall_h / steps, "note": "page-locked caller clouds; per frame raw scan H2D, filtered cloud D2H + H2D (the two nodelets' message), aligned cloud + result D2H"},
         "e2e_pageable": e2e_pageable,
+        "e2e_fused": e2e_fused,
         "gpu_launches": int(launches_timed),
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align<7>" if is_ndt else "k_gicp_align", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                      "traffic": load_traffic("k_ndt_align_single" if is_ndt else "k_gicp_align"), "traffic_unit": "DRAM bytes per launch (ncu --set full capture of one registration of this workload)",
@@ -817,7 +829,7 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-scan stress leg (BASELINE configs[4]) of the default run")
     ap.add_argument("--dense-targets", type=int, default=0, help="new keyframes of the dense-scan stress batch; 0 = 16 per GPU (1024 pairs on 8 GPUs, BASELINE configs[4])")
     ap.add_argument("--dense-candidates", type=int, default=8)
-    ap.add_argument("--filter-sms", type=int, default=40, help="SMs given to the prefilter handle's persistent kernel in the pipelined front end (the registration takes the rest)")
+    ap.add_argument("--filter-sms", type=int, default=52, help="SMs given to the prefilter handle's persistent kernel in the pipelined front end (the registration takes the rest)")
     ap.add_argument("--gicp-frames", type=int, default=300, help="frames of the sequence the FAST_GICP leg runs per step")
     args = ap.parse_args()
 
@@ -839,6 +851,8 @@ def main():
         """The few numbers of a leg a reader needs first; the JSON line ends with these (the driver keeps the line's tail)."""
         b = {"value": round(d["value"], 1), "e2e": round(d["e2e"]["value"], 1), "unit": d["unit"], "ms_per_step": round(d["ms_per_step"], 3), "n_gpus": d["n_gpus"],
              "frac": round(d["roofline"]["frac"], 4)}
+        if d.get("e2e_fused"):
+            b["e2e_fused"] = round(d["e2e_fused"]["value"], 1)
         st = d.get("stats", {})
         for k in ("align_ms", "fitness_ms", "other_ms"):
             if k in st:
@@ -857,7 +871,7 @@ def main():
         out["summary"] = {"loop_batch": brief(out)}
     else:
         out = bench_odometry(ctx)
-        keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "stats", "e2e", "e2e_pageable", "e2e_new_keyframes_only", "gpu_launches", "roofline", "cpu_baseline", "checks")
+        keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "stats", "e2e", "e2e_pageable", "e2e_fused", "e2e_new_keyframes_only", "gpu_launches", "roofline", "cpu_baseline", "checks")
         summary = {"odometry": brief(out)}
         if not args.no_loop:
             lb = bench_loop(ctx, max(1, min(args.steps, 2)), 3)

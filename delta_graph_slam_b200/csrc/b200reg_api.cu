@@ -57,6 +57,9 @@ struct b200reg_handle {
   VoxelSort vg_sort;
   DevBuf<uint32_t> vg_id, vg_count;
   DevBuf<float4> vg_sorted;  // the scan's points in sorted (voxel, input) order: k_vg_gather -> k_vg_centroids
+  bool align_pending = false;  // b200reg_internal_align_begin .. _end
+  float* align_aligned_out = nullptr;
+  bool align_aligned_direct = false;
   DevBuf<float4> in_xf_buf;  // the scan in the base_link frame (b200reg_set_input_transform)
   bool in_xf_on = false;
   InputXf in_xf{};
@@ -590,6 +593,18 @@ int run_gicp_single(b200reg_handle* h, const float* guess_colmajor) {
   prm.search_d2 = prm.corr_dist2 >= 3.0e38 ? 3.402823466e+38f : (float)prm.corr_dist2 * 1.0001f + 1e-6f;
   const double rings = ceil(d / (double)kNnCell) + 1.0;
   prm.far_ring = rings > (double)kFarRing ? kFarRing : (int)rings;
+  {
+    // lanes per source point in the near search of a linearize pass: as many (4, 2, 1) as still let ONE sweep of the grid's
+    // warps cover the cloud.  More lanes shorten a query's chain of dependent loads, but a second sweep costs more than
+    // that gains: on the 48 k-point scans of the odometry leg four lanes (four sweeps on 108 SMs) measured 1456
+    // registrations/s, two lanes 1470, one lane 1535.  B200_GICP_LANES overrides (A/B runs).
+    static const int forced = getenv("B200_GICP_LANES") ? atoi(getenv("B200_GICP_LANES")) : 0;
+    const long long warps = (long long)G * kGicpWarps;
+    int ql = 1;
+    if ((long long)h->n_src * 4 <= warps * 32) ql = 4;
+    else if ((long long)h->n_src * 2 <= warps * 32) ql = 2;
+    prm.query_lanes = (forced == 1 || forced == 2 || forced == 4) ? forced : ql;
+  }
   prm.trans_eps = h->cfg.transformation_epsilon;
   prm.rot_eps = h->cfg.rotation_epsilon;
   prm.max_iterations = h->cfg.maximum_iterations;
@@ -920,10 +935,14 @@ int b200reg_prepare_promotion(b200reg_handle* h) {
   return B200REG_OK;
 }
 
-int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
+// align in two halves (internal, used by the front end of b200reg_odometry.cu): _begin enqueues the registration (and the
+// kernel + copy that fill `output`) and returns; _end waits for the result.  Between the two the host is free — the
+// front end enqueues the NEXT scan's filter there, under the registration that is running.
+int b200reg_internal_align_begin(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
   auto set_error = [&](const std::string& s) { h->err = s; };
   if (!h) return B200REG_E_INVALID;
   h->have_result = false;
+  h->align_pending = false;
   if (!h->have_tgt) { h->err = "No input target dataset was given!"; return B200REG_E_STATE; }
   int rc = set_device(h);
   if (rc) return rc;
@@ -938,22 +957,41 @@ int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
     return B200REG_E_STATE;
   }
   if (h->prepare_pending && (rc = launch_side_build(h))) return rc;  // under the registration that has just been launched
-  bool aligned_direct = false;
+  h->align_aligned_out = aligned_xyzw;
+  h->align_aligned_direct = false;
   if (aligned_xyzw) {
     // pcl::Registration::align fills `output` with the transformed source [REF apps/scan_matching_odometry_nodelet.cpp:217-218]:
     // one kernel behind the registration, then DMA straight into a page-locked caller cloud, or through the
     // handle's pinned staging buffer into a pageable one
     B200_CUDA_TRY(h->aligned.reserve(h->n_src));
-    aligned_direct = is_pinned_host(aligned_xyzw);
-    if (!aligned_direct) B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
+    h->align_aligned_direct = is_pinned_host(aligned_xyzw);
+    if (!h->align_aligned_direct) B200_CUDA_TRY(h->pin_out.reserve(h->n_src));
     launch_counter() += 1;
     k_transform_cloud<<<(h->n_src + 255) / 256, 256, 0, h->stream>>>(h->src.p, h->n_src, h->d_result.p, h->aligned.p);
-    B200_CUDA_TRY(cudaMemcpyAsync(aligned_direct ? (void*)aligned_xyzw : (void*)h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(h->align_aligned_direct ? (void*)aligned_xyzw : (void*)h->pin_out.p, h->aligned.p, (size_t)h->n_src * 16, cudaMemcpyDeviceToHost, h->stream));
   }
-  if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
-  if (aligned_xyzw && !aligned_direct) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  h->align_pending = true;
   return B200REG_OK;
+}
+
+int b200reg_internal_align_end(b200reg_handle* h) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  if (!h->align_pending) { h->err = "no registration in flight on this handle"; return B200REG_E_STATE; }
+  h->align_pending = false;
+  int rc = set_device(h);
+  if (rc) return rc;
+  float* aligned_xyzw = h->align_aligned_out;
+  if (aligned_xyzw) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
+  if (aligned_xyzw && !h->align_aligned_direct) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  return B200REG_OK;
+}
+
+int b200reg_align(b200reg_handle* h, const float* guess, float* aligned_xyzw) {
+  const int rc = b200reg_internal_align_begin(h, guess, aligned_xyzw);
+  if (rc) return rc;
+  return b200reg_internal_align_end(h);
 }
 
 int b200reg_has_converged(b200reg_handle* h, int* out) {
@@ -1041,834 +1079,9 @@ int b200reg_get_inlier_fraction(b200reg_handle* h, double max_dist, double* out)
   return B200REG_OK;
 }
 
-// ---- VoxelGrid -------------------------------------------------------------------------------
-static int vg_run(b200reg_handle* h, const float4* d_in, size_t n, const float leaf[3], unsigned min_pts, int dense, float4* d_out, float4* host_out = nullptr, size_t host_cap = 0) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  B200_CUDA_TRY(h->vg_id.reserve(n ? n : 1));
-  B200_CUDA_TRY(h->vg_count.reserve(n ? n : 1));
-  B200_CUDA_TRY(h->vg_counts.reserve(1));
-  B200_CUDA_TRY(h->vg_sorted.reserve(n ? n : 1));
-  if (h->in_xf_on && n) {  // base_link frame first, as cloud_callback does [REF apps/prefiltering_nodelet.cpp:123-148]
-    B200_CUDA_TRY(h->in_xf_buf.reserve(n));
-    launch_counter() += 1;
-    k_input_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_in, (int)n, h->in_xf, dense, h->in_xf_buf.p);
-    d_in = h->in_xf_buf.p;
-  }
-  bool gathered = false;  // the one-sweep sort's last pass writes the points in sorted order itself
-  B200_CUDA_TRY(h->vg_sort.run(h->stream, d_in, (int)n, dense, leaf[0], leaf[1], leaf[2], true, h->gate, h->vg_sorted.p, &gathered));
-  const int blocks = n ? (int)((n + 255) / 256) : 1;
-  launch_counter() += (gathered ? 1 : 2) + (min_pts > 1 ? 1 : 0);
-  if (!gathered) k_vg_gather<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sort.meta.p, h->vg_sorted.p);
-  // the overflow case publishes from k_vg_centroids even when a compaction pass follows
-  VgCounts* hc = const_cast<VgCounts*>(&h->mail->vg);
-  unsigned int* hf = const_cast<unsigned int*>(&h->mail->vg_seq);
-  const unsigned int seq = ++h->vg_seq;
-  if (!h->vg_done.p) {  // completion counter of k_vg_centroids: zeroed once, the last block restores it
-    B200_CUDA_TRY(h->vg_done.reserve(1));
-    B200_CUDA_TRY(cudaMemsetAsync(h->vg_done.p, 0, h->vg_done.cap * sizeof(unsigned int), h->stream));
-  }
-  k_vg_centroids<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->vg_sort.vals_a.p, h->vg_sort.vals_b.p, h->vg_sorted.p, h->vg_sort.seg_first.p, h->vg_sort.meta.p, h->vg_sort.vox_start.p, h->vg_sort.vox_key.p,
-                                                min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq, h->vg_done.p, min_pts > 1 ? 0 : 1, host_out,
-                                                (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->gate.on);
-  if (h->gate.on) {  // only acts in the "leaf size too small" case: the output is then the gated input
-    launch_counter() += 1;
-    k_gate_copy<<<1, 1024, 0, h->stream>>>(d_in, (int)n, h->gate, h->vg_sort.meta.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap), h->vg_counts.p, hc, hf, seq);
-  }
-  if (min_pts > 1) k_vg_compact<<<1, 1024, 0, h->stream>>>(h->vg_sort.meta.p, min_pts, d_out, h->vg_id.p, h->vg_count.p, h->vg_counts.p, hc, hf, seq);
-  B200_CUDA_TRY(cudaGetLastError());
-  h->vg_last_n = (int)n;
-  return B200REG_OK;
-}
+#include "b200reg_api_filters.inl"
 
-// The filter as two halves.  begin: everything is enqueued on the handle's stream and the call
-// returns; end: wait for the point count the last kernel publishes through the mailbox.  The
-// synchronous entry points below are begin + end.
-int b200reg_voxelgrid_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out) {
-  if (!h || !leaf || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
-  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
-  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  if ((rc = vg_run(h, (const float4*)d_xyzw, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
-  h->vg_pending = b200reg_handle::VgPending();
-  h->vg_pending.active = true;
-  return B200REG_OK;
-}
-
-int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* out, size_t cap) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !leaf || (n && !xyzw)) return B200REG_E_INVALID;
-  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
-  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
-  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  // input: page-locked caller memory is read by DMA while this call has already returned (the caller
-  // keeps it unchanged until _end); pageable memory goes through the handle's pinned staging buffer,
-  // which is not touched again before the next _begin
-  B200_CUDA_TRY(h->stage_in.reserve(n ? n : 1));
-  B200_CUDA_TRY(h->stage_out.reserve(n ? n : 1));
-  if (n) {
-    if (stride == 16 && is_pinned_host(xyzw)) {
-      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
-    } else {
-      B200_CUDA_TRY(h->pin_in.reserve(n));
-      if (stride == 16) {
-        memcpy(h->pin_in.p, xyzw, n * 16);
-      } else {
-        const unsigned char* b = (const unsigned char*)xyzw;
-        for (size_t i = 0; i < n; ++i) {
-          const float* p = (const float*)(b + i * stride);
-          h->pin_in.p[i] = make_float4(p[0], p[1], p[2], 1.0f);
-        }
-      }
-      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, h->pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
-    }
-  }
-  // output: a page-locked caller cloud is written by the centroid kernel itself (mapped memory);
-  // min_points_per_voxel > 1 compacts on the device first, and pageable memory needs staging: both
-  // copy in _end
-  const bool zero_copy = out && cap && min_pts <= 1 && is_pinned_host(out);
-  if ((rc = vg_run(h, h->stage_in.p, n, leaf, min_pts, dense, h->stage_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
-  h->vg_pending.active = true;
-  h->vg_pending.host_out = out;
-  h->vg_pending.cap = cap;
-  h->vg_pending.zero_copy = zero_copy;
-  return B200REG_OK;
-}
-
-// host scan in, filtered cloud left on the device (a fused front end hands it to the registration without a round trip
-// through host memory)
-int b200reg_voxelgrid_filter_host_to_device_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* d_out) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !leaf || (n && (!xyzw || !d_out))) return B200REG_E_INVALID;
-  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) return B200REG_E_INVALID;
-  if (h->vg_pending.active) { h->err = "a filter call is already in flight on this handle (b200reg_voxelgrid_filter_end first)"; return B200REG_E_STATE; }
-  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  B200_CUDA_TRY(h->stage_in.reserve(n ? n : 1));
-  if (n) {
-    if (stride == 16 && is_pinned_host(xyzw)) {
-      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
-    } else {
-      B200_CUDA_TRY(h->pin_in.reserve(n));
-      if (stride == 16) {
-        memcpy(h->pin_in.p, xyzw, n * 16);
-      } else {
-        const unsigned char* b = (const unsigned char*)xyzw;
-        for (size_t i = 0; i < n; ++i) {
-          const float* p = (const float*)(b + i * stride);
-          h->pin_in.p[i] = make_float4(p[0], p[1], p[2], 1.0f);
-        }
-      }
-      B200_CUDA_TRY(cudaMemcpyAsync(h->stage_in.p, h->pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
-    }
-  }
-  if ((rc = vg_run(h, h->stage_in.p, n, leaf, min_pts, dense, (float4*)d_out))) return rc;
-  h->vg_pending = b200reg_handle::VgPending();
-  h->vg_pending.active = true;
-  return B200REG_OK;
-}
-
-int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  if (!h->vg_pending.active) { h->err = "no filter call in flight on this handle"; return B200REG_E_STATE; }
-  const b200reg_handle::VgPending pend = h->vg_pending;
-  h->vg_pending.active = false;
-  int rc = set_device(h);
-  if (rc) return rc;
-  if ((rc = wait_mail(h, &h->mail->vg_seq, h->vg_seq))) return rc;
-  const size_t m = h->mail->vg.n_out;
-  *n_out = m;
-  h->vg_last_out = (int)m;
-  if (!pend.host_out && !pend.cap) return B200REG_OK;  // device variant
-  if (m > pend.cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
-  if (!m || pend.zero_copy) return B200REG_OK;
-  if (!pend.host_out) return B200REG_E_INVALID;
-  if (is_pinned_host(pend.host_out)) {
-    B200_CUDA_TRY(cudaMemcpyAsync(pend.host_out, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  } else {
-    B200_CUDA_TRY(h->pin_out.reserve(m));
-    B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    memcpy(pend.host_out, h->pin_out.p, m * 16);
-  }
-  return B200REG_OK;
-}
-
-int b200reg_voxelgrid_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, const float leaf[3], unsigned min_pts, int dense, float* d_out, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  int rc = b200reg_voxelgrid_filter_device_begin(h, d_xyzw, n, leaf, min_pts, dense, d_out);
-  if (rc) return rc;
-  return b200reg_voxelgrid_filter_end(h, n_out);
-}
-
-int b200reg_voxelgrid_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const float leaf[3], unsigned min_pts, int dense, float* out, size_t cap,
-                             size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_voxelgrid_filter_begin(h, xyzw, n, stride, leaf, min_pts, dense, out, cap);
-  if (rc) return rc;
-  return b200reg_voxelgrid_filter_end(h, n_out);
-}
-
-int b200reg_set_distance_filter(b200reg_handle* h, int use, double near_thresh, double far_thresh) {
-  if (!h) return B200REG_E_INVALID;
-  h->gate.on = use ? 1 : 0;
-  h->gate.near_thresh = near_thresh;
-  h->gate.far_thresh = far_thresh;
-  return B200REG_OK;
-}
-
-int b200reg_set_input_transform(b200reg_handle* h, const double* matrix4x4_colmajor) {
-  if (!h) return B200REG_E_INVALID;
-  h->in_xf_on = matrix4x4_colmajor != nullptr;
-  if (matrix4x4_colmajor)
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 4; ++c) h->in_xf.m[4 * r + c] = matrix4x4_colmajor[4 * c + r];
-  return B200REG_OK;
-}
-
-// ---- RadiusOutlierRemoval ----------------------------------------------------------------------
-// which outlier filter a call runs: pcl::RadiusOutlierRemoval or pcl::StatisticalOutlierRemoval
-struct OutlierSpec {
-  bool statistical = false;
-  double radius = 0.0;
-  int min_neighbors = 0;
-  int mean_k = 0;
-  double stddev_mul = 0.0;
-  // filtered2D of the prefilter nodelet: height gate -> normal test -> flatten (b200reg_flat_filter)
-  bool flat = false;
-  double lidar_z = 0.0;
-  int normal_k = 0;
-  float normal_thresh = 0.f;
-  // distance_filter on its own (down-sampling NONE) [REF apps/prefiltering_nodelet.cpp:275-291]
-  bool gate_only = false;
-  double near_thresh = 0.0, far_thresh = 0.0;
-  bool valid() const {
-    if (gate_only) return near_thresh == near_thresh && far_thresh == far_thresh;
-    if (flat) return normal_k >= 1 && normal_k <= 32 && lidar_z == lidar_z && normal_thresh == normal_thresh;
-    return statistical ? (mean_k >= 1 && mean_k <= 31 && stddev_mul == stddev_mul) : (radius > 0 && min_neighbors >= 0);
-  }
-};
-
-static int ror_run(b200reg_handle* h, const float4* d_in, size_t n, const OutlierSpec& spec, float4* d_out, float4* host_out, size_t host_cap) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  const double radius = spec.radius;
-  const int min_neighbors = spec.min_neighbors;
-  PointGate gate = kNoGate;
-  if (spec.flat) { gate.on = 2; gate.near_thresh = spec.lidar_z; }  // height_filtering as a gate of the lattice build: no intermediate cloud
-  if (spec.gate_only && h->in_xf_on && n) {  // distance_filter is the first stage of a prefilter without a down-sampler: base_link frame first
-    B200_CUDA_TRY(h->in_xf_buf.reserve(n));
-    launch_counter() += 1;
-    k_input_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_in, (int)n, h->in_xf, /*is_dense=*/0, h->in_xf_buf.p);
-    d_in = h->in_xf_buf.p;
-  }
-  if (!spec.gate_only) B200_CUDA_TRY(h->nn_ror.build(h->stream, d_in, (int)n, /*is_dense=*/0, gate));
-  const int blocks = n ? (int)((n + 255) / 256) : 1;
-  B200_CUDA_TRY(h->ror_keep.reserve(n ? n : 1));
-  B200_CUDA_TRY(h->ror_block_count.reserve(blocks));
-  B200_CUDA_TRY(h->ror_counts.reserve(1));
-  if (!h->ror_done.p) {
-    B200_CUDA_TRY(h->ror_done.reserve(1));
-    B200_CUDA_TRY(cudaMemsetAsync(h->ror_done.p, 0, h->ror_done.cap * sizeof(unsigned int), h->stream));
-  }
-  const float r2 = (float)(radius * radius);
-  int rings = (int)ceil(radius / (double)kNnCell);
-  if (rings < 1) rings = 1;
-  RorCounts* hc = const_cast<RorCounts*>(&h->mail->ror);
-  unsigned int* hf = const_cast<unsigned int*>(&h->mail->ror_seq);
-  const unsigned int seq = ++h->ror_seq;
-  if (spec.gate_only) {
-    PointGate dg = {1, spec.near_thresh, spec.far_thresh};
-    launch_counter() += 2;
-    k_gate_flags<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, dg, h->ror_keep.p, h->ror_block_count.p);
-  } else if (spec.flat) {
-    // |n_z| per point that passed the height gate; NaN (never kept) everywhere else
-    B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
-    B200_CUDA_TRY(h->sor_pending.reserve(n ? n : 1));
-    B200_CUDA_TRY(h->sor_n_pending.reserve(1));
-    B200_CUDA_TRY(cudaMemsetAsync(h->sor_dist.p, 0xFF, (n ? n : 1) * sizeof(float), h->stream));
-    B200_CUDA_TRY(cudaMemsetAsync(h->sor_n_pending.p, 0, sizeof(unsigned int), h->stream));
-    launch_counter() += 4;
-    if (n) {
-      k_gicp_knn<kKnnNormalNz><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-      k_gicp_knn_brute<kKnnNormalNz><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.normal_k, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-    }
-    k_nz_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.normal_thresh, h->ror_keep.p, h->ror_block_count.p);
-  } else if (spec.statistical) {
-    // the k-NN kernels write one float per finite point; everything else stays at the "not counted" mark (< 0)
-    B200_CUDA_TRY(h->sor_dist.reserve(n ? n : 1));
-    B200_CUDA_TRY(h->sor_stats.reserve(1));
-    B200_CUDA_TRY(h->sor_pending.reserve(n ? n : 1));
-    B200_CUDA_TRY(h->sor_n_pending.reserve(1));
-    B200_CUDA_TRY(cudaMemsetAsync(h->sor_dist.p, 0xBF, (n ? n : 1) * sizeof(float), h->stream));
-    B200_CUDA_TRY(cudaMemsetAsync(h->sor_n_pending.p, 0, sizeof(unsigned int), h->stream));
-    launch_counter() += 5;
-    if (n) {
-      k_gicp_knn<kKnnMeanDistance><<<(int)((n + 7) / 8), 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-      k_gicp_knn_brute<kKnnMeanDistance><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(h->nn_ror.view(), d_in, spec.mean_k + 1, nullptr, h->sor_pending.p, h->sor_n_pending.p, h->sor_dist.p);
-    }
-    k_sor_threshold<<<1, 1024, 0, h->stream>>>(h->sor_dist.p, (int)n, spec.stddev_mul, h->sor_stats.p);
-    k_sor_flags<<<blocks, 256, 0, h->stream>>>(h->sor_dist.p, (int)n, h->sor_stats.p, h->ror_keep.p, h->ror_block_count.p);
-  } else {
-    launch_counter() += 2;
-    k_ror_flags<<<blocks, 256, 0, h->stream>>>(h->nn_ror.view(), d_in, (int)n, r2, rings, min_neighbors, h->ror_keep.p, h->ror_block_count.p);
-  }
-  k_ror_scatter<<<blocks, 256, 0, h->stream>>>(d_in, (int)n, h->ror_keep.p, h->ror_block_count.p, d_out, host_out, (unsigned)(host_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : host_cap),
-                                               h->ror_counts.p, hc, hf, seq, h->ror_done.p, spec.gate_only ? nullptr : h->nn_ror.sort.meta.p, spec.flat ? 1 : 0);
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200REG_OK;
-}
-
-static int outlier_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, const OutlierSpec& spec, float* d_out) {
-  if (!h || !spec.valid() || (n && (!d_xyzw || !d_out))) return B200REG_E_INVALID;
-  if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  if ((rc = ror_run(h, (const float4*)d_xyzw, n, spec, (float4*)d_out, nullptr, 0))) return rc;
-  h->ror_pending = b200reg_handle::RorPending();
-  h->ror_pending.active = true;
-  h->ror_pending.device = true;
-  return B200REG_OK;
-}
-
-static OutlierSpec radius_spec(double radius, int min_neighbors) {
-  OutlierSpec s;
-  s.radius = radius; s.min_neighbors = min_neighbors;
-  return s;
-}
-static OutlierSpec statistical_spec(int mean_k, double stddev_mul) {
-  OutlierSpec s;
-  s.statistical = true; s.mean_k = mean_k; s.stddev_mul = stddev_mul;
-  return s;
-}
-int b200reg_radius_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out) {
-  return outlier_device_begin(h, d_xyzw, n, radius_spec(radius, min_neighbors), d_out);
-}
-int b200reg_statistical_outlier_removal_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out) {
-  if (h && (mean_k < 1 || mean_k > 31)) { h->err = "statistical_mean_k must lie in 1..31 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
-  return outlier_device_begin(h, d_xyzw, n, statistical_spec(mean_k, stddev_mul), d_out);
-}
-
-static int outlier_host_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, const OutlierSpec& spec, float* out, size_t cap) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !spec.valid() || (n && !xyzw)) return B200REG_E_INVALID;
-  if (h->ror_pending.active) { h->err = "an outlier-removal call is already in flight on this handle"; return B200REG_E_STATE; }
-  if (stride < 12 || (stride % 4) != 0) { h->err = "stride_bytes must be a multiple of 4 and at least 12"; return B200REG_E_INVALID; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  B200_CUDA_TRY(h->ror_in.reserve(n ? n : 1));
-  B200_CUDA_TRY(h->ror_out.reserve(n ? n : 1));
-  if (n) {
-    if (stride == 16 && is_pinned_host(xyzw)) {
-      B200_CUDA_TRY(cudaMemcpyAsync(h->ror_in.p, xyzw, n * 16, cudaMemcpyHostToDevice, h->stream));
-    } else {
-      B200_CUDA_TRY(h->ror_pin_in.reserve(n));
-      const unsigned char* b = (const unsigned char*)xyzw;
-      for (size_t i = 0; i < n; ++i) {
-        const float* p = (const float*)(b + i * stride);
-        h->ror_pin_in.p[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 1.0f);
-      }
-      B200_CUDA_TRY(cudaMemcpyAsync(h->ror_in.p, h->ror_pin_in.p, n * 16, cudaMemcpyHostToDevice, h->stream));
-    }
-  }
-  const bool zero_copy = out && cap && is_pinned_host(out);
-  if ((rc = ror_run(h, h->ror_in.p, n, spec, h->ror_out.p, zero_copy ? (float4*)out : nullptr, cap))) return rc;
-  h->ror_pending = b200reg_handle::RorPending();
-  h->ror_pending.active = true;
-  h->ror_pending.host_out = out;
-  h->ror_pending.cap = cap;
-  h->ror_pending.zero_copy = zero_copy;
-  return B200REG_OK;
-}
-
-int b200reg_radius_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap) {
-  return outlier_host_begin(h, xyzw, n, stride, radius_spec(radius, min_neighbors), out, cap);
-}
-int b200reg_statistical_outlier_removal_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, int mean_k, double stddev_mul, float* out, size_t cap) {
-  if (h && (mean_k < 1 || mean_k > 31)) { h->err = "statistical_mean_k must lie in 1..31 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
-  return outlier_host_begin(h, xyzw, n, stride, statistical_spec(mean_k, stddev_mul), out, cap);
-}
-
-int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  if (!h->ror_pending.active) { h->err = "no outlier-removal call in flight on this handle"; return B200REG_E_STATE; }
-  const b200reg_handle::RorPending pend = h->ror_pending;
-  h->ror_pending.active = false;
-  int rc = set_device(h);
-  if (rc) return rc;
-  if ((rc = wait_mail(h, &h->mail->ror_seq, h->ror_seq))) return rc;
-  if (h->mail->ror.overflow) {
-    h->err = "outlier removal: the cloud spans more than 2^31 cells of the 0.5 m search lattice (gate it with the distance filter first); no result";
-    return B200REG_E_INVALID;
-  }
-  const size_t m = h->mail->ror.n_out;
-  *n_out = m;
-  if (pend.device) return B200REG_OK;
-  if (m > pend.cap) { h->err = "output capacity too small"; return B200REG_E_CAPACITY; }
-  if (!m || pend.zero_copy) return B200REG_OK;
-  if (!pend.host_out) return B200REG_E_INVALID;
-  B200_CUDA_TRY(h->ror_pin_out.reserve(m));
-  B200_CUDA_TRY(cudaMemcpyAsync(h->ror_pin_out.p, h->ror_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  memcpy(pend.host_out, h->ror_pin_out.p, m * 16);
-  return B200REG_OK;
-}
-
-int b200reg_radius_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double radius, int min_neighbors, float* out, size_t cap, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_radius_outlier_removal_begin(h, xyzw, n, stride, radius, min_neighbors, out, cap);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-
-int b200reg_radius_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, double radius, int min_neighbors, float* d_out, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_radius_outlier_removal_device_begin(h, d_xyzw, n, radius, min_neighbors, d_out);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-
-int b200reg_statistical_outlier_removal_end(b200reg_handle* h, size_t* n_out) { return b200reg_radius_outlier_removal_end(h, n_out); }
-
-int b200reg_statistical_outlier_removal(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, int mean_k, double stddev_mul, float* out, size_t cap, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_statistical_outlier_removal_begin(h, xyzw, n, stride, mean_k, stddev_mul, out, cap);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-
-int b200reg_statistical_outlier_removal_device(b200reg_handle* h, const float* d_xyzw, size_t n, int mean_k, double stddev_mul, float* d_out, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_statistical_outlier_removal_device_begin(h, d_xyzw, n, mean_k, stddev_mul, d_out);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-
-// ---- distance_filter on its own (the prefilter nodelet with downsample_method NONE) ------------------
-static OutlierSpec gate_spec(double near_thresh, double far_thresh) {
-  OutlierSpec s;
-  s.gate_only = true; s.near_thresh = near_thresh; s.far_thresh = far_thresh;
-  return s;
-}
-int b200reg_distance_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double near_thresh, double far_thresh, float* out, size_t cap, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = outlier_host_begin(h, xyzw, n, stride, gate_spec(near_thresh, far_thresh), out, cap);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-int b200reg_distance_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double near_thresh, double far_thresh, float* d_out, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = outlier_device_begin(h, d_xyzw, n, gate_spec(near_thresh, far_thresh), d_out);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-
-// ---- filtered2D: height_filtering -> normal_filtering -> flatten ----------------------------------
-static OutlierSpec flat_spec(double lidar_z, int k, double thresh) {
-  OutlierSpec s;
-  s.flat = true; s.lidar_z = lidar_z; s.normal_k = k; s.normal_thresh = (float)thresh;
-  return s;
-}
-static int flat_check(b200reg_handle* h, int k) {
-  if (h && (k < 1 || k > 32)) { h->err = "normal_k must lie in 1..32 (the device k-NN holds one neighbour per warp lane)"; return B200REG_E_INVALID; }
-  return B200REG_OK;
-}
-int b200reg_flat_filter_begin(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double lidar_z, int normal_k, double normal_thresh, float* out, size_t cap) {
-  int rc = flat_check(h, normal_k);
-  if (rc) return rc;
-  return outlier_host_begin(h, xyzw, n, stride, flat_spec(lidar_z, normal_k, normal_thresh), out, cap);
-}
-int b200reg_flat_filter_device_begin(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out) {
-  int rc = flat_check(h, normal_k);
-  if (rc) return rc;
-  return outlier_device_begin(h, d_xyzw, n, flat_spec(lidar_z, normal_k, normal_thresh), d_out);
-}
-int b200reg_flat_filter_end(b200reg_handle* h, size_t* n_out) { return b200reg_radius_outlier_removal_end(h, n_out); }
-int b200reg_flat_filter(b200reg_handle* h, const float* xyzw, size_t n, size_t stride, double lidar_z, int normal_k, double normal_thresh, float* out, size_t cap, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_flat_filter_begin(h, xyzw, n, stride, lidar_z, normal_k, normal_thresh, out, cap);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-int b200reg_flat_filter_device(b200reg_handle* h, const float* d_xyzw, size_t n, double lidar_z, int normal_k, double normal_thresh, float* d_out, size_t* n_out) {
-  if (!n_out) return B200REG_E_INVALID;
-  *n_out = 0;
-  int rc = b200reg_flat_filter_device_begin(h, d_xyzw, n, lidar_z, normal_k, normal_thresh, d_out);
-  if (rc) return rc;
-  return b200reg_radius_outlier_removal_end(h, n_out);
-}
-// |n_z| per input point of the last flat-filter call (NaN: below the height gate, or no normal)
-int b200reg_flat_filter_last_nz(b200reg_handle* h, float* nz, size_t n) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || !nz) return B200REG_E_INVALID;
-  if (!h->sor_dist.p || n > h->sor_dist.cap) return B200REG_E_STATE;
-  int rc = set_device(h);
-  if (rc) return rc;
-  B200_CUDA_TRY(cudaMemcpyAsync(nz, h->sor_dist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return B200REG_OK;
-}
-
-// mean / stddev / cut of the last statistical call (after its _end), its count of points with a full
-// neighbour list and whether the index-order summation had to run; dist (optional, n floats): the per-point
-// mean neighbour distances, 0 for the points upstream leaves uncounted
-int b200reg_statistical_last_stats(b200reg_handle* h, double stats3[3], unsigned long long* valid, int* exact_pass, float* dist, size_t n) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h) return B200REG_E_INVALID;
-  if (!h->sor_stats.p) return B200REG_E_STATE;
-  int rc = set_device(h);
-  if (rc) return rc;
-  SorStats st;
-  B200_CUDA_TRY(cudaMemcpyAsync(&st, h->sor_stats.p, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
-  if (dist && n) {
-    if (n > h->sor_dist.cap) return B200REG_E_INVALID;
-    B200_CUDA_TRY(cudaMemcpyAsync(dist, h->sor_dist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  }
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (dist) for (size_t i = 0; i < n; ++i) if (dist[i] < 0.f) dist[i] = 0.f;
-  if (stats3) { stats3[0] = st.mean; stats3[1] = st.stddev; stats3[2] = st.threshold; }
-  if (valid) *valid = st.valid;
-  if (exact_pass) *exact_pass = (int)st.exact_pass;
-  return B200REG_OK;
-}
-
-int b200reg_voxelgrid_last_layout(b200reg_handle* h, uint32_t* voxel_id, uint32_t* count, size_t n_vox, uint32_t* key, size_t n_points, int32_t* grid6, int* overflow) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h) return B200REG_E_INVALID;
-  if (!h->vg_sort.meta.p) return B200REG_E_STATE;
-  int rc = set_device(h);
-  if (rc) return rc;
-  SortMeta meta;
-  B200_CUDA_TRY(cudaMemcpyAsync(&meta, h->vg_sort.meta.p, sizeof(meta), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (overflow) *overflow = meta.grid.overflow;
-  if (grid6) for (int a = 0; a < 3; ++a) { grid6[a] = meta.grid.min_b[a]; grid6[3 + a] = meta.grid.div_b[a]; }
-  if (meta.grid.overflow) return B200REG_OK;
-  size_t nv = n_vox < (size_t)h->vg_last_out ? n_vox : (size_t)h->vg_last_out;
-  if (voxel_id && nv) B200_CUDA_TRY(cudaMemcpyAsync(voxel_id, h->vg_id.p, nv * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (count && nv) B200_CUDA_TRY(cudaMemcpyAsync(count, h->vg_count.p, nv * 4, cudaMemcpyDeviceToHost, h->stream));
-  size_t np = n_points < (size_t)h->vg_last_n ? n_points : (size_t)h->vg_last_n;
-  if (key && np) B200_CUDA_TRY(cudaMemcpyAsync(key, h->vg_sort.point_key.p, np * 4, cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return B200REG_OK;
-}
-
-// ---- loop-closure batches --------------------------------------------------------------------
-static CachedCloud* cache_find(b200reg_handle* h, long long id) {
-  auto it = h->cache.find(id);
-  return it == h->cache.end() ? nullptr : &it->second;
-}
-
-int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n, size_t stride) {
-  if (!h || (n && !xyzw)) return B200REG_E_INVALID;
-  int rc = set_device(h);
-  if (rc) return rc;
-  CachedCloud& c = h->cache[(long long)id];
-  if ((rc = upload_cloud(h, xyzw, n, stride, c.pts, /*defer_pinned=*/true))) return rc;
-  c.n = (int)n;
-  c.has_ndt = c.has_nn = false;
-  return B200REG_OK;
-}
-
-int b200reg_cloud_put_device(b200reg_handle* h, int64_t id, const float* d_xyzw, size_t n) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h || (n && !d_xyzw)) return B200REG_E_INVALID;
-  int rc = set_device(h);
-  if (rc) return rc;
-  CachedCloud& c = h->cache[(long long)id];
-  B200_CUDA_TRY(c.pts.reserve(n ? n : 1));
-  if (n) B200_CUDA_TRY(cudaMemcpyAsync(c.pts.p, d_xyzw, n * 16, cudaMemcpyDeviceToDevice, h->stream));
-  c.n = (int)n;
-  c.has_ndt = c.has_nn = false;
-  return B200REG_OK;
-}
-
-int b200reg_cloud_drop(b200reg_handle* h, int64_t id) {
-  if (!h) return B200REG_E_INVALID;
-  auto it = h->cache.find((long long)id);
-  if (it == h->cache.end()) return B200REG_E_INVALID;
-  cudaSetDevice(h->cfg.device);
-  cudaStreamSynchronize(h->stream);
-  it->second.release();
-  h->cache.erase(it);
-  return B200REG_OK;
-}
-
-int b200reg_cloud_clear(b200reg_handle* h) {
-  if (!h) return B200REG_E_INVALID;
-  cudaSetDevice(h->cfg.device);
-  cudaStreamSynchronize(h->stream);
-  for (auto& kv : h->cache) kv.second.release();
-  h->cache.clear();
-  return B200REG_OK;
-}
-
-int b200reg_cloud_sync(b200reg_handle* h) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  if (!h) return B200REG_E_INVALID;
-  int rc = set_device(h);
-  if (rc) return rc;
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return B200REG_OK;
-}
-
-int b200reg_cloud_count(b200reg_handle* h, size_t* out) {
-  if (!h || !out) return B200REG_E_INVALID;
-  *out = h->cache.size();
-  return B200REG_OK;
-}
-
-// do_align = 0: no registration, the pair's `guess` IS the transform the fitness is evaluated at
-// (b200reg_calc_fitness_batch); only the exact-NN product of the targets is needed then
-// results == nullptr with d_results_out != nullptr: the records stay on the device (slot i of *d_results_out belongs to
-// pairs[i]); everything is only ENQUEUED on the handle's stream — the multi-GPU entry (b200reg_multi.cu) gathers them
-// with one NCCL all-gather and synchronises once.  `min_slots`: capacity the record array must have (the gather's slot).
-static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int do_align, int with_fitness, double fitness_max_range, b200reg_result* results,
-                     b200reg_result** d_results_out = nullptr, size_t min_slots = 0) {
-  auto set_error = [&](const std::string& s) { h->err = s; };
-  const bool keep_on_device = results == nullptr && d_results_out != nullptr;
-  if (!h || (n_pairs && (!pairs || (!results && !keep_on_device)))) return B200REG_E_INVALID;
-  if (keep_on_device) {
-    if (set_device(h)) return B200REG_E_CUDA;
-    B200_CUDA_TRY(h->batch_results.reserve(std::max(n_pairs, min_slots) + 1));
-    *d_results_out = h->batch_results.p;
-  }
-  if (!n_pairs) return B200REG_OK;
-  if (do_align && h->cfg.method != B200REG_METHOD_NDT) { h->err = "align_batch: this handle's registration method has no batch path"; return B200REG_E_STATE; }
-  int rc = set_device(h);
-  if (rc) return rc;
-  const float res = (float)h->cfg.resolution;
-  // ---- look up the clouds; build the target products once per distinct target
-  std::vector<CachedCloud*> tgt(n_pairs), src(n_pairs);
-  for (size_t i = 0; i < n_pairs; ++i) {
-    tgt[i] = cache_find(h, pairs[i].target_id);
-    src[i] = cache_find(h, pairs[i].source_id);
-    if (!tgt[i] || !src[i]) { h->err = "align_batch: pair " + std::to_string(i) + " names a cloud id that was never put"; return B200REG_E_INVALID; }
-    if (tgt[i]->n == 0) { h->err = "align_batch: pair " + std::to_string(i) + ": Invalid or empty point cloud dataset given!"; return B200REG_E_INVALID; }
-  }
-  {
-    // fork: the lanes start after everything already queued on the handle's stream (cloud uploads)
-    std::vector<CachedCloud*> todo;
-    for (size_t i = 0; i < n_pairs; ++i) {
-      CachedCloud& c = *tgt[i];
-      const bool need = (do_align && (!c.has_ndt || c.ndt_res != res)) || (with_fitness && !c.has_nn);
-      if (need && std::find(todo.begin(), todo.end(), &c) == todo.end()) todo.push_back(&c);
-    }
-    if (!todo.empty()) {
-      if (!h->ev_fork) B200_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-      B200_CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
-      const int n_lanes = (int)std::min<size_t>(todo.size(), (size_t)b200reg_handle::kBuildLanes);
-      for (int l = 0; l < n_lanes; ++l) {
-        auto& ln = h->lanes[l];
-        if (!ln.st) {
-          B200_CUDA_TRY(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-          B200_CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-        }
-        B200_CUDA_TRY(cudaStreamWaitEvent(ln.st, h->ev_fork, 0));
-      }
-      for (size_t k = 0; k < todo.size(); ++k) {
-        auto& ln = h->lanes[k % n_lanes];
-        CachedCloud& c = *todo[k];
-        if (do_align && (!c.has_ndt || c.ndt_res != res)) B200_CUDA_TRY(cache_build_ndt(ln.st, ln.grid, c, res));
-        if (with_fitness && !c.has_nn) B200_CUDA_TRY(cache_build_nn(ln.st, ln.nn, c));
-      }
-      for (int l = 0; l < n_lanes; ++l) {  // join
-        B200_CUDA_TRY(cudaEventRecord(h->lanes[l].done, h->lanes[l].st));
-        B200_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->lanes[l].done, 0));
-      }
-    }
-  }
-  // ---- jobs (pairs with an empty source never reach the kernel: PCL's initCompute fails, converged_ stays false)
-  B200_CUDA_TRY(h->pin_batch.reserve(n_pairs * (sizeof(NdtJob) + sizeof(FitJob) + sizeof(b200reg_result))));
-  NdtJob* hj = reinterpret_cast<NdtJob*>(h->pin_batch.p);
-  FitJob* hf = reinterpret_cast<FitJob*>(h->pin_batch.p + n_pairs * sizeof(NdtJob));
-  b200reg_result* hr = reinterpret_cast<b200reg_result*>(h->pin_batch.p + n_pairs * (sizeof(NdtJob) + sizeof(FitJob)));
-  B200_CUDA_TRY(h->jobs.reserve(n_pairs));
-  B200_CUDA_TRY(h->batch_results.reserve(n_pairs));
-  int n_jobs = 0;
-  std::vector<int> job_pair;
-  job_pair.reserve(n_pairs);
-  for (size_t i = 0; i < n_pairs; ++i) {
-    b200reg_result& r = hr[i];
-    memset(&r, 0, sizeof(r));
-    memcpy(r.transformation, pairs[i].guess, 64);
-    r.fitness = 1.7976931348623157e308;
-    if (src[i]->n == 0) continue;
-    NdtJob& j = hj[n_jobs];
-    memset(&j, 0, sizeof(j));
-    j.src = src[i]->pts.p;
-    j.n_src = src[i]->n;
-    j.grid = tgt[i]->ndt_view();
-    j.result = h->batch_results.p + i;
-    const float* g = pairs[i].guess;
-    for (int rr = 0; rr < 3; ++rr)
-      for (int c = 0; c < 4; ++c) j.guess[4 * rr + c] = g[4 * c + rr];
-    float eul[3];
-    euler_xyz_from_colmajor(g, eul);
-    j.p0[0] = g[12]; j.p0[1] = g[13]; j.p0[2] = g[14];
-    j.p0[3] = eul[0]; j.p0[4] = eul[1]; j.p0[5] = eul[2];
-    job_pair.push_back((int)i);
-    ++n_jobs;
-  }
-  B200_CUDA_TRY(cudaMemcpyAsync(h->batch_results.p, hr, n_pairs * sizeof(b200reg_result), cudaMemcpyHostToDevice, h->stream));
-  h->batch_align_ms = h->batch_fitness_ms = 0.0;
-  if (n_jobs && do_align) {
-    B200_CUDA_TRY(cudaMemcpyAsync(h->jobs.p, hj, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, h->stream));
-    // few pairs: several SMs cooperate on each; a full batch: one SM per registration, no grid-wide sync at all
-    int G = h->num_sm / n_jobs;
-    if (G < 1) {
-      // more pairs than SMs: the batch runs in rounds of num_sm / G registrations, and the last round is
-      // rarely full — 512 pairs on 148 SMs are 3.46 rounds of one-CTA registrations, i.e. 4.  Two or
-      // four CTAs per registration halve / quarter a registration's time and waste less of the last round
-      // (512 pairs: 7 rounds of half-length registrations = 3.5).  A group pays a barrier per pass (~1 %).
-      double best_cost = 0.0;
-      for (int g = 1; g <= 4; ++g) {
-        const int groups = h->num_sm / g;
-        const int rounds = (n_jobs + groups - 1) / groups;
-        const double cost = (double)rounds * (1.0 / g) * (g > 1 ? 1.02 : 1.0);
-        if (g == 1 || cost < best_cost * 0.97) { best_cost = cost; G = g; }
-      }
-    }
-    const int n_groups = h->num_sm / G;
-    B200_CUDA_TRY(h->partials.reserve((size_t)n_groups * 2 * G * kAccStride));
-    if ((rc = ensure_barriers(h, (size_t)(n_groups + 1) * 32))) return rc;
-    if ((rc = drain_events(h))) return rc;
-    if ((rc = begin_timed_launch(h))) return rc;
-    // more pairs than SMs: CTAs work through target runs and steal at the end (see NdtTargetQueue)
-    NdtTargetQueue tq{nullptr, nullptr, 0};
-    if (G == 1 && n_jobs > n_groups) {
-      std::vector<uint2> runs;
-      for (int j = 0; j < n_jobs; ++j) {
-        if (j > 0 && hj[j].grid.table == hj[j - 1].grid.table) runs.back().y += 1u;
-        else runs.push_back(make_uint2((unsigned)j, 1u));
-      }
-      B200_CUDA_TRY(h->pin_runs.reserve(runs.size()));
-      memcpy(h->pin_runs.p, runs.data(), runs.size() * sizeof(uint2));
-      B200_CUDA_TRY(h->tq_runs.reserve(runs.size()));
-      B200_CUDA_TRY(h->tq_next.reserve(runs.size()));
-      B200_CUDA_TRY(cudaMemcpyAsync(h->tq_runs.p, h->pin_runs.p, runs.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
-      B200_CUDA_TRY(cudaMemsetAsync(h->tq_next.p, 0, runs.size() * sizeof(unsigned int), h->stream));
-      tq.runs = h->tq_runs.p; tq.next = h->tq_next.p; tq.n_runs = (int)runs.size();
-    }
-    B200_CUDA_TRY(launch_ndt_mode(h, n_jobs, G, n_groups, nullptr, tq));
-    launch_counter() += 1;
-    if ((rc = end_timed_launch(h))) return rc;
-  }
-  // ---- getFitnessScore(max_range) for every pair, in chunks that bound the d2 scratch
-  cudaEvent_t evf0 = nullptr, evf1 = nullptr;
-  if (with_fitness && n_jobs) {
-    const float max_d2 = fitness_max_range >= 3.0e38 ? 3.402823466e+38f : (float)fitness_max_range * 1.0001f + 1e-6f;
-    const long long kChunkPoints = 32ll << 20;
-    B200_CUDA_TRY(h->fit_jobs.reserve(n_jobs));
-    B200_CUDA_TRY(h->batch_n_pending.reserve(2));
-    if (h->timing) { B200_CUDA_TRY(cudaEventCreate(&evf0)); B200_CUDA_TRY(cudaEventCreate(&evf1)); B200_CUDA_TRY(cudaEventRecord(evf0, h->stream)); }
-    int j0 = 0;
-    while (j0 < n_jobs) {
-      long long pts = 0;
-      int j1 = j0, max_n = 0;
-      while (j1 < n_jobs && j1 - j0 < 65535 && (j1 == j0 || pts + src[job_pair[j1]]->n <= kChunkPoints)) {
-        const int i = job_pair[j1];
-        FitJob& f = hf[j1];
-        f.view = tgt[i]->nn_view();
-        f.src = src[i]->pts.p;
-        f.n_src = src[i]->n;
-        f.result = i;
-        f.d2_offset = pts;
-        pts += src[i]->n;
-        if (src[i]->n > max_n) max_n = src[i]->n;
-        ++j1;
-      }
-      const int nj = j1 - j0;
-      B200_CUDA_TRY(h->batch_d2.reserve((size_t)pts));
-      B200_CUDA_TRY(h->batch_pending.reserve((size_t)pts));
-      B200_CUDA_TRY(h->batch_pending2.reserve((size_t)pts));
-      B200_CUDA_TRY(cudaMemcpyAsync(h->fit_jobs.p + j0, hf + j0, (size_t)nj * sizeof(FitJob), cudaMemcpyHostToDevice, h->stream));
-      B200_CUDA_TRY(cudaMemsetAsync(h->batch_n_pending.p, 0, 2 * sizeof(unsigned int), h->stream));
-      launch_counter() += 4;
-      k_nn_search_batch<<<dim3((max_n + 255) / 256, nj), 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, max_d2, h->batch_d2.p, h->batch_pending.p, h->batch_n_pending.p);
-      k_nn_far_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending.p, h->batch_n_pending.p, max_d2, h->batch_d2.p, h->batch_pending2.p,
-                                                         h->batch_n_pending.p + 1);
-      k_nn_bruteforce_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending2.p, h->batch_n_pending.p + 1, h->batch_d2.p);
-      k_fitness_batch<<<nj, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_d2.p, fitness_max_range, h->batch_results.p);
-      B200_CUDA_TRY(cudaGetLastError());
-      j0 = j1;
-    }
-    if (h->timing) B200_CUDA_TRY(cudaEventRecord(evf1, h->stream));
-  }
-  if (keep_on_device) {
-    if (evf0) { cudaEventDestroy(evf0); cudaEventDestroy(evf1); }
-    return B200REG_OK;
-  }
-  B200_CUDA_TRY(cudaMemcpyAsync(hr, h->batch_results.p, n_pairs * sizeof(b200reg_result), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  memcpy(results, hr, n_pairs * sizeof(b200reg_result));
-  if (!with_fitness)
-    for (size_t i = 0; i < n_pairs; ++i) results[i].fitness = 1.7976931348623157e308;
-  if (h->timing && n_jobs && do_align) {
-    const double before = h->align_ms;
-    if ((rc = drain_events(h))) return rc;
-    h->batch_align_ms = h->align_ms - before;
-    if (evf0) {
-      float ms = 0.f;
-      B200_CUDA_TRY(cudaEventElapsedTime(&ms, evf0, evf1));
-      h->batch_fitness_ms = (double)ms;
-    }
-  }
-  if (evf0) { cudaEventDestroy(evf0); cudaEventDestroy(evf1); }
-  return B200REG_OK;
-}
-
-int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
-  return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, results);
-}
-
-// internal (not in include/b200reg.h): the batch enqueued only, records left on the device — see b200reg_multi.cu
-int b200reg_internal_align_batch_device(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, size_t min_slots, b200reg_result** d_results) {
-  if (!d_results) return B200REG_E_INVALID;
-  if (!n_pairs) {  // a device without a share still takes part in the gather: it needs a send buffer
-    b200reg_pair none;
-    (void)none;
-    auto set_error = [&](const std::string& s) { h->err = s; };
-    if (!h) return B200REG_E_INVALID;
-    int rc = set_device(h);
-    if (rc) return rc;
-    B200_CUDA_TRY(h->batch_results.reserve(min_slots + 1));
-    *d_results = h->batch_results.p;
-    return B200REG_OK;
-  }
-  return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, nullptr, d_results, min_slots);
-}
-
-int b200reg_calc_fitness_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, double max_range, double* out) {
-  if (!h || (n_pairs && (!pairs || !out))) return B200REG_E_INVALID;
-  std::vector<b200reg_result> res(n_pairs);
-  const int rc = batch_run(h, pairs, n_pairs, 0, 1, max_range, res.data());
-  if (rc) return rc;
-  for (size_t i = 0; i < n_pairs; ++i) out[i] = res[i].fitness;
-  return B200REG_OK;
-}
-
-int b200reg_get_batch_timing(b200reg_handle* h, double* align_kernel_ms, double* fitness_ms) {
-  if (!h) return B200REG_E_INVALID;
-  if (align_kernel_ms) *align_kernel_ms = h->batch_align_ms;
-  if (fitness_ms) *fitness_ms = h->batch_fitness_ms;
-  return B200REG_OK;
-}
+#include "b200reg_api_batch.inl"
 
 #include "b200reg_api_map.inl"
 

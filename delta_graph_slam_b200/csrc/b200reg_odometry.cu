@@ -27,6 +27,10 @@
 #include "../../include/b200reg.h"
 #include "common.cuh"
 
+// internal to the library (b200reg_api.cu): b200reg_align in two halves
+extern "C" int b200reg_internal_align_begin(b200reg_handle* h, const float* guess, float* aligned_xyzw);
+extern "C" int b200reg_internal_align_end(b200reg_handle* h);
+
 namespace {
 
 inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -131,6 +135,7 @@ struct b200reg_odometry {
   long long n_hints = 0;
   // host wall clock spent inside matching(), by phase (b200reg_frontend_get_timing): {set source, align launch -> result, keyframe promotion}
   double t_source = 0.0, t_align = 0.0, t_promote = 0.0;
+  double pend_stamp = 0.0, pend_dist_before = 0.0, pend_t1 = 0.0;  // matching_begin .. matching_end
   long long n_match = 0, n_promote = 0;
 };
 
@@ -177,7 +182,11 @@ int b200reg_odometry_reset(b200reg_odometry* o) {
 // matching(stamp, cloud): the cloud is the odometry nodelet's input (the prefiltered scan); `device` != 0 means xyzw is
 // a device pointer on the registration handle's GPU.  guess_delta16 (column-major, may be NULL = identity) is the
 // msf / robot-odometry delta the reference multiplies onto prev_trans (:190-214).
-static int matching_impl(b200reg_odometry* o, double stamp, const float* xyzw, size_t n, size_t stride, int device, const float* guess_delta16, float* aligned_out, float* odom16) {
+// matching() in two halves: _begin runs the state machine up to the launch of the registration, _end takes the result
+// and finishes the frame.  *finished = true: the frame needed no registration (first keyframe) or failed early, odom16 is
+// final and _end must not be called.
+static int matching_begin(b200reg_odometry* o, double stamp, const float* xyzw, size_t n, size_t stride, int device, const float* guess_delta16, float* aligned_out, float* odom16, bool* finished) {
+  *finished = true;
   if (!o || !odom16 || (n && !xyzw)) return B200REG_E_INVALID;
   b200reg_handle* reg = o->reg;
   auto fail = [&](int rc) {
@@ -212,20 +221,35 @@ static int matching_impl(b200reg_odometry* o, double stamp, const float* xyzw, s
   // scheduling hint for the engine (not part of the reference's logic, never changes a result): when the motion since the
   // keyframe says this scan will probably become the next keyframe, its target structures are built on a side stream
   // while it is being aligned, and the promotion below only swaps them in
-  const double dist_before = (double)norm3(o->prev_trans);
-  if (o->prepare_promotion == 2 || (o->prepare_promotion == 1 && dist_before + o->last_step > 0.95 * o->cfg.keyframe_delta_trans)) {
+  o->pend_dist_before = (double)norm3(o->prev_trans);
+  if (o->prepare_promotion == 2 || (o->prepare_promotion == 1 && o->pend_dist_before + o->last_step > 0.95 * o->cfg.keyframe_delta_trans)) {
     b200reg_prepare_promotion(reg);
     o->n_hints += 1;
   }
-  rc = b200reg_align(reg, g16, aligned_out);
+  rc = b200reg_internal_align_begin(reg, g16, aligned_out);
   if (rc == B200REG_E_STATE) {  // PCL logs and returns with converged_ == false
     o->last_converged = 0;
     to_colmajor(mul4(o->keyframe_pose, o->prev_trans), odom16);
     return B200REG_OK;
   }
   if (rc != B200REG_OK) return fail(rc);
+  o->pend_stamp = stamp;
+  o->pend_t1 = t1;
+  *finished = false;
+  return B200REG_OK;
+}
+
+static int matching_end(b200reg_odometry* o, float* odom16) {
+  b200reg_handle* reg = o->reg;
+  auto fail = [&](int rc) {
+    o->err = b200reg_last_error(reg);
+    return rc;
+  };
+  const double stamp = o->pend_stamp, dist_before = o->pend_dist_before;
+  int rc = b200reg_internal_align_end(reg);
+  if (rc != B200REG_OK) return fail(rc);
   if ((rc = b200reg_get_result(reg, &o->last)) != B200REG_OK) return fail(rc);
-  o->t_align += now_us() - t1;
+  o->t_align += now_us() - o->pend_t1;
   o->last_converged = o->last.converged;
   if (!o->last.converged) {  // "scan matching has not converged!! ignore this frame": state untouched (:222-226)
     to_colmajor(mul4(o->keyframe_pose, o->prev_trans), odom16);
@@ -264,6 +288,13 @@ static int matching_impl(b200reg_odometry* o, double stamp, const float* xyzw, s
   }
   to_colmajor(odom, odom16);
   return B200REG_OK;
+}
+
+static int matching_impl(b200reg_odometry* o, double stamp, const float* xyzw, size_t n, size_t stride, int device, const float* guess_delta16, float* aligned_out, float* odom16) {
+  bool finished = true;
+  const int rc = matching_begin(o, stamp, xyzw, n, stride, device, guess_delta16, aligned_out, odom16, &finished);
+  if (rc != B200REG_OK || finished) return rc;
+  return matching_end(o, odom16);
 }
 
 int b200reg_odometry_matching(b200reg_odometry* o, double stamp, const float* xyzw, size_t n, size_t stride_bytes, const float* guess_delta16, float* aligned_xyzw, float* odom16) {
@@ -336,7 +367,7 @@ void b200reg_frontend_default_config(b200reg_frontend_config* c) {
   c->use_distance_filter = 1;       // the gate runs on every scan [REF :150]
   c->distance_near_thresh = 1.0;    // [REF :101-102]
   c->distance_far_thresh = 100.0;
-  c->filter_sms = 40;
+  c->filter_sms = 52;  // 36 CTAs for the filter's sort: 16 keys per thread of an HDL-64 scan (32 CTAs and fewer need 32), see DESIGN 5c
   c->prepare_promotion = 0;
   c->side_sms = 16;
 }
@@ -463,13 +494,21 @@ static int fe_step(b200reg_frontend* fe, double next_stamp, const float* next_xy
   const float* host_cloud = fe->host_out_in_flight;
   fe->n_last_filtered = n;
   if (n_filtered) *n_filtered = n;
-  if (next_xyzw || next_n) {
-    if ((rc = fe_begin(fe, next_stamp, next_xyzw, next_n, next_stride, next_device, next_filtered_out, next_filtered_cap))) return rc;
-  }
-  fe->t_begin_next += now_us() - t1;
-  if (host_cloud) rc = matching_impl(fe->odo, stamp, host_cloud, n, 16, 0, nullptr, aligned_out, odom16);
-  else rc = matching_impl(fe->odo, stamp, fe->d_out[cur], n, 16, 1, nullptr, aligned_out, odom16);
+  // the registration of this scan is launched first; the next scan's filter is enqueued while it runs (the host work of
+  // that — ~11 us of launches — used to sit in front of the registration on the frame's critical path)
+  bool finished = true;
+  if (host_cloud) rc = matching_begin(fe->odo, stamp, host_cloud, n, 16, 0, nullptr, aligned_out, odom16, &finished);
+  else rc = matching_begin(fe->odo, stamp, fe->d_out[cur], n, 16, 1, nullptr, aligned_out, odom16, &finished);
   if (rc != B200REG_OK) { fe->err = b200reg_odometry_last_error(fe->odo); return rc; }
+  const double t2 = now_us();
+  int rc_next = B200REG_OK;
+  if (next_xyzw || next_n) rc_next = fe_begin(fe, next_stamp, next_xyzw, next_n, next_stride, next_device, next_filtered_out, next_filtered_cap);
+  fe->t_begin_next += now_us() - t2;
+  if (!finished) {
+    rc = matching_end(fe->odo, odom16);
+    if (rc != B200REG_OK) { fe->err = b200reg_odometry_last_error(fe->odo); return rc; }
+  }
+  if (rc_next != B200REG_OK) return rc_next;
   fe->t_step += now_us() - t0;
   fe->n_steps += 1;
   return B200REG_OK;

@@ -539,7 +539,6 @@ __global__ void __launch_bounds__(128) k_gicp_regularize(int n, int reg_method, 
 // ---- the alignment kernel -------------------------------------------------------------------------
 constexpr int kGicpThreads = 512;
 constexpr int kGicpWarps = kGicpThreads / 32;
-constexpr int kGicpQueryLanes = 4;  // lanes that share one source point's near search in a linearize pass
 constexpr int kGicpAcc = 29;  // H upper triangle [21], b [6], sum of errors, correspondences
 constexpr int kGicpStride = 32;
 
@@ -552,6 +551,7 @@ struct GicpParams {
   double trans_eps, rot_eps;
   int max_iterations, lsq, lm_max_iterations;
   double lm_init_lambda_factor;
+  int query_lanes;    // lanes that share one source point's near search in a linearize pass: 1, 2 or 4
 };
 
 struct GicpJob {
@@ -858,15 +858,16 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
     // 32-point groups are dealt round-robin over the warps of all CTAs (like the NDT pass): source
     // points without a correspondence come in spatial clumps, and their far searches would otherwise
     // all land in a few CTAs while the rest of the grid waits at the group barrier
-    // linearize: kGicpQueryLanes lanes share a query in the near phase (nn_query_near_group), so a warp takes 32 /
-    // kGicpQueryLanes points; the error passes keep a point per lane.  Either way every point is visited once.
-    const int per_warp = phase == GP_LINEARIZE ? 32 / kGicpQueryLanes : 32;
+    // linearize: prm.query_lanes lanes share a query in the near phase (nn_query_near_group), so a warp takes 32 /
+    // query_lanes points; the error passes keep a point per lane.  Either way every point is visited once.
+    const int ql = prm.query_lanes;
+    const int per_warp = phase == GP_LINEARIZE ? 32 / ql : 32;
     const int n_groups = (n_src + per_warp - 1) / per_warp;
-    const int sub = lane % kGicpQueryLanes;
+    const int sub = lane % ql;
     const bool leader = phase != GP_LINEARIZE || sub == 0;
     for (int q0 = 0; q0 < n_groups; q0 += stride) {
       const int qg = q0 + warp * G + rank;
-      const int i = qg * per_warp + (phase == GP_LINEARIZE ? lane / kGicpQueryLanes : lane);
+      const int i = qg * per_warp + (phase == GP_LINEARIZE ? lane / ql : lane);
       const bool active = qg < n_groups && i < n_src;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) p = __ldg(job.src + i);
@@ -889,7 +890,9 @@ __global__ void __launch_bounds__(kGicpThreads, 1) k_gicp_align(const __grid_con
             best_idx = cp;
           }
         }
-        st = nn_query_near_group<kGicpQueryLanes, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, sub, active && grid_ok, best, best_idx);
+        if (ql == 4) st = nn_query_near_group<4, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, sub, active && grid_ok, best, best_idx);
+        else if (ql == 2) st = nn_query_near_group<2, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, sub, active && grid_ok, best, best_idx);
+        else if (active && grid_ok) st = nn_query_near<4, true>(job.tgt, gp, nn_make_query(gp, qx, qy, qz), prm.search_d2, best, best_idx);
         const bool ok = st == kNnDone;
         // queue slots in thread order (ballot compaction): the far points are always dealt to the same
         // warps, so the summation order — and with it the result — is reproducible bit for bit

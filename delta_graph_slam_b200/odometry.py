@@ -185,7 +185,7 @@ class FrontEnd:
     rest, so both are resident together.  The poses are those of the sequential loop
     (`for cloud: matching(stamp, downsample(cloud))`) run with the same SM budgets."""
 
-    def __init__(self, prefilter, odometry, out_bufs, filter_sms=40, total_sms=148, ror_bufs=None, side_sms=16):
+    def __init__(self, prefilter, odometry, out_bufs, filter_sms=52, total_sms=148, ror_bufs=None, side_sms=16):
         if len(out_bufs) < 3:
             raise ValueError("the pipelined front end needs three output clouds in rotation")
         self.prefilter, self.odometry, self.out_bufs = prefilter, odometry, list(out_bufs)
@@ -374,7 +374,7 @@ class NativeFrontEnd:
     module, without an interpreter between the kernels (the reference's nodelets are compiled C++).  `params` takes the
     two nodelets' parameter names (this module's classes document them)."""
 
-    def __init__(self, params=None, device=0, filter_sms=40, prepare_promotion=0, side_sms=16):
+    def __init__(self, params=None, device=0, filter_sms=52, prepare_promotion=0, side_sms=16):
         import ctypes as C
         from . import _lib
         p = dict(params or {})
