@@ -233,7 +233,7 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
       B200_CUDA_TRY(cudaMemcpyAsync(h->fit_jobs.p + j0, hf + j0, (size_t)nj * sizeof(FitJob), cudaMemcpyHostToDevice, h->stream));
       B200_CUDA_TRY(cudaMemsetAsync(h->batch_n_pending.p, 0, 2 * sizeof(unsigned int), h->stream));
       launch_counter() += 4;
-      k_nn_search_batch<<<dim3((max_n + 255) / 256, nj), 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, max_d2, h->batch_d2.p, h->batch_pending.p, h->batch_n_pending.p);
+      k_nn_search_batch<<<dim3((max_n + 256 / B200_FIT_LANES - 1) / (256 / B200_FIT_LANES), nj), 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, max_d2, h->batch_d2.p, h->batch_pending.p, h->batch_n_pending.p);
       k_nn_far_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending.p, h->batch_n_pending.p, max_d2, h->batch_d2.p, h->batch_pending2.p,
                                                          h->batch_n_pending.p + 1);
       k_nn_bruteforce_batch<<<kNumSM * 8, 256, 0, h->stream>>>(h->fit_jobs.p + j0, h->batch_results.p, h->batch_pending2.p, h->batch_n_pending.p + 1, h->batch_d2.p);

@@ -21,6 +21,9 @@
 #ifndef B200_FIT_DEPTH
 #define B200_FIT_DEPTH 4
 #endif
+#ifndef B200_FIT_LANES
+#define B200_FIT_LANES 1  // lanes per query of the batched near search.  Measured on the 4096-pair batch (fitness part of a step): 1 lane 65.3 ms, 2 lanes 67.4, 4 lanes 72.6 — unlike the GICP linearize pass the batch has queries for every thread, so sharing one only adds votes
+#endif
 #ifndef B200_FIT_MINB
 #define B200_FIT_MINB 6  // 40 registers: six resident CTAs per SM (measured: 15.8 ms per 1024 pairs; with the 66 registers ptxas picks when left alone, 18.6)
 #endif
@@ -110,22 +113,33 @@ __device__ __forceinline__ void fit_transform(const float* T, const float4 p, fl
 __global__ void __launch_bounds__(256, B200_FIT_MINB) k_nn_search_batch(const FitJob* __restrict__ jobs, const b200reg_result* __restrict__ results, float max_d2, float* __restrict__ d2_out,
                                                          uint2* __restrict__ pending, unsigned int* __restrict__ n_pending) {
   const FitJob& job = jobs[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= job.n_src) return;
+  constexpr int QL = B200_FIT_LANES;            // lanes that share one query (1 = a thread per query)
+  constexpr int PER_BLOCK = 256 / QL;
+  const int i = blockIdx.x * PER_BLOCK + threadIdx.x / QL;
+  if (blockIdx.x * PER_BLOCK >= job.n_src) return;
   __shared__ float T[16];
   __shared__ GridParams s_gp;  // the target's cell lattice, shared by the CTA instead of 20 registers per thread
   if (threadIdx.x < 16) T[threadIdx.x] = results[job.result].transformation[threadIdx.x];
   if (threadIdx.x >= 32 && threadIdx.x < 32 + (int)(sizeof(GridParams) / 4))
     reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(&job.view.meta->grid)[threadIdx.x - 32];
   __syncthreads();
-  if (i >= job.n_src) return;
+  const bool active = i < job.n_src;
+  if (QL == 1 && !active) return;
   const GridParams& gp = s_gp;
-  float qx, qy, qz;
-  fit_transform(T, __ldg(job.src + i), qx, qy, qz);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) fit_transform(T, __ldg(job.src + i), qx, qy, qz);
   float best = 3.402823466e+38f;
   int best_idx = kNoIndex;
   int st = kNnDone;
-  if (job.view.n > 0 && gp.any && !gp.overflow) st = nn_query_near<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  const bool searchable = job.view.n > 0 && gp.any && !gp.overflow;
+  if (QL == 1) {
+    if (searchable) st = nn_query_near<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+  } else {
+    // QL lanes walk one query together (nn_query_near_group): the per-thread loops of a thread-per-query search have very
+    // different trip counts (ncu: 10 of 32 lanes active), a group's lanes share them
+    st = nn_query_near_group<(QL > 1 ? QL : 2), false>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, (int)(threadIdx.x % QL), active && searchable, best, best_idx);
+    if (!active || (threadIdx.x % QL) != 0) return;
+  }
   d2_out[job.d2_offset + i] = best_idx != kNoIndex ? best : kNoNeighbour;
   if (st != kNnDone) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)i | (st == kNnBail ? kBailFlag : 0u));
 }
