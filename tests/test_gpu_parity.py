@@ -83,6 +83,56 @@ def test_voxelgrid_edge_cases(eng, oracle):
     assert len(out) == len(ref["out"]) and np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
 
 
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
+def test_voxelgrid_edge_cases_on_every_sort_path(eng, oracle, path):
+    """The ragged and degenerate clouds through each sort path (0 default, 1 three launches per digit, 2 one-sweep with the
+    gather in its last pass, 3 cooperative): sizes around the tile and warp boundaries of the one-sweep passes (2048-key
+    tiles, 256-record centroid tiles), a cloud whose points all share ONE voxel (no significant key bit: the one-sweep
+    path's forced first pass), one voxel holding thousands of points (a run across many centroid tiles), NaN rows, the
+    distance gate letting nothing through, and PCL's leaf-too-small copy."""
+    from delta_graph_slam_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(17 + path)
+    try:
+        assert L.b200reg_set_sort_path(path) == 0
+        vg = eng.VoxelGrid()
+        for n in (1, 2, 31, 32, 33, 255, 256, 257, 2047, 2048, 2049, 4097, 6000):
+            pts = np.ones((n, 4), np.float32)
+            pts[:, :3] = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+            if n > 40:
+                pts[::13, 2] = np.nan
+            vg.setLeafSize(0.3, 0.3, 0.3)
+            vg.setInputCloud(pts, is_dense=False)
+            ref = oracle.voxelgrid(pts, 0.3, is_dense=False)
+            out = vg.filter()
+            assert len(out) == len(ref["out"]) and np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32)), n
+        # all points in one voxel
+        one = np.ones((5000, 4), np.float32)
+        one[:, :3] = rng.uniform(0.01, 0.09, (5000, 3)).astype(np.float32)
+        vg.setLeafSize(0.1, 0.1, 0.1)
+        vg.setInputCloud(one, is_dense=True)
+        ref = oracle.voxelgrid(one, 0.1, is_dense=True)
+        out = vg.filter()
+        assert len(ref["out"]) == 1 and np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+        # one crowded voxel among sparse ones: its run spans many 256-record tiles
+        mix = np.ones((9000, 4), np.float32)
+        mix[:, :3] = rng.uniform(-20, 20, (9000, 3)).astype(np.float32)
+        mix[1000:7000, :3] = rng.uniform(5.01, 5.09, (6000, 3)).astype(np.float32)
+        vg.setInputCloud(mix, is_dense=True)
+        ref = oracle.voxelgrid(mix, 0.1, is_dense=True)
+        out = vg.filter()
+        assert ref["count"].max() >= 6000 and np.array_equal(out.view(np.uint32), ref["out"].view(np.uint32))
+        # the gate lets nothing through; then PCL's leaf-too-small copy with the gate on
+        vg.setDistanceFilter(True, 500.0, 600.0)
+        assert len(vg.filter()) == 0
+        vg.setDistanceFilter(True, 1.0, 100.0)
+        vg.setLeafSize(1e-4, 1e-4, 1e-4)
+        gated = oracle.distance_filter(mix, 1.0, 100.0)
+        assert np.array_equal(vg.filter().view(np.uint32), gated.view(np.uint32))
+    finally:
+        L.b200reg_set_sort_path(0)
+
+
 def test_ndt_target_grid(eng, oracle, scans):
     ref = oracle.Registration(oracle.NDT, resolution=1.0)
     ref.setInputTarget(scans["ds0"])
