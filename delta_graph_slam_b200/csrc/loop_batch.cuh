@@ -24,6 +24,9 @@
 #ifndef B200_FIT_LANES
 #define B200_FIT_LANES 1  // lanes per query of the batched near search.  Measured on the 4096-pair batch (fitness part of a step): 1 lane 65.3 ms, 2 lanes 67.4, 4 lanes 72.6 — unlike the GICP linearize pass the batch has queries for every thread, so sharing one only adds votes
 #endif
+#ifndef B200_FIT_COMPACT
+#define B200_FIT_COMPACT 1  // ring 1 of the batched near search on a compacted queue (k_nn_search_batch)
+#endif
 #ifndef B200_FIT_MINB
 #define B200_FIT_MINB 6  // 40 registers: six resident CTAs per SM (measured: 15.8 ms per 1024 pairs; with the 66 registers ptxas picks when left alone, 18.6)
 #endif
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(256, B200_FIT_MINB) k_nn_search_batch(const Fi
     reinterpret_cast<uint32_t*>(&s_gp)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(&job.view.meta->grid)[threadIdx.x - 32];
   __syncthreads();
   const bool active = i < job.n_src;
-  if (QL == 1 && !active) return;
+  if (QL == 1 && !B200_FIT_COMPACT && !active) return;
   const GridParams& gp = s_gp;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (active) fit_transform(T, __ldg(job.src + i), qx, qy, qz);
@@ -132,7 +135,41 @@ __global__ void __launch_bounds__(256, B200_FIT_MINB) k_nn_search_batch(const Fi
   int best_idx = kNoIndex;
   int st = kNnDone;
   const bool searchable = job.view.n > 0 && gp.any && !gp.overflow;
-  if (QL == 1) {
+  if (QL == 1 && B200_FIT_COMPACT) {
+    // ring 0 by every thread; the queries it leaves open are packed into a queue in shared memory and ring 1 is walked by
+    // the first threads of the block, one open query each: full warps instead of scattered lanes
+    __shared__ float4 s_q[256];   // transformed point, w = best so far
+    __shared__ int2 s_qi[256];    // (best index, source index)
+    __shared__ int s_wn[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool open = false;
+    if (active && searchable) open = !nn_near_ring0<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
+    const unsigned m = __ballot_sync(0xffffffffu, open);
+    if (lane == 0) s_wn[warp] = __popc(m);
+    if (active && !open) d2_out[job.d2_offset + i] = best_idx != kNoIndex ? best : kNoNeighbour;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) base += s_wn[w];
+      total += s_wn[w];
+    }
+    if (open) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      s_q[slot] = make_float4(qx, qy, qz, best);
+      s_qi[slot] = make_int2(best_idx, i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= total) return;
+    const float4 e = s_q[threadIdx.x];
+    const int2 ei = s_qi[threadIdx.x];
+    best = e.w;
+    best_idx = ei.x;
+    st = nn_near_ring1<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, e.x, e.y, e.z), max_d2, best, best_idx);
+    d2_out[job.d2_offset + ei.y] = best_idx != kNoIndex ? best : kNoNeighbour;
+    if (st != kNnDone) pending[atomicAdd(n_pending, 1u)] = make_uint2(blockIdx.y, (unsigned)ei.y);
+    return;
+  } else if (QL == 1) {
     if (searchable) st = nn_query_near<B200_FIT_DEPTH>(job.view, gp, nn_make_query(gp, qx, qy, qz), max_d2, best, best_idx);
   } else {
     // QL lanes walk one query together (nn_query_near_group): the per-thread loops of a thread-per-query search have very

@@ -244,6 +244,39 @@ __device__ __forceinline__ int nn_query_near(const NnView& g, const GridParams& 
   return nn_settled(gp, q, kNearRing + 1, best, max_d2) ? kNnDone : kNnOpen;
 }
 
+// nn_query_near in two steps, for kernels that compact the queries ring 0 left open before walking ring 1 (the lanes of a
+// thread-per-query warp otherwise idle while their neighbours walk on: ncu counted 10 of 32 lanes active in the batched
+// fitness search).  nn_near_ring0: the query's own cell; true = settled.  nn_near_ring1: the 26 neighbours, then the
+// same closing test as nn_query_near.  Same candidates, same (distance, index) order: the same exact neighbour.
+template <int DEPTH = 4>
+__device__ __forceinline__ bool nn_near_ring0(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, float& best, int& best_idx) {
+  best = 3.402823466e+38f;
+  best_idx = kNoIndex;
+  if (q.cx >= gp.min_b[0] && q.cx <= gp.max_b[0] && q.cy >= gp.min_b[1] && q.cy <= gp.max_b[1] && q.cz >= gp.min_b[2] && q.cz <= gp.max_b[2] &&
+      !(nn_box_d2(gp, q, q.cx, q.cy, q.cz) > fminf(best, max_d2)))
+    nn_scan_cell<DEPTH>(g, gp, q, q.cx, q.cy, q.cz, best, best_idx);
+  return nn_settled(gp, q, 1, best, max_d2);
+}
+template <int DEPTH = 4>
+__device__ __forceinline__ int nn_near_ring1(const NnView& g, const GridParams& gp, const NnQuery& q, float max_d2, float& best, int& best_idx) {
+  static_assert(kNearRing == 1, "ring 1 is the last ring of the near phase");
+  const int z0 = max(q.cz - 1, gp.min_b[2]), z1 = min(q.cz + 1, gp.max_b[2]);
+  const int y0 = max(q.cy - 1, gp.min_b[1]), y1 = min(q.cy + 1, gp.max_b[1]);
+  for (int iz = z0; iz <= z1; ++iz) {
+    const bool zface = (iz == q.cz - 1) || (iz == q.cz + 1);
+    for (int iy = y0; iy <= y1; ++iy) {
+      const bool face = zface || (iy == q.cy - 1) || (iy == q.cy + 1);
+      const int xstep = face ? 1 : 2;
+      for (int ix = q.cx - 1; ix <= q.cx + 1; ix += xstep) {
+        if (ix < gp.min_b[0] || ix > gp.max_b[0]) continue;
+        if (nn_box_d2(gp, q, ix, iy, iz) > fminf(best, max_d2)) continue;
+        nn_scan_cell<DEPTH>(g, gp, q, ix, iy, iz, best, best_idx);
+      }
+    }
+  }
+  return nn_settled(gp, q, kNearRing + 1, best, max_d2) ? kNnDone : kNnOpen;
+}
+
 // The near phase for ONE query by a group of LANES adjacent lanes (2, 4 or 8; all 32 lanes of the warp call it, `sub` =
 // lane % LANES, `active` false for a group without a query).  A thread-per-query walk of rings 0..1 is a chain of
 // dependent L2 round trips — hash slot, then the cell's points, cell after cell — and a pass of k_gicp_align over a
