@@ -853,6 +853,8 @@ def main():
              "frac": round(d["roofline"]["frac"], 4)}
         if d.get("e2e_fused"):
             b["e2e_fused"] = round(d["e2e_fused"]["value"], 1)
+        if d.get("e2e_new_keyframes_only"):
+            b["e2e_new_keyframes_only"] = round(d["e2e_new_keyframes_only"]["value"], 1)
         st = d.get("stats", {})
         for k in ("align_ms", "fitness_ms", "other_ms"):
             if k in st:
