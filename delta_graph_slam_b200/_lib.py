@@ -37,7 +37,7 @@ EXPORTS = [
     "b200reg_statistical_outlier_removal", "b200reg_statistical_outlier_removal_device", "b200reg_statistical_outlier_removal_begin", "b200reg_statistical_outlier_removal_device_begin",
     "b200reg_statistical_outlier_removal_end", "b200reg_statistical_last_stats",
     "b200reg_flat_filter", "b200reg_flat_filter_device", "b200reg_flat_filter_begin", "b200reg_flat_filter_device_begin", "b200reg_flat_filter_end", "b200reg_flat_filter_last_nz",
-    "b200reg_cloud_put", "b200reg_cloud_sync", "b200reg_cloud_put_device", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
+    "b200reg_cloud_put", "b200reg_cloud_sync", "b200reg_cloud_put_device", "b200reg_set_source_cached", "b200reg_set_target_cached", "b200reg_cloud_drop", "b200reg_cloud_clear", "b200reg_cloud_count", "b200reg_align_batch", "b200reg_calc_fitness_batch", "b200reg_get_batch_timing",
     "b200reg_map_cloud", "b200reg_map_cloud_cached",
     "b200reg_batch_create", "b200reg_batch_destroy", "b200reg_batch_last_error", "b200reg_batch_cloud_put", "b200reg_batch_cloud_drop", "b200reg_batch_run", "b200reg_batch_get_info",
     "b200reg_ndt_num_leaves", "b200reg_ndt_get_leaves", "b200reg_ndt_derivatives", "b200reg_set_timing", "b200reg_get_counters", "b200reg_get_profile", "b200reg_set_profile", "b200reg_get_trace", "b200reg_set_sort_path", "b200reg_get_nn_stats", "b200reg_get_stream",
@@ -184,6 +184,8 @@ def load():
     L.b200reg_voxelgrid_last_layout.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.POINTER(C.c_int)]
     L.b200reg_cloud_put.argtypes = [vp, C.c_int64, vp, C.c_size_t, C.c_size_t]
     L.b200reg_cloud_put_device.argtypes = [vp, C.c_int64, vp, C.c_size_t]
+    L.b200reg_set_source_cached.argtypes = [vp, C.c_int64]
+    L.b200reg_set_target_cached.argtypes = [vp, C.c_int64]
     L.b200reg_cloud_drop.argtypes = [vp, C.c_int64]
     L.b200reg_cloud_sync.argtypes = [vp]
     L.b200reg_cloud_clear.argtypes = [vp]

@@ -519,7 +519,7 @@ int run_ndt_single(b200reg_handle* h, const float* guess_colmajor, const double*
 }
 
 // ---- FAST_GICP ---------------------------------------------------------------------------------
-cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const float4* pts, int n, double* covs) {
+cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnView& nnv, const float4* pts, int n, double* covs) {
   if (n <= 0) return cudaSuccess;
   const int k = h->cfg.correspondence_randomness, reg = h->cfg.regularization;
   cudaError_t e;
@@ -528,8 +528,8 @@ cudaError_t launch_gicp_covariances(b200reg_handle* h, const NnGrid& nn, const f
   if ((e = cudaMemsetAsync(h->gicp_n_pending.p, 0, sizeof(unsigned int), h->stream)) != cudaSuccess) return e;
   const int blocks = (n + 7) / 8;  // one warp per query, 8 warps per CTA
   launch_counter() += 3;
-  k_gicp_knn<kKnnCovariance><<<blocks, 256, 0, h->stream>>>(nn.view(), pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
-  k_gicp_knn_brute<kKnnCovariance><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(nn.view(), pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
+  k_gicp_knn<kKnnCovariance><<<blocks, 256, 0, h->stream>>>(nnv, pts, n, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
+  k_gicp_knn_brute<kKnnCovariance><<<kNumSM * 2, kBruteWarps * 32, 0, h->stream>>>(nnv, pts, k, covs, h->gicp_pending.p, h->gicp_n_pending.p, nullptr);
   k_gicp_regularize<<<(n + 127) / 128, 128, 0, h->stream>>>(n, reg, covs);
   return cudaGetLastError();
 }
@@ -542,7 +542,7 @@ int ensure_gicp_structures(b200reg_handle* h) {
   if (h->cfg.correspondence_randomness > 32) { h->err = "reg_correspondence_randomness above 32 is not supported by the device k-NN (one neighbour per warp lane)"; return B200REG_E_INVALID; }
   if (!h->cov_tgt_ok) {
     B200_CUDA_TRY(h->cov_tgt.reserve((size_t)h->n_tgt * 6));
-    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn, h->tgt.p, h->n_tgt, h->cov_tgt.p));
+    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn.view(), h->tgt.p, h->n_tgt, h->cov_tgt.p));
     h->cov_tgt_ok = true;
   }
   if (!h->cov_src_ok) {
@@ -551,7 +551,7 @@ int ensure_gicp_structures(b200reg_handle* h) {
       h->nn_src_stale = false;
     }
     B200_CUDA_TRY(h->cov_src.reserve((size_t)(h->n_src > 0 ? h->n_src : 1) * 6));
-    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn_src, h->src.p, h->n_src, h->cov_src.p));
+    B200_CUDA_TRY(launch_gicp_covariances(h, h->nn_src.view(), h->src.p, h->n_src, h->cov_src.p));
     h->cov_src_ok = true;
   }
   return B200REG_OK;

@@ -266,6 +266,54 @@ static int batch_run(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pair
   return B200REG_OK;
 }
 
+// ---- cached clouds as the source / target of a plain align (the serial loop of a FAST_GICP LoopDetector) -----------------
+// A candidate keyframe is registered against many new keyframes over a run [REF include/hdl_graph_slam/loop_detector.hpp:
+// 83-111,124-156]; with its cloud in the cache (b200reg_cloud_put) a FAST_GICP handle computes its covariances — NN lattice,
+// k-NN, regularisation: ~0.4 ms per 48 k-point cloud, more than the upload — once in the keyframe's life instead of once
+// per pair.  Same kernels on the same cloud: the registration is bit-identical to b200reg_set_source(cloud) + align.
+static int cached_covariances(b200reg_handle* h, CachedCloud& c) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  const int k = h->cfg.correspondence_randomness, reg = h->cfg.regularization;
+  if (c.has_cov && c.cov_k == k && c.cov_reg == reg) return B200REG_OK;
+  if (k > 32) { h->err = "reg_correspondence_randomness above 32 is not supported by the device k-NN (one neighbour per warp lane)"; return B200REG_E_INVALID; }
+  if (!c.has_nn) B200_CUDA_TRY(cache_build_nn(h->stream, h->nn_src, c));  // nn_src serves as the builder: its own view goes stale
+  h->nn_src_stale = true;
+  B200_CUDA_TRY(c.cov.reserve((size_t)(c.n > 0 ? c.n : 1) * 6));
+  B200_CUDA_TRY(launch_gicp_covariances(h, c.nn_view(), c.pts.p, c.n, c.cov.p));
+  c.has_cov = true; c.cov_k = k; c.cov_reg = reg;
+  return B200REG_OK;
+}
+
+int b200reg_set_source_cached(b200reg_handle* h, int64_t id) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  CachedCloud* c = cache_find(h, (long long)id);
+  if (!c) { h->err = "set_source_cached: cloud id " + std::to_string((long long)id) + " was never put"; return B200REG_E_INVALID; }
+  int rc = b200reg_set_source_device(h, reinterpret_cast<const float*>(c->pts.p), (size_t)c->n);
+  if (rc) return rc;
+  if (h->cfg.method != B200REG_METHOD_GICP || c->n == 0) return B200REG_OK;
+  if ((rc = cached_covariances(h, *c))) return rc;
+  B200_CUDA_TRY(h->cov_src.reserve((size_t)c->n * 6));
+  B200_CUDA_TRY(cudaMemcpyAsync(h->cov_src.p, c->cov.p, (size_t)c->n * 48, cudaMemcpyDeviceToDevice, h->stream));
+  h->cov_src_ok = true;
+  return B200REG_OK;
+}
+
+int b200reg_set_target_cached(b200reg_handle* h, int64_t id) {
+  auto set_error = [&](const std::string& s) { h->err = s; };
+  if (!h) return B200REG_E_INVALID;
+  CachedCloud* c = cache_find(h, (long long)id);
+  if (!c) { h->err = "set_target_cached: cloud id " + std::to_string((long long)id) + " was never put"; return B200REG_E_INVALID; }
+  int rc = b200reg_set_target_device(h, reinterpret_cast<const float*>(c->pts.p), (size_t)c->n);
+  if (rc) return rc;
+  if (h->cfg.method != B200REG_METHOD_GICP || c->n == 0) return B200REG_OK;
+  if ((rc = cached_covariances(h, *c))) return rc;
+  B200_CUDA_TRY(h->cov_tgt.reserve((size_t)c->n * 6));
+  B200_CUDA_TRY(cudaMemcpyAsync(h->cov_tgt.p, c->cov.p, (size_t)c->n * 48, cudaMemcpyDeviceToDevice, h->stream));
+  h->cov_tgt_ok = true;
+  return B200REG_OK;
+}
+
 int b200reg_align_batch(b200reg_handle* h, const b200reg_pair* pairs, size_t n_pairs, int with_fitness, double fitness_max_range, b200reg_result* results) {
   return batch_run(h, pairs, n_pairs, 1, with_fitness, fitness_max_range, results);
 }

@@ -50,8 +50,14 @@ struct CachedCloud {
   DevBuf<SortMeta> nn_meta;
   DevBuf<uint32_t> nn_occ;
   uint32_t nn_cap = 0;
+  // FAST_GICP product: regularised covariances of the cloud's points (k nearest neighbours), 6 doubles per point
+  bool has_cov = false;
+  int cov_k = 0, cov_reg = 0;
+  DevBuf<double> cov;
 
   void release() {
+    cov.release();
+    has_cov = false;
     pts.release(); voxels.release(); centroids.release(); table.release(); gmeta.release(); meta.release();
     nn_pts.release(); nn_table.release(); nn_meta.release(); nn_occ.release();
     has_ndt = has_nn = false;

@@ -151,11 +151,25 @@ class LoopDetector:
             res = reg.alignBatch([(new_keyframe.id, c.id, g) for c, g in zip(candidates, guesses)], with_fitness=True, fitness_max_range=self.fitness_score_max_range)
             return ([bool(r["converged"]) for r in res], [float(r["fitness"]) for r in res],
                     [np.array(r["transformation"], np.float32).reshape(4, 4).T.copy() for r in res])
-        # the reference's serial sequence on a plain pcl::Registration surface
-        reg.setInputTarget(new_keyframe.cloud)
+        # the reference's serial sequence [REF include/hdl_graph_slam/loop_detector.hpp:124-156].  On an engine handle (FAST_GICP:
+        # the launch file's loop detector) the clouds come from the keyframe cache: no upload per pair, and a keyframe's
+        # covariances are computed once in its life (b200reg_set_source_cached); on a plain pcl::Registration surface the
+        # clouds are handed over as the reference does
+        cached = hasattr(reg, "setInputSourceCached") and hasattr(reg, "cloudPut")
+        if cached:
+            self._ensure_cached(new_keyframe)
+            for c in candidates:
+                self._ensure_cached(c)
+            self._evict({new_keyframe.id} | {c.id for c in candidates})
+            reg.setInputTargetCached(new_keyframe.id)
+        else:
+            reg.setInputTarget(new_keyframe.cloud)
         conv, scores, Ts = [], [], []
         for c, g in zip(candidates, guesses):
-            reg.setInputSource(c.cloud)
+            if cached:
+                reg.setInputSourceCached(c.id)
+            else:
+                reg.setInputSource(c.cloud)
             reg.align(g)
             scores.append(reg.getFitnessScore(self.fitness_score_max_range))
             conv.append(reg.hasConverged())

@@ -188,6 +188,16 @@ class Registration:
         """Wait until every cloud put so far has left the caller's (page-locked) memory."""
         self._ck(_lib.load().b200reg_cloud_sync(self._h))
 
+    def setInputSourceCached(self, cloud_id):
+        """setInputSource with a cloud of the keyframe cache (b200reg_set_source_cached): no upload, and on a FAST_GICP handle
+        the keyframe's covariances are computed once in its life instead of once per pair."""
+        self._ck(_lib.load().b200reg_set_source_cached(self._h, int(cloud_id)))
+        self._src_ref = None
+
+    def setInputTargetCached(self, cloud_id):
+        """setInputTarget with a cloud of the keyframe cache (b200reg_set_target_cached)."""
+        self._ck(_lib.load().b200reg_set_target_cached(self._h, int(cloud_id)))
+
     def cloudDrop(self, cloud_id):
         self._ck(_lib.load().b200reg_cloud_drop(self._h, int(cloud_id)))
 

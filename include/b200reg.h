@@ -275,6 +275,16 @@ typedef struct b200reg_pair {
 int b200reg_cloud_put(b200reg_handle* h, int64_t id, const float* xyzw, size_t n, size_t stride_bytes);
 int b200reg_cloud_sync(b200reg_handle* h);
 int b200reg_cloud_put_device(b200reg_handle* h, int64_t id, const float* d_xyzw, size_t n);
+/* A cached cloud as the source / target of a plain b200reg_align: the serial loop LoopDetector::matching runs when its
+ * registration object is not NDT — the launch file's loop detector uses FAST_GICP [REF launch/delta_graph_slam.launch:95;
+ * include/hdl_graph_slam/loop_detector.hpp:124-156: setInputTarget(new keyframe) once, then setInputSource(candidate) +
+ * align + getFitnessScore per candidate].  Equivalent to b200reg_set_source / _set_target with that keyframe's cloud (no
+ * upload: a device copy); on a FAST_GICP handle the cloud's covariances (k nearest neighbours + regularisation, what
+ * setInputSource / setInputTarget make fast_gicp compute lazily) are computed ONCE per cached keyframe and reused for
+ * every pair it takes part in — same kernels on the same cloud, so the registration is bit-identical.  They are kept for
+ * the handle's current correspondence_randomness / regularisation and recomputed when those change. */
+int b200reg_set_source_cached(b200reg_handle* h, int64_t id);
+int b200reg_set_target_cached(b200reg_handle* h, int64_t id);
 int b200reg_cloud_drop(b200reg_handle* h, int64_t id);
 int b200reg_cloud_clear(b200reg_handle* h);
 int b200reg_cloud_count(b200reg_handle* h, size_t* out);

@@ -183,7 +183,9 @@ def test_loop_detector_batch_equals_reference_serial_loop(eng, oracle, scenario)
 def test_loop_detector_with_fast_gicp_runs_the_serial_loop(eng, oracle, scenario):
     """registration_method FAST_GICP is what the launch file gives the loop detector [REF launch/delta_graph_slam.launch:95]:
     no batch path for it, so LoopDetector drives the handle through the reference's own sequence (setInputTarget once,
-    then setInputSource / align / getFitnessScore per candidate) and must agree with the oracle's FAST_GICP doing the same."""
+    then setInputSource / align / getFitnessScore per candidate) and must agree with the oracle's FAST_GICP doing the same.
+    The clouds come from the keyframe cache (b200reg_set_source_cached / _set_target_cached: no upload per pair, a
+    keyframe's covariances computed once in its life) — bit-identical to handing the clouds over one by one."""
     from delta_graph_slam_b200.loop_detector import KeyFrame, LoopDetector, isometry2d
     clouds, pairs = scenario["clouds"], scenario["pairs"]
     params = dict(distance_thresh=35.0, accum_distance_thresh=8.0, min_edge_interval=1.0, fitness_score_thresh=0.5, registration_method="FAST_GICP")
@@ -200,7 +202,22 @@ def test_loop_detector_with_fast_gicp_runs_the_serial_loop(eng, oracle, scenario
         old.append(KeyFrame(int(p["source_id"]), clouds[int(p["source_id"])], new_est @ g2, accum_distance=1.0))
     c0, s0, T0 = ld_ref.register_candidates(old, new)
     c1, s1, T1 = ld_gpu.register_candidates(old, new)
-    assert c0 == c1 and ld_gpu.registration.cloudCount() == 0
+    assert c0 == c1 and ld_gpu.registration.cloudCount() == len(old) + 1
+    # the same sequence with the clouds handed over per call on a fresh handle: same bits
+    plain = eng.select_registration_method(dict(registration_method="FAST_GICP"), out=io.StringIO())
+    plain.setInputTarget(new.cloud)
+    for c, conv, score, T in zip(old, c1, s1, T1):
+        from delta_graph_slam_b200.loop_detector import candidate_guess
+        plain.setInputSource(c.cloud)
+        plain.align(candidate_guess(new, c))
+        assert plain.hasConverged() == conv and plain.getFitnessScore(ld_gpu.fitness_score_max_range) == score
+        assert np.array_equal(plain.getFinalTransformation(), T)
+    # a second detection reuses the cached covariances of every keyframe: same bits again
+    c2, s2, T2 = ld_gpu.register_candidates(old, new)
+    assert c2 == c1 and s2 == s1 and all(np.array_equal(a, b) for a, b in zip(T1, T2))
+    # an id that was never put is an argument error, not a crash
+    with pytest.raises(eng.B200RegError):
+        ld_gpu.registration.setInputSourceCached(987654)
     for a, b, Ta, Tb in zip(s0, s1, T0, T1):
         assert np.max(np.abs(Ta[:3, 3] - Tb[:3, 3])) < TOL_T and rot_angle(Ta[:3, :3], Tb[:3, :3]) < TOL_R
         assert abs(a - b) <= TOL_FIT * abs(a)
