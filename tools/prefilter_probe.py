@@ -1,6 +1,5 @@
 """The whole prefilter nodelet per scan through HOST buffers (page-locked in / out): distance gate + VoxelGrid 0.1 m ->
 statistical outlier filter (20, 1.0) -> filtered3D, then height / normal / flatten -> filtered2D, next to the OpenMP oracle.
-Not run yet on a GPU (written after this round's GPU budget was spent): the first thing to run next round.
 python tools/prefilter_probe.py [n_scans]"""
 import json
 import os
