@@ -563,6 +563,9 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
     nchk = min(50, F)
     poses_dev = [last_dev["poses"][k] for k in range(nchk)]
     legs_equal = bool(np.array_equal(last_dev["poses"], last_dev["poses_host_pinned"]))
+    _dl = np.abs(np.asarray(last_dev["poses"], np.float64).reshape(F, -1) - np.asarray(last_dev["poses_host_pinned"], np.float64).reshape(F, -1)).max(axis=1)
+    legs_first_diff = int(np.nonzero(_dl)[0][0]) if np.any(_dl) else None
+    legs_max_delta = float(np.nanmax(_dl)) if len(_dl) else 0.0
     # the Python mirror (eng.FrontEnd over Prefilter + ScanMatchingOdometry: what the oracle parity tests drive), pipelined
     # and as the plain loop (filter, then match, one scan at a time), on the same SM budgets
     fe_c, _, _ = new_front_end(ds_bufs)
@@ -618,7 +621,7 @@ def bench_odometry(ctx, odom_params=None, frames=None, steps=None, warmup=None, 
                           "note": "a registration is a chain of dependent passes (each: point sweep, reduction across the SMs, optimiser step); the per-pass latency, not bandwidth, sets the kernel time — per-phase split in profiles/"},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
-        "checks": {"device_and_host_legs_bit_identical": bool(legs_equal), "python_mirror_pipelined_equals_sequential_first_frames": bool(pipeline_equal),
+        "checks": {"device_and_host_legs_bit_identical": bool(legs_equal), "legs_first_differing_frame": legs_first_diff, "legs_max_abs_pose_delta": legs_max_delta, "python_mirror_pipelined_equals_sequential_first_frames": bool(pipeline_equal),
                    "native_front_end_vs_python_mirror_max_pose_delta": float(mirror_dev), "frames_checked": nchk, "position_error_m_after_frames_checked": drift,
                    "wall_ms_per_step": 1e3 * wall_d / steps, "parity_vs_oracle": parity},
     }

@@ -57,6 +57,7 @@ struct b200reg_handle {
   VoxelSort vg_sort;
   DevBuf<uint32_t> vg_id, vg_count;
   DevBuf<float4> vg_sorted;  // the scan's points in sorted (voxel, input) order: k_vg_gather -> k_vg_centroids
+  bool defer_source_sync = false;  // b200reg_set_source of a page-locked cloud returns without waiting for the DMA (front end only)
   bool align_pending = false;  // b200reg_internal_align_begin .. _end
   float* align_aligned_out = nullptr;
   bool align_aligned_direct = false;
@@ -816,7 +817,9 @@ int b200reg_set_source(b200reg_handle* h, const float* xyzw, size_t n, size_t st
   int rc = set_device(h);
   if (rc) return rc;
   if ((rc = retire_spec(h))) return rc;
-  if ((rc = upload_cloud(h, xyzw, n, stride, h->src))) return rc;
+  // (defer_source_sync: the front end's filtered clouds stay valid until two scans later; the copy is ordered in front of the
+  // registration on the stream, and the host goes on to launch it instead of waiting for the DMA)
+  if ((rc = upload_cloud(h, xyzw, n, stride, h->src, /*defer_pinned=*/h->defer_source_sync))) return rc;
   h->n_src = (int)n;
   h->have_src = true;
   h->src_is_tgt = false;
@@ -985,6 +988,12 @@ int b200reg_internal_align_end(b200reg_handle* h) {
   if (aligned_xyzw) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
   if (aligned_xyzw && !h->align_aligned_direct) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  return B200REG_OK;
+}
+
+int b200reg_internal_set_defer_source_sync(b200reg_handle* h, int on) {
+  if (!h) return B200REG_E_INVALID;
+  h->defer_source_sync = on != 0;
   return B200REG_OK;
 }
 

@@ -30,6 +30,7 @@
 // internal to the library (b200reg_api.cu): b200reg_align in two halves
 extern "C" int b200reg_internal_align_begin(b200reg_handle* h, const float* guess, float* aligned_xyzw);
 extern "C" int b200reg_internal_align_end(b200reg_handle* h);
+extern "C" int b200reg_internal_set_defer_source_sync(b200reg_handle* h, int on);
 
 namespace {
 
@@ -406,6 +407,8 @@ int b200reg_frontend_create(const b200reg_frontend_config* cfg, b200reg_frontend
     b200reg_set_sm_budget(fe->reg, total - cfg->filter_sms);
     if (side) b200reg_set_side_budget(fe->reg, side);
   }
+  // the caller's filtered clouds rotate (>= 3) and stay valid until two scans later: setInputSource does not wait for its DMA
+  b200reg_internal_set_defer_source_sync(fe->reg, 1);
   *out = fe;
   return B200REG_OK;
 }

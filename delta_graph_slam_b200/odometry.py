@@ -478,6 +478,10 @@ class NativeFrontEnd:
         self._ck(self._L.b200reg_frontend_run_device(self._h, ptrs, ns, None, F, odom.ctypes.data, res.ctypes.data if want_results else None, nf.ctypes.data, C.byref(kf)))
         return odom.reshape(F, 4, 4).transpose(0, 2, 1).copy(), res, nf
 
+    def reset(self):
+        """Back to the state of a freshly created front end (b200reg_frontend_reset): no keyframe, nothing in flight."""
+        self._ck(self._L.b200reg_frontend_reset(self._h))
+
     def run_host(self, clouds, filtered_bufs=None, aligned_out=None, stamps=None):
         """Host scans one by one through begin / step.  filtered_bufs: three (M, 4) float32 host clouds in rotation
         (the two-nodelet form: filtered cloud to the host, uploaded again for the registration) or None (fused)."""
@@ -494,6 +498,7 @@ class NativeFrontEnd:
             return b.ctypes.data, len(b)
         if F == 0:
             return poses.reshape(0, 4, 4)
+        self.reset()  # a new sequence: first scan -> first keyframe (run_device resets inside the library)
         c0 = clouds[0]
         p0, cap0 = fb(0)
         self._ck(self._L.b200reg_frontend_begin(self._h, stamp(0), c0.ctypes.data, len(c0), 16, p0, cap0))

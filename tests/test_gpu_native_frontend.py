@@ -81,6 +81,8 @@ def test_native_front_end_host_scans(scans, python_mirror, form):
         bufs = [np.zeros((cap, 4), np.float32) for _ in range(3)]
     poses = fe.run_host(scans, filtered_bufs=bufs, aligned_out=aligned)
     check(poses, python_mirror)
+    # a second sequence through the same object starts from a clean state (first scan -> first keyframe): same poses again
+    assert np.array_equal(fe.run_host(scans, filtered_bufs=bufs, aligned_out=aligned), poses)
     if bufs is not None:  # the last scan's filtered cloud reached the caller, and `aligned` is the final transform applied to it
         from oracle import oracle_py as O
         k = FRAMES - 1
