@@ -369,6 +369,9 @@ int b200reg_odometry_get_state(b200reg_odometry* o, int* num_keyframes, int* las
  *   filtered_out != NULL  the reference's two nodelets: the filtered cloud lands in the caller's host cloud (the
  *                         /filtered_points message; a page-locked cloud is written by the filter kernel itself) and the
  *                         odometry side uploads it again, as setInputSource of a separate nodelet would;
+ *                         the cloud must stay valid and untouched until the _step that MATCHES that scan has returned (a
+ *                         page-locked cloud is read by DMA in front of the registration, without a host-side wait): hand
+ *                         in at least three clouds in rotation, as a message queue would hold them;
  *   filtered_out == NULL  fused: the filtered cloud stays on the device and reaches the registration by a device copy.
  * Device-resident scans (_begin_device / _step_device / _run_device) always take the fused form. */
 typedef struct b200reg_frontend_config {
@@ -378,7 +381,7 @@ typedef struct b200reg_frontend_config {
   double downsample_resolution;     /* prefilter VoxelGrid leaf, 0.1 [REF apps/prefiltering_nodelet.cpp:56-57] */
   int use_distance_filter;          /* 1: the gate runs on every scan, as the reference's cloud_callback does [REF :150] */
   double distance_near_thresh, distance_far_thresh; /* 1.0 / 100.0 [REF :101-102] */
-  int filter_sms;                   /* SMs of the prefilter handle's persistent kernel (the registration takes the rest); 0 = no split */
+  int filter_sms;                   /* SMs of the prefilter handle's persistent kernel (the registration takes the rest), 52; 0 = no split */
   int prepare_promotion;            /* scheduling only, results unchanged: 0 off; 1 build a scan's target structures on a side stream during
                                        its own registration when the motion so far says it will become the keyframe; 2 for every scan */
   int side_sms;                     /* SMs (out of filter_sms) of that side build's persistent sort kernel, 16 */
