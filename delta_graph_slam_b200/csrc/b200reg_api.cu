@@ -16,6 +16,7 @@
 #include <map>
 
 #include "gicp.cuh"
+#include "host_copy.hpp"
 #include "loop_batch.cuh"
 #include "map_cloud.cuh"
 #include "ndt_align.cuh"
@@ -232,7 +233,7 @@ int upload_cloud(b200reg_handle* h, const float* xyzw, size_t n, size_t stride_b
   }
   B200_CUDA_TRY(h->pin_in.reserve(n));
   if (stride_bytes == 16) {
-    memcpy(h->pin_in.p, xyzw, n * 16);
+    host_copy(h->pin_in.p, xyzw, n * 16);  // a pageable cloud: split over the copy pool (host_copy.hpp)
   } else {
     const unsigned char* b = (const unsigned char*)xyzw;
     for (size_t i = 0; i < n; ++i) {
@@ -987,7 +988,7 @@ int b200reg_internal_align_end(b200reg_handle* h) {
   float* aligned_xyzw = h->align_aligned_out;
   if (aligned_xyzw) B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
   if ((rc = fetch_result(h, aligned_xyzw != nullptr))) return rc;
-  if (aligned_xyzw && !h->align_aligned_direct) memcpy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
+  if (aligned_xyzw && !h->align_aligned_direct) host_copy(aligned_xyzw, h->pin_out.p, (size_t)h->n_src * 16);
   return B200REG_OK;
 }
 

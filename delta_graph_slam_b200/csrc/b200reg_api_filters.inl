@@ -75,7 +75,7 @@ int b200reg_voxelgrid_filter_begin(b200reg_handle* h, const float* xyzw, size_t 
     } else {
       B200_CUDA_TRY(h->pin_in.reserve(n));
       if (stride == 16) {
-        memcpy(h->pin_in.p, xyzw, n * 16);
+        host_copy(h->pin_in.p, xyzw, n * 16);
       } else {
         const unsigned char* b = (const unsigned char*)xyzw;
         for (size_t i = 0; i < n; ++i) {
@@ -115,7 +115,7 @@ int b200reg_voxelgrid_filter_host_to_device_begin(b200reg_handle* h, const float
     } else {
       B200_CUDA_TRY(h->pin_in.reserve(n));
       if (stride == 16) {
-        memcpy(h->pin_in.p, xyzw, n * 16);
+        host_copy(h->pin_in.p, xyzw, n * 16);
       } else {
         const unsigned char* b = (const unsigned char*)xyzw;
         for (size_t i = 0; i < n; ++i) {
@@ -156,7 +156,7 @@ int b200reg_voxelgrid_filter_end(b200reg_handle* h, size_t* n_out) {
     B200_CUDA_TRY(h->pin_out.reserve(m));
     B200_CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->stage_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    memcpy(pend.host_out, h->pin_out.p, m * 16);
+    host_copy(pend.host_out, h->pin_out.p, m * 16);
   }
   return B200REG_OK;
 }
@@ -379,7 +379,7 @@ int b200reg_radius_outlier_removal_end(b200reg_handle* h, size_t* n_out) {
   B200_CUDA_TRY(h->ror_pin_out.reserve(m));
   B200_CUDA_TRY(cudaMemcpyAsync(h->ror_pin_out.p, h->ror_out.p, m * 16, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  memcpy(pend.host_out, h->ror_pin_out.p, m * 16);
+  host_copy(pend.host_out, h->ror_pin_out.p, m * 16);
   return B200REG_OK;
 }
 
