@@ -168,6 +168,48 @@ def test_prefilter_mirror_reads_the_reference_parameters(monkeypatch):
     assert pre.filter is None and pre.distance_filter_on and pre._reg is pre.outlier_removal_filter._reg
 
 
+def test_prefilter_mirror_base_link_step_on_recorders(monkeypatch):
+    """The base_link step of cloud_callback [REF apps/prefiltering_nodelet.cpp:123-148] on recorders: the x / y translation
+    is zeroed before the matrix reaches the handle of the chain's FIRST stage, the remaining translation is the lidar
+    position, None switches the transform off, and a chain with no first stage to attach it to says so."""
+    import io
+    import delta_graph_slam_b200.odometry as odo
+    calls = []
+
+    class Handle:
+        def setInputTransform(self, m):
+            calls.append(None if m is None else np.array(m, np.float64).copy())
+
+    class Rec:
+        def __init__(self):
+            self._reg = Handle()
+
+        def __getattr__(self, attr):
+            return lambda *a, **k: None
+
+    monkeypatch.setattr(odo, "VoxelGrid", lambda device=0: Rec())
+    monkeypatch.setattr(odo, "StatisticalOutlierRemoval", lambda device=0, registration=None: Rec())
+    monkeypatch.setattr(odo, "RadiusOutlierRemoval", lambda device=0, registration=None: Rec())
+    m = base_link_transform(None)
+    pre = odo.Prefilter(LAUNCH, out=io.StringIO())
+    lidar = pre.setBaseLinkTransform(m)
+    assert np.array_equal(lidar, [0.0, 0.0, 1.9]) and np.array_equal(pre.lidar_position, lidar)
+    want = m.copy()
+    want[0, 3] = want[1, 3] = 0.0
+    assert len(calls) == 1 and np.array_equal(calls[0], want) and m[0, 3] == 0.8, "the caller's matrix is not modified"
+    assert np.array_equal(pre.setBaseLinkTransform(None), [0.0, 0.0, 0.0]) and calls[-1] is None
+    # down-sampling NONE: the stand-alone gate's handle (the outlier filter's) is the first stage
+    calls.clear()
+    pre = odo.Prefilter(dict(downsample_method="NONE", outlier_removal_method="RADIUS"), out=io.StringIO())
+    pre.setBaseLinkTransform(m)
+    assert len(calls) == 1 and np.array_equal(calls[0], want)
+    # neither a VoxelGrid nor the gate: nothing to attach the transform to
+    pre = odo.Prefilter(dict(downsample_method="NONE", outlier_removal_method="RADIUS", b200_skip_distance_filter=True), out=io.StringIO())
+    with pytest.raises(ValueError):
+        pre.setBaseLinkTransform(m)
+    assert np.array_equal(pre.setBaseLinkTransform(None), [0.0, 0.0, 0.0])
+
+
 def base_link_transform(rng):
     """a sensor -> base_link transform as tf would hand it over: tilted, yawed, mounted 1.9 m up and off-centre"""
     a, b, c = 0.03, -0.02, 0.7
