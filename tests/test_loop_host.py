@@ -141,6 +141,60 @@ def test_batch_path_is_ndt_only_and_the_keyframe_cache_is_bounded(oracle, scenar
     assert set(ld._cached) == {new.id, old[0].id, old[1].id, old[2].id}
 
 
+def test_serial_loop_of_a_gicp_handle_takes_its_clouds_from_the_keyframe_cache(oracle, scenario):
+    """An engine handle that has no batch path for its method but offers the cached setters (b200reg_set_source_cached /
+    _set_target_cached: a FAST_GICP handle) is driven through the reference's sequence [REF include/hdl_graph_slam/
+    loop_detector.hpp:124-156] with keyframe ids instead of clouds: every keyframe is put once, the new keyframe becomes
+    the target once, each candidate the source once, and the outcome is the plain serial loop's."""
+    from delta_graph_slam_b200 import _lib
+    clouds, pairs = scenario
+    log = []
+
+    class CachedGicpLike(OracleBatchEngine):
+        method = _lib.METHOD_GICP
+
+        def alignBatch(self, *a, **k):
+            raise AssertionError("the batch path must not be taken for a FAST_GICP handle")
+
+        def cloudPut(self, cid, cloud):
+            log.append(("put", int(cid)))
+            super().cloudPut(cid, cloud)
+
+        def cloudDrop(self, cid):
+            log.append(("drop", int(cid)))
+            del self.clouds[int(cid)]
+
+        def setInputTargetCached(self, cid):
+            log.append(("target", int(cid)))
+            self.reg.setInputTarget(self.clouds[int(cid)])
+
+        def setInputSourceCached(self, cid):
+            log.append(("source", int(cid)))
+            self.reg.setInputSource(self.clouds[int(cid)])
+
+        def setInputTarget(self, cloud):
+            raise AssertionError("clouds are not handed over when the handle has a keyframe cache")
+
+        setInputSource = setInputTarget
+
+        def __getattr__(self, name):
+            return getattr(self.reg, name)
+
+    old = [KeyFrame(int(p["source_id"]), clouds[int(p["source_id"])], isometry2d(0.4 * k, 0.0, 0.0), 1.0) for k, p in enumerate(pairs[:3])]
+    new = KeyFrame(0, clouds[0], isometry2d(0.5, 0.0, 0.0), 50.0)
+    params = dict(distance_thresh=5.0, accum_distance_thresh=8.0, min_edge_interval=5.0, fitness_score_thresh=10.0)
+    serial = LoopDetector(params, registration=oracle.Registration(oracle.NDT, resolution=1.0, nn_search=2, trans_eps=0.01, max_iter=64), out=io.StringIO())
+    cached = LoopDetector(dict(params, b200_max_cached_keyframes=3), registration=CachedGicpLike(oracle), out=io.StringIO())
+    c0, s0, T0 = serial.register_candidates(old[:2], new)
+    c1, s1, T1 = cached.register_candidates(old[:2], new)
+    assert c0 == c1 and s0 == s1 and all(np.array_equal(a, b) for a, b in zip(T0, T1))
+    assert log == [("put", new.id), ("put", old[0].id), ("put", old[1].id), ("target", new.id), ("source", old[0].id), ("source", old[1].id)]
+    # the second detection puts only the keyframe it has not seen and evicts the least recently used one above the cap
+    log.clear()
+    cached.register_candidates(old[2:3], new)
+    assert log == [("put", old[2].id), ("drop", old[0].id), ("target", new.id), ("source", old[2].id)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
