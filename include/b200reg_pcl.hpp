@@ -241,6 +241,10 @@ class VoxelGrid : public pcl::Filter<pcl::PointXYZ> {
   void setMinimumPointsNumberPerVoxel(unsigned n) { min_points_ = n; }
   // PrefilteringNodelet::distance_filter fused into this filter [REF apps/prefiltering_nodelet.cpp:100-102,275-291]
   void setDistanceFilter(bool use, double near_thresh, double far_thresh) { b200reg_set_distance_filter(h_, use ? 1 : 0, near_thresh, far_thresh); }
+  // the base_link step of cloud_callback in front of this filter [REF apps/prefiltering_nodelet.cpp:123-148]:
+  // setInputTransform(transform_isometry.matrix().data()) — 16 doubles, column-major, x / y translation already zeroed —
+  // replaces pcl::transformPointCloud(*src_cloud, *transformed, ...); nullptr switches it off
+  void setInputTransform(const double* matrix4x4_colmajor) { b200reg_set_input_transform(h_, matrix4x4_colmajor); }
   b200reg_handle* handle() { return h_; }
 
  protected:

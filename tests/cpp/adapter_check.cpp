@@ -30,6 +30,11 @@ int main() {
     auto vg = std::make_shared<b200reg::VoxelGrid>();
     vg->setLeafSize(0.1f, 0.1f, 0.1f);
     vg->setDistanceFilter(true, 0.1, 100.0);
+    {  // the base_link step [REF apps/prefiltering_nodelet.cpp:123-148]: set (identity here) and switched off again
+      const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      vg->setInputTransform(I);
+      vg->setInputTransform(nullptr);
+    }
     downsample_filter = vg;
     auto rad = std::make_shared<b200reg::RadiusOutlierRemoval>();
     rad->setRadiusSearch(0.5);
